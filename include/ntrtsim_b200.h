@@ -1,0 +1,243 @@
+/*
+ * ntrtsim_b200.h -- C ABI of the B200-native batched tensegrity step.
+ *
+ * One `tgb_world` holds N independent copies ("environments") of one flattened
+ * NTRTsim world: rigid bodies (rods / compounds of cylinders), two-point
+ * spring-cables with their actuators, one ground, one gravity value.  Every
+ * call below replaces a piece of the per-step path of the reference
+ * (paths relative to the NTRTsim source tree):
+ *
+ *   tgb_create / tgb_destroy     src/core/tgWorld.cpp:75-96  (tgWorld ctor/reset -> new tgWorldBulletPhysicsImpl)
+ *                                 src/core/tgWorldBulletPhysicsImpl.cpp:114-152 (gravity, ground body)
+ *   tgb_add_model_flat           src/tgcreator/tgStructureInfo.cpp:277-289 (buildInto: bodies + cables reach the world)
+ *                                 src/core/tgBulletUtil.cpp:39-77 (createRigidBody), src/core/tgSpringCable.cpp:33-60
+ *   tgb_finalize                 src/core/tgSimulation.cpp:65-82 (addModel -> setup): state becomes steppable
+ *   tgb_step                     src/core/tgSimulation.cpp:193-225 (world step, then model/actuator/cable step)
+ *                                 = tgWorldImpl::step (src/core/tgWorldImpl.h:56) + tgBasicActuator::step
+ *                                 (src/core/tgBasicActuator.cpp:96-113) for every environment, n_steps times
+ *   tgb_set_control_input        src/core/tgBasicActuator.cpp:149-168 (setControlInput(input, dt) -> moveMotors)
+ *   tgb_set_controller           device-side forms of the shipped observers:
+ *                                 src/examples/craterEscape/EscapeController.cpp:100-117,245-291 (sine)
+ *                                 src/examples/SUPERball/controllers/T6TensionController.cpp:69-83 (tension)
+ *                                 src/examples/motorModel/tsTestRig.cpp:181-188 (set-point / motor torque)
+ *   tgb_get_rod_state            src/core/tgBaseRigid.cpp:74-103 (centerOfMass / orientation)
+ *   tgb_get_cable_obs            src/core/tgBulletSpringCable.cpp:143-155 (getActualLength / getTension),
+ *                                 src/core/tgSpringCable.cpp:65-68 (getRestLength)
+ *   tgb_get_scores               src/examples/craterEscape/EscapeController.cpp:119-135 (displacement score)
+ *
+ * Plain pointers and sizes only; all host-side numbers are double (the
+ * reference is double precision throughout); the device computes in the
+ * precision chosen in tgb_world_cfg.  No call falls back to a CPU
+ * implementation: without a CUDA device tgb_create fails with TGB_ERR_CUDA.
+ *
+ * Thread-safety: like the reference (single-threaded, no re-entrancy) a
+ * tgb_world must be used from one host thread at a time.
+ */
+#ifndef NTRTSIM_B200_H
+#define NTRTSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGB_ABI_VERSION 1
+
+typedef enum {
+    TGB_OK = 0,
+    TGB_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference (dt<=0, negative input, bad config) */
+    TGB_ERR_STATE = 2,            /* call order (e.g. step before finalize) */
+    TGB_ERR_CUDA = 3,             /* no device / CUDA runtime failure */
+    TGB_ERR_UNSUPPORTED = 4,      /* model outside the compiled limits */
+    TGB_ERR_RUNTIME = 5           /* std::runtime_error in the reference (controllers) */
+} tgb_status;
+
+typedef enum { TGB_F32 = 0, TGB_F64 = 1 } tgb_precision;
+
+typedef enum {
+    TGB_GROUND_EMPTY = 0, /* tgEmptyGround: no ground body (tgWorldBulletPhysicsImpl.cpp:125-128) */
+    TGB_GROUND_BOX = 1,   /* tgBoxGround: top face of the static box, friction 0.5 / restitution 0 (Bullet defaults) */
+    TGB_GROUND_PLANE = 2  /* tgPlaneGround: btStaticPlaneShape, friction/restitution from its Config */
+} tgb_ground_kind;
+
+typedef struct {
+    double gravity;        /* tgWorld::Config::gravity; acts along -Y */
+    int32_t n_env;         /* number of independent environments held by this world */
+    int32_t precision;     /* tgb_precision: arithmetic type of the device state */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t solver_iterations; /* contact PGS iterations, 0 -> 10 (Bullet default numIterations) */
+} tgb_world_cfg;
+
+typedef struct {
+    int32_t kind;          /* tgb_ground_kind */
+    double normal[3];      /* unit normal of the contact surface (world) */
+    double offset;         /* surface is { x : normal.x = offset } */
+    double friction;
+    double rolling_friction;
+    double restitution;
+    double margin;         /* collision margin of the ground shape (0.04 for the box) */
+} tgb_ground_desc;
+
+/* One rigid body = btRigidBody of the reference (a rod, or an auto-compound of rods). */
+typedef struct {
+    double mass;           /* already squeezed through float, tgBulletUtil.cpp:39-42 ; 0 => static */
+    double inertia[3];     /* local diagonal inertia from calculateLocalInertia */
+    double pos[3];         /* initial centre-of-mass position */
+    double quat[4];        /* initial orientation, (x,y,z,w) */
+    double friction;
+    double rolling_friction;
+    double restitution;
+    int32_t shape_begin;   /* first child collision shape in the shape array */
+    int32_t shape_count;
+    int32_t gyroscopic;    /* BT_ENABLE_GYROPSCOPIC_FORCE, tgRigidInfo.cpp:118 */
+    int32_t reserved;
+} tgb_body_desc;
+
+/* One collision primitive of a body: flat-ended cylinder along its local Y (tgRodInfo.cpp:105-106). */
+typedef struct {
+    double radius;
+    double half_length;
+    double margin;         /* Bullet setSafeMargin: min(0.04, 0.1*min(radius, half_length)) */
+    double pos[3];         /* child transform in the body frame */
+    double quat[4];
+} tgb_shape_desc;
+
+typedef enum {
+    TGB_ACT_PASSIVE = 0,   /* tgBulletSpringCable with no motor */
+    TGB_ACT_BASIC = 1,     /* tgBasicActuator */
+    TGB_ACT_KINEMATIC = 2  /* tgKinematicActuator */
+} tgb_actuator_kind;
+
+/* One two-anchor spring-cable plus its actuator (tgBulletSpringCable + tgSpringCableActuator::Config). */
+typedef struct {
+    int32_t body_a, body_b;
+    double local_a[3], local_b[3]; /* anchor points in the body frames (tgBulletSpringCableAnchor.cpp:54-55) */
+    double stiffness, damping;
+    double rest_length;    /* initial: |p2-p1| - pretension/k (tgSpringCable.cpp:49-59) */
+    double prev_length;    /* initial: == rest_length (first-step damping artefact) */
+    int32_t actuator;      /* tgb_actuator_kind */
+    int32_t backdrivable;
+    double max_tension, target_velocity, min_actual_length, min_rest_length;
+    double motor_radius, motor_friction, motor_inertia; /* tgKinematicActuator::Config */
+} tgb_cable_desc;
+
+typedef enum {
+    TGB_CTRL_NONE = 0,
+    /* params per env: [C] preferred lengths; every step setControlInput(pref, dt) (tsTestRig.cpp:181-188) */
+    TGB_CTRL_SETPOINT = 1,
+    /* params per env: [1] tension set point; tgTensionController::control(dt, T) on every cable
+       (T6TensionController.cpp:69-83 -> tgTensionController.cpp:50-88) */
+    TGB_CTRL_TENSION = 2,
+    /* params per env: [8][4] = amplitude, angular frequency, phase change, dc offset per cluster, already
+       passed through transformActions; followed by [1] initial length L0.  EscapeController.cpp:100-117,245-291 */
+    TGB_CTRL_ESCAPE_SINE = 3,
+    /* params per env: [C] desired motor torque, re-applied every step (tsTestRig.cpp:181-188, kinematic) */
+    TGB_CTRL_TORQUE = 4
+} tgb_controller_kind;
+
+#define TGB_ESCAPE_PARAMS 33
+
+/* Per-rod state record exchanged with the host: pos(3) quat(4, xyzw) linvel(3) angvel(3). */
+#define TGB_ROD_STATE_DOUBLES 13
+/* Per-cable observation record: rest length, actual length, tension (no damping term), motor velocity. */
+#define TGB_CABLE_OBS_DOUBLES 4
+
+typedef struct tgb_world tgb_world;
+
+int          tgb_abi_version(void);
+const char*  tgb_last_error(void);
+int          tgb_device_count(void);
+
+tgb_status tgb_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, tgb_world** out);
+tgb_status tgb_destroy(tgb_world* w);
+
+/* Append one flattened model (indices in `cables` are relative to `bodies`). May be called several times
+   before tgb_finalize, like tgSimulation::addModel. */
+tgb_status tgb_add_model_flat(tgb_world* w,
+                              const tgb_body_desc* bodies, int32_t n_bodies,
+                              const tgb_shape_desc* shapes, int32_t n_shapes,
+                              const tgb_cable_desc* cables, int32_t n_cables);
+
+/* Allocate the device buffers and replicate the model's initial state into all n_env environments. */
+tgb_status tgb_finalize(tgb_world* w);
+
+tgb_status tgb_num_bodies(const tgb_world* w, int32_t* out);
+tgb_status tgb_num_cables(const tgb_world* w, int32_t* out);
+tgb_status tgb_num_envs(const tgb_world* w, int32_t* out);
+
+/* state: [env_count][n_bodies][13] doubles (host). */
+tgb_status tgb_set_rod_state(tgb_world* w, int32_t env_begin, int32_t env_count, const double* state);
+tgb_status tgb_get_rod_state(tgb_world* w, int32_t env_begin, int32_t env_count, double* state);
+
+/* rest_prev: [env_count][n_cables][2] doubles (rest length, previous length). */
+tgb_status tgb_set_cable_state(tgb_world* w, int32_t env_begin, int32_t env_count, const double* rest_prev);
+/* obs: [env_count][n_cables][4] doubles (rest, length, tension, motor velocity). */
+tgb_status tgb_get_cable_obs(tgb_world* w, int32_t env_begin, int32_t env_count, double* obs);
+
+/* Install a device-side controller. params: [env_count][params_per_env] doubles; if broadcast != 0 `params`
+   holds ONE row that is copied to every environment in the range. */
+tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, int32_t params_per_env,
+                              int32_t env_begin, int32_t env_count, int32_t broadcast);
+
+/* tgBasicActuator::setControlInput(input, dt) on every cable of every env in the range, once, now.
+   input: [n_cables] (broadcast != 0) or [env_count][n_cables]. Negative input -> TGB_ERR_INVALID_ARGUMENT
+   (tgBasicActuator.cpp:139-142); a NaN entry leaves that cable untouched. */
+tgb_status tgb_set_control_input(tgb_world* w, int32_t env_begin, int32_t env_count,
+                                 const double* input, int32_t broadcast, double dt);
+
+/* n_steps x tgSimulation::step(dt) for every environment. Asynchronous on the world's stream. dt<=0 ->
+   TGB_ERR_INVALID_ARGUMENT (tgSimulation.cpp:197-200). */
+tgb_status tgb_step(tgb_world* w, double dt, int32_t n_steps);
+tgb_status tgb_sync(tgb_world* w);
+
+/* Host-buffer round trip in one call: upload rod+cable state, step, download rod state + cable observations.
+   This is the reference-facing end-to-end path (bench.py "e2e"). Buffers as in the set/get calls, all envs. */
+tgb_status tgb_rollout_host(tgb_world* w, const double* rod_state_in, const double* cable_rest_prev_in,
+                            double dt, int32_t n_steps, double* rod_state_out, double* cable_obs_out);
+
+/* Simulated time of the world = sum of dt over all steps (tgSimView.cpp m_totalTime equivalent). */
+tgb_status tgb_get_time(const tgb_world* w, double* out);
+
+/* Per-env status flags: bit0 = non-finite state seen, bit1 = centre of mass left [height_lo, height_hi]. */
+tgb_status tgb_get_status(tgb_world* w, int32_t env_begin, int32_t env_count, int32_t* out);
+
+/* scores: [env_count][2]: XZ distance of the mass-weighted COM from its position at tgb_finalize /
+   tgb_mark_episode_start, and 0 (energy: history logging is off in every shipped config). */
+tgb_status tgb_mark_episode_start(tgb_world* w);
+tgb_status tgb_get_scores(tgb_world* w, int32_t env_begin, int32_t env_count, double* scores);
+
+/* Device-resident score buffer (float[n_env][2]) for NCCL allgather without a host hop. */
+tgb_status tgb_scores_device_ptr(tgb_world* w, void** ptr, size_t* bytes);
+
+/* Timing helper: run `reps` launches of n_steps each, bracketed by CUDA events on the world's stream;
+   ms_out[reps]. Used by bench.py because torch.cuda.Event only sees torch's current stream. */
+tgb_status tgb_step_timed(tgb_world* w, double dt, int32_t n_steps, int32_t reps, float* ms_out);
+
+/* Kernel launches issued by this world since creation (bench.py "gpu_launches"). */
+tgb_status tgb_launch_count(const tgb_world* w, int64_t* out);
+
+/* Launch geometry chosen for this world: lanes per environment, threads per block, blocks. */
+tgb_status tgb_launch_geometry(const tgb_world* w, int32_t* lanes_per_env, int32_t* block, int32_t* grid);
+/* Override lanes per env (1,2,4,8,16,32) before tgb_finalize; 0 = automatic. */
+tgb_status tgb_set_lanes_per_env(tgb_world* w, int32_t lanes);
+
+/* Threads per CTA of the step kernel (32, 64, 96, 128; a multiple of lanes per env); 0 = automatic
+   (also settable through the environment variable TGB_BLOCK_THREADS). */
+tgb_status tgb_set_block_threads(tgb_world* w, int32_t threads);
+
+/* Bytes of device state per environment (the HBM traffic of one launch is 2x this per env). */
+tgb_status tgb_state_bytes_per_env(const tgb_world* w, size_t* out);
+
+/* Height window of the status flag bit1: the check of BaseSpineCPGControl::onStep
+   (src/examples/learningSpines/BaseSpineCPGControl.cpp:271-278: 1.0 < y_COM < 25). lo > hi disables it (default). */
+tgb_status tgb_set_height_window(tgb_world* w, double lo, double hi);
+
+/* The CUDA stream (cudaStream_t) all work of this world is issued on. */
+tgb_status tgb_stream_handle(tgb_world* w, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTRTSIM_B200_H */

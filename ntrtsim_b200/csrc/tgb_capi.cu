@@ -1,0 +1,706 @@
+/*
+ * tgb_capi.cu -- the C ABI of include/ntrtsim_b200.h over the CUDA kernels.  Each entry point cites the reference
+ * interface it replaces in the header; this file owns the device buffers, the packing of the flattened model and the
+ * launch geometry.  There is no CPU implementation behind any call: without a usable CUDA device tgb_create fails.
+ */
+#include "../../include/ntrtsim_b200.h"
+#include "tgb_ops.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+
+tgb_status fail(tgb_status st, const std::string& msg) {
+    g_error = msg;
+    return st;
+}
+tgb_status cudaFail(cudaError_t e, const char* what) {
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return TGB_ERR_CUDA;
+}
+#define TGB_CUDA(call)                                       \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cudaFail(e__, #call); \
+    } while (0)
+
+int nextPow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+} // namespace
+
+struct tgb_world {
+    tgb_world_cfg cfg;
+    tgb_ground_desc ground;
+    std::vector<tgb_body_desc> bodies;
+    std::vector<tgb_shape_desc> shapes;
+    std::vector<tgb_cable_desc> cables;
+    bool finalized = false;
+    const tgb_ops* ops = nullptr;
+    size_t scalarBytes = 4;
+    int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0;
+    int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0;
+    cudaStream_t stream = nullptr;
+    void* d_state = nullptr;
+    double* d_frame = nullptr;
+    double* d_ctrl = nullptr;
+    double* d_com0 = nullptr;
+    int* d_status = nullptr;
+    void* d_model_t = nullptr;
+    int* d_model_i = nullptr;
+    int modelTWords = 0, modelIWords = 0;
+    double* d_stage = nullptr;  /* staging for double records exchanged with the host */
+    size_t stageDoubles = 0;
+    double* h_stage = nullptr;  /* pinned */
+    size_t hStageDoubles = 0;
+    float* d_scores = nullptr;
+    int ctrlKind = TGB_CTRL_NONE, ctrlStride = 0;
+    double time = 0.0;
+    int64_t launches = 0;
+    double heightLo = 1.0, heightHi = 0.0; /* disabled */
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    tgb::tgb_io_args ioArgs(int envBegin, int envCount) const {
+        tgb::tgb_io_args a;
+        a.state = d_state; a.frame = d_frame; a.com0 = d_com0; a.model_t = d_model_t; a.model_i = d_model_i;
+        a.n_env = cfg.n_env; a.R = R; a.C = C; a.S = S; a.stride = stride; a.frame_body = frameBody;
+        a.env_begin = envBegin; a.env_count = envCount;
+        return a;
+    }
+    tgb_status ensureStage(size_t doubles) {
+        if (doubles > stageDoubles) {
+            if (d_stage) cudaFree(d_stage);
+            d_stage = nullptr; stageDoubles = 0;
+            TGB_CUDA(cudaMalloc(&d_stage, doubles * sizeof(double)));
+            stageDoubles = doubles;
+        }
+        return TGB_OK;
+    }
+    tgb_status ensureHostStage(size_t doubles) {
+        if (doubles > hStageDoubles) {
+            if (h_stage) cudaFreeHost(h_stage);
+            h_stage = nullptr; hStageDoubles = 0;
+            TGB_CUDA(cudaMallocHost(&h_stage, doubles * sizeof(double)));
+            hStageDoubles = doubles;
+        }
+        return TGB_OK;
+    }
+    void release() {
+        if (d_state) cudaFree(d_state);
+        if (d_frame) cudaFree(d_frame);
+        if (d_ctrl) cudaFree(d_ctrl);
+        if (d_com0) cudaFree(d_com0);
+        if (d_status) cudaFree(d_status);
+        if (d_model_t) cudaFree(d_model_t);
+        if (d_model_i) cudaFree(d_model_i);
+        if (d_stage) cudaFree(d_stage);
+        if (h_stage) cudaFreeHost(h_stage);
+        if (d_scores) cudaFree(d_scores);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+bool rangeOk(const tgb_world* w, int envBegin, int envCount) {
+    return envBegin >= 0 && envCount >= 0 && (int64_t)envBegin + envCount <= w->cfg.n_env;
+}
+
+template <typename T>
+void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vector<int>& ints, int& nInc) {
+    const int R = w->R, C = w->C, S = w->S;
+    std::vector<T> t((size_t)TGB_NBF * R + (size_t)TGB_NSF * S + (size_t)TGB_NCF * C, T(0));
+    T* bt = t.data();
+    T* st = bt + (size_t)TGB_NBF * R;
+    T* ct = st + (size_t)TGB_NSF * S;
+    std::vector<std::vector<int> > incidence(R);
+    for (int c = 0; c < C; ++c) {
+        incidence[w->cables[c].body_a].push_back(c);
+        incidence[w->cables[c].body_b].push_back(c | (1 << 24));
+    }
+    nInc = 2 * C;
+    ints.assign((size_t)TGB_NBI * R + (size_t)TGB_NCI * C + nInc, 0);
+    int* bi = ints.data();
+    int* ci = bi + (size_t)TGB_NBI * R;
+    int* inc = ci + (size_t)TGB_NCI * C;
+    int incPos = 0;
+    for (int b = 0; b < R; ++b) {
+        const tgb_body_desc& d = w->bodies[b];
+        /* btRigidBody::setMassProps: inverse mass and inverse local inertia; static when mass == 0 */
+        const double invMass = d.mass != 0.0 ? 1.0 / d.mass : 0.0;
+        double invI[3];
+        for (int k = 0; k < 3; ++k) invI[k] = (d.mass != 0.0 && d.inertia[k] != 0.0) ? 1.0 / d.inertia[k] : 0.0;
+        bt[BF_INVMASS * R + b] = (T)invMass;
+        /* btRigidBody::setGravity: m_gravity = acceleration * (1 / inverseMass) */
+        bt[BF_GFY * R + b] = invMass != 0.0 ? (T)(-w->cfg.gravity * (1.0 / invMass)) : T(0);
+        for (int k = 0; k < 3; ++k) {
+            bt[(BF_INVIX + k) * R + b] = (T)invI[k];
+            bt[(BF_IX + k) * R + b] = invI[k] != 0.0 ? (T)(1.0 / invI[k]) : T(0);
+        }
+        double mu = d.friction * w->ground.friction;
+        mu = std::max(-10.0, std::min(10.0, mu));
+        bt[BF_MU * R + b] = (T)mu;
+        bt[BF_RESTITUTION * R + b] = (T)d.restitution;
+        bt[BF_MASS * R + b] = (T)d.mass;
+        bi[BI_SHAPE_BEGIN * R + b] = d.shape_begin;
+        bi[BI_SHAPE_COUNT * R + b] = d.shape_count;
+        bi[BI_INC_BEGIN * R + b] = incPos;
+        bi[BI_INC_COUNT * R + b] = (int)incidence[b].size();
+        bi[BI_GYRO * R + b] = d.gyroscopic;
+        /* applyImpulse order inside one tgSimulation::step is cable order, end A before end B */
+        std::vector<int> sorted = incidence[b];
+        std::sort(sorted.begin(), sorted.end(), [](int x, int y) {
+            const int cx = x & 0xffffff, cy = y & 0xffffff;
+            return cx != cy ? cx < cy : x < y;
+        });
+        for (size_t k = 0; k < sorted.size(); ++k) inc[incPos++] = sorted[k];
+    }
+    for (int s = 0; s < S; ++s) {
+        const tgb_shape_desc& d = w->shapes[s];
+        st[SF_RADIUS * S + s] = (T)d.radius;
+        st[SF_HALFLEN * S + s] = (T)d.half_length;
+        st[SF_MARGIN * S + s] = (T)d.margin;
+        st[SF_POSX * S + s] = (T)d.pos[0]; st[SF_POSY * S + s] = (T)d.pos[1]; st[SF_POSZ * S + s] = (T)d.pos[2];
+        /* btMatrix3x3::setRotation in double, then narrowed */
+        const double x = d.quat[0], y = d.quat[1], z = d.quat[2], q = d.quat[3];
+        const double dd = x * x + y * y + z * z + q * q;
+        const double sc = 2.0 / dd;
+        const double xs = x * sc, ys = y * sc, zs = z * sc;
+        const double wx = q * xs, wy = q * ys, wz = q * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+        const double m[9] = {1.0 - (yy + zz), xy - wz, xz + wy, xy + wz, 1.0 - (xx + zz), yz - wx, xz - wy, yz + wx, 1.0 - (xx + yy)};
+        for (int k = 0; k < 9; ++k) st[(SF_ROT0 + k) * S + s] = (T)m[k];
+    }
+    for (int c = 0; c < C; ++c) {
+        const tgb_cable_desc& d = w->cables[c];
+        for (int k = 0; k < 3; ++k) { ct[(CF_LAX + k) * C + c] = (T)d.local_a[k]; ct[(CF_LBX + k) * C + c] = (T)d.local_b[k]; }
+        ct[CF_K * C + c] = (T)d.stiffness; ct[CF_C * C + c] = (T)d.damping;
+        ct[CF_MAXTENS * C + c] = (T)d.max_tension; ct[CF_TVEL * C + c] = (T)d.target_velocity;
+        ct[CF_MINAL * C + c] = (T)d.min_actual_length; ct[CF_MINRL * C + c] = (T)d.min_rest_length;
+        ct[CF_MRADIUS * C + c] = (T)d.motor_radius; ct[CF_MFRICTION * C + c] = (T)d.motor_friction; ct[CF_MINERTIA * C + c] = (T)d.motor_inertia;
+        ci[CI_A * C + c] = d.body_a; ci[CI_B * C + c] = d.body_b;
+        ci[CI_ACTUATOR * C + c] = d.actuator; ci[CI_BACKDRIVABLE * C + c] = d.backdrivable;
+    }
+    tbytes.resize(t.size() * sizeof(T));
+    std::memcpy(tbytes.data(), t.data(), tbytes.size());
+}
+
+tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
+    tgb_step_args a;
+    std::memset(&a, 0, sizeof(a));
+    a.state = w->d_state; a.frame = w->d_frame; a.ctrl = w->ctrlKind != TGB_CTRL_NONE ? w->d_ctrl : nullptr; a.status = w->d_status;
+    a.model_t = w->d_model_t; a.model_i = w->d_model_i;
+    a.n_env = w->cfg.n_env; a.n_steps = nSteps;
+    a.R = w->R; a.C = w->C; a.S = w->S; a.n_inc = w->nInc;
+    a.stride = w->stride; a.cap_contacts = w->capContacts; a.frame_body = w->frameBody;
+    a.ctrl_kind = w->ctrlKind; a.ctrl_stride = w->ctrlKind != TGB_CTRL_NONE ? w->ctrlStride : 0;
+    a.iterations = w->cfg.solver_iterations > 0 ? w->cfg.solver_iterations : 10;
+    a.ground_kind = w->ground.kind;
+    a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
+    a.dt = dt;
+    a.gn[0] = w->ground.normal[0]; a.gn[1] = w->ground.normal[1]; a.gn[2] = w->ground.normal[2];
+    a.goff = w->ground.offset;
+    a.ground_restitution = w->ground.restitution;
+    a.height_lo = w->heightLo; a.height_hi = w->heightHi;
+    return a;
+}
+
+tgb_status launchStep(tgb_world* w, double dt, int nSteps) {
+    const tgb_step_args a = stepArgs(w, dt, nSteps);
+    cudaError_t e = w->ops->step(a, w->lanes, w->threads, w->stream);
+    if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
+    w->launches += 1;
+    w->time += dt * nSteps;
+    return TGB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int tgb_abi_version(void) { return TGB_ABI_VERSION; }
+const char* tgb_last_error(void) { return g_error.c_str(); }
+int tgb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+tgb_status tgb_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, tgb_world** out) {
+    if (!cfg || !ground || !out) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_create: NULL argument");
+    *out = nullptr;
+    if (cfg->n_env < 1) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_create: n_env must be positive");
+    if (cfg->precision != TGB_F32 && cfg->precision != TGB_F64) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_create: unknown precision");
+    if (ground->kind < TGB_GROUND_EMPTY || ground->kind > TGB_GROUND_PLANE) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_create: unknown ground kind");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(TGB_ERR_CUDA, "tgb_create: no CUDA device is available (this library has no CPU path)");
+    }
+    if (cfg->device < 0 || cfg->device >= n) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_create: device ordinal out of range");
+    TGB_CUDA(cudaSetDevice(cfg->device));
+    tgb_world* w = new tgb_world();
+    w->cfg = *cfg;
+    w->ground = *ground;
+    w->ops = cfg->precision == TGB_F64 ? tgb_ops_f64() : tgb_ops_f32();
+    w->scalarBytes = w->ops->scalar_bytes;
+    e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
+    if (e != cudaSuccess) { w->release(); delete w; return cudaFail(e, "tgb_create: stream/event creation"); }
+    *out = w;
+    return TGB_OK;
+}
+
+tgb_status tgb_destroy(tgb_world* w) {
+    if (!w) return TGB_OK;
+    cudaSetDevice(w->cfg.device);
+    if (w->stream) cudaStreamSynchronize(w->stream);
+    w->release();
+    delete w;
+    return TGB_OK;
+}
+
+tgb_status tgb_add_model_flat(tgb_world* w, const tgb_body_desc* bodies, int32_t n_bodies, const tgb_shape_desc* shapes, int32_t n_shapes,
+                              const tgb_cable_desc* cables, int32_t n_cables) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_model_flat: NULL world");
+    if (w->finalized) return fail(TGB_ERR_STATE, "tgb_add_model_flat: world already finalized");
+    if (n_bodies < 0 || n_shapes < 0 || n_cables < 0 || (n_bodies && !bodies) || (n_shapes && !shapes) || (n_cables && !cables))
+        return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_model_flat: bad array arguments");
+    const int body0 = (int)w->bodies.size(), shape0 = (int)w->shapes.size();
+    for (int i = 0; i < n_bodies; ++i) {
+        const tgb_body_desc& b = bodies[i];
+        if (b.mass < 0.0 || b.shape_begin < 0 || b.shape_count < 0 || b.shape_begin + b.shape_count > n_shapes)
+            return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_model_flat: bad body descriptor");
+    }
+    for (int i = 0; i < n_cables; ++i) {
+        const tgb_cable_desc& c = cables[i];
+        if (c.body_a < 0 || c.body_a >= n_bodies || c.body_b < 0 || c.body_b >= n_bodies)
+            return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_model_flat: cable body index out of range");
+        /* same checks as tgSpringCableActuator::Config (tgSpringCableActuator.cpp:61-87) */
+        if (c.stiffness < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "stiffness is negative.");
+        if (c.damping < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "damping is negative.");
+        if (c.max_tension < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "max tension is negative.");
+        if (c.min_actual_length < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "min Actual Length is negative.");
+        if (c.min_rest_length < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "min Rest Length is negative.");
+        if (c.actuator < TGB_ACT_PASSIVE || c.actuator > TGB_ACT_KINEMATIC) return fail(TGB_ERR_INVALID_ARGUMENT, "unknown actuator kind");
+        if (!(c.rest_length > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "Pretension causes string to shorten past rest length!");
+    }
+    for (int i = 0; i < n_shapes; ++i) w->shapes.push_back(shapes[i]);
+    for (int i = 0; i < n_bodies; ++i) {
+        tgb_body_desc b = bodies[i];
+        b.shape_begin += shape0;
+        w->bodies.push_back(b);
+    }
+    for (int i = 0; i < n_cables; ++i) {
+        tgb_cable_desc c = cables[i];
+        c.body_a += body0; c.body_b += body0;
+        w->cables.push_back(c);
+    }
+    return TGB_OK;
+}
+
+tgb_status tgb_set_lanes_per_env(tgb_world* w, int32_t lanes) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (w->finalized) return fail(TGB_ERR_STATE, "tgb_set_lanes_per_env: world already finalized");
+    if (lanes != 0 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return fail(TGB_ERR_INVALID_ARGUMENT, "lanes per env must be 0 (automatic), 2, 4, 8, 16 or 32");
+    w->lanesOverride = lanes;
+    return TGB_OK;
+}
+
+tgb_status tgb_set_block_threads(tgb_world* w, int32_t threads) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (threads != 0 && threads != 32 && threads != 64 && threads != 96 && threads != 128)
+        return fail(TGB_ERR_INVALID_ARGUMENT, "block threads must be 0 (automatic), 32, 64, 96 or 128");
+    w->threadsOverride = threads;
+    if (w->finalized && threads) {
+        if (threads % w->lanes) return fail(TGB_ERR_INVALID_ARGUMENT, "block threads must be a multiple of lanes per env");
+        w->threads = threads;
+    }
+    return TGB_OK;
+}
+
+tgb_status tgb_finalize(tgb_world* w) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (w->finalized) return TGB_OK;
+    w->R = (int)w->bodies.size(); w->C = (int)w->cables.size(); w->S = (int)w->shapes.size();
+    if (w->R < 1) return fail(TGB_ERR_STATE, "tgb_finalize: the world has no bodies");
+    if (w->R > 32) return fail(TGB_ERR_UNSUPPORTED, "tgb_finalize: more than 32 rigid bodies per environment");
+    if (w->C >= (1 << 24)) return fail(TGB_ERR_UNSUPPORTED, "tgb_finalize: too many cables");
+    TGB_CUDA(cudaSetDevice(w->cfg.device));
+    const int n = w->cfg.n_env;
+    const int vecWords = (int)(16 / w->scalarBytes);
+    w->stride = w->R * TGB_NBS + w->C * TGB_NCS;
+    w->stride = (w->stride + vecWords - 1) / vecWords * vecWords;
+    int maxShapes = 1;
+    w->frameBody = 0;
+    bool haveDynamic = false;
+    for (int b = 0; b < w->R; ++b) {
+        maxShapes = std::max(maxShapes, (int)w->bodies[b].shape_count);
+        if (!haveDynamic && w->bodies[b].mass != 0.0) { w->frameBody = b; haveDynamic = true; }
+    }
+    w->capContacts = 4 * maxShapes; /* at most 4 manifold points per collision shape */
+    w->lanes = w->lanesOverride ? w->lanesOverride : std::max(2, nextPow2(w->R));
+    if (w->lanes < w->R) return fail(TGB_ERR_INVALID_ARGUMENT, "lanes per env is smaller than the number of bodies");
+    /* block size: enough CTAs to spread over all SMs; a group never spans warps */
+    int threads = w->threadsOverride;
+    if (!threads) {
+        const char* envThreads = std::getenv("TGB_BLOCK_THREADS");
+        if (envThreads) threads = std::atoi(envThreads);
+    }
+    if (!threads) {
+        const long long totalThreads = (long long)n * w->lanes;
+        threads = totalThreads >= 148LL * 16 * 128 ? 128 : totalThreads >= 148LL * 16 * 64 ? 64 : 32;
+    }
+    if (threads % 32 || threads < 32 || threads > 128) return fail(TGB_ERR_INVALID_ARGUMENT, "bad block size");
+    w->threads = threads;
+
+    std::vector<unsigned char> tbytes;
+    std::vector<int> ints;
+    if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc);
+    else packModel<float>(w, tbytes, ints, w->nInc);
+    w->modelTWords = (int)(tbytes.size() / w->scalarBytes);
+    w->modelIWords = (int)ints.size();
+    TGB_CUDA(cudaMalloc(&w->d_model_t, std::max<size_t>(tbytes.size(), 16)));
+    TGB_CUDA(cudaMalloc(&w->d_model_i, std::max<size_t>(ints.size() * sizeof(int), 16)));
+    TGB_CUDA(cudaMemcpy(w->d_model_t, tbytes.data(), tbytes.size(), cudaMemcpyHostToDevice));
+    TGB_CUDA(cudaMemcpy(w->d_model_i, ints.data(), ints.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TGB_CUDA(cudaMalloc(&w->d_state, (size_t)n * w->stride * w->scalarBytes));
+    TGB_CUDA(cudaMemset(w->d_state, 0, (size_t)n * w->stride * w->scalarBytes));
+    TGB_CUDA(cudaMalloc(&w->d_frame, (size_t)n * TGB_NFR * sizeof(double)));
+    TGB_CUDA(cudaMemset(w->d_frame, 0, (size_t)n * TGB_NFR * sizeof(double)));
+    TGB_CUDA(cudaMalloc(&w->d_com0, (size_t)n * 3 * sizeof(double)));
+    TGB_CUDA(cudaMalloc(&w->d_status, (size_t)n * sizeof(int)));
+    TGB_CUDA(cudaMemset(w->d_status, 0, (size_t)n * sizeof(int)));
+    TGB_CUDA(cudaMalloc(&w->d_scores, (size_t)n * 2 * sizeof(float)));
+    TGB_CUDA(cudaMemset(w->d_scores, 0, (size_t)n * 2 * sizeof(float)));
+
+    /* the step kernel must fit its shared memory */
+    {
+        tgb_step_args a = stepArgs(w, 1e-3, 1);
+        a.ctrl_stride = std::max(w->C, TGB_ESCAPE_PARAMS);
+        const size_t smem = w->ops->step_smem(a, w->lanes, w->threads);
+        if (smem > 227 * 1024) return fail(TGB_ERR_UNSUPPORTED, "tgb_finalize: model too large for one CTA's shared memory");
+    }
+
+    /* replicate the model's initial state into every environment */
+    std::vector<double> rods((size_t)w->R * TGB_NBS, 0.0), cab((size_t)std::max(1, w->C) * 2, 0.0);
+    for (int b = 0; b < w->R; ++b) {
+        double* s = &rods[(size_t)b * TGB_NBS];
+        for (int k = 0; k < 3; ++k) s[k] = w->bodies[b].pos[k];
+        for (int k = 0; k < 4; ++k) s[3 + k] = w->bodies[b].quat[k];
+    }
+    for (int c = 0; c < w->C; ++c) { cab[2 * c] = w->cables[c].rest_length; cab[2 * c + 1] = w->cables[c].prev_length; }
+    tgb_status st = w->ensureStage(rods.size() + cab.size());
+    if (st != TGB_OK) return st;
+    TGB_CUDA(cudaMemcpyAsync(w->d_stage, rods.data(), rods.size() * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    TGB_CUDA(cudaMemcpyAsync(w->d_stage + rods.size(), cab.data(), cab.size() * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    const tgb::tgb_io_args io = w->ioArgs(0, n);
+    TGB_CUDA(w->ops->pack_rods(io, w->d_stage, 1, w->stream));
+    TGB_CUDA(w->ops->pack_cables(io, w->d_stage + rods.size(), 1, 1, w->stream));
+    TGB_CUDA(w->ops->com(io, 0, nullptr, nullptr, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    w->finalized = true;
+    return TGB_OK;
+}
+
+#define TGB_NEED_FINAL(w)                                                          \
+    do {                                                                           \
+        if (!(w)) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");             \
+        if (!(w)->finalized) return fail(TGB_ERR_STATE, "world is not finalized"); \
+        TGB_CUDA(cudaSetDevice((w)->cfg.device));                                  \
+    } while (0)
+
+tgb_status tgb_num_bodies(const tgb_world* w, int32_t* out) {
+    if (!w || !out) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = (int32_t)w->bodies.size();
+    return TGB_OK;
+}
+tgb_status tgb_num_cables(const tgb_world* w, int32_t* out) {
+    if (!w || !out) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = (int32_t)w->cables.size();
+    return TGB_OK;
+}
+tgb_status tgb_num_envs(const tgb_world* w, int32_t* out) {
+    if (!w || !out) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = w->cfg.n_env;
+    return TGB_OK;
+}
+
+tgb_status tgb_set_rod_state(tgb_world* w, int32_t env_begin, int32_t env_count, const double* state) {
+    TGB_NEED_FINAL(w);
+    if (!state || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_rod_state: bad range or NULL buffer");
+    if (env_count == 0) return TGB_OK;
+    const size_t n = (size_t)env_count * w->R * TGB_NBS;
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(cudaMemcpyAsync(w->d_stage, state, n * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    const tgb::tgb_io_args io = w->ioArgs(env_begin, env_count);
+    TGB_CUDA(w->ops->pack_rods(io, w->d_stage, 0, w->stream));
+    TGB_CUDA(w->ops->com(io, 0, nullptr, nullptr, w->stream)); /* a new state starts a new episode for the scores */
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_get_rod_state(tgb_world* w, int32_t env_begin, int32_t env_count, double* state) {
+    TGB_NEED_FINAL(w);
+    if (!state || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_rod_state: bad range or NULL buffer");
+    if (env_count == 0) return TGB_OK;
+    const size_t n = (size_t)env_count * w->R * TGB_NBS;
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(w->ops->unpack_rods(w->ioArgs(env_begin, env_count), w->d_stage, w->stream));
+    TGB_CUDA(cudaMemcpyAsync(state, w->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_set_cable_state(tgb_world* w, int32_t env_begin, int32_t env_count, const double* rest_prev) {
+    TGB_NEED_FINAL(w);
+    if (!rest_prev || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cable_state: bad range or NULL buffer");
+    if (env_count == 0 || w->C == 0) return TGB_OK;
+    const size_t n = (size_t)env_count * w->C * 2;
+    for (size_t i = 0; i < n; i += 2)
+        if (!(rest_prev[i] > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cable_state: rest length must be positive");
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(cudaMemcpyAsync(w->d_stage, rest_prev, n * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    TGB_CUDA(w->ops->pack_cables(w->ioArgs(env_begin, env_count), w->d_stage, 0, 0, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_get_cable_obs(tgb_world* w, int32_t env_begin, int32_t env_count, double* obs) {
+    TGB_NEED_FINAL(w);
+    if (!obs || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_cable_obs: bad range or NULL buffer");
+    if (env_count == 0 || w->C == 0) return TGB_OK;
+    const size_t n = (size_t)env_count * w->C * TGB_CABLE_OBS_DOUBLES;
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(w->ops->cable_obs(w->ioArgs(env_begin, env_count), w->d_stage, w->stream));
+    TGB_CUDA(cudaMemcpyAsync(obs, w->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, int32_t params_per_env, int32_t env_begin, int32_t env_count,
+                              int32_t broadcast) {
+    TGB_NEED_FINAL(w);
+    if (!rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: bad env range");
+    int need = 0;
+    switch (kind) {
+    case TGB_CTRL_NONE: need = 0; break;
+    case TGB_CTRL_SETPOINT: case TGB_CTRL_TORQUE: need = w->C; break;
+    case TGB_CTRL_TENSION: need = 1; break;
+    case TGB_CTRL_ESCAPE_SINE: need = TGB_ESCAPE_PARAMS; break;
+    default: return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: unknown controller kind");
+    }
+    if (kind == TGB_CTRL_NONE) { w->ctrlKind = TGB_CTRL_NONE; return TGB_OK; }
+    if (!params || params_per_env != need) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: wrong parameter count for this controller");
+    const int n = w->cfg.n_env;
+    if (w->ctrlKind != kind) {
+        /* one controller kind per world: switching kinds needs parameters for every environment */
+        if (!(env_begin == 0 && env_count == n)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: a new controller kind must cover all environments");
+        if (w->d_ctrl) { cudaFree(w->d_ctrl); w->d_ctrl = nullptr; }
+        TGB_CUDA(cudaMalloc(&w->d_ctrl, (size_t)n * need * sizeof(double)));
+        w->ctrlStride = need;
+        {
+            tgb_step_args a = stepArgs(w, 1e-3, 1);
+            a.ctrl_stride = need;
+            if (w->ops->step_smem(a, w->lanes, w->threads) > 227 * 1024) return fail(TGB_ERR_UNSUPPORTED, "controller parameters do not fit in shared memory");
+        }
+    }
+    if (env_count > 0) {
+        if (broadcast) {
+            std::vector<double> rows((size_t)env_count * need);
+            for (int e = 0; e < env_count; ++e) std::memcpy(&rows[(size_t)e * need], params, need * sizeof(double));
+            TGB_CUDA(cudaMemcpy(w->d_ctrl + (size_t)env_begin * need, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+        } else {
+            TGB_CUDA(cudaMemcpy(w->d_ctrl + (size_t)env_begin * need, params, (size_t)env_count * need * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        /* controller time restarts (EscapeController::onSetup: m_totalTime = 0) */
+        TGB_CUDA(cudaStreamSynchronize(w->stream));
+        TGB_CUDA(cudaMemset2D(w->d_frame + (size_t)env_begin * TGB_NFR + FR_CTRLTIME, TGB_NFR * sizeof(double), 0, sizeof(double), env_count));
+    }
+    w->ctrlKind = kind;
+    return TGB_OK;
+}
+
+tgb_status tgb_set_control_input(tgb_world* w, int32_t env_begin, int32_t env_count, const double* input, int32_t broadcast, double dt) {
+    TGB_NEED_FINAL(w);
+    if (!input || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_control_input: bad range or NULL buffer");
+    if (!(dt > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "dt is not positive.");
+    if (env_count == 0 || w->C == 0) return TGB_OK;
+    const size_t n = (size_t)(broadcast ? 1 : env_count) * w->C;
+    for (size_t i = 0; i < n; ++i)
+        if (input[i] < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "Rest length is negative."); /* tgBasicActuator.cpp:139-142 */
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(cudaMemcpyAsync(w->d_stage, input, n * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    TGB_CUDA(w->ops->control_input(w->ioArgs(env_begin, env_count), w->d_stage, broadcast, dt, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_step(tgb_world* w, double dt, int32_t n_steps) {
+    TGB_NEED_FINAL(w);
+    if (!(dt > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "dt is not positive"); /* tgSimulation.cpp:197-200 */
+    if (n_steps < 0) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_step: negative step count");
+    if (n_steps == 0) return TGB_OK;
+    return launchStep(w, dt, n_steps);
+}
+
+tgb_status tgb_sync(tgb_world* w) {
+    TGB_NEED_FINAL(w);
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_rollout_host(tgb_world* w, const double* rod_state_in, const double* cable_rest_prev_in, double dt, int32_t n_steps,
+                            double* rod_state_out, double* cable_obs_out) {
+    TGB_NEED_FINAL(w);
+    if (!(dt > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "dt is not positive");
+    if (n_steps < 0) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_rollout_host: negative step count");
+    const int n = w->cfg.n_env;
+    const size_t rodN = (size_t)n * w->R * TGB_NBS, cabInN = (size_t)n * w->C * 2, cabOutN = (size_t)n * w->C * TGB_CABLE_OBS_DOUBLES;
+    const size_t stageN = std::max(rodN + cabInN, rodN + cabOutN);
+    tgb_status st = w->ensureStage(stageN);
+    if (st != TGB_OK) return st;
+    const tgb::tgb_io_args io = w->ioArgs(0, n);
+    if (rod_state_in) {
+        TGB_CUDA(cudaMemcpyAsync(w->d_stage, rod_state_in, rodN * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+        TGB_CUDA(w->ops->pack_rods(io, w->d_stage, 0, w->stream));
+        TGB_CUDA(w->ops->com(io, 0, nullptr, nullptr, w->stream));
+    }
+    if (cable_rest_prev_in && w->C) {
+        TGB_CUDA(cudaMemcpyAsync(w->d_stage + rodN, cable_rest_prev_in, cabInN * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+        TGB_CUDA(w->ops->pack_cables(io, w->d_stage + rodN, 0, 0, w->stream));
+    }
+    if (n_steps > 0) {
+        st = launchStep(w, dt, n_steps);
+        if (st != TGB_OK) return st;
+    }
+    if (rod_state_out) {
+        TGB_CUDA(w->ops->unpack_rods(io, w->d_stage, w->stream));
+        TGB_CUDA(cudaMemcpyAsync(rod_state_out, w->d_stage, rodN * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    }
+    if (cable_obs_out && w->C) {
+        TGB_CUDA(w->ops->cable_obs(io, w->d_stage + rodN, w->stream));
+        TGB_CUDA(cudaMemcpyAsync(cable_obs_out, w->d_stage + rodN, cabOutN * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    }
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_get_time(const tgb_world* w, double* out) {
+    if (!w || !out) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = w->time;
+    return TGB_OK;
+}
+
+tgb_status tgb_set_height_window(tgb_world* w, double lo, double hi) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    w->heightLo = lo; w->heightHi = hi;
+    return TGB_OK;
+}
+
+tgb_status tgb_get_status(tgb_world* w, int32_t env_begin, int32_t env_count, int32_t* out) {
+    TGB_NEED_FINAL(w);
+    if (!out || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_status: bad range or NULL buffer");
+    if (env_count == 0) return TGB_OK;
+    TGB_CUDA(cudaMemcpyAsync(out, w->d_status + env_begin, (size_t)env_count * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_mark_episode_start(tgb_world* w) {
+    TGB_NEED_FINAL(w);
+    TGB_CUDA(w->ops->com(w->ioArgs(0, w->cfg.n_env), 0, nullptr, nullptr, w->stream));
+    TGB_CUDA(cudaMemsetAsync(w->d_status, 0, (size_t)w->cfg.n_env * sizeof(int), w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_get_scores(tgb_world* w, int32_t env_begin, int32_t env_count, double* scores) {
+    TGB_NEED_FINAL(w);
+    if (!scores || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_scores: bad range or NULL buffer");
+    if (env_count == 0) return TGB_OK;
+    const size_t n = (size_t)env_count * 2;
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(w->ops->com(w->ioArgs(env_begin, env_count), 1, w->d_stage, w->d_scores, w->stream));
+    TGB_CUDA(cudaMemcpyAsync(scores, w->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_scores_device_ptr(tgb_world* w, void** ptr, size_t* bytes) {
+    TGB_NEED_FINAL(w);
+    if (!ptr || !bytes) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    /* refresh the float score buffer for all environments */
+    TGB_CUDA(w->ops->com(w->ioArgs(0, w->cfg.n_env), 1, nullptr, w->d_scores, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    *ptr = w->d_scores;
+    *bytes = (size_t)w->cfg.n_env * 2 * sizeof(float);
+    return TGB_OK;
+}
+
+tgb_status tgb_step_timed(tgb_world* w, double dt, int32_t n_steps, int32_t reps, float* ms_out) {
+    TGB_NEED_FINAL(w);
+    if (!(dt > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "dt is not positive");
+    if (n_steps < 1 || reps < 1 || !ms_out) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_step_timed: bad arguments");
+    for (int r = 0; r < reps; ++r) {
+        TGB_CUDA(cudaEventRecord(w->ev0, w->stream));
+        tgb_status st = launchStep(w, dt, n_steps);
+        if (st != TGB_OK) return st;
+        TGB_CUDA(cudaEventRecord(w->ev1, w->stream));
+        TGB_CUDA(cudaEventSynchronize(w->ev1));
+        TGB_CUDA(cudaEventElapsedTime(&ms_out[r], w->ev0, w->ev1));
+    }
+    return TGB_OK;
+}
+
+tgb_status tgb_launch_count(const tgb_world* w, int64_t* out) {
+    if (!w || !out) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = w->launches;
+    return TGB_OK;
+}
+
+tgb_status tgb_launch_geometry(const tgb_world* w, int32_t* lanes_per_env, int32_t* block, int32_t* grid) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (!w->finalized) return fail(TGB_ERR_STATE, "world is not finalized");
+    const int groups = w->threads / w->lanes;
+    if (lanes_per_env) *lanes_per_env = w->lanes;
+    if (block) *block = w->threads;
+    if (grid) *grid = (w->cfg.n_env + groups - 1) / groups;
+    return TGB_OK;
+}
+
+tgb_status tgb_state_bytes_per_env(const tgb_world* w, size_t* out) {
+    if (!w || !out) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!w->finalized) return fail(TGB_ERR_STATE, "world is not finalized");
+    *out = (size_t)w->stride * w->scalarBytes + TGB_NFR * sizeof(double);
+    return TGB_OK;
+}
+
+tgb_status tgb_stream_handle(tgb_world* w, void** stream) {
+    if (!w || !stream) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *stream = (void*)w->stream;
+    return TGB_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,78 @@
+/*
+ * tgb_dev.h -- data layout shared by the host side of the C ABI (tgb_capi.cu) and the kernels.
+ *
+ * HBM layout (one tgb_world, n_env environments, scalar type T = float or double):
+ *   state  T[n_env][stride]        env-major records: R bodies x 13 {pos3 (relative to the env frame origin), quat4 xyzw,
+ *                                   linvel3 (relative to the env frame velocity), angvel3} then C cables x 4
+ *                                   {rest length, previous length, preferred length, motor velocity}; stride is padded
+ *                                   to a 16-byte multiple so that a group of lanes moves its record with 128-bit
+ *                                   accesses and a CTA's records form one contiguous span.
+ *   frame  double[n_env][8]         env frame: origin O(3), velocity V(3), controller time, spare.  World position of
+ *                                   a body = O + pos, world velocity = V + linvel.  Keeping the common translation of a
+ *                                   free-falling structure in double keeps the float state small, so cable stretch
+ *                                   (a difference of anchor positions) does not lose digits far from the origin.
+ *   ctrl   double[n_env][ctrl_stride] controller parameter rows (tgb_set_controller)
+ *   com0   double[n_env][3]         mass-weighted centre of mass at episode start (scores)
+ *   status int[n_env]
+ *
+ * The model (everything identical across environments) is packed once into two small arrays, field-major so that
+ * lanes that index consecutive bodies / cables read consecutive shared-memory words:
+ *   model_t T[]   : body fields [TGB_NBF][R], shape fields [TGB_NSF][S], cable fields [TGB_NCF][C]
+ *   model_i int[] : body ints [TGB_NBI][R], cable ints [TGB_NCI][C], incidence list [n_inc]
+ */
+#ifndef TGB_DEV_H
+#define TGB_DEV_H
+
+#include <stdint.h>
+
+/* body T-fields */
+enum { BF_INVMASS = 0, BF_GFY, BF_INVIX, BF_INVIY, BF_INVIZ, BF_IX, BF_IY, BF_IZ, BF_MU, BF_RESTITUTION, BF_MASS, TGB_NBF };
+/* body int-fields */
+enum { BI_SHAPE_BEGIN = 0, BI_SHAPE_COUNT, BI_INC_BEGIN, BI_INC_COUNT, BI_GYRO, TGB_NBI };
+/* shape T-fields */
+enum { SF_RADIUS = 0, SF_HALFLEN, SF_MARGIN, SF_POSX, SF_POSY, SF_POSZ, SF_ROT0, TGB_NSF = SF_ROT0 + 9 };
+/* cable T-fields */
+enum {
+    CF_LAX = 0, CF_LAY, CF_LAZ, CF_LBX, CF_LBY, CF_LBZ, CF_K, CF_C, CF_MAXTENS, CF_TVEL, CF_MINAL, CF_MINRL,
+    CF_MRADIUS, CF_MFRICTION, CF_MINERTIA, TGB_NCF
+};
+/* cable int-fields */
+enum { CI_A = 0, CI_B, CI_ACTUATOR, CI_BACKDRIVABLE, TGB_NCI };
+/* per-cable state words in the env record */
+enum { CS_REST = 0, CS_PREV, CS_PREF, CS_MOTORVEL, TGB_NCS };
+/* per-body state words in the env record */
+enum { TGB_NBS = 13 };
+/* per-contact solver row words kept in shared memory */
+enum {
+    CT_RXN = 0, CT_ANGN = 3, CT_INVDIAGN = 6, CT_RHSN, CT_RHSPEN, CT_LAMN, CT_LAMPUSH, CT_T = 11, CT_RXT = 14, CT_ANGT = 17,
+    CT_INVDIAGT = 20, CT_RHST, CT_LAMT, TGB_NCT
+};
+/* frame doubles */
+enum { FR_O = 0, FR_V = 3, FR_CTRLTIME = 6, FR_SPARE = 7, TGB_NFR = 8 };
+
+#define TGB_STATUS_NONFINITE 1
+#define TGB_STATUS_HEIGHT 2
+
+struct tgb_step_args {
+    void* state;          /* T[n_env][stride] */
+    double* frame;        /* [n_env][TGB_NFR] */
+    const double* ctrl;   /* [n_env][ctrl_stride] or NULL */
+    int* status;          /* [n_env] */
+    const void* model_t;  /* packed T fields */
+    const int* model_i;   /* packed int fields */
+    int n_env, n_steps;
+    int R, C, S, n_inc;
+    int stride;           /* T words per env record */
+    int cap_contacts;     /* contact slots per body */
+    int frame_body;       /* body whose position/velocity the env frame follows */
+    int ctrl_kind, ctrl_stride;
+    int iterations;       /* PGS iterations */
+    int ground_kind;
+    int model_t_words, model_i_words;
+    double dt;
+    double gn[3], goff;   /* ground surface { x : gn.x = goff } */
+    double ground_restitution;
+    double height_lo, height_hi; /* status bit1 when the mass centre leaves [lo, hi]; lo > hi disables */
+};
+
+#endif

@@ -1,0 +1,610 @@
+/*
+ * tgb_step.cuh -- the fused batched step kernel: n_steps x tgSimulation::step(dt) for every environment.
+ *
+ * Reference path replaced (paths relative to the NTRTsim tree):
+ *   tgSimulation::step                 src/core/tgSimulation.cpp:193-225     world step first, then the models
+ *   tgWorldBulletPhysicsImpl::step     src/core/tgWorldBulletPhysicsImpl.cpp:209-221 -> Bullet stepSimulation(dt,1,dt)
+ *   tgBasicActuator::step / moveMotors src/core/tgBasicActuator.cpp:96-113,170-225
+ *   tgKinematicActuator                src/core/tgKinematicActuator.cpp:135-225
+ *   tgBulletSpringCable                src/core/tgBulletSpringCable.cpp:90-141
+ *   anchors                            src/core/tgBulletSpringCableAnchor.cpp:76-87
+ *   controllers                        src/controllers/tgTensionController.cpp:50-88,
+ *                                      src/examples/craterEscape/EscapeController.cpp:100-117,245-291,
+ *                                      src/examples/motorModel/tsTestRig.cpp:170-199
+ *
+ * Mapping.  A group of LPE consecutive lanes of one warp owns one environment for the whole launch.  Lane j of the
+ * group is body j (rigid-body state lives in its registers across all n_steps) and cables j, j+LPE, ...  Per step:
+ *   cable phase   lanes over cables : controller -> motors -> Hooke + damping force from the published body poses;
+ *                                     the impulse J = F dt of each cable goes to shared memory
+ *   body phase    lanes over bodies : gather the impulses of the incident cables in cable order (static incidence
+ *                                     list; deterministic, no atomics), then the whole world step of that body:
+ *                                     gravity + gyroscopic term, ground contact manifold, projected Gauss-Seidel,
+ *                                     transform integration; publish the new pose
+ * Bodies only interact through cables, and the ground is static, so the contact solve of each body is independent
+ * and a body never leaves its lane.  Two __syncwarp() per step, no block-level barrier inside the step loop.
+ * HBM is touched only at launch boundaries: the CTA's environment records are one contiguous span that is moved
+ * with 128-bit accesses into shared memory and back.
+ *
+ * No tensor cores: nothing here is a dense contraction.
+ */
+#pragma once
+#include "../../include/ntrtsim_b200.h"
+#include "tgb_dev.h"
+#include "tgb_math.cuh"
+
+namespace tgb {
+
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { typedef float4 type; enum { N = 4 }; };
+template <> struct Vec16<double> { typedef double2 type; enum { N = 2 }; };
+
+/* Bullet 2.82 btContactSolverInfo defaults reached through tgWorldBulletPhysicsImpl.cpp:134-146 (left untouched). */
+template <typename T> struct SolverConst {
+    static TGB_D T erp() { return T(0.2); }
+    static TGB_D T erp2() { return T(0.8); }
+    static TGB_D T splitThreshold() { return T(-0.04); }
+    static TGB_D T turnErp() { return T(0.1); }
+    static TGB_D T maxGyro() { return T(100.0); }
+    static TGB_D T breakingThreshold() { return T(0.02); }
+    static TGB_D T angularMotionThreshold() { return T(0.5 * 1.57079632679489661923); }
+};
+
+/* Rigid-body state held in the registers of the lane that owns the body. */
+template <typename T>
+struct BodyReg {
+    V3<T> x;      /* position relative to the env frame origin */
+    Q4<T> q;
+    V3<T> v;      /* linear velocity relative to the env frame velocity */
+    V3<T> w;
+    M3<T> B;      /* basis = fromQuat(q) */
+    M3<T> Iinv;   /* world inverse inertia */
+};
+
+/* btTransformUtil::integrateTransform on (x, q) */
+template <typename T>
+TGB_D void integrateTransform(V3<T>& x, Q4<T>& q, const V3<T>& linvel, const V3<T>& angvel, T dt) {
+    x = x + linvel * dt;
+    V3<T> axis;
+    T fAngle = angvel.length();
+    if (fAngle * dt > SolverConst<T>::angularMotionThreshold()) fAngle = SolverConst<T>::angularMotionThreshold() / dt;
+    if (fAngle < T(0.001)) {
+        axis = angvel * (T(0.5) * dt - (dt * dt * dt) * T(0.020833333333) * fAngle * fAngle);
+    } else {
+        axis = angvel * (tsin(T(0.5) * fAngle * dt) / fAngle);
+    }
+    Q4<T> dorn(axis.x, axis.y, axis.z, tcos(fAngle * dt * T(0.5)));
+    Q4<T> p = qmul(dorn, q);
+    T l = tsqrt(p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w);
+    q = Q4<T>(p.x / l, p.y / l, p.z / l, p.w / l);
+}
+
+/* btPlaneSpace1, first vector */
+template <typename T>
+TGB_D V3<T> planeSpace1(const V3<T>& n) {
+    if (tabs(n.z) > T(0.7071067811865475244008443621048490)) {
+        T a = n.y * n.y + n.z * n.z;
+        T k = T(1) / tsqrt(a);
+        return V3<T>(T(0), -n.z * k, n.y * k);
+    }
+    T a = n.x * n.x + n.y * n.y;
+    T k = T(1) / tsqrt(a);
+    return V3<T>(-n.y * k, n.x * k, T(0));
+}
+
+template <typename T> TGB_D T epsilonOf();
+template <> TGB_D float epsilonOf<float>() { return 1.1920928955078125e-7f; }
+template <> TGB_D double epsilonOf<double>() { return 2.2204460492503131e-16; }
+
+/* sin of a double-precision phase: exact-type sin for double, range-reduced sinf for float */
+TGB_D double sinPhase(double arg, double) { return sin(arg); }
+TGB_D float sinPhase(double arg, float) {
+    const double twoPi = 6.283185307179586476925286766559;
+    double r = arg - twoPi * rint(arg * (1.0 / twoPi));
+    return sinf((float)r);
+}
+
+/* Views of the packed model in shared memory. */
+template <typename T>
+struct ModelView {
+    const T* bt; const T* st; const T* ct;
+    const int* bi; const int* ci; const int* inc;
+    int R, S, C;
+    TGB_D T body(int f, int b) const { return bt[f * R + b]; }
+    TGB_D int bodyi(int f, int b) const { return bi[f * R + b]; }
+    TGB_D T shape(int f, int s) const { return st[f * S + s]; }
+    TGB_D T cable(int f, int c) const { return ct[f * C + c]; }
+    TGB_D int cablei(int f, int c) const { return ci[f * C + c]; }
+};
+
+template <typename T, int LPE>
+__global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef typename Vec16<T>::type vec_t;
+    const int VN = Vec16<T>::N;
+
+    const int tid = threadIdx.x;
+    const int lane = tid % LPE;
+    const int grp = tid / LPE;
+    const int groupsPerBlock = blockDim.x / LPE;
+    const int envRaw = blockIdx.x * groupsPerBlock + grp;
+    const bool live = envRaw < a.n_env;
+    const int env = live ? envRaw : a.n_env - 1; /* tail groups shadow the last env and never store */
+    /* lanes of this group inside the warp, for shuffles */
+    const unsigned fullMask = 0xffffffffu;
+    const int warpLane = tid & 31;
+    const int groupLane0 = warpLane - lane;
+
+    const int R = a.R, C = a.C, S = a.S;
+
+    /* ---- shared memory carve-up ----------------------------------------------------------------------- */
+    /* [model T][per-group T regions][per-group double regions][model ints] */
+    T* sModelT = reinterpret_cast<T*>(smem_raw);
+    const int modelTWords = (a.model_t_words + 3) & ~3;
+    const int poseWords = 12 * LPE;
+    const int jWords = 3 * C;
+    const int ctWords = a.cap_contacts * TGB_NCT * LPE;
+    int groupTWords = a.stride + poseWords + jWords + ctWords;
+    groupTWords = (groupTWords + 3) & ~3;
+    /* keep group regions LPE banks apart so that the groups of one warp do not collide */
+    if (LPE < 32) { while ((groupTWords & 31) != (LPE < 4 ? 4 : LPE)) groupTWords += 4; }
+    T* sGroupT = sModelT + modelTWords + grp * groupTWords;
+    T* sState = sGroupT;                       /* env record: bodies then cables */
+    T* sPose = sState + a.stride;              /* [12][LPE] : pos3, basis9 of each body */
+    T* sJ = sPose + poseWords;                 /* [C][3] */
+    T* sCt = sJ + jWords;                      /* [cap][TGB_NCT][LPE] */
+    const int groupDWords = a.ctrl_stride + 8;
+    double* sD = reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) + grp * groupDWords;
+    double* sCtrl = sD;                        /* controller parameter row */
+    double* sCum = sD + a.ctrl_stride;         /* sine controller: cumulative phase per cluster */
+    int* sModelI = reinterpret_cast<int*>(reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) +
+                                          groupsPerBlock * groupDWords);
+
+    /* ---- stage the model and this group's env record ----------------------------------------------------- */
+    {
+        const T* gmt = reinterpret_cast<const T*>(a.model_t);
+        for (int i = tid; i < a.model_t_words; i += blockDim.x) sModelT[i] = gmt[i];
+        for (int i = tid; i < a.model_i_words; i += blockDim.x) sModelI[i] = a.model_i[i];
+        const vec_t* gs = reinterpret_cast<const vec_t*>(reinterpret_cast<const T*>(a.state) + (size_t)env * a.stride);
+        vec_t* ss = reinterpret_cast<vec_t*>(sState);
+        for (int i = lane; i < a.stride / VN; i += LPE) ss[i] = gs[i];
+        if (a.ctrl != nullptr)
+            for (int i = lane; i < a.ctrl_stride; i += LPE) sCtrl[i] = a.ctrl[(size_t)env * a.ctrl_stride + i];
+    }
+    __syncthreads();
+
+    ModelView<T> M;
+    M.R = R; M.S = S; M.C = C;
+    M.bt = sModelT; M.st = M.bt + TGB_NBF * R; M.ct = M.st + TGB_NSF * S;
+    M.bi = sModelI; M.ci = M.bi + TGB_NBI * R; M.inc = M.ci + TGB_NCI * C;
+
+    const T dt = (T)a.dt;
+    const V3<T> gn((T)a.gn[0], (T)a.gn[1], (T)a.gn[2]);
+    const int ctrlKind = a.ctrl_kind;
+
+    /* env frame (every lane of the group keeps an identical copy) */
+    double Ox, Oy, Oz, Vx, Vy, Vz, ctrlTime;
+    {
+        const double* f = a.frame + (size_t)env * TGB_NFR;
+        Ox = f[FR_O]; Oy = f[FR_O + 1]; Oz = f[FR_O + 2];
+        Vx = f[FR_V]; Vy = f[FR_V + 1]; Vz = f[FR_V + 2];
+        ctrlTime = f[FR_CTRLTIME];
+    }
+
+    if (ctrlKind == TGB_CTRL_ESCAPE_SINE && lane == 0) {
+        /* EscapeController.cpp:279-290: the phase grows by the cluster's phase change at every cluster boundary */
+        double ph = 0.0;
+        sCum[0] = 0.0;
+        for (int c = 1; c < 8; ++c) { ph += sCtrl[c * 4 + 2]; sCum[c] = ph; }
+    }
+
+    /* ---- body state into registers ------------------------------------------------------------------------ */
+    const bool hasBody = lane < R;
+    const int bidx = hasBody ? lane : 0;
+    BodyReg<T> b;
+    {
+        const T* s = sState + bidx * TGB_NBS;
+        b.x = V3<T>(s[0], s[1], s[2]);
+        b.q = Q4<T>(s[3], s[4], s[5], s[6]);
+        b.v = V3<T>(s[7], s[8], s[9]);
+        b.w = V3<T>(s[10], s[11], s[12]);
+        b.B = M3<T>::fromQuat(b.q);
+    }
+    const T invMass = M.body(BF_INVMASS, bidx);
+    const V3<T> invI(M.body(BF_INVIX, bidx), M.body(BF_INVIY, bidx), M.body(BF_INVIZ, bidx));
+    const V3<T> inertia(M.body(BF_IX, bidx), M.body(BF_IY, bidx), M.body(BF_IZ, bidx));
+    const T gfy = M.body(BF_GFY, bidx);
+    const T mu = M.body(BF_MU, bidx);
+    const T restitutionCombined = M.body(BF_RESTITUTION, bidx) * (T)a.ground_restitution;
+    const int shapeBegin = M.bodyi(BI_SHAPE_BEGIN, bidx), shapeCount = M.bodyi(BI_SHAPE_COUNT, bidx);
+    const int incBegin = M.bodyi(BI_INC_BEGIN, bidx), incCount = M.bodyi(BI_INC_COUNT, bidx);
+    const bool gyro = M.bodyi(BI_GYRO, bidx) != 0;
+    const bool dynamic = hasBody && invMass != T(0);
+    b.Iinv = b.B.conjugateDiag(invI);
+
+    auto publishPose = [&]() {
+        if (hasBody) {
+            sPose[0 * LPE + lane] = b.x.x; sPose[1 * LPE + lane] = b.x.y; sPose[2 * LPE + lane] = b.x.z;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) sPose[(3 + i * 3 + j) * LPE + lane] = b.B.m[i][j];
+        }
+    };
+    publishPose();
+    __syncwarp();
+
+#define CT(slot, f) sCt[((slot) * TGB_NCT + (f)) * LPE + lane]
+
+    for (int step = 0; step < a.n_steps; ++step) {
+        /* =============================== world step (tgSimulation.cpp:205) =============================== */
+        if (dynamic) {
+            /* applyGravity + solver-body external impulses */
+            V3<T> extLin(T(0), (gfy * invMass) * dt, T(0));
+            V3<T> extAng(T(0), T(0), T(0));
+            if (gyro) {
+                /* btRigidBody::computeGyroscopicForce, explicit, clamped at maxGyroscopicForce */
+                M3<T> Iw = b.B.conjugateDiag(inertia);
+                V3<T> tmp = Iw * b.w;
+                V3<T> gf = b.w.cross(tmp);
+                T l2 = gf.length2();
+                if (l2 > SolverConst<T>::maxGyro() * SolverConst<T>::maxGyro()) gf *= T(1) / tsqrt(l2) * SolverConst<T>::maxGyro();
+                extAng -= b.Iinv.tmul(gf) * dt;
+            }
+            const V3<T> Vf((T)Vx, (T)Vy, (T)Vz);
+            const V3<T> linvel = b.v + Vf; /* world linear velocity */
+
+            /* ---- ground contact manifold (analytic cylinder rim points against the ground surface) ---- */
+            int nc = 0;
+            if (a.ground_kind != TGB_GROUND_EMPTY) {
+                /* signed height of the frame origin above the surface, formed in double */
+                const T originHeight = (T)(a.gn[0] * Ox + a.gn[1] * Oy + a.gn[2] * Oz - a.goff);
+                for (int si = shapeBegin; si < shapeBegin + shapeCount; ++si) {
+                    const T radius = M.shape(SF_RADIUS, si), halfLen = M.shape(SF_HALFLEN, si), margin = M.shape(SF_MARGIN, si);
+                    const V3<T> spos(M.shape(SF_POSX, si), M.shape(SF_POSY, si), M.shape(SF_POSZ, si));
+                    /* R = B * shapeRot: only columns 0 and 1 are needed */
+                    V3<T> r0(M.shape(SF_ROT0 + 0, si), M.shape(SF_ROT0 + 3, si), M.shape(SF_ROT0 + 6, si)); /* column 0 of shapeRot */
+                    V3<T> r1(M.shape(SF_ROT0 + 1, si), M.shape(SF_ROT0 + 4, si), M.shape(SF_ROT0 + 7, si)); /* column 1 */
+                    const V3<T> col0 = b.B * r0;
+                    const V3<T> axisDir = b.B * r1;
+                    const V3<T> c = b.B * spos + b.x;
+                    const T rc = radius - margin, hc = halfLen - margin;
+                    const T na = gn.dot(axisDir);
+                    const V3<T> perp = -(gn - axisDir * na);
+                    const T pl = perp.length();
+                    V3<T> u;
+                    if (pl > T(1e-9)) u = perp / pl;
+                    else u = col0;
+                    const V3<T> wdir = axisDir.cross(u);
+                    int count = 0;
+                    for (int e = 0; e < 2 && count < 4; ++e) {
+                        const V3<T> ce = c + axisDir * (e == 0 ? -hc : hc);
+                        for (int k = 0; k < 4 && count < 4; ++k) {
+                            const V3<T> dir = (k == 0) ? u : (k == 1) ? wdir : (k == 2) ? -u : -wdir;
+                            const V3<T> pc = ce + dir * rc;
+                            const T dist = (gn.dot(pc) + originHeight) - margin;
+                            if (dist <= SolverConst<T>::breakingThreshold()) {
+                                /* ---- setupContactConstraint / setupFrictionConstraint for this point ---- */
+                                const V3<T> r = (pc - gn * margin) - b.x;
+                                const V3<T> rxn = r.cross(gn);
+                                const V3<T> angN = b.Iinv * rxn;
+                                const T denom = invMass + gn.dot(angN.cross(r));
+                                const T invDiagN = T(1) / denom;
+                                const V3<T> vel = linvel + b.w.cross(r);
+                                const T relVel = gn.dot(vel);
+                                T restitution = restitutionCombined * -relVel;
+                                if (restitution <= T(0)) restitution = T(0);
+                                const V3<T> lat = vel - gn * relVel;
+                                const T lat2 = lat.length2();
+                                V3<T> t;
+                                if (lat2 > epsilonOf<T>()) t = lat * (T(1) / tsqrt(lat2));
+                                else t = planeSpace1(gn);
+                                const T velDotN = gn.dot(linvel + extLin) + rxn.dot(b.w + extAng);
+                                T velocityError = restitution - velDotN;
+                                const T penetration = dist;
+                                T erp = SolverConst<T>::erp2();
+                                if (penetration > SolverConst<T>::splitThreshold()) erp = SolverConst<T>::erp();
+                                T positionalError = T(0);
+                                if (penetration > T(0)) velocityError -= penetration / dt;
+                                else positionalError = -penetration * erp / dt;
+                                const T penetrationImpulse = positionalError * invDiagN;
+                                const T velocityImpulse = velocityError * invDiagN;
+                                T rhsN, rhsPen;
+                                if (penetration > SolverConst<T>::splitThreshold()) { rhsN = penetrationImpulse + velocityImpulse; rhsPen = T(0); }
+                                else { rhsN = velocityImpulse; rhsPen = penetrationImpulse; }
+                                const V3<T> rxt = r.cross(t);
+                                const V3<T> angT = b.Iinv * rxt;
+                                const T denomT = invMass + t.dot(angT.cross(r));
+                                const T invDiagT = T(1) / denomT;
+                                const T relT = t.dot(linvel + extLin) + rxt.dot(b.w);
+                                const T rhsT = (T(0) - relT) * invDiagT;
+                                CT(nc, CT_RXN + 0) = rxn.x; CT(nc, CT_RXN + 1) = rxn.y; CT(nc, CT_RXN + 2) = rxn.z;
+                                CT(nc, CT_ANGN + 0) = angN.x; CT(nc, CT_ANGN + 1) = angN.y; CT(nc, CT_ANGN + 2) = angN.z;
+                                CT(nc, CT_INVDIAGN) = invDiagN; CT(nc, CT_RHSN) = rhsN; CT(nc, CT_RHSPEN) = rhsPen;
+                                CT(nc, CT_LAMN) = T(0); CT(nc, CT_LAMPUSH) = T(0);
+                                CT(nc, CT_T + 0) = t.x; CT(nc, CT_T + 1) = t.y; CT(nc, CT_T + 2) = t.z;
+                                CT(nc, CT_RXT + 0) = rxt.x; CT(nc, CT_RXT + 1) = rxt.y; CT(nc, CT_RXT + 2) = rxt.z;
+                                CT(nc, CT_ANGT + 0) = angT.x; CT(nc, CT_ANGT + 1) = angT.y; CT(nc, CT_ANGT + 2) = angT.z;
+                                CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = T(0);
+                                ++nc;
+                                ++count;
+                            }
+                        }
+                    }
+                }
+            }
+
+            /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
+            V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
+            if (nc > 0) {
+                for (int it = 0; it < a.iterations; ++it) {
+                    for (int c = 0; c < nc; ++c) {
+                        const T rhsPen = CT(c, CT_RHSPEN);
+                        if (rhsPen == T(0)) continue;
+                        const V3<T> rxn(CT(c, CT_RXN + 0), CT(c, CT_RXN + 1), CT(c, CT_RXN + 2));
+                        const V3<T> angN(CT(c, CT_ANGN + 0), CT(c, CT_ANGN + 1), CT(c, CT_ANGN + 2));
+                        const T invDiagN = CT(c, CT_INVDIAGN);
+                        T delta = rhsPen;
+                        const T dv = gn.dot(push) + rxn.dot(turn);
+                        delta -= dv * invDiagN;
+                        const T lam = CT(c, CT_LAMPUSH);
+                        const T sum = lam + delta;
+                        if (sum < T(0)) { delta = -lam; CT(c, CT_LAMPUSH) = T(0); }
+                        else CT(c, CT_LAMPUSH) = sum;
+                        push += gn * (invMass * delta);
+                        turn += angN * delta;
+                    }
+                }
+                for (int it = 0; it < a.iterations; ++it) {
+                    for (int c = 0; c < nc; ++c) {
+                        const V3<T> rxn(CT(c, CT_RXN + 0), CT(c, CT_RXN + 1), CT(c, CT_RXN + 2));
+                        const V3<T> angN(CT(c, CT_ANGN + 0), CT(c, CT_ANGN + 1), CT(c, CT_ANGN + 2));
+                        const T invDiagN = CT(c, CT_INVDIAGN);
+                        T delta = CT(c, CT_RHSN);
+                        const T dv = gn.dot(dLin) + rxn.dot(dAng);
+                        delta -= dv * invDiagN;
+                        const T lam = CT(c, CT_LAMN);
+                        const T sum = lam + delta;
+                        if (sum < T(0)) { delta = -lam; CT(c, CT_LAMN) = T(0); }
+                        else CT(c, CT_LAMN) = sum;
+                        dLin += gn * (invMass * delta);
+                        dAng += angN * delta;
+                    }
+                    for (int c = 0; c < nc; ++c) {
+                        const T lamN = CT(c, CT_LAMN);
+                        if (!(lamN > T(0))) continue;
+                        const V3<T> t(CT(c, CT_T + 0), CT(c, CT_T + 1), CT(c, CT_T + 2));
+                        const V3<T> rxt(CT(c, CT_RXT + 0), CT(c, CT_RXT + 1), CT(c, CT_RXT + 2));
+                        const V3<T> angT(CT(c, CT_ANGT + 0), CT(c, CT_ANGT + 1), CT(c, CT_ANGT + 2));
+                        const T invDiagT = CT(c, CT_INVDIAGT);
+                        const T lo = -mu * lamN, hi = mu * lamN;
+                        T delta = CT(c, CT_RHST);
+                        const T dv = t.dot(dLin) + rxt.dot(dAng);
+                        delta -= dv * invDiagT;
+                        const T lam = CT(c, CT_LAMT);
+                        const T sum = lam + delta;
+                        if (sum < lo) { delta = lo - lam; CT(c, CT_LAMT) = lo; }
+                        else if (sum > hi) { delta = hi - lam; CT(c, CT_LAMT) = hi; }
+                        else CT(c, CT_LAMT) = sum;
+                        dLin += t * (invMass * delta);
+                        dAng += angT * delta;
+                    }
+                }
+            }
+
+            /* ---- write back, split-impulse correction, integrateTransforms ---- */
+            b.v = (b.v + dLin) + extLin;
+            b.w = (b.w + dAng) + extAng;
+            if (push.nonzero() || turn.nonzero()) integrateTransform(b.x, b.q, push, turn * SolverConst<T>::turnErp(), dt);
+            integrateTransform(b.x, b.q, b.v, b.w, dt);
+            b.B = M3<T>::fromQuat(b.q);
+            b.Iinv = b.B.conjugateDiag(invI);
+        }
+
+        /* ---- env frame: advance the origin with the frame velocity, then re-centre on the frame body ---- */
+        {
+            Ox += Vx * a.dt; Oy += Vy * a.dt; Oz += Vz * a.dt;
+            const int src = groupLane0 + a.frame_body;
+            const T sx = __shfl_sync(fullMask, b.x.x, src), sy = __shfl_sync(fullMask, b.x.y, src), sz = __shfl_sync(fullMask, b.x.z, src);
+            const T svx = __shfl_sync(fullMask, b.v.x, src), svy = __shfl_sync(fullMask, b.v.y, src), svz = __shfl_sync(fullMask, b.v.z, src);
+            Ox += (double)sx; Oy += (double)sy; Oz += (double)sz;
+            Vx += (double)svx; Vy += (double)svy; Vz += (double)svz;
+            b.x -= V3<T>(sx, sy, sz);
+            b.v -= V3<T>(svx, svy, svz);
+        }
+        publishPose();
+        __syncwarp();
+
+        /* =============================== models step (tgSimulation.cpp:208-211) =============================== */
+        if (ctrlKind == TGB_CTRL_ESCAPE_SINE) ctrlTime += a.dt; /* EscapeController::m_totalTime */
+        for (int c = lane; c < C; c += LPE) {
+            const int ia = M.cablei(CI_A, c), ib = M.cablei(CI_B, c);
+            const int actuator = M.cablei(CI_ACTUATOR, c);
+            const V3<T> la(M.cable(CF_LAX, c), M.cable(CF_LAY, c), M.cable(CF_LAZ, c));
+            const V3<T> lb(M.cable(CF_LBX, c), M.cable(CF_LBY, c), M.cable(CF_LBZ, c));
+            const T k = M.cable(CF_K, c), damp = M.cable(CF_C, c);
+            V3<T> xa(sPose[0 * LPE + ia], sPose[1 * LPE + ia], sPose[2 * LPE + ia]);
+            V3<T> xb(sPose[0 * LPE + ib], sPose[1 * LPE + ib], sPose[2 * LPE + ib]);
+            M3<T> Ba, Bb;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { Ba.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ia]; Bb.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ib]; }
+            /* anchors: tgBulletSpringCableAnchor.cpp:83-87 */
+            const V3<T> p1 = Ba * la + xa, p2 = Bb * lb + xb;
+            const V3<T> dist = p2 - p1;
+            const T L = dist.length();
+
+            T* cs = sState + R * TGB_NBS + c * TGB_NCS;
+            T rest = cs[CS_REST], prev = cs[CS_PREV], pref = cs[CS_PREF], motorVel = cs[CS_MOTORVEL];
+            T desiredTorque = T(0);
+
+            /* tgBasicActuator::moveMotors, tgBasicActuator.cpp:170-225 */
+            auto moveMotors = [&]() {
+                const T stepSize = M.cable(CF_TVEL, c) * dt;
+                const T maxTens = M.cable(CF_MAXTENS, c);
+                if ((L - pref) * k > maxTens) pref = L - maxTens / k;
+                const T diff = pref - rest;
+                const T fabsDiff = tabs(diff);
+                if ((L > M.cable(CF_MINAL, c)) || (diff > T(0))) {
+                    if (fabsDiff > stepSize) rest += (diff / fabsDiff) * stepSize;
+                    else rest += diff;
+                }
+                const T minRL = M.cable(CF_MINRL, c);
+                rest = (rest > minRL) ? rest : minRL;
+            };
+
+            /* ---- model-level controllers (run before the children step) ---- */
+            if (ctrlKind == TGB_CTRL_SETPOINT) {
+                if (actuator == TGB_ACT_BASIC) {
+                    const T input = (T)sCtrl[c];
+                    if (!(input < T(0))) { pref = input; moveMotors(); }
+                }
+            } else if (ctrlKind == TGB_CTRL_TORQUE) {
+                if (actuator == TGB_ACT_KINEMATIC) desiredTorque = (T)sCtrl[c];
+            } else if (ctrlKind == TGB_CTRL_TENSION) {
+                if (actuator == TGB_ACT_BASIC) {
+                    /* tgTensionController::control(dt, setPoint): tgTensionController.cpp:50-88 */
+                    const T setPoint = (T)sCtrl[0];
+                    T tension = (L - rest) * k;
+                    tension = tension < T(0) ? T(0) : tension;
+                    const T delta = setPoint - tension;
+                    const T diff = delta / k;
+                    T newLength = rest - diff;
+                    newLength = newLength < T(0) ? T(0) : newLength;
+                    pref = newLength;
+                    moveMotors();
+                }
+            } else if (ctrlKind == TGB_CTRL_ESCAPE_SINE) {
+                if (c < 24) {
+                    /* EscapeController::setPreferredMuscleLengths, EscapeController.cpp:245-291 */
+                    const int cluster = c < 16 ? (c >> 2) : 4 + ((c - 16) >> 1);
+                    const bool firstOfCluster = c < 16 ? ((c & 3) == 0) : (((c - 16) & 1) == 0);
+                    const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
+                    const double arg = sCtrl[cluster * 4 + 1] * ctrlTime + phase;
+                    T newLength = (T)sCtrl[cluster * 4 + 0] * sinPhase(arg, T(0)) + (T)sCtrl[cluster * 4 + 3];
+                    const T L0 = (T)sCtrl[32];
+                    const T minLength = L0 * (T(1) - T(0.50)), maxLength = L0 * (T(1) + T(0.50));
+                    if (newLength <= minLength) newLength = minLength;
+                    else if (newLength >= maxLength) newLength = maxLength;
+                    if (!(newLength < T(0))) { pref = newLength; moveMotors(); }
+                }
+                moveMotors(); /* EscapeController.cpp:108-116: every muscle's motors move a second time */
+            }
+
+            /* ---- tgKinematicActuator::integrateRestLength, tgKinematicActuator.cpp:186-225 ---- */
+            if (actuator == TGB_ACT_KINEMATIC) {
+                T tension = (L - rest) * k;
+                tension = tension < T(0) ? T(0) : tension;
+                const T mRadius = M.cable(CF_MRADIUS, c);
+                T maxTorque = M.cable(CF_MAXTENS, c) * mRadius * (T(1) - mRadius * tabs(motorVel) / M.cable(CF_TVEL, c));
+                maxTorque = maxTorque < T(0) ? T(0) : maxTorque;
+                const T applied = tabs(desiredTorque) < maxTorque ? desiredTorque : desiredTorque / tabs(desiredTorque) * maxTorque;
+                const T acc = (applied - M.cable(CF_MFRICTION, c) * motorVel + tension * mRadius) / M.cable(CF_MINERTIA, c);
+                if (M.cablei(CI_BACKDRIVABLE, c) == 0 && acc * applied <= T(0))
+                    motorVel = motorVel + acc * dt > T(0) ? T(0) : motorVel + acc * dt;
+                else
+                    motorVel += acc * dt;
+                rest += mRadius * motorVel * dt;
+                const T minRL = M.cable(CF_MINRL, c);
+                rest = (rest > minRL) ? rest : minRL;
+            }
+
+            /* ---- tgBulletSpringCable::calculateAndApplyForce, tgBulletSpringCable.cpp:90-141 ---- */
+            const V3<T> unit = dist / L;
+            const T stretch = L - rest;
+            T magnitude = k * stretch;
+            const T deltaStretch = L - prev;
+            const T velocity = deltaStretch / dt;
+            T damping = damp * velocity;
+            if (tabs(magnitude) * T(1) < tabs(damping)) damping = (damping > T(0) ? magnitude * T(1) : -magnitude * T(1));
+            magnitude += damping;
+            V3<T> force(T(0), T(0), T(0));
+            if (L > rest) force = unit * magnitude;
+            prev = L;
+            const V3<T> J = force * dt;
+            sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
+            cs[CS_REST] = rest; cs[CS_PREV] = prev; cs[CS_PREF] = pref; cs[CS_MOTORVEL] = motorVel;
+        }
+        __syncwarp();
+
+        /* ---- applyImpulse of every incident cable end, in cable order (btRigidBody::applyImpulse) ---- */
+        if (dynamic) {
+            for (int i = incBegin; i < incBegin + incCount; ++i) {
+                const int code = M.inc[i];
+                const int c = code & 0xffffff;
+                const bool sideB = (code >> 24) != 0;
+                V3<T> J(sJ[c * 3 + 0], sJ[c * 3 + 1], sJ[c * 3 + 2]);
+                const V3<T> local = sideB ? V3<T>(M.cable(CF_LBX, c), M.cable(CF_LBY, c), M.cable(CF_LBZ, c))
+                                          : V3<T>(M.cable(CF_LAX, c), M.cable(CF_LAY, c), M.cable(CF_LAZ, c));
+                if (sideB) J = -J;
+                const V3<T> rel = (b.B * local + b.x) - b.x;
+                b.v += J * invMass;
+                b.w += b.Iinv * rel.cross(J);
+            }
+        }
+    }
+#undef CT
+
+    /* ---- store: bodies back into the record, record back to HBM, frame, status ---------------------------- */
+    if (hasBody) {
+        T* s = sState + lane * TGB_NBS;
+        s[0] = b.x.x; s[1] = b.x.y; s[2] = b.x.z;
+        s[3] = b.q.x; s[4] = b.q.y; s[5] = b.q.z; s[6] = b.q.w;
+        s[7] = b.v.x; s[8] = b.v.y; s[9] = b.v.z;
+        s[10] = b.w.x; s[11] = b.w.y; s[12] = b.w.z;
+    }
+    /* status: non-finite state, mass centre outside the height window */
+    {
+        bool bad = false;
+        if (hasBody) {
+            const T sum = b.x.x + b.x.y + b.x.z + b.q.x + b.q.y + b.q.z + b.q.w + b.v.x + b.v.y + b.v.z + b.w.x + b.w.y + b.w.z;
+            bad = !(tabs(sum) <= T(1e30));
+        }
+        T my = hasBody ? M.body(BF_MASS, bidx) * b.x.y : T(0);
+        T mm = hasBody ? M.body(BF_MASS, bidx) : T(0);
+        unsigned anyBad = 0;
+#pragma unroll
+        for (int off = LPE / 2; off > 0; off >>= 1) {
+            my += __shfl_xor_sync(fullMask, my, off);
+            mm += __shfl_xor_sync(fullMask, mm, off);
+        }
+        anyBad = __ballot_sync(fullMask, bad);
+        const unsigned groupMask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
+        int st = 0;
+        if (anyBad & groupMask) st |= TGB_STATUS_NONFINITE;
+        if (a.height_lo <= a.height_hi && mm > T(0)) {
+            const double h = Oy + (double)(my / mm);
+            if (!(h > a.height_lo && h < a.height_hi)) st |= TGB_STATUS_HEIGHT;
+        }
+        if (live && lane == 0 && st != 0) a.status[env] |= st;
+    }
+    __syncwarp();
+    if (live) {
+        vec_t* gs = reinterpret_cast<vec_t*>(reinterpret_cast<T*>(a.state) + (size_t)env * a.stride);
+        const vec_t* ss = reinterpret_cast<const vec_t*>(sState);
+        for (int i = lane; i < a.stride / VN; i += LPE) gs[i] = ss[i];
+        if (lane == 0) {
+            double* f = a.frame + (size_t)env * TGB_NFR;
+            f[FR_O] = Ox; f[FR_O + 1] = Oy; f[FR_O + 2] = Oz;
+            f[FR_V] = Vx; f[FR_V + 1] = Vy; f[FR_V + 2] = Vz;
+            f[FR_CTRLTIME] = ctrlTime;
+        }
+    }
+}
+
+/* Shared memory a launch of this kernel needs; mirrors the carve-up above. */
+inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
+    const int groupsPerBlock = threads / lpe;
+    const int modelTWords = (a.model_t_words + 3) & ~3;
+    int groupTWords = a.stride + 12 * lpe + 3 * a.C + a.cap_contacts * TGB_NCT * lpe;
+    groupTWords = (groupTWords + 3) & ~3;
+    if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
+    const int groupDWords = a.ctrl_stride + 8;
+    size_t bytes = (size_t)(modelTWords + groupsPerBlock * groupTWords) * sizeofT;
+    bytes = (bytes + 7) & ~(size_t)7;
+    bytes += (size_t)groupsPerBlock * groupDWords * sizeof(double);
+    bytes += (size_t)a.model_i_words * sizeof(int);
+    return bytes + 16;
+}
+
+} // namespace tgb

@@ -1,0 +1,147 @@
+/*
+ * tgb_host_capi.cpp -- C entry points over the C++ host API, so that Python (ctypes) tests and bench.py can
+ * build the shipped example models through tgStructure / tgBuildSpec / tgStructureInfo and read the flattened
+ * descriptors, or drive a whole tgSimulation on the device.  World settings per example follow the reference
+ * apps: AppPrismModel.cpp:46-80, AppSUPERball.cpp:45-91, AppEscape.cpp:61-151, MotorTimestep_test.cpp:81-215.
+ */
+#include "tgb_examples.h"
+
+#include <cstring>
+#include <string>
+
+namespace {
+thread_local std::string g_error;
+
+struct Example {
+    tgWorld* world;
+    tgSimView* view;
+    tgSimulation* sim;
+    tgModel* model; /* owned by sim */
+    double dt;
+    Example() : world(0), view(0), sim(0), model(0), dt(0.001) {}
+    ~Example() {
+        delete sim;
+        delete view;
+        delete world;
+    }
+};
+
+Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) {
+    Example* e = new Example();
+    try {
+        if (name == "3_prism" || name == "3_prism_noground") {
+            tgGround* ground = name == "3_prism" ? static_cast<tgGround*>(new tgBoxGround(tgBoxGround::Config(btVector3(0.0, 0.0, 0.0))))
+                                                 : static_cast<tgGround*>(new tgEmptyGround());
+            e->world = new tgWorld(tgWorld::Config(981), ground);
+            e->dt = 0.001;
+            e->model = new PrismModel();
+        } else if (name == "SUPERball" || name == "SUPERball_flat") {
+            const double pitch = name == "SUPERball" ? M_PI / 15.0 : 0.0;
+            e->world = new tgWorld(tgWorld::Config(98.1), new tgBoxGround(tgBoxGround::Config(btVector3(0.0, pitch, 0.0))));
+            e->dt = 0.001;
+            e->model = new T6Model();
+        } else if (name == "Escape" || name == "Escape_c3") {
+            /* AppEscape: box ground half extents (10000, 2, 10000), dt = 1/600. "_c3" = BASELINE config 3:
+               default box ground, dt = 1e-3. */
+            tgBoxGround::Config gc = name == "Escape"
+                                         ? tgBoxGround::Config(btVector3(0, 0, 0), 0.5, 0.0, btVector3(10000.0, 2, 10000.0), btVector3(0, 0, 0))
+                                         : tgBoxGround::Config();
+            e->world = new tgWorld(tgWorld::Config(98.1), new tgBoxGround(gc));
+            e->dt = name == "Escape" ? 1.0 / 60.0 / 10.0 : 0.001;
+            e->model = new EscapeModel();
+        } else if (name == "tsTestRig_basic" || name == "tsTestRig_kinematic") {
+            e->world = new tgWorld(tgWorld::Config(981)); /* MotorTimestep_test: default ground */
+            e->dt = 0.001;
+            e->model = new tsTestRig(name == "tsTestRig_kinematic");
+        } else {
+            g_error = "unknown example: " + name;
+            delete e;
+            return 0;
+        }
+        e->world->setBatch(n_env, (tgb_precision)precision, 0);
+        e->view = new tgSimView(*e->world, e->dt, 1.0 / 60.0 < e->dt ? e->dt : 1.0 / 60.0);
+        e->sim = new tgSimulation(*e->view);
+        e->sim->addModel(e->model);
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        delete e;
+        return 0;
+    }
+    return e;
+}
+} // namespace
+
+extern "C" {
+
+typedef struct tgh_model tgh_model;
+
+const char* tgh_last_error(void) { return g_error.c_str(); }
+
+tgh_model* tgh_build_example(const char* name) { return reinterpret_cast<tgh_model*>(build(name ? name : "")); }
+
+void tgh_free(tgh_model* m) { delete reinterpret_cast<Example*>(m); }
+
+int tgh_counts(const tgh_model* m, int* n_bodies, int* n_shapes, int* n_cables) {
+    const Example* e = reinterpret_cast<const Example*>(m);
+    if (!e) return 1;
+    const tgWorldB200Impl& w = e->world->b200();
+    *n_bodies = (int)w.bodies().size();
+    *n_shapes = (int)w.shapes().size();
+    *n_cables = (int)w.cables().size();
+    return 0;
+}
+
+int tgh_copy(const tgh_model* m, tgb_body_desc* bodies, tgb_shape_desc* shapes, tgb_cable_desc* cables, tgb_ground_desc* ground, double* gravity,
+             double* dt) {
+    const Example* e = reinterpret_cast<const Example*>(m);
+    if (!e) return 1;
+    const tgWorldB200Impl& w = e->world->b200();
+    if (bodies && !w.bodies().empty()) std::memcpy(bodies, w.bodies().data(), w.bodies().size() * sizeof(tgb_body_desc));
+    if (shapes && !w.shapes().empty()) std::memcpy(shapes, w.shapes().data(), w.shapes().size() * sizeof(tgb_shape_desc));
+    if (cables && !w.cables().empty()) std::memcpy(cables, w.cables().data(), w.cables().size() * sizeof(tgb_cable_desc));
+    if (ground) *ground = w.ground();
+    if (gravity) *gravity = w.gravity();
+    if (dt) *dt = e->dt;
+    return 0;
+}
+
+/* The model tree as the reference would print it: number of tgRod and tgSpringCableActuator descendants. */
+int tgh_tree_counts(const tgh_model* m, int* n_rods, int* n_actuators) {
+    const Example* e = reinterpret_cast<const Example*>(m);
+    if (!e) return 1;
+    std::vector<tgModel*> all = e->model->getDescendants();
+    *n_rods = (int)tgCast::filter<tgModel, tgRod>(all).size();
+    *n_actuators = (int)tgCast::filter<tgModel, tgSpringCableActuator>(all).size();
+    return 0;
+}
+
+void tgh_escape_transform_actions(const double* actions01, double initial_length, double* out33) {
+    tgbEscapeTransformActions(actions01, initial_length, out33);
+}
+
+/* Drop-in demonstration: the example app's main loop on the device through the host API only
+   (tgSimulation::run -> tgWorldB200Impl -> C ABI). Outputs like tgb_get_rod_state / tgb_get_cable_obs. */
+int tgh_run_example(const char* name, int n_env, int precision, int steps, double* rod_state_out, double* cable_obs_out) {
+    Example* e = 0;
+    try {
+        e = build(name ? name : "", n_env, precision);
+        if (!e) return TGB_ERR_INVALID_ARGUMENT;
+        e->sim->run(steps);
+        tgWorldB200Impl& w = e->world->b200();
+        int st = TGB_OK;
+        if (rod_state_out) st = tgb_get_rod_state(w.handle(), 0, n_env, rod_state_out);
+        if (st == TGB_OK && cable_obs_out) st = tgb_get_cable_obs(w.handle(), 0, n_env, cable_obs_out);
+        delete e;
+        return st;
+    } catch (const std::invalid_argument& ex) {
+        g_error = ex.what();
+        delete e;
+        return TGB_ERR_INVALID_ARGUMENT;
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        delete e;
+        return TGB_ERR_RUNTIME;
+    }
+}
+
+} // extern "C"

@@ -1,0 +1,177 @@
+"""BatchedWorld: numpy-facing wrapper of one tgb_world (N environments of one flattened NTRTsim model).
+Every method is a single C-ABI call; all arithmetic happens in the CUDA library."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class FlatModel(object):
+    """The flattened descriptors of one model: what tgStructureInfo::buildInto hands to the world
+    (reference: src/tgcreator/tgStructureInfo.cpp:277-289) plus the world settings of its app."""
+
+    def __init__(self, bodies, shapes, cables, ground, gravity, dt, name=""):
+        self.bodies, self.shapes, self.cables = bodies, shapes, cables
+        self.ground, self.gravity, self.dt, self.name = ground, gravity, dt, name
+
+    @property
+    def n_bodies(self):
+        return len(self.bodies)
+
+    @property
+    def n_cables(self):
+        return len(self.cables)
+
+    def initial_rod_state(self):
+        s = np.zeros((self.n_bodies, capi.ROD_STATE_DOUBLES))
+        for i, b in enumerate(self.bodies):
+            s[i, 0:3] = list(b.pos)
+            s[i, 3:7] = list(b.quat)
+        return s
+
+    def initial_cable_state(self):
+        return np.array([[c.rest_length, c.prev_length] for c in self.cables], dtype=np.float64).reshape(self.n_cables, 2)
+
+
+class BatchedWorld(object):
+    def __init__(self, model, n_env, precision="f32", device=0, solver_iterations=0, lanes_per_env=0, block_threads=0):
+        self._lib = capi.load()
+        self.model = model
+        self.n_env = int(n_env)
+        self.precision = precision
+        cfg = capi.WorldCfg(model.gravity, self.n_env, capi.TGB_F64 if precision == "f64" else capi.TGB_F32, device, solver_iterations)
+        h = C.c_void_p()
+        capi.check(self._lib.tgb_create(C.byref(cfg), C.byref(model.ground), C.byref(h)))
+        self._h = h
+        try:
+            capi.check(self._lib.tgb_add_model_flat(h, model.bodies, len(model.bodies), model.shapes, len(model.shapes),
+                                                    model.cables, len(model.cables)))
+            if lanes_per_env:
+                capi.check(self._lib.tgb_set_lanes_per_env(h, lanes_per_env))
+            if block_threads:
+                capi.check(self._lib.tgb_set_block_threads(h, block_threads))
+            capi.check(self._lib.tgb_finalize(h))
+        except Exception:
+            self.close()
+            raise
+        self.R, self.C = model.n_bodies, model.n_cables
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.tgb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state -------------------------------------------------------------------------------------------
+    def set_rod_state(self, state, env_begin=0):
+        state = np.ascontiguousarray(state, dtype=np.float64).reshape(-1, self.R, capi.ROD_STATE_DOUBLES)
+        capi.check(self._lib.tgb_set_rod_state(self._h, env_begin, state.shape[0], _ptr(state)))
+
+    def get_rod_state(self, env_begin=0, env_count=None):
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.empty((n, self.R, capi.ROD_STATE_DOUBLES))
+        capi.check(self._lib.tgb_get_rod_state(self._h, env_begin, n, _ptr(out)))
+        return out
+
+    def set_cable_state(self, rest_prev, env_begin=0):
+        rest_prev = np.ascontiguousarray(rest_prev, dtype=np.float64).reshape(-1, self.C, 2)
+        capi.check(self._lib.tgb_set_cable_state(self._h, env_begin, rest_prev.shape[0], _ptr(rest_prev)))
+
+    def get_cable_obs(self, env_begin=0, env_count=None):
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.empty((n, self.C, capi.CABLE_OBS_DOUBLES))
+        capi.check(self._lib.tgb_get_cable_obs(self._h, env_begin, n, _ptr(out)))
+        return out
+
+    # ---- control -----------------------------------------------------------------------------------------
+    def set_controller(self, kind, params=None, env_begin=0, env_count=None, broadcast=False):
+        n = self.n_env - env_begin if env_count is None else env_count
+        if params is None:
+            capi.check(self._lib.tgb_set_controller(self._h, kind, None, 0, env_begin, n, 0))
+            return
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        per_env = params.shape[-1]
+        capi.check(self._lib.tgb_set_controller(self._h, kind, _ptr(params), per_env, env_begin, n, 1 if broadcast else 0))
+
+    def set_control_input(self, inputs, dt, env_begin=0, env_count=None):
+        n = self.n_env - env_begin if env_count is None else env_count
+        inputs = np.ascontiguousarray(inputs, dtype=np.float64)
+        broadcast = 1 if inputs.ndim == 1 else 0
+        capi.check(self._lib.tgb_set_control_input(self._h, env_begin, n, _ptr(inputs), broadcast, dt))
+
+    # ---- stepping ----------------------------------------------------------------------------------------
+    def step(self, dt, n_steps=1):
+        capi.check(self._lib.tgb_step(self._h, dt, n_steps))
+
+    def sync(self):
+        capi.check(self._lib.tgb_sync(self._h))
+
+    def step_timed(self, dt, n_steps, reps):
+        ms = (C.c_float * reps)()
+        capi.check(self._lib.tgb_step_timed(self._h, dt, n_steps, reps, ms))
+        return [float(x) for x in ms]
+
+    def rollout_host(self, rod_in, cable_in, dt, n_steps, rod_out=None, cable_out=None):
+        """Host buffers in, host buffers out (the reference-facing end-to-end call)."""
+        if rod_out is None:
+            rod_out = np.empty((self.n_env, self.R, capi.ROD_STATE_DOUBLES))
+        if cable_out is None:
+            cable_out = np.empty((self.n_env, self.C, capi.CABLE_OBS_DOUBLES))
+        capi.check(self._lib.tgb_rollout_host(self._h, _ptr(rod_in) if rod_in is not None else None,
+                                              _ptr(cable_in) if cable_in is not None else None, dt, n_steps,
+                                              _ptr(rod_out), _ptr(cable_out)))
+        return rod_out, cable_out
+
+    # ---- bookkeeping ---------------------------------------------------------------------------------------
+    def time(self):
+        t = C.c_double()
+        capi.check(self._lib.tgb_get_time(self._h, C.byref(t)))
+        return t.value
+
+    def status(self, env_begin=0, env_count=None):
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.empty(n, dtype=np.int32)
+        capi.check(self._lib.tgb_get_status(self._h, env_begin, n, _ptr(out)))
+        return out
+
+    def set_height_window(self, lo, hi):
+        capi.check(self._lib.tgb_set_height_window(self._h, lo, hi))
+
+    def mark_episode_start(self):
+        capi.check(self._lib.tgb_mark_episode_start(self._h))
+
+    def scores(self, env_begin=0, env_count=None):
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.empty((n, 2))
+        capi.check(self._lib.tgb_get_scores(self._h, env_begin, n, _ptr(out)))
+        return out
+
+    def scores_device_ptr(self):
+        p, nbytes = C.c_void_p(), C.c_size_t()
+        capi.check(self._lib.tgb_scores_device_ptr(self._h, C.byref(p), C.byref(nbytes)))
+        return p.value, nbytes.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        capi.check(self._lib.tgb_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def launch_geometry(self):
+        a, b, g = C.c_int32(), C.c_int32(), C.c_int32()
+        capi.check(self._lib.tgb_launch_geometry(self._h, C.byref(a), C.byref(b), C.byref(g)))
+        return a.value, b.value, g.value
+
+    def state_bytes_per_env(self):
+        n = C.c_size_t()
+        capi.check(self._lib.tgb_state_bytes_per_env(self._h, C.byref(n)))
+        return n.value

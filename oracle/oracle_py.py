@@ -1,0 +1,136 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so). TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs import this."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.path.join(_HERE, "liboracle.so")
+    if not os.path.exists(path):
+        raise OSError("%s missing: run `make oracle/liboracle.so`" % path)
+    lib = C.CDLL(path)
+    vp, dbl, i = C.c_void_p, C.c_double, C.c_int
+    lib.tgo_create.restype = vp
+    lib.tgo_create.argtypes = [vp, vp]
+    lib.tgo_destroy.argtypes = [vp]
+    lib.tgo_add_model_flat.argtypes = [vp, vp, i, vp, i, vp, i]
+    lib.tgo_num_bodies.argtypes = [vp]
+    lib.tgo_num_cables.argtypes = [vp]
+    lib.tgo_set_rod_state.argtypes = [vp, vp]
+    lib.tgo_get_rod_state.argtypes = [vp, vp]
+    lib.tgo_set_cable_state.argtypes = [vp, vp]
+    lib.tgo_get_cable_obs.argtypes = [vp, vp]
+    lib.tgo_set_controller.argtypes = [vp, i, vp, i]
+    lib.tgo_set_control_input.argtypes = [vp, vp, dbl]
+    lib.tgo_step.argtypes = [vp, dbl, i]
+    lib.tgo_world_step.argtypes = [vp, dbl]
+    lib.tgo_models_step.argtypes = [vp, dbl]
+    lib.tgo_get_time.restype = dbl
+    lib.tgo_get_time.argtypes = [vp]
+    lib.tgo_mark_episode_start.argtypes = [vp]
+    lib.tgo_get_scores.argtypes = [vp, vp]
+    lib.tgo_num_contacts.argtypes = [vp]
+    lib.tgo_rollout_batch.argtypes = [vp, vp, vp, i, vp, i, vp, i, i, vp, i, vp, dbl, i, vp, vp, dbl, i, i, vp, vp]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleWorld(object):
+    """One environment stepped by the CPU oracle."""
+
+    def __init__(self, model, cfg_cls, solver_iterations=0):
+        self._lib = load()
+        self.model = model
+        cfg = cfg_cls(model.gravity, 1, 1, 0, solver_iterations)
+        self._h = C.c_void_p(self._lib.tgo_create(C.byref(cfg), C.byref(model.ground)))
+        self._lib.tgo_add_model_flat(self._h, model.bodies, len(model.bodies), model.shapes, len(model.shapes), model.cables,
+                                     len(model.cables))
+        self.R, self.C = len(model.bodies), len(model.cables)
+
+    def close(self):
+        if self._h:
+            self._lib.tgo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_rod_state(self, s):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        self._lib.tgo_set_rod_state(self._h, _p(s))
+
+    def get_rod_state(self):
+        out = np.empty((self.R, 13))
+        self._lib.tgo_get_rod_state(self._h, _p(out))
+        return out
+
+    def set_cable_state(self, rp):
+        rp = np.ascontiguousarray(rp, dtype=np.float64)
+        self._lib.tgo_set_cable_state(self._h, _p(rp))
+
+    def get_cable_obs(self):
+        out = np.empty((self.C, 4))
+        self._lib.tgo_get_cable_obs(self._h, _p(out))
+        return out
+
+    def set_controller(self, kind, params):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self._lib.tgo_set_controller(self._h, kind, _p(params), params.size)
+
+    def set_control_input(self, inputs, dt):
+        inputs = np.ascontiguousarray(inputs, dtype=np.float64)
+        return self._lib.tgo_set_control_input(self._h, _p(inputs), dt)
+
+    def step(self, dt, n=1):
+        return self._lib.tgo_step(self._h, dt, n)
+
+    def num_contacts(self):
+        return self._lib.tgo_num_contacts(self._h)
+
+    def scores(self):
+        out = np.empty(2)
+        self._lib.tgo_get_scores(self._h, _p(out))
+        return out
+
+    def mark_episode_start(self):
+        self._lib.tgo_mark_episode_start(self._h)
+
+    def time(self):
+        return self._lib.tgo_get_time(self._h)
+
+
+def rollout_batch(model, cfg_cls, rod_in, cable_in, dt, n_steps, ctrl_kind=0, ctrl_params=None, setup_input=None, setup_dt=0.0,
+                  n_threads=1, solver_iterations=0):
+    """n_env independent oracle environments from their own states; returns (rod_state, cable_obs)."""
+    lib = load()
+    rod_in = None if rod_in is None else np.ascontiguousarray(rod_in, dtype=np.float64)
+    cable_in = None if cable_in is None else np.ascontiguousarray(cable_in, dtype=np.float64)
+    R, Cn = len(model.bodies), len(model.cables)
+    n_env = rod_in.shape[0] if rod_in is not None else (cable_in.shape[0] if cable_in is not None else 1)
+    per_env = 0
+    if ctrl_params is not None:
+        ctrl_params = np.ascontiguousarray(ctrl_params, dtype=np.float64).reshape(n_env, -1)
+        per_env = ctrl_params.shape[1]
+    if setup_input is not None:
+        setup_input = np.ascontiguousarray(setup_input, dtype=np.float64)
+    cfg = cfg_cls(model.gravity, 1, 1, 0, solver_iterations)
+    rod_out = np.empty((n_env, R, 13))
+    cab_out = np.empty((n_env, Cn, 4))
+    rc = lib.tgo_rollout_batch(C.byref(cfg), C.byref(model.ground), model.bodies, R, model.shapes, len(model.shapes), model.cables, Cn,
+                               ctrl_kind, _p(ctrl_params), per_env, _p(setup_input), setup_dt, n_env, _p(rod_in), _p(cable_in), dt,
+                               n_steps, n_threads, _p(rod_out), _p(cab_out))
+    if rc != 0:
+        raise ValueError("oracle rollout failed: %d" % rc)
+    return rod_out, cab_out

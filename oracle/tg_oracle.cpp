@@ -1,0 +1,736 @@
+/*
+ * tg_oracle.cpp -- CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT). See tg_oracle.h for the
+ * reference lines each function follows and for the parity status of each piece.
+ *
+ * Everything is double precision and sequential, in the reference's own evaluation order
+ * (bodies in creation order, cables in addPair order, applyImpulse one cable at a time).
+ */
+#include "tg_oracle.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct V3 {
+    double x, y, z;
+    V3() : x(0), y(0), z(0) {}
+    V3(double a, double b, double c) : x(a), y(b), z(c) {}
+    V3 operator+(const V3& o) const { return V3(x + o.x, y + o.y, z + o.z); }
+    V3 operator-(const V3& o) const { return V3(x - o.x, y - o.y, z - o.z); }
+    V3 operator-() const { return V3(-x, -y, -z); }
+    V3 operator*(double s) const { return V3(x * s, y * s, z * s); }
+    V3 operator/(double s) const { double i = 1.0 / s; return V3(x * i, y * i, z * i); } /* btVector3::operator/ multiplies by 1/s */
+    V3& operator+=(const V3& o) { x += o.x; y += o.y; z += o.z; return *this; }
+    V3& operator-=(const V3& o) { x -= o.x; y -= o.y; z -= o.z; return *this; }
+    V3& operator*=(double s) { x *= s; y *= s; z *= s; return *this; }
+    double dot(const V3& o) const { return x * o.x + y * o.y + z * o.z; }
+    V3 cross(const V3& o) const { return V3(y * o.z - z * o.y, z * o.x - x * o.z, x * o.y - y * o.x); }
+    double length2() const { return dot(*this); }
+    double length() const { return std::sqrt(length2()); }
+};
+
+struct Q4 {
+    double x, y, z, w;
+    Q4() : x(0), y(0), z(0), w(1) {}
+    Q4(double a, double b, double c, double d) : x(a), y(b), z(c), w(d) {}
+};
+
+/* btQuaternion operator*(q1, q2) */
+static Q4 qmul(const Q4& a, const Q4& b) {
+    return Q4(a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+              a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+              a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x,
+              a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z);
+}
+
+struct M3 {
+    double m[3][3];
+    V3 row(int i) const { return V3(m[i][0], m[i][1], m[i][2]); }
+    V3 col(int j) const { return V3(m[0][j], m[1][j], m[2][j]); }
+    V3 operator*(const V3& v) const { return V3(row(0).dot(v), row(1).dot(v), row(2).dot(v)); }
+    M3 operator*(const M3& o) const {
+        M3 r;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) r.m[i][j] = m[i][0] * o.m[0][j] + m[i][1] * o.m[1][j] + m[i][2] * o.m[2][j];
+        return r;
+    }
+    M3 transpose() const {
+        M3 r;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) r.m[i][j] = m[j][i];
+        return r;
+    }
+    /* btMatrix3x3::scaled: column j multiplied by s[j] */
+    M3 scaled(const V3& s) const {
+        M3 r;
+        for (int i = 0; i < 3; ++i) { r.m[i][0] = m[i][0] * s.x; r.m[i][1] = m[i][1] * s.y; r.m[i][2] = m[i][2] * s.z; }
+        return r;
+    }
+    /* btMatrix3x3::setRotation */
+    static M3 fromQuat(const Q4& q) {
+        double d = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+        double s = 2.0 / d;
+        double xs = q.x * s, ys = q.y * s, zs = q.z * s;
+        double wx = q.w * xs, wy = q.w * ys, wz = q.w * zs;
+        double xx = q.x * xs, xy = q.x * ys, xz = q.x * zs;
+        double yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
+        M3 r;
+        r.m[0][0] = 1.0 - (yy + zz); r.m[0][1] = xy - wz;         r.m[0][2] = xz + wy;
+        r.m[1][0] = xy + wz;         r.m[1][1] = 1.0 - (xx + zz); r.m[1][2] = yz - wx;
+        r.m[2][0] = xz - wy;         r.m[2][1] = yz + wx;         r.m[2][2] = 1.0 - (xx + yy);
+        return r;
+    }
+    /* btMatrix3x3::getRotation */
+    Q4 toQuat() const {
+        double trace = m[0][0] + m[1][1] + m[2][2];
+        double t[4];
+        if (trace > 0.0) {
+            double s = std::sqrt(trace + 1.0);
+            t[3] = s * 0.5;
+            s = 0.5 / s;
+            t[0] = (m[2][1] - m[1][2]) * s;
+            t[1] = (m[0][2] - m[2][0]) * s;
+            t[2] = (m[1][0] - m[0][1]) * s;
+        } else {
+            int i = m[0][0] < m[1][1] ? (m[1][1] < m[2][2] ? 2 : 1) : (m[0][0] < m[2][2] ? 2 : 0);
+            int j = (i + 1) % 3, k = (i + 2) % 3;
+            double s = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0);
+            t[i] = s * 0.5;
+            s = 0.5 / s;
+            t[3] = (m[k][j] - m[j][k]) * s;
+            t[j] = (m[j][i] + m[i][j]) * s;
+            t[k] = (m[k][i] + m[i][k]) * s;
+        }
+        return Q4(t[0], t[1], t[2], t[3]);
+    }
+};
+
+/* v * M (row vector times matrix), btVector3 operator*(v, m) */
+static V3 vecMat(const V3& v, const M3& m) { return V3(m.col(0).dot(v), m.col(1).dot(v), m.col(2).dot(v)); }
+
+struct Shape {
+    double radius, halfLen, margin;
+    V3 pos;
+    M3 rot;
+};
+
+struct Body {
+    double mass, invMass;
+    V3 invInertiaLocal;
+    V3 pos;
+    M3 basis;
+    V3 linvel, angvel;
+    M3 invInertiaWorld;
+    V3 gravityForce; /* btRigidBody::m_gravity = acceleration * mass */
+    V3 totalForce, totalTorque;
+    double friction, rollingFriction, restitution;
+    int shapeBegin, shapeCount;
+    bool gyro;
+    void updateInertiaTensor() { invInertiaWorld = basis.scaled(invInertiaLocal) * basis.transpose(); }
+};
+
+struct Cable {
+    int a, b;
+    V3 la, lb;
+    double k, c;
+    double rest, prev;
+    double velocity, damping;
+    int actuator;
+    bool backdrivable;
+    double maxTens, tVel, minAL, minRL;
+    double mRadius, mFriction, mInertia;
+    /* tgBasicActuator */
+    double preferred;
+    /* tgKinematicActuator */
+    double motorVel, desiredTorque;
+};
+
+struct Contact {
+    int body;
+    V3 n;        /* ground -> rod */
+    V3 r;        /* contact point on the rod relative to its centre of mass */
+    double dist;
+    /* normal row */
+    V3 rxn, angN;
+    double invDiagN, rhsN, rhsPen, lamN, lamPush;
+    /* friction row */
+    V3 t, rxt, angT;
+    double invDiagT, rhsT, lamT, mu;
+};
+
+/* Bullet 2.82 btContactSolverInfo defaults (tgWorldBulletPhysicsImpl.cpp:134-146 leaves them alone). */
+const double kErp = 0.2, kErp2 = 0.8, kSplitThreshold = -0.04, kTurnErp = 0.1, kMaxGyro = 100.0;
+const double kBreakingThreshold = 0.02;            /* gContactBreakingThreshold */
+const double kAngularMotionThreshold = 0.5 * 1.57079632679489661923; /* 0.5*SIMD_HALF_PI */
+
+/* btTransformUtil::integrateTransform */
+static void integrateTransform(const V3& pos, const M3& basis, const V3& linvel, const V3& angvel, double dt,
+                               V3& posOut, M3& basisOut) {
+    posOut = pos + linvel * dt;
+    V3 axis;
+    double fAngle = angvel.length();
+    if (fAngle * dt > kAngularMotionThreshold) fAngle = kAngularMotionThreshold / dt;
+    if (fAngle < 0.001) {
+        axis = angvel * (0.5 * dt - (dt * dt * dt) * 0.020833333333 * fAngle * fAngle);
+    } else {
+        axis = angvel * (std::sin(0.5 * fAngle * dt) / fAngle);
+    }
+    Q4 dorn(axis.x, axis.y, axis.z, std::cos(fAngle * dt * 0.5));
+    Q4 orn0 = basis.toQuat();
+    Q4 p = qmul(dorn, orn0);
+    double l = std::sqrt(p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w);
+    p.x /= l; p.y /= l; p.z /= l; p.w /= l;
+    basisOut = M3::fromQuat(p);
+}
+
+/* btPlaneSpace1, first vector only */
+static V3 planeSpace1(const V3& n) {
+    if (std::fabs(n.z) > 0.7071067811865475244008443621048490) {
+        double a = n.y * n.y + n.z * n.z;
+        double k = 1.0 / std::sqrt(a);
+        return V3(0, -n.z * k, n.y * k);
+    }
+    double a = n.x * n.x + n.y * n.y;
+    double k = 1.0 / std::sqrt(a);
+    return V3(-n.y * k, n.x * k, 0);
+}
+
+} // namespace
+
+struct tgo_world {
+    tgb_world_cfg cfg;
+    tgb_ground_desc ground;
+    std::vector<Body> bodies;
+    std::vector<Shape> shapes;
+    std::vector<Cable> cables;
+    std::vector<Contact> contacts;
+    int ctrlKind = TGB_CTRL_NONE;
+    std::vector<double> ctrlParams;
+    double time = 0.0;     /* tgSimView-style accumulated time */
+    double ctrlTime = 0.0; /* EscapeController::m_totalTime */
+    V3 episodeStartCom;
+    int iterations = 10;
+
+    /* ---- cables ---------------------------------------------------------------------------- */
+    V3 anchorWorld(const Body& b, const V3& local) const { return b.basis * local + b.pos; }
+
+    double cableLength(const Cable& c) const {
+        V3 d = anchorWorld(bodies[c.b], c.lb) - anchorWorld(bodies[c.a], c.la);
+        return d.length();
+    }
+    double cableTension(const Cable& c) const {
+        double t = (cableLength(c) - c.rest) * c.k;
+        return t < 0.0 ? 0.0 : t;
+    }
+
+    static void applyImpulse(Body& b, const V3& J, const V3& rel) {
+        if (b.invMass != 0.0) {
+            b.linvel += J * b.invMass;
+            b.angvel += b.invInertiaWorld * rel.cross(J);
+        }
+    }
+
+    /* tgBulletSpringCable::calculateAndApplyForce */
+    void cableForce(Cable& c, double dt) {
+        Body& A = bodies[c.a];
+        Body& B = bodies[c.b];
+        V3 p1 = anchorWorld(A, c.la), p2 = anchorWorld(B, c.lb);
+        V3 dist = p2 - p1;
+        double L = dist.length();
+        V3 unit = dist / L;
+        double stretch = L - c.rest;
+        double magnitude = c.k * stretch;
+        double deltaStretch = L - c.prev;
+        c.velocity = deltaStretch / dt;
+        c.damping = c.c * c.velocity;
+        if (std::fabs(magnitude) * 1.0 < std::fabs(c.damping))
+            c.damping = (c.damping > 0.0 ? magnitude * 1.0 : -magnitude * 1.0);
+        magnitude += c.damping;
+        V3 force(0, 0, 0);
+        if (L > c.rest) force = unit * magnitude;
+        c.prev = L;
+        applyImpulse(A, force * dt, p1 - A.pos);
+        applyImpulse(B, -force * dt, p2 - B.pos);
+    }
+
+    /* tgBasicActuator::moveMotors */
+    void moveMotors(Cable& c, double dt) {
+        double stepSize = c.tVel * dt;
+        double actual = cableLength(c);
+        if ((actual - c.preferred) * c.k > c.maxTens) c.preferred = actual - c.maxTens / c.k;
+        double diff = c.preferred - c.rest;
+        double fabsDiff = std::fabs(diff);
+        if ((actual > c.minAL) || (diff > 0)) {
+            if (std::fabs(diff) > stepSize) c.rest += (diff / fabsDiff) * stepSize;
+            else c.rest += diff;
+        }
+        c.rest = (c.rest > c.minRL) ? c.rest : c.minRL;
+    }
+    /* tgBasicActuator::setControlInput(input, dt) */
+    int setControlInput(Cable& c, double input, double dt) {
+        if (input < 0.0) return TGB_ERR_INVALID_ARGUMENT;
+        c.preferred = input;
+        moveMotors(c, dt);
+        return 0;
+    }
+    /* tgKinematicActuator::integrateRestLength + getAppliedTorque */
+    void integrateRestLength(Cable& c, double dt) {
+        double tension = cableTension(c);
+        double maxTorque = c.maxTens * c.mRadius * (1.0 - c.mRadius * std::fabs(c.motorVel) / c.tVel);
+        maxTorque = maxTorque < 0.0 ? 0.0 : maxTorque;
+        double applied = std::fabs(c.desiredTorque) < maxTorque ? c.desiredTorque
+                                                                 : c.desiredTorque / std::fabs(c.desiredTorque) * maxTorque;
+        double acc = (applied - c.mFriction * c.motorVel + tension * c.mRadius) / c.mInertia;
+        if (!c.backdrivable && acc * applied <= 0.0)
+            c.motorVel = c.motorVel + acc * dt > 0.0 ? 0.0 : c.motorVel + acc * dt;
+        else
+            c.motorVel += acc * dt;
+        c.rest += c.mRadius * c.motorVel * dt;
+        c.rest = (c.rest > c.minRL) ? c.rest : c.minRL;
+    }
+
+    /* ---- controllers (model-level observers, run before the children step) ------------------- */
+    void controllersStep(double dt) {
+        const int C = (int)cables.size();
+        switch (ctrlKind) {
+        case TGB_CTRL_SETPOINT: /* tsTestRig.cpp:187 */
+            for (int i = 0; i < C; ++i)
+                if (cables[i].actuator == TGB_ACT_BASIC) setControlInput(cables[i], ctrlParams[i], dt);
+            break;
+        case TGB_CTRL_TORQUE:   /* tsTestRig.cpp:183 */
+            for (int i = 0; i < C; ++i)
+                if (cables[i].actuator == TGB_ACT_KINEMATIC) cables[i].desiredTorque = ctrlParams[i];
+            break;
+        case TGB_CTRL_TENSION: { /* T6TensionController.cpp:69-83 -> tgTensionController.cpp:50-88 */
+            double setPoint = ctrlParams[0];
+            for (int i = 0; i < C; ++i) {
+                Cable& c = cables[i];
+                if (c.actuator != TGB_ACT_BASIC) continue;
+                double currentTension = cableTension(c);
+                double delta = setPoint - currentTension;
+                double diff = delta / c.k;
+                double newLength = c.rest - diff;
+                newLength = newLength < 0.0 ? 0.0 : newLength;
+                setControlInput(c, newLength, dt);
+            }
+            break;
+        }
+        case TGB_CTRL_ESCAPE_SINE: { /* EscapeController.cpp:100-117,245-291 */
+            ctrlTime += dt;
+            const double* P = ctrlParams.data(); /* [8][4] amplitude, angFreq, phaseChange, dcOffset ; [32] = L0 */
+            const double L0 = P[32];
+            double phase = 0.0;
+            int cluster = 0, oldCluster = 0;
+            const int nMuscles = C < 24 ? C : 24;
+            for (int i = 0; i < nMuscles; ++i) {
+                oldCluster = cluster;
+                if (i < 4) cluster = 0; else if (i < 8) cluster = 1; else if (i < 12) cluster = 2;
+                else if (i < 16) cluster = 3; else if (i < 18) cluster = 4; else if (i < 20) cluster = 5;
+                else if (i < 22) cluster = 6; else cluster = 7;
+                double newLength = P[cluster * 4 + 0] * std::sin(P[cluster * 4 + 1] * ctrlTime + phase) + P[cluster * 4 + 3];
+                double minLength = L0 * (1 - 0.50), maxLength = L0 * (1 + 0.50);
+                if (newLength <= minLength) newLength = minLength;
+                else if (newLength >= maxLength) newLength = maxLength;
+                setControlInput(cables[i], newLength, dt);
+                if (oldCluster != cluster) phase += P[cluster * 4 + 2];
+            }
+            for (int i = 0; i < C; ++i) moveMotors(cables[i], dt); /* EscapeController.cpp:108-116 */
+            break;
+        }
+        default: break;
+        }
+    }
+
+    /* tgModel::step over the children: each actuator's step in addPair order */
+    void modelsStep(double dt) {
+        controllersStep(dt);
+        for (size_t i = 0; i < cables.size(); ++i) {
+            Cable& c = cables[i];
+            if (c.actuator == TGB_ACT_KINEMATIC) {
+                integrateRestLength(c, dt);
+                cableForce(c, dt);
+                c.desiredTorque = 0.0; /* tgKinematicActuator.cpp:155-156 */
+            } else {
+                cableForce(c, dt);
+            }
+        }
+    }
+
+    /* ---- world step (Bullet restatement) ----------------------------------------------------- */
+
+    /* Analytic cylinder-vs-plane manifold: per cylinder end cap, four rim points of the margin-shrunk core
+       cylinder, starting at the rim point deepest along -n; a point is a contact when its distance (after both
+       margins) is within the contact breaking threshold; at most 4 per cylinder (btPersistentManifold cap). */
+    void generateContacts() {
+        contacts.clear();
+        if (ground.kind == TGB_GROUND_EMPTY) return;
+        const V3 n(ground.normal[0], ground.normal[1], ground.normal[2]);
+        for (size_t bi = 0; bi < bodies.size(); ++bi) {
+            Body& b = bodies[bi];
+            if (b.invMass == 0.0) continue;
+            for (int si = b.shapeBegin; si < b.shapeBegin + b.shapeCount; ++si) {
+                const Shape& s = shapes[si];
+                M3 R = b.basis * s.rot;
+                V3 c = b.basis * s.pos + b.pos;
+                V3 a = R.col(1);
+                double rc = s.radius - s.margin, hc = s.halfLen - s.margin;
+                double na = n.dot(a);
+                V3 perp = -(n - a * na);
+                double pl = perp.length();
+                V3 u;
+                if (pl > 1e-9) u = perp / pl;
+                else u = R.col(0);
+                V3 w = a.cross(u);
+                int count = 0;
+                for (int e = 0; e < 2 && count < 4; ++e) {
+                    V3 ce = c + a * (e == 0 ? -hc : hc);
+                    for (int k = 0; k < 4 && count < 4; ++k) {
+                        V3 dir = (k == 0) ? u : (k == 1) ? w : (k == 2) ? -u : -w;
+                        V3 pc = ce + dir * rc;
+                        double dist = n.dot(pc) - ground.offset - s.margin;
+                        if (dist <= kBreakingThreshold) {
+                            Contact ct;
+                            ct.body = (int)bi;
+                            ct.n = n;
+                            ct.r = (pc - n * s.margin) - b.pos;
+                            ct.dist = dist;
+                            double mu = b.friction * ground.friction;
+                            if (mu < -10.0) mu = -10.0;
+                            if (mu > 10.0) mu = 10.0;
+                            ct.mu = mu;
+                            contacts.push_back(ct);
+                            ++count;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    void worldStep(double dt) {
+        /* applyGravity */
+        for (Body& b : bodies)
+            if (b.invMass != 0.0) b.totalForce += b.gravityForce;
+
+        /* performDiscreteCollisionDetection on the current transforms */
+        generateContacts();
+
+        /* solver bodies: external impulses (btSequentialImpulseConstraintSolver::initSolverBody + gyro) */
+        const size_t nb = bodies.size();
+        std::vector<V3> extLin(nb), extAng(nb), dLin(nb), dAng(nb), push(nb), turn(nb);
+        for (size_t i = 0; i < nb; ++i) {
+            Body& b = bodies[i];
+            if (b.invMass == 0.0) continue;
+            extLin[i] = b.totalForce * b.invMass * dt;
+            extAng[i] = vecMat(b.totalTorque, b.invInertiaWorld) * dt;
+            if (b.gyro) {
+                V3 inertiaLocal(b.invInertiaLocal.x != 0 ? 1.0 / b.invInertiaLocal.x : 0,
+                                b.invInertiaLocal.y != 0 ? 1.0 / b.invInertiaLocal.y : 0,
+                                b.invInertiaLocal.z != 0 ? 1.0 / b.invInertiaLocal.z : 0);
+                M3 Iw = b.basis.scaled(inertiaLocal) * b.basis.transpose();
+                V3 tmp = Iw * b.angvel;
+                V3 gf = b.angvel.cross(tmp);
+                double l2 = gf.length2();
+                if (l2 > kMaxGyro * kMaxGyro) gf *= 1.0 / std::sqrt(l2) * kMaxGyro;
+                extAng[i] -= vecMat(gf, b.invInertiaWorld) * dt;
+            }
+        }
+
+        /* contact rows (setupContactConstraint / setupFrictionConstraint, one friction direction) */
+        for (Contact& c : contacts) {
+            Body& b = bodies[c.body];
+            const int i = c.body;
+            c.rxn = c.r.cross(c.n);
+            c.angN = b.invInertiaWorld * c.rxn;
+            double denom = b.invMass + c.n.dot(c.angN.cross(c.r));
+            c.invDiagN = 1.0 / denom;
+            V3 vel = b.linvel + b.angvel.cross(c.r);
+            double relVel = c.n.dot(vel);
+            double combinedRestitution = b.restitution * ground.restitution;
+            double restitution = combinedRestitution * -relVel;
+            if (restitution <= 0.0) restitution = 0.0;
+            /* friction direction from the lateral velocity, else btPlaneSpace1 */
+            V3 lat = vel - c.n * relVel;
+            double lat2 = lat.length2();
+            if (lat2 > DBL_EPSILON) c.t = lat * (1.0 / std::sqrt(lat2));
+            else c.t = planeSpace1(c.n);
+            c.lamN = 0.0; c.lamPush = 0.0; c.lamT = 0.0; /* no persistent manifold => no warm start */
+            double velDotN = c.n.dot(b.linvel + extLin[i]) + c.rxn.dot(b.angvel + extAng[i]);
+            double velocityError = restitution - velDotN;
+            double penetration = c.dist;
+            double erp = kErp2;
+            if (penetration > kSplitThreshold) erp = kErp;
+            double positionalError = 0.0;
+            if (penetration > 0) velocityError -= penetration / dt;
+            else positionalError = -penetration * erp / dt;
+            double penetrationImpulse = positionalError * c.invDiagN;
+            double velocityImpulse = velocityError * c.invDiagN;
+            if (penetration > kSplitThreshold) { c.rhsN = penetrationImpulse + velocityImpulse; c.rhsPen = 0.0; }
+            else { c.rhsN = velocityImpulse; c.rhsPen = penetrationImpulse; }
+            /* friction row */
+            c.rxt = c.r.cross(c.t);
+            c.angT = b.invInertiaWorld * c.rxt;
+            double denomT = b.invMass + c.t.dot(c.angT.cross(c.r));
+            c.invDiagT = 1.0 / denomT;
+            double relT = c.t.dot(b.linvel + extLin[i]) + c.rxt.dot(b.angvel);
+            c.rhsT = (0.0 - relT) * c.invDiagT;
+        }
+
+        /* split-impulse iterations, then velocity iterations (fixed-iteration PGS in place of Dantzig) */
+        for (int it = 0; it < iterations; ++it) {
+            for (Contact& c : contacts) {
+                if (c.rhsPen == 0.0) continue;
+                Body& b = bodies[c.body];
+                const int i = c.body;
+                double delta = c.rhsPen;
+                double dv = c.n.dot(push[i]) + c.rxn.dot(turn[i]);
+                delta -= dv * c.invDiagN;
+                double sum = c.lamPush + delta;
+                if (sum < 0.0) { delta = -c.lamPush; c.lamPush = 0.0; }
+                else c.lamPush = sum;
+                push[i] += c.n * (b.invMass * delta);
+                turn[i] += c.angN * delta;
+            }
+        }
+        for (int it = 0; it < iterations; ++it) {
+            for (Contact& c : contacts) {
+                Body& b = bodies[c.body];
+                const int i = c.body;
+                double delta = c.rhsN;
+                double dv = c.n.dot(dLin[i]) + c.rxn.dot(dAng[i]);
+                delta -= dv * c.invDiagN;
+                double sum = c.lamN + delta;
+                if (sum < 0.0) { delta = -c.lamN; c.lamN = 0.0; }
+                else c.lamN = sum;
+                dLin[i] += c.n * (b.invMass * delta);
+                dAng[i] += c.angN * delta;
+            }
+            for (Contact& c : contacts) {
+                if (!(c.lamN > 0.0)) continue;
+                Body& b = bodies[c.body];
+                const int i = c.body;
+                double lo = -c.mu * c.lamN, hi = c.mu * c.lamN;
+                double delta = c.rhsT;
+                double dv = c.t.dot(dLin[i]) + c.rxt.dot(dAng[i]);
+                delta -= dv * c.invDiagT;
+                double sum = c.lamT + delta;
+                if (sum < lo) { delta = lo - c.lamT; c.lamT = lo; }
+                else if (sum > hi) { delta = hi - c.lamT; c.lamT = hi; }
+                else c.lamT = sum;
+                dLin[i] += c.t * (b.invMass * delta);
+                dAng[i] += c.angT * delta;
+            }
+        }
+
+        /* write back + split-impulse transform correction */
+        for (size_t i = 0; i < nb; ++i) {
+            Body& b = bodies[i];
+            if (b.invMass == 0.0) continue;
+            b.linvel = (b.linvel + dLin[i]) + extLin[i];
+            b.angvel = (b.angvel + dAng[i]) + extAng[i];
+            const V3& p = push[i];
+            const V3& t = turn[i];
+            if (p.x != 0 || p.y != 0 || p.z != 0 || t.x != 0 || t.y != 0 || t.z != 0) {
+                V3 np; M3 nb2;
+                integrateTransform(b.pos, b.basis, p, t * kTurnErp, dt, np, nb2);
+                b.pos = np; b.basis = nb2;
+            }
+        }
+
+        /* integrateTransforms: predictIntegratedTransform + proceedToTransform */
+        for (Body& b : bodies) {
+            if (b.invMass == 0.0) continue;
+            V3 np; M3 nb2;
+            integrateTransform(b.pos, b.basis, b.linvel, b.angvel, dt, np, nb2);
+            b.pos = np; b.basis = nb2;
+            b.updateInertiaTensor();
+        }
+        /* clearForces */
+        for (Body& b : bodies) { b.totalForce = V3(); b.totalTorque = V3(); }
+    }
+
+    V3 centerOfMass() const {
+        V3 s; double m = 0;
+        for (const Body& b : bodies) { s += b.pos * b.mass; m += b.mass; }
+        return m > 0 ? s / m : V3();
+    }
+};
+
+extern "C" {
+
+tgo_world* tgo_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground) {
+    tgo_world* w = new tgo_world();
+    w->cfg = *cfg;
+    w->ground = *ground;
+    w->iterations = cfg->solver_iterations > 0 ? cfg->solver_iterations : 10;
+    return w;
+}
+
+void tgo_destroy(tgo_world* w) { delete w; }
+
+int tgo_add_model_flat(tgo_world* w, const tgb_body_desc* bodies, int n_bodies, const tgb_shape_desc* shapes,
+                       int n_shapes, const tgb_cable_desc* cables, int n_cables) {
+    const int body0 = (int)w->bodies.size();
+    const int shape0 = (int)w->shapes.size();
+    for (int i = 0; i < n_shapes; ++i) {
+        Shape s;
+        s.radius = shapes[i].radius; s.halfLen = shapes[i].half_length; s.margin = shapes[i].margin;
+        s.pos = V3(shapes[i].pos[0], shapes[i].pos[1], shapes[i].pos[2]);
+        s.rot = M3::fromQuat(Q4(shapes[i].quat[0], shapes[i].quat[1], shapes[i].quat[2], shapes[i].quat[3]));
+        w->shapes.push_back(s);
+    }
+    for (int i = 0; i < n_bodies; ++i) {
+        const tgb_body_desc& d = bodies[i];
+        Body b;
+        b.mass = d.mass;
+        b.invMass = d.mass != 0.0 ? 1.0 / d.mass : 0.0; /* btRigidBody::setMassProps */
+        b.invInertiaLocal = V3(d.inertia[0] != 0.0 ? 1.0 / d.inertia[0] : 0.0, d.inertia[1] != 0.0 ? 1.0 / d.inertia[1] : 0.0,
+                               d.inertia[2] != 0.0 ? 1.0 / d.inertia[2] : 0.0);
+        if (d.mass == 0.0) b.invInertiaLocal = V3();
+        b.pos = V3(d.pos[0], d.pos[1], d.pos[2]);
+        b.basis = M3::fromQuat(Q4(d.quat[0], d.quat[1], d.quat[2], d.quat[3]));
+        b.friction = d.friction; b.rollingFriction = d.rolling_friction; b.restitution = d.restitution;
+        b.shapeBegin = shape0 + d.shape_begin; b.shapeCount = d.shape_count;
+        b.gyro = d.gyroscopic != 0;
+        /* btRigidBody::setGravity: m_gravity = acceleration * (1 / m_inverseMass) */
+        if (b.invMass != 0.0) b.gravityForce = V3(0, -w->cfg.gravity, 0) * (1.0 / b.invMass);
+        b.updateInertiaTensor();
+        w->bodies.push_back(b);
+    }
+    for (int i = 0; i < n_cables; ++i) {
+        const tgb_cable_desc& d = cables[i];
+        Cable c;
+        c.a = body0 + d.body_a; c.b = body0 + d.body_b;
+        c.la = V3(d.local_a[0], d.local_a[1], d.local_a[2]);
+        c.lb = V3(d.local_b[0], d.local_b[1], d.local_b[2]);
+        c.k = d.stiffness; c.c = d.damping;
+        c.rest = d.rest_length; c.prev = d.prev_length;
+        c.velocity = 0; c.damping = 0;
+        c.actuator = d.actuator; c.backdrivable = d.backdrivable != 0;
+        c.maxTens = d.max_tension; c.tVel = d.target_velocity; c.minAL = d.min_actual_length; c.minRL = d.min_rest_length;
+        c.mRadius = d.motor_radius; c.mFriction = d.motor_friction; c.mInertia = d.motor_inertia;
+        c.preferred = c.rest; /* tgBasicActuator ctor: m_preferredLength(m_restLength) */
+        c.motorVel = 0; c.desiredTorque = 0;
+        w->cables.push_back(c);
+    }
+    w->episodeStartCom = w->centerOfMass();
+    return 0;
+}
+
+int tgo_num_bodies(const tgo_world* w) { return (int)w->bodies.size(); }
+int tgo_num_cables(const tgo_world* w) { return (int)w->cables.size(); }
+
+void tgo_set_rod_state(tgo_world* w, const double* s) {
+    for (size_t i = 0; i < w->bodies.size(); ++i, s += 13) {
+        Body& b = w->bodies[i];
+        b.pos = V3(s[0], s[1], s[2]);
+        b.basis = M3::fromQuat(Q4(s[3], s[4], s[5], s[6]));
+        b.linvel = V3(s[7], s[8], s[9]);
+        b.angvel = V3(s[10], s[11], s[12]);
+        b.updateInertiaTensor();
+    }
+    w->episodeStartCom = w->centerOfMass();
+}
+
+void tgo_get_rod_state(const tgo_world* w, double* s) {
+    for (size_t i = 0; i < w->bodies.size(); ++i, s += 13) {
+        const Body& b = w->bodies[i];
+        Q4 q = b.basis.toQuat();
+        s[0] = b.pos.x; s[1] = b.pos.y; s[2] = b.pos.z;
+        s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
+        s[7] = b.linvel.x; s[8] = b.linvel.y; s[9] = b.linvel.z;
+        s[10] = b.angvel.x; s[11] = b.angvel.y; s[12] = b.angvel.z;
+    }
+}
+
+void tgo_set_cable_state(tgo_world* w, const double* rp) {
+    for (size_t i = 0; i < w->cables.size(); ++i) {
+        w->cables[i].rest = rp[2 * i];
+        w->cables[i].prev = rp[2 * i + 1];
+        w->cables[i].preferred = w->cables[i].rest;
+    }
+}
+
+void tgo_get_cable_obs(const tgo_world* w, double* o) {
+    for (size_t i = 0; i < w->cables.size(); ++i) {
+        const Cable& c = w->cables[i];
+        o[4 * i + 0] = c.rest;
+        o[4 * i + 1] = w->cableLength(c);
+        o[4 * i + 2] = w->cableTension(c);
+        o[4 * i + 3] = c.motorVel;
+    }
+}
+
+int tgo_set_controller(tgo_world* w, int kind, const double* params, int n_params) {
+    w->ctrlKind = kind;
+    w->ctrlParams.assign(params, params + n_params);
+    w->ctrlTime = 0.0;
+    return 0;
+}
+
+int tgo_set_control_input(tgo_world* w, const double* input, double dt) {
+    for (size_t i = 0; i < w->cables.size(); ++i) {
+        if (w->cables[i].actuator != TGB_ACT_BASIC) continue;
+        int rc = w->setControlInput(w->cables[i], input[i], dt);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+void tgo_world_step(tgo_world* w, double dt) { w->worldStep(dt); }
+void tgo_models_step(tgo_world* w, double dt) { w->modelsStep(dt); }
+
+int tgo_step(tgo_world* w, double dt, int n_steps) {
+    if (!(dt > 0.0)) return TGB_ERR_INVALID_ARGUMENT;
+    for (int s = 0; s < n_steps; ++s) {
+        w->worldStep(dt);   /* tgSimulation.cpp:205 */
+        w->modelsStep(dt);  /* tgSimulation.cpp:208-211 */
+        w->time += dt;
+    }
+    return 0;
+}
+
+double tgo_get_time(const tgo_world* w) { return w->time; }
+void tgo_mark_episode_start(tgo_world* w) { w->episodeStartCom = w->centerOfMass(); }
+void tgo_get_scores(const tgo_world* w, double* s) {
+    V3 c = w->centerOfMass();
+    double dx = c.x - w->episodeStartCom.x, dz = c.z - w->episodeStartCom.z;
+    s[0] = std::sqrt(dx * dx + dz * dz);
+    s[1] = 0.0;
+}
+int tgo_num_contacts(const tgo_world* w) { return (int)w->contacts.size(); }
+
+int tgo_rollout_batch(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, const tgb_body_desc* bodies, int n_bodies,
+                      const tgb_shape_desc* shapes, int n_shapes, const tgb_cable_desc* cables, int n_cables, int ctrl_kind,
+                      const double* ctrl_params, int params_per_env, const double* setup_input, double setup_dt, int n_env,
+                      const double* rod_state_in, const double* cable_state_in, double dt, int n_steps, int n_threads,
+                      double* rod_state_out, double* cable_obs_out) {
+    if (!(dt > 0.0)) return TGB_ERR_INVALID_ARGUMENT;
+    if (n_threads < 1) n_threads = 1;
+    auto work = [&](int t) {
+        for (int e = t; e < n_env; e += n_threads) {
+            tgo_world* w = tgo_create(cfg, ground);
+            tgo_add_model_flat(w, bodies, n_bodies, shapes, n_shapes, cables, n_cables);
+            if (rod_state_in) tgo_set_rod_state(w, rod_state_in + (size_t)e * n_bodies * 13);
+            if (cable_state_in) tgo_set_cable_state(w, cable_state_in + (size_t)e * n_cables * 2);
+            if (setup_input) tgo_set_control_input(w, setup_input, setup_dt);
+            if (ctrl_kind != TGB_CTRL_NONE) tgo_set_controller(w, ctrl_kind, ctrl_params + (size_t)e * params_per_env, params_per_env);
+            tgo_step(w, dt, n_steps);
+            if (rod_state_out) tgo_get_rod_state(w, rod_state_out + (size_t)e * n_bodies * 13);
+            if (cable_obs_out) tgo_get_cable_obs(w, cable_obs_out + (size_t)e * n_cables * 4);
+            tgo_destroy(w);
+        }
+    };
+    if (n_threads == 1) { work(0); return 0; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,85 @@
+/*
+ * tg_oracle.h -- CPU oracle for the batched tensegrity step (TEST INFRASTRUCTURE, NOT PRODUCT).
+ *
+ * A plain double-precision, one-environment-at-a-time restatement of the reference's
+ * per-step path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may use anything in oracle/.  The shipped library
+ * (ntrtsim_b200/csrc) never includes, links or calls it.
+ *
+ * What it follows (paths relative to the NTRTsim tree):
+ *   step order            src/core/tgSimulation.cpp:193-225   (world first, then models)
+ *   cable force           src/core/tgBulletSpringCable.cpp:90-141
+ *   anchors               src/core/tgBulletSpringCableAnchor.cpp:76-87
+ *   tension / length      src/core/tgBulletSpringCable.cpp:143-155
+ *   motors                src/core/tgBasicActuator.cpp:137-225, src/core/tgKinematicActuator.cpp:135-225
+ *   controllers           src/controllers/tgTensionController.cpp:50-88,
+ *                         src/examples/craterEscape/EscapeController.cpp:100-117,245-291,
+ *                         src/examples/motorModel/tsTestRig.cpp:170-199
+ *   world step            Bullet 2.82 btDiscreteDynamicsWorld::stepSimulation(dt,1,dt) as reached from
+ *                         src/core/tgWorldBulletPhysicsImpl.cpp:209-221 -- Bullet itself is NOT in the
+ *                         reference tree (conf/default/bullet.conf.default:34,44); its semantics are
+ *                         restated from SURVEY.md Appendix B.
+ *
+ * PARITY STATUS: pieces (1) cables and (2) motors/controllers are pinned against the reference's
+ * own sources compiled in place (oracle/_ref, see oracle/ref/README.md) through tests/golden/.
+ * Piece (3) rigid-body integration is pinned by analytic invariants only; piece (4) contact is
+ * "parity unpinned": Bullet's GJK/persistent-manifold narrowphase and its Dantzig LCP solver are
+ * replaced here by an analytic cylinder-rim manifold and fixed-iteration projected Gauss-Seidel.
+ */
+#ifndef TG_ORACLE_H
+#define TG_ORACLE_H
+
+#include "../include/ntrtsim_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tgo_world tgo_world;
+
+/* One environment. Same descriptors as the device library so both sides see identical inputs. */
+tgo_world* tgo_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground);
+void       tgo_destroy(tgo_world* w);
+int        tgo_add_model_flat(tgo_world* w, const tgb_body_desc* bodies, int n_bodies,
+                              const tgb_shape_desc* shapes, int n_shapes,
+                              const tgb_cable_desc* cables, int n_cables);
+int  tgo_num_bodies(const tgo_world* w);
+int  tgo_num_cables(const tgo_world* w);
+
+void tgo_set_rod_state(tgo_world* w, const double* state13);   /* [n_bodies][13] */
+void tgo_get_rod_state(const tgo_world* w, double* state13);
+void tgo_set_cable_state(tgo_world* w, const double* rest_prev); /* [n_cables][2] */
+void tgo_get_cable_obs(const tgo_world* w, double* obs4);        /* [n_cables][4] */
+
+int  tgo_set_controller(tgo_world* w, int kind, const double* params, int n_params);
+int  tgo_set_control_input(tgo_world* w, const double* input, double dt); /* [n_cables] */
+
+/* n_steps x tgSimulation::step(dt). Returns 0, or TGB_ERR_INVALID_ARGUMENT when dt <= 0. */
+int  tgo_step(tgo_world* w, double dt, int n_steps);
+
+/* The two halves of one step, exposed for the reference-source harness (oracle/ref): */
+void tgo_world_step(tgo_world* w, double dt);     /* Bullet stepSimulation(dt,1,dt) restatement */
+void tgo_models_step(tgo_world* w, double dt);    /* controllers + motors + cable impulses */
+
+double tgo_get_time(const tgo_world* w);
+void   tgo_mark_episode_start(tgo_world* w);
+void   tgo_get_scores(const tgo_world* w, double* scores2);
+int    tgo_num_contacts(const tgo_world* w);      /* contacts generated in the last world step */
+
+/* Batched convenience for tests and the CPU baseline: run `n_env` independent environments that share one
+   model, each from its own rod state / cable state / controller row, for n_steps; OpenMP-free, `n_threads`
+   std::threads.  Outputs as in tgb_get_rod_state / tgb_get_cable_obs. */
+int tgo_rollout_batch(const tgb_world_cfg* cfg, const tgb_ground_desc* ground,
+                      const tgb_body_desc* bodies, int n_bodies,
+                      const tgb_shape_desc* shapes, int n_shapes,
+                      const tgb_cable_desc* cables, int n_cables,
+                      int ctrl_kind, const double* ctrl_params, int params_per_env,
+                      const double* setup_input, double setup_dt,
+                      int n_env, const double* rod_state_in, const double* cable_state_in,
+                      double dt, int n_steps, int n_threads,
+                      double* rod_state_out, double* cable_obs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

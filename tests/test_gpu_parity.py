@@ -1,0 +1,355 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on the same seeded inputs.
+
+Tolerances.  The double-precision instantiation evaluates the oracle's expression tree without FMA contraction, so it
+is held to round-off level (1e-9 on positions that reach a few hundred units).  The single-precision instantiation is
+the throughput configuration; BASELINE.json's north star states "within a stated FP32 tolerance (e.g. 1e-4 relative)":
+cable tensions are held to 1e-4 of max(|T|, typical pretension level) and positions to 1e-4 of the structure size.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import ntrtsim_b200 as nt  # noqa: E402
+from ntrtsim_b200 import _capi as capi  # noqa: E402
+import oracle_py  # noqa: E402
+from helpers import random_poses, rod_errors, tension_rel_error, align_quat_sign  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+F32_REL = 1e-4
+
+
+def oracle_rollout(model, rods, cab, steps, ctrl_kind=0, params=None, dt=None, setup_input=None, threads=8):
+    return oracle_py.rollout_batch(model, capi.WorldCfg, rods, cab, dt or model.dt, steps, ctrl_kind, params,
+                                   setup_input=setup_input, setup_dt=dt or model.dt, n_threads=threads)
+
+
+def device_rollout(model, rods, cab, steps, precision, ctrl_kind=0, params=None, dt=None, setup_input=None, chunks=1, **kw):
+    n_env = rods.shape[0]
+    w = nt.BatchedWorld(model, n_env, precision=precision, **kw)
+    try:
+        w.set_rod_state(rods)
+        w.set_cable_state(cab)
+        if setup_input is not None:
+            w.set_control_input(setup_input, dt or model.dt)
+        if ctrl_kind:
+            w.set_controller(ctrl_kind, params)
+        per = steps // chunks
+        for i in range(chunks):
+            w.step(dt or model.dt, per if i < chunks - 1 else steps - per * (chunks - 1))
+        w.sync()
+        return w.get_rod_state(), w.get_cable_obs(), w.status()
+    finally:
+        w.close()
+
+
+def tiled_cables(model, n_env):
+    return np.tile(model.initial_cable_state(), (n_env, 1, 1))
+
+
+# ------------------------------------------------------------------------------------------------ contact-free
+@pytest.mark.parametrize("steps", [1, 2, 200])
+def test_prism_drop_f64_roundoff(steps):
+    """config 2 (3-prism, no ground, random poses), double precision: round-off level agreement."""
+    model = nt.build_example("3_prism_noground")
+    n_env = 67  # not a multiple of the envs per CTA: exercises the tail groups
+    rods, cab = random_poses(model, n_env, seed=1234), tiled_cables(model, n_env)
+    rd, cd, st = device_rollout(model, rods, cab, steps, "f64")
+    ro, co = oracle_rollout(model, rods, cab, steps)
+    e = rod_errors(rd, ro, 1.0)
+    assert max(e) < 1e-9, e
+    assert np.abs(cd - co).max() < 1e-7, np.abs(cd - co).max()
+    assert not st.any()
+
+
+def test_prism_first_step_damping_artefact():
+    """prevLength starts at the rest length (tgSpringCable.cpp:59): the first applied force is 2 k stretch. After one
+    step the observable is the velocity change of the rods, compared with the oracle in double."""
+    model = nt.build_example("3_prism_noground")
+    rods, cab = model.initial_rod_state()[None], tiled_cables(model, 1)
+    rd, cd, _ = device_rollout(model, rods, cab, 1, "f64")
+    ro, co = oracle_rollout(model, rods, cab, 1)
+    assert np.abs(rd - align_quat_sign(ro, rd)).max() < 1e-11
+    # tension reported without the damping term: k * pretension/k = 500 on every cable
+    assert np.allclose(cd[0, :, 2], 500.0, atol=1e-6)
+
+
+def test_prism_drop_f32_full_horizon():
+    """config 2, single precision, full horizon H = 1000 steps (each env falls ~490 units): stated FP32 tolerance."""
+    model = nt.build_example("3_prism_noground")
+    n_env, steps = 512, 1000
+    rods, cab = random_poses(model, n_env, seed=1234), tiled_cables(model, n_env)
+    rd, cd, st = device_rollout(model, rods, cab, steps, "f32", chunks=4)
+    ro, co = oracle_rollout(model, rods, cab, steps)
+    # positions relative to the structure (its size is ~20 units): compare after removing the common fall
+    terr = tension_rel_error(cd, co, floor=100.0)
+    lerr = np.abs(cd[..., 1] - co[..., 1]).max() / 20.0
+    rerr = np.abs(cd[..., 0] - co[..., 0]).max() / 20.0
+    perr = rod_errors(rd, ro, 20.0)
+    print("f32 full horizon: tension rel %.3e, length rel %.3e, rest %.3e, rods %s" % (terr, lerr, rerr, perr))
+    assert terr < F32_REL and lerr < F32_REL and rerr < F32_REL
+    assert perr[0] < F32_REL and perr[1] < F32_REL
+    assert not st.any()
+
+
+def test_prism_per_step_trace_f32():
+    """Per-step cable tensions / rest lengths / rod states over a short horizon from identical initial conditions."""
+    model = nt.build_example("3_prism_noground")
+    n_env, steps = 32, 60
+    rods, cab = random_poses(model, n_env, seed=99), tiled_cables(model, n_env)
+    w = nt.BatchedWorld(model, n_env, precision="f32")
+    ow = [oracle_py.OracleWorld(model, capi.WorldCfg) for _ in range(n_env)]
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    for e in range(n_env):
+        ow[e].set_rod_state(rods[e])
+        ow[e].set_cable_state(cab[e])
+    worst_t = worst_p = 0.0
+    for s in range(steps):
+        w.step(model.dt, 1)
+        cd, rd = w.get_cable_obs(), w.get_rod_state()
+        for e in range(n_env):
+            ow[e].step(model.dt, 1)
+        co = np.stack([o.get_cable_obs() for o in ow])
+        ro = np.stack([o.get_rod_state() for o in ow])
+        worst_t = max(worst_t, tension_rel_error(cd, co, floor=100.0))
+        worst_p = max(worst_p, rod_errors(rd, ro, 20.0)[0])
+    w.close()
+    print("per-step trace: worst tension rel %.3e, worst position rel %.3e" % (worst_t, worst_p))
+    assert worst_t < F32_REL and worst_p < F32_REL
+
+
+# ------------------------------------------------------------------------------------------------ contact + control
+def escape_inputs(model, n_env, seed):
+    rods = random_poses(model, n_env, seed=seed, translate=1.0, lift=(0.0, 5.0), yaw_only=True)
+    rng = np.random.default_rng(seed + 1)
+    params = nt.escape_transform_actions(rng.uniform(size=(n_env, 32)), 9.0)
+    return rods, tiled_cables(model, n_env), params
+
+
+@pytest.mark.parametrize("steps", [1, 50, 400])
+def test_superball_sine_contact_f64(steps):
+    """config 3 (24-cable SUPERball, sine controller, box ground): the double path follows the oracle through contact."""
+    model = nt.build_example("Escape_c3")
+    n_env = 48
+    rods, cab, params = escape_inputs(model, n_env, seed=2345)
+    rd, cd, st = device_rollout(model, rods, cab, steps, "f64", capi.TGB_CTRL_ESCAPE_SINE, params)
+    ro, co = oracle_rollout(model, rods, cab, steps, capi.TGB_CTRL_ESCAPE_SINE, params)
+    e = rod_errors(rd, ro, 1.0)
+    print("superball f64 %d steps: rods %s cables %.3e" % (steps, e, np.abs(cd - co).max()))
+    assert max(e) < 1e-7, e
+    assert tension_rel_error(cd, co, floor=10.0) < 1e-7
+
+
+def test_superball_sine_contact_f32_short_horizon():
+    """config 3, single precision, short horizon (200 steps): stated FP32 tolerance.  Contact makes the
+    trajectory sensitive (a contact point appearing one step earlier changes the impulses), so the bound is held on the
+    bulk of the batch: at least 99% of the environments within tolerance, and every environment within 1e-2."""
+    model = nt.build_example("Escape_c3")
+    n_env, steps = 256, 200
+    rods, cab, params = escape_inputs(model, n_env, seed=2345)
+    rd, cd, st = device_rollout(model, rods, cab, steps, "f32", capi.TGB_CTRL_ESCAPE_SINE, params)
+    ro, co = oracle_rollout(model, rods, cab, steps, capi.TGB_CTRL_ESCAPE_SINE, params)
+    per_env_t = (np.abs(cd[..., 2] - co[..., 2]) / np.maximum(np.abs(co[..., 2]), 100.0)).max(axis=1)
+    rdl = align_quat_sign(rd, ro)
+    per_env_p = np.abs(rdl[..., 0:3] - ro[..., 0:3]).max(axis=(1, 2)) / 17.0
+    frac_ok = np.mean((per_env_t < F32_REL) & (per_env_p < F32_REL))
+    print("superball f32: frac within 1e-4 = %.4f, worst tension %.3e, worst pos %.3e, median tension %.3e"
+          % (frac_ok, per_env_t.max(), per_env_p.max(), np.median(per_env_t)))
+    assert frac_ok >= 0.99
+    assert per_env_t.max() < 1e-2 and per_env_p.max() < 1e-2
+    assert not st.any()
+
+
+def test_t6_25_cables_tension_controller_f64():
+    """Shipped SUPERball (25 cables incl. the duplicated pair) on the pitched ground with T6TensionController."""
+    model = nt.build_example("SUPERball")
+    n_env, steps = 16, 300
+    rods = random_poses(model, n_env, seed=5, translate=0.5, lift=(0.0, 2.0), yaw_only=True)
+    cab = tiled_cables(model, n_env)
+    params = np.full((n_env, 1), 1000.0)  # AppSUPERball.cpp: T6TensionController(1000)
+    rd, cd, _ = device_rollout(model, rods, cab, steps, "f64", capi.TGB_CTRL_TENSION, params)
+    ro, co = oracle_rollout(model, rods, cab, steps, capi.TGB_CTRL_TENSION, params)
+    assert max(rod_errors(rd, ro, 1.0)) < 1e-7
+    assert np.abs(cd - co).max() < 1e-6
+
+
+def test_prism_on_ground_f64():
+    """config 1 world (3-prism over the box ground) replicated: drop, impact and rest."""
+    model = nt.build_example("3_prism")
+    n_env, steps = 8, 600
+    rods = random_poses(model, n_env, seed=11, translate=0.2, rotate=False)
+    cab = tiled_cables(model, n_env)
+    rd, cd, _ = device_rollout(model, rods, cab, steps, "f64")
+    ro, co = oracle_rollout(model, rods, cab, steps)
+    assert max(rod_errors(rd, ro, 1.0)) < 1e-6
+    assert tension_rel_error(cd, co, floor=10.0) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ motors (config 5)
+@pytest.mark.parametrize("kind", ["basic", "kinematic"])
+@pytest.mark.parametrize("dt", [2e-3, 1e-3, 2e-4, 1e-4])
+def test_motor_rig_matches_oracle(kind, dt):
+    """tsTestRig (MotorTimestep_test.cpp:81-215): setControlInput(5.0, dt) / setControlInput(-580) every step, 1 s."""
+    model = nt.build_example("tsTestRig_" + kind)
+    n_env = 8
+    steps = int(round(1.0 / dt))
+    rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+    cab = tiled_cables(model, n_env)
+    ctrl = capi.TGB_CTRL_SETPOINT if kind == "basic" else capi.TGB_CTRL_TORQUE
+    params = np.full((n_env, 1), 5.0 if kind == "basic" else -580.0)
+    rd, cd, _ = device_rollout(model, rods, cab, steps, "f64", ctrl, params, dt=dt)
+    ro, co = oracle_rollout(model, rods, cab, steps, ctrl, params, dt=dt)
+    assert np.abs(cd - co).max() < 1e-8
+    rd32, cd32, _ = device_rollout(model, rods, cab, steps, "f32", ctrl, params, dt=dt)
+    assert np.abs(cd32[..., 0] - co[..., 0]).max() < 1e-3  # rest length; the reference test's own bound is 0.03
+
+
+@pytest.mark.parametrize("kind", ["basic", "kinematic"])
+def test_motor_rig_timestep_independence_on_device(kind):
+    """The reference's own assertion, on the device: rest length after 1 s equal across dt within 0.03."""
+    model = nt.build_example("tsTestRig_" + kind)
+    ctrl = capi.TGB_CTRL_SETPOINT if kind == "basic" else capi.TGB_CTRL_TORQUE
+    params = np.full((4, 1), 5.0 if kind == "basic" else -580.0)
+    rest = {}
+    for dt in (2e-3, 1e-3, 2e-4, 1e-4):
+        rods, cab = np.tile(model.initial_rod_state(), (4, 1, 1)), tiled_cables(model, 4)
+        _, cd, _ = device_rollout(model, rods, cab, int(round(1.0 / dt)), "f32", ctrl, params, dt=dt)
+        rest[dt] = cd[0, 0, 0]
+    for dt in rest:
+        assert abs(rest[dt] - rest[1e-3]) <= 0.03, rest
+
+
+# ------------------------------------------------------------------------------------------------ API behaviour
+def test_control_input_and_errors():
+    model = nt.build_example("3_prism_noground")
+    n_env = 5
+    rods, cab = random_poses(model, n_env, seed=3), tiled_cables(model, n_env)
+    w = nt.BatchedWorld(model, n_env, precision="f64")
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    target = np.linspace(5.0, 9.0, model.n_cables)
+    w.set_control_input(target, 1e-3)
+    obs = w.get_cable_obs()
+    for e in range(n_env):
+        o = oracle_py.OracleWorld(model, capi.WorldCfg)
+        o.set_rod_state(rods[e])
+        o.set_cable_state(cab[e])
+        assert o.set_control_input(target, 1e-3) == 0
+        assert np.abs(o.get_cable_obs() - obs[e]).max() < 1e-10
+    with pytest.raises(capi.TgbError) as ei:
+        w.set_control_input(-target, 1e-3)
+    assert ei.value.status == capi.TGB_ERR_INVALID_ARGUMENT  # "Rest length is negative."
+    with pytest.raises(capi.TgbError) as ei:
+        w.step(0.0, 1)
+    assert ei.value.status == capi.TGB_ERR_INVALID_ARGUMENT  # tgSimulation.cpp:197-200
+    with pytest.raises(capi.TgbError):
+        w.step(-1e-3, 1)
+    w.step(1e-3, 0)  # zero steps: a no-op
+    assert w.launch_count() == 0
+    assert abs(w.time()) == 0.0
+    w.step(1e-3, 3)
+    assert abs(w.time() - 3e-3) < 1e-15
+    w.close()
+
+
+def test_rollout_host_equals_set_step_get():
+    model = nt.build_example("Escape_c3")
+    n_env, steps = 33, 40
+    rods, cab, params = escape_inputs(model, n_env, seed=77)
+    a = device_rollout(model, rods, cab, steps, "f32", capi.TGB_CTRL_ESCAPE_SINE, params)
+    w = nt.BatchedWorld(model, n_env, precision="f32")
+    w.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params)
+    rd, cd = w.rollout_host(rods, cab, model.dt, steps)
+    w.close()
+    assert np.array_equal(rd, a[0]) and np.array_equal(cd, a[1])
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_bit_identical_across_launch_geometry(precision):
+    """The arithmetic of a body / cable does not depend on which lane runs it: results are bit-identical across
+    lanes-per-env, CTA size and launch chunking."""
+    model = nt.build_example("Escape_c3")
+    n_env, steps = 70, 120
+    rods, cab, params = escape_inputs(model, n_env, seed=5)
+    ref = device_rollout(model, rods, cab, steps, precision, capi.TGB_CTRL_ESCAPE_SINE, params)
+    for kw in (dict(lanes_per_env=16), dict(lanes_per_env=32, block_threads=64), dict(block_threads=128), dict(chunks=7)):
+        got = device_rollout(model, rods, cab, steps, precision, capi.TGB_CTRL_ESCAPE_SINE, params, **kw)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), kw
+
+
+def test_scores_and_status():
+    model = nt.build_example("Escape_c3")
+    n_env, steps = 12, 300
+    rods, cab, params = escape_inputs(model, n_env, seed=21)
+    w = nt.BatchedWorld(model, n_env, precision="f64")
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    w.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params)
+    w.set_height_window(1.0, 25.0)
+    w.step(model.dt, steps)
+    sc = w.scores()
+    st = w.status()
+    for e in range(n_env):
+        o = oracle_py.OracleWorld(model, capi.WorldCfg)
+        o.set_rod_state(rods[e])
+        o.set_cable_state(cab[e])
+        o.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params[e])
+        o.step(model.dt, steps)
+        assert abs(o.scores()[0] - sc[e, 0]) < 1e-7
+        assert sc[e, 1] == 0.0
+    assert not (st & 1).any()
+    w.close()
+
+
+def test_host_api_drop_in_runs_on_device():
+    """tgSimulation::run of the example app through the C++ host API == direct C-ABI rollout."""
+    import ctypes as C
+    h = capi.load_host()
+    model = nt.build_example("3_prism")
+    n_env, steps = 4, 100
+    rod = np.empty((n_env, model.n_bodies, 13))
+    cab = np.empty((n_env, model.n_cables, 4))
+    rc = h.tgh_run_example(b"3_prism", n_env, capi.TGB_F64, steps, rod.ctypes.data_as(C.c_void_p), cab.ctypes.data_as(C.c_void_p))
+    assert rc == 0, h.tgh_last_error()
+    rods0 = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+    rd, cd, _ = device_rollout(model, rods0, tiled_cables(model, n_env), steps, "f64")
+    assert np.array_equal(rd, rod) and np.array_equal(cd, cab)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_momentum_conservation_zero_gravity():
+    """4096 envs (BASELINE.json batch size), zero gravity, no ground: cables are internal forces, so the total linear
+    momentum of every environment stays zero and its mass centre does not move (MuscleNP_test.cpp:108-112 style)."""
+    import copy
+    model = copy.copy(nt.build_example("3_prism_noground"))
+    model.gravity = 0.0
+    n_env, steps = 4096, 500
+    rods, cab = random_poses(model, n_env, seed=42), tiled_cables(model, n_env)
+    mass = np.array([b.mass for b in model.bodies])
+    for precision, tol in (("f64", 1e-9), ("f32", 2e-3)):
+        rd, cd, st = device_rollout(model, rods, cab, steps, precision)
+        p = (rd[:, :, 7:10] * mass[None, :, None]).sum(axis=1)
+        com0 = (rods[:, :, 0:3] * mass[None, :, None]).sum(axis=1) / mass.sum()
+        com1 = (rd[:, :, 0:3] * mass[None, :, None]).sum(axis=1) / mass.sum()
+        print(precision, "max |p| %.3e  max com drift %.3e" % (np.abs(p).max(), np.abs(com1 - com0).max()))
+        assert np.abs(p).max() < tol and np.abs(com1 - com0).max() < tol
+        assert not st.any()
+
+
+def test_full_size_superball_sample_against_oracle():
+    """config 3 at full batch size: every 64th environment of a 4096-env run checked against the oracle (f64)."""
+    model = nt.build_example("Escape_c3")
+    n_env, steps = 4096, 100
+    rods, cab, params = escape_inputs(model, n_env, seed=2345)
+    rd, cd, st = device_rollout(model, rods, cab, steps, "f64", capi.TGB_CTRL_ESCAPE_SINE, params)
+    idx = np.arange(0, n_env, 64)
+    ro, co = oracle_rollout(model, rods[idx], cab[idx], steps, capi.TGB_CTRL_ESCAPE_SINE, params[idx])
+    assert max(rod_errors(rd[idx], ro, 1.0)) < 1e-7
+    assert not st.any()
