@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched tensegrity step on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], SURVEY.md section 8d "C3"): 4096 environments per GPU of the 24-cable SUPERball
+(craterEscape EscapeModel: 6 rods, 24 tgBasicActuator cables), flat tgBoxGround, g = 98.1, dt = 1e-3, the EscapeController
+sine controller with per-env parameters U(0,1)^32 mapped by transformActions (L0 = 9), start pose = model pose + U(0,5)
+extra height + random yaw, seed 2345.  One bench "step" = one pass of the hot path over the batch = ONE call
+tgb_step(world, dt, H) that advances every environment H = --sim-steps simulation steps (env state stays in
+registers/shared memory for the H steps; HBM is touched at the launch boundaries).
+
+  value  env-steps/s with the state resident in HBM, CUDA events on the world's stream, L2 flushed between steps
+  e2e    the same through tgb_rollout_host with pinned HOST buffers: H2D of rod + cable state, H steps, D2H of rod
+         state + cable observations, all inside the timed region
+  roofline  algorithmic bytes (2*4*(13R+2C)+4*P_ctrl = 1136 B per env-step) x env-steps per launch /
+            launch duration against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (FP64 restatement of the NTRTsim/Bullet-2.82 path; Bullet is not in the reference tree,
+                so the reference itself cannot be built: kind "port") on all host cores, bounded sample
+
+python bench.py --impl reference times that CPU port alone, all host threads, same workload/metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "env-steps/sec (SUPERball, 4096 envs) at 1/2/4/8 B200; % HBM roofline"
+UNIT = "env-steps/s"
+SEED = 2345
+
+
+def build_workload(name, n_env, seed):
+    import ntrtsim_b200 as nt
+    from ntrtsim_b200 import _capi as capi
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import random_poses
+    if name == "superball":
+        model = nt.build_example("Escape_c3")
+        rods = random_poses(model, n_env, seed=seed, translate=1.0, lift=(0.0, 5.0), yaw_only=True)
+        rng = np.random.default_rng(seed + 1)
+        params = nt.escape_transform_actions(rng.uniform(size=(n_env, 32)), 9.0)
+        ctrl = capi.TGB_CTRL_ESCAPE_SINE
+        p_ctrl = 32
+    elif name == "prism":
+        model = nt.build_example("3_prism_noground")
+        rods = random_poses(model, n_env, seed=seed)
+        params, ctrl, p_ctrl = None, capi.TGB_CTRL_NONE, 0
+    else:
+        raise ValueError(name)
+    cab = np.tile(model.initial_cable_state(), (n_env, 1, 1))
+    b_alg = 2 * 4 * (13 * model.n_bodies + 2 * model.n_cables) + 4 * p_ctrl
+    return model, rods, cab, ctrl, params, b_alg
+
+
+def workload_desc(name, n_env, H, n_gpus):
+    what = {"superball": "SUPERball (EscapeModel: 6 rods, 24 basic-actuator cables) + EscapeController sine, flat box ground, g=98.1",
+            "prism": "3-prism (3 rods, 9 cables), no ground, g=981 (contact-free drop)"}[name]
+    return "%s; %d envs/GPU x %d GPU; dt=1e-3; %d sim steps per launch" % (what, n_env, n_gpus, H)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
+            self.thread = threading.Thread(target=self._read)
+            self.thread.daemon = True
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch(workload, H):
+    """dram bytes per launch of the step kernel from the committed ncu capture, if one matches this configuration."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            key = "%s_H%d" % (workload, H)
+            if key in d:
+                return d[key]
+        except Exception:
+            pass
+    return None
+
+
+def cpu_port_rate(model, rods, cab, ctrl, params, H, n_env_sample, threads):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    from ntrtsim_b200 import _capi as capi
+    p = None if params is None else params[:n_env_sample]
+    t0 = time.perf_counter()
+    oracle_py.rollout_batch(model, capi.WorldCfg, rods[:n_env_sample], cab[:n_env_sample], model.dt, H, ctrl, p, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n_env_sample * H / dt, dt
+
+
+def run_reference(args):
+    """The reference arm: the CPU port of the path (oracle) with every host thread, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ntrtsim_b200.build import build_all
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        build_all()
+    cores = os.cpu_count() or 1
+    H = args.sim_steps
+    sample_env = min(args.envs, cores * 8)
+    model, rods, cab, ctrl, params, _ = build_workload(args.workload, sample_env, SEED)
+    for _ in range(args.warmup):
+        cpu_port_rate(model, rods, cab, ctrl, params, H, sample_env, cores)
+    total = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_port_rate(model, rods, cab, ctrl, params, H, sample_env, cores)
+        total += dt
+    value = sample_env * H * args.steps / total
+    sample = "%d envs x %d sim steps per step, %d threads (first envs of the same seeded workload)" % (sample_env, H, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload_desc(args.workload, args.envs, H, args.gpus)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--sim-steps", type=int, default=1000, help="simulation steps per launch (H)")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--workload", default="superball", choices=["superball", "prism"])
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import ntrtsim_b200 as nt
+    from ntrtsim_b200 import _capi as capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available() or capi.load().tgb_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the step has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n_env, H = args.envs, args.sim_steps
+    # env-axis sharding: rank r owns envs [r*n_env, (r+1)*n_env) of the global seeded batch; no exchange inside an episode
+    model, rods_all, cab_all, ctrl, params_all, b_alg = build_workload(args.workload, n_env * world_size, SEED)
+    sl = slice(rank * n_env, (rank + 1) * n_env)
+    rods, cab = np.ascontiguousarray(rods_all[sl]), np.ascontiguousarray(cab_all[sl])
+    params = None if params_all is None else np.ascontiguousarray(params_all[sl])
+
+    w = nt.BatchedWorld(model, n_env, precision=args.precision, device=local_rank, lanes_per_env=args.lanes, block_threads=args.threads)
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    if ctrl:
+        w.set_controller(ctrl, params)
+    lanes, block, grid = w.launch_geometry()
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def flush_l2():
+        flush.fill_(rank & 0xff)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # the path's only collective: allgather of per-rollout scores after an episode chunk (N > 1)
+    scores_all = None
+    if dist is not None:
+        scores_all = torch.empty(world_size * n_env * 2, dtype=torch.float32, device="cuda")
+
+    def gather_scores():
+        ptr, nbytes = w.scores_device_ptr()
+
+        class _Wrap(object):
+            __cuda_array_interface__ = {"shape": (n_env * 2,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        local = torch.as_tensor(_Wrap(), device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(scores_all, local)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    # ---- warm-up ---------------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        w.step_timed(model.dt, H, 1)
+        if dist is not None:
+            gather_scores()
+
+    # ---- timed region: device-resident state ---------------------------------------------------------------------
+    launches0 = w.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t_wall0 = time.perf_counter()
+    ms_kernel, ms_gather = [], []
+    for _ in range(args.steps):
+        flush_l2()
+        ms_kernel.append(w.step_timed(model.dt, H, 1)[0])
+        if dist is not None:
+            ms_gather.append(gather_scores())
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    launches = w.launch_count() - launches0
+    total_ms = sum(ms_kernel) + sum(ms_gather)
+    status_bad = int((w.status() & 1).sum())
+
+    # ---- end to end through the C ABI with pinned host buffers ---------------------------------------------------
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+        v = t.numpy()
+        v[...] = a
+        return t, v
+    rods_t, rods_p = pinned(rods)
+    cab_t, cab_p = pinned(cab)
+    rod_out_t, rod_out = pinned(np.zeros((n_env, w.R, capi.ROD_STATE_DOUBLES)))
+    cab_out_t, cab_out = pinned(np.zeros((n_env, w.C, capi.CABLE_OBS_DOUBLES)))
+    h2d = rods_p.nbytes + cab_p.nbytes
+    d2h = rod_out.nbytes + cab_out.nbytes
+    if ctrl:
+        w.set_controller(ctrl, params)
+    for _ in range(2):
+        w.rollout_host(rods_p, cab_p, model.dt, H, rod_out, cab_out)
+    barrier()
+    e2e_s = []
+    for _ in range(args.steps):
+        flush_l2()
+        t0 = time.perf_counter()
+        w.rollout_host(rods_p, cab_p, model.dt, H, rod_out, cab_out)  # synchronises its stream before returning
+        e2e_s.append(time.perf_counter() - t0)
+    barrier()
+    e2e_total = sum(e2e_s)
+    e2e_checksum = float(np.abs(cab_out[..., 2]).mean())
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_total, float(launches), float(status_bad)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = float(t[0]), float(t[1])
+
+    if rank == 0:
+        env_steps = float(world_size) * n_env * H * args.steps
+        value = env_steps / (total_ms * 1e-3)
+        e2e_value = env_steps / e2e_total
+        peak, peak_src = measured_hbm_peak()
+        k_ms = float(np.mean(ms_kernel))
+        achieved = b_alg * n_env * H / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": workload_desc(args.workload, n_env, H, world_size), "envs_per_gpu": n_env, "sim_steps_per_launch": H,
+                       "lanes_per_env": lanes, "block_threads": block, "grid": grid, "l2": "flushed between timed steps (256 MiB write)",
+                       "seed": SEED, "wall_s_timed_region": t_wall, "nonfinite_envs": status_bad},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_total / args.steps, "checksum_mean_tension": e2e_checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic_per_launch(args.workload, H), "kernel": "tgb_step_kernel<%s,%d>" % (args.precision, lanes),
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_env_step": b_alg, "env_steps_per_launch": n_env * H,
+                         "peak_source": peak_src,
+                         "note": "effective figure: env state stays on chip for the H fused steps, real DRAM traffic is ~1/H of it"},
+        }
+        if world_size > 1:
+            line["config"]["allgather_ms_per_step"] = float(np.mean(ms_gather))
+        if world_size == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            # calibrate, then size the sample for ~10 s of CPU work
+            cal_env = min(n_env, cores * 2)
+            rate, _ = cpu_port_rate(model, rods, cab, ctrl, params, min(H, 200), cal_env, cores)
+            sample_env = int(min(n_env, max(cores, rate * 10.0 / H)))
+            sample_env = max(cores, sample_env // cores * cores)
+            rate, secs = cpu_port_rate(model, rods, cab, ctrl, params, H, sample_env, cores)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d envs x %d sim steps of the same workload, %d threads, %.1f s (FP64 CPU restatement of the "
+                                              "NTRTsim/Bullet-2.82 path; Bullet is absent so the reference cannot be built)" % (sample_env, H, cores, secs)}
+        print(json.dumps(line))
+    w.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

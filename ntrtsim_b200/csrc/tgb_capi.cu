@@ -75,6 +75,7 @@ struct tgb_world {
         tgb::tgb_io_args a;
         a.state = d_state; a.frame = d_frame; a.com0 = d_com0; a.model_t = d_model_t; a.model_i = d_model_i;
         a.n_env = cfg.n_env; a.R = R; a.C = C; a.S = S; a.stride = stride; a.frame_body = frameBody;
+        a.frame_static = bodies[frameBody].mass == 0.0 ? 1 : 0;
         a.env_begin = envBegin; a.env_count = envCount;
         return a;
     }
@@ -347,11 +348,12 @@ tgb_status tgb_finalize(tgb_world* w) {
     w->stride = w->R * TGB_NBS + w->C * TGB_NCS;
     w->stride = (w->stride + vecWords - 1) / vecWords * vecWords;
     int maxShapes = 1;
+    /* the env frame follows the first static body if there is one (then it never moves and static bodies stay
+       bit-exactly in place), else the first body */
     w->frameBody = 0;
-    bool haveDynamic = false;
-    for (int b = 0; b < w->R; ++b) {
+    for (int b = w->R - 1; b >= 0; --b) {
         maxShapes = std::max(maxShapes, (int)w->bodies[b].shape_count);
-        if (!haveDynamic && w->bodies[b].mass != 0.0) { w->frameBody = b; haveDynamic = true; }
+        if (w->bodies[b].mass == 0.0) w->frameBody = b;
     }
     w->capContacts = 4 * maxShapes; /* at most 4 manifold points per collision shape */
     w->lanes = w->lanesOverride ? w->lanesOverride : std::max(2, nextPow2(w->R));

@@ -25,6 +25,7 @@ struct tgb_io_args {
     const void* model_t;
     const int* model_i;
     int n_env, R, C, S, stride, frame_body;
+    int frame_static; /* the frame body is a static body: the frame never moves (V = 0) */
     int env_begin, env_count;
 };
 
@@ -38,15 +39,16 @@ __global__ void pack_rods_kernel(tgb_io_args a, const double* __restrict__ src, 
     const double* rec = src + (size_t)(broadcast ? 0 : e) * a.R * TGB_NBS;
     const double* s = rec + b * TGB_NBS;
     const double* f = rec + a.frame_body * TGB_NBS;
+    const double fv[3] = {a.frame_static ? 0.0 : f[7], a.frame_static ? 0.0 : f[8], a.frame_static ? 0.0 : f[9]};
     T* d = reinterpret_cast<T*>(a.state) + (size_t)env * a.stride + b * TGB_NBS;
     d[0] = (T)(s[0] - f[0]); d[1] = (T)(s[1] - f[1]); d[2] = (T)(s[2] - f[2]);
     d[3] = (T)s[3]; d[4] = (T)s[4]; d[5] = (T)s[5]; d[6] = (T)s[6];
-    d[7] = (T)(s[7] - f[7]); d[8] = (T)(s[8] - f[8]); d[9] = (T)(s[9] - f[9]);
+    d[7] = (T)(s[7] - fv[0]); d[8] = (T)(s[8] - fv[1]); d[9] = (T)(s[9] - fv[2]);
     d[10] = (T)s[10]; d[11] = (T)s[11]; d[12] = (T)s[12];
     if (b == 0) {
         double* fr = a.frame + (size_t)env * TGB_NFR;
         fr[FR_O] = f[0]; fr[FR_O + 1] = f[1]; fr[FR_O + 2] = f[2];
-        fr[FR_V] = f[7]; fr[FR_V + 1] = f[8]; fr[FR_V + 2] = f[9];
+        fr[FR_V] = fv[0]; fr[FR_V + 1] = fv[1]; fr[FR_V + 2] = fv[2];
     }
 }
 

@@ -232,6 +232,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     };
     publishPose();
     __syncwarp();
+    /* a frame tied to a static body never moves: static bodies then stay bit-exactly in place */
+    const bool frameMoves = M.body(BF_INVMASS, a.frame_body) != T(0);
 
 #define CT(slot, f) sCt[((slot) * TGB_NCT + (f)) * LPE + lane]
 
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
 
         /* ---- env frame: advance the origin with the frame velocity, then re-centre on the frame body ---- */
-        {
+        if (frameMoves) {
             Ox += Vx * a.dt; Oy += Vy * a.dt; Oz += Vz * a.dt;
             const int src = groupLane0 + a.frame_body;
             const T sx = __shfl_sync(fullMask, b.x.x, src), sy = __shfl_sync(fullMask, b.x.y, src), sz = __shfl_sync(fullMask, b.x.z, src);

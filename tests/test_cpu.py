@@ -1,0 +1,274 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every declared symbol, the host-side model builder
+reproduces the reference's construction arithmetic, and the oracle satisfies the invariants and reference-test pins
+that exist for this path."""
+import ctypes as C
+import math
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import ntrtsim_b200 as nt  # noqa: E402
+from ntrtsim_b200 import _capi as capi  # noqa: E402
+import oracle_py  # noqa: E402
+from helpers import random_poses, quat_rotate  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------------ the boundary
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ntrtsim_b200.h")).read()
+    declared = set(re.findall(r"\b(tgb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"tgb_world"}
+    assert declared == set(capi.ABI_SYMBOLS), declared ^ set(capi.ABI_SYMBOLS)
+    lib = capi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tgb_abi_version() == 1
+
+
+def test_create_fails_loudly_without_a_gpu():
+    lib = capi.load()
+    if lib.tgb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    model = nt.build_example("3_prism")
+    with pytest.raises(capi.TgbError) as ei:
+        nt.BatchedWorld(model, 4)
+    assert ei.value.status == capi.TGB_ERR_CUDA
+    assert "no CPU path" in str(ei.value)
+
+
+def test_product_never_touches_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "ntrtsim_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(base, f), errors="replace").read()
+                assert "oracle_py" not in text and "tg_oracle" not in text and "liboracle" not in text, os.path.join(base, f)
+
+
+def test_create_argument_validation():
+    lib = capi.load()
+    h = C.c_void_p()
+    model = nt.build_example("3_prism")
+    cfg = capi.WorldCfg(981.0, 0, 0, 0, 0)
+    assert lib.tgb_create(C.byref(cfg), C.byref(model.ground), C.byref(h)) == capi.TGB_ERR_INVALID_ARGUMENT
+    assert lib.tgb_create(None, C.byref(model.ground), C.byref(h)) == capi.TGB_ERR_INVALID_ARGUMENT
+    cfg = capi.WorldCfg(981.0, 1, 7, 0, 0)
+    assert lib.tgb_create(C.byref(cfg), C.byref(model.ground), C.byref(h)) == capi.TGB_ERR_INVALID_ARGUMENT
+
+
+# ------------------------------------------------------------------------------------------------ model builder
+def test_prism_builder_matches_reference_construction():
+    m = nt.build_example("3_prism")
+    assert (m.n_bodies, m.n_cables) == (3, 9) and nt.tree_counts("3_prism") == (3, 9)
+    # mass = (float)(pi r^2 L rho): tgRodInfo.cpp:116-123 through tgBulletUtil.cpp:39-42
+    lengths = [math.sqrt(10 ** 2 + 20 ** 2), math.sqrt(5 ** 2 + 20 ** 2 + 10 ** 2), math.sqrt(5 ** 2 + 20 ** 2 + 10 ** 2)]
+    for b, L in zip(m.bodies, lengths):
+        mass = float(np.float32(math.pi * 0.31 ** 2 * L * 0.2))
+        assert b.mass == mass
+        # btCylinderShape(r, L/2, r)::calculateLocalInertia, axis Y
+        assert abs(b.inertia[1] - 0.5 * mass * 0.31 ** 2) < 1e-12
+        assert abs(b.inertia[0] - (mass / 12 * L ** 2 + mass / 4 * 0.31 ** 2)) < 1e-9
+        assert b.inertia[0] == b.inertia[2] and b.gyroscopic == 1
+    assert abs(m.bodies[0].mass - 1.3501694) < 1e-6 and abs(m.bodies[1].mass - 1.3835119) < 1e-6
+    # rest = |p2 - p1| - pretension / k with the anchors moved to the rod surface; prev = rest (tgSpringCable.cpp:49-59)
+    st = m.initial_rod_state()
+    for c in m.cables:
+        pa = quat_rotate(st[c.body_a, 3:7], np.array(list(c.local_a))) + st[c.body_a, 0:3]
+        pb = quat_rotate(st[c.body_b, 3:7], np.array(list(c.local_b))) + st[c.body_b, 0:3]
+        assert abs(np.linalg.norm(pb - pa) - 500.0 / 1000.0 - c.rest_length) < 1e-9
+        assert c.prev_length == c.rest_length and c.actuator == capi.TGB_ACT_BASIC
+        # anchor sits on the cylinder surface: distance from the rod axis == radius
+        assert abs(math.hypot(c.local_a[0], c.local_a[2]) - 0.31) < 1e-9
+    assert m.ground.kind == capi.TGB_GROUND_BOX and m.ground.offset == 1.5 and m.ground.friction == 0.5
+
+
+def test_superball_builder_quirks():
+    t6 = nt.build_example("SUPERball")
+    esc = nt.build_example("Escape_c3")
+    assert t6.n_cables == 25 and esc.n_cables == 24  # duplicated (2,4)/(4,2) pair: T6Model.cpp:143,153
+    assert abs(t6.bodies[0].mass - 3.4978709) < 1e-6
+    assert abs(t6.bodies[0].inertia[0] - 82.746) < 1e-2 and abs(t6.bodies[0].inertia[1] - 0.16807) < 1e-4
+    # "pitch" of AppSUPERball.cpp:53-58 goes through btQuaternion::setEuler(yaw, pitch, roll): a tilt about X
+    n = list(t6.ground.normal)
+    assert abs(n[0]) < 1e-12 and abs(n[1] - math.cos(math.pi / 15)) < 1e-12 and abs(abs(n[2]) - math.sin(math.pi / 15)) < 1e-12
+    # EscapeModel.cpp:184-185 positional slip: pretension 0 -> rest length == start length
+    st = esc.initial_rod_state()
+    c = esc.cables[0]
+    pa = quat_rotate(st[c.body_a, 3:7], np.array(list(c.local_a))) + st[c.body_a, 0:3]
+    pb = quat_rotate(st[c.body_b, 3:7], np.array(list(c.local_b))) + st[c.body_b, 0:3]
+    assert abs(np.linalg.norm(pb - pa) - c.rest_length) < 1e-9
+    assert c.max_tension == 100000 and c.target_velocity == 10000 and c.stiffness == 3152.36 and c.damping == 50.0
+
+
+def test_motor_rig_builder():
+    m = nt.build_example("tsTestRig_kinematic")
+    assert m.n_bodies == 2 and m.n_cables == 1
+    masses = sorted(b.mass for b in m.bodies)
+    assert masses[0] == 0.0 and masses[1] > 0.0  # density 0 -> static body (tsTestRig.cpp:113,135)
+    assert m.cables[0].actuator == capi.TGB_ACT_KINEMATIC and m.cables[0].motor_radius == 1.0 and m.cables[0].backdrivable == 0
+
+
+def test_escape_transform_actions():
+    a = np.full(32, 0.5)
+    p = nt.escape_transform_actions(a, 9.0)
+    # amplitude in L0*(0.9 -+ 0.5), angular frequency in [0.3, 20], phase change in [-pi, pi], dcOffset forced to 1
+    assert np.allclose(p[0:4], [9.0 * 0.9, 10.15, 0.0, 1.0]) and p[32] == 9.0
+
+
+# ------------------------------------------------------------------------------------------------ oracle pins
+def _oracle(model, rods=None, cab=None):
+    o = oracle_py.OracleWorld(model, capi.WorldCfg)
+    if rods is not None:
+        o.set_rod_state(rods)
+    if cab is not None:
+        o.set_cable_state(cab)
+    return o
+
+
+def test_oracle_step_rejects_nonpositive_dt():
+    o = _oracle(nt.build_example("3_prism"))
+    assert o.step(0.0, 1) == capi.TGB_ERR_INVALID_ARGUMENT and o.step(-1.0, 1) == capi.TGB_ERR_INVALID_ARGUMENT
+
+
+def test_oracle_first_step_is_gravity_only_then_double_force():
+    """World step runs before the cables (tgSimulation.cpp:205-211): the first world step sees gravity only; the first
+    cable force is 2 k stretch (prevLength = restLength, damping clamped to |k stretch|)."""
+    m = nt.build_example("3_prism_noground")
+    o = _oracle(m)
+    s0 = o.get_rod_state()
+    o.step(1e-3, 1)
+    s1 = o.get_rod_state()
+    g, dt = 981.0, 1e-3
+    # positions moved by exactly the gravity-only velocity g dt over dt
+    assert np.allclose(s1[:, 1] - s0[:, 1], -g * dt * dt, atol=1e-12)
+    assert np.allclose(s1[:, 0] - s0[:, 0], 0.0, atol=1e-15)
+    # velocity after step 1 = gravity + impulses of 2 * 500 on each incident cable end
+    st = s1
+    J = np.zeros((3, 3))
+    for c in m.cables:
+        pa = quat_rotate(st[c.body_a, 3:7], np.array(list(c.local_a))) + st[c.body_a, 0:3]
+        pb = quat_rotate(st[c.body_b, 3:7], np.array(list(c.local_b))) + st[c.body_b, 0:3]
+        d = pb - pa
+        L = np.linalg.norm(d)
+        stretch = L - c.rest_length
+        f = d / L * (2.0 * c.stiffness * stretch)
+        J[c.body_a] += f * dt
+        J[c.body_b] -= f * dt
+    for b in range(3):
+        v = np.array([0, -g * dt, 0]) + J[b] / m.bodies[b].mass
+        assert np.allclose(s1[b, 7:10], v, atol=1e-9)
+
+
+def test_oracle_momentum_conserved_without_gravity():
+    import copy
+    m = copy.copy(nt.build_example("3_prism_noground"))
+    m.gravity = 0.0
+    rods = random_poses(m, 1, seed=3)[0]
+    o = _oracle(m, rods, m.initial_cable_state())
+    mass = np.array([b.mass for b in m.bodies])
+    o.step(1e-3, 2000)
+    s = o.get_rod_state()
+    p = (s[:, 7:10] * mass[:, None]).sum(axis=0)
+    assert np.abs(p).max() < 1e-10  # MuscleNP_test.cpp:108-112 bound
+    # and the structure has rung down: cable tensions settle near equilibrium, all positive
+    assert (o.get_cable_obs()[:, 2] > 0).all()
+
+
+def test_oracle_free_fall_and_gyroscopic_spin():
+    """A single free rod (cables detached by zero stiffness is not possible, so use the rig's dynamic rod with the cable
+    slack): free fall x = -g/2 t(t+dt) for semi-implicit Euler; spin about the symmetry axis is steady under the
+    gyroscopic term."""
+    import copy
+    m = copy.copy(nt.build_example("tsTestRig_basic"))
+    m.ground = capi.GroundDesc(capi.TGB_GROUND_EMPTY, (0.0, 1.0, 0.0), 0.0, 0.5, 0.0, 0.0, 0.04)
+    dyn = [i for i, b in enumerate(m.bodies) if b.mass > 0][0]
+    rods = m.initial_rod_state()
+    rods[dyn, 10:13] = quat_rotate(rods[dyn, 3:7], np.array([0.0, 7.0, 0.0]))  # spin about the rod axis
+    cab = m.initial_cable_state() * 0 + 1000.0  # rest length 1000: slack for the whole fall, no force
+    o = _oracle(m, rods, cab)
+    n, dt = 500, 1e-3
+    o.step(dt, n)
+    s = o.get_rod_state()
+    t = n * dt
+    assert abs((s[dyn, 1] - rods[dyn, 1]) - (-0.5 * 981.0 * t * (t + dt))) < 1e-9
+    assert abs(s[dyn, 8] + 981.0 * t) < 1e-9
+    assert np.allclose(s[dyn, 10:13], rods[dyn, 10:13], atol=1e-9)
+
+
+def test_oracle_rod_rests_on_the_ground():
+    """3-prism dropped on the box ground (config 1): after the impact transient the lowest rim point of every rod ends
+    within the contact margin band of the surface and the structure is at rest."""
+    m = nt.build_example("3_prism")
+    o = _oracle(m)
+    o.step(1e-3, 10000)
+    s = o.get_rod_state()
+    assert np.abs(s[:, 7:10]).max() < 1.0, s[:, 7:10]  # settled to a slow creep (impact speed was ~130)
+    assert o.num_contacts() >= 3
+    lows = []
+    for b, body in enumerate(m.bodies):
+        sh = m.shapes[body.shape_begin]
+        axis = quat_rotate(s[b, 3:7], np.array([0.0, 1.0, 0.0]))
+        ends = [s[b, 0:3] + axis * sh.half_length, s[b, 0:3] - axis * sh.half_length]
+        lows.append(min(e[1] for e in ends) - sh.radius * math.sqrt(max(0.0, 1 - axis[1] ** 2)))
+    assert min(lows) > 1.5 - 0.1 and min(lows) < 1.5 + 0.1, lows
+
+
+@pytest.mark.parametrize("kind,command", [("basic", 5.0), ("kinematic", -580.0)])
+def test_oracle_motor_timestep_independence(kind, command):
+    """MotorTimestep_test.cpp:81-215: 1000 steps @1e-3 vs 500 @2e-3 vs 5000 @2e-4: rest length equal within 0.03."""
+    m = nt.build_example("tsTestRig_" + kind)
+    ctrl = capi.TGB_CTRL_SETPOINT if kind == "basic" else capi.TGB_CTRL_TORQUE
+    rest = {}
+    for dt, n in ((1e-3, 1000), (2e-3, 500), (2e-4, 5000)):
+        o = _oracle(m)
+        o.set_controller(ctrl, np.array([command]))
+        o.step(dt, n)
+        assert abs(o.time() - 1.0) < 1e-9
+        rest[dt] = o.get_cable_obs()[0, 0]
+    assert abs(rest[2e-3] - rest[1e-3]) <= 0.03 and abs(rest[2e-4] - rest[1e-3]) <= 0.03, rest
+    if kind == "basic":
+        assert abs(rest[1e-3] - 5.0) < 1e-9  # commanded rest length reached (tsTestRig.cpp:187)
+
+
+def test_oracle_sine_controller_moves_motors_twice():
+    """EscapeController.cpp:100-117: setControlInput(L, dt) then moveMotors(dt) again -> two motor steps per sim step."""
+    m = nt.build_example("Escape_c3")
+    o = _oracle(m)
+    params = np.zeros(33)
+    params[3::4][:8] = 1.0  # dcOffset
+    params[32] = 9.0
+    for c in range(8):
+        params[c * 4 + 0] = 0.0   # amplitude 0 -> target = dc = 1 -> clamped to L0/2 = 4.5
+        params[c * 4 + 1] = 1.0
+    o.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params)
+    rest0 = o.get_cable_obs()[:, 0].copy()
+    o.step(1e-3, 1)
+    rest1 = o.get_cable_obs()[:, 0]
+    # targetVelocity 10000 * dt 1e-3 = 10 per motor move: the rest length (~10.4) reaches 4.5 within the first move
+    assert np.allclose(rest1, 4.5, atol=1e-12), rest1
+    # tighter motors: tVel such that one move covers less than the gap -> exactly two steps taken
+    for c in m.cables:
+        c.target_velocity = 1000.0
+    o = _oracle(m)
+    o.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params)
+    o.step(1e-3, 1)
+    assert np.allclose(o.get_cable_obs()[:, 0], rest0 - 2.0, atol=1e-12)
+
+
+def test_oracle_batch_rollout_matches_single():
+    m = nt.build_example("Escape_c3")
+    rods = random_poses(m, 5, seed=9, translate=1.0, lift=(0, 3), yaw_only=True)
+    cab = np.tile(m.initial_cable_state(), (5, 1, 1))
+    params = nt.escape_transform_actions(np.random.default_rng(1).uniform(size=(5, 32)))
+    ro, co = oracle_py.rollout_batch(m, capi.WorldCfg, rods, cab, 1e-3, 100, capi.TGB_CTRL_ESCAPE_SINE, params, n_threads=3)
+    for e in range(5):
+        o = _oracle(m, rods[e], cab[e])
+        o.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params[e])
+        o.step(1e-3, 100)
+        assert np.array_equal(o.get_rod_state(), ro[e]) and np.array_equal(o.get_cable_obs(), co[e])
