@@ -1,0 +1,175 @@
+/*
+ * ref_harness.cpp -- drives the REFERENCE's own cable / anchor / actuator / controller / CPG sources, compiled unchanged
+ * and in place from /root/reference/src (see build_ref.py), against the shim headers in oracle/ref/shim.
+ * TEST INFRASTRUCTURE: its only purpose is to validate oracle/tg_oracle.cpp and to generate tests/golden/*.json.
+ * The world step (Bullet) is not part of this harness; callers move the shim rigid bodies themselves.
+ */
+#include "core/tgBasicActuator.h"
+#include "core/tgKinematicActuator.h"
+#include "core/tgBulletSpringCable.h"
+#include "core/tgBulletSpringCableAnchor.h"
+#include "core/tgSpringCableActuator.h"
+#include "controllers/tgTensionController.h"
+#include "controllers/tgImpedanceController.h"
+#include "util/CPGEquations.h"
+#include "BulletDynamics/Dynamics/btRigidBody.h"
+
+#include <stdexcept>
+#include <vector>
+
+struct ref_world {
+    std::vector<btRigidBody*> bodies;
+    std::vector<btVector3> invInertiaLocal;
+    std::vector<tgSpringCableActuator*> actuators;
+    std::vector<tgBulletSpringCable*> cables;
+    std::vector<tgTensionController*> tensionControllers;
+    std::vector<int> kinds;
+    ~ref_world() {
+        for (size_t i = 0; i < tensionControllers.size(); ++i) delete tensionControllers[i];
+        for (size_t i = 0; i < actuators.size(); ++i) delete actuators[i]; /* deletes its cable and the anchors */
+        for (size_t i = 0; i < bodies.size(); ++i) delete bodies[i];
+    }
+};
+
+static void setBody(ref_world* w, int b, const double* s) {
+    btRigidBody* rb = w->bodies[b];
+    rb->m_xf.setOrigin(btVector3(s[0], s[1], s[2]));
+    rb->m_xf.setRotation(btQuaternion(s[3], s[4], s[5], s[6]));
+    rb->m_linvel = btVector3(s[7], s[8], s[9]);
+    rb->m_angvel = btVector3(s[10], s[11], s[12]);
+    /* btRigidBody::updateInertiaTensor */
+    rb->m_invInertiaWorld = rb->m_xf.getBasis().scaled(w->invInertiaLocal[b]) * rb->m_xf.getBasis().transpose();
+}
+
+extern "C" {
+
+ref_world* ref_create() { return new ref_world(); }
+void ref_destroy(ref_world* w) { delete w; }
+
+int ref_add_body(ref_world* w, const double* state13, double mass, const double* inertia) {
+    btRigidBody* rb = new btRigidBody();
+    rb->m_invMass = mass != 0.0 ? 1.0 / mass : 0.0;
+    w->bodies.push_back(rb);
+    w->invInertiaLocal.push_back(mass != 0.0 ? btVector3(inertia[0] != 0.0 ? 1.0 / inertia[0] : 0.0, inertia[1] != 0.0 ? 1.0 / inertia[1] : 0.0,
+                                                          inertia[2] != 0.0 ? 1.0 / inertia[2] : 0.0)
+                                             : btVector3(0, 0, 0));
+    setBody(w, (int)w->bodies.size() - 1, state13);
+    return (int)w->bodies.size() - 1;
+}
+
+void ref_set_body(ref_world* w, int b, const double* state13) { setBody(w, b, state13); }
+
+void ref_get_body(ref_world* w, int b, double* s) {
+    btRigidBody* rb = w->bodies[b];
+    const btVector3& o = rb->m_xf.getOrigin();
+    btQuaternion q = rb->m_xf.getRotation();
+    s[0] = o.x(); s[1] = o.y(); s[2] = o.z();
+    s[3] = q.x(); s[4] = q.y(); s[5] = q.z(); s[6] = q.w();
+    s[7] = rb->m_linvel.x(); s[8] = rb->m_linvel.y(); s[9] = rb->m_linvel.z();
+    s[10] = rb->m_angvel.x(); s[11] = rb->m_angvel.y(); s[12] = rb->m_angvel.z();
+}
+
+/* kind 1 = tgBasicActuator, 2 = tgKinematicActuator. cfg = {k, c, pretension, maxTens, tVel, minAL, minRL, radius, friction, inertia, backdrivable}.
+   Returns the cable index or -1 - and the exception text through ref_last_error - when the reference constructor throws. */
+static std::string g_err;
+const char* ref_last_error() { return g_err.c_str(); }
+
+int ref_add_cable(ref_world* w, int a, int b, const double* worldA, const double* worldB, int kind, const double* cfg) {
+    try {
+        std::vector<tgBulletSpringCableAnchor*> anchors;
+        anchors.push_back(new tgBulletSpringCableAnchor(w->bodies[a], btVector3(worldA[0], worldA[1], worldA[2])));
+        anchors.push_back(new tgBulletSpringCableAnchor(w->bodies[b], btVector3(worldB[0], worldB[1], worldB[2])));
+        tgBulletSpringCable* cable = new tgBulletSpringCable(anchors, cfg[0], cfg[1], cfg[2]);
+        tgSpringCableActuator* act = 0;
+        if (kind == 2) {
+            tgKinematicActuator::Config kc(cfg[0], cfg[1], cfg[2], cfg[7], cfg[8], cfg[9], cfg[10] != 0.0, false, cfg[3], cfg[4], cfg[5], cfg[6]);
+            act = new tgKinematicActuator(cable, tgTags("muscle"), kc);
+        } else {
+            tgSpringCableActuator::Config bc(cfg[0], cfg[1], cfg[2], false, cfg[3], cfg[4], cfg[5], cfg[6]);
+            act = new tgBasicActuator(cable, tgTags("muscle"), bc);
+        }
+        w->cables.push_back(cable);
+        w->actuators.push_back(act);
+        w->kinds.push_back(kind);
+        w->tensionControllers.push_back(kind == 1 ? new tgTensionController(static_cast<tgBasicActuator*>(act), 0.0) : 0);
+        return (int)w->actuators.size() - 1;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+/* out = {actuator rest length, cable rest length, actual length, tension, cable velocity, actuator getVelocity, start length, damping} */
+void ref_get_cable(ref_world* w, int c, double* out) {
+    out[0] = w->actuators[c]->getRestLength();
+    out[1] = w->cables[c]->getRestLength();
+    out[2] = w->actuators[c]->getCurrentLength();
+    out[3] = w->actuators[c]->getTension();
+    out[4] = w->cables[c]->getVelocity();
+    out[5] = w->actuators[c]->getVelocity();
+    out[6] = w->actuators[c]->getStartLength();
+    out[7] = w->cables[c]->getDamping();
+}
+
+/* tgBasicActuator::setControlInput(input, dt); 1 = std::invalid_argument */
+int ref_set_control_input_dt(ref_world* w, int c, double input, double dt) {
+    try {
+        w->actuators[c]->setControlInput(input, dt);
+        return 0;
+    } catch (const std::invalid_argument& e) { g_err = e.what(); return 1; }
+}
+/* tgControllable::setControlInput(input): preferred length (basic) or desired torque (kinematic) */
+int ref_set_control_input(ref_world* w, int c, double input) {
+    try {
+        w->actuators[c]->setControlInput(input);
+        return 0;
+    } catch (const std::invalid_argument& e) { g_err = e.what(); return 1; }
+}
+void ref_move_motors(ref_world* w, int c, double dt) {
+    if (w->kinds[c] == 1) static_cast<tgBasicActuator*>(w->actuators[c])->moveMotors(dt);
+}
+/* T6TensionController::onStep body for one actuator: tgTensionController::control(dt, setPoint) */
+int ref_tension_control(ref_world* w, int c, double dt, double setPoint) {
+    try {
+        w->tensionControllers[c]->control(dt, setPoint);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 5; }
+}
+/* tgImpedanceController(T0, Kp, Kv).control(tgBasicActuator&, dt, newPosition, offsetVel); returns the set tension */
+double ref_impedance_control(ref_world* w, int c, double dt, double T0, double Kp, double Kv, double newPosition, double offsetVel) {
+    tgImpedanceController ic(T0, Kp, Kv);
+    return ic.control(*static_cast<tgBasicActuator*>(w->actuators[c]), dt, newPosition, offsetVel);
+}
+/* tgModel::step over the connectors: every actuator's step(dt) in creation order; 1 = std::invalid_argument */
+int ref_step_actuators(ref_world* w, double dt) {
+    try {
+        for (size_t i = 0; i < w->actuators.size(); ++i) w->actuators[i]->step(dt);
+        return 0;
+    } catch (const std::invalid_argument& e) { g_err = e.what(); return 1; }
+}
+
+/* ---- CPG ------------------------------------------------------------------------------------------------- */
+CPGEquations* ref_cpg_create(int maxSteps) { return new CPGEquations(maxSteps); }
+void ref_cpg_destroy(CPGEquations* c) { delete c; }
+int ref_cpg_add_node(CPGEquations* c, const double* params7) {
+    std::vector<double> p(params7, params7 + 7);
+    return c->addNode(p);
+}
+void ref_cpg_define_connections(CPGEquations* c, int node, int n, const int* conn, const double* weights, const double* phases) {
+    c->defineConnections(node, std::vector<int>(conn, conn + n), std::vector<double>(weights, weights + n), std::vector<double>(phases, phases + n));
+}
+/* 0 ok, 5 = std::runtime_error ("Inefficient CPG Parameters") */
+int ref_cpg_update(CPGEquations* c, const double* descCom, int n, double dt) {
+    std::vector<double> d(descCom, descCom + n);
+    try {
+        c->update(d, dt);
+        return 0;
+    } catch (const std::runtime_error& e) { g_err = e.what(); return 5; }
+}
+double ref_cpg_value(CPGEquations* c, int i) { return (*c)[i]; }
+void ref_cpg_state(CPGEquations* c, double* x) {
+    std::vector<double>& v = c->getXVars();
+    for (size_t i = 0; i < v.size(); ++i) x[i] = v[i];
+}
+
+} /* extern "C" */
