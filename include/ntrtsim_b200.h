@@ -134,14 +134,43 @@ typedef enum {
        passed through transformActions; followed by [1] initial length L0.  EscapeController.cpp:100-117,245-291 */
     TGB_CTRL_ESCAPE_SINE = 3,
     /* params per env: [C] desired motor torque, re-applied every step (tsTestRig.cpp:181-188, kinematic) */
-    TGB_CTRL_TORQUE = 4
+    TGB_CTRL_TORQUE = 4,
+    /* CPG + impedance control of the learningSpines examples, installed with tgb_set_cpg_controller:
+       BaseSpineCPGControl::onStep (BaseSpineCPGControl.cpp:253-279) -> CPGEquations::update (util/CPGEquations.cpp:231-267),
+       tgCPGActuatorControl::onStep (tgCPGActuatorControl.cpp:79-100) -> tgImpedanceController::control
+       (controllers/tgImpedanceController.cpp:151-185) -> tgTensionController::control (tgTensionController.cpp:90-114) */
+    TGB_CTRL_CPG_IMPEDANCE = 5
 } tgb_controller_kind;
+
+/* Static part of a CPG + impedance controller: one CPG node per cable (node i drives cable i, the order of
+   tgCPGActuatorControl::assignNodeNumber), the coupling lists of tgCPGActuatorControl::setConnectivity in CSR form, and the
+   impedance gains of each cable.  The per-environment parameter row is
+       [0] frequency parameter (CPGNode frequencyOffset = frequencyScale), [1] radius parameter (radiusOffset = radiusScale),
+       then n_pairs x (coupling weight, coupling phase offset);  coupling_pair[] selects the pair of each coupling. */
+typedef struct {
+    int32_t n_nodes;
+    int32_t n_couplings;
+    const int32_t* coupling_begin;  /* [n_nodes + 1] */
+    const int32_t* coupling_target; /* [n_couplings] node index */
+    const int32_t* coupling_pair;   /* [n_couplings] index into the env's (weight, phase) pairs */
+    int32_t n_pairs;
+    int32_t max_steps;              /* CPGEquations(maxSteps): more right-hand-side evaluations in one update set status bit2 */
+    const double* impedance;        /* [n_nodes][4]: offset tension, length stiffness, velocity stiffness, control length */
+    double r_const, d_min, d_max;   /* CPGNode params[4..6]: 20, 0, 5 (tgCPGActuatorControl.cpp:102-119) */
+    double descending_command;      /* 2.0 (BaseSpineCPGControl.cpp:261) */
+    double control_time;            /* BaseSpineCPGControl::Config::controlTime */
+    double cable_control_step;      /* tgCPGActuatorControl::m_controlStep, 1e-4 */
+    int32_t score_body;             /* body whose centre of mass is scored and height-checked (the segment's compound body) */
+    int32_t reserved;
+    double height_lo, height_hi;    /* 1.0 and 25 (BaseSpineCPGControl.cpp:271-278): outside -> status bit1, score -1 */
+} tgb_cpg_desc;
 
 #define TGB_ESCAPE_PARAMS 33
 
 /* Per-rod state record exchanged with the host: pos(3) quat(4, xyzw) linvel(3) angvel(3). */
 #define TGB_ROD_STATE_DOUBLES 13
-/* Per-cable observation record: rest length, actual length, tension (no damping term), motor velocity. */
+/* Per-cable observation record: rest length, actual length, tension (no damping term), velocity (tgKinematicActuator: motor
+   velocity m_motorVel; otherwise the cable's m_velocity = (length - previous length) / dt of the last force evaluation). */
 #define TGB_CABLE_OBS_DOUBLES 4
 
 typedef struct tgb_world tgb_world;
@@ -181,6 +210,15 @@ tgb_status tgb_get_cable_obs(tgb_world* w, int32_t env_begin, int32_t env_count,
 tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, int32_t params_per_env,
                               int32_t env_begin, int32_t env_count, int32_t broadcast);
 
+/* Install the CPG + impedance controller (TGB_CTRL_CPG_IMPEDANCE). params_per_env must be 2 + 2 * n_pairs. The CPG state
+   (phase, radius, radius rate of every node) of the environments in the range restarts at zero, like a new CPGEquations. */
+tgb_status tgb_set_cpg_controller(tgb_world* w, const tgb_cpg_desc* desc, const double* params, int32_t params_per_env,
+                                  int32_t env_begin, int32_t env_count, int32_t broadcast);
+
+/* CPG state of the environments in the range: [env_count][n_nodes][3] doubles (phase, radius, radius rate), the XVars of
+   CPGEquations::getXVars (util/CPGEquations.cpp:118-131). */
+tgb_status tgb_get_cpg_state(tgb_world* w, int32_t env_begin, int32_t env_count, double* out);
+
 /* tgBasicActuator::setControlInput(input, dt) on every cable of every env in the range, once, now.
    input: [n_cables] (broadcast != 0) or [env_count][n_cables]. Negative input -> TGB_ERR_INVALID_ARGUMENT
    (tgBasicActuator.cpp:139-142); a NaN entry leaves that cable untouched. */
@@ -200,7 +238,8 @@ tgb_status tgb_rollout_host(tgb_world* w, const double* rod_state_in, const doub
 /* Simulated time of the world = sum of dt over all steps (tgSimView.cpp m_totalTime equivalent). */
 tgb_status tgb_get_time(const tgb_world* w, double* out);
 
-/* Per-env status flags: bit0 = non-finite state seen, bit1 = centre of mass left [height_lo, height_hi]. */
+/* Per-env status flags: bit0 = non-finite state seen, bit1 = centre of mass left [height_lo, height_hi],
+   bit2 = a CPG update needed more than max_steps right-hand-side evaluations ("Inefficient CPG Parameters"). */
 tgb_status tgb_get_status(tgb_world* w, int32_t env_begin, int32_t env_count, int32_t* out);
 
 /* scores: [env_count][2]: XZ distance of the mass-weighted COM from its position at tgb_finalize /

@@ -11,7 +11,7 @@ TGB_OK, TGB_ERR_INVALID_ARGUMENT, TGB_ERR_STATE, TGB_ERR_CUDA, TGB_ERR_UNSUPPORT
 TGB_F32, TGB_F64 = 0, 1
 TGB_GROUND_EMPTY, TGB_GROUND_BOX, TGB_GROUND_PLANE = 0, 1, 2
 TGB_ACT_PASSIVE, TGB_ACT_BASIC, TGB_ACT_KINEMATIC = 0, 1, 2
-TGB_CTRL_NONE, TGB_CTRL_SETPOINT, TGB_CTRL_TENSION, TGB_CTRL_ESCAPE_SINE, TGB_CTRL_TORQUE = range(5)
+TGB_CTRL_NONE, TGB_CTRL_SETPOINT, TGB_CTRL_TENSION, TGB_CTRL_ESCAPE_SINE, TGB_CTRL_TORQUE, TGB_CTRL_CPG_IMPEDANCE = range(6)
 TGB_ESCAPE_PARAMS = 33
 ROD_STATE_DOUBLES = 13
 CABLE_OBS_DOUBLES = 4
@@ -46,6 +46,15 @@ class CableDesc(C.Structure):
                 ("motor_radius", C.c_double), ("motor_friction", C.c_double), ("motor_inertia", C.c_double)]
 
 
+class CpgDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("n_couplings", C.c_int32), ("coupling_begin", C.POINTER(C.c_int32)),
+                ("coupling_target", C.POINTER(C.c_int32)), ("coupling_pair", C.POINTER(C.c_int32)), ("n_pairs", C.c_int32),
+                ("max_steps", C.c_int32), ("impedance", C.POINTER(C.c_double)), ("r_const", C.c_double), ("d_min", C.c_double),
+                ("d_max", C.c_double), ("descending_command", C.c_double), ("control_time", C.c_double),
+                ("cable_control_step", C.c_double), ("score_body", C.c_int32), ("reserved", C.c_int32), ("height_lo", C.c_double),
+                ("height_hi", C.c_double)]
+
+
 class TgbError(RuntimeError):
     def __init__(self, status, message):
         RuntimeError.__init__(self, "tgb status %d: %s" % (status, message))
@@ -55,7 +64,7 @@ class TgbError(RuntimeError):
 # every symbol include/ntrtsim_b200.h declares; tests check that the library exports all of them
 ABI_SYMBOLS = [
     "tgb_abi_version", "tgb_last_error", "tgb_device_count", "tgb_create", "tgb_destroy", "tgb_add_model_flat",
-    "tgb_finalize", "tgb_num_bodies", "tgb_num_cables", "tgb_num_envs", "tgb_set_rod_state", "tgb_get_rod_state",
+    "tgb_finalize", "tgb_set_cpg_controller", "tgb_get_cpg_state", "tgb_num_bodies", "tgb_num_cables", "tgb_num_envs", "tgb_set_rod_state", "tgb_get_rod_state",
     "tgb_set_cable_state", "tgb_get_cable_obs", "tgb_set_controller", "tgb_set_control_input", "tgb_step", "tgb_sync",
     "tgb_rollout_host", "tgb_get_time", "tgb_get_status", "tgb_mark_episode_start", "tgb_get_scores",
     "tgb_scores_device_ptr", "tgb_step_timed", "tgb_launch_count", "tgb_launch_geometry", "tgb_set_lanes_per_env",
@@ -102,6 +111,8 @@ def load():
     lib.tgb_get_cable_obs.argtypes = [_vp, _i32, _i32, _vp]
     lib.tgb_set_controller.argtypes = [_vp, _i32, _vp, _i32, _i32, _i32, _i32]
     lib.tgb_set_control_input.argtypes = [_vp, _i32, _i32, _vp, _i32, C.c_double]
+    lib.tgb_get_cpg_state.argtypes = [_vp, _i32, _i32, _vp]
+    lib.tgb_set_cpg_controller.argtypes = [_vp, C.POINTER(CpgDesc), _vp, _i32, _i32, _i32, _i32]
     lib.tgb_step.argtypes = [_vp, C.c_double, _i32]
     lib.tgb_sync.argtypes = [_vp]
     lib.tgb_rollout_host.argtypes = [_vp, _vp, _vp, C.c_double, _i32, _vp, _vp]
@@ -147,6 +158,8 @@ def load_host():
     h.tgh_escape_transform_actions.restype = None
     h.tgh_run_example.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp]
     h.tgh_run_example.restype = C.c_int
+    h.tgh_tetraspine_cpg.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _vp, _vp, _vp, _vp]
+    h.tgh_tetraspine_param_row.argtypes = [_vp, _vp, C.c_int, _vp]
     _host = h
     return h
 

@@ -66,6 +66,11 @@ struct tgb_world {
     size_t hStageDoubles = 0;
     float* d_scores = nullptr;
     int ctrlKind = TGB_CTRL_NONE, ctrlStride = 0;
+    /* CPG + impedance controller */
+    tgb_cpg_desc cpg;
+    int* d_cpg_topo = nullptr;
+    double* d_cpg_imp = nullptr;
+    double* d_cpg_state = nullptr;
     double time = 0.0;
     int64_t launches = 0;
     double heightLo = 1.0, heightHi = 0.0; /* disabled */
@@ -76,6 +81,8 @@ struct tgb_world {
         a.state = d_state; a.frame = d_frame; a.com0 = d_com0; a.model_t = d_model_t; a.model_i = d_model_i;
         a.n_env = cfg.n_env; a.R = R; a.C = C; a.S = S; a.stride = stride; a.frame_body = frameBody;
         a.frame_static = bodies[frameBody].mass == 0.0 ? 1 : 0;
+        a.score_body = ctrlKind == TGB_CTRL_CPG_IMPEDANCE ? cpg.score_body : -1;
+        a.status = d_status;
         a.env_begin = envBegin; a.env_count = envCount;
         return a;
     }
@@ -108,6 +115,9 @@ struct tgb_world {
         if (d_stage) cudaFree(d_stage);
         if (h_stage) cudaFreeHost(h_stage);
         if (d_scores) cudaFree(d_scores);
+        if (d_cpg_topo) cudaFree(d_cpg_topo);
+        if (d_cpg_imp) cudaFree(d_cpg_imp);
+        if (d_cpg_state) cudaFree(d_cpg_state);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -215,6 +225,14 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.goff = w->ground.offset;
     a.ground_restitution = w->ground.restitution;
     a.height_lo = w->heightLo; a.height_hi = w->heightHi;
+    if (w->ctrlKind == TGB_CTRL_CPG_IMPEDANCE) {
+        a.cpg_n_couplings = w->cpg.n_couplings; a.cpg_n_pairs = w->cpg.n_pairs; a.cpg_max_steps = w->cpg.max_steps;
+        a.cpg_score_body = w->cpg.score_body;
+        a.cpg_topo = w->d_cpg_topo; a.cpg_imp = w->d_cpg_imp; a.cpg_state = w->d_cpg_state;
+        a.cpg_r_const = w->cpg.r_const; a.cpg_d_min = w->cpg.d_min; a.cpg_d_max = w->cpg.d_max; a.cpg_desc = w->cpg.descending_command;
+        a.cpg_control_time = w->cpg.control_time; a.cpg_cable_step = w->cpg.cable_control_step;
+        a.cpg_height_lo = w->cpg.height_lo; a.cpg_height_hi = w->cpg.height_hi;
+    }
     return a;
 }
 
@@ -509,6 +527,7 @@ tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, 
     case TGB_CTRL_SETPOINT: case TGB_CTRL_TORQUE: need = w->C; break;
     case TGB_CTRL_TENSION: need = 1; break;
     case TGB_CTRL_ESCAPE_SINE: need = TGB_ESCAPE_PARAMS; break;
+    case TGB_CTRL_CPG_IMPEDANCE: return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: use tgb_set_cpg_controller for the CPG controller");
     default: return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: unknown controller kind");
     }
     if (kind == TGB_CTRL_NONE) { w->ctrlKind = TGB_CTRL_NONE; return TGB_OK; }
@@ -539,6 +558,86 @@ tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, 
         TGB_CUDA(cudaMemset2D(w->d_frame + (size_t)env_begin * TGB_NFR + FR_CTRLTIME, TGB_NFR * sizeof(double), 0, sizeof(double), env_count));
     }
     w->ctrlKind = kind;
+    return TGB_OK;
+}
+
+tgb_status tgb_set_cpg_controller(tgb_world* w, const tgb_cpg_desc* d, const double* params, int32_t params_per_env, int32_t env_begin,
+                                  int32_t env_count, int32_t broadcast) {
+    TGB_NEED_FINAL(w);
+    if (!d || !params || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: bad arguments");
+    if (d->n_nodes != w->C || d->n_couplings < 0 || d->n_pairs < 0 || !d->coupling_begin || !d->impedance ||
+        (d->n_couplings && (!d->coupling_target || !d->coupling_pair)))
+        return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: one CPG node per cable is required");
+    if (params_per_env != 2 + 2 * d->n_pairs) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: params_per_env must be 2 + 2 * n_pairs");
+    if (d->score_body < 0 || d->score_body >= w->R) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: score body out of range");
+    if (!(d->control_time >= 0.0) || !(d->cable_control_step >= 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "control time is negative.");
+    if (d->coupling_begin[0] != 0 || d->coupling_begin[d->n_nodes] != d->n_couplings) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: bad CSR offsets");
+    for (int i = 0; i < d->n_couplings; ++i)
+        if (d->coupling_target[i] < 0 || d->coupling_target[i] >= d->n_nodes || d->coupling_pair[i] < 0 || d->coupling_pair[i] >= d->n_pairs)
+            return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: coupling index out of range");
+    for (int i = 0; i < 4 * d->n_nodes; ++i)
+        if (d->impedance[i] < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "impedance control gains must not be negative.");
+    const int n = w->cfg.n_env;
+    const bool fresh = w->ctrlKind != TGB_CTRL_CPG_IMPEDANCE;
+    if (fresh && !(env_begin == 0 && env_count == n))
+        return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: a new controller kind must cover all environments");
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    /* static part */
+    std::vector<int> topo;
+    topo.insert(topo.end(), d->coupling_begin, d->coupling_begin + d->n_nodes + 1);
+    topo.insert(topo.end(), d->coupling_target, d->coupling_target + d->n_couplings);
+    topo.insert(topo.end(), d->coupling_pair, d->coupling_pair + d->n_couplings);
+    if (w->d_cpg_topo) { cudaFree(w->d_cpg_topo); w->d_cpg_topo = nullptr; }
+    if (w->d_cpg_imp) { cudaFree(w->d_cpg_imp); w->d_cpg_imp = nullptr; }
+    TGB_CUDA(cudaMalloc(&w->d_cpg_topo, topo.size() * sizeof(int)));
+    TGB_CUDA(cudaMemcpy(w->d_cpg_topo, topo.data(), topo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    TGB_CUDA(cudaMalloc(&w->d_cpg_imp, (size_t)4 * d->n_nodes * sizeof(double)));
+    TGB_CUDA(cudaMemcpy(w->d_cpg_imp, d->impedance, (size_t)4 * d->n_nodes * sizeof(double), cudaMemcpyHostToDevice));
+    const size_t stateDoubles = (size_t)3 * w->C + 2;
+    if (fresh || w->ctrlStride != params_per_env) {
+        if (w->d_ctrl) { cudaFree(w->d_ctrl); w->d_ctrl = nullptr; }
+        TGB_CUDA(cudaMalloc(&w->d_ctrl, (size_t)n * params_per_env * sizeof(double)));
+        w->ctrlStride = params_per_env;
+    }
+    if (!w->d_cpg_state) TGB_CUDA(cudaMalloc(&w->d_cpg_state, (size_t)n * stateDoubles * sizeof(double)));
+    w->cpg = *d;
+    w->cpg.coupling_begin = nullptr; w->cpg.coupling_target = nullptr; w->cpg.coupling_pair = nullptr; w->cpg.impedance = nullptr;
+    w->ctrlKind = TGB_CTRL_CPG_IMPEDANCE;
+    {
+        tgb_step_args a = stepArgs(w, 1e-3, 1);
+        if (w->ops->step_smem(a, w->lanes, w->threads) > 227 * 1024) {
+            w->ctrlKind = TGB_CTRL_NONE;
+            return fail(TGB_ERR_UNSUPPORTED, "CPG controller work space does not fit in shared memory");
+        }
+    }
+    if (env_count > 0) {
+        if (broadcast) {
+            std::vector<double> rows((size_t)env_count * params_per_env);
+            for (int e = 0; e < env_count; ++e) std::memcpy(&rows[(size_t)e * params_per_env], params, params_per_env * sizeof(double));
+            TGB_CUDA(cudaMemcpy(w->d_ctrl + (size_t)env_begin * params_per_env, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+        } else {
+            TGB_CUDA(cudaMemcpy(w->d_ctrl + (size_t)env_begin * params_per_env, params, (size_t)env_count * params_per_env * sizeof(double),
+                                cudaMemcpyHostToDevice));
+        }
+        /* a new CPGEquations: every node starts at phase 0, radius 0 (CPGNode.cpp:36-52); timers restart */
+        TGB_CUDA(cudaMemset(w->d_cpg_state + (size_t)env_begin * stateDoubles, 0, (size_t)env_count * stateDoubles * sizeof(double)));
+        TGB_CUDA(cudaMemset(w->d_status + env_begin, 0, (size_t)env_count * sizeof(int)));
+        /* BaseSpineCPGControl::onSetup: initConditions = the scored segment's centre of mass */
+        TGB_CUDA(w->ops->com(w->ioArgs(env_begin, env_count), 0, nullptr, nullptr, w->stream));
+        TGB_CUDA(cudaStreamSynchronize(w->stream));
+    }
+    return TGB_OK;
+}
+
+tgb_status tgb_get_cpg_state(tgb_world* w, int32_t env_begin, int32_t env_count, double* out) {
+    TGB_NEED_FINAL(w);
+    if (!out || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_cpg_state: bad range or NULL buffer");
+    if (w->ctrlKind != TGB_CTRL_CPG_IMPEDANCE || !w->d_cpg_state) return fail(TGB_ERR_STATE, "tgb_get_cpg_state: no CPG controller installed");
+    if (env_count == 0) return TGB_OK;
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    const size_t stride = (size_t)3 * w->C + 2;
+    TGB_CUDA(cudaMemcpy2D(out, (size_t)3 * w->C * sizeof(double), w->d_cpg_state + (size_t)env_begin * stride, stride * sizeof(double),
+                          (size_t)3 * w->C * sizeof(double), env_count, cudaMemcpyDeviceToHost));
     return TGB_OK;
 }
 

@@ -52,6 +52,7 @@ enum { FR_O = 0, FR_V = 3, FR_CTRLTIME = 6, FR_SPARE = 7, TGB_NFR = 8 };
 
 #define TGB_STATUS_NONFINITE 1
 #define TGB_STATUS_HEIGHT 2
+#define TGB_STATUS_CPG_INEFFICIENT 4
 
 struct tgb_step_args {
     void* state;          /* T[n_env][stride] */
@@ -73,6 +74,13 @@ struct tgb_step_args {
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */
     double ground_restitution;
     double height_lo, height_hi; /* status bit1 when the mass centre leaves [lo, hi]; lo > hi disables */
+
+    /* CPG + impedance controller (TGB_CTRL_CPG_IMPEDANCE); ctrl rows are [freq, radius, n_pairs x (weight, phase)] */
+    int cpg_n_couplings, cpg_n_pairs, cpg_max_steps, cpg_score_body;
+    const int* cpg_topo;      /* begin[C + 1], target[n_couplings], pair[n_couplings] */
+    const double* cpg_imp;    /* [C][4] offset tension, length stiffness, velocity stiffness, control length */
+    double* cpg_state;        /* [n_env][3 C + 2]: (phase, radius, radius rate) per node, update time, cable control time */
+    double cpg_r_const, cpg_d_min, cpg_d_max, cpg_desc, cpg_control_time, cpg_cable_step, cpg_height_lo, cpg_height_hi;
 };
 
 #endif

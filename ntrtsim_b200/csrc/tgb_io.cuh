@@ -26,6 +26,8 @@ struct tgb_io_args {
     const int* model_i;
     int n_env, R, C, S, stride, frame_body;
     int frame_static; /* the frame body is a static body: the frame never moves (V = 0) */
+    int score_body;   /* >= 0: scores follow this body's centre of mass (CPG controller), -1: the mass centre of all bodies */
+    const int* status; /* with score_body >= 0: status bit1 (height window left) turns the score into -1 */
     int env_begin, env_count;
 };
 
@@ -176,12 +178,17 @@ __global__ void com_kernel(tgb_io_args a, int mode, double* __restrict__ scores,
         m += mass;
     }
     if (m > 0) { const double im = 1.0 / m; sx *= im; sy *= im; sz *= im; }
+    if (a.score_body >= 0) {
+        const T* s = rec + a.score_body * TGB_NBS;
+        sx = fr[FR_O] + (double)s[0]; sy = fr[FR_O + 1] + (double)s[1]; sz = fr[FR_O + 2] + (double)s[2];
+    }
     double* c0 = a.com0 + (size_t)env * 3;
     if (mode == 0) {
         c0[0] = sx; c0[1] = sy; c0[2] = sz;
     } else {
         const double dx = sx - c0[0], dz = sz - c0[2];
-        const double d = sqrt(dx * dx + dz * dz);
+        double d = sqrt(dx * dx + dz * dz);
+        if (a.score_body >= 0 && a.status != nullptr && (a.status[env] & TGB_STATUS_HEIGHT)) d = -1.0; /* bogus episode */
         if (scores) { scores[(size_t)e * 2] = d; scores[(size_t)e * 2 + 1] = 0.0; }
         if (scores_f) { scores_f[(size_t)env * 2] = (float)d; scores_f[(size_t)env * 2 + 1] = 0.0f; }
     }

@@ -103,6 +103,13 @@ TGB_D float sinPhase(double arg, float) {
     return sinf((float)r);
 }
 
+/* doubles of shared memory per env group: controller row, sine cumulative phases, CPG work space */
+__host__ __device__ inline int tgb_group_double_words(const tgb_step_args& a) {
+    int n = a.ctrl_stride + 8;
+    if (a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) n += 3 * a.cpg_n_pairs + (3 + 3 + 3 + 21 + 1) * a.C;
+    return n;
+}
+
 /* Views of the packed model in shared memory. */
 template <typename T>
 struct ModelView {
@@ -152,10 +159,18 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     T* sPose = sState + a.stride;              /* [12][LPE] : pos3, basis9 of each body */
     T* sJ = sPose + poseWords;                 /* [C][3] */
     T* sCt = sJ + jWords;                      /* [cap][TGB_NCT][LPE] */
-    const int groupDWords = a.ctrl_stride + 8;
+    const bool cpgOn = a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE;
+    const int groupDWords = tgb_group_double_words(a);
     double* sD = reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) + grp * groupDWords;
     double* sCtrl = sD;                        /* controller parameter row */
     double* sCum = sD + a.ctrl_stride;         /* sine controller: cumulative phase per cluster */
+    /* CPG: pair table (weight, cos phase, sin phase), state x, stage state, published (sin, cos, r), k1..k7, node values */
+    double* sPair = sCum + 8;
+    double* sX = sPair + 3 * a.cpg_n_pairs;
+    double* sXt = sX + 3 * C;
+    double* sTrig = sXt + 3 * C;
+    double* sK = sTrig + 3 * C;                /* [7][3 C] */
+    double* sNodeValue = sK + 21 * C;
     int* sModelI = reinterpret_cast<int*>(reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) +
                                           groupsPerBlock * groupDWords);
 
@@ -197,6 +212,24 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         for (int c = 1; c < 8; ++c) { ph += sCtrl[c * 4 + 2]; sCum[c] = ph; }
     }
 
+    double cpgUpdateTime = 0.0, cpgCableTime = 0.0;
+    if (cpgOn) {
+        const double* cs = a.cpg_state + (size_t)env * (3 * C + 2);
+        for (int i = lane; i < 3 * C; i += LPE) sX[i] = cs[i];
+        cpgUpdateTime = cs[3 * C];
+        cpgCableTime = cs[3 * C + 1];
+        for (int p = lane; p < a.cpg_n_pairs; p += LPE) {
+            double sn, cn;
+            sincos(sCtrl[2 + 2 * p + 1], &sn, &cn);
+            sPair[3 * p] = sCtrl[2 + 2 * p];
+            sPair[3 * p + 1] = cn;
+            sPair[3 * p + 2] = sn;
+        }
+        __syncwarp();
+        for (int i = lane; i < C; i += LPE) sNodeValue[i] = sX[3 * i + 1] * cos(sX[3 * i]); /* CPGNode::updateNodeValues */
+    }
+    int statusAcc = 0;
+
     /* ---- body state into registers ------------------------------------------------------------------------ */
     const bool hasBody = lane < R;
     const int bidx = hasBody ? lane : 0;
@@ -236,6 +269,118 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     const bool frameMoves = M.body(BF_INVMASS, a.frame_body) != T(0);
 
 #define CT(slot, f) sCt[((slot) * TGB_NCT + (f)) * LPE + lane]
+
+    /* ---- CPG: CPGNode::updateDTs for this lane's nodes (CPGNode.cpp:71-88). Every lane of the warp calls this the same
+       number of times (it synchronises); `act` masks groups that have nothing to do. sin(phi_j - phi_i - theta) is
+       expanded over the published (sin phi, cos phi) of the nodes and the precomputed (cos theta, sin theta). */
+    const int* topoBegin = a.cpg_topo;
+    const int* topoTarget = a.cpg_topo + (C + 1);
+    const int* topoPair = topoTarget + a.cpg_n_couplings;
+    auto cpgRhs = [&](const double* xin, double* kout, bool act) {
+        if (act)
+            for (int i = lane; i < C; i += LPE) {
+                double sn, cn;
+                sincos(xin[3 * i], &sn, &cn);
+                sTrig[3 * i] = sn; sTrig[3 * i + 1] = cn; sTrig[3 * i + 2] = xin[3 * i + 1];
+            }
+        __syncwarp();
+        if (act) {
+            const double d = a.cpg_desc;
+            const bool inRange = d >= a.cpg_d_min && d <= a.cpg_d_max;
+            const double freq = inRange ? sCtrl[0] * d + sCtrl[0] : 0.0;   /* nodeEquation(d, c0, c1) with c0 = c1 */
+            const double radius = inRange ? sCtrl[1] * d + sCtrl[1] : 0.0;
+            for (int i = lane; i < C; i += LPE) {
+                const double si = sTrig[3 * i], ci = sTrig[3 * i + 1];
+                double phiDot = 2 * 3.14159265358979323846 * freq;
+                for (int k = topoBegin[i]; k < topoBegin[i + 1]; ++k) {
+                    const int j = topoTarget[k], p = topoPair[k];
+                    const double sj = sTrig[3 * j], cj = sTrig[3 * j + 1], rj = sTrig[3 * j + 2];
+                    const double sd = sj * ci - cj * si, cd = cj * ci + sj * si;
+                    phiDot += sPair[3 * p] * rj * (sd * sPair[3 * p + 1] - cd * sPair[3 * p + 2]);
+                }
+                const double r = xin[3 * i + 1], rd = xin[3 * i + 2];
+                kout[3 * i] = phiDot;
+                kout[3 * i + 1] = rd;
+                kout[3 * i + 2] = a.cpg_r_const * (a.cpg_r_const / 4 * (radius - r) - rd);
+            }
+        }
+        __syncwarp();
+    };
+    /* CPGEquations::update (CPGEquations.cpp:231-267) = Boost.Odeint integrate(): controlled Dormand-Prince 5(4), FSAL,
+       eps_abs = eps_rel = 1e-6 (see oracle/tg_odeint.h for the restated algorithm). `want` = this group updates now. */
+    auto cpgUpdate = [&](double tEnd, bool want) {
+        const double eps = 2.220446049250313e-16;
+        double dtc = tEnd <= 0.1 ? tEnd : 0.1;
+        double t = 0.0;
+        int numSteps = 0;
+        double* k1 = sK; double* k2 = sK + 3 * C; double* k3 = sK + 6 * C; double* k4 = sK + 9 * C; double* k5 = sK + 12 * C;
+        double* k6 = sK + 15 * C; double* k7 = sK + 18 * C;
+        cpgRhs(sX, k1, want);
+        numSteps += 1;
+        int trials = 0;
+        bool active = want && (tEnd - t > eps);
+        while (__any_sync(fullMask, active)) {
+            if (active && trials == 0 && (t + dtc) - tEnd > eps) dtc = tEnd - t;
+            const double b21 = 1.0 / 5.0, b31 = 3.0 / 40.0, b32 = 9.0 / 40.0, b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
+            const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
+            const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0, b65 = -5103.0 / 18656.0;
+            const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
+            const double dc1 = c1 - 5179.0 / 57600.0, dc3 = c3 - 7571.0 / 16695.0, dc4 = c4 - 393.0 / 640.0,
+                         dc5 = c5 - (-92097.0 / 339200.0), dc6 = c6 - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
+            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
+                sXt[v] = 1.0 * sX[v] + (dtc * b21) * k1[v];
+            cpgRhs(sXt, k2, active);
+            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
+                sXt[v] = 1.0 * sX[v] + (dtc * b31) * k1[v] + (dtc * b32) * k2[v];
+            cpgRhs(sXt, k3, active);
+            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
+                sXt[v] = 1.0 * sX[v] + (dtc * b41) * k1[v] + (dtc * b42) * k2[v] + (dtc * b43) * k3[v];
+            cpgRhs(sXt, k4, active);
+            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
+                sXt[v] = 1.0 * sX[v] + (dtc * b51) * k1[v] + (dtc * b52) * k2[v] + (dtc * b53) * k3[v] + (dtc * b54) * k4[v];
+            cpgRhs(sXt, k5, active);
+            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
+                sXt[v] = 1.0 * sX[v] + (dtc * b61) * k1[v] + (dtc * b62) * k2[v] + (dtc * b63) * k3[v] + (dtc * b64) * k4[v] + (dtc * b65) * k5[v];
+            cpgRhs(sXt, k6, active);
+            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
+                sXt[v] = 1.0 * sX[v] + (dtc * c1) * k1[v] + (dtc * c3) * k3[v] + (dtc * c4) * k4[v] + (dtc * c5) * k5[v] + (dtc * c6) * k6[v];
+            cpgRhs(sXt, k7, active);
+            if (active) numSteps += 6;
+            /* error estimate, maximum over the group's nodes */
+            double err = 0.0;
+            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v) {
+                const double xe = (dtc * dc1) * k1[v] + (dtc * dc3) * k3[v] + (dtc * dc4) * k4[v] + (dtc * dc5) * k5[v] + (dtc * dc6) * k6[v] + (dtc * dc7) * k7[v];
+                const double e = fabs(xe) / (1e-6 + 1e-6 * (1.0 * fabs(sX[v]) + (1.0 * dtc) * fabs(k1[v])));
+                err = fmax(err, e);
+            }
+#pragma unroll
+            for (int off = LPE / 2; off > 0; off >>= 1) err = fmax(err, __shfl_xor_sync(fullMask, err, off));
+            if (active) {
+                if (err > 1.0) {
+                    dtc *= fmax(9.0 / 10.0 * pow(err, -1.0 / (4.0 - 1.0)), 1.0 / 5.0);
+                    trials += 1;
+                    if (trials >= 1000) { statusAcc |= TGB_STATUS_CPG_INEFFICIENT; active = false; } /* odeint throws overflow_error */
+                } else {
+                    if (err < 0.5) {
+                        err = fmax(pow(5.0, -5.0), err);
+                        t += dtc;
+                        dtc *= 9.0 / 10.0 * pow(err, -1.0 / 5.0);
+                    } else {
+                        t += dtc;
+                    }
+                    for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v) { sX[v] = sXt[v]; k1[v] = k7[v]; }
+                    trials = 0;
+                    active = tEnd - t > eps;
+                }
+            }
+            __syncwarp();
+        }
+        if (want) {
+            for (int i = lane; i < C; i += LPE) sNodeValue[i] = sX[3 * i + 1] * cos(sX[3 * i]);
+            if (numSteps > a.cpg_max_steps) statusAcc |= TGB_STATUS_CPG_INEFFICIENT;
+        }
+        __syncwarp();
+    };
 
     for (int step = 0; step < a.n_steps; ++step) {
         /* =============================== world step (tgSimulation.cpp:205) =============================== */
@@ -418,6 +563,24 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
         /* =============================== models step (tgSimulation.cpp:208-211) =============================== */
         if (ctrlKind == TGB_CTRL_ESCAPE_SINE) ctrlTime += a.dt; /* EscapeController::m_totalTime */
+        bool cpgCableControl = false;
+        double cpgCableDt = 0.0;
+        if (cpgOn) {
+            /* BaseSpineCPGControl::onStep, BaseSpineCPGControl.cpp:253-279 */
+            cpgUpdateTime += a.dt;
+            const bool want = cpgUpdateTime >= a.cpg_control_time;
+            if (__any_sync(fullMask, want)) cpgUpdate(cpgUpdateTime, want);
+            if (want) cpgUpdateTime = 0.0;
+            if (hasBody && lane == a.cpg_score_body) {
+                const double h = Oy + (double)b.x.y;
+                if (h > a.cpg_height_hi || h < a.cpg_height_lo) statusAcc |= TGB_STATUS_HEIGHT; /* bogus */
+            }
+            /* tgCPGActuatorControl::onStep timing, tgCPGActuatorControl.cpp:79-100 (identical for every cable) */
+            cpgCableTime += a.dt;
+            cpgCableControl = cpgCableTime >= a.cpg_cable_step;
+            cpgCableDt = cpgCableTime;
+            if (cpgCableControl) cpgCableTime = 0.0;
+        }
         for (int c = lane; c < C; c += LPE) {
             const int ia = M.cablei(CI_A, c), ib = M.cablei(CI_B, c);
             const int actuator = M.cablei(CI_ACTUATOR, c);
@@ -441,8 +604,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             T desiredTorque = T(0);
 
             /* tgBasicActuator::moveMotors, tgBasicActuator.cpp:170-225 */
-            auto moveMotors = [&]() {
-                const T stepSize = M.cable(CF_TVEL, c) * dt;
+            auto moveMotors = [&](T dtm) {
+                const T stepSize = M.cable(CF_TVEL, c) * dtm;
                 const T maxTens = M.cable(CF_MAXTENS, c);
                 if ((L - pref) * k > maxTens) pref = L - maxTens / k;
                 const T diff = pref - rest;
@@ -459,7 +622,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             if (ctrlKind == TGB_CTRL_SETPOINT) {
                 if (actuator == TGB_ACT_BASIC) {
                     const T input = (T)sCtrl[c];
-                    if (!(input < T(0))) { pref = input; moveMotors(); }
+                    if (!(input < T(0))) { pref = input; moveMotors(dt); }
                 }
             } else if (ctrlKind == TGB_CTRL_TORQUE) {
                 if (actuator == TGB_ACT_KINEMATIC) desiredTorque = (T)sCtrl[c];
@@ -474,7 +637,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                     T newLength = rest - diff;
                     newLength = newLength < T(0) ? T(0) : newLength;
                     pref = newLength;
-                    moveMotors();
+                    moveMotors(dt);
                 }
             } else if (ctrlKind == TGB_CTRL_ESCAPE_SINE) {
                 if (c < 24) {
@@ -488,9 +651,30 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                     const T minLength = L0 * (T(1) - T(0.50)), maxLength = L0 * (T(1) + T(0.50));
                     if (newLength <= minLength) newLength = minLength;
                     else if (newLength >= maxLength) newLength = maxLength;
-                    if (!(newLength < T(0))) { pref = newLength; moveMotors(); }
+                    if (!(newLength < T(0))) { pref = newLength; moveMotors(dt); }
                 }
-                moveMotors(); /* EscapeController.cpp:108-116: every muscle's motors move a second time */
+                moveMotors(dt); /* EscapeController.cpp:108-116: every muscle's motors move a second time */
+            } else if (cpgOn) {
+                if (actuator == TGB_ACT_BASIC) {
+                    if (cpgCableControl) {
+                        /* tgImpedanceController::controlTension(tgBasicActuator&, ...), tgImpedanceController.cpp:163-185 */
+                        const double* g = a.cpg_imp + 4 * c;
+                        const T vel = motorVel; /* velocity slot of a basic actuator = the cable's m_velocity */
+                        T setTension = (T)g[0] + (T)g[1] * (L - (T)g[3]) + (T)g[2] * (vel - (T)sNodeValue[c]);
+                        setTension = setTension > T(0) ? setTension : T(0);
+                        /* static tgTensionController::control(sca, dt, setPoint), tgTensionController.cpp:90-114 */
+                        T tension = (L - rest) * k;
+                        tension = tension < T(0) ? T(0) : tension;
+                        const T delta = setTension - tension;
+                        const T diff = delta / k;
+                        T newLength = rest - diff;
+                        newLength = newLength < T(0.1) ? T(0.1) : newLength;
+                        pref = newLength;
+                        moveMotors((T)cpgCableDt);
+                    } else {
+                        moveMotors(dt);
+                    }
+                }
             }
 
             /* ---- tgKinematicActuator::integrateRestLength, tgKinematicActuator.cpp:186-225 ---- */
@@ -525,7 +709,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             prev = L;
             const V3<T> J = force * dt;
             sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
-            cs[CS_REST] = rest; cs[CS_PREV] = prev; cs[CS_PREF] = pref; cs[CS_MOTORVEL] = motorVel;
+            cs[CS_REST] = rest; cs[CS_PREV] = prev; cs[CS_PREF] = pref;
+            cs[CS_MOTORVEL] = actuator == TGB_ACT_KINEMATIC ? motorVel : velocity;
         }
         __syncwarp();
 
@@ -573,6 +758,9 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         anyBad = __ballot_sync(fullMask, bad);
         const unsigned groupMask = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
         int st = 0;
+#pragma unroll
+        for (int off = LPE / 2; off > 0; off >>= 1) statusAcc |= __shfl_xor_sync(fullMask, statusAcc, off);
+        st |= statusAcc;
         if (anyBad & groupMask) st |= TGB_STATUS_NONFINITE;
         if (a.height_lo <= a.height_hi && mm > T(0)) {
             const double h = Oy + (double)(my / mm);
@@ -585,6 +773,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         vec_t* gs = reinterpret_cast<vec_t*>(reinterpret_cast<T*>(a.state) + (size_t)env * a.stride);
         const vec_t* ss = reinterpret_cast<const vec_t*>(sState);
         for (int i = lane; i < a.stride / VN; i += LPE) gs[i] = ss[i];
+        if (cpgOn) {
+            double* cs = a.cpg_state + (size_t)env * (3 * C + 2);
+            for (int i = lane; i < 3 * C; i += LPE) cs[i] = sX[i];
+            if (lane == 0) { cs[3 * C] = cpgUpdateTime; cs[3 * C + 1] = cpgCableTime; }
+        }
         if (lane == 0) {
             double* f = a.frame + (size_t)env * TGB_NFR;
             f[FR_O] = Ox; f[FR_O + 1] = Oy; f[FR_O + 2] = Oz;
@@ -601,7 +794,7 @@ inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, 
     int groupTWords = a.stride + 12 * lpe + 3 * a.C + a.cap_contacts * TGB_NCT * lpe;
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
-    const int groupDWords = a.ctrl_stride + 8;
+    const int groupDWords = tgb_group_double_words(a);
     size_t bytes = (size_t)(modelTWords + groupsPerBlock * groupTWords) * sizeofT;
     bytes = (bytes + 7) & ~(size_t)7;
     bytes += (size_t)groupsPerBlock * groupDWords * sizeof(double);

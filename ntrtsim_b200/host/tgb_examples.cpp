@@ -2,6 +2,7 @@
 #include "tgb_examples.h"
 
 #include <cmath>
+#include <sstream>
 
 namespace {
 
@@ -191,6 +192,149 @@ void tsTestRig::teardown() {
     notifyTeardown();
     m_muscles.clear();
     tgModel::teardown();
+}
+
+/* ---- tetrahedral spine -------------------------------------------------------------------------------------------- */
+namespace {
+double round5(double d) {
+    /* tgUtil::round(d, 5), tgUtil.h:354-359 */
+    const int m = static_cast<int>(std::pow(10.0, 5));
+    return std::floor(d * m + 0.5) / m;
+}
+std::string numbered(const std::string& s, int i) {
+    std::ostringstream ss;
+    ss << s << i;
+    return ss.str();
+}
+} // namespace
+
+TetraSpineLearningModel::TetraSpineLearningModel(std::size_t segments) : m_segments(segments) {}
+void TetraSpineLearningModel::setup(tgWorld& world) {
+    const double edge = 38.1;
+    const double height = round5(std::sqrt(3.0) / 2 * edge);
+    tgStructure tetra;
+    tetra.addNode(-edge / 2.0, 0, 0);                                         /* right */
+    tetra.addNode(edge / 2.0, 0, 0);                                          /* left */
+    tetra.addNode(0, height, 0);                                              /* top */
+    tetra.addNode(0, height / 2.0, round5(std::sqrt(3.0) / 2.0 * height));    /* front */
+    const IndexPair rods[6] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    const char* rodTags[6] = {"back bottom rod", "back right rod", "front right rod", "back left rod", "front left rod", "front top rod"};
+    for (int i = 0; i < 6; ++i) tetra.addPair(rods[i].a, rods[i].b, rodTags[i]);
+    tetra.move(btVector3(0.0, 2.0, 100.0));
+
+    tgStructure snake;
+    const btVector3 offset(0, 0, -edge * 0.75);
+    for (std::size_t i = 0; i < m_segments; ++i) {
+        tgStructure* const t = new tgStructure(tetra);
+        t->addTags(numbered("segment num", (int)i + 1));
+        t->move((btScalar)(i + 1) * offset);
+        snake.addChild(t);
+    }
+    const std::vector<tgStructure*>& children = snake.getChildren();
+    for (std::size_t i = 1; i < children.size(); ++i) {
+        const tgNodes& n0 = children[i - 1]->getNodes();
+        const tgNodes& n1 = children[i]->getNodes();
+        snake.addPair(n0[0], n1[0], "outer right muscle");
+        snake.addPair(n0[1], n1[1], "outer left muscle");
+        snake.addPair(n0[2], n1[2], "outer top muscle");
+        snake.addPair(n0[0], n1[3], "inner right muscle");
+        snake.addPair(n0[1], n1[3], "inner left muscle");
+        snake.addPair(n0[2], n1[3], "inner top muscle");
+    }
+
+    const double density = .00311, radius = 0.635, friction = 0.5;
+    const tgRod::Config rodConfig(radius, density, friction);
+    tgBuildSpec spec;
+    spec.addBuilder("rod", new tgRodInfo(rodConfig));
+    /* positional arguments as shipped (TetraSpineLearningModel.cpp:192): pretension = false, hist = 0 */
+    tgSpringCableActuator::Config muscleConfig(10000, 10, false, 0, 7000, 7.0);
+    spec.addBuilder("muscle", new tgBasicActuatorInfo(muscleConfig));
+    tgStructureInfo structureInfo(snake, spec);
+    structureInfo.buildInto(*this, world);
+
+    m_allMuscles = find<tgSpringCableActuator>(std::string("muscle"));
+    m_allSegments = find<tgModel>(std::string("segment"));
+    notifySetup();
+    tgModel::setup(world);
+}
+void TetraSpineLearningModel::step(double dt) {
+    notifyStep(dt);
+    tgModel::step(dt);
+}
+void TetraSpineLearningModel::teardown() {
+    notifyTeardown();
+    tgModel::teardown();
+    m_allMuscles.clear();
+    m_allSegments.clear();
+}
+
+tgbSpineControlConfig::tgbSpineControlConfig(int ss, int tm, int om, int param, int segnum, double ct)
+    : segmentSpan(ss), theirMuscles(tm), ourMuscles(om), params(param), segmentNumber(segnum), controlTime(ct), lowAmp(0), highAmp(30),
+      lowPhase(-1 * M_PI), highPhase(M_PI), lowFreq(0.0), highFreq(30.0) {
+    if (ss <= 0) throw std::invalid_argument("segmentSpan parameter is negative.");
+    else if (tm <= 0) throw std::invalid_argument("theirMuscles parameter is negative.");
+    else if (om <= 0) throw std::invalid_argument("Our Muscles parameter is negative.");
+    else if (param <= 0) throw std::invalid_argument("Edge parameters is negative.");
+    else if (segnum < 0) throw std::invalid_argument("Segment number is negative.");
+    else if (ct < 0.0) throw std::invalid_argument("control time is negative.");
+}
+
+void tgbSpineCpgTopology(const std::vector<tgb_cable_desc>& cables, const tgbSpineControlConfig& cfg, std::vector<int32_t>& begin,
+                         std::vector<int32_t>& target, std::vector<int32_t>& pair) {
+    const int n = (int)cables.size();
+    const int muscleSize = cfg.theirMuscles; /* edgeParams.shape()[1] */
+    begin.assign(1, 0);
+    target.clear();
+    pair.clear();
+    for (int m = 0; m < n; ++m) {
+        for (int t = 0; t < n; ++t) {
+            if (t == m) continue;
+            /* "all to all" connectivity for shared rigid bodies */
+            if (cables[m].body_a == cables[t].body_a || cables[m].body_b == cables[t].body_b || cables[m].body_a == cables[t].body_b ||
+                cables[m].body_b == cables[t].body_a) {
+                const int rp = ((m - t) / muscleSize) + 1; /* integer division: -1 behind, 0 same row, 1 ahead */
+                const int j = m % muscleSize, k = t % muscleSize;
+                if (rp < 0 || rp >= cfg.segmentSpan) throw std::runtime_error("CPG coupling outside the segment span");
+                const int lo = j > k ? k : j, hi = j > k ? j : k;
+                target.push_back(t);
+                pair.push_back((rp * cfg.theirMuscles + lo) * cfg.ourMuscles + hi);
+            }
+        }
+        begin.push_back((int32_t)target.size());
+    }
+}
+
+int tgbSpineScaleEdgeActions(const double* actions, int n_actions, const tgbSpineControlConfig& cfg, double* table) {
+    const double range = cfg.highPhase - cfg.lowPhase;
+    for (int i = 0; i < cfg.tablePairs() * 2; ++i) table[i] = 0.0;
+    int remaining = n_actions;
+    int i = 0, j = 0, k = 0;
+    while (i < cfg.segmentSpan) {
+        while (j < cfg.theirMuscles) {
+            while (k < cfg.ourMuscles) {
+                if (remaining == 0) break; /* "ran out before table populated!" */
+                if (!(i == 1 && j == k)) {
+                    const double* edgeParam = actions + 2 * (remaining - 1); /* actions.back() */
+                    double* e = table + 2 * ((i * cfg.theirMuscles + j) * cfg.ourMuscles + k);
+                    e[0] = edgeParam[0];
+                    e[1] = edgeParam[1] * (range) + cfg.lowPhase;
+                    --remaining;
+                }
+                k++;
+            }
+            j++;
+            k = j;
+        }
+        j = 0;
+        k = 0;
+        i++;
+    }
+    return n_actions - remaining;
+}
+
+void tgbSpineScaleNodeActions(const double* a, const tgbSpineControlConfig& cfg, double* out) {
+    out[0] = (a[0] * (cfg.highFreq - cfg.lowFreq)) + cfg.lowFreq;
+    out[1] = (a[1] * (cfg.highAmp - cfg.lowAmp)) + cfg.lowAmp;
 }
 
 /* ---- sine controller parameter map ---------------------------------------------------------------------- */

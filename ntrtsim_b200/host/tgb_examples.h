@@ -57,6 +57,41 @@ private:
     std::vector<tgSpringCableActuator*> m_muscles;
 };
 
+/* 3-segment tetrahedral spine of the learning examples: every tetrahedron's 6 rods auto-compound into one body, 6 cables
+   between consecutive segments (src/examples/learningSpines/TetraSpine/TetraSpineLearningModel.cpp:54-213) */
+class TetraSpineLearningModel : public tgSubject<TetraSpineLearningModel>, public tgModel {
+public:
+    explicit TetraSpineLearningModel(std::size_t segments);
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt);
+    virtual void teardown();
+    const std::vector<tgSpringCableActuator*>& getAllMuscles() const { return m_allMuscles; }
+    std::size_t getSegments() const { return m_segments; }
+    const std::vector<tgModel*>& getAllSegments() const { return m_allSegments; }
+private:
+    std::size_t m_segments;
+    std::vector<tgSpringCableActuator*> m_allMuscles;
+    std::vector<tgModel*> m_allSegments;
+};
+
+/* ---- CPG + impedance control of the spine examples, flattened for tgb_set_cpg_controller ------------------------- */
+/* BaseSpineCPGControl::Config (BaseSpineCPGControl.h:60-77) with its defaults */
+struct tgbSpineControlConfig {
+    int segmentSpan, theirMuscles, ourMuscles, params, segmentNumber;
+    double controlTime, lowAmp, highAmp, lowPhase, highPhase, lowFreq, highFreq;
+    tgbSpineControlConfig(int ss, int tm, int om, int param, int segnum = 6, double ct = 0.1);
+    int tablePairs() const { return segmentSpan * theirMuscles * ourMuscles; }
+};
+/* tgCPGActuatorControl::setConnectivity (tgCPGActuatorControl.cpp:121-173): couplings of every cable's CPG node in CSR form;
+   pair[] indexes the [segmentSpan][theirMuscles][ourMuscles] edge table. */
+void tgbSpineCpgTopology(const std::vector<tgb_cable_desc>& cables, const tgbSpineControlConfig& cfg, std::vector<int32_t>& begin,
+                         std::vector<int32_t>& target, std::vector<int32_t>& pair);
+/* BaseSpineCPGControl::scaleEdgeActions (BaseSpineCPGControl.cpp:363-434): the action list (popped from the back) fills the upper
+   triangle of the edge table. actions: [n][2] in [0,1]; table: [tablePairs()][2] (weight, phase); returns the number consumed. */
+int tgbSpineScaleEdgeActions(const double* actions, int n_actions, const tgbSpineControlConfig& cfg, double* table);
+/* BaseSpineCPGControl::scaleNodeActions (BaseSpineCPGControl.cpp:435-468): [frequency, amplitude] of controller 0 */
+void tgbSpineScaleNodeActions(const double* actions2, const tgbSpineControlConfig& cfg, double* out2);
+
 /* EscapeController::transformActions (EscapeController.cpp:142-177) + applyActions' dcOffset = 1 (:179-194):
    maps 8x4 numbers in [0,1] to amplitude / angular frequency / phase change / dc offset. out = 33 doubles
    (32 + initial length), the TGB_CTRL_ESCAPE_SINE parameter row. */

@@ -53,6 +53,11 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
             e->world = new tgWorld(tgWorld::Config(981)); /* MotorTimestep_test: default ground */
             e->dt = 0.001;
             e->model = new tsTestRig(name == "tsTestRig_kinematic");
+        } else if (name == "TetraSpine") {
+            /* AppTetraSpineLearning.cpp:48-109: tgWorld(Config(981)) with the default box ground, dt = 1e-3, 3 segments */
+            e->world = new tgWorld(tgWorld::Config(981));
+            e->dt = 0.001;
+            e->model = new TetraSpineLearningModel(3);
         } else {
             g_error = "unknown example: " + name;
             delete e;
@@ -117,6 +122,56 @@ int tgh_tree_counts(const tgh_model* m, int* n_rods, int* n_actuators) {
 
 void tgh_escape_transform_actions(const double* actions01, double initial_length, double* out33) {
     tgbEscapeTransformActions(actions01, initial_length, out33);
+}
+
+/* CPG + impedance controller of TetraSpineCPGControl flattened for tgb_set_cpg_controller
+   (AppTetraSpineLearning.cpp:77-86: Config(segmentSpan 3, 6, 6, 2, segment 1, controlTime .001);
+   TetraSpineCPGControl.cpp:58-126: impedance gains by the "outer" tag).
+   Call with NULL arrays to get the sizes: n_nodes, n_couplings, n_pairs. */
+int tgh_tetraspine_cpg(const tgh_model* m, int* n_nodes, int* n_couplings, int* n_pairs, int32_t* begin, int32_t* target, int32_t* pair,
+                       double* impedance, double* scalars /* r_const, d_min, d_max, desc, control_time, cable_step, lo, hi */,
+                       int* ints /* max_steps, score_body */) {
+    const Example* e = reinterpret_cast<const Example*>(m);
+    if (!e) return 1;
+    const tgWorldB200Impl& w = e->world->b200();
+    const tgbSpineControlConfig cfg(3, 6, 6, 2, 1, .001);
+    std::vector<int32_t> b, t, p;
+    try {
+        tgbSpineCpgTopology(w.cables(), cfg, b, t, p);
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        return 5;
+    }
+    *n_nodes = (int)w.cables().size();
+    *n_couplings = (int)t.size();
+    *n_pairs = cfg.tablePairs();
+    if (begin) std::memcpy(begin, b.data(), b.size() * sizeof(int32_t));
+    if (target) std::memcpy(target, t.data(), t.size() * sizeof(int32_t));
+    if (pair) std::memcpy(pair, p.data(), p.size() * sizeof(int32_t));
+    if (impedance) {
+        const TetraSpineLearningModel* model = dynamic_cast<const TetraSpineLearningModel*>(e->model);
+        if (!model) return 1;
+        const std::vector<tgSpringCableActuator*>& muscles = model->getAllMuscles();
+        for (std::size_t i = 0; i < muscles.size(); ++i) {
+            const bool outer = muscles[i]->hasTag("outer");
+            double* g = impedance + 4 * muscles[i]->cableIndex();
+            g[0] = 100.0; g[1] = outer ? 100.0 : 500.0; g[2] = 200.0; g[3] = outer ? 19.5 : 16.5;
+        }
+    }
+    if (scalars) {
+        scalars[0] = 20.0; scalars[1] = 0.0; scalars[2] = 5.0; scalars[3] = 2.0; scalars[4] = cfg.controlTime; scalars[5] = 1.0 / 10000.0;
+        scalars[6] = 1.0; scalars[7] = 25.0;
+    }
+    if (ints) { ints[0] = 200; ints[1] = cfg.segmentNumber; }
+    return 0;
+}
+
+/* scaleNodeActions + scaleEdgeActions for the TetraSpine configuration: node_actions[2], edge_actions[n_edge][2] in [0,1]
+   -> one parameter row [2 + 2 * n_pairs] for tgb_set_cpg_controller. Returns the number of edge actions consumed. */
+int tgh_tetraspine_param_row(const double* node_actions, const double* edge_actions, int n_edge, double* row) {
+    const tgbSpineControlConfig cfg(3, 6, 6, 2, 1, .001);
+    tgbSpineScaleNodeActions(node_actions, cfg, row);
+    return tgbSpineScaleEdgeActions(edge_actions, n_edge, cfg, row + 2);
 }
 
 /* Drop-in demonstration: the example app's main loop on the device through the host API only

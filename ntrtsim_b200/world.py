@@ -103,6 +103,19 @@ class BatchedWorld(object):
         per_env = params.shape[-1]
         capi.check(self._lib.tgb_set_controller(self._h, kind, _ptr(params), per_env, env_begin, n, 1 if broadcast else 0))
 
+    def set_cpg_controller(self, desc, params, env_begin=0, env_count=None, broadcast=False):
+        """desc: a CpgController (ntrtsim_b200.examples.tetraspine_cpg); params: [n, 2 + 2 * n_pairs] rows"""
+        n = self.n_env - env_begin if env_count is None else env_count
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        capi.check(self._lib.tgb_set_cpg_controller(self._h, C.byref(desc.desc), _ptr(params), params.shape[-1], env_begin, n,
+                                                    1 if broadcast else 0))
+
+    def get_cpg_state(self, env_begin=0, env_count=None):
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.empty((n, self.C, 3))
+        capi.check(self._lib.tgb_get_cpg_state(self._h, env_begin, n, _ptr(out)))
+        return out
+
     def set_control_input(self, inputs, dt, env_begin=0, env_count=None):
         n = self.n_env - env_begin if env_count is None else env_count
         inputs = np.ascontiguousarray(inputs, dtype=np.float64)

@@ -38,7 +38,10 @@ def load():
     lib.tgo_mark_episode_start.argtypes = [vp]
     lib.tgo_get_scores.argtypes = [vp, vp]
     lib.tgo_num_contacts.argtypes = [vp]
-    lib.tgo_rollout_batch.argtypes = [vp, vp, vp, i, vp, i, vp, i, i, vp, i, vp, dbl, i, vp, vp, dbl, i, i, vp, vp]
+    lib.tgo_rollout_batch.argtypes = [vp, vp, vp, i, vp, i, vp, i, i, vp, i, vp, dbl, i, vp, vp, dbl, i, i, vp, vp, vp, vp, vp]
+    lib.tgo_set_cpg_controller.argtypes = [vp, vp, vp, i]
+    lib.tgo_get_status.argtypes = [vp]
+    lib.tgo_get_cpg_state.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -110,10 +113,23 @@ class OracleWorld(object):
     def time(self):
         return self._lib.tgo_get_time(self._h)
 
+    def set_cpg_controller(self, desc, params):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        return self._lib.tgo_set_cpg_controller(self._h, C.byref(desc), _p(params), params.size)
+
+    def status(self):
+        return self._lib.tgo_get_status(self._h)
+
+    def cpg_state(self):
+        out = np.empty((self.C, 3))
+        self._lib.tgo_get_cpg_state(self._h, _p(out))
+        return out
+
 
 def rollout_batch(model, cfg_cls, rod_in, cable_in, dt, n_steps, ctrl_kind=0, ctrl_params=None, setup_input=None, setup_dt=0.0,
-                  n_threads=1, solver_iterations=0):
-    """n_env independent oracle environments from their own states; returns (rod_state, cable_obs)."""
+                  n_threads=1, solver_iterations=0, cpg_desc=None, want_scores=False):
+    """n_env independent oracle environments from their own states; returns (rod_state, cable_obs) or, with
+    want_scores, (rod_state, cable_obs, scores, status). cpg_desc: a ctypes tgb_cpg_desc for TGB_CTRL_CPG_IMPEDANCE."""
     lib = load()
     rod_in = None if rod_in is None else np.ascontiguousarray(rod_in, dtype=np.float64)
     cable_in = None if cable_in is None else np.ascontiguousarray(cable_in, dtype=np.float64)
@@ -128,9 +144,14 @@ def rollout_batch(model, cfg_cls, rod_in, cable_in, dt, n_steps, ctrl_kind=0, ct
     cfg = cfg_cls(model.gravity, 1, 1, 0, solver_iterations)
     rod_out = np.empty((n_env, R, 13))
     cab_out = np.empty((n_env, Cn, 4))
+    scores = np.empty((n_env, 2))
+    status = np.zeros(n_env, dtype=np.int32)
     rc = lib.tgo_rollout_batch(C.byref(cfg), C.byref(model.ground), model.bodies, R, model.shapes, len(model.shapes), model.cables, Cn,
                                ctrl_kind, _p(ctrl_params), per_env, _p(setup_input), setup_dt, n_env, _p(rod_in), _p(cable_in), dt,
-                               n_steps, n_threads, _p(rod_out), _p(cab_out))
+                               n_steps, n_threads, _p(rod_out), _p(cab_out), None if cpg_desc is None else C.byref(cpg_desc),
+                               _p(scores), _p(status))
     if rc != 0:
         raise ValueError("oracle rollout failed: %d" % rc)
+    if want_scores:
+        return rod_out, cab_out, scores, status
     return rod_out, cab_out

@@ -158,6 +158,49 @@ def main():
             ref.move_motors(i, dt_)
     ts, rods, cabs = hybrid_rollout(m, 0.0, rods0, 1e-3, steps, sine, keep=sample_steps(steps))
     np.savez_compressed(os.path.join(OUT, "escape_sine.npz"), rods0=rods0, dt=1e-3, steps=ts, rods=rods, cables=cabs, params=params)
+    # ---- 3. TetraSpine: CPGEquations + tgImpedanceController (reference code) + tgCPGActuatorControl timing --------------
+    m = nt.build_example("TetraSpine")
+    ctl = nt.tetraspine_cpg()
+    res = os.path.join(os.environ.get("NTRT_REFERENCE", "/root/reference"), "resources", "src", "learningSpines", "TetraSpine", "logs")
+
+    def nnw(name):
+        return [float(x) for x in open(os.path.join(res, name)).read().strip().split(",")]
+    node_actions = np.array(nnw("bestParameters-default_node-0.nnw"))
+    edge_actions = np.array([nnw("bestParameters-default_edge-%d.nnw" % i) for i in range(57)])
+    row = nt.tetraspine_param_rows(node_actions[None], edge_actions[None])[0]
+    cpg = ref_py.RefCPG(ctl.desc.max_steps)
+    nC = m.n_cables
+    for _ in range(nC):
+        cpg.add_node([row[0], row[0], row[1], row[1], ctl.desc.r_const, ctl.desc.d_min, ctl.desc.d_max])  # assignNodeNumber
+    for i in range(nC):                                                                                   # setConnectivity
+        ks = range(ctl.begin[i], ctl.begin[i + 1])
+        cpg.define_connections(i, [ctl.target[k] for k in ks], [row[2 + 2 * ctl.pair[k]] for k in ks], [row[3 + 2 * ctl.pair[k]] for k in ks])
+    st = {"update": 0.0, "cable": [0.0] * nC, "bogus": False, "cpg": []}
+
+    def spine(ref, s, dt_):
+        st["update"] += dt_                                        # BaseSpineCPGControl::onStep
+        if st["update"] >= ctl.desc.control_time:
+            assert cpg.update([ctl.desc.descending_command] * nC, st["update"]) == 0
+            st["update"] = 0.0
+        h = ref.get_bodies()[ctl.desc.score_body, 1]
+        if h > ctl.desc.height_hi or h < ctl.desc.height_lo:
+            st["bogus"] = True
+        vals = cpg.values()
+        for i in range(nC):                                        # tgCPGActuatorControl::onStep
+            st["cable"][i] += dt_
+            if st["cable"][i] >= ctl.desc.cable_control_step:
+                g = ctl.impedance[i]
+                ref.impedance_control(i, st["cable"][i], g[0], g[1], g[2], g[3], vals[i])
+                st["cable"][i] = 0.0
+            else:
+                ref.move_motors(i, dt_)
+        st["cpg"].append(cpg.state())
+    steps = 400
+    keep = sample_steps(steps)
+    ts, rods, cabs = hybrid_rollout(m, 0.0, m.initial_rod_state(), 1e-3, steps, spine, keep=keep)
+    np.savez_compressed(os.path.join(OUT, "tetraspine_cpg.npz"), rods0=m.initial_rod_state(), dt=1e-3, steps=ts, rods=rods, cables=cabs,
+                        node_actions=node_actions, edge_actions=edge_actions, param_row=row, cpg_states=np.array(st["cpg"])[keep],
+                        bogus=st["bogus"])
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-28s %6d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

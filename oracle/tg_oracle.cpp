@@ -6,6 +6,7 @@
  * (bodies in creation order, cables in addPair order, applyImpulse one cable at a time).
  */
 #include "tg_oracle.h"
+#include "tg_odeint.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -215,6 +216,86 @@ struct tgo_world {
     double ctrlTime = 0.0; /* EscapeController::m_totalTime */
     V3 episodeStartCom;
     int iterations = 10;
+    int status = 0;
+
+    /* ---- CPG + impedance controller (TGB_CTRL_CPG_IMPEDANCE) ---------------------------------------------- */
+    struct Cpg {
+        int nNodes = 0;
+        std::vector<int> begin, target, pair;
+        std::vector<double> impedance; /* [n][4] */
+        double rConst = 20, dMin = 0, dMax = 5, descCom = 2, controlTime = 0.001, cableStep = 1e-4, heightLo = 1, heightHi = 25;
+        int maxSteps = 200, scoreBody = 0;
+        double freqParam = 0, radiusParam = 0;
+        std::vector<double> pairs;       /* [nPairs][2] weight, phase */
+        std::vector<double> x;           /* [n][3] phi, r, rDot */
+        std::vector<double> nodeValue;   /* r cos(phi) */
+        double updateTime = 0;
+        std::vector<double> cableTime;   /* tgCPGActuatorControl::m_controlTime of every cable */
+        int numSteps = 0;
+    } cpg;
+
+    /* CPGNode::nodeEquation, CPGNode.cpp:90-101 */
+    static double nodeEquation(double d, double c0, double c1, double dMin, double dMax) {
+        if (d >= dMin && d <= dMax) return c1 * d + c0;
+        return 0;
+    }
+    /* integrate_function::operator() -> CPGEquations::updateNodes -> CPGNode::updateDTs, CPGNode.cpp:71-88 */
+    void cpgRhs(const std::vector<double>& x, std::vector<double>& dxdt) {
+        const int n = cpg.nNodes;
+        for (int i = 0; i < n; ++i) {
+            const double phi = x[3 * i], r = x[3 * i + 1], rd = x[3 * i + 2];
+            double phiDot = 2 * M_PI * nodeEquation(cpg.descCom, cpg.freqParam, cpg.freqParam, cpg.dMin, cpg.dMax);
+            for (int k = cpg.begin[i]; k < cpg.begin[i + 1]; ++k) {
+                const int j = cpg.target[k];
+                const double w = cpg.pairs[2 * cpg.pair[k]], th = cpg.pairs[2 * cpg.pair[k] + 1];
+                phiDot += w * x[3 * j + 1] * std::sin(x[3 * j] - phi - th);
+            }
+            const double rDD = cpg.rConst * (cpg.rConst / 4 * (nodeEquation(cpg.descCom, cpg.radiusParam, cpg.radiusParam, cpg.dMin, cpg.dMax) - r) - rd);
+            dxdt[3 * i] = phiDot;
+            dxdt[3 * i + 1] = rd;
+            dxdt[3 * i + 2] = rDD;
+        }
+        ++cpg.numSteps;
+    }
+    /* CPGEquations::update, CPGEquations.cpp:231-267 */
+    void cpgUpdate(double dt) {
+        double stepSize = dt <= 0.1 ? dt : 0.1;
+        cpg.numSteps = 0;
+        struct Sys {
+            tgo_world* w;
+            void operator()(const std::vector<double>& x, std::vector<double>& dxdt, double) { w->cpgRhs(x, dxdt); }
+        } sys = {this};
+        struct Obs {
+            void operator()(const std::vector<double>&, double) {}
+        } obs;
+        tg_odeint::integrate(sys, cpg.x, 0.0, dt, stepSize, obs);
+        for (int i = 0; i < cpg.nNodes; ++i) cpg.nodeValue[i] = cpg.x[3 * i + 1] * std::cos(cpg.x[3 * i]); /* CPGNode::updateNodeValues */
+        if (cpg.numSteps > cpg.maxSteps) status |= 4; /* "Inefficient CPG Parameters" */
+    }
+    /* tgCPGActuatorControl::onStep (tgCPGActuatorControl.cpp:79-100) for cable i */
+    void cpgCableControl(int i, double dt) {
+        Cable& c = cables[i];
+        cpg.cableTime[i] += dt;
+        if (cpg.cableTime[i] >= cpg.cableStep) {
+            const double ct = cpg.cableTime[i];
+            const double* g = &cpg.impedance[4 * i];
+            /* tgImpedanceController::controlTension(tgBasicActuator&, ...), tgImpedanceController.cpp:163-185 */
+            const double actualLength = cableLength(c);
+            const double vel = c.velocity;
+            double setTension = g[0] + g[1] * (actualLength - g[3]) + g[2] * (vel - cpg.nodeValue[i]);
+            setTension = std::max(0.0, setTension);
+            /* static tgTensionController::control(sca, dt, setPoint), tgTensionController.cpp:90-114 */
+            const double currentTension = cableTension(c);
+            const double delta = setTension - currentTension;
+            const double diff = delta / c.k;
+            double newLength = c.rest - diff;
+            newLength = newLength < 0.1 ? 0.1 : newLength;
+            setControlInput(c, newLength, ct);
+            cpg.cableTime[i] = 0;
+        } else {
+            moveMotors(c, dt);
+        }
+    }
 
     /* ---- cables ---------------------------------------------------------------------------- */
     V3 anchorWorld(const Body& b, const V3& local) const { return b.basis * local + b.pos; }
@@ -342,6 +423,16 @@ struct tgo_world {
             for (int i = 0; i < C; ++i) moveMotors(cables[i], dt); /* EscapeController.cpp:108-116 */
             break;
         }
+        case TGB_CTRL_CPG_IMPEDANCE: { /* BaseSpineCPGControl::onStep, BaseSpineCPGControl.cpp:253-279 */
+            cpg.updateTime += dt;
+            if (cpg.updateTime >= cpg.controlTime) {
+                cpgUpdate(cpg.updateTime);
+                cpg.updateTime = 0;
+            }
+            const double h = bodies[cpg.scoreBody].pos.y;
+            if (h > cpg.heightHi || h < cpg.heightLo) status |= 2; /* bogus */
+            break;
+        }
         default: break;
         }
     }
@@ -351,6 +442,7 @@ struct tgo_world {
         controllersStep(dt);
         for (size_t i = 0; i < cables.size(); ++i) {
             Cable& c = cables[i];
+            if (ctrlKind == TGB_CTRL_CPG_IMPEDANCE && c.actuator == TGB_ACT_BASIC) cpgCableControl((int)i, dt); /* notifyStep of the actuator */
             if (c.actuator == TGB_ACT_KINEMATIC) {
                 integrateRestLength(c, dt);
                 cableForce(c, dt);
@@ -554,6 +646,12 @@ struct tgo_world {
         for (Body& b : bodies) { b.totalForce = V3(); b.totalTorque = V3(); }
     }
 
+    /* the point whose XZ displacement is the score: the scored segment's body under the CPG controller, else the
+       mass-weighted centre of all rods (EscapeModel::getBallCOM) */
+    V3 scoreCom() const {
+        if (ctrlKind == TGB_CTRL_CPG_IMPEDANCE) return bodies[cpg.scoreBody].pos;
+        return centerOfMass();
+    }
     V3 centerOfMass() const {
         V3 s; double m = 0;
         for (const Body& b : bodies) { s += b.pos * b.mass; m += b.mass; }
@@ -634,7 +732,7 @@ void tgo_set_rod_state(tgo_world* w, const double* s) {
         b.angvel = V3(s[10], s[11], s[12]);
         b.updateInertiaTensor();
     }
-    w->episodeStartCom = w->centerOfMass();
+    w->episodeStartCom = w->scoreCom();
 }
 
 void tgo_get_rod_state(const tgo_world* w, double* s) {
@@ -662,7 +760,7 @@ void tgo_get_cable_obs(const tgo_world* w, double* o) {
         o[4 * i + 0] = c.rest;
         o[4 * i + 1] = w->cableLength(c);
         o[4 * i + 2] = w->cableTension(c);
-        o[4 * i + 3] = c.motorVel;
+        o[4 * i + 3] = c.actuator == TGB_ACT_KINEMATIC ? c.motorVel : c.velocity;
     }
 }
 
@@ -696,12 +794,41 @@ int tgo_step(tgo_world* w, double dt, int n_steps) {
 }
 
 double tgo_get_time(const tgo_world* w) { return w->time; }
-void tgo_mark_episode_start(tgo_world* w) { w->episodeStartCom = w->centerOfMass(); }
+void tgo_mark_episode_start(tgo_world* w) { w->episodeStartCom = w->scoreCom(); w->status = 0; }
 void tgo_get_scores(const tgo_world* w, double* s) {
-    V3 c = w->centerOfMass();
+    V3 c = w->scoreCom();
     double dx = c.x - w->episodeStartCom.x, dz = c.z - w->episodeStartCom.z;
     s[0] = std::sqrt(dx * dx + dz * dz);
+    if (w->ctrlKind == TGB_CTRL_CPG_IMPEDANCE && (w->status & 2)) s[0] = -1.0; /* bogus, BaseSpineCPGControl.cpp:296-299 */
     s[1] = 0.0;
+}
+int tgo_get_status(const tgo_world* w) { return w->status; }
+/* one CPGEquations::update(descCom, dt) on its own (known-answer test of the reference suite) */
+void tgo_cpg_update(tgo_world* w, double dt) { w->cpgUpdate(dt); }
+void tgo_get_cpg_state(const tgo_world* w, double* x) {
+    for (size_t i = 0; i < w->cpg.x.size(); ++i) x[i] = w->cpg.x[i];
+}
+int tgo_set_cpg_controller(tgo_world* w, const tgb_cpg_desc* d, const double* params, int n_params) {
+    if (!d || !params || n_params != 2 + 2 * d->n_pairs || d->n_nodes != (int)w->cables.size()) return TGB_ERR_INVALID_ARGUMENT;
+    tgo_world::Cpg& c = w->cpg;
+    c = tgo_world::Cpg();
+    c.nNodes = d->n_nodes;
+    c.begin.assign(d->coupling_begin, d->coupling_begin + d->n_nodes + 1);
+    c.target.assign(d->coupling_target, d->coupling_target + d->n_couplings);
+    c.pair.assign(d->coupling_pair, d->coupling_pair + d->n_couplings);
+    c.impedance.assign(d->impedance, d->impedance + 4 * d->n_nodes);
+    c.rConst = d->r_const; c.dMin = d->d_min; c.dMax = d->d_max; c.descCom = d->descending_command;
+    c.controlTime = d->control_time; c.cableStep = d->cable_control_step; c.maxSteps = d->max_steps; c.scoreBody = d->score_body;
+    c.heightLo = d->height_lo; c.heightHi = d->height_hi;
+    c.freqParam = params[0]; c.radiusParam = params[1];
+    c.pairs.assign(params + 2, params + 2 + 2 * d->n_pairs);
+    c.x.assign(3 * d->n_nodes, 0.0);
+    c.nodeValue.assign(d->n_nodes, 0.0);
+    c.cableTime.assign(d->n_nodes, 0.0);
+    w->ctrlKind = TGB_CTRL_CPG_IMPEDANCE;
+    w->status = 0;
+    w->episodeStartCom = w->scoreCom();
+    return 0;
 }
 int tgo_num_contacts(const tgo_world* w) { return (int)w->contacts.size(); }
 
@@ -709,7 +836,7 @@ int tgo_rollout_batch(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, c
                       const tgb_shape_desc* shapes, int n_shapes, const tgb_cable_desc* cables, int n_cables, int ctrl_kind,
                       const double* ctrl_params, int params_per_env, const double* setup_input, double setup_dt, int n_env,
                       const double* rod_state_in, const double* cable_state_in, double dt, int n_steps, int n_threads,
-                      double* rod_state_out, double* cable_obs_out) {
+                      double* rod_state_out, double* cable_obs_out, const tgb_cpg_desc* cpg_desc, double* scores_out, int* status_out) {
     if (!(dt > 0.0)) return TGB_ERR_INVALID_ARGUMENT;
     if (n_threads < 1) n_threads = 1;
     auto work = [&](int t) {
@@ -719,10 +846,13 @@ int tgo_rollout_batch(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, c
             if (rod_state_in) tgo_set_rod_state(w, rod_state_in + (size_t)e * n_bodies * 13);
             if (cable_state_in) tgo_set_cable_state(w, cable_state_in + (size_t)e * n_cables * 2);
             if (setup_input) tgo_set_control_input(w, setup_input, setup_dt);
-            if (ctrl_kind != TGB_CTRL_NONE) tgo_set_controller(w, ctrl_kind, ctrl_params + (size_t)e * params_per_env, params_per_env);
+            if (ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) tgo_set_cpg_controller(w, cpg_desc, ctrl_params + (size_t)e * params_per_env, params_per_env);
+            else if (ctrl_kind != TGB_CTRL_NONE) tgo_set_controller(w, ctrl_kind, ctrl_params + (size_t)e * params_per_env, params_per_env);
             tgo_step(w, dt, n_steps);
             if (rod_state_out) tgo_get_rod_state(w, rod_state_out + (size_t)e * n_bodies * 13);
             if (cable_obs_out) tgo_get_cable_obs(w, cable_obs_out + (size_t)e * n_cables * 4);
+            if (scores_out) tgo_get_scores(w, scores_out + (size_t)e * 2);
+            if (status_out) status_out[e] = tgo_get_status(w);
             tgo_destroy(w);
         }
     };

@@ -53,6 +53,11 @@ void tgo_get_cable_obs(const tgo_world* w, double* obs4);        /* [n_cables][4
 
 int  tgo_set_controller(tgo_world* w, int kind, const double* params, int n_params);
 int  tgo_set_control_input(tgo_world* w, const double* input, double dt); /* [n_cables] */
+/* CPG + impedance controller of the learningSpines examples; params = one row as in tgb_set_cpg_controller */
+int  tgo_set_cpg_controller(tgo_world* w, const tgb_cpg_desc* desc, const double* params, int n_params);
+void tgo_cpg_update(tgo_world* w, double dt);          /* one CPGEquations::update on its own */
+int  tgo_get_status(const tgo_world* w);              /* bit1 height window left (bogus), bit2 inefficient CPG */
+void tgo_get_cpg_state(const tgo_world* w, double* x); /* [n_nodes][3] phase, radius, radius rate */
 
 /* n_steps x tgSimulation::step(dt). Returns 0, or TGB_ERR_INVALID_ARGUMENT when dt <= 0. */
 int  tgo_step(tgo_world* w, double dt, int n_steps);
@@ -77,7 +82,8 @@ int tgo_rollout_batch(const tgb_world_cfg* cfg, const tgb_ground_desc* ground,
                       const double* setup_input, double setup_dt,
                       int n_env, const double* rod_state_in, const double* cable_state_in,
                       double dt, int n_steps, int n_threads,
-                      double* rod_state_out, double* cable_obs_out);
+                      double* rod_state_out, double* cable_obs_out,
+                      const tgb_cpg_desc* cpg_desc, double* scores_out, int* status_out);
 
 #ifdef __cplusplus
 }

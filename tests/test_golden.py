@@ -63,3 +63,76 @@ def test_oracle_reproduces_reference_trace(fixture, example, ctrl, param_key):
         assert np.abs(obs[:, 1] - ref[:, 2]).max() < 1e-9, (fixture, s, "length")
         assert (np.abs(obs[:, 2] - ref[:, 3]) / np.maximum(1.0, np.abs(ref[:, 3]))).max() < 1e-9, (fixture, s, "tension")
     print(fixture, "worst relative rod deviation %.2e over %d steps" % (worst, done))
+
+
+def test_oracle_tetraspine_cpg_impedance_reproduces_reference_trace():
+    """config 4: CPGEquations / CPGNode / tgImpedanceController / static tgTensionController::control executed by reference
+    code (tests/golden/tetraspine_cpg.npz) vs the oracle's restatement, shipped TetraSpine .nnw parameters injected as
+    vectors."""
+    g = np.load(os.path.join(GOLDEN, "tetraspine_cpg.npz"))
+    model = nt.build_example("TetraSpine")
+    ctl = nt.tetraspine_cpg()
+    row = nt.tetraspine_param_rows(g["node_actions"][None], g["edge_actions"][None])[0]
+    assert np.array_equal(row, g["param_row"])
+    o = oracle_py.OracleWorld(model, capi.WorldCfg)
+    o.set_rod_state(g["rods0"])
+    assert o.set_cpg_controller(ctl.desc, row) == 0
+    dt, done = float(g["dt"]), 0
+    for k, s in enumerate(g["steps"]):
+        o.step(dt, int(s) - done)
+        done = int(s)
+        rods = align_quat_sign(o.get_rod_state(), g["rods"][k])
+        obs, ref = o.get_cable_obs(), g["cables"][k]
+        # The spine bounces on the ground on stiff cables (k = 10000): round-off differences (the harness passes the pose through
+        # a quaternion every step) grow ~10x every 25 steps. Round-off-level agreement is required while that growth is below
+        # 1e-8; afterwards only the CPG (decoupled from the bodies) must keep matching exactly.
+        assert np.abs(o.cpg_state().ravel() - g["cpg_states"][k]).max() < 1e-9, s
+        if s <= 81:
+            assert np.abs(rods - g["rods"][k]).max() < 1e-8, s
+            assert np.abs(obs[:, 0] - ref[:, 0]).max() < 1e-8 and np.abs(obs[:, 1] - ref[:, 2]).max() < 1e-8, s
+            assert (np.abs(obs[:, 2] - ref[:, 3]) / np.maximum(1.0, np.abs(ref[:, 3]))).max() < 1e-6, s
+            assert np.abs(obs[:, 3] - ref[:, 4]).max() < 1e-6, s              # cable velocity m_velocity
+        else:
+            assert np.abs(rods[:, 0:3] - g["rods"][k][:, 0:3]).max() < 0.1, s
+    assert bool(o.status() & 2) == bool(g["bogus"])
+
+
+def test_cpg_known_answer_of_the_reference_test_suite():
+    """test/util/CPGEquations_test.cpp:142-173: 3 coupled nodes after 20 s are at (0, -1, 0) +- 1e-7, and 1 x 20 s equals
+    100 x 0.2 s +- 1e-7 -- here on the oracle's restated CPG + Boost.Odeint integrate()."""
+    import math
+    g = np.load(os.path.join(GOLDEN, "cpg.npz"))
+    model = nt.build_example("3_prism_noground")   # any model with >= 3 cables hosts the 3 nodes (cables 3..8 get idle nodes)
+    n = model.n_cables
+
+    def system():
+        conn = {0: ([1, 2], [1.0, 1.0], [math.pi / 2.0, 0.0]), 1: ([0, 2], [1.0, 1.0], [math.pi / 2.0, math.pi / 2.0]),
+                2: ([0, 1], [1.0, 1.0], [0.0, math.pi / 2.0])}
+        begin, target, pair, pairs = [0], [], [], []
+        for i in range(n):
+            if i in conn:
+                for t, w, p in zip(*conn[i]):
+                    target.append(t); pair.append(len(pairs)); pairs.append((w, p))
+            begin.append(len(target))
+        ctl = nt.CpgController(begin, target, pair, len(pairs), np.zeros((n, 4)), 20.0, 0.0, 5.0, 0.0, 1e9, 1e9, 5000, 0, -1e9, 1e9)
+        # frequency offset 1, scale 0 and radius offset 1, scale 0 of the test == (c0 = c1 = 1) at descending command 0
+        row = np.concatenate([[1.0, 1.0], np.array(pairs).ravel()])
+        o = oracle_py.OracleWorld(model, capi.WorldCfg)
+        assert o.set_cpg_controller(ctl.desc, row) == 0
+        return o, ctl
+    lib = oracle_py.load()
+    import ctypes as C
+    lib.tgo_cpg_update.argtypes = [C.c_void_p, C.c_double]
+    a, _ka = system()
+    lib.tgo_cpg_update(a._h, 20.0)
+    xa = a.cpg_state()
+    va = xa[:3, 1] * np.cos(xa[:3, 0])
+    assert abs(va[0]) < 1e-7 and abs(va[1] + 1.0) < 1e-7 and abs(va[2]) < 1e-7
+    b, _kb = system()
+    for k in range(100):
+        lib.tgo_cpg_update(b._h, 0.2)
+        assert np.abs(b.cpg_state()[:3].ravel() - g["trace_100x02"][k]).max() < 1e-9     # reference CPGNode/CPGEquations code
+    xb = b.cpg_state()
+    vb = xb[:3, 1] * np.cos(xb[:3, 0])
+    assert np.abs(va - vb).max() < 1e-7
+    assert np.abs(va - g["known_values_20s"]).max() < 1e-9 and np.abs(vb - g["known_values_100x02"]).max() < 1e-9

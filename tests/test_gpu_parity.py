@@ -353,3 +353,83 @@ def test_full_size_superball_sample_against_oracle():
     ro, co = oracle_rollout(model, rods[idx], cab[idx], steps, capi.TGB_CTRL_ESCAPE_SINE, params[idx])
     assert max(rod_errors(rd[idx], ro, 1.0)) < 1e-7
     assert not st.any()
+
+
+# ------------------------------------------------------------------------------------------------ config 4: TetraSpine + CPG
+def spine_inputs(n_env, seed=3456):
+    """Shipped TetraSpine parameters (tests/golden/tetraspine_cpg.npz carries the .nnw values), every member perturbed by
+    N(0, 0.03) clipped to [0, 1] like NeuroEvoMember::mutate (SURVEY.md 8d, C4)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tetraspine_cpg.npz"))
+    rng = np.random.default_rng(seed)
+    node = np.clip(g["node_actions"][None] + rng.normal(0, 0.03, size=(n_env, 2)), 0, 1)
+    edge = np.clip(g["edge_actions"][None] + rng.normal(0, 0.03, size=(n_env, 57, 2)), 0, 1)
+    node[0], edge[0] = g["node_actions"], g["edge_actions"]
+    return nt.tetraspine_param_rows(node, edge)
+
+
+@pytest.mark.parametrize("steps", [1, 10, 60])
+def test_tetraspine_cpg_f64(steps):
+    model, ctl = nt.build_example("TetraSpine"), nt.tetraspine_cpg()
+    n_env = 21
+    rows = spine_inputs(n_env)
+    rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+    cab = tiled_cables(model, n_env)
+    w = nt.BatchedWorld(model, n_env, precision="f64")
+    w.set_cpg_controller(ctl, rows)
+    w.step(model.dt, steps)
+    rd, cd, x = w.get_rod_state(), w.get_cable_obs(), w.get_cpg_state()
+    sc, st = w.scores(), w.status()
+    w.close()
+    ro, co, so, sto = oracle_py.rollout_batch(model, capi.WorldCfg, rods, cab, model.dt, steps, capi.TGB_CTRL_CPG_IMPEDANCE, rows,
+                                              cpg_desc=ctl.desc, want_scores=True, n_threads=8)
+    xo = []
+    for e in range(n_env):
+        o = oracle_py.OracleWorld(model, capi.WorldCfg)
+        o.set_cpg_controller(ctl.desc, rows[e])
+        o.step(model.dt, steps)
+        xo.append(o.cpg_state())
+    print("tetraspine f64 %d steps: rods %s, cables %.2e, cpg %.2e" % (steps, rod_errors(rd, ro, 1.0), np.abs(cd - co).max(),
+                                                                         np.abs(x - np.array(xo)).max()))
+    assert np.abs(x - np.array(xo)).max() < 1e-9           # CPG is decoupled from the bodies: tight at any horizon
+    assert max(rod_errors(rd, ro, 1.0)) < 1e-6             # stiff contact amplifies round-off ~10x / 25 steps (tests/test_golden.py)
+    assert tension_rel_error(cd, co, floor=10.0) < 1e-6
+    assert np.abs(sc - so).max() < 1e-6 and np.array_equal(st & 6, sto & 6)
+
+
+def test_tetraspine_cpg_f32_short_horizon():
+    model, ctl = nt.build_example("TetraSpine"), nt.tetraspine_cpg()
+    n_env, steps = 64, 30
+    rows = spine_inputs(n_env)
+    rods, cab = np.tile(model.initial_rod_state(), (n_env, 1, 1)), tiled_cables(model, n_env)
+    w = nt.BatchedWorld(model, n_env, precision="f32")
+    w.set_cpg_controller(ctl, rows)
+    w.step(model.dt, steps)
+    rd, cd, x = w.get_rod_state(), w.get_cable_obs(), w.get_cpg_state()
+    w.close()
+    ro, co = oracle_py.rollout_batch(model, capi.WorldCfg, rods, cab, model.dt, steps, capi.TGB_CTRL_CPG_IMPEDANCE, rows, cpg_desc=ctl.desc,
+                                     n_threads=8)
+    perr = rod_errors(rd, ro, 38.1)
+    lerr = np.abs(cd[..., 1] - co[..., 1]).max() / 38.1
+    rerr = np.abs(cd[..., 0] - co[..., 0]).max() / 38.1
+    print("tetraspine f32 %d steps: rods %s length %.2e rest %.2e" % (steps, perr, lerr, rerr))
+    assert perr[0] < F32_REL and perr[1] < F32_REL and lerr < F32_REL and rerr < F32_REL
+
+
+def test_population_evaluation_matches_oracle_scores():
+    """NeuroEvo-style evaluate(params) -> scores on the device vs the oracle, incl. a member that leaves the height window."""
+    from ntrtsim_b200.neuroevo import evaluate_population
+    model, ctl = nt.build_example("TetraSpine"), nt.tetraspine_cpg()
+    n_env, steps = 10, 50
+    rows = spine_inputs(n_env)
+    scores, status = evaluate_population(model, ctl, rows, steps, precision="f64")
+    rods, cab = np.tile(model.initial_rod_state(), (n_env, 1, 1)), tiled_cables(model, n_env)
+    _, _, so, sto = oracle_py.rollout_batch(model, capi.WorldCfg, rods, cab, model.dt, steps, capi.TGB_CTRL_CPG_IMPEDANCE, rows,
+                                            cpg_desc=ctl.desc, want_scores=True)
+    assert scores.shape == (n_env, 2) and np.abs(scores - so).max() < 1e-6
+    assert np.array_equal(status & 6, sto & 6)
+    # bogus episode: a height window the spine is outside of from the first step -> score -1 (BaseSpineCPGControl.cpp:296-299)
+    import copy
+    ctl2 = nt.tetraspine_cpg()
+    ctl2.desc.height_lo, ctl2.desc.height_hi = 100.0, 200.0
+    s2, st2 = evaluate_population(model, ctl2, rows[:3], 5, precision="f32")
+    assert np.all(s2[:, 0] == -1.0) and np.all(st2 & 2)
