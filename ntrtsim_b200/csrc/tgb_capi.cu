@@ -200,6 +200,7 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         ct[CF_K * C + c] = (T)d.stiffness; ct[CF_C * C + c] = (T)d.damping;
         ct[CF_MAXTENS * C + c] = (T)d.max_tension; ct[CF_TVEL * C + c] = (T)d.target_velocity;
         ct[CF_MINAL * C + c] = (T)d.min_actual_length; ct[CF_MINRL * C + c] = (T)d.min_rest_length;
+        ct[CF_MAXSTRETCH * C + c] = (T)(d.max_tension / d.stiffness);
         ct[CF_MRADIUS * C + c] = (T)d.motor_radius; ct[CF_MFRICTION * C + c] = (T)d.motor_friction; ct[CF_MINERTIA * C + c] = (T)d.motor_inertia;
         ci[CI_A * C + c] = d.body_a; ci[CI_B * C + c] = d.body_b;
         ci[CI_ACTUATOR * C + c] = d.actuator; ci[CI_BACKDRIVABLE * C + c] = d.backdrivable;

@@ -34,7 +34,7 @@ enum { SF_RADIUS = 0, SF_HALFLEN, SF_MARGIN, SF_POSX, SF_POSY, SF_POSZ, SF_ROT0,
 /* cable T-fields */
 enum {
     CF_LAX = 0, CF_LAY, CF_LAZ, CF_LBX, CF_LBY, CF_LBZ, CF_K, CF_C, CF_MAXTENS, CF_TVEL, CF_MINAL, CF_MINRL,
-    CF_MRADIUS, CF_MFRICTION, CF_MINERTIA, TGB_NCF
+    CF_MRADIUS, CF_MFRICTION, CF_MINERTIA, CF_MAXSTRETCH /* max tension / stiffness */, TGB_NCF
 };
 /* cable int-fields */
 enum { CI_A = 0, CI_B, CI_ACTUATOR, CI_BACKDRIVABLE, TGB_NCI };

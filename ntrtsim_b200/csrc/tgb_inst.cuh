@@ -9,19 +9,24 @@ namespace {
 
 typedef TGB_SCALAR scalar_t;
 
-template <int LPE>
-cudaError_t launch_step(const tgb_step_args& a, int threads, cudaStream_t s) {
+template <int LPE, bool CPG>
+cudaError_t launch_step_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
     const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, threads, sizeof(scalar_t));
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     const int groupsPerBlock = threads / LPE;
     const int grid = (a.n_env + groupsPerBlock - 1) / groupsPerBlock;
-    tgb::tgb_step_kernel<scalar_t, LPE><<<grid, threads, smem, s>>>(a);
+    tgb::tgb_step_kernel<scalar_t, LPE, CPG><<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
+}
+template <int LPE>
+cudaError_t launch_step(const tgb_step_args& a, int threads, cudaStream_t s) {
+    if (a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) return launch_step_impl<LPE, true>(a, threads, s);
+    return launch_step_impl<LPE, false>(a, threads, s);
 }
 
 cudaError_t step(const tgb_step_args& a, int lpe, int threads, cudaStream_t s) {

@@ -145,7 +145,7 @@ __global__ void control_input_kernel(tgb_io_args a, const double* __restrict__ i
     T pref = (T)in, rest = cs[CS_REST];
     const T stepSize = ct[CF_TVEL * a.C + c] * dt;
     const T maxTens = ct[CF_MAXTENS * a.C + c];
-    if ((L - pref) * k > maxTens) pref = L - maxTens / k;
+    if ((L - pref) * k > maxTens) pref = L - ct[CF_MAXSTRETCH * a.C + c];
     const T diff = pref - rest;
     const T fabsDiff = tabs(diff);
     if ((L > ct[CF_MINAL * a.C + c]) || (diff > T(0))) {

@@ -20,6 +20,16 @@ TGB_D float tsin(float x) { return sinf(x); }
 TGB_D double tsin(double x) { return sin(x); }
 TGB_D float tcos(float x) { return cosf(x); }
 TGB_D double tcos(double x) { return cos(x); }
+/* reciprocal / reciprocal square root / copysign: exact IEEE forms in double (the parity instrument), the fast hardware
+   approximations (MUFU + refinement, <= 2 ulp) in float (the throughput configuration) */
+TGB_D float trcp(float x) { return __fdividef(1.0f, x); }
+TGB_D double trcp(double x) { return 1.0 / x; }
+TGB_D float tdiv(float a, float b) { return __fdividef(a, b); }
+TGB_D double tdiv(double a, double b) { return a / b; }
+TGB_D float trsqrt(float x) { return rsqrtf(x); }
+TGB_D double trsqrt(double x) { return 1.0 / sqrt(x); }
+TGB_D float tcopysign(float a, float b) { return copysignf(a, b); }
+TGB_D double tcopysign(double a, double b) { return copysign(a, b); }
 
 template <typename T>
 struct V3 {
@@ -68,7 +78,7 @@ struct M3 {
     /* btMatrix3x3::setRotation */
     TGB_D static M3 fromQuat(const Q4<T>& q) {
         T d = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
-        T s = T(2) / d;
+        T s = tdiv(T(2), d);
         T xs = q.x * s, ys = q.y * s, zs = q.z * s;
         T wx = q.w * xs, wy = q.w * ys, wz = q.w * zs;
         T xx = q.x * xs, xy = q.x * ys, xz = q.x * zs;

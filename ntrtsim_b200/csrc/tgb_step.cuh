@@ -32,6 +32,8 @@
 #include "tgb_dev.h"
 #include "tgb_math.cuh"
 
+#include <type_traits>
+
 namespace tgb {
 
 template <typename T> struct Vec16;
@@ -76,6 +78,27 @@ TGB_D void integrateTransform(V3<T>& x, Q4<T>& q, const V3<T>& linvel, const V3<
     Q4<T> p = qmul(dorn, q);
     T l = tsqrt(p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w);
     q = Q4<T>(p.x / l, p.y / l, p.z / l, p.w / l);
+}
+/* Single precision: the same map with the half angle h = |w| dt / 2 <= pi/8 (the clamp above) handled by even polynomials
+   in h^2 for sin(h)/h and cos(h) (truncation < 1e-11), no square root or division on the common path, and the quaternion
+   renormalised with the hardware reciprocal square root. */
+TGB_D void integrateTransform(V3<float>& x, Q4<float>& q, const V3<float>& linvel, const V3<float>& angvel, float dt) {
+    x = x + linvel * dt;
+    const float w2 = angvel.length2();
+    const float thr = SolverConst<float>::angularMotionThreshold();
+    float h2 = w2 * (0.25f * dt * dt);         /* (|w| dt / 2)^2 */
+    float scale = 0.5f * dt;                   /* axis = angvel * sin(h)/|w| = angvel * (dt/2) * sin(h)/h */
+    if (w2 * dt * dt > thr * thr) {            /* rare: clamp the angle to pi/4 per step */
+        const float fAngle = thr / dt;
+        h2 = 0.25f * thr * thr;
+        scale = 0.5f * dt * fAngle * rsqrtf(w2);
+    }
+    const float sinc = 1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f + h2 * (-1.0f / 5040.0f + h2 * (1.0f / 362880.0f))));
+    const float cs = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f + h2 * (-1.0f / 3628800.0f)))));
+    const V3<float> axis = angvel * (scale * sinc);
+    Q4<float> p = qmul(Q4<float>(axis.x, axis.y, axis.z, cs), q);
+    const float il = rsqrtf(p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w);
+    q = Q4<float>(p.x * il, p.y * il, p.z * il, p.w * il);
 }
 
 /* btPlaneSpace1, first vector */
@@ -123,11 +146,14 @@ struct ModelView {
     TGB_D int cablei(int f, int c) const { return ci[f * C + c]; }
 };
 
-template <typename T, int LPE>
+/* CPG = the CPG + impedance controller is compiled in (a separate instantiation keeps its Dormand-Prince integrator out of the
+   register budget of the other controllers) */
+template <typename T, int LPE, bool CPG>
 __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename Vec16<T>::type vec_t;
     const int VN = Vec16<T>::N;
+    constexpr bool kFast = std::is_same<T, float>::value; /* float: reassociated sums and fast reciprocals; double: the oracle's order */
 
     const int tid = threadIdx.x;
     const int lane = tid % LPE;
@@ -148,7 +174,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     T* sModelT = reinterpret_cast<T*>(smem_raw);
     const int modelTWords = (a.model_t_words + 3) & ~3;
     const int poseWords = 12 * LPE;
-    const int jWords = 3 * C;
+    const int jWords = (kFast ? 9 : 3) * C;     /* impulse J per cable; float also publishes the torques of both ends */
     const int ctWords = a.cap_contacts * TGB_NCT * LPE;
     int groupTWords = a.stride + poseWords + jWords + ctWords;
     groupTWords = (groupTWords + 3) & ~3;
@@ -159,7 +185,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     T* sPose = sState + a.stride;              /* [12][LPE] : pos3, basis9 of each body */
     T* sJ = sPose + poseWords;                 /* [C][3] */
     T* sCt = sJ + jWords;                      /* [cap][TGB_NCT][LPE] */
-    const bool cpgOn = a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE;
+    constexpr bool cpgOn = CPG;
     const int groupDWords = tgb_group_double_words(a);
     double* sD = reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) + grp * groupDWords;
     double* sCtrl = sD;                        /* controller parameter row */
@@ -193,6 +219,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     M.bi = sModelI; M.ci = M.bi + TGB_NBI * R; M.inc = M.ci + TGB_NCI * C;
 
     const T dt = (T)a.dt;
+    const T invDt = (T)(1.0 / a.dt);
     const V3<T> gn((T)a.gn[0], (T)a.gn[1], (T)a.gn[2]);
     const int ctrlKind = a.ctrl_kind;
 
@@ -390,18 +417,28 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             V3<T> extAng(T(0), T(0), T(0));
             if (gyro) {
                 /* btRigidBody::computeGyroscopicForce, explicit, clamped at maxGyroscopicForce */
-                M3<T> Iw = b.B.conjugateDiag(inertia);
-                V3<T> tmp = Iw * b.w;
-                V3<T> gf = b.w.cross(tmp);
-                T l2 = gf.length2();
-                if (l2 > SolverConst<T>::maxGyro() * SolverConst<T>::maxGyro()) gf *= T(1) / tsqrt(l2) * SolverConst<T>::maxGyro();
-                extAng -= b.Iinv.tmul(gf) * dt;
+                if (kFast) {
+                    /* same quantity evaluated in the body frame: Iinv^T (w x (I_w w)) = B (invI o (wl x (I o wl))) */
+                    const V3<T> wl = b.B.tmul(b.w);
+                    V3<T> gfl = wl.cross(V3<T>(inertia.x * wl.x, inertia.y * wl.y, inertia.z * wl.z));
+                    const T l2 = gfl.length2();
+                    if (l2 > SolverConst<T>::maxGyro() * SolverConst<T>::maxGyro()) gfl *= trsqrt(l2) * SolverConst<T>::maxGyro();
+                    extAng -= (b.B * V3<T>(invI.x * gfl.x, invI.y * gfl.y, invI.z * gfl.z)) * dt;
+                } else {
+                    M3<T> Iw = b.B.conjugateDiag(inertia);
+                    V3<T> tmp = Iw * b.w;
+                    V3<T> gf = b.w.cross(tmp);
+                    T l2 = gf.length2();
+                    if (l2 > SolverConst<T>::maxGyro() * SolverConst<T>::maxGyro()) gf *= T(1) / tsqrt(l2) * SolverConst<T>::maxGyro();
+                    extAng -= b.Iinv.tmul(gf) * dt;
+                }
             }
             const V3<T> Vf((T)Vx, (T)Vy, (T)Vz);
             const V3<T> linvel = b.v + Vf; /* world linear velocity */
 
             /* ---- ground contact manifold (analytic cylinder rim points against the ground surface) ---- */
             int nc = 0;
+            bool anyPen = false;
             if (a.ground_kind != TGB_GROUND_EMPTY) {
                 /* signed height of the frame origin above the surface, formed in double */
                 const T originHeight = (T)(a.gn[0] * Ox + a.gn[1] * Oy + a.gn[2] * Oz - a.goff);
@@ -418,6 +455,9 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                     const T na = gn.dot(axisDir);
                     const V3<T> perp = -(gn - axisDir * na);
                     const T pl = perp.length();
+                    /* the lowest rim point is at n.c - |n.a| hc - rc |perp| (exact arithmetic): a shape clearly above the
+                       contact band contributes nothing (the 1e-3 slack covers round-off; no result changes) */
+                    if (((gn.dot(c) + originHeight) - margin) - tabs(na) * hc - rc * pl > SolverConst<T>::breakingThreshold() + T(1e-3)) continue;
                     V3<T> u;
                     if (pl > T(1e-9)) u = perp / pl;
                     else u = col0;
@@ -435,7 +475,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                                 const V3<T> rxn = r.cross(gn);
                                 const V3<T> angN = b.Iinv * rxn;
                                 const T denom = invMass + gn.dot(angN.cross(r));
-                                const T invDiagN = T(1) / denom;
+                                const T invDiagN = trcp(denom);
                                 const V3<T> vel = linvel + b.w.cross(r);
                                 const T relVel = gn.dot(vel);
                                 T restitution = restitutionCombined * -relVel;
@@ -443,7 +483,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                                 const V3<T> lat = vel - gn * relVel;
                                 const T lat2 = lat.length2();
                                 V3<T> t;
-                                if (lat2 > epsilonOf<T>()) t = lat * (T(1) / tsqrt(lat2));
+                                if (lat2 > epsilonOf<T>()) t = lat * (kFast ? trsqrt(lat2) : T(1) / tsqrt(lat2));
                                 else t = planeSpace1(gn);
                                 const T velDotN = gn.dot(linvel + extLin) + rxn.dot(b.w + extAng);
                                 T velocityError = restitution - velDotN;
@@ -451,17 +491,17 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                                 T erp = SolverConst<T>::erp2();
                                 if (penetration > SolverConst<T>::splitThreshold()) erp = SolverConst<T>::erp();
                                 T positionalError = T(0);
-                                if (penetration > T(0)) velocityError -= penetration / dt;
-                                else positionalError = -penetration * erp / dt;
+                                if (penetration > T(0)) velocityError -= tdiv(penetration, dt);
+                                else positionalError = tdiv(-penetration * erp, dt);
                                 const T penetrationImpulse = positionalError * invDiagN;
                                 const T velocityImpulse = velocityError * invDiagN;
                                 T rhsN, rhsPen;
                                 if (penetration > SolverConst<T>::splitThreshold()) { rhsN = penetrationImpulse + velocityImpulse; rhsPen = T(0); }
-                                else { rhsN = velocityImpulse; rhsPen = penetrationImpulse; }
+                                else { rhsN = velocityImpulse; rhsPen = penetrationImpulse; anyPen = anyPen || rhsPen != T(0); }
                                 const V3<T> rxt = r.cross(t);
                                 const V3<T> angT = b.Iinv * rxt;
                                 const T denomT = invMass + t.dot(angT.cross(r));
-                                const T invDiagT = T(1) / denomT;
+                                const T invDiagT = trcp(denomT);
                                 const T relT = t.dot(linvel + extLin) + rxt.dot(b.w);
                                 const T rhsT = (T(0) - relT) * invDiagT;
                                 CT(nc, CT_RXN + 0) = rxn.x; CT(nc, CT_RXN + 1) = rxn.y; CT(nc, CT_RXN + 2) = rxn.z;
@@ -483,6 +523,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
             if (nc > 0) {
+                if (anyPen)
                 for (int it = 0; it < a.iterations; ++it) {
                     for (int c = 0; c < nc; ++c) {
                         const T rhsPen = CT(c, CT_RHSPEN);
@@ -595,7 +636,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { Ba.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ia]; Bb.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ib]; }
             /* anchors: tgBulletSpringCableAnchor.cpp:83-87 */
-            const V3<T> p1 = Ba * la + xa, p2 = Bb * lb + xb;
+            const V3<T> ra = Ba * la, rb = Bb * lb;
+            const V3<T> p1 = ra + xa, p2 = rb + xb;
             const V3<T> dist = p2 - p1;
             const T L = dist.length();
 
@@ -607,11 +649,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             auto moveMotors = [&](T dtm) {
                 const T stepSize = M.cable(CF_TVEL, c) * dtm;
                 const T maxTens = M.cable(CF_MAXTENS, c);
-                if ((L - pref) * k > maxTens) pref = L - maxTens / k;
+                if ((L - pref) * k > maxTens) pref = L - M.cable(CF_MAXSTRETCH, c);
                 const T diff = pref - rest;
                 const T fabsDiff = tabs(diff);
                 if ((L > M.cable(CF_MINAL, c)) || (diff > T(0))) {
-                    if (fabsDiff > stepSize) rest += (diff / fabsDiff) * stepSize;
+                    if (fabsDiff > stepSize) rest += tcopysign(stepSize, diff); /* (diff / |diff|) * stepSize, exactly */
                     else rest += diff;
                 }
                 const T minRL = M.cable(CF_MINRL, c);
@@ -696,11 +738,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             }
 
             /* ---- tgBulletSpringCable::calculateAndApplyForce, tgBulletSpringCable.cpp:90-141 ---- */
-            const V3<T> unit = dist / L;
+            const V3<T> unit = dist * trcp(L);
             const T stretch = L - rest;
             T magnitude = k * stretch;
             const T deltaStretch = L - prev;
-            const T velocity = deltaStretch / dt;
+            const T velocity = kFast ? deltaStretch * invDt : deltaStretch / dt;
             T damping = damp * velocity;
             if (tabs(magnitude) * T(1) < tabs(damping)) damping = (damping > T(0) ? magnitude * T(1) : -magnitude * T(1));
             magnitude += damping;
@@ -708,7 +750,14 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             if (L > rest) force = unit * magnitude;
             prev = L;
             const V3<T> J = force * dt;
-            sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
+            if (kFast) {
+                /* also publish the torque of the impulse about both bodies' centres: r x J and r x (-J) */
+                const V3<T> ta = ra.cross(J), tb = J.cross(rb);
+                T* o = sJ + c * 9;
+                o[0] = J.x; o[1] = J.y; o[2] = J.z; o[3] = ta.x; o[4] = ta.y; o[5] = ta.z; o[6] = tb.x; o[7] = tb.y; o[8] = tb.z;
+            } else {
+                sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
+            }
             cs[CS_REST] = rest; cs[CS_PREV] = prev; cs[CS_PREF] = pref;
             cs[CS_MOTORVEL] = actuator == TGB_ACT_KINEMATIC ? motorVel : velocity;
         }
@@ -716,17 +765,30 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
         /* ---- applyImpulse of every incident cable end, in cable order (btRigidBody::applyImpulse) ---- */
         if (dynamic) {
-            for (int i = incBegin; i < incBegin + incCount; ++i) {
-                const int code = M.inc[i];
-                const int c = code & 0xffffff;
-                const bool sideB = (code >> 24) != 0;
-                V3<T> J(sJ[c * 3 + 0], sJ[c * 3 + 1], sJ[c * 3 + 2]);
-                const V3<T> local = sideB ? V3<T>(M.cable(CF_LBX, c), M.cable(CF_LBY, c), M.cable(CF_LBZ, c))
-                                          : V3<T>(M.cable(CF_LAX, c), M.cable(CF_LAY, c), M.cable(CF_LAZ, c));
-                if (sideB) J = -J;
-                const V3<T> rel = (b.B * local + b.x) - b.x;
-                b.v += J * invMass;
-                b.w += b.Iinv * rel.cross(J);
+            if (kFast) {
+                /* sum the impulses and torques of the incident cable ends first, then one multiplication each */
+                V3<T> sumJ(T(0), T(0), T(0)), sumT(T(0), T(0), T(0));
+                for (int i = incBegin; i < incBegin + incCount; ++i) {
+                    const int code = M.inc[i];
+                    const T* o = sJ + (code & 0xffffff) * 9;
+                    if ((code >> 24) != 0) { sumJ -= V3<T>(o[0], o[1], o[2]); sumT += V3<T>(o[6], o[7], o[8]); }
+                    else { sumJ += V3<T>(o[0], o[1], o[2]); sumT += V3<T>(o[3], o[4], o[5]); }
+                }
+                b.v += sumJ * invMass;
+                b.w += b.Iinv * sumT;
+            } else {
+                for (int i = incBegin; i < incBegin + incCount; ++i) {
+                    const int code = M.inc[i];
+                    const int c = code & 0xffffff;
+                    const bool sideB = (code >> 24) != 0;
+                    V3<T> J(sJ[c * 3 + 0], sJ[c * 3 + 1], sJ[c * 3 + 2]);
+                    const V3<T> local = sideB ? V3<T>(M.cable(CF_LBX, c), M.cable(CF_LBY, c), M.cable(CF_LBZ, c))
+                                              : V3<T>(M.cable(CF_LAX, c), M.cable(CF_LAY, c), M.cable(CF_LAZ, c));
+                    if (sideB) J = -J;
+                    const V3<T> rel = (b.B * local + b.x) - b.x;
+                    b.v += J * invMass;
+                    b.w += b.Iinv * rel.cross(J);
+                }
             }
         }
     }
@@ -791,7 +853,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
     const int groupsPerBlock = threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
-    int groupTWords = a.stride + 12 * lpe + 3 * a.C + a.cap_contacts * TGB_NCT * lpe;
+    int groupTWords = a.stride + 12 * lpe + (sizeofT == 4 ? 9 : 3) * a.C + a.cap_contacts * TGB_NCT * lpe;
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
     const int groupDWords = tgb_group_double_words(a);
