@@ -155,7 +155,7 @@ def run_reference(args):
         build_all()
     cores = os.cpu_count() or 1
     H = args.sim_steps
-    sample_env = min(args.envs, cores * 8)
+    sample_env = min(args.envs, cores * 32)
     model, rods, cab, ctrl, params, _ = build_workload(args.workload, sample_env, SEED)
     for _ in range(args.warmup):
         cpu_port_rate(model, rods, cab, ctrl, params, H, sample_env, cores)

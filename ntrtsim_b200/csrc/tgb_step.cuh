@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     T* sModelT = reinterpret_cast<T*>(smem_raw);
     const int modelTWords = (a.model_t_words + 3) & ~3;
     const int poseWords = 12 * LPE;
-    const int jWords = (kFast ? 9 : 3) * C;     /* impulse J per cable; float also publishes the torques of both ends */
+    const int jWords = (kFast ? 12 : 3) * C;    /* impulse J per cable; float publishes (J, torque) for end A and (-J, torque) for end B */
     const int ctWords = a.cap_contacts * TGB_NCT * LPE;
     int groupTWords = a.stride + poseWords + jWords + ctWords;
     groupTWords = (groupTWords + 3) & ~3;
@@ -463,9 +463,18 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                     else u = col0;
                     const V3<T> wdir = axisDir.cross(u);
                     int count = 0;
+                    /* heights of the rim points in closed form, used only to skip points that are clearly out of the contact
+                       band before any vector work (same 1e-3 slack as above; accepted points still pass the exact test) */
+                    const T hCentre = (gn.dot(c) + originHeight) - margin;
+                    const T hu = rc * gn.dot(u), hw = rc * gn.dot(wdir);
+                    const T skipAbove = SolverConst<T>::breakingThreshold() + T(1e-3);
                     for (int e = 0; e < 2 && count < 4; ++e) {
+                        const T hEnd = hCentre + (e == 0 ? -hc : hc) * na;
+                        if (hEnd - tabs(hu) - tabs(hw) > skipAbove) continue;
                         const V3<T> ce = c + axisDir * (e == 0 ? -hc : hc);
                         for (int k = 0; k < 4 && count < 4; ++k) {
+                            const T hk = hEnd + ((k == 0) ? hu : (k == 1) ? hw : (k == 2) ? -hu : -hw);
+                            if (hk > skipAbove) continue;
                             const V3<T> dir = (k == 0) ? u : (k == 1) ? wdir : (k == 2) ? -u : -wdir;
                             const V3<T> pc = ce + dir * rc;
                             const T dist = (gn.dot(pc) + originHeight) - margin;
@@ -522,7 +531,68 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
-            if (nc > 0) {
+            if (nc > 0 && nc <= 2) {
+                /* one or two contact points (a rod touching with one rim point or lying on a rim line): the rows are read into
+                   registers once and all iterations run there; same operations in the same order as the general path below */
+                T rxn[2][3], angN[2][3], invDiagN[2], rhsN[2], rhsPen[2], lamN[2], lamPush[2];
+                T tt[2][3], rxt[2][3], angT[2][3], invDiagT[2], rhsT[2], lamT[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int cc = c < nc ? c : 0;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        rxn[c][j] = CT(cc, CT_RXN + j); angN[c][j] = CT(cc, CT_ANGN + j);
+                        tt[c][j] = CT(cc, CT_T + j); rxt[c][j] = CT(cc, CT_RXT + j); angT[c][j] = CT(cc, CT_ANGT + j);
+                    }
+                    invDiagN[c] = CT(cc, CT_INVDIAGN); rhsN[c] = CT(cc, CT_RHSN); rhsPen[c] = CT(cc, CT_RHSPEN);
+                    invDiagT[c] = CT(cc, CT_INVDIAGT); rhsT[c] = CT(cc, CT_RHST);
+                    lamN[c] = T(0); lamPush[c] = T(0); lamT[c] = T(0);
+                }
+                if (anyPen)
+                    for (int it = 0; it < a.iterations; ++it) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (c >= nc || rhsPen[c] == T(0)) continue;
+                            T delta = rhsPen[c];
+                            const T dv = gn.dot(push) + (rxn[c][0] * turn.x + rxn[c][1] * turn.y + rxn[c][2] * turn.z);
+                            delta -= dv * invDiagN[c];
+                            const T sum = lamPush[c] + delta;
+                            if (sum < T(0)) { delta = -lamPush[c]; lamPush[c] = T(0); }
+                            else lamPush[c] = sum;
+                            push += gn * (invMass * delta);
+                            turn += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
+                        }
+                    }
+                for (int it = 0; it < a.iterations; ++it) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c >= nc) continue;
+                        T delta = rhsN[c];
+                        const T dv = gn.dot(dLin) + (rxn[c][0] * dAng.x + rxn[c][1] * dAng.y + rxn[c][2] * dAng.z);
+                        delta -= dv * invDiagN[c];
+                        const T sum = lamN[c] + delta;
+                        if (sum < T(0)) { delta = -lamN[c]; lamN[c] = T(0); }
+                        else lamN[c] = sum;
+                        dLin += gn * (invMass * delta);
+                        dAng += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c >= nc || !(lamN[c] > T(0))) continue;
+                        const V3<T> t(tt[c][0], tt[c][1], tt[c][2]);
+                        const T lo = -mu * lamN[c], hi = mu * lamN[c];
+                        T delta = rhsT[c];
+                        const T dv = t.dot(dLin) + (rxt[c][0] * dAng.x + rxt[c][1] * dAng.y + rxt[c][2] * dAng.z);
+                        delta -= dv * invDiagT[c];
+                        const T sum = lamT[c] + delta;
+                        if (sum < lo) { delta = lo - lamT[c]; lamT[c] = lo; }
+                        else if (sum > hi) { delta = hi - lamT[c]; lamT[c] = hi; }
+                        else lamT[c] = sum;
+                        dLin += t * (invMass * delta);
+                        dAng += V3<T>(angT[c][0], angT[c][1], angT[c][2]) * delta;
+                    }
+                }
+            } else if (nc > 0) {
                 if (anyPen)
                 for (int it = 0; it < a.iterations; ++it) {
                     for (int c = 0; c < nc; ++c) {
@@ -628,6 +698,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             const V3<T> la(M.cable(CF_LAX, c), M.cable(CF_LAY, c), M.cable(CF_LAZ, c));
             const V3<T> lb(M.cable(CF_LBX, c), M.cable(CF_LBY, c), M.cable(CF_LBZ, c));
             const T k = M.cable(CF_K, c), damp = M.cable(CF_C, c);
+            const T cTVel = M.cable(CF_TVEL, c), cMaxTens = M.cable(CF_MAXTENS, c), cMaxStretch = M.cable(CF_MAXSTRETCH, c);
+            const T cMinAL = M.cable(CF_MINAL, c), cMinRL = M.cable(CF_MINRL, c);
             V3<T> xa(sPose[0 * LPE + ia], sPose[1 * LPE + ia], sPose[2 * LPE + ia]);
             V3<T> xb(sPose[0 * LPE + ib], sPose[1 * LPE + ib], sPose[2 * LPE + ib]);
             M3<T> Ba, Bb;
@@ -647,17 +719,15 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
             /* tgBasicActuator::moveMotors, tgBasicActuator.cpp:170-225 */
             auto moveMotors = [&](T dtm) {
-                const T stepSize = M.cable(CF_TVEL, c) * dtm;
-                const T maxTens = M.cable(CF_MAXTENS, c);
-                if ((L - pref) * k > maxTens) pref = L - M.cable(CF_MAXSTRETCH, c);
+                const T stepSize = cTVel * dtm;
+                if ((L - pref) * k > cMaxTens) pref = L - cMaxStretch;
                 const T diff = pref - rest;
                 const T fabsDiff = tabs(diff);
-                if ((L > M.cable(CF_MINAL, c)) || (diff > T(0))) {
+                if ((L > cMinAL) || (diff > T(0))) {
                     if (fabsDiff > stepSize) rest += tcopysign(stepSize, diff); /* (diff / |diff|) * stepSize, exactly */
                     else rest += diff;
                 }
-                const T minRL = M.cable(CF_MINRL, c);
-                rest = (rest > minRL) ? rest : minRL;
+                rest = (rest > cMinRL) ? rest : cMinRL;
             };
 
             /* ---- model-level controllers (run before the children step) ---- */
@@ -753,8 +823,9 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             if (kFast) {
                 /* also publish the torque of the impulse about both bodies' centres: r x J and r x (-J) */
                 const V3<T> ta = ra.cross(J), tb = J.cross(rb);
-                T* o = sJ + c * 9;
-                o[0] = J.x; o[1] = J.y; o[2] = J.z; o[3] = ta.x; o[4] = ta.y; o[5] = ta.z; o[6] = tb.x; o[7] = tb.y; o[8] = tb.z;
+                T* o = sJ + c * 12;
+                o[0] = J.x; o[1] = J.y; o[2] = J.z; o[3] = ta.x; o[4] = ta.y; o[5] = ta.z;
+                o[6] = -J.x; o[7] = -J.y; o[8] = -J.z; o[9] = tb.x; o[10] = tb.y; o[11] = tb.z;
             } else {
                 sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
             }
@@ -770,9 +841,9 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 V3<T> sumJ(T(0), T(0), T(0)), sumT(T(0), T(0), T(0));
                 for (int i = incBegin; i < incBegin + incCount; ++i) {
                     const int code = M.inc[i];
-                    const T* o = sJ + (code & 0xffffff) * 9;
-                    if ((code >> 24) != 0) { sumJ -= V3<T>(o[0], o[1], o[2]); sumT += V3<T>(o[6], o[7], o[8]); }
-                    else { sumJ += V3<T>(o[0], o[1], o[2]); sumT += V3<T>(o[3], o[4], o[5]); }
+                    const T* o = sJ + (code & 0xffffff) * 12 + (code >> 24) * 6;
+                    sumJ += V3<T>(o[0], o[1], o[2]);
+                    sumT += V3<T>(o[3], o[4], o[5]);
                 }
                 b.v += sumJ * invMass;
                 b.w += b.Iinv * sumT;
@@ -853,7 +924,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
     const int groupsPerBlock = threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
-    int groupTWords = a.stride + 12 * lpe + (sizeofT == 4 ? 9 : 3) * a.C + a.cap_contacts * TGB_NCT * lpe;
+    int groupTWords = a.stride + 12 * lpe + (sizeofT == 4 ? 12 : 3) * a.C + a.cap_contacts * TGB_NCT * lpe;
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
     const int groupDWords = tgb_group_double_words(a);
