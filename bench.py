@@ -343,9 +343,9 @@ def main():
             # calibrate, then size the sample (whole batch, H x reps sim steps) for ~10-15 s of CPU work
             cal_env = min(n_env, cores * 2)
             rate, _ = cpu_port_rate(model, rods, cab, ctrl, params, min(H, 200), cal_env, cores)
-            sample_env = int(min(n_env, max(cores, rate * 12.0 / H)))
+            sample_env = int(min(n_env, max(cores, rate * 20.0 / H)))
             sample_env = max(cores, sample_env // cores * cores)
-            reps = int(max(1, min(50, rate * 12.0 / (sample_env * H))))
+            reps = int(max(1, min(50, rate * 20.0 / (sample_env * H))))
             rate, secs = cpu_port_rate(model, rods, cab, ctrl, params, H * reps, sample_env, cores)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d envs x %d sim steps of the same workload, %d threads, %.1f s (FP64 CPU restatement of the "
