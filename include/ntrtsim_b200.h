@@ -230,6 +230,13 @@ tgb_status tgb_set_control_input(tgb_world* w, int32_t env_begin, int32_t env_co
 tgb_status tgb_step(tgb_world* w, double dt, int32_t n_steps);
 tgb_status tgb_sync(tgb_world* w);
 
+/* The two halves of one tgSimulation::step(dt), for callers that run host-side observers between them exactly where the
+   reference runs them: tgb_step_world = tgWorld::step (src/core/tgSimulation.cpp:205, src/core/tgWorld.cpp:119-130);
+   tgb_step_models = the models' step (tgSimulation.cpp:208-211): device-side controller, motors, cable forces.
+   tgb_step(w, dt, 1) == tgb_step_world(w, dt) followed by tgb_step_models(w, dt). */
+tgb_status tgb_step_world(tgb_world* w, double dt);
+tgb_status tgb_step_models(tgb_world* w, double dt);
+
 /* Host-buffer round trip in one call: upload rod+cable state, step, download rod state + cable observations.
    This is the reference-facing end-to-end path (bench.py "e2e"). Buffers as in the set/get calls, all envs. */
 tgb_status tgb_rollout_host(tgb_world* w, const double* rod_state_in, const double* cable_rest_prev_in,

@@ -65,7 +65,7 @@ class TgbError(RuntimeError):
 ABI_SYMBOLS = [
     "tgb_abi_version", "tgb_last_error", "tgb_device_count", "tgb_create", "tgb_destroy", "tgb_add_model_flat",
     "tgb_finalize", "tgb_set_cpg_controller", "tgb_get_cpg_state", "tgb_num_bodies", "tgb_num_cables", "tgb_num_envs", "tgb_set_rod_state", "tgb_get_rod_state",
-    "tgb_set_cable_state", "tgb_get_cable_obs", "tgb_set_controller", "tgb_set_control_input", "tgb_step", "tgb_sync",
+    "tgb_set_cable_state", "tgb_get_cable_obs", "tgb_set_controller", "tgb_set_control_input", "tgb_step", "tgb_step_world", "tgb_step_models", "tgb_sync",
     "tgb_rollout_host", "tgb_get_time", "tgb_get_status", "tgb_mark_episode_start", "tgb_get_scores",
     "tgb_scores_device_ptr", "tgb_step_timed", "tgb_launch_count", "tgb_launch_geometry", "tgb_set_lanes_per_env",
     "tgb_set_block_threads", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
@@ -115,6 +115,8 @@ def load():
     lib.tgb_set_cpg_controller.argtypes = [_vp, C.POINTER(CpgDesc), _vp, _i32, _i32, _i32, _i32]
     lib.tgb_step.argtypes = [_vp, C.c_double, _i32]
     lib.tgb_sync.argtypes = [_vp]
+    lib.tgb_step_world.argtypes = [_vp, C.c_double]
+    lib.tgb_step_models.argtypes = [_vp, C.c_double]
     lib.tgb_rollout_host.argtypes = [_vp, _vp, _vp, C.c_double, _i32, _vp, _vp]
     lib.tgb_get_time.argtypes = [_vp, _dp]
     lib.tgb_get_status.argtypes = [_vp, _i32, _i32, _vp]
@@ -158,6 +160,8 @@ def load_host():
     h.tgh_escape_transform_actions.restype = None
     h.tgh_run_example.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp]
     h.tgh_run_example.restype = C.c_int
+    h.tgh_run_example_stepwise.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    h.tgh_run_example_stepwise.restype = C.c_int
     h.tgh_tetraspine_cpg.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _vp, _vp, _vp, _vp]
     h.tgh_tetraspine_param_row.argtypes = [_vp, _vp, C.c_int, _vp]
     _host = h

@@ -215,6 +215,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.state = w->d_state; a.frame = w->d_frame; a.ctrl = w->ctrlKind != TGB_CTRL_NONE ? w->d_ctrl : nullptr; a.status = w->d_status;
     a.model_t = w->d_model_t; a.model_i = w->d_model_i;
     a.n_env = w->cfg.n_env; a.n_steps = nSteps;
+    a.phases = 3;
     a.R = w->R; a.C = w->C; a.S = w->S; a.n_inc = w->nInc;
     a.stride = w->stride; a.cap_contacts = w->capContacts; a.frame_body = w->frameBody;
     a.ctrl_kind = w->ctrlKind; a.ctrl_stride = w->ctrlKind != TGB_CTRL_NONE ? w->ctrlStride : 0;
@@ -237,12 +238,13 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     return a;
 }
 
-tgb_status launchStep(tgb_world* w, double dt, int nSteps) {
-    const tgb_step_args a = stepArgs(w, dt, nSteps);
+tgb_status launchStep(tgb_world* w, double dt, int nSteps, int phases = 3) {
+    tgb_step_args a = stepArgs(w, dt, nSteps);
+    a.phases = phases;
     cudaError_t e = w->ops->step(a, w->lanes, w->threads, w->stream);
     if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
     w->launches += 1;
-    w->time += dt * nSteps;
+    if (phases & 1) w->time += dt * nSteps;
     return TGB_OK;
 }
 
@@ -664,6 +666,18 @@ tgb_status tgb_step(tgb_world* w, double dt, int32_t n_steps) {
     if (n_steps < 0) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_step: negative step count");
     if (n_steps == 0) return TGB_OK;
     return launchStep(w, dt, n_steps);
+}
+
+tgb_status tgb_step_world(tgb_world* w, double dt) {
+    TGB_NEED_FINAL(w);
+    if (!(dt > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "dt is not positive"); /* tgWorld.cpp:121-124 */
+    return launchStep(w, dt, 1, 1);
+}
+
+tgb_status tgb_step_models(tgb_world* w, double dt) {
+    TGB_NEED_FINAL(w);
+    if (!(dt > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "dt is not positive."); /* tgBasicActuator.cpp:101-104 */
+    return launchStep(w, dt, 1, 2);
 }
 
 tgb_status tgb_sync(tgb_world* w) {

@@ -409,9 +409,10 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         __syncwarp();
     };
 
+    const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
     for (int step = 0; step < a.n_steps; ++step) {
         /* =============================== world step (tgSimulation.cpp:205) =============================== */
-        if (dynamic) {
+        if (dynamic && doWorld) {
             /* applyGravity + solver-body external impulses */
             V3<T> extLin(T(0), (gfy * invMass) * dt, T(0));
             V3<T> extAng(T(0), T(0), T(0));
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
 
         /* ---- env frame: advance the origin with the frame velocity, then re-centre on the frame body ---- */
-        if (frameMoves) {
+        if (frameMoves && doWorld) {
             Ox += Vx * a.dt; Oy += Vy * a.dt; Oz += Vz * a.dt;
             const int src = groupLane0 + a.frame_body;
             const T sx = __shfl_sync(fullMask, b.x.x, src), sy = __shfl_sync(fullMask, b.x.y, src), sz = __shfl_sync(fullMask, b.x.z, src);
@@ -673,6 +674,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         __syncwarp();
 
         /* =============================== models step (tgSimulation.cpp:208-211) =============================== */
+        if (!doModels) continue; /* warp-uniform: a world-half-only launch (host observers run between the halves) */
         if (ctrlKind == TGB_CTRL_ESCAPE_SINE) ctrlTime += a.dt; /* EscapeController::m_totalTime */
         bool cpgCableControl = false;
         double cpgCableDt = 0.0;

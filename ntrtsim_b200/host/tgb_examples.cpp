@@ -186,6 +186,9 @@ void tsTestRig::setup(tgWorld& world) {
 void tsTestRig::step(double dt) {
     if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
     notifyStep(dt);
+    /* tsTestRig.cpp:181-188 */
+    if (m_kinematic) m_muscles[0]->setControlInput(-580.0);
+    else m_muscles[0]->setControlInput(5.0, dt);
     tgModel::step(dt);
 }
 void tsTestRig::teardown() {

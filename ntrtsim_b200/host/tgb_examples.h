@@ -15,6 +15,7 @@ public:
     virtual void setup(tgWorld& world);
     virtual void step(double dt);
     virtual void teardown();
+    virtual bool stepsOnHost() const { return numObservers() > 0; } /* model-level observers run on the host every step */
     const std::vector<tgSpringCableActuator*>& getAllActuators() const { return m_actuators; }
 private:
     std::vector<tgSpringCableActuator*> m_actuators;
@@ -27,6 +28,7 @@ public:
     virtual void setup(tgWorld& world);
     virtual void step(double dt);
     virtual void teardown();
+    virtual bool stepsOnHost() const { return numObservers() > 0; } /* model-level observers run on the host every step */
     const std::vector<tgBasicActuator*>& getAllActuators() const { return m_actuators; }
 private:
     std::vector<tgBasicActuator*> m_actuators;
@@ -39,6 +41,7 @@ public:
     virtual void setup(tgWorld& world);
     virtual void step(double dt);
     virtual void teardown();
+    virtual bool stepsOnHost() const { return numObservers() > 0; } /* model-level observers run on the host every step */
     const std::vector<tgBasicActuator*>& getAllMuscles() const { return m_actuators; }
 private:
     std::vector<tgBasicActuator*> m_actuators;
@@ -51,6 +54,7 @@ public:
     virtual void setup(tgWorld& world);
     virtual void step(double dt);
     virtual void teardown();
+    virtual bool stepsOnHost() const { return true; } /* step() commands the motor every step (tsTestRig.cpp:181-188) */
     const std::vector<tgSpringCableActuator*>& getAllMuscles() const { return m_muscles; }
 private:
     bool m_kinematic;
@@ -65,6 +69,7 @@ public:
     virtual void setup(tgWorld& world);
     virtual void step(double dt);
     virtual void teardown();
+    virtual bool stepsOnHost() const { return numObservers() > 0; } /* model-level observers run on the host every step */
     const std::vector<tgSpringCableActuator*>& getAllMuscles() const { return m_allMuscles; }
     std::size_t getSegments() const { return m_segments; }
     const std::vector<tgModel*>& getAllSegments() const { return m_allSegments; }

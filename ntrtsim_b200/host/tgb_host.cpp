@@ -187,6 +187,20 @@ void tgWorldB200Impl::run(double dt, int steps) {
     check(tgb_step(handle(), dt, steps));
     m_cacheValid = false;
 }
+void tgWorldB200Impl::stepWorld(double dt) {
+    check(tgb_step_world(handle(), dt));
+    m_cacheValid = false;
+}
+void tgWorldB200Impl::stepModels(double dt) {
+    check(tgb_step_models(handle(), dt));
+    m_cacheValid = false;
+}
+void tgWorldB200Impl::setMotorTorque(int cable, double torque) {
+    if (m_torque.size() != m_cables.size()) m_torque.assign(m_cables.size(), 0.0);
+    if (m_torque.at(cable) == torque && m_handle) return;
+    m_torque[cable] = torque;
+    check(tgb_set_controller(handle(), TGB_CTRL_TORQUE, m_torque.data(), (int32_t)m_torque.size(), 0, m_nEnv, 1));
+}
 void tgWorldB200Impl::refreshCache() {
     if (m_cacheValid) return;
     m_rodCache.resize((std::size_t)m_nEnv * m_bodies.size() * TGB_ROD_STATE_DOUBLES);
@@ -440,6 +454,8 @@ void tgKinematicActuator::setup(tgWorld& world) {
 void tgKinematicActuator::step(double dt) {
     if (dt <= 0.0) throw std::invalid_argument("dt is not positive.");
     notifyStep(dt);
+    /* the desired torque of this step reaches the device before the models half runs; like the reference it lasts one step */
+    m_world->setMotorTorque(m_cable, m_desiredTorque);
     tgModel::step(dt);
     m_desiredTorque = 0.0;
 }
@@ -465,7 +481,7 @@ void tgSimView::teardown() { m_initialized = false; }
 void tgSimView::run() { run(10); }
 void tgSimView::run(int steps) {
     if (!m_pSimulation) throw std::runtime_error("The view is not bound to a simulation");
-    if (!m_pSimulation->hasHostObservers()) {
+    if (!m_pSimulation->hasHostObservers() && !m_pSimulation->hasHostStepCode()) {
         m_pSimulation->runFused(m_stepSize, steps);
         return;
     }
@@ -512,12 +528,21 @@ bool tgSimulation::hasHostObservers() const {
     }
     return false;
 }
+bool tgSimulation::hasHostStepCode() const {
+    for (std::size_t i = 0; i < m_models.size(); ++i)
+        if (m_models[i]->stepsOnHost()) return true;
+    return false;
+}
 void tgSimulation::step(double dt) const {
     if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
-    /* world step + cable/actuator/controller step of every environment run on the device */
-    m_view.world().step(dt);
-    /* host-side observers (model tree walk, tgSimulation.cpp:208-211) */
+    /* (A) world step of every environment on the device (tgSimulation.cpp:205) */
+    m_view.world().b200().stepWorld(dt);
+    /* (B) model tree walk on the host (tgSimulation.cpp:208-211): observers and the models' own step code see the state after
+       the world step and may move motors through the C ABI, exactly where the reference runs them ... */
     for (std::size_t i = 0; i < m_models.size(); ++i) m_models[i]->step(dt);
+    /* ... then the cable forces of every actuator's step on the device. A cable force depends only on body poses and its own
+       rest length, so evaluating all of them after all observers equals the reference's per-actuator interleaving. */
+    m_view.world().b200().stepModels(dt);
 }
 void tgSimulation::runFused(double dt, int steps) const {
     if (dt <= 0.0) throw std::invalid_argument("dt is not positive");

@@ -213,6 +213,9 @@ public:
     void finalize();                 /* throws std::runtime_error when no CUDA device is usable */
     tgb_world* handle();             /* finalizes on first use */
     void step(double dt);            /* one tgSimulation::step for every environment */
+    void stepWorld(double dt);       /* its world half (tgSimulation.cpp:205) */
+    void stepModels(double dt);      /* its models half: device-side controller, motors, cable forces (tgSimulation.cpp:208-211) */
+    void setMotorTorque(int cable, double torque); /* tgKinematicActuator::setControlInput, all environments, until changed */
     void run(double dt, int steps);  /* `steps` of them in one device launch sequence */
 
     /* observation side: valid for the state after the last completed step */
@@ -239,6 +242,7 @@ private:
     tgb_world* m_handle;
     bool m_cacheValid;
     std::vector<double> m_rodCache, m_cableCache;
+    std::vector<double> m_torque;
 };
 
 class tgWorld {
@@ -283,6 +287,9 @@ public:
     virtual void setup(tgWorld& world);
     virtual void teardown();
     virtual void step(double dt);
+    /* batched extension: true when this model's step() does work on the host every step (its own control code or model-level
+       observers), so that tgSimView::run must not fuse steps on the device */
+    virtual bool stepsOnHost() const { return false; }
     virtual void onVisit(const tgModelVisitor& r) const;
     void addChild(tgModel* pChild); /* takes ownership; NULL -> std::invalid_argument */
     virtual std::string toString(std::string prefix = "") const;
@@ -498,6 +505,7 @@ public:
     tgWorld& getWorld() const;
     /* True when any model-level or actuator-level host observer is attached (forces per-step host round trips). */
     bool hasHostObservers() const;
+    bool hasHostStepCode() const;
     /* batched fast path: `steps` steps with no host observer in the loop */
     void runFused(double dt, int steps) const;
 private:

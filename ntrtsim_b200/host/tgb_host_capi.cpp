@@ -124,6 +124,31 @@ void tgh_escape_transform_actions(const double* actions01, double initial_length
     tgbEscapeTransformActions(actions01, initial_length, out33);
 }
 
+/* The same, but stepping through tgSimulation::step one step at a time: the host model tree walk (observers, the models' own
+   step code such as tsTestRig::step commanding its motor) runs between the world half and the models half of every step. */
+int tgh_run_example_stepwise(const char* name, int n_env, int precision, int steps, double* rod_state_out, double* cable_obs_out) {
+    Example* e = 0;
+    try {
+        e = build(name ? name : "", n_env, precision);
+        if (!e) return TGB_ERR_INVALID_ARGUMENT;
+        for (int i = 0; i < steps; ++i) e->sim->step(e->dt);
+        tgWorldB200Impl& w = e->world->b200();
+        int st = TGB_OK;
+        if (rod_state_out) st = tgb_get_rod_state(w.handle(), 0, n_env, rod_state_out);
+        if (st == TGB_OK && cable_obs_out) st = tgb_get_cable_obs(w.handle(), 0, n_env, cable_obs_out);
+        delete e;
+        return st;
+    } catch (const std::invalid_argument& ex) {
+        g_error = ex.what();
+        delete e;
+        return TGB_ERR_INVALID_ARGUMENT;
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        delete e;
+        return TGB_ERR_RUNTIME;
+    }
+}
+
 /* CPG + impedance controller of TetraSpineCPGControl flattened for tgb_set_cpg_controller
    (AppTetraSpineLearning.cpp:77-86: Config(segmentSpan 3, 6, 6, 2, segment 1, controlTime .001);
    TetraSpineCPGControl.cpp:58-126: impedance gains by the "outer" tag).

@@ -126,6 +126,12 @@ class BatchedWorld(object):
     def step(self, dt, n_steps=1):
         capi.check(self._lib.tgb_step(self._h, dt, n_steps))
 
+    def step_world(self, dt):
+        capi.check(self._lib.tgb_step_world(self._h, dt))
+
+    def step_models(self, dt):
+        capi.check(self._lib.tgb_step_models(self._h, dt))
+
     def sync(self):
         capi.check(self._lib.tgb_sync(self._h))
 

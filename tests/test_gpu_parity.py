@@ -433,3 +433,43 @@ def test_population_evaluation_matches_oracle_scores():
     ctl2.desc.height_lo, ctl2.desc.height_hi = 100.0, 200.0
     s2, st2 = evaluate_population(model, ctl2, rows[:3], 5, precision="f32")
     assert np.all(s2[:, 0] == -1.0) and np.all(st2 & 2)
+
+
+@pytest.mark.parametrize("kind", ["basic", "kinematic"])
+def test_host_step_code_runs_between_the_halves(kind):
+    """tsTestRig::step commands its motor on the host every step (tsTestRig.cpp:181-188). Stepping through the host API's
+    tgSimulation::step (world half -> host model walk -> models half) must equal the device-side controller rollout and
+    the oracle: the host code runs exactly where the reference runs it, not one step late."""
+    import ctypes as C
+    h = capi.load_host()
+    name = "tsTestRig_" + kind
+    model = nt.build_example(name)
+    n_env, steps = 3, 400
+    rod = np.empty((n_env, model.n_bodies, 13))
+    cab = np.empty((n_env, model.n_cables, 4))
+    rc = h.tgh_run_example_stepwise(name.encode(), n_env, capi.TGB_F64, steps, rod.ctypes.data_as(C.c_void_p), cab.ctypes.data_as(C.c_void_p))
+    assert rc == 0, h.tgh_last_error()
+    ctrl = capi.TGB_CTRL_SETPOINT if kind == "basic" else capi.TGB_CTRL_TORQUE
+    params = np.full((n_env, 1), 5.0 if kind == "basic" else -580.0)
+    rods0 = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+    rd, cd, _ = device_rollout(model, rods0, tiled_cables(model, n_env), steps, "f64", ctrl, params)
+    assert np.array_equal(rd, rod) and np.array_equal(cd, cab)
+    ro, co = oracle_rollout(model, rods0, tiled_cables(model, n_env), steps, ctrl, params)
+    assert np.abs(cab - co).max() < 1e-8
+
+
+def test_world_and_models_halves_compose_to_a_step():
+    model = nt.build_example("Escape_c3")
+    n_env, steps = 9, 25
+    rods, cab, params = escape_inputs(model, n_env, seed=31)
+    ref = device_rollout(model, rods, cab, steps, "f32", capi.TGB_CTRL_ESCAPE_SINE, params)
+    w = nt.BatchedWorld(model, n_env, precision="f32")
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    w.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params)
+    for _ in range(steps):
+        w.step_world(model.dt)
+        w.step_models(model.dt)
+    assert abs(w.time() - steps * model.dt) < 1e-12
+    assert np.array_equal(w.get_rod_state(), ref[0]) and np.array_equal(w.get_cable_obs(), ref[1])
+    w.close()
