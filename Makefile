@@ -16,15 +16,18 @@ all: $(LIBDIR)/libntrtsim_b200.so $(LIBDIR)/libtgb_host.so oracle/liboracle.so
 $(BUILD) $(LIBDIR):
 	mkdir -p $@
 
-$(BUILD)/tgb_step_f32.o: $(CSRC)/tgb_step_f32.cu $(DEV_HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+STEP_OBJS := $(foreach p,f32 f64,$(foreach c,simple sine cpg,$(BUILD)/tgb_step_$(p)_$(c).o))
+TGB_EXTRA ?=
+
+$(BUILD)/tgb_step_f32.o $(BUILD)/tgb_step_f32_simple.o $(BUILD)/tgb_step_f32_sine.o $(BUILD)/tgb_step_f32_cpg.o: $(BUILD)/%.o: $(CSRC)/%.cu $(DEV_HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) $(TGB_EXTRA) -c $< -o $@
 # the double instantiation evaluates the oracle's expression tree: no FMA contraction
-$(BUILD)/tgb_step_f64.o: $(CSRC)/tgb_step_f64.cu $(DEV_HDRS) | $(BUILD)
-	$(NVCC) $(NVFLAGS) --fmad=false -c $< -o $@
+$(BUILD)/tgb_step_f64.o $(BUILD)/tgb_step_f64_simple.o $(BUILD)/tgb_step_f64_sine.o $(BUILD)/tgb_step_f64_cpg.o: $(BUILD)/%.o: $(CSRC)/%.cu $(DEV_HDRS) | $(BUILD)
+	$(NVCC) $(NVFLAGS) $(TGB_EXTRA) --fmad=false -c $< -o $@
 $(BUILD)/tgb_capi.o: $(CSRC)/tgb_capi.cu $(DEV_HDRS) | $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(LIBDIR)/libntrtsim_b200.so: $(BUILD)/tgb_step_f32.o $(BUILD)/tgb_step_f64.o $(BUILD)/tgb_capi.o | $(LIBDIR)
+$(LIBDIR)/libntrtsim_b200.so: $(BUILD)/tgb_step_f32.o $(BUILD)/tgb_step_f64.o $(STEP_OBJS) $(BUILD)/tgb_capi.o | $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 
 HOST_SRCS := $(HOST)/tgb_host.cpp $(HOST)/tgb_creator.cpp $(HOST)/tgb_examples.cpp $(HOST)/tgb_host_capi.cpp

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("TGB_LIB_DIR") or os.path.join(_HERE, "lib")  # TGB_LIB_DIR: kernel-variant A/B runs (tools/)
 
 TGB_OK, TGB_ERR_INVALID_ARGUMENT, TGB_ERR_STATE, TGB_ERR_CUDA, TGB_ERR_UNSUPPORTED, TGB_ERR_RUNTIME = range(6)
 TGB_F32, TGB_F64 = 0, 1

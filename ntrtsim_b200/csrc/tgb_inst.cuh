@@ -1,43 +1,24 @@
 /*
- * tgb_inst.cuh -- instantiates every kernel for the scalar type TGB_SCALAR and defines the launch table
- * TGB_OPS_NAME. Included exactly once by tgb_step_f32.cu / tgb_step_f64.cu.
+ * tgb_inst.cuh -- instantiates the I/O kernels for the scalar type TGB_SCALAR and defines the launch table TGB_OPS_NAME; the step
+ * kernels of the three controller classes live in their own translation units (tgb_inst_step.cuh) and are declared here.
+ * Included exactly once by tgb_step_f32.cu / tgb_step_f64.cu.
  */
 #include "tgb_ops.h"
 #include "tgb_step.cuh"
+
+cudaError_t TGB_STEP_SIMPLE(const tgb_step_args& a, int lpe, int threads, cudaStream_t s);
+cudaError_t TGB_STEP_SINE(const tgb_step_args& a, int lpe, int threads, cudaStream_t s);
+cudaError_t TGB_STEP_CPG(const tgb_step_args& a, int lpe, int threads, cudaStream_t s);
 
 namespace {
 
 typedef TGB_SCALAR scalar_t;
 
-template <int LPE, bool CPG>
-cudaError_t launch_step_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
-    const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, threads, sizeof(scalar_t));
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    const int groupsPerBlock = threads / LPE;
-    const int grid = (a.n_env + groupsPerBlock - 1) / groupsPerBlock;
-    tgb::tgb_step_kernel<scalar_t, LPE, CPG><<<grid, threads, smem, s>>>(a);
-    return cudaGetLastError();
-}
-template <int LPE>
-cudaError_t launch_step(const tgb_step_args& a, int threads, cudaStream_t s) {
-    if (a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) return launch_step_impl<LPE, true>(a, threads, s);
-    return launch_step_impl<LPE, false>(a, threads, s);
-}
-
 cudaError_t step(const tgb_step_args& a, int lpe, int threads, cudaStream_t s) {
-    if (threads < 32 || threads > 128 || (threads % 32) != 0) return cudaErrorInvalidValue;
-    switch (lpe) {
-    case 2: return launch_step<2>(a, threads, s);
-    case 4: return launch_step<4>(a, threads, s);
-    case 8: return launch_step<8>(a, threads, s);
-    case 16: return launch_step<16>(a, threads, s);
-    case 32: return launch_step<32>(a, threads, s);
-    default: return cudaErrorInvalidValue;
+    switch (tgb::tgb_ctrl_class(a.ctrl_kind)) {
+    case tgb::TGB_CLASS_CPG: return TGB_STEP_CPG(a, lpe, threads, s);
+    case tgb::TGB_CLASS_SINE: return TGB_STEP_SINE(a, lpe, threads, s);
+    default: return TGB_STEP_SIMPLE(a, lpe, threads, s);
     }
 }
 

@@ -1,0 +1,47 @@
+/*
+ * tgb_inst_step.cuh -- instantiates tgb_step_kernel for the scalar type TGB_SCALAR and the controller class TGB_STEP_CLASS
+ * (all lanes-per-env values, with and without ground) and defines the launch function TGB_STEP_FN.  One translation unit per
+ * (scalar type, class) keeps the build parallel; see the Makefile.
+ */
+#include "tgb_ops.h"
+#include "tgb_step.cuh"
+
+namespace {
+
+typedef TGB_SCALAR scalar_t;
+
+template <int LPE, bool GROUND>
+cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
+    const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, threads, sizeof(scalar_t));
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int groupsPerBlock = threads / LPE;
+    const int grid = (a.n_env + groupsPerBlock - 1) / groupsPerBlock;
+    tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND><<<grid, threads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int LPE>
+cudaError_t launch(const tgb_step_args& a, int threads, cudaStream_t s) {
+    if (a.ground_kind == TGB_GROUND_EMPTY) return launch_impl<LPE, false>(a, threads, s);
+    return launch_impl<LPE, true>(a, threads, s);
+}
+
+} // namespace
+
+cudaError_t TGB_STEP_FN(const tgb_step_args& a, int lpe, int threads, cudaStream_t s) {
+    if (threads < 32 || threads > 128 || (threads % 32) != 0) return cudaErrorInvalidValue;
+    switch (lpe) {
+    case 2: return launch<2>(a, threads, s);
+    case 4: return launch<4>(a, threads, s);
+    case 8: return launch<8>(a, threads, s);
+    case 16: return launch<16>(a, threads, s);
+    case 32: return launch<32>(a, threads, s);
+    default: return cudaErrorInvalidValue;
+    }
+}

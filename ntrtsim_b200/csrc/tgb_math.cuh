@@ -9,6 +9,7 @@
 #include <math.h>
 
 #define TGB_D __device__ __forceinline__
+#define TGB_HOST_DEVICE_INLINE __host__ __device__ inline
 
 namespace tgb {
 

@@ -34,6 +34,10 @@
 
 #include <type_traits>
 
+#ifndef TGB_CABLE_UNROLL
+#define TGB_CABLE_UNROLL 0 /* 0 = automatic */
+#endif
+
 namespace tgb {
 
 template <typename T> struct Vec16;
@@ -121,10 +125,97 @@ template <> TGB_D double epsilonOf<double>() { return 2.2204460492503131e-16; }
 /* sin of a double-precision phase: exact-type sin for double, range-reduced sinf for float */
 TGB_D double sinPhase(double arg, double) { return sin(arg); }
 TGB_D float sinPhase(double arg, float) {
+    /* the phase grows with time: reduce it in double to [-pi, pi] before the single-precision sine */
     const double twoPi = 6.283185307179586476925286766559;
-    double r = arg - twoPi * rint(arg * (1.0 / twoPi));
+    const double r = arg - twoPi * rint(arg * (1.0 / twoPi));
     return sinf((float)r);
 }
+
+/* Projected Gauss-Seidel over contact rows kept in shared memory (bodies with more than two contact points: compound bodies,
+   rods lying flat).  Inlined: a real call here costs more on the hot path (register shuffling around the call site; measured
+   -5% on B200) than the cold code costs in instruction-cache footprint. */
+template <typename T>
+__device__ __forceinline__ void pgsSharedRows(T* ct, int laneStride, int nc, int iterations, bool anyPen, V3<T> gn, T invMass, T mu,
+                                           V3<T>& dLin, V3<T>& dAng, V3<T>& push, V3<T>& turn) {
+#define CTG(slot, f) ct[((slot) * TGB_NCT + (f)) * laneStride]
+    if (anyPen)
+        for (int it = 0; it < iterations; ++it) {
+            for (int c = 0; c < nc; ++c) {
+                const T rhsPen = CTG(c, CT_RHSPEN);
+                if (rhsPen == T(0)) continue;
+                const V3<T> rxn(CTG(c, CT_RXN + 0), CTG(c, CT_RXN + 1), CTG(c, CT_RXN + 2));
+                const V3<T> angN(CTG(c, CT_ANGN + 0), CTG(c, CT_ANGN + 1), CTG(c, CT_ANGN + 2));
+                const T invDiagN = CTG(c, CT_INVDIAGN);
+                T delta = rhsPen;
+                const T dv = gn.dot(push) + rxn.dot(turn);
+                delta -= dv * invDiagN;
+                const T lam = CTG(c, CT_LAMPUSH);
+                const T sum = lam + delta;
+                if (sum < T(0)) { delta = -lam; CTG(c, CT_LAMPUSH) = T(0); }
+                else CTG(c, CT_LAMPUSH) = sum;
+                push += gn * (invMass * delta);
+                turn += angN * delta;
+            }
+        }
+    for (int it = 0; it < iterations; ++it) {
+        for (int c = 0; c < nc; ++c) {
+            const V3<T> rxn(CTG(c, CT_RXN + 0), CTG(c, CT_RXN + 1), CTG(c, CT_RXN + 2));
+            const V3<T> angN(CTG(c, CT_ANGN + 0), CTG(c, CT_ANGN + 1), CTG(c, CT_ANGN + 2));
+            const T invDiagN = CTG(c, CT_INVDIAGN);
+            T delta = CTG(c, CT_RHSN);
+            const T dv = gn.dot(dLin) + rxn.dot(dAng);
+            delta -= dv * invDiagN;
+            const T lam = CTG(c, CT_LAMN);
+            const T sum = lam + delta;
+            if (sum < T(0)) { delta = -lam; CTG(c, CT_LAMN) = T(0); }
+            else CTG(c, CT_LAMN) = sum;
+            dLin += gn * (invMass * delta);
+            dAng += angN * delta;
+        }
+        for (int c = 0; c < nc; ++c) {
+            const T lamN = CTG(c, CT_LAMN);
+            if (!(lamN > T(0))) continue;
+            const V3<T> t(CTG(c, CT_T + 0), CTG(c, CT_T + 1), CTG(c, CT_T + 2));
+            const V3<T> rxt(CTG(c, CT_RXT + 0), CTG(c, CT_RXT + 1), CTG(c, CT_RXT + 2));
+            const V3<T> angT(CTG(c, CT_ANGT + 0), CTG(c, CT_ANGT + 1), CTG(c, CT_ANGT + 2));
+            const T invDiagT = CTG(c, CT_INVDIAGT);
+            const T lo = -mu * lamN, hi = mu * lamN;
+            T delta = CTG(c, CT_RHST);
+            const T dv = t.dot(dLin) + rxt.dot(dAng);
+            delta -= dv * invDiagT;
+            const T lam = CTG(c, CT_LAMT);
+            const T sum = lam + delta;
+            if (sum < lo) { delta = lo - lam; CTG(c, CT_LAMT) = lo; }
+            else if (sum > hi) { delta = hi - lam; CTG(c, CT_LAMT) = hi; }
+            else CTG(c, CT_LAMT) = sum;
+            dLin += t * (invMass * delta);
+            dAng += angT * delta;
+        }
+    }
+#undef CTG
+}
+
+/* One cable's working set in registers (the cable phase keeps several of these in flight per lane). */
+template <typename T>
+struct CableRegs {
+    int c, actuator;
+    bool valid;
+    V3<T> ra, rb, dist, J;
+    T L, k, damp, tVel, maxTens, maxStretch, minAL, minRL;
+    T rest, prev, pref, motorVel, desiredTorque, velocity;
+    /* tgBasicActuator::moveMotors, tgBasicActuator.cpp:170-225 */
+    TGB_D void moveMotors(T dtm) {
+        const T stepSize = tVel * dtm;
+        if ((L - pref) * k > maxTens) pref = L - maxStretch;
+        const T diff = pref - rest;
+        const T fabsDiff = tabs(diff);
+        if ((L > minAL) || (diff > T(0))) {
+            if (fabsDiff > stepSize) rest += tcopysign(stepSize, diff); /* (diff / |diff|) * stepSize, exactly */
+            else rest += diff;
+        }
+        rest = (rest > minRL) ? rest : minRL;
+    }
+};
 
 /* doubles of shared memory per env group: controller row, sine cumulative phases, CPG work space */
 __host__ __device__ inline int tgb_group_double_words(const tgb_step_args& a) {
@@ -146,9 +237,17 @@ struct ModelView {
     TGB_D int cablei(int f, int c) const { return ci[f * C + c]; }
 };
 
-/* CPG = the CPG + impedance controller is compiled in (a separate instantiation keeps its Dormand-Prince integrator out of the
-   register budget of the other controllers) */
-template <typename T, int LPE, bool CPG>
+/* Controller classes a kernel is compiled for (the controller kind inside a class is a warp-uniform run-time switch):
+   SIMPLE = none / set-point / torque / tension, SINE = EscapeController, CPG = CPG + impedance (its Dormand-Prince integrator
+   needs 231 registers).  GROUND = false compiles the contact manifold and the contact solver out (tgEmptyGround).  Keeping the
+   hot loop's code small matters: it is ~20 KB of instructions against a 32 KB L1.5 instruction cache, and at 4096 environments
+   there are too few warps per SM to hide instruction-fetch misses. */
+enum { TGB_CLASS_SIMPLE = 0, TGB_CLASS_SINE = 1, TGB_CLASS_CPG = 2 };
+TGB_HOST_DEVICE_INLINE int tgb_ctrl_class(int kind) {
+    return kind == TGB_CTRL_CPG_IMPEDANCE ? TGB_CLASS_CPG : kind == TGB_CTRL_ESCAPE_SINE ? TGB_CLASS_SINE : TGB_CLASS_SIMPLE;
+}
+
+template <typename T, int LPE, int CLASS, bool GROUND>
 __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename Vec16<T>::type vec_t;
@@ -185,7 +284,12 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     T* sPose = sState + a.stride;              /* [12][LPE] : pos3, basis9 of each body */
     T* sJ = sPose + poseWords;                 /* [C][3] */
     T* sCt = sJ + jWords;                      /* [cap][TGB_NCT][LPE] */
-    constexpr bool cpgOn = CPG;
+    constexpr bool cpgOn = CLASS == TGB_CLASS_CPG;
+    constexpr bool sineOn = CLASS == TGB_CLASS_SINE;
+    constexpr bool simpleOn = CLASS == TGB_CLASS_SIMPLE;
+    /* cables in flight per lane in the cable phase: 3 where the instruction footprint allows it (no contact code), else 1 --
+       measured on B200: 3 is +7% without ground and -10% with ground (the hot loop then overflows the instruction cache) */
+    constexpr int CU = TGB_CABLE_UNROLL ? TGB_CABLE_UNROLL : (GROUND ? 1 : 3);
     const int groupDWords = tgb_group_double_words(a);
     double* sD = reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) + grp * groupDWords;
     double* sCtrl = sD;                        /* controller parameter row */
@@ -232,7 +336,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         ctrlTime = f[FR_CTRLTIME];
     }
 
-    if (ctrlKind == TGB_CTRL_ESCAPE_SINE && lane == 0) {
+    if (sineOn && lane == 0) {
         /* EscapeController.cpp:279-290: the phase grows by the cluster's phase change at every cluster boundary */
         double ph = 0.0;
         sCum[0] = 0.0;
@@ -440,7 +544,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             /* ---- ground contact manifold (analytic cylinder rim points against the ground surface) ---- */
             int nc = 0;
             bool anyPen = false;
-            if (a.ground_kind != TGB_GROUND_EMPTY) {
+            if (GROUND) {
                 /* signed height of the frame origin above the surface, formed in double */
                 const T originHeight = (T)(a.gn[0] * Ox + a.gn[1] * Oy + a.gn[2] * Oz - a.goff);
                 for (int si = shapeBegin; si < shapeBegin + shapeCount; ++si) {
@@ -594,60 +698,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                     }
                 }
             } else if (nc > 0) {
-                if (anyPen)
-                for (int it = 0; it < a.iterations; ++it) {
-                    for (int c = 0; c < nc; ++c) {
-                        const T rhsPen = CT(c, CT_RHSPEN);
-                        if (rhsPen == T(0)) continue;
-                        const V3<T> rxn(CT(c, CT_RXN + 0), CT(c, CT_RXN + 1), CT(c, CT_RXN + 2));
-                        const V3<T> angN(CT(c, CT_ANGN + 0), CT(c, CT_ANGN + 1), CT(c, CT_ANGN + 2));
-                        const T invDiagN = CT(c, CT_INVDIAGN);
-                        T delta = rhsPen;
-                        const T dv = gn.dot(push) + rxn.dot(turn);
-                        delta -= dv * invDiagN;
-                        const T lam = CT(c, CT_LAMPUSH);
-                        const T sum = lam + delta;
-                        if (sum < T(0)) { delta = -lam; CT(c, CT_LAMPUSH) = T(0); }
-                        else CT(c, CT_LAMPUSH) = sum;
-                        push += gn * (invMass * delta);
-                        turn += angN * delta;
-                    }
-                }
-                for (int it = 0; it < a.iterations; ++it) {
-                    for (int c = 0; c < nc; ++c) {
-                        const V3<T> rxn(CT(c, CT_RXN + 0), CT(c, CT_RXN + 1), CT(c, CT_RXN + 2));
-                        const V3<T> angN(CT(c, CT_ANGN + 0), CT(c, CT_ANGN + 1), CT(c, CT_ANGN + 2));
-                        const T invDiagN = CT(c, CT_INVDIAGN);
-                        T delta = CT(c, CT_RHSN);
-                        const T dv = gn.dot(dLin) + rxn.dot(dAng);
-                        delta -= dv * invDiagN;
-                        const T lam = CT(c, CT_LAMN);
-                        const T sum = lam + delta;
-                        if (sum < T(0)) { delta = -lam; CT(c, CT_LAMN) = T(0); }
-                        else CT(c, CT_LAMN) = sum;
-                        dLin += gn * (invMass * delta);
-                        dAng += angN * delta;
-                    }
-                    for (int c = 0; c < nc; ++c) {
-                        const T lamN = CT(c, CT_LAMN);
-                        if (!(lamN > T(0))) continue;
-                        const V3<T> t(CT(c, CT_T + 0), CT(c, CT_T + 1), CT(c, CT_T + 2));
-                        const V3<T> rxt(CT(c, CT_RXT + 0), CT(c, CT_RXT + 1), CT(c, CT_RXT + 2));
-                        const V3<T> angT(CT(c, CT_ANGT + 0), CT(c, CT_ANGT + 1), CT(c, CT_ANGT + 2));
-                        const T invDiagT = CT(c, CT_INVDIAGT);
-                        const T lo = -mu * lamN, hi = mu * lamN;
-                        T delta = CT(c, CT_RHST);
-                        const T dv = t.dot(dLin) + rxt.dot(dAng);
-                        delta -= dv * invDiagT;
-                        const T lam = CT(c, CT_LAMT);
-                        const T sum = lam + delta;
-                        if (sum < lo) { delta = lo - lam; CT(c, CT_LAMT) = lo; }
-                        else if (sum > hi) { delta = hi - lam; CT(c, CT_LAMT) = hi; }
-                        else CT(c, CT_LAMT) = sum;
-                        dLin += t * (invMass * delta);
-                        dAng += angT * delta;
-                    }
-                }
+                pgsSharedRows<T>(sCt + lane, LPE, nc, a.iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
             }
 
             /* ---- write back, split-impulse correction, integrateTransforms ---- */
@@ -675,7 +726,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
         /* =============================== models step (tgSimulation.cpp:208-211) =============================== */
         if (!doModels) continue; /* warp-uniform: a world-half-only launch (host observers run between the halves) */
-        if (ctrlKind == TGB_CTRL_ESCAPE_SINE) ctrlTime += a.dt; /* EscapeController::m_totalTime */
+        if (sineOn) ctrlTime += a.dt; /* EscapeController::m_totalTime */
         bool cpgCableControl = false;
         double cpgCableDt = 0.0;
         if (cpgOn) {
@@ -694,145 +745,177 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             cpgCableDt = cpgCableTime;
             if (cpgCableControl) cpgCableTime = 0.0;
         }
-        for (int c = lane; c < C; c += LPE) {
-            const int ia = M.cablei(CI_A, c), ib = M.cablei(CI_B, c);
-            const int actuator = M.cablei(CI_ACTUATOR, c);
-            const V3<T> la(M.cable(CF_LAX, c), M.cable(CF_LAY, c), M.cable(CF_LAZ, c));
-            const V3<T> lb(M.cable(CF_LBX, c), M.cable(CF_LBY, c), M.cable(CF_LBZ, c));
-            const T k = M.cable(CF_K, c), damp = M.cable(CF_C, c);
-            const T cTVel = M.cable(CF_TVEL, c), cMaxTens = M.cable(CF_MAXTENS, c), cMaxStretch = M.cable(CF_MAXSTRETCH, c);
-            const T cMinAL = M.cable(CF_MINAL, c), cMinRL = M.cable(CF_MINRL, c);
-            V3<T> xa(sPose[0 * LPE + ia], sPose[1 * LPE + ia], sPose[2 * LPE + ia]);
-            V3<T> xb(sPose[0 * LPE + ib], sPose[1 * LPE + ib], sPose[2 * LPE + ib]);
-            M3<T> Ba, Bb;
+        /* Cables of this lane are processed CU at a time in three passes (loads, arithmetic, stores) over independent
+           register sets, so that the loads and the dependent chains of different cables overlap instead of queueing. */
+        for (int c0 = lane; c0 < C; c0 += CU * LPE) {
+            CableRegs<T> cr[CU];
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+            for (int u = 0; u < CU; ++u) {
+                CableRegs<T>& q = cr[u];
+                const int cu = c0 + u * LPE;
+                q.valid = cu < C;
+                const int c = q.valid ? cu : c0; /* an idle slot shadows cable c0 and never stores */
+                q.c = c;
+                const int ia = M.cablei(CI_A, c), ib = M.cablei(CI_B, c);
+                q.actuator = M.cablei(CI_ACTUATOR, c);
+                const V3<T> la(M.cable(CF_LAX, c), M.cable(CF_LAY, c), M.cable(CF_LAZ, c));
+                const V3<T> lb(M.cable(CF_LBX, c), M.cable(CF_LBY, c), M.cable(CF_LBZ, c));
+                q.k = M.cable(CF_K, c); q.damp = M.cable(CF_C, c);
+                q.tVel = M.cable(CF_TVEL, c); q.maxTens = M.cable(CF_MAXTENS, c); q.maxStretch = M.cable(CF_MAXSTRETCH, c);
+                q.minAL = M.cable(CF_MINAL, c); q.minRL = M.cable(CF_MINRL, c);
+                const V3<T> xa(sPose[0 * LPE + ia], sPose[1 * LPE + ia], sPose[2 * LPE + ia]);
+                const V3<T> xb(sPose[0 * LPE + ib], sPose[1 * LPE + ib], sPose[2 * LPE + ib]);
+                M3<T> Ba, Bb;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) { Ba.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ia]; Bb.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ib]; }
-            /* anchors: tgBulletSpringCableAnchor.cpp:83-87 */
-            const V3<T> ra = Ba * la, rb = Bb * lb;
-            const V3<T> p1 = ra + xa, p2 = rb + xb;
-            const V3<T> dist = p2 - p1;
-            const T L = dist.length();
-
-            T* cs = sState + R * TGB_NBS + c * TGB_NCS;
-            T rest = cs[CS_REST], prev = cs[CS_PREV], pref = cs[CS_PREF], motorVel = cs[CS_MOTORVEL];
-            T desiredTorque = T(0);
-
-            /* tgBasicActuator::moveMotors, tgBasicActuator.cpp:170-225 */
-            auto moveMotors = [&](T dtm) {
-                const T stepSize = cTVel * dtm;
-                if ((L - pref) * k > cMaxTens) pref = L - cMaxStretch;
-                const T diff = pref - rest;
-                const T fabsDiff = tabs(diff);
-                if ((L > cMinAL) || (diff > T(0))) {
-                    if (fabsDiff > stepSize) rest += tcopysign(stepSize, diff); /* (diff / |diff|) * stepSize, exactly */
-                    else rest += diff;
-                }
-                rest = (rest > cMinRL) ? rest : cMinRL;
-            };
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) { Ba.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ia]; Bb.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ib]; }
+                /* anchors: tgBulletSpringCableAnchor.cpp:83-87 */
+                q.ra = Ba * la; q.rb = Bb * lb;
+                const V3<T> p1 = q.ra + xa, p2 = q.rb + xb;
+                q.dist = p2 - p1;
+                q.L = q.dist.length();
+                const T* cs = sState + R * TGB_NBS + c * TGB_NCS;
+                q.rest = cs[CS_REST]; q.prev = cs[CS_PREV]; q.pref = cs[CS_PREF]; q.motorVel = cs[CS_MOTORVEL];
+                q.desiredTorque = T(0);
+            }
 
             /* ---- model-level controllers (run before the children step) ---- */
-            if (ctrlKind == TGB_CTRL_SETPOINT) {
-                if (actuator == TGB_ACT_BASIC) {
-                    const T input = (T)sCtrl[c];
-                    if (!(input < T(0))) { pref = input; moveMotors(dt); }
+            if (simpleOn && ctrlKind == TGB_CTRL_SETPOINT) {
+#pragma unroll
+                for (int u = 0; u < CU; ++u) {
+                    CableRegs<T>& q = cr[u];
+                    if (q.actuator == TGB_ACT_BASIC) {
+                        const T input = (T)sCtrl[q.c];
+                        if (!(input < T(0))) { q.pref = input; q.moveMotors(dt); }
+                    }
                 }
-            } else if (ctrlKind == TGB_CTRL_TORQUE) {
-                if (actuator == TGB_ACT_KINEMATIC) desiredTorque = (T)sCtrl[c];
-            } else if (ctrlKind == TGB_CTRL_TENSION) {
-                if (actuator == TGB_ACT_BASIC) {
-                    /* tgTensionController::control(dt, setPoint): tgTensionController.cpp:50-88 */
-                    const T setPoint = (T)sCtrl[0];
-                    T tension = (L - rest) * k;
-                    tension = tension < T(0) ? T(0) : tension;
-                    const T delta = setPoint - tension;
-                    const T diff = delta / k;
-                    T newLength = rest - diff;
-                    newLength = newLength < T(0) ? T(0) : newLength;
-                    pref = newLength;
-                    moveMotors(dt);
-                }
-            } else if (ctrlKind == TGB_CTRL_ESCAPE_SINE) {
-                if (c < 24) {
-                    /* EscapeController::setPreferredMuscleLengths, EscapeController.cpp:245-291 */
-                    const int cluster = c < 16 ? (c >> 2) : 4 + ((c - 16) >> 1);
-                    const bool firstOfCluster = c < 16 ? ((c & 3) == 0) : (((c - 16) & 1) == 0);
-                    const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
-                    const double arg = sCtrl[cluster * 4 + 1] * ctrlTime + phase;
-                    T newLength = (T)sCtrl[cluster * 4 + 0] * sinPhase(arg, T(0)) + (T)sCtrl[cluster * 4 + 3];
-                    const T L0 = (T)sCtrl[32];
-                    const T minLength = L0 * (T(1) - T(0.50)), maxLength = L0 * (T(1) + T(0.50));
-                    if (newLength <= minLength) newLength = minLength;
-                    else if (newLength >= maxLength) newLength = maxLength;
-                    if (!(newLength < T(0))) { pref = newLength; moveMotors(dt); }
-                }
-                moveMotors(dt); /* EscapeController.cpp:108-116: every muscle's motors move a second time */
-            } else if (cpgOn) {
-                if (actuator == TGB_ACT_BASIC) {
-                    if (cpgCableControl) {
-                        /* tgImpedanceController::controlTension(tgBasicActuator&, ...), tgImpedanceController.cpp:163-185 */
-                        const double* g = a.cpg_imp + 4 * c;
-                        const T vel = motorVel; /* velocity slot of a basic actuator = the cable's m_velocity */
-                        T setTension = (T)g[0] + (T)g[1] * (L - (T)g[3]) + (T)g[2] * (vel - (T)sNodeValue[c]);
-                        setTension = setTension > T(0) ? setTension : T(0);
-                        /* static tgTensionController::control(sca, dt, setPoint), tgTensionController.cpp:90-114 */
-                        T tension = (L - rest) * k;
+            } else if (simpleOn && ctrlKind == TGB_CTRL_TORQUE) {
+#pragma unroll
+                for (int u = 0; u < CU; ++u)
+                    if (cr[u].actuator == TGB_ACT_KINEMATIC) cr[u].desiredTorque = (T)sCtrl[cr[u].c];
+            } else if (simpleOn && ctrlKind == TGB_CTRL_TENSION) {
+                const T setPoint = (T)sCtrl[0];
+#pragma unroll
+                for (int u = 0; u < CU; ++u) {
+                    CableRegs<T>& q = cr[u];
+                    if (q.actuator == TGB_ACT_BASIC) {
+                        /* tgTensionController::control(dt, setPoint): tgTensionController.cpp:50-88 */
+                        T tension = (q.L - q.rest) * q.k;
                         tension = tension < T(0) ? T(0) : tension;
-                        const T delta = setTension - tension;
-                        const T diff = delta / k;
-                        T newLength = rest - diff;
-                        newLength = newLength < T(0.1) ? T(0.1) : newLength;
-                        pref = newLength;
-                        moveMotors((T)cpgCableDt);
-                    } else {
-                        moveMotors(dt);
+                        const T delta = setPoint - tension;
+                        const T diff = delta / q.k;
+                        T newLength = q.rest - diff;
+                        newLength = newLength < T(0) ? T(0) : newLength;
+                        q.pref = newLength;
+                        q.moveMotors(dt);
+                    }
+                }
+            } else if (sineOn) {
+                const T L0 = (T)sCtrl[32];
+                const T minLength = L0 * (T(1) - T(0.50)), maxLength = L0 * (T(1) + T(0.50));
+#pragma unroll
+                for (int u = 0; u < CU; ++u) {
+                    CableRegs<T>& q = cr[u];
+                    const int c = q.c;
+                    if (c < 24) {
+                        /* EscapeController::setPreferredMuscleLengths, EscapeController.cpp:245-291 */
+                        const int cluster = c < 16 ? (c >> 2) : 4 + ((c - 16) >> 1);
+                        const bool firstOfCluster = c < 16 ? ((c & 3) == 0) : (((c - 16) & 1) == 0);
+                        const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
+                        const double arg = sCtrl[cluster * 4 + 1] * ctrlTime + phase;
+                        T newLength = (T)sCtrl[cluster * 4 + 0] * sinPhase(arg, T(0)) + (T)sCtrl[cluster * 4 + 3];
+                        if (newLength <= minLength) newLength = minLength;
+                        else if (newLength >= maxLength) newLength = maxLength;
+                        if (!(newLength < T(0))) { q.pref = newLength; q.moveMotors(dt); }
+                    }
+                    q.moveMotors(dt); /* EscapeController.cpp:108-116: every muscle's motors move a second time */
+                }
+            } else if (cpgOn) {
+#pragma unroll
+                for (int u = 0; u < CU; ++u) {
+                    CableRegs<T>& q = cr[u];
+                    if (q.actuator == TGB_ACT_BASIC) {
+                        if (cpgCableControl) {
+                            /* tgImpedanceController::controlTension(tgBasicActuator&, ...), tgImpedanceController.cpp:163-185 */
+                            const double* g = a.cpg_imp + 4 * q.c;
+                            const T vel = q.motorVel; /* velocity slot of a basic actuator = the cable's m_velocity */
+                            T setTension = (T)g[0] + (T)g[1] * (q.L - (T)g[3]) + (T)g[2] * (vel - (T)sNodeValue[q.c]);
+                            setTension = setTension > T(0) ? setTension : T(0);
+                            /* static tgTensionController::control(sca, dt, setPoint), tgTensionController.cpp:90-114 */
+                            T tension = (q.L - q.rest) * q.k;
+                            tension = tension < T(0) ? T(0) : tension;
+                            const T delta = setTension - tension;
+                            const T diff = delta / q.k;
+                            T newLength = q.rest - diff;
+                            newLength = newLength < T(0.1) ? T(0.1) : newLength;
+                            q.pref = newLength;
+                            q.moveMotors((T)cpgCableDt);
+                        } else {
+                            q.moveMotors(dt);
+                        }
                     }
                 }
             }
 
             /* ---- tgKinematicActuator::integrateRestLength, tgKinematicActuator.cpp:186-225 ---- */
-            if (actuator == TGB_ACT_KINEMATIC) {
-                T tension = (L - rest) * k;
-                tension = tension < T(0) ? T(0) : tension;
-                const T mRadius = M.cable(CF_MRADIUS, c);
-                T maxTorque = M.cable(CF_MAXTENS, c) * mRadius * (T(1) - mRadius * tabs(motorVel) / M.cable(CF_TVEL, c));
-                maxTorque = maxTorque < T(0) ? T(0) : maxTorque;
-                const T applied = tabs(desiredTorque) < maxTorque ? desiredTorque : desiredTorque / tabs(desiredTorque) * maxTorque;
-                const T acc = (applied - M.cable(CF_MFRICTION, c) * motorVel + tension * mRadius) / M.cable(CF_MINERTIA, c);
-                if (M.cablei(CI_BACKDRIVABLE, c) == 0 && acc * applied <= T(0))
-                    motorVel = motorVel + acc * dt > T(0) ? T(0) : motorVel + acc * dt;
-                else
-                    motorVel += acc * dt;
-                rest += mRadius * motorVel * dt;
-                const T minRL = M.cable(CF_MINRL, c);
-                rest = (rest > minRL) ? rest : minRL;
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
+                CableRegs<T>& q = cr[u];
+                if (q.actuator == TGB_ACT_KINEMATIC) {
+                    const int c = q.c;
+                    T tension = (q.L - q.rest) * q.k;
+                    tension = tension < T(0) ? T(0) : tension;
+                    const T mRadius = M.cable(CF_MRADIUS, c);
+                    T maxTorque = q.maxTens * mRadius * (T(1) - mRadius * tabs(q.motorVel) / q.tVel);
+                    maxTorque = maxTorque < T(0) ? T(0) : maxTorque;
+                    const T applied = tabs(q.desiredTorque) < maxTorque ? q.desiredTorque : q.desiredTorque / tabs(q.desiredTorque) * maxTorque;
+                    const T acc = (applied - M.cable(CF_MFRICTION, c) * q.motorVel + tension * mRadius) / M.cable(CF_MINERTIA, c);
+                    if (M.cablei(CI_BACKDRIVABLE, c) == 0 && acc * applied <= T(0))
+                        q.motorVel = q.motorVel + acc * dt > T(0) ? T(0) : q.motorVel + acc * dt;
+                    else
+                        q.motorVel += acc * dt;
+                    q.rest += mRadius * q.motorVel * dt;
+                    q.rest = (q.rest > q.minRL) ? q.rest : q.minRL;
+                }
             }
 
             /* ---- tgBulletSpringCable::calculateAndApplyForce, tgBulletSpringCable.cpp:90-141 ---- */
-            const V3<T> unit = dist * trcp(L);
-            const T stretch = L - rest;
-            T magnitude = k * stretch;
-            const T deltaStretch = L - prev;
-            const T velocity = kFast ? deltaStretch * invDt : deltaStretch / dt;
-            T damping = damp * velocity;
-            if (tabs(magnitude) * T(1) < tabs(damping)) damping = (damping > T(0) ? magnitude * T(1) : -magnitude * T(1));
-            magnitude += damping;
-            V3<T> force(T(0), T(0), T(0));
-            if (L > rest) force = unit * magnitude;
-            prev = L;
-            const V3<T> J = force * dt;
-            if (kFast) {
-                /* also publish the torque of the impulse about both bodies' centres: r x J and r x (-J) */
-                const V3<T> ta = ra.cross(J), tb = J.cross(rb);
-                T* o = sJ + c * 12;
-                o[0] = J.x; o[1] = J.y; o[2] = J.z; o[3] = ta.x; o[4] = ta.y; o[5] = ta.z;
-                o[6] = -J.x; o[7] = -J.y; o[8] = -J.z; o[9] = tb.x; o[10] = tb.y; o[11] = tb.z;
-            } else {
-                sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
+                CableRegs<T>& q = cr[u];
+                const V3<T> unit = q.dist * trcp(q.L);
+                const T stretch = q.L - q.rest;
+                T magnitude = q.k * stretch;
+                const T deltaStretch = q.L - q.prev;
+                q.velocity = kFast ? deltaStretch * invDt : deltaStretch / dt;
+                T damping = q.damp * q.velocity;
+                if (tabs(magnitude) * T(1) < tabs(damping)) damping = (damping > T(0) ? magnitude * T(1) : -magnitude * T(1));
+                magnitude += damping;
+                V3<T> force(T(0), T(0), T(0));
+                if (q.L > q.rest) force = unit * magnitude;
+                q.prev = q.L;
+                q.J = force * dt;
             }
-            cs[CS_REST] = rest; cs[CS_PREV] = prev; cs[CS_PREF] = pref;
-            cs[CS_MOTORVEL] = actuator == TGB_ACT_KINEMATIC ? motorVel : velocity;
+#pragma unroll
+            for (int u = 0; u < CU; ++u) {
+                const CableRegs<T>& q = cr[u];
+                if (!q.valid) continue;
+                const int c = q.c;
+                const V3<T> J = q.J;
+                if (kFast) {
+                    /* also publish the torque of the impulse about both bodies' centres: r x J and r x (-J) */
+                    const V3<T> ta = q.ra.cross(J), tb = J.cross(q.rb);
+                    T* o = sJ + c * 12;
+                    o[0] = J.x; o[1] = J.y; o[2] = J.z; o[3] = ta.x; o[4] = ta.y; o[5] = ta.z;
+                    o[6] = -J.x; o[7] = -J.y; o[8] = -J.z; o[9] = tb.x; o[10] = tb.y; o[11] = tb.z;
+                } else {
+                    sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
+                }
+                T* cs = sState + R * TGB_NBS + c * TGB_NCS;
+                cs[CS_REST] = q.rest; cs[CS_PREV] = q.prev; cs[CS_PREF] = q.pref;
+                cs[CS_MOTORVEL] = q.actuator == TGB_ACT_KINEMATIC ? q.motorVel : q.velocity;
+            }
         }
         __syncwarp();
 
