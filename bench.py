@@ -48,6 +48,15 @@ def build_workload(name, n_env, seed):
         params = nt.escape_transform_actions(rng.uniform(size=(n_env, 32)), 9.0)
         ctrl = capi.TGB_CTRL_ESCAPE_SINE
         p_ctrl = 32
+    elif name == "superball_noground":   # tuning aid: the same workload without the ground (upper bound for contact-side work)
+        model = nt.build_example("Escape_c3")
+        model.ground = capi.GroundDesc(capi.TGB_GROUND_EMPTY, (0.0, 1.0, 0.0), 0.0, 0.5, 0.0, 0.0, 0.04)
+        model.gravity = 0.0
+        rods = random_poses(model, n_env, seed=seed, translate=1.0, lift=(0.0, 5.0), yaw_only=True)
+        rng = np.random.default_rng(seed + 1)
+        params = nt.escape_transform_actions(rng.uniform(size=(n_env, 32)), 9.0)
+        ctrl = capi.TGB_CTRL_ESCAPE_SINE
+        p_ctrl = 32
     elif name == "prism":
         model = nt.build_example("3_prism_noground")
         rods = random_poses(model, n_env, seed=seed)
@@ -60,7 +69,8 @@ def build_workload(name, n_env, seed):
 
 
 def workload_desc(name, n_env, H, n_gpus):
-    what = {"superball": "SUPERball (EscapeModel: 6 rods, 24 basic-actuator cables) + EscapeController sine, flat box ground, g=98.1",
+    what = {"superball_noground": "SUPERball + sine controller, NO ground, zero gravity (tuning aid)",
+            "superball": "SUPERball (EscapeModel: 6 rods, 24 basic-actuator cables) + EscapeController sine, flat box ground, g=98.1",
             "prism": "3-prism (3 rods, 9 cables), no ground, g=981 (contact-free drop)"}[name]
     return "%s; %d envs/GPU x %d GPU; dt=1e-3; %d sim steps per launch" % (what, n_env, n_gpus, H)
 
@@ -185,7 +195,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--sim-steps", type=int, default=1000, help="simulation steps per launch (H)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--workload", default="superball", choices=["superball", "prism"])
+    ap.add_argument("--workload", default="superball", choices=["superball", "prism", "superball_noground"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
