@@ -50,7 +50,7 @@ struct tgb_world {
     const tgb_ops* ops = nullptr;
     size_t scalarBytes = 4;
     int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0;
-    int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0, envsPerWarp = 0;
+    int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0;
     cudaStream_t stream = nullptr;
     void* d_state = nullptr;
     double* d_frame = nullptr;
@@ -216,7 +216,6 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.model_t = w->d_model_t; a.model_i = w->d_model_i;
     a.n_env = w->cfg.n_env; a.n_steps = nSteps;
     a.phases = 3;
-    a.envs_per_warp = w->envsPerWarp;
     a.R = w->R; a.C = w->C; a.S = w->S; a.n_inc = w->nInc;
     a.stride = w->stride; a.cap_contacts = w->capContacts; a.frame_body = w->frameBody;
     a.ctrl_kind = w->ctrlKind; a.ctrl_stride = w->ctrlKind != TGB_CTRL_NONE ? w->ctrlStride : 0;
@@ -392,12 +391,6 @@ tgb_status tgb_finalize(tgb_world* w) {
     }
     if (threads % 32 || threads < 32 || threads > 128) return fail(TGB_ERR_INVALID_ARGUMENT, "bad block size");
     w->threads = threads;
-    /* environments per warp: all 32 / lanes groups by default; TGB_ENVS_PER_WARP trades lane occupancy for more warps */
-    w->envsPerWarp = 32 / w->lanes;
-    if (const char* epw = std::getenv("TGB_ENVS_PER_WARP")) {
-        const int v = std::atoi(epw);
-        if (v >= 1 && v <= 32 / w->lanes) w->envsPerWarp = v;
-    }
 
     std::vector<unsigned char> tbytes;
     std::vector<int> ints;
@@ -806,7 +799,7 @@ tgb_status tgb_launch_count(const tgb_world* w, int64_t* out) {
 tgb_status tgb_launch_geometry(const tgb_world* w, int32_t* lanes_per_env, int32_t* block, int32_t* grid) {
     if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
     if (!w->finalized) return fail(TGB_ERR_STATE, "world is not finalized");
-    const int groups = (w->threads / 32) * w->envsPerWarp;
+    const int groups = w->threads / w->lanes;
     if (lanes_per_env) *lanes_per_env = w->lanes;
     if (block) *block = w->threads;
     if (grid) *grid = (w->cfg.n_env + groups - 1) / groups;

@@ -62,7 +62,6 @@ struct tgb_step_args {
     const void* model_t;  /* packed T fields */
     const int* model_i;   /* packed int fields */
     int n_env, n_steps;
-    int envs_per_warp;    /* live env groups per warp (1 .. 32 / lanes per env): fewer, fuller-latency-hiding warps vs. more warps */
     int phases;           /* bit0: world half of tgSimulation::step, bit1: models half (controllers, motors, cable forces) */
     int R, C, S, n_inc;
     int stride;           /* T words per env record */

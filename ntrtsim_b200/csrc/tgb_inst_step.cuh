@@ -10,28 +10,26 @@ namespace {
 
 typedef TGB_SCALAR scalar_t;
 
-template <int LPE, bool GROUND, bool BLOCKSOLVE>
+template <int LPE, bool GROUND>
 cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
     const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, threads, sizeof(scalar_t));
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, BLOCKSOLVE>,
+        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    const int envsPerBlock = (threads / 32) * a.envs_per_warp;
-    const int grid = (a.n_env + envsPerBlock - 1) / envsPerBlock;
-    tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, BLOCKSOLVE><<<grid, threads, smem, s>>>(a);
+    const int groupsPerBlock = threads / LPE;
+    const int grid = (a.n_env + groupsPerBlock - 1) / groupsPerBlock;
+    tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND><<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 template <int LPE>
 cudaError_t launch(const tgb_step_args& a, int threads, cudaStream_t s) {
-    if (a.ground_kind == TGB_GROUND_EMPTY) return launch_impl<LPE, false, false>(a, threads, s);
-    /* with a ground and a CTA of several warps the contact solve is compacted across the CTA */
-    if (threads >= 64) return launch_impl<LPE, true, true>(a, threads, s);
-    return launch_impl<LPE, true, false>(a, threads, s);
+    if (a.ground_kind == TGB_GROUND_EMPTY) return launch_impl<LPE, false>(a, threads, s);
+    return launch_impl<LPE, true>(a, threads, s);
 }
 
 } // namespace

@@ -241,15 +241,13 @@ struct ModelView {
    SIMPLE = none / set-point / torque / tension, SINE = EscapeController, CPG = CPG + impedance (its Dormand-Prince integrator
    needs 231 registers).  GROUND = false compiles the contact manifold and the contact solver out (tgEmptyGround).  Keeping the
    hot loop's code small matters: it is ~20 KB of instructions against a 32 KB L1.5 instruction cache, and at 4096 environments
-   there are too few warps per SM to hide instruction-fetch misses.
-   BLOCKSOLVE = the contact solve of all bodies of a CTA that touch the ground is compacted onto consecutive threads (see
-   "block-level contact solve" below); needs a CTA of at least two warps. */
+   there are too few warps per SM to hide instruction-fetch misses. */
 enum { TGB_CLASS_SIMPLE = 0, TGB_CLASS_SINE = 1, TGB_CLASS_CPG = 2 };
 TGB_HOST_DEVICE_INLINE int tgb_ctrl_class(int kind) {
     return kind == TGB_CTRL_CPG_IMPEDANCE ? TGB_CLASS_CPG : kind == TGB_CTRL_ESCAPE_SINE ? TGB_CLASS_SINE : TGB_CLASS_SIMPLE;
 }
 
-template <typename T, int LPE, int CLASS, bool GROUND, bool BLOCKSOLVE>
+template <typename T, int LPE, int CLASS, bool GROUND>
 __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename Vec16<T>::type vec_t;
@@ -258,18 +256,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
     const int tid = threadIdx.x;
     const int lane = tid % LPE;
-    /* Only the first envs_per_warp groups of every warp own an environment.  A group without one (beyond envs_per_warp, or past
-       the last environment) shadows the first group of its warp: same environment, same shared-memory region, bit-identical
-       arithmetic, so its writes are the same values to the same addresses; it never stores to global memory.  This keeps every
-       lane in every __syncwarp / shuffle without special cases. */
-    const int groupInWarp = (tid & 31) / LPE;
-    const int warpsPerBlock = blockDim.x / 32;
-    const int groupsPerBlock = warpsPerBlock * a.envs_per_warp;
-    const int warpEnv0 = (blockIdx.x * warpsPerBlock + (tid >> 5)) * a.envs_per_warp;
-    const bool live = groupInWarp < a.envs_per_warp && warpEnv0 + groupInWarp < a.n_env;
-    const int grp = (tid >> 5) * a.envs_per_warp + (live ? groupInWarp : 0);
-    /* the first group of a warp is past the end only in the last, partly filled block: it then shadows the last environment */
-    const int env = live ? warpEnv0 + groupInWarp : (warpEnv0 < a.n_env ? warpEnv0 : a.n_env - 1);
+    const int grp = tid / LPE;
+    const int groupsPerBlock = blockDim.x / LPE;
+    const int envRaw = blockIdx.x * groupsPerBlock + grp;
+    const bool live = envRaw < a.n_env;
+    const int env = live ? envRaw : a.n_env - 1; /* tail groups shadow the last env and never store */
     /* lanes of this group inside the warp, for shuffles */
     const unsigned fullMask = 0xffffffffu;
     const int warpLane = tid & 31;
@@ -312,13 +303,6 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     double* sNodeValue = sK + 21 * C;
     int* sModelI = reinterpret_cast<int*>(reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) +
                                           groupsPerBlock * groupDWords);
-    /* block-level contact solve: two task counters (double-buffered by step parity), one task record and one result record per
-       thread */
-    int* sTaskCount = sModelI + ((a.model_i_words + 3) & ~3);
-    int* sTask = sTaskCount + 4;                                 /* [blockDim][4]: rows offset, nc | anyPen << 8, owner thread, - */
-    T* sTaskT = reinterpret_cast<T*>(sTask + 4 * blockDim.x);   /* [blockDim][2]: inverse mass, friction coefficient */
-    T* sResult = sTaskT + 2 * blockDim.x;                        /* [blockDim][12]: dLin, dAng, push, turn of the owner's body */
-    if (BLOCKSOLVE && tid < 4) sTaskCount[tid] = 0;
 
     /* ---- stage the model and this group's env record ----------------------------------------------------- */
     {
@@ -529,86 +513,13 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         __syncwarp();
     };
 
-    /* ---- projected Gauss-Seidel of one body: split-impulse rows, then velocity rows; ctp = the body's rows in shared memory ---- */
-#define CTP(slot, f) ctp[((slot) * TGB_NCT + (f)) * LPE]
-    auto solveRows = [&](T* ctp, int nc, bool anyPen, T invMass, T mu, V3<T>& dLin, V3<T>& dAng, V3<T>& push, V3<T>& turn) {
-    if (nc > 0 && nc <= 2) {
-        /* one or two contact points (a rod touching with one rim point or lying on a rim line): the rows are read into
-           registers once and all iterations run there; same operations in the same order as the general path below */
-        T rxn[2][3], angN[2][3], invDiagN[2], rhsN[2], rhsPen[2], lamN[2], lamPush[2];
-        T tt[2][3], rxt[2][3], angT[2][3], invDiagT[2], rhsT[2], lamT[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int cc = c < nc ? c : 0;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                rxn[c][j] = CTP(cc, CT_RXN + j); angN[c][j] = CTP(cc, CT_ANGN + j);
-                tt[c][j] = CTP(cc, CT_T + j); rxt[c][j] = CTP(cc, CT_RXT + j); angT[c][j] = CTP(cc, CT_ANGT + j);
-            }
-            invDiagN[c] = CTP(cc, CT_INVDIAGN); rhsN[c] = CTP(cc, CT_RHSN); rhsPen[c] = CTP(cc, CT_RHSPEN);
-            invDiagT[c] = CTP(cc, CT_INVDIAGT); rhsT[c] = CTP(cc, CT_RHST);
-            lamN[c] = T(0); lamPush[c] = T(0); lamT[c] = T(0);
-        }
-        if (anyPen)
-            for (int it = 0; it < a.iterations; ++it) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    if (c >= nc || rhsPen[c] == T(0)) continue;
-                    T delta = rhsPen[c];
-                    const T dv = gn.dot(push) + (rxn[c][0] * turn.x + rxn[c][1] * turn.y + rxn[c][2] * turn.z);
-                    delta -= dv * invDiagN[c];
-                    const T sum = lamPush[c] + delta;
-                    if (sum < T(0)) { delta = -lamPush[c]; lamPush[c] = T(0); }
-                    else lamPush[c] = sum;
-                    push += gn * (invMass * delta);
-                    turn += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
-                }
-            }
-        for (int it = 0; it < a.iterations; ++it) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (c >= nc) continue;
-                T delta = rhsN[c];
-                const T dv = gn.dot(dLin) + (rxn[c][0] * dAng.x + rxn[c][1] * dAng.y + rxn[c][2] * dAng.z);
-                delta -= dv * invDiagN[c];
-                const T sum = lamN[c] + delta;
-                if (sum < T(0)) { delta = -lamN[c]; lamN[c] = T(0); }
-                else lamN[c] = sum;
-                dLin += gn * (invMass * delta);
-                dAng += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                if (c >= nc || !(lamN[c] > T(0))) continue;
-                const V3<T> t(tt[c][0], tt[c][1], tt[c][2]);
-                const T lo = -mu * lamN[c], hi = mu * lamN[c];
-                T delta = rhsT[c];
-                const T dv = t.dot(dLin) + (rxt[c][0] * dAng.x + rxt[c][1] * dAng.y + rxt[c][2] * dAng.z);
-                delta -= dv * invDiagT[c];
-                const T sum = lamT[c] + delta;
-                if (sum < lo) { delta = lo - lamT[c]; lamT[c] = lo; }
-                else if (sum > hi) { delta = hi - lamT[c]; lamT[c] = hi; }
-                else lamT[c] = sum;
-                dLin += t * (invMass * delta);
-                dAng += V3<T>(angT[c][0], angT[c][1], angT[c][2]) * delta;
-            }
-        }
-    } else if (nc > 0) {
-        pgsSharedRows<T>(ctp, LPE, nc, a.iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
-    }
-    };
-#undef CTP
-
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
     for (int step = 0; step < a.n_steps; ++step) {
         /* =============================== world step (tgSimulation.cpp:205) =============================== */
-        V3<T> extLin(T(0), T(0), T(0)), extAng(T(0), T(0), T(0));
-        V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
-        int ncBody = 0;
-        bool anyPenBody = false;
         if (dynamic && doWorld) {
             /* applyGravity + solver-body external impulses */
-            extLin = V3<T>(T(0), (gfy * invMass) * dt, T(0));
+            V3<T> extLin(T(0), (gfy * invMass) * dt, T(0));
+            V3<T> extAng(T(0), T(0), T(0));
             if (gyro) {
                 /* btRigidBody::computeGyroscopicForce, explicit, clamped at maxGyroscopicForce */
                 if (kFast) {
@@ -724,46 +635,72 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             }
 
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
-            if (!BLOCKSOLVE) solveRows(sCt + lane, nc, anyPen, invMass, mu, dLin, dAng, push, turn);
-            ncBody = nc; anyPenBody = anyPen;
-        }
+            V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
+            if (nc > 0 && nc <= 2) {
+                /* one or two contact points (a rod touching with one rim point or lying on a rim line): the rows are read into
+                   registers once and all iterations run there; same operations in the same order as the general path below */
+                T rxn[2][3], angN[2][3], invDiagN[2], rhsN[2], rhsPen[2], lamN[2], lamPush[2];
+                T tt[2][3], rxt[2][3], angT[2][3], invDiagT[2], rhsT[2], lamT[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int cc = c < nc ? c : 0;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        rxn[c][j] = CT(cc, CT_RXN + j); angN[c][j] = CT(cc, CT_ANGN + j);
+                        tt[c][j] = CT(cc, CT_T + j); rxt[c][j] = CT(cc, CT_RXT + j); angT[c][j] = CT(cc, CT_ANGT + j);
+                    }
+                    invDiagN[c] = CT(cc, CT_INVDIAGN); rhsN[c] = CT(cc, CT_RHSN); rhsPen[c] = CT(cc, CT_RHSPEN);
+                    invDiagT[c] = CT(cc, CT_INVDIAGT); rhsT[c] = CT(cc, CT_RHST);
+                    lamN[c] = T(0); lamPush[c] = T(0); lamT[c] = T(0);
+                }
+                if (anyPen)
+                    for (int it = 0; it < a.iterations; ++it) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (c >= nc || rhsPen[c] == T(0)) continue;
+                            T delta = rhsPen[c];
+                            const T dv = gn.dot(push) + (rxn[c][0] * turn.x + rxn[c][1] * turn.y + rxn[c][2] * turn.z);
+                            delta -= dv * invDiagN[c];
+                            const T sum = lamPush[c] + delta;
+                            if (sum < T(0)) { delta = -lamPush[c]; lamPush[c] = T(0); }
+                            else lamPush[c] = sum;
+                            push += gn * (invMass * delta);
+                            turn += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
+                        }
+                    }
+                for (int it = 0; it < a.iterations; ++it) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c >= nc) continue;
+                        T delta = rhsN[c];
+                        const T dv = gn.dot(dLin) + (rxn[c][0] * dAng.x + rxn[c][1] * dAng.y + rxn[c][2] * dAng.z);
+                        delta -= dv * invDiagN[c];
+                        const T sum = lamN[c] + delta;
+                        if (sum < T(0)) { delta = -lamN[c]; lamN[c] = T(0); }
+                        else lamN[c] = sum;
+                        dLin += gn * (invMass * delta);
+                        dAng += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c >= nc || !(lamN[c] > T(0))) continue;
+                        const V3<T> t(tt[c][0], tt[c][1], tt[c][2]);
+                        const T lo = -mu * lamN[c], hi = mu * lamN[c];
+                        T delta = rhsT[c];
+                        const T dv = t.dot(dLin) + (rxt[c][0] * dAng.x + rxt[c][1] * dAng.y + rxt[c][2] * dAng.z);
+                        delta -= dv * invDiagT[c];
+                        const T sum = lamT[c] + delta;
+                        if (sum < lo) { delta = lo - lamT[c]; lamT[c] = lo; }
+                        else if (sum > hi) { delta = hi - lamT[c]; lamT[c] = hi; }
+                        else lamT[c] = sum;
+                        dLin += t * (invMass * delta);
+                        dAng += V3<T>(angT[c][0], angT[c][1], angT[c][2]) * delta;
+                    }
+                }
+            } else if (nc > 0) {
+                pgsSharedRows<T>(sCt + lane, LPE, nc, a.iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
+            }
 
-        /* ---- block-level contact solve -------------------------------------------------------------------------------------
-           Only a few of a warp's 24..32 bodies touch the ground in a given step, yet a warp pays for the solver's instructions as
-           soon as one does.  With a CTA of several warps the bodies that have contact rows are therefore queued (one task per
-           body) and solved by consecutive threads of the CTA, so the solver is issued once per 32 touching bodies instead of once
-           per warp; the arithmetic of a body is unchanged, so results are bit-identical to the per-lane solve. */
-        if (BLOCKSOLVE && doWorld) {
-            const int par = step & 1;
-            if (dynamic && ncBody > 0 && (live || groupInWarp == 0)) {
-                const int slot = atomicAdd(&sTaskCount[par], 1);
-                sTask[4 * slot + 0] = (int)((sCt + lane) - sModelT);
-                sTask[4 * slot + 1] = ncBody | (anyPenBody ? 256 : 0);
-                sTask[4 * slot + 2] = tid;
-                sTaskT[2 * slot + 0] = invMass;
-                sTaskT[2 * slot + 1] = mu;
-            }
-            __syncthreads();
-            const int nTasks = sTaskCount[par];
-            if (tid == 0) sTaskCount[par ^ 1] = 0;
-            for (int t = tid; t < nTasks; t += blockDim.x) {
-                V3<T> tl(T(0), T(0), T(0)), ta(T(0), T(0), T(0)), tp(T(0), T(0), T(0)), tt2(T(0), T(0), T(0));
-                const int code = sTask[4 * t + 1];
-                solveRows(sModelT + sTask[4 * t + 0], code & 255, (code & 256) != 0, sTaskT[2 * t + 0], sTaskT[2 * t + 1], tl, ta, tp, tt2);
-                T* o = sResult + 12 * sTask[4 * t + 2];
-                o[0] = tl.x; o[1] = tl.y; o[2] = tl.z; o[3] = ta.x; o[4] = ta.y; o[5] = ta.z;
-                o[6] = tp.x; o[7] = tp.y; o[8] = tp.z; o[9] = tt2.x; o[10] = tt2.y; o[11] = tt2.z;
-            }
-            __syncthreads();
-            if (dynamic && ncBody > 0) {
-                /* a group without an environment reads the result of the group it shadows */
-                const T* o = sResult + 12 * ((live || groupInWarp == 0) ? tid : tid - groupInWarp * LPE);
-                dLin = V3<T>(o[0], o[1], o[2]); dAng = V3<T>(o[3], o[4], o[5]);
-                push = V3<T>(o[6], o[7], o[8]); turn = V3<T>(o[9], o[10], o[11]);
-            }
-        }
-
-        if (dynamic && doWorld) {
             /* ---- write back, split-impulse correction, integrateTransforms ---- */
             b.v = (b.v + dLin) + extLin;
             b.w = (b.w + dAng) + extAng;
@@ -1070,7 +1007,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
 /* Shared memory a launch of this kernel needs; mirrors the carve-up above. */
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
-    const int groupsPerBlock = (threads / 32) * a.envs_per_warp;
+    const int groupsPerBlock = threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
     int groupTWords = a.stride + 12 * lpe + (sizeofT == 4 ? 12 : 3) * a.C + a.cap_contacts * TGB_NCT * lpe;
     groupTWords = (groupTWords + 3) & ~3;
@@ -1079,8 +1016,7 @@ inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, 
     size_t bytes = (size_t)(modelTWords + groupsPerBlock * groupTWords) * sizeofT;
     bytes = (bytes + 7) & ~(size_t)7;
     bytes += (size_t)groupsPerBlock * groupDWords * sizeof(double);
-    bytes += (size_t)((a.model_i_words + 3) & ~3) * sizeof(int);
-    if (threads >= 64) bytes += (size_t)(4 + 4 * threads) * sizeof(int) + (size_t)(2 + 12) * threads * sizeofT; /* block-level solve */
+    bytes += (size_t)a.model_i_words * sizeof(int);
     return bytes + 16;
 }
 
