@@ -34,6 +34,9 @@
 
 #include <type_traits>
 
+#ifndef TGB_MATRIX_PGS
+#define TGB_MATRIX_PGS 1
+#endif
 #ifndef TGB_CABLE_UNROLL
 #define TGB_CABLE_UNROLL 0 /* 0 = automatic */
 #endif
@@ -668,6 +671,67 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                             turn += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
                         }
                     }
+                if (kFast && TGB_MATRIX_PGS) {
+                    /* Single precision: the same projected Gauss-Seidel in matrix form.  With A[r][s] = J_r M^-1 J_s^T over the
+                       rows (N0, N1, T0, T1) the relative velocity change dv_r of every row is carried along and updated by one
+                       multiply-add per applied impulse, instead of being re-formed from the body's velocity change by two dot
+                       products: the dependent chain per row drops from ~10 to ~5 operations and the instruction count by ~4x.
+                       Equal in exact arithmetic to the sequential-impulse form (kept for double precision, the parity path). */
+                    T jl[4][3], ja[4][3], bl[4][3], ba[4][3], A[4][4], dv[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        jl[c][0] = gn.x; jl[c][1] = gn.y; jl[c][2] = gn.z;
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            ja[c][j] = rxn[c][j]; ba[c][j] = angN[c][j]; bl[c][j] = jl[c][j] * invMass;
+                            jl[2 + c][j] = tt[c][j]; ja[2 + c][j] = rxt[c][j]; ba[2 + c][j] = angT[c][j]; bl[2 + c][j] = tt[c][j] * invMass;
+                        }
+                    }
+                    const bool two = nc > 1;
+                    /* A is symmetric: the upper triangle is computed (only the rows of the first contact when there is one) */
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int q = r; q < 4; ++q) {
+                            T v = T(0);
+                            if (two || ((r & 1) == 0 && (q & 1) == 0))
+                                v = (jl[r][0] * bl[q][0] + jl[r][1] * bl[q][1] + jl[r][2] * bl[q][2]) +
+                                    (ja[r][0] * ba[q][0] + ja[r][1] * ba[q][1] + ja[r][2] * ba[q][2]);
+                            A[r][q] = v;
+                            A[q][r] = v;
+                        }
+                    for (int it = 0; it < a.iterations; ++it) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (c == 1 && !two) continue;
+                            T delta = rhsN[c] - dv[c] * invDiagN[c];
+                            const T sum = lamN[c] + delta;
+                            if (sum < T(0)) { delta = -lamN[c]; lamN[c] = T(0); }
+                            else lamN[c] = sum;
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) dv[r] += A[r][c] * delta;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if ((c == 1 && !two) || !(lamN[c] > T(0))) continue;
+                            const T lo = -mu * lamN[c], hi = mu * lamN[c];
+                            T delta = rhsT[c] - dv[2 + c] * invDiagT[c];
+                            const T sum = lamT[c] + delta;
+                            if (sum < lo) { delta = lo - lamT[c]; lamT[c] = lo; }
+                            else if (sum > hi) { delta = hi - lamT[c]; lamT[c] = hi; }
+                            else lamT[c] = sum;
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) dv[r] += A[r][2 + c] * delta;
+                        }
+                    }
+                    /* the body's velocity change from the accumulated impulses */
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c == 1 && !two) continue;
+                        dLin += V3<T>(bl[c][0], bl[c][1], bl[c][2]) * lamN[c] + V3<T>(bl[2 + c][0], bl[2 + c][1], bl[2 + c][2]) * lamT[c];
+                        dAng += V3<T>(ba[c][0], ba[c][1], ba[c][2]) * lamN[c] + V3<T>(ba[2 + c][0], ba[2 + c][1], ba[2 + c][2]) * lamT[c];
+                    }
+                } else
                 for (int it = 0; it < a.iterations; ++it) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
