@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     if (LPE < 32) { while ((groupTWords & 31) != (LPE < 4 ? 4 : LPE)) groupTWords += 4; }
     T* sGroupT = sModelT + modelTWords + grp * groupTWords;
     T* sState = sGroupT;                       /* env record: bodies then cables */
-    T* sPose = sState + a.stride;              /* [12][LPE] : pos3, basis9 of each body */
+    T* sPose = sState + a.stride;              /* [LPE][12] : pos3, basis9 of each body, one 16-byte aligned record per body */
     T* sJ = sPose + poseWords;                 /* [C][3] */
     T* sCt = sJ + jWords;                      /* [cap][TGB_NCT][LPE] */
     constexpr bool cpgOn = CLASS == TGB_CLASS_CPG;
@@ -390,11 +390,12 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
     auto publishPose = [&]() {
         if (hasBody) {
-            sPose[0 * LPE + lane] = b.x.x; sPose[1 * LPE + lane] = b.x.y; sPose[2 * LPE + lane] = b.x.z;
+            /* 128-bit stores / loads: a body's record is 12 scalars = 3 (float) or 6 (double) vectors */
+            T rec[12] = {b.x.x, b.x.y, b.x.z, b.B.m[0][0], b.B.m[0][1], b.B.m[0][2], b.B.m[1][0], b.B.m[1][1], b.B.m[1][2],
+                         b.B.m[2][0], b.B.m[2][1], b.B.m[2][2]};
+            vec_t* dst = reinterpret_cast<vec_t*>(sPose + 12 * lane);
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) sPose[(3 + i * 3 + j) * LPE + lane] = b.B.m[i][j];
+            for (int i = 0; i < 12 / VN; ++i) dst[i] = *reinterpret_cast<vec_t*>(&rec[i * VN]);
         }
     };
     publishPose();
@@ -827,13 +828,22 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 q.k = M.cable(CF_K, c); q.damp = M.cable(CF_C, c);
                 q.tVel = M.cable(CF_TVEL, c); q.maxTens = M.cable(CF_MAXTENS, c); q.maxStretch = M.cable(CF_MAXSTRETCH, c);
                 q.minAL = M.cable(CF_MINAL, c); q.minRL = M.cable(CF_MINRL, c);
-                const V3<T> xa(sPose[0 * LPE + ia], sPose[1 * LPE + ia], sPose[2 * LPE + ia]);
-                const V3<T> xb(sPose[0 * LPE + ib], sPose[1 * LPE + ib], sPose[2 * LPE + ib]);
+                T pa[12], pb[12];
+                {
+                    const vec_t* srcA = reinterpret_cast<const vec_t*>(sPose + 12 * ia);
+                    const vec_t* srcB = reinterpret_cast<const vec_t*>(sPose + 12 * ib);
+#pragma unroll
+                    for (int i = 0; i < 12 / VN; ++i) {
+                        *reinterpret_cast<vec_t*>(&pa[i * VN]) = srcA[i];
+                        *reinterpret_cast<vec_t*>(&pb[i * VN]) = srcB[i];
+                    }
+                }
+                const V3<T> xa(pa[0], pa[1], pa[2]), xb(pb[0], pb[1], pb[2]);
                 M3<T> Ba, Bb;
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) { Ba.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ia]; Bb.m[i][j] = sPose[(3 + i * 3 + j) * LPE + ib]; }
+                    for (int j = 0; j < 3; ++j) { Ba.m[i][j] = pa[3 + i * 3 + j]; Bb.m[i][j] = pb[3 + i * 3 + j]; }
                 /* anchors: tgBulletSpringCableAnchor.cpp:83-87 */
                 q.ra = Ba * la; q.rb = Bb * lb;
                 const V3<T> p1 = q.ra + xa, p2 = q.rb + xb;
