@@ -9,8 +9,8 @@ tgb_step(world, dt, H) that advances every environment H = --sim-steps simulatio
 registers/shared memory for the H steps; HBM is touched at the launch boundaries).
 
   value  env-steps/s with the state resident in HBM, CUDA events on the world's stream, L2 flushed between steps
-  e2e    the same through tgb_rollout_host with pinned HOST buffers: H2D of rod + cable state, H steps, D2H of rod
-         state + cable observations, all inside the timed region
+  e2e    the same episodes through tgb_rollout_host with pinned HOST buffers: H2D of rod + cable state, H steps, D2H of rod
+         state + cable observations, all inside the timed region; call i+1 starts from the host copy of call i's results
   roofline  algorithmic bytes (2*4*(13R+2C)+4*P_ctrl = 1136 B per env-step) x env-steps per launch /
             launch duration against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the CPU oracle (FP64 restatement of the NTRTsim/Bullet-2.82 path; Bullet is not in the reference tree,
@@ -301,10 +301,20 @@ def main():
     cab_out_t, cab_out = pinned(np.zeros((n_env, w.C, capi.CABLE_OBS_DOUBLES)))
     h2d = rods_p.nbytes + cab_p.nbytes
     d2h = rod_out.nbytes + cab_out.nbytes
+    # The end-to-end arm replays the same episodes as the device-resident arm: it restarts from the seeded initial state and
+    # controller time, and every call's inputs are the previous call's outputs (rod records; cable rest length and length),
+    # handed over on the host.  Warm-up calls = the warm-up episodes above, so timed call i simulates the same second of
+    # each rollout as timed step i above.  Each timed call moves that step's inputs host->device and its results back.
     if ctrl:
         w.set_controller(ctrl, params)
-    for _ in range(2):
+
+    def hand_over():
+        rods_p[...] = rod_out
+        cab_p[..., 0] = cab_out[..., 0]  # rest length
+        cab_p[..., 1] = cab_out[..., 1]  # current length = the next step's previous length
+    for _ in range(args.warmup):
         w.rollout_host(rods_p, cab_p, model.dt, H, rod_out, cab_out)
+        hand_over()
     barrier()
     e2e_s = []
     for _ in range(args.steps):
@@ -312,6 +322,7 @@ def main():
         t0 = time.perf_counter()
         w.rollout_host(rods_p, cab_p, model.dt, H, rod_out, cab_out)  # synchronises its stream before returning
         e2e_s.append(time.perf_counter() - t0)
+        hand_over()
     barrier()
     e2e_total = sum(e2e_s)
     e2e_checksum = float(np.abs(cab_out[..., 2]).mean())

@@ -75,6 +75,12 @@ struct tgb_world {
     int64_t launches = 0;
     double heightLo = 1.0, heightHi = 0.0; /* disabled */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long* d_stats = nullptr; /* TGB_STATS=1 with a -DTGB_STATS build of the kernels (tools/) */
+    /* tgb_rollout_host pipelines env chunks over these streams: the copies of one chunk overlap the steps of the others */
+    enum { kPipe = 4 };
+    cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipeDone[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipeStart = nullptr;
 
     tgb::tgb_io_args ioArgs(int envBegin, int envCount) const {
         tgb::tgb_io_args a;
@@ -120,6 +126,11 @@ struct tgb_world {
         if (d_cpg_state) cudaFree(d_cpg_state);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (int i = 0; i < kPipe; ++i) {
+            if (pipeDone[i]) cudaEventDestroy(pipeDone[i]);
+            if (pipe[i]) cudaStreamDestroy(pipe[i]);
+        }
+        if (pipeStart) cudaEventDestroy(pipeStart);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -215,6 +226,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.state = w->d_state; a.frame = w->d_frame; a.ctrl = w->ctrlKind != TGB_CTRL_NONE ? w->d_ctrl : nullptr; a.status = w->d_status;
     a.model_t = w->d_model_t; a.model_i = w->d_model_i;
     a.n_env = w->cfg.n_env; a.n_steps = nSteps;
+    a.stats = w->d_stats;
     a.phases = 3;
     a.R = w->R; a.C = w->C; a.S = w->S; a.n_inc = w->nInc;
     a.stride = w->stride; a.cap_contacts = w->capContacts; a.frame_body = w->frameBody;
@@ -245,6 +257,17 @@ tgb_status launchStep(tgb_world* w, double dt, int nSteps, int phases = 3) {
     if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
     w->launches += 1;
     if (phases & 1) w->time += dt * nSteps;
+    return TGB_OK;
+}
+
+/* the same for the environments [envBegin, envBegin + envCount) only, on stream s; does not advance the world's clock */
+tgb_status launchStepRange(tgb_world* w, double dt, int nSteps, int envBegin, int envCount, cudaStream_t s) {
+    tgb_step_args a = stepArgs(w, dt, nSteps);
+    a.env_begin = envBegin;
+    a.n_env = envBegin + envCount;
+    cudaError_t e = w->ops->step(a, w->lanes, w->threads, s);
+    if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
+    w->launches += 1;
     return TGB_OK;
 }
 
@@ -283,6 +306,12 @@ tgb_status tgb_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, t
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
     if (e != cudaSuccess) { w->release(); delete w; return cudaFail(e, "tgb_create: stream/event creation"); }
+    if (std::getenv("TGB_STATS")) {
+        if (cudaMalloc(&w->d_stats, 128 * sizeof(unsigned long long)) == cudaSuccess) {
+            cudaMemset(w->d_stats, 0, 128 * sizeof(unsigned long long));
+            cudaMemset(w->d_stats + 53, 0xff, sizeof(unsigned long long));
+        }
+    }
     *out = w;
     return TGB_OK;
 }
@@ -291,6 +320,15 @@ tgb_status tgb_destroy(tgb_world* w) {
     if (!w) return TGB_OK;
     cudaSetDevice(w->cfg.device);
     if (w->stream) cudaStreamSynchronize(w->stream);
+    if (w->d_stats) {
+        unsigned long long h[128];
+        if (cudaMemcpy(h, w->d_stats, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            std::fprintf(stderr, "TGB_STATS");
+            for (int i = 0; i < 128; ++i) std::fprintf(stderr, " %llu", h[i]);
+            std::fprintf(stderr, "\n");
+        }
+        cudaFree(w->d_stats);
+    }
     w->release();
     delete w;
     return TGB_OK;
@@ -693,31 +731,68 @@ tgb_status tgb_rollout_host(tgb_world* w, const double* rod_state_in, const doub
     if (n_steps < 0) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_rollout_host: negative step count");
     const int n = w->cfg.n_env;
     const size_t rodN = (size_t)n * w->R * TGB_NBS, cabInN = (size_t)n * w->C * 2, cabOutN = (size_t)n * w->C * TGB_CABLE_OBS_DOUBLES;
-    const size_t stageN = std::max(rodN + cabInN, rodN + cabOutN);
+    const size_t stageN = rodN + cabInN + cabOutN; /* chunks in flight use disjoint staging regions */
     tgb_status st = w->ensureStage(stageN);
     if (st != TGB_OK) return st;
-    const tgb::tgb_io_args io = w->ioArgs(0, n);
-    if (rod_state_in) {
-        TGB_CUDA(cudaMemcpyAsync(w->d_stage, rod_state_in, rodN * sizeof(double), cudaMemcpyHostToDevice, w->stream));
-        TGB_CUDA(w->ops->pack_rods(io, w->d_stage, 0, w->stream));
-        TGB_CUDA(w->ops->com(io, 0, nullptr, nullptr, w->stream));
+    /* Environments are independent, so a large batch is cut into chunks that run on their own streams: the host-to-device copy
+       and packing of one chunk, the steps of another and the device-to-host copy of a third overlap (TGB_ROLLOUT_CHUNKS=1..4
+       overrides the choice for batches of at least 1024 environments). */
+    int chunks = n >= 16384 ? (int)tgb_world::kPipe : 1; /* below that the copies are a few percent of the steps: one launch */
+    {
+        const char* envChunks = std::getenv("TGB_ROLLOUT_CHUNKS");
+        if (envChunks && n >= 1024) chunks = std::max(1, std::min((int)tgb_world::kPipe, std::atoi(envChunks)));
     }
-    if (cable_rest_prev_in && w->C) {
-        TGB_CUDA(cudaMemcpyAsync(w->d_stage + rodN, cable_rest_prev_in, cabInN * sizeof(double), cudaMemcpyHostToDevice, w->stream));
-        TGB_CUDA(w->ops->pack_cables(io, w->d_stage + rodN, 0, 0, w->stream));
+    if (chunks > 1 && !w->pipeStart) {
+        cudaError_t e = cudaEventCreateWithFlags(&w->pipeStart, cudaEventDisableTiming);
+        for (int i = 0; i < tgb_world::kPipe && e == cudaSuccess; ++i) {
+            e = cudaStreamCreateWithFlags(&w->pipe[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->pipeDone[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) return cudaFail(e, "tgb_rollout_host: stream/event creation");
     }
-    if (n_steps > 0) {
-        st = launchStep(w, dt, n_steps);
-        if (st != TGB_OK) return st;
+    if (chunks > 1) TGB_CUDA(cudaEventRecord(w->pipeStart, w->stream));
+    const int groups = w->threads / w->lanes;
+    int per = (n + chunks - 1) / chunks;
+    per = (per + groups - 1) / groups * groups; /* whole CTAs per chunk */
+    double* dRodStage = w->d_stage;
+    double* dCabStage = w->d_stage + rodN;
+    double* dObsStage = dCabStage + cabInN;
+    for (int k = 0; k < chunks; ++k) {
+        const int b = k * per, cnt = std::min(per, n - b);
+        if (cnt <= 0) break;
+        cudaStream_t s = chunks > 1 ? w->pipe[k] : w->stream;
+        if (chunks > 1) TGB_CUDA(cudaStreamWaitEvent(s, w->pipeStart, 0));
+        const tgb::tgb_io_args io = w->ioArgs(b, cnt);
+        const size_t rodOff = (size_t)b * w->R * TGB_NBS, rodCnt = (size_t)cnt * w->R * TGB_NBS;
+        if (rod_state_in) {
+            TGB_CUDA(cudaMemcpyAsync(dRodStage + rodOff, rod_state_in + rodOff, rodCnt * sizeof(double), cudaMemcpyHostToDevice, s));
+            TGB_CUDA(w->ops->pack_rods(io, dRodStage + rodOff, 0, s));
+            TGB_CUDA(w->ops->com(io, 0, nullptr, nullptr, s));
+        }
+        if (cable_rest_prev_in && w->C) {
+            const size_t off = (size_t)b * w->C * 2, cn = (size_t)cnt * w->C * 2;
+            TGB_CUDA(cudaMemcpyAsync(dCabStage + off, cable_rest_prev_in + off, cn * sizeof(double), cudaMemcpyHostToDevice, s));
+            TGB_CUDA(w->ops->pack_cables(io, dCabStage + off, 0, 0, s));
+        }
+        if (n_steps > 0) {
+            st = launchStepRange(w, dt, n_steps, b, cnt, s);
+            if (st != TGB_OK) return st;
+        }
+        if (rod_state_out) {
+            TGB_CUDA(w->ops->unpack_rods(io, dRodStage + rodOff, s));
+            TGB_CUDA(cudaMemcpyAsync(rod_state_out + rodOff, dRodStage + rodOff, rodCnt * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        if (cable_obs_out && w->C) {
+            const size_t off = (size_t)b * w->C * TGB_CABLE_OBS_DOUBLES, cn = (size_t)cnt * w->C * TGB_CABLE_OBS_DOUBLES;
+            TGB_CUDA(w->ops->cable_obs(io, dObsStage + off, s));
+            TGB_CUDA(cudaMemcpyAsync(cable_obs_out + off, dObsStage + off, cn * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        if (chunks > 1) {
+            TGB_CUDA(cudaEventRecord(w->pipeDone[k], s));
+            TGB_CUDA(cudaStreamWaitEvent(w->stream, w->pipeDone[k], 0));
+        }
     }
-    if (rod_state_out) {
-        TGB_CUDA(w->ops->unpack_rods(io, w->d_stage, w->stream));
-        TGB_CUDA(cudaMemcpyAsync(rod_state_out, w->d_stage, rodN * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
-    }
-    if (cable_obs_out && w->C) {
-        TGB_CUDA(w->ops->cable_obs(io, w->d_stage + rodN, w->stream));
-        TGB_CUDA(cudaMemcpyAsync(cable_obs_out, w->d_stage + rodN, cabOutN * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
-    }
+    if (n_steps > 0) w->time += dt * n_steps;
     TGB_CUDA(cudaStreamSynchronize(w->stream));
     return TGB_OK;
 }

@@ -61,7 +61,9 @@ struct tgb_step_args {
     int* status;          /* [n_env] */
     const void* model_t;  /* packed T fields */
     const int* model_i;   /* packed int fields */
-    int n_env, n_steps;
+    unsigned long long* stats; /* instrumentation variant only (-DTGB_STATS, tools/), else unused */
+    int n_env, n_steps;   /* a launch covers environments [env_begin, n_env) */
+    int env_begin;
     int phases;           /* bit0: world half of tgSimulation::step, bit1: models half (controllers, motors, cable forces) */
     int R, C, S, n_inc;
     int stride;           /* T words per env record */

@@ -21,7 +21,8 @@ cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
         configured = smem;
     }
     const int groupsPerBlock = threads / LPE;
-    const int grid = (a.n_env + groupsPerBlock - 1) / groupsPerBlock;
+    const int grid = (a.n_env - a.env_begin + groupsPerBlock - 1) / groupsPerBlock;
+    if (grid <= 0) return cudaSuccess;
     tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND><<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
 }

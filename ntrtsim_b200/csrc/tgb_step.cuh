@@ -37,6 +37,9 @@
 #ifndef TGB_MATRIX_PGS
 #define TGB_MATRIX_PGS 1
 #endif
+#ifndef TGB_SINGLE_CONTACT_PGS
+#define TGB_SINGLE_CONTACT_PGS 1
+#endif
 #ifndef TGB_CABLE_UNROLL
 #define TGB_CABLE_UNROLL 0 /* 0 = automatic */
 #endif
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     const int lane = tid % LPE;
     const int grp = tid / LPE;
     const int groupsPerBlock = blockDim.x / LPE;
-    const int envRaw = blockIdx.x * groupsPerBlock + grp;
+    const int envRaw = a.env_begin + blockIdx.x * groupsPerBlock + grp;
     const bool live = envRaw < a.n_env;
     const int env = live ? envRaw : a.n_env - 1; /* tail groups shadow the last env and never store */
     /* lanes of this group inside the warp, for shuffles */
@@ -518,7 +521,13 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     };
 
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
+#ifdef TGB_STATS
+    const long long statT0 = clock64();
+#endif
     for (int step = 0; step < a.n_steps; ++step) {
+#ifdef TGB_STATS
+        int statNc = 0; bool statPen = false;
+#endif
         /* =============================== world step (tgSimulation.cpp:205) =============================== */
         if (dynamic && doWorld) {
             /* applyGravity + solver-body external impulses */
@@ -571,19 +580,31 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                     if (pl > T(1e-9)) u = perp / pl;
                     else u = col0;
                     const V3<T> wdir = axisDir.cross(u);
-                    int count = 0;
-                    /* heights of the rim points in closed form, used only to skip points that are clearly out of the contact
-                       band before any vector work (same 1e-3 slack as above; accepted points still pass the exact test) */
+                    /* heights of the eight rim points in closed form (two end caps x four directions), used only to drop points
+                       that are clearly out of the contact band before any vector work (same 1e-3 slack as above; a candidate
+                       still has to pass the exact test).  The candidates are collected in a bit mask, then visited in the
+                       manifold's order (end cap major, direction minor): lanes whose contacts sit at different rim points
+                       run the row set-up below together instead of one candidate slot after the other. */
                     const T hCentre = (gn.dot(c) + originHeight) - margin;
                     const T hu = rc * gn.dot(u), hw = rc * gn.dot(wdir);
                     const T skipAbove = SolverConst<T>::breakingThreshold() + T(1e-3);
-                    for (int e = 0; e < 2 && count < 4; ++e) {
+                    unsigned candidates = 0;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
                         const T hEnd = hCentre + (e == 0 ? -hc : hc) * na;
-                        if (hEnd - tabs(hu) - tabs(hw) > skipAbove) continue;
-                        const V3<T> ce = c + axisDir * (e == 0 ? -hc : hc);
-                        for (int k = 0; k < 4 && count < 4; ++k) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
                             const T hk = hEnd + ((k == 0) ? hu : (k == 1) ? hw : (k == 2) ? -hu : -hw);
-                            if (hk > skipAbove) continue;
+                            if (!(hk > skipAbove)) candidates |= 1u << (e * 4 + k);
+                        }
+                    }
+                    int count = 0;
+                    while (candidates != 0 && count < 4) {
+                        const int slot = __ffs(candidates) - 1;
+                        candidates &= candidates - 1;
+                        const int e = slot >> 2, k = slot & 3;
+                        {
+                            const V3<T> ce = c + axisDir * (e == 0 ? -hc : hc);
                             const V3<T> dir = (k == 0) ? u : (k == 1) ? wdir : (k == 2) ? -u : -wdir;
                             const V3<T> pc = ce + dir * rc;
                             const T dist = (gn.dot(pc) + originHeight) - margin;
@@ -638,9 +659,64 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 }
             }
 
+#ifdef TGB_STATS
+            statNc = nc; statPen = anyPen;
+#endif
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
-            if (nc > 0 && nc <= 2) {
+            if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
+                /* Single precision, one contact point (by far the commonest case: a rod end touching the ground): the matrix form
+                   of the solver below for the two rows (normal, friction) of that point, straight-line and branch-free.  The
+                   relative velocity change of each row is carried along: dvN = ANN lamN + ANT lamT, dvT = ANT lamN + ATT lamT. */
+                const V3<T> rxn(CT(0, CT_RXN + 0), CT(0, CT_RXN + 1), CT(0, CT_RXN + 2));
+                const V3<T> angN(CT(0, CT_ANGN + 0), CT(0, CT_ANGN + 1), CT(0, CT_ANGN + 2));
+                const V3<T> t(CT(0, CT_T + 0), CT(0, CT_T + 1), CT(0, CT_T + 2));
+                const V3<T> rxt(CT(0, CT_RXT + 0), CT(0, CT_RXT + 1), CT(0, CT_RXT + 2));
+                const V3<T> angT(CT(0, CT_ANGT + 0), CT(0, CT_ANGT + 1), CT(0, CT_ANGT + 2));
+                const T invDiagN = CT(0, CT_INVDIAGN), rhsN = CT(0, CT_RHSN), rhsPen = CT(0, CT_RHSPEN);
+                const T invDiagT = CT(0, CT_INVDIAGT), rhsT = CT(0, CT_RHST);
+                const V3<T> bn = gn * invMass, bt = t * invMass;
+                const T ANN = gn.dot(bn) + rxn.dot(angN);
+                const T ANT = gn.dot(bt) + rxn.dot(angT);
+                const T ATT = t.dot(bt) + rxt.dot(angT);
+                if (rhsPen != T(0)) {
+                    T lamPush = T(0), dvp = T(0);
+                    for (int it = 0; it < a.iterations; ++it) {
+                        T delta = rhsPen - dvp * invDiagN;
+                        const T sum = lamPush + delta;
+                        const bool neg = sum < T(0);
+                        delta = neg ? -lamPush : delta;
+                        lamPush = neg ? T(0) : sum;
+                        dvp += ANN * delta;
+                    }
+                    push = bn * lamPush;
+                    turn = angN * lamPush;
+                }
+                T lamN = T(0), lamT = T(0), dvN = T(0), dvT = T(0);
+                for (int it = 0; it < a.iterations; ++it) {
+                    T delta = rhsN - dvN * invDiagN;
+                    const T sum = lamN + delta;
+                    const bool neg = sum < T(0);
+                    delta = neg ? -lamN : delta;
+                    lamN = neg ? T(0) : sum;
+                    dvN += ANN * delta;
+                    dvT += ANT * delta;
+                    /* friction row, skipped (zero impulse change) while the normal impulse is zero */
+                    const T hi = mu * lamN, lo = -hi;
+                    T deltaT = rhsT - dvT * invDiagT;
+                    const T sumT = lamT + deltaT;
+                    T newT = sumT;
+                    if (sumT < lo) { deltaT = lo - lamT; newT = lo; }
+                    else if (sumT > hi) { deltaT = hi - lamT; newT = hi; }
+                    const bool on = lamN > T(0);
+                    deltaT = on ? deltaT : T(0);
+                    lamT = on ? newT : lamT;
+                    dvN += ANT * deltaT;
+                    dvT += ATT * deltaT;
+                }
+                dLin = bn * lamN + bt * lamT;
+                dAng = angN * lamN + angT * lamT;
+            } else if (nc > 0 && nc <= 2) {
                 /* one or two contact points (a rod touching with one rim point or lying on a rim line): the rows are read into
                    registers once and all iterations run there; same operations in the same order as the general path below */
                 T rxn[2][3], angN[2][3], invDiagN[2], rhsN[2], rhsPen[2], lamN[2], lamPush[2];
@@ -788,6 +864,22 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
         publishPose();
         __syncwarp();
+#ifdef TGB_STATS
+        if (a.stats) {
+            /* per warp and step: [0..8] histogram of the largest contact count of a lane, [16..48] histogram of the number of
+               lanes with contacts, [49] warp-steps with a split-impulse row, [50] warp-steps */
+            int mx = statNc;
+            for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(fullMask, mx, off));
+            const int touching = __popc(__ballot_sync(fullMask, statNc > 0));
+            const bool pen = __any_sync(fullMask, statPen);
+            if (warpLane == 0) {
+                atomicAdd(a.stats + min(mx, 8), 1ULL);
+                atomicAdd(a.stats + 16 + touching, 1ULL);
+                if (pen) atomicAdd(a.stats + 49, 1ULL);
+                atomicAdd(a.stats + 50, 1ULL);
+            }
+        }
+#endif
 
         /* =============================== models step (tgSimulation.cpp:208-211) =============================== */
         if (!doModels) continue; /* warp-uniform: a world-half-only launch (host observers run between the halves) */
@@ -1024,6 +1116,14 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     }
 #undef CT
 
+#ifdef TGB_STATS
+    if (a.stats && warpLane == 0) {
+        const unsigned long long cyc = (unsigned long long)(clock64() - statT0);
+        atomicAdd(a.stats + 51, cyc); atomicMax(a.stats + 52, cyc); atomicMin(a.stats + 53, cyc); atomicAdd(a.stats + 54, 1ULL);
+        const int bucket = (int)min(31ULL, cyc * 16ULL / (unsigned long long)(a.n_steps * 14000LL)); /* cycles per step / 14000 * 16 */
+        atomicAdd(a.stats + 64 + bucket, 1ULL);
+    }
+#endif
     /* ---- store: bodies back into the record, record back to HBM, frame, status ---------------------------- */
     if (hasBody) {
         T* s = sState + lane * TGB_NBS;

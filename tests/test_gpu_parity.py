@@ -271,6 +271,28 @@ def test_rollout_host_equals_set_step_get():
     assert np.array_equal(rd, a[0]) and np.array_equal(cd, a[1])
 
 
+def test_pipelined_rollout_host_equals_set_step_get(monkeypatch):
+    """For large batches (or with TGB_ROLLOUT_CHUNKS set) tgb_rollout_host cuts the batch into chunks on separate streams
+    (copies of one chunk overlap the steps of another); a ragged size must give bit-identical results to one launch
+    over the whole batch."""
+    monkeypatch.setenv("TGB_ROLLOUT_CHUNKS", "4")
+    model = nt.build_example("Escape_c3")
+    n_env, steps = 1500 + 3, 30
+    rods, cab, params = escape_inputs(model, n_env, seed=78)
+    a = device_rollout(model, rods, cab, steps, "f32", capi.TGB_CTRL_ESCAPE_SINE, params)
+    w = nt.BatchedWorld(model, n_env, precision="f32")
+    w.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params)
+    rd, cd = w.rollout_host(rods, cab, model.dt, steps)
+    assert w.launch_count() == 4
+    assert abs(w.time() - steps * model.dt) < 1e-12
+    # a second rollout from the same inputs (controller time restarted): no state leaks between chunks or calls
+    w.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params)
+    rd2, cd2 = w.rollout_host(rods, cab, model.dt, steps)
+    w.close()
+    assert np.array_equal(rd, a[0]) and np.array_equal(cd, a[1])
+    assert np.array_equal(rd2, a[0]) and np.array_equal(cd2, a[1])
+
+
 @pytest.mark.parametrize("precision", ["f32", "f64"])
 def test_bit_identical_across_launch_geometry(precision):
     """The arithmetic of a body / cable does not depend on which lane runs it: results are bit-identical across
