@@ -55,6 +55,7 @@ struct tgb_world {
     void* d_state = nullptr;
     double* d_frame = nullptr;
     double* d_ctrl = nullptr;
+    double* d_sine = nullptr;   /* sine controller phase pairs, see tgb_step_args::sine_state */
     double* d_com0 = nullptr;
     int* d_status = nullptr;
     void* d_model_t = nullptr;
@@ -114,6 +115,7 @@ struct tgb_world {
         if (d_state) cudaFree(d_state);
         if (d_frame) cudaFree(d_frame);
         if (d_ctrl) cudaFree(d_ctrl);
+        if (d_sine) cudaFree(d_sine);
         if (d_com0) cudaFree(d_com0);
         if (d_status) cudaFree(d_status);
         if (d_model_t) cudaFree(d_model_t);
@@ -224,6 +226,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     tgb_step_args a;
     std::memset(&a, 0, sizeof(a));
     a.state = w->d_state; a.frame = w->d_frame; a.ctrl = w->ctrlKind != TGB_CTRL_NONE ? w->d_ctrl : nullptr; a.status = w->d_status;
+    a.sine_state = w->ctrlKind == TGB_CTRL_ESCAPE_SINE ? w->d_sine : nullptr;
     a.model_t = w->d_model_t; a.model_i = w->d_model_i;
     a.n_env = w->cfg.n_env; a.n_steps = nSteps;
     a.stats = w->d_stats;
@@ -580,9 +583,11 @@ tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, 
         if (w->d_ctrl) { cudaFree(w->d_ctrl); w->d_ctrl = nullptr; }
         TGB_CUDA(cudaMalloc(&w->d_ctrl, (size_t)n * need * sizeof(double)));
         w->ctrlStride = need;
+        if (kind == TGB_CTRL_ESCAPE_SINE && !w->d_sine) TGB_CUDA(cudaMalloc(&w->d_sine, (size_t)n * 48 * sizeof(double)));
         {
             tgb_step_args a = stepArgs(w, 1e-3, 1);
             a.ctrl_stride = need;
+            a.ctrl_kind = kind;
             if (w->ops->step_smem(a, w->lanes, w->threads) > 227 * 1024) return fail(TGB_ERR_UNSUPPORTED, "controller parameters do not fit in shared memory");
         }
     }
@@ -594,9 +599,11 @@ tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, 
         } else {
             TGB_CUDA(cudaMemcpy(w->d_ctrl + (size_t)env_begin * need, params, (size_t)env_count * need * sizeof(double), cudaMemcpyHostToDevice));
         }
-        /* controller time restarts (EscapeController::onSetup: m_totalTime = 0) */
+        /* controller time restarts (EscapeController::onSetup: m_totalTime = 0); the spare word after it is cleared too: the
+           sine phases of these environments start again from exact values */
         TGB_CUDA(cudaStreamSynchronize(w->stream));
-        TGB_CUDA(cudaMemset2D(w->d_frame + (size_t)env_begin * TGB_NFR + FR_CTRLTIME, TGB_NFR * sizeof(double), 0, sizeof(double), env_count));
+        static_assert(FR_SPARE == FR_CTRLTIME + 1, "controller time and spare word are adjacent");
+        TGB_CUDA(cudaMemset2D(w->d_frame + (size_t)env_begin * TGB_NFR + FR_CTRLTIME, TGB_NFR * sizeof(double), 0, 2 * sizeof(double), env_count));
     }
     w->ctrlKind = kind;
     return TGB_OK;

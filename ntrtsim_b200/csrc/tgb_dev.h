@@ -7,7 +7,7 @@
  *                                   {rest length, previous length, preferred length, motor velocity}; stride is padded
  *                                   to a 16-byte multiple so that a group of lanes moves its record with 128-bit
  *                                   accesses and a CTA's records form one contiguous span.
- *   frame  double[n_env][8]         env frame: origin O(3), velocity V(3), controller time, spare.  World position of
+ *   frame  double[n_env][8]         env frame: origin O(3), velocity V(3), controller time, spare (sine controller: 1 when sine_state holds this env's phases).  World position of
  *                                   a body = O + pos, world velocity = V + linvel.  Keeping the common translation of a
  *                                   free-falling structure in double keeps the float state small, so cable stretch
  *                                   (a difference of anchor positions) does not lose digits far from the origin.
@@ -58,6 +58,8 @@ struct tgb_step_args {
     void* state;          /* T[n_env][stride] */
     double* frame;        /* [n_env][TGB_NFR] */
     const double* ctrl;   /* [n_env][ctrl_stride] or NULL */
+    double* sine_state;   /* sine controller, single precision: [n_env][24][2] (sin, cos) of each cable's phase; valid when the frame's
+                             spare word is non-zero */
     int* status;          /* [n_env] */
     const void* model_t;  /* packed T fields */
     const int* model_i;   /* packed int fields */

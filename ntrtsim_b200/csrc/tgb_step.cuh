@@ -210,22 +210,23 @@ struct CableRegs {
     T L, k, damp, tVel, maxTens, maxStretch, minAL, minRL;
     T rest, prev, pref, motorVel, desiredTorque, velocity;
     /* tgBasicActuator::moveMotors, tgBasicActuator.cpp:170-225 */
-    TGB_D void moveMotors(T dtm) {
+    TGB_D void moveMotors(T dtm, bool enable = true) {
+        /* written with selects only: the same values as the reference's branches, no divergence in the cable phase */
         const T stepSize = tVel * dtm;
-        if ((L - pref) * k > maxTens) pref = L - maxStretch;
-        const T diff = pref - rest;
-        const T fabsDiff = tabs(diff);
-        if ((L > minAL) || (diff > T(0))) {
-            if (fabsDiff > stepSize) rest += tcopysign(stepSize, diff); /* (diff / |diff|) * stepSize, exactly */
-            else rest += diff;
-        }
-        rest = (rest > minRL) ? rest : minRL;
+        const T newPref = ((L - pref) * k > maxTens) ? L - maxStretch : pref;
+        const T diff = newPref - rest;
+        const T move = (tabs(diff) > stepSize) ? tcopysign(stepSize, diff) : diff; /* (diff / |diff|) * stepSize, exactly */
+        T newRest = ((L > minAL) || (diff > T(0))) ? rest + move : rest;
+        newRest = (newRest > minRL) ? newRest : minRL;
+        pref = enable ? newPref : pref;
+        rest = enable ? newRest : rest;
     }
 };
 
 /* doubles of shared memory per env group: controller row, sine cumulative phases, CPG work space */
 __host__ __device__ inline int tgb_group_double_words(const tgb_step_args& a) {
     int n = a.ctrl_stride + 8;
+    if (a.ctrl_kind == TGB_CTRL_ESCAPE_SINE) n += 4 * 24 + 2 * 8; /* per cable (sin, cos, amplitude, offset), per cluster (cos, sin) of the phase step */
     if (a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) n += 3 * a.cpg_n_pairs + (3 + 3 + 3 + 21 + 1) * a.C;
     return n;
 }
@@ -301,6 +302,9 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     double* sCtrl = sD;                        /* controller parameter row */
     double* sCum = sD + a.ctrl_stride;         /* sine controller: cumulative phase per cluster */
     /* CPG: pair table (weight, cos phase, sin phase), state x, stage state, published (sin, cos, r), k1..k7, node values */
+    /* sine controller, single precision: (sin, cos) of each cable's phase advanced by a rotation per step, see below */
+    double* sSine = sCum + 8;                  /* [24][4] sin, cos, amplitude, offset */
+    double* sRot = sSine + 4 * 24;             /* [8][2] cos, sin of frequency * dt */
     double* sPair = sCum + 8;
     double* sX = sPair + 3 * a.cpg_n_pairs;
     double* sXt = sX + 3 * C;
@@ -334,9 +338,10 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     const int ctrlKind = a.ctrl_kind;
 
     /* env frame (every lane of the group keeps an identical copy) */
-    double Ox, Oy, Oz, Vx, Vy, Vz, ctrlTime;
+    double Ox, Oy, Oz, Vx, Vy, Vz, ctrlTime, frameSpare;
     {
         const double* f = a.frame + (size_t)env * TGB_NFR;
+        frameSpare = f[FR_SPARE];
         Ox = f[FR_O]; Oy = f[FR_O + 1]; Oz = f[FR_O + 2];
         Vx = f[FR_V]; Vy = f[FR_V + 1]; Vz = f[FR_V + 2];
         ctrlTime = f[FR_CTRLTIME];
@@ -347,6 +352,34 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         double ph = 0.0;
         sCum[0] = 0.0;
         for (int c = 1; c < 8; ++c) { ph += sCtrl[c * 4 + 2]; sCum[c] = ph; }
+    }
+    /* Single precision: the sine of each cable's phase is not re-evaluated every step but advanced by the rotation
+       (cos, sin)(frequency dt) in double precision (error ~1e-16 per step, far below single-precision resolution; saves a
+       double-precision range reduction and a sine per cable and step).  The (sin, cos) pairs start from exact values when the
+       controller is installed and travel through HBM between launches, so results do not depend on how an episode is cut
+       into launches. */
+    const bool sineRecurrence = sineOn && kFast && a.sine_state != nullptr;
+    if (sineRecurrence) {
+        __syncwarp();
+        double* gsine = a.sine_state + (size_t)env * 48;
+        for (int c = lane; c < 24 && c < C; c += LPE) {
+            const int cluster = c < 16 ? (c >> 2) : 4 + ((c - 16) >> 1);
+            double sn, cn;
+            if (frameSpare != 0.0) {
+                sn = gsine[2 * c]; cn = gsine[2 * c + 1];
+            } else {
+                const bool firstOfCluster = c < 16 ? ((c & 3) == 0) : (((c - 16) & 1) == 0);
+                const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
+                sincos(sCtrl[cluster * 4 + 1] * ctrlTime + phase, &sn, &cn);
+            }
+            sSine[4 * c] = sn; sSine[4 * c + 1] = cn; sSine[4 * c + 2] = sCtrl[cluster * 4 + 0]; sSine[4 * c + 3] = sCtrl[cluster * 4 + 3];
+        }
+        for (int cl = lane; cl < 8; cl += LPE) {
+            double sn, cn;
+            sincos(sCtrl[cl * 4 + 1] * a.dt, &sn, &cn);
+            sRot[2 * cl] = cn; sRot[2 * cl + 1] = sn;
+        }
+        __syncwarp();
     }
 
     double cpgUpdateTime = 0.0, cpgCableTime = 0.0;
@@ -987,13 +1020,24 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                     if (c < 24) {
                         /* EscapeController::setPreferredMuscleLengths, EscapeController.cpp:245-291 */
                         const int cluster = c < 16 ? (c >> 2) : 4 + ((c - 16) >> 1);
-                        const bool firstOfCluster = c < 16 ? ((c & 3) == 0) : (((c - 16) & 1) == 0);
-                        const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
-                        const double arg = sCtrl[cluster * 4 + 1] * ctrlTime + phase;
-                        T newLength = (T)sCtrl[cluster * 4 + 0] * sinPhase(arg, T(0)) + (T)sCtrl[cluster * 4 + 3];
+                        T newLength;
+                        if (sineRecurrence) {
+                            double* sc = sSine + 4 * c;
+                            const double s0 = sc[0], c0r = sc[1], cd = sRot[2 * cluster], sd = sRot[2 * cluster + 1];
+                            const double s1 = s0 * cd + c0r * sd, c1 = c0r * cd - s0 * sd;
+                            sc[0] = s1; sc[1] = c1;
+                            newLength = (T)(sc[2] * s1 + sc[3]);
+                        } else {
+                            const bool firstOfCluster = c < 16 ? ((c & 3) == 0) : (((c - 16) & 1) == 0);
+                            const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
+                            const double arg = sCtrl[cluster * 4 + 1] * ctrlTime + phase;
+                            newLength = (T)sCtrl[cluster * 4 + 0] * sinPhase(arg, T(0)) + (T)sCtrl[cluster * 4 + 3];
+                        }
                         if (newLength <= minLength) newLength = minLength;
                         else if (newLength >= maxLength) newLength = maxLength;
-                        if (!(newLength < T(0))) { q.pref = newLength; q.moveMotors(dt); }
+                        const bool accept = !(newLength < T(0));
+                        q.pref = accept ? newLength : q.pref;
+                        q.moveMotors(dt, accept);
                     }
                     q.moveMotors(dt); /* EscapeController.cpp:108-116: every muscle's motors move a second time */
                 }
@@ -1175,6 +1219,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             f[FR_O] = Ox; f[FR_O + 1] = Oy; f[FR_O + 2] = Oz;
             f[FR_V] = Vx; f[FR_V + 1] = Vy; f[FR_V + 2] = Vz;
             f[FR_CTRLTIME] = ctrlTime;
+            if (sineRecurrence && doModels) f[FR_SPARE] = 1.0;
+        }
+        if (sineRecurrence && doModels) {
+            double* gsine = a.sine_state + (size_t)env * 48;
+            for (int c = lane; c < 24 && c < C; c += LPE) { gsine[2 * c] = sSine[4 * c]; gsine[2 * c + 1] = sSine[4 * c + 1]; }
         }
     }
 }
