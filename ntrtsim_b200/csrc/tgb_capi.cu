@@ -49,7 +49,7 @@ struct tgb_world {
     bool finalized = false;
     const tgb_ops* ops = nullptr;
     size_t scalarBytes = 4;
-    int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0;
+    int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0, maxInc = 0;
     int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0;
     cudaStream_t stream = nullptr;
     void* d_state = nullptr;
@@ -60,7 +60,7 @@ struct tgb_world {
     int* d_status = nullptr;
     void* d_model_t = nullptr;
     int* d_model_i = nullptr;
-    int modelTWords = 0, modelIWords = 0;
+    int modelTWords = 0, modelIWords = 0, modelCrecOff = 0, modelCirecOff = 0;
     double* d_stage = nullptr;  /* staging for double records exchanged with the host */
     size_t stageDoubles = 0;
     double* h_stage = nullptr;  /* pinned */
@@ -144,9 +144,10 @@ bool rangeOk(const tgb_world* w, int envBegin, int envCount) {
 }
 
 template <typename T>
-void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vector<int>& ints, int& nInc) {
+void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vector<int>& ints, int& nInc, int& crecOff, int& cirecOff, int& maxInc) {
     const int R = w->R, C = w->C, S = w->S;
-    std::vector<T> t((size_t)TGB_NBF * R + (size_t)TGB_NSF * S + (size_t)TGB_NCF * C, T(0));
+    crecOff = (TGB_NBF * R + TGB_NSF * S + TGB_NCF * C + 3) & ~3;
+    std::vector<T> t((size_t)crecOff + (size_t)TGB_CREC * C, T(0));
     T* bt = t.data();
     T* st = bt + (size_t)TGB_NBF * R;
     T* ct = st + (size_t)TGB_NSF * S;
@@ -156,11 +157,14 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         incidence[w->cables[c].body_b].push_back(c | (1 << 24));
     }
     nInc = 2 * C;
-    ints.assign((size_t)TGB_NBI * R + (size_t)TGB_NCI * C + nInc, 0);
+    cirecOff = (TGB_NBI * R + TGB_NCI * C + nInc + 3) & ~3;
+    ints.assign((size_t)cirecOff + (size_t)TGB_CIREC * C, 0);
     int* bi = ints.data();
     int* ci = bi + (size_t)TGB_NBI * R;
     int* inc = ci + (size_t)TGB_NCI * C;
     int incPos = 0;
+    maxInc = 0;
+    std::vector<int> slotA(std::max(1, C), 0), slotB(std::max(1, C), 0);
     for (int b = 0; b < R; ++b) {
         const tgb_body_desc& d = w->bodies[b];
         /* btRigidBody::setMassProps: inverse mass and inverse local inertia; static when mass == 0 */
@@ -190,7 +194,13 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
             const int cx = x & 0xffffff, cy = y & 0xffffff;
             return cx != cy ? cx < cy : x < y;
         });
-        for (size_t k = 0; k < sorted.size(); ++k) inc[incPos++] = sorted[k];
+        for (size_t k = 0; k < sorted.size(); ++k) {
+            inc[incPos++] = sorted[k];
+            /* position of this cable end in the body's list, for the cable's record below */
+            const int cab = sorted[k] & 0xffffff;
+            (((sorted[k] >> 24) != 0) ? slotB : slotA)[cab] = (int)k;
+        }
+        maxInc = std::max(maxInc, (int)sorted.size());
     }
     for (int s = 0; s < S; ++s) {
         const tgb_shape_desc& d = w->shapes[s];
@@ -217,6 +227,14 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         ct[CF_MRADIUS * C + c] = (T)d.motor_radius; ct[CF_MFRICTION * C + c] = (T)d.motor_friction; ct[CF_MINERTIA * C + c] = (T)d.motor_inertia;
         ci[CI_A * C + c] = d.body_a; ci[CI_B * C + c] = d.body_b;
         ci[CI_ACTUATOR * C + c] = d.actuator; ci[CI_BACKDRIVABLE * C + c] = d.backdrivable;
+        /* the same constants as one record per cable (TGB_CREC / TGB_CIREC) */
+        T* r = t.data() + crecOff + (size_t)TGB_CREC * c;
+        for (int k = 0; k < 3; ++k) { r[k] = (T)d.local_a[k]; r[4 + k] = (T)d.local_b[k]; }
+        r[3] = (T)d.stiffness; r[7] = (T)d.damping;
+        r[8] = (T)d.target_velocity; r[9] = (T)d.max_tension; r[10] = (T)(d.max_tension / d.stiffness); r[11] = (T)d.min_actual_length;
+        r[12] = (T)d.min_rest_length;
+        int* ri = ints.data() + cirecOff + (size_t)TGB_CIREC * c;
+        ri[0] = d.body_a; ri[1] = d.body_b; ri[2] = d.actuator | (d.backdrivable ? 1 << 8 : 0); ri[3] = slotA[c] | (slotB[c] << 16);
     }
     tbytes.resize(t.size() * sizeof(T));
     std::memcpy(tbytes.data(), t.data(), tbytes.size());
@@ -231,12 +249,13 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.n_env = w->cfg.n_env; a.n_steps = nSteps;
     a.stats = w->d_stats;
     a.phases = 3;
-    a.R = w->R; a.C = w->C; a.S = w->S; a.n_inc = w->nInc;
+    a.R = w->R; a.C = w->C; a.S = w->S; a.n_inc = w->nInc; a.max_inc = w->maxInc;
     a.stride = w->stride; a.cap_contacts = w->capContacts; a.frame_body = w->frameBody;
     a.ctrl_kind = w->ctrlKind; a.ctrl_stride = w->ctrlKind != TGB_CTRL_NONE ? w->ctrlStride : 0;
     a.iterations = w->cfg.solver_iterations > 0 ? w->cfg.solver_iterations : 10;
     a.ground_kind = w->ground.kind;
     a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
+    a.model_crec_off = w->modelCrecOff; a.model_cirec_off = w->modelCirecOff;
     a.dt = dt;
     a.gn[0] = w->ground.normal[0]; a.gn[1] = w->ground.normal[1]; a.gn[2] = w->ground.normal[2];
     a.goff = w->ground.offset;
@@ -407,7 +426,7 @@ tgb_status tgb_finalize(tgb_world* w) {
     TGB_CUDA(cudaSetDevice(w->cfg.device));
     const int n = w->cfg.n_env;
     const int vecWords = (int)(16 / w->scalarBytes);
-    w->stride = w->R * TGB_NBS + w->C * TGB_NCS;
+    w->stride = TGB_CABLE_BASE(w->R) + w->C * TGB_NCS;
     w->stride = (w->stride + vecWords - 1) / vecWords * vecWords;
     int maxShapes = 1;
     /* the env frame follows the first static body if there is one (then it never moves and static bodies stay
@@ -435,8 +454,8 @@ tgb_status tgb_finalize(tgb_world* w) {
 
     std::vector<unsigned char> tbytes;
     std::vector<int> ints;
-    if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc);
-    else packModel<float>(w, tbytes, ints, w->nInc);
+    if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc);
+    else packModel<float>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc);
     w->modelTWords = (int)(tbytes.size() / w->scalarBytes);
     w->modelIWords = (int)ints.size();
     TGB_CUDA(cudaMalloc(&w->d_model_t, std::max<size_t>(tbytes.size(), 16)));

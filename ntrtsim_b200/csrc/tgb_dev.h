@@ -3,7 +3,7 @@
  *
  * HBM layout (one tgb_world, n_env environments, scalar type T = float or double):
  *   state  T[n_env][stride]        env-major records: R bodies x 13 {pos3 (relative to the env frame origin), quat4 xyzw,
- *                                   linvel3 (relative to the env frame velocity), angvel3} then C cables x 4
+ *                                   linvel3 (relative to the env frame velocity), angvel3}, padding to 16 bytes, then C cables x 4
  *                                   {rest length, previous length, preferred length, motor velocity}; stride is padded
  *                                   to a 16-byte multiple so that a group of lanes moves its record with 128-bit
  *                                   accesses and a CTA's records form one contiguous span.
@@ -19,6 +19,7 @@
  * lanes that index consecutive bodies / cables read consecutive shared-memory words:
  *   model_t T[]   : body fields [TGB_NBF][R], shape fields [TGB_NSF][S], cable fields [TGB_NCF][C]
  *   model_i int[] : body ints [TGB_NBI][R], cable ints [TGB_NCI][C], incidence list [n_inc]
+ * followed by the per-cable records of the cable phase (TGB_CREC / TGB_CIREC below) at 16-byte aligned offsets.
  */
 #ifndef TGB_DEV_H
 #define TGB_DEV_H
@@ -38,6 +39,13 @@ enum {
 };
 /* cable int-fields */
 enum { CI_A = 0, CI_B, CI_ACTUATOR, CI_BACKDRIVABLE, TGB_NCI };
+/* per-cable constants once more as one record per cable for the step kernel's cable phase (128-bit shared-memory loads): T words
+   [la.xyz, k][lb.xyz, damping][tVel, maxTens, maxStretch, minAL][minRL, 0, 0, 0][pad x 4]; the stride of 20 words keeps eight
+   consecutive records on distinct banks.  Ints: [body a, body b, actuator | backdrivable << 8, ka | kb << 16] with ka / kb the
+   position of this cable's end in the incidence list of body a / b (slot of the impulse exchange, see tgb_step.cuh). */
+enum { TGB_CREC = 20, TGB_CIREC = 4 };
+/* first word of the cable block in an env record: 16-byte aligned for both scalar types */
+#define TGB_CABLE_BASE(R) ((((R) * TGB_NBS) + 3) & ~3)
 /* per-cable state words in the env record */
 enum { CS_REST = 0, CS_PREV, CS_PREF, CS_MOTORVEL, TGB_NCS };
 /* per-body state words in the env record */
@@ -68,6 +76,7 @@ struct tgb_step_args {
     int env_begin;
     int phases;           /* bit0: world half of tgSimulation::step, bit1: models half (controllers, motors, cable forces) */
     int R, C, S, n_inc;
+    int max_inc;          /* longest incidence list of a body */
     int stride;           /* T words per env record */
     int cap_contacts;     /* contact slots per body */
     int frame_body;       /* body whose position/velocity the env frame follows */
@@ -75,6 +84,7 @@ struct tgb_step_args {
     int iterations;       /* PGS iterations */
     int ground_kind;
     int model_t_words, model_i_words;
+    int model_crec_off, model_cirec_off; /* word offsets of the per-cable records inside model_t / model_i */
     double dt;
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */
     double ground_restitution;

@@ -77,7 +77,7 @@ __global__ void pack_cables_kernel(tgb_io_args a, const double* __restrict__ src
     const int e = i / a.C, c = i - e * a.C;
     const int env = a.env_begin + e;
     const double* s = src + ((size_t)(broadcast ? 0 : e) * a.C + c) * 2;
-    T* d = reinterpret_cast<T*>(a.state) + (size_t)env * a.stride + a.R * TGB_NBS + c * TGB_NCS;
+    T* d = reinterpret_cast<T*>(a.state) + (size_t)env * a.stride + TGB_CABLE_BASE(a.R) + c * TGB_NCS;
     d[CS_REST] = (T)s[0];
     d[CS_PREV] = (T)s[1];
     d[CS_PREF] = (T)s[0];
@@ -112,7 +112,7 @@ __global__ void cable_obs_kernel(tgb_io_args a, double* __restrict__ dst) {
     const int e = i / a.C, c = i - e * a.C;
     const int env = a.env_begin + e;
     const T* rec = reinterpret_cast<const T*>(a.state) + (size_t)env * a.stride;
-    const T* cs = rec + a.R * TGB_NBS + c * TGB_NCS;
+    const T* cs = rec + TGB_CABLE_BASE(a.R) + c * TGB_NCS;
     const T* mt = reinterpret_cast<const T*>(a.model_t);
     const T k = (mt + TGB_NBF * a.R + TGB_NSF * a.S)[CF_K * a.C + c];
     const T L = cable_length<T>(a, rec, c);
@@ -137,7 +137,7 @@ __global__ void control_input_kernel(tgb_io_args a, const double* __restrict__ i
     const int* ci = a.model_i + TGB_NBI * a.R;
     if (ci[CI_ACTUATOR * a.C + c] != TGB_ACT_BASIC) return;
     T* rec = reinterpret_cast<T*>(a.state) + (size_t)env * a.stride;
-    T* cs = rec + a.R * TGB_NBS + c * TGB_NCS;
+    T* cs = rec + TGB_CABLE_BASE(a.R) + c * TGB_NCS;
     const T* ct = reinterpret_cast<const T*>(a.model_t) + TGB_NBF * a.R + TGB_NSF * a.S;
     const T dt = (T)dt_d;
     const T k = ct[CF_K * a.C + c];

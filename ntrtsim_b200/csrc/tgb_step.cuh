@@ -40,6 +40,18 @@
 #ifndef TGB_SINGLE_CONTACT_PGS
 #define TGB_SINGLE_CONTACT_PGS 1
 #endif
+#ifndef TGB_EXCHANGE_UNION
+#define TGB_EXCHANGE_UNION 1
+#endif
+#ifndef TGB_SINE_REC
+#define TGB_SINE_REC 4
+#endif
+#ifndef TGB_VEC_CS
+#define TGB_VEC_CS 1
+#endif
+#ifndef TGB_VEC_CREC
+#define TGB_VEC_CREC 1
+#endif
 #ifndef TGB_CABLE_UNROLL
 #define TGB_CABLE_UNROLL 0 /* 0 = automatic */
 #endif
@@ -204,7 +216,7 @@ __device__ __forceinline__ void pgsSharedRows(T* ct, int laneStride, int nc, int
 /* One cable's working set in registers (the cable phase keeps several of these in flight per lane). */
 template <typename T>
 struct CableRegs {
-    int c, actuator;
+    int c, actuator, slots, ia, ib;
     bool valid;
     V3<T> ra, rb, dist, J;
     T L, k, damp, tVel, maxTens, maxStretch, minAL, minRL;
@@ -226,9 +238,9 @@ struct CableRegs {
 /* doubles of shared memory per env group: controller row, sine cumulative phases, CPG work space */
 __host__ __device__ inline int tgb_group_double_words(const tgb_step_args& a) {
     int n = a.ctrl_stride + 8;
-    if (a.ctrl_kind == TGB_CTRL_ESCAPE_SINE) n += 4 * 24 + 2 * 8; /* per cable (sin, cos, amplitude, offset), per cluster (cos, sin) of the phase step */
+    if (a.ctrl_kind == TGB_CTRL_ESCAPE_SINE) n += TGB_SINE_REC * 24 + 2 * 8; /* per cable (sin, cos[, amplitude, offset]) of the phase, per cluster (cos, sin) of the phase step */
     if (a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) n += 3 * a.cpg_n_pairs + (3 + 3 + 3 + 21 + 1) * a.C;
-    return n;
+    return (n + 1) & ~1; /* even: the int region behind the doubles stays 16-byte aligned */
 }
 
 /* Views of the packed model in shared memory. */
@@ -236,6 +248,7 @@ template <typename T>
 struct ModelView {
     const T* bt; const T* st; const T* ct;
     const int* bi; const int* ci; const int* inc;
+    const T* crec; const int* cirec; /* per-cable records of the cable phase */
     int R, S, C;
     TGB_D T body(int f, int b) const { return bt[f * R + b]; }
     TGB_D int bodyi(int f, int b) const { return bi[f * R + b]; }
@@ -280,9 +293,16 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     T* sModelT = reinterpret_cast<T*>(smem_raw);
     const int modelTWords = (a.model_t_words + 3) & ~3;
     const int poseWords = 12 * LPE;
-    const int jWords = (kFast ? 12 : 3) * C;    /* impulse J per cable; float publishes (J, torque) for end A and (-J, torque) for end B */
+    /* impulse exchange between the cable phase and the bodies.  Double: J per cable [C][3], gathered through the incidence list.
+       Float: every cable end writes (J, torque about the body's centre) into the slot [position in the body's incidence
+       list][body lane] as two float4, so that the gather of a body lane is a run of 128-bit loads at consecutive addresses
+       across lanes: no index loads, no bank conflicts. */
+    const int jWords = kFast ? a.max_inc * LPE * 8 : 3 * C;
     const int ctWords = a.cap_contacts * TGB_NCT * LPE;
-    int groupTWords = a.stride + poseWords + jWords + ctWords;
+    /* the contact rows (live from contact generation to the end of the solver) and the cable impulses (live from the cable
+       phase to the impulse gather) share one region: shared memory per environment decides how many CTAs an SM holds */
+    const int exchangeWords = TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords;
+    int groupTWords = a.stride + poseWords + exchangeWords;
     groupTWords = (groupTWords + 3) & ~3;
     /* keep group regions LPE banks apart so that the groups of one warp do not collide */
     if (LPE < 32) { while ((groupTWords & 31) != (LPE < 4 ? 4 : LPE)) groupTWords += 4; }
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     T* sState = sGroupT;                       /* env record: bodies then cables */
     T* sPose = sState + a.stride;              /* [LPE][12] : pos3, basis9 of each body, one 16-byte aligned record per body */
     T* sJ = sPose + poseWords;                 /* [C][3] */
-    T* sCt = sJ + jWords;                      /* [cap][TGB_NCT][LPE] */
+    T* sCt = TGB_EXCHANGE_UNION ? sJ : sJ + jWords; /* [cap][TGB_NCT][LPE], same region */
     constexpr bool cpgOn = CLASS == TGB_CLASS_CPG;
     constexpr bool sineOn = CLASS == TGB_CLASS_SINE;
     constexpr bool simpleOn = CLASS == TGB_CLASS_SIMPLE;
@@ -303,8 +323,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     double* sCum = sD + a.ctrl_stride;         /* sine controller: cumulative phase per cluster */
     /* CPG: pair table (weight, cos phase, sin phase), state x, stage state, published (sin, cos, r), k1..k7, node values */
     /* sine controller, single precision: (sin, cos) of each cable's phase advanced by a rotation per step, see below */
-    double* sSine = sCum + 8;                  /* [24][4] sin, cos, amplitude, offset */
-    double* sRot = sSine + 4 * 24;             /* [8][2] cos, sin of frequency * dt */
+    double* sSine = sCum + 8;                  /* [24][TGB_SINE_REC] sin, cos[, amplitude, offset] */
+    double* sRot = sSine + TGB_SINE_REC * 24;             /* [8][2] cos, sin of frequency * dt */
     double* sPair = sCum + 8;
     double* sX = sPair + 3 * a.cpg_n_pairs;
     double* sXt = sX + 3 * C;
@@ -331,6 +351,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     M.R = R; M.S = S; M.C = C;
     M.bt = sModelT; M.st = M.bt + TGB_NBF * R; M.ct = M.st + TGB_NSF * S;
     M.bi = sModelI; M.ci = M.bi + TGB_NBI * R; M.inc = M.ci + TGB_NCI * C;
+    M.crec = sModelT + a.model_crec_off; M.cirec = sModelI + a.model_cirec_off;
 
     const T dt = (T)a.dt;
     const T invDt = (T)(1.0 / a.dt);
@@ -372,7 +393,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
                 sincos(sCtrl[cluster * 4 + 1] * ctrlTime + phase, &sn, &cn);
             }
-            sSine[4 * c] = sn; sSine[4 * c + 1] = cn; sSine[4 * c + 2] = sCtrl[cluster * 4 + 0]; sSine[4 * c + 3] = sCtrl[cluster * 4 + 3];
+            sSine[TGB_SINE_REC * c] = sn; sSine[TGB_SINE_REC * c + 1] = cn;
+            if (TGB_SINE_REC == 4) { sSine[4 * c + 2] = sCtrl[cluster * 4 + 0]; sSine[4 * c + 3] = sCtrl[cluster * 4 + 3]; }
         }
         for (int cl = lane; cl < 8; cl += LPE) {
             double sn, cn;
@@ -560,6 +582,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     for (int step = 0; step < a.n_steps; ++step) {
 #ifdef TGB_STATS
         int statNc = 0; bool statPen = false;
+        const long long statA = clock64();
 #endif
         /* =============================== world step (tgSimulation.cpp:205) =============================== */
         if (dynamic && doWorld) {
@@ -709,43 +732,28 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 const T invDiagN = CT(0, CT_INVDIAGN), rhsN = CT(0, CT_RHSN), rhsPen = CT(0, CT_RHSPEN);
                 const T invDiagT = CT(0, CT_INVDIAGT), rhsT = CT(0, CT_RHST);
                 const V3<T> bn = gn * invMass, bt = t * invMass;
-                const T ANN = gn.dot(bn) + rxn.dot(angN);
+                /* With one point the two rows couple through ANT = J_N M^-1 J_T^T only, and 1 / invDiag is the row's own diagonal
+                   entry, so an iteration  lam += rhs - (A lam)_row * invDiag  collapses to
+                       lamN <- max(0, rhsN - kN lamT),   lamT <- clamp(rhsT - kT lamN, -mu lamN, mu lamN)
+                   with kN = ANT invDiagN, kT = ANT invDiagT: the same fixed-point iteration in exact arithmetic with a dependent
+                   chain of five operations per iteration instead of eleven.  The split-impulse row is alone in its system:
+                   every iteration leaves it at max(0, rhsPen). */
                 const T ANT = gn.dot(bt) + rxn.dot(angT);
-                const T ATT = t.dot(bt) + rxt.dot(angT);
-                if (rhsPen != T(0)) {
-                    T lamPush = T(0), dvp = T(0);
-                    for (int it = 0; it < a.iterations; ++it) {
-                        T delta = rhsPen - dvp * invDiagN;
-                        const T sum = lamPush + delta;
-                        const bool neg = sum < T(0);
-                        delta = neg ? -lamPush : delta;
-                        lamPush = neg ? T(0) : sum;
-                        dvp += ANN * delta;
-                    }
+                const T kN = ANT * invDiagN, kT = ANT * invDiagT;
+                if (rhsPen != T(0) && a.iterations > 0) {
+                    const T lamPush = rhsPen > T(0) ? rhsPen : T(0);
                     push = bn * lamPush;
                     turn = angN * lamPush;
                 }
-                T lamN = T(0), lamT = T(0), dvN = T(0), dvT = T(0);
+                T lamN = T(0), lamT = T(0);
                 for (int it = 0; it < a.iterations; ++it) {
-                    T delta = rhsN - dvN * invDiagN;
-                    const T sum = lamN + delta;
-                    const bool neg = sum < T(0);
-                    delta = neg ? -lamN : delta;
-                    lamN = neg ? T(0) : sum;
-                    dvN += ANN * delta;
-                    dvT += ANT * delta;
-                    /* friction row, skipped (zero impulse change) while the normal impulse is zero */
-                    const T hi = mu * lamN, lo = -hi;
-                    T deltaT = rhsT - dvT * invDiagT;
-                    const T sumT = lamT + deltaT;
-                    T newT = sumT;
-                    if (sumT < lo) { deltaT = lo - lamT; newT = lo; }
-                    else if (sumT > hi) { deltaT = hi - lamT; newT = hi; }
-                    const bool on = lamN > T(0);
-                    deltaT = on ? deltaT : T(0);
-                    lamT = on ? newT : lamT;
-                    dvN += ANT * deltaT;
-                    dvT += ATT * deltaT;
+                    const T sumN = rhsN - kN * lamT;
+                    lamN = sumN < T(0) ? T(0) : sumN;
+                    /* friction row: skipped (impulse kept) while the normal impulse is zero */
+                    const T hi = mu * lamN;
+                    T sumT = rhsT - kT * lamN;
+                    sumT = sumT < -hi ? -hi : (sumT > hi ? hi : sumT);
+                    lamT = lamN > T(0) ? sumT : lamT;
                 }
                 dLin = bn * lamN + bt * lamT;
                 dAng = angN * lamN + angT * lamT;
@@ -912,6 +920,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 atomicAdd(a.stats + 50, 1ULL);
             }
         }
+        const long long statB = clock64();
 #endif
 
         /* =============================== models step (tgSimulation.cpp:208-211) =============================== */
@@ -946,13 +955,32 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 q.valid = cu < C;
                 const int c = q.valid ? cu : c0; /* an idle slot shadows cable c0 and never stores */
                 q.c = c;
+#if TGB_VEC_CREC
+                T rc_[16];
+                {
+                    const vec_t* src = reinterpret_cast<const vec_t*>(M.crec + c * TGB_CREC);
+#pragma unroll
+                    for (int i = 0; i < 16 / VN; ++i) *reinterpret_cast<vec_t*>(&rc_[i * VN]) = src[i];
+                }
+                const int4 ri = *reinterpret_cast<const int4*>(M.cirec + c * TGB_CIREC);
+                const int ia = ri.x, ib = ri.y;
+                q.actuator = ri.z & 0xff;
+                q.slots = ri.w; q.ia = ia; q.ib = ib;
+                const V3<T> la(rc_[0], rc_[1], rc_[2]);
+                const V3<T> lb(rc_[4], rc_[5], rc_[6]);
+                q.k = rc_[3]; q.damp = rc_[7];
+                q.tVel = rc_[8]; q.maxTens = rc_[9]; q.maxStretch = rc_[10];
+                q.minAL = rc_[11]; q.minRL = rc_[12];
+#else
                 const int ia = M.cablei(CI_A, c), ib = M.cablei(CI_B, c);
                 q.actuator = M.cablei(CI_ACTUATOR, c);
+                q.slots = M.cirec[c * TGB_CIREC + 3]; q.ia = ia; q.ib = ib;
                 const V3<T> la(M.cable(CF_LAX, c), M.cable(CF_LAY, c), M.cable(CF_LAZ, c));
                 const V3<T> lb(M.cable(CF_LBX, c), M.cable(CF_LBY, c), M.cable(CF_LBZ, c));
                 q.k = M.cable(CF_K, c); q.damp = M.cable(CF_C, c);
                 q.tVel = M.cable(CF_TVEL, c); q.maxTens = M.cable(CF_MAXTENS, c); q.maxStretch = M.cable(CF_MAXSTRETCH, c);
                 q.minAL = M.cable(CF_MINAL, c); q.minRL = M.cable(CF_MINRL, c);
+#endif
                 T pa[12], pb[12];
                 {
                     const vec_t* srcA = reinterpret_cast<const vec_t*>(sPose + 12 * ia);
@@ -974,7 +1002,16 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 const V3<T> p1 = q.ra + xa, p2 = q.rb + xb;
                 q.dist = p2 - p1;
                 q.L = q.dist.length();
-                const T* cs = sState + R * TGB_NBS + c * TGB_NCS;
+#if TGB_VEC_CS
+                T cs[TGB_NCS];
+                {
+                    const vec_t* src = reinterpret_cast<const vec_t*>(sState + TGB_CABLE_BASE(R) + c * TGB_NCS);
+#pragma unroll
+                    for (int i = 0; i < TGB_NCS / VN; ++i) *reinterpret_cast<vec_t*>(&cs[i * VN]) = src[i];
+                }
+#else
+                const T* cs = sState + TGB_CABLE_BASE(R) + c * TGB_NCS;
+#endif
                 q.rest = cs[CS_REST]; q.prev = cs[CS_PREV]; q.pref = cs[CS_PREF]; q.motorVel = cs[CS_MOTORVEL];
                 q.desiredTorque = T(0);
             }
@@ -1022,11 +1059,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                         const int cluster = c < 16 ? (c >> 2) : 4 + ((c - 16) >> 1);
                         T newLength;
                         if (sineRecurrence) {
-                            double* sc = sSine + 4 * c;
+                            double* sc = sSine + TGB_SINE_REC * c;
                             const double s0 = sc[0], c0r = sc[1], cd = sRot[2 * cluster], sd = sRot[2 * cluster + 1];
                             const double s1 = s0 * cd + c0r * sd, c1 = c0r * cd - s0 * sd;
                             sc[0] = s1; sc[1] = c1;
-                            newLength = (T)(sc[2] * s1 + sc[3]);
+                            newLength = TGB_SINE_REC == 4 ? (T)(sc[2] * s1 + sc[3]) : (T)(sCtrl[cluster * 4 + 0] * s1 + sCtrl[cluster * 4 + 3]);
                         } else {
                             const bool firstOfCluster = c < 16 ? ((c & 3) == 0) : (((c - 16) & 1) == 0);
                             const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
@@ -1116,29 +1153,43 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 if (kFast) {
                     /* also publish the torque of the impulse about both bodies' centres: r x J and r x (-J) */
                     const V3<T> ta = q.ra.cross(J), tb = J.cross(q.rb);
-                    T* o = sJ + c * 12;
-                    o[0] = J.x; o[1] = J.y; o[2] = J.z; o[3] = ta.x; o[4] = ta.y; o[5] = ta.z;
-                    o[6] = -J.x; o[7] = -J.y; o[8] = -J.z; o[9] = tb.x; o[10] = tb.y; o[11] = tb.z;
+                    float4* oa = reinterpret_cast<float4*>(sJ) + ((q.slots & 0xffff) * LPE + q.ia) * 2;
+                    float4* ob = reinterpret_cast<float4*>(sJ) + ((q.slots >> 16) * LPE + q.ib) * 2;
+                    oa[0] = make_float4(J.x, J.y, J.z, 0.0f); oa[1] = make_float4(ta.x, ta.y, ta.z, 0.0f);
+                    ob[0] = make_float4(-J.x, -J.y, -J.z, 0.0f); ob[1] = make_float4(tb.x, tb.y, tb.z, 0.0f);
                 } else {
                     sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
                 }
-                T* cs = sState + R * TGB_NBS + c * TGB_NCS;
+#if TGB_VEC_CS
+                T cs[TGB_NCS];
                 cs[CS_REST] = q.rest; cs[CS_PREV] = q.prev; cs[CS_PREF] = q.pref;
                 cs[CS_MOTORVEL] = q.actuator == TGB_ACT_KINEMATIC ? q.motorVel : q.velocity;
+                vec_t* dst = reinterpret_cast<vec_t*>(sState + TGB_CABLE_BASE(R) + c * TGB_NCS);
+#pragma unroll
+                for (int i = 0; i < TGB_NCS / VN; ++i) dst[i] = *reinterpret_cast<vec_t*>(&cs[i * VN]);
+#else
+                T* cs = sState + TGB_CABLE_BASE(R) + c * TGB_NCS;
+                cs[CS_REST] = q.rest; cs[CS_PREV] = q.prev; cs[CS_PREF] = q.pref;
+                cs[CS_MOTORVEL] = q.actuator == TGB_ACT_KINEMATIC ? q.motorVel : q.velocity;
+#endif
             }
         }
         __syncwarp();
+#ifdef TGB_STATS
+        const long long statC = clock64();
+#endif
 
         /* ---- applyImpulse of every incident cable end, in cable order (btRigidBody::applyImpulse) ---- */
         if (dynamic) {
             if (kFast) {
                 /* sum the impulses and torques of the incident cable ends first, then one multiplication each */
                 V3<T> sumJ(T(0), T(0), T(0)), sumT(T(0), T(0), T(0));
-                for (int i = incBegin; i < incBegin + incCount; ++i) {
-                    const int code = M.inc[i];
-                    const T* o = sJ + (code & 0xffffff) * 12 + (code >> 24) * 6;
-                    sumJ += V3<T>(o[0], o[1], o[2]);
-                    sumT += V3<T>(o[3], o[4], o[5]);
+                const float4* o = reinterpret_cast<const float4*>(sJ) + lane * 2;
+                for (int k = 0; k < incCount; ++k) {
+                    const float4 j4 = o[0], t4 = o[1];
+                    o += LPE * 2;
+                    sumJ += V3<T>(j4.x, j4.y, j4.z);
+                    sumT += V3<T>(t4.x, t4.y, t4.z);
                 }
                 b.v += sumJ * invMass;
                 b.w += b.Iinv * sumT;
@@ -1157,6 +1208,15 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 }
             }
         }
+        if (TGB_EXCHANGE_UNION) __syncwarp(); /* the next step's contact rows reuse the impulse region */
+#ifdef TGB_STATS
+        if (a.stats && warpLane == 0) {
+            /* cycles of this warp in the body phase, the cable phase and the gather */
+            atomicAdd(a.stats + 100, (unsigned long long)(statB - statA));
+            atomicAdd(a.stats + 101, (unsigned long long)(statC - statB));
+            atomicAdd(a.stats + 102, (unsigned long long)(clock64() - statC));
+        }
+#endif
     }
 #undef CT
 
@@ -1223,7 +1283,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
         if (sineRecurrence && doModels) {
             double* gsine = a.sine_state + (size_t)env * 48;
-            for (int c = lane; c < 24 && c < C; c += LPE) { gsine[2 * c] = sSine[4 * c]; gsine[2 * c + 1] = sSine[4 * c + 1]; }
+            for (int c = lane; c < 24 && c < C; c += LPE) { gsine[2 * c] = sSine[TGB_SINE_REC * c]; gsine[2 * c + 1] = sSine[TGB_SINE_REC * c + 1]; }
         }
     }
 }
@@ -1232,7 +1292,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
     const int groupsPerBlock = threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
-    int groupTWords = a.stride + 12 * lpe + (sizeofT == 4 ? 12 : 3) * a.C + a.cap_contacts * TGB_NCT * lpe;
+    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * TGB_NCT * lpe;
+    int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords);
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
     const int groupDWords = tgb_group_double_words(a);
