@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     const int poseWords = 12 * LPE;
     /* impulse exchange between the cable phase and the bodies.  Double: J per cable [C][3], gathered through the incidence list.
        Float: every cable end writes (J, torque about the body's centre) into the slot [position in the body's incidence
-       list][body lane] as two float4, so that the gather of a body lane is a run of 128-bit loads at consecutive addresses
+       list][body lane] of two float4 planes, so that the gather of a body lane is a run of 128-bit loads at consecutive addresses
        across lanes: no index loads, no bank conflicts. */
     const int jWords = kFast ? a.max_inc * LPE * 8 : 3 * C;
     const int ctWords = a.cap_contacts * TGB_NCT * LPE;
@@ -1153,10 +1153,14 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 if (kFast) {
                     /* also publish the torque of the impulse about both bodies' centres: r x J and r x (-J) */
                     const V3<T> ta = q.ra.cross(J), tb = J.cross(q.rb);
-                    float4* oa = reinterpret_cast<float4*>(sJ) + ((q.slots & 0xffff) * LPE + q.ia) * 2;
-                    float4* ob = reinterpret_cast<float4*>(sJ) + ((q.slots >> 16) * LPE + q.ib) * 2;
-                    oa[0] = make_float4(J.x, J.y, J.z, 0.0f); oa[1] = make_float4(ta.x, ta.y, ta.z, 0.0f);
-                    ob[0] = make_float4(-J.x, -J.y, -J.z, 0.0f); ob[1] = make_float4(tb.x, tb.y, tb.z, 0.0f);
+                    /* slot of (position k in the body's list, body b): plane J at [k][(b + k) mod LPE], plane torque behind it; the
+                       skew by k spreads the ends of one body (distinct k) over the banks for the scattered stores */
+                    const int ka = q.slots & 0xffff, kb = q.slots >> 16;
+                    float4* oa = reinterpret_cast<float4*>(sJ) + ka * LPE + ((q.ia + ka) & (LPE - 1));
+                    float4* ob = reinterpret_cast<float4*>(sJ) + kb * LPE + ((q.ib + kb) & (LPE - 1));
+                    const int plane = a.max_inc * LPE;
+                    oa[0] = make_float4(J.x, J.y, J.z, 0.0f); oa[plane] = make_float4(ta.x, ta.y, ta.z, 0.0f);
+                    ob[0] = make_float4(-J.x, -J.y, -J.z, 0.0f); ob[plane] = make_float4(tb.x, tb.y, tb.z, 0.0f);
                 } else {
                     sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
                 }
@@ -1184,10 +1188,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             if (kFast) {
                 /* sum the impulses and torques of the incident cable ends first, then one multiplication each */
                 V3<T> sumJ(T(0), T(0), T(0)), sumT(T(0), T(0), T(0));
-                const float4* o = reinterpret_cast<const float4*>(sJ) + lane * 2;
+                const float4* o = reinterpret_cast<const float4*>(sJ);
+                const int plane = a.max_inc * LPE;
                 for (int k = 0; k < incCount; ++k) {
-                    const float4 j4 = o[0], t4 = o[1];
-                    o += LPE * 2;
+                    const int slot = k * LPE + ((lane + k) & (LPE - 1));
+                    const float4 j4 = o[slot], t4 = o[slot + plane];
                     sumJ += V3<T>(j4.x, j4.y, j4.z);
                     sumT += V3<T>(t4.x, t4.y, t4.z);
                 }

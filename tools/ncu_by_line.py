@@ -41,6 +41,9 @@ def main():
     iex, ithr = h.index("Instructions Executed"), h.index("Thread Instructions Executed")
     ismp = h.index("Warp Stall Sampling (All Samples)")
     stall_cols = [(j, n) for j, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
+    iwf = h.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in h else None
+    iwx = h.index("L1 Wavefronts Shared Excessive") if "L1 Wavefronts Shared Excessive" in h else None
+    smem = defaultdict(lambda: [0, 0, ""])
     base = None
     agg = defaultdict(lambda: [0, 0, 0, defaultdict(int)])
     tot = [0, 0, 0]
@@ -62,6 +65,9 @@ def main():
             v = int(r[j] or 0)
             e[3][n] += v
             stall_tot[n] += v
+        if iwf is not None and (r[iwf] or "0") not in ("0", "-"):
+            w = smem[(line, r[isrc].strip().split(";")[0][:48])]
+            w[0] += int(r[iwf] or 0); w[1] += int(r[iwx] or 0)
         op = r[isrc].strip().split()[0] if r[isrc].strip() else "?"
         if op.startswith("@"):
             op = r[isrc].strip().split()[1]
@@ -76,6 +82,12 @@ def main():
     for line, e in sorted(agg.items(), key=lambda x: -x[1][2])[:top]:
         st = ", ".join("%s %d" % (n[6:], v) for n, v in sorted(e[3].items(), key=lambda x: -x[1])[:3] if v)
         print("  %-22s %6.2f%% instr  %6.2f%% samples  lanes %.1f   [%s]" % (line, 100.0 * e[0] / tot[0], 100.0 * e[2] / max(1, tot[2]), e[1] / max(1, e[0]), st))
+    if smem:
+        tw, tx = sum(v[0] for v in smem.values()), sum(v[1] for v in smem.values())
+        print("\n-- shared-memory wavefronts: %d total, %d excessive (bank conflicts); top instructions by excessive wavefronts" % (tw, tx))
+        for (line, src), v in sorted(smem.items(), key=lambda x: -x[1][1])[:top]:
+            if v[1]:
+                print("  %-22s %-50s wavefronts %10d  excessive %10d (%.0f%%)" % (line, src, v[0], v[1], 100.0 * v[1] / max(1, v[0])))
 
 
 if __name__ == "__main__":
