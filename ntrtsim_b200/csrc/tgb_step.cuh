@@ -257,6 +257,13 @@ struct ModelView {
     TGB_D int cablei(int f, int c) const { return ci[f * C + c]; }
 };
 
+/* Constants of one collision shape (a cylinder in the body frame). */
+template <typename T>
+struct ShapeConst {
+    T radius, halfLen, margin;
+    V3<T> spos, r0, r1; /* position, columns 0 and 1 of the rotation */
+};
+
 /* Controller classes a kernel is compiled for (the controller kind inside a class is a warp-uniform run-time switch):
    SIMPLE = none / set-point / torque / tension, SINE = EscapeController, CPG = CPG + impedance (its Dormand-Prince integrator
    needs 231 registers).  GROUND = false compiles the contact manifold and the contact solver out (tgEmptyGround).  Keeping the
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     double* sCum = sD + a.ctrl_stride;         /* sine controller: cumulative phase per cluster */
     /* CPG: pair table (weight, cos phase, sin phase), state x, stage state, published (sin, cos, r), k1..k7, node values */
     /* sine controller, single precision: (sin, cos) of each cable's phase advanced by a rotation per step, see below */
-    double* sSine = sCum + 8;                  /* [24][TGB_SINE_REC] sin, cos[, amplitude, offset] */
+    double* sSine = sCum + 8;                  /* [TGB_SINE_REC][24] planes: sin, cos[, amplitude, offset] (consecutive cables on consecutive banks) */
     double* sRot = sSine + TGB_SINE_REC * 24;             /* [8][2] cos, sin of frequency * dt */
     double* sPair = sCum + 8;
     double* sX = sPair + 3 * a.cpg_n_pairs;
@@ -393,8 +400,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
                 sincos(sCtrl[cluster * 4 + 1] * ctrlTime + phase, &sn, &cn);
             }
-            sSine[TGB_SINE_REC * c] = sn; sSine[TGB_SINE_REC * c + 1] = cn;
-            if (TGB_SINE_REC == 4) { sSine[4 * c + 2] = sCtrl[cluster * 4 + 0]; sSine[4 * c + 3] = sCtrl[cluster * 4 + 3]; }
+            sSine[c] = sn; sSine[24 + c] = cn;
+            if (TGB_SINE_REC == 4) { sSine[48 + c] = sCtrl[cluster * 4 + 0]; sSine[72 + c] = sCtrl[cluster * 4 + 3]; }
         }
         for (int cl = lane; cl < 8; cl += LPE) {
             double sn, cn;
@@ -575,6 +582,19 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         __syncwarp();
     };
 
+    auto loadShape = [&](int si) {
+        ShapeConst<T> sc;
+        sc.radius = M.shape(SF_RADIUS, si); sc.halfLen = M.shape(SF_HALFLEN, si); sc.margin = M.shape(SF_MARGIN, si);
+        sc.spos = V3<T>(M.shape(SF_POSX, si), M.shape(SF_POSY, si), M.shape(SF_POSZ, si));
+        sc.r0 = V3<T>(M.shape(SF_ROT0 + 0, si), M.shape(SF_ROT0 + 3, si), M.shape(SF_ROT0 + 6, si));
+        sc.r1 = V3<T>(M.shape(SF_ROT0 + 1, si), M.shape(SF_ROT0 + 4, si), M.shape(SF_ROT0 + 7, si));
+        return sc;
+    };
+    const ShapeConst<T> shape0 = loadShape(shapeCount > 0 ? shapeBegin : 0);
+    const bool shape0Aligned = shape0.spos.x == T(0) && shape0.spos.y == T(0) && shape0.spos.z == T(0) &&
+                               shape0.r0.x == T(1) && shape0.r0.y == T(0) && shape0.r0.z == T(0) &&
+                               shape0.r1.x == T(0) && shape0.r1.y == T(1) && shape0.r1.z == T(0);
+
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
 #ifdef TGB_STATS
     const long long statT0 = clock64();
@@ -617,14 +637,21 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 /* signed height of the frame origin above the surface, formed in double */
                 const T originHeight = (T)(a.gn[0] * Ox + a.gn[1] * Oy + a.gn[2] * Oz - a.goff);
                 for (int si = shapeBegin; si < shapeBegin + shapeCount; ++si) {
-                    const T radius = M.shape(SF_RADIUS, si), halfLen = M.shape(SF_HALFLEN, si), margin = M.shape(SF_MARGIN, si);
-                    const V3<T> spos(M.shape(SF_POSX, si), M.shape(SF_POSY, si), M.shape(SF_POSZ, si));
-                    /* R = B * shapeRot: only columns 0 and 1 are needed */
-                    V3<T> r0(M.shape(SF_ROT0 + 0, si), M.shape(SF_ROT0 + 3, si), M.shape(SF_ROT0 + 6, si)); /* column 0 of shapeRot */
-                    V3<T> r1(M.shape(SF_ROT0 + 1, si), M.shape(SF_ROT0 + 4, si), M.shape(SF_ROT0 + 7, si)); /* column 1 */
-                    const V3<T> col0 = b.B * r0;
-                    const V3<T> axisDir = b.B * r1;
-                    const V3<T> c = b.B * spos + b.x;
+                    /* the first shape's constants stay in registers across the steps (a rod is a single cylinder) */
+                    const ShapeConst<T> sc = si == shapeBegin ? shape0 : loadShape(si);
+                    const T radius = sc.radius, halfLen = sc.halfLen, margin = sc.margin;
+                    V3<T> col0, axisDir, c;
+                    if (si == shapeBegin && shape0Aligned) {
+                        /* cylinder frame = body frame (a plain rod): the products below reduce to columns of the basis, bit for bit */
+                        col0 = V3<T>(b.B.m[0][0], b.B.m[1][0], b.B.m[2][0]);
+                        axisDir = V3<T>(b.B.m[0][1], b.B.m[1][1], b.B.m[2][1]);
+                        c = b.x;
+                    } else {
+                        /* R = B * shapeRot: only columns 0 and 1 are needed */
+                        col0 = b.B * sc.r0;
+                        axisDir = b.B * sc.r1;
+                        c = b.B * sc.spos + b.x;
+                    }
                     const T rc = radius - margin, hc = halfLen - margin;
                     const T na = gn.dot(axisDir);
                     const V3<T> perp = -(gn - axisDir * na);
@@ -1059,11 +1086,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                         const int cluster = c < 16 ? (c >> 2) : 4 + ((c - 16) >> 1);
                         T newLength;
                         if (sineRecurrence) {
-                            double* sc = sSine + TGB_SINE_REC * c;
-                            const double s0 = sc[0], c0r = sc[1], cd = sRot[2 * cluster], sd = sRot[2 * cluster + 1];
+                            double* sc = sSine + c;
+                            const double s0 = sc[0], c0r = sc[24], cd = sRot[2 * cluster], sd = sRot[2 * cluster + 1];
                             const double s1 = s0 * cd + c0r * sd, c1 = c0r * cd - s0 * sd;
-                            sc[0] = s1; sc[1] = c1;
-                            newLength = TGB_SINE_REC == 4 ? (T)(sc[2] * s1 + sc[3]) : (T)(sCtrl[cluster * 4 + 0] * s1 + sCtrl[cluster * 4 + 3]);
+                            sc[0] = s1; sc[24] = c1;
+                            newLength = TGB_SINE_REC == 4 ? (T)(sc[48] * s1 + sc[72]) : (T)(sCtrl[cluster * 4 + 0] * s1 + sCtrl[cluster * 4 + 3]);
                         } else {
                             const bool firstOfCluster = c < 16 ? ((c & 3) == 0) : (((c - 16) & 1) == 0);
                             const double phase = (firstOfCluster && cluster > 0) ? sCum[cluster - 1] : sCum[cluster];
@@ -1288,7 +1315,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
         if (sineRecurrence && doModels) {
             double* gsine = a.sine_state + (size_t)env * 48;
-            for (int c = lane; c < 24 && c < C; c += LPE) { gsine[2 * c] = sSine[TGB_SINE_REC * c]; gsine[2 * c + 1] = sSine[TGB_SINE_REC * c + 1]; }
+            for (int c = lane; c < 24 && c < C; c += LPE) { gsine[2 * c] = sSine[c]; gsine[2 * c + 1] = sSine[24 + c]; }
         }
     }
 }
