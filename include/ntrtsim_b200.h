@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define TGB_ABI_VERSION 1
+#define TGB_ABI_VERSION 2
 
 typedef enum {
     TGB_OK = 0,
@@ -138,7 +138,8 @@ typedef enum {
     /* CPG + impedance control of the learningSpines examples, installed with tgb_set_cpg_controller:
        BaseSpineCPGControl::onStep (BaseSpineCPGControl.cpp:253-279) -> CPGEquations::update (util/CPGEquations.cpp:231-267),
        tgCPGActuatorControl::onStep (tgCPGActuatorControl.cpp:79-100) -> tgImpedanceController::control
-       (controllers/tgImpedanceController.cpp:151-185) -> tgTensionController::control (tgTensionController.cpp:90-114) */
+       (controllers/tgImpedanceController.cpp:151-185) -> tgTensionController::control (tgTensionController.cpp:90-114);
+       or, with tgb_cpg_desc.cable_control = 1, tgCPGCableControl::onStep -> tgPIDController -> tgKinematicActuator */
     TGB_CTRL_CPG_IMPEDANCE = 5
 } tgb_controller_kind;
 
@@ -161,8 +162,16 @@ typedef struct {
     double control_time;            /* BaseSpineCPGControl::Config::controlTime */
     double cable_control_step;      /* tgCPGActuatorControl::m_controlStep, 1e-4 */
     int32_t score_body;             /* body whose centre of mass is scored and height-checked (the segment's compound body) */
-    int32_t reserved;
+    /* Per-cable controller attached by setupCPGs:
+         0  tgCPGActuatorControl (BaseSpineCPGControl.cpp:211-213; tgCPGActuatorControl.cpp:79-100): tgBasicActuator cables only; the
+            impedance controller is called with the accumulated control time as dt
+         1  tgCPGCableControl (KinematicSpineCPGControl.cpp:69-76; tgCPGCableControl.cpp:63-98): tgKinematicActuator cables run
+            tgImpedanceController::control(tgBasicController&, ...) (tgImpedanceController.cpp:105-150) through a tgPIDController
+            (controllers/tgPIDController.cpp:80-98) whose output is the desired motor torque, and between control steps the PID
+            keeps tracking the last commanded tension; tgBasicActuator cables are controlled as in 0 but with the step's dt */
+    int32_t cable_control;
     double height_lo, height_hi;    /* 1.0 and 25 (BaseSpineCPGControl.cpp:271-278): outside -> status bit1, score -1 */
+    double pid_kp, pid_ki, pid_kd;  /* cable_control 1: signed gains of tgPIDController::Config (tension control: -p, -i, -d) */
 } tgb_cpg_desc;
 
 #define TGB_ESCAPE_PARAMS 33

@@ -51,8 +51,8 @@ class CpgDesc(C.Structure):
                 ("coupling_target", C.POINTER(C.c_int32)), ("coupling_pair", C.POINTER(C.c_int32)), ("n_pairs", C.c_int32),
                 ("max_steps", C.c_int32), ("impedance", C.POINTER(C.c_double)), ("r_const", C.c_double), ("d_min", C.c_double),
                 ("d_max", C.c_double), ("descending_command", C.c_double), ("control_time", C.c_double),
-                ("cable_control_step", C.c_double), ("score_body", C.c_int32), ("reserved", C.c_int32), ("height_lo", C.c_double),
-                ("height_hi", C.c_double)]
+                ("cable_control_step", C.c_double), ("score_body", C.c_int32), ("cable_control", C.c_int32), ("height_lo", C.c_double),
+                ("height_hi", C.c_double), ("pid_kp", C.c_double), ("pid_ki", C.c_double), ("pid_kd", C.c_double)]
 
 
 class TgbError(RuntimeError):
@@ -164,6 +164,8 @@ def load_host():
     h.tgh_run_example_stepwise.restype = C.c_int
     h.tgh_tetraspine_cpg.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _vp, _vp, _vp, _vp]
     h.tgh_tetraspine_param_row.argtypes = [_vp, _vp, C.c_int, _vp]
+    h.tgh_flemons_cpg.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _vp, _vp, _vp, _vp]
+    h.tgh_flemons_param_row.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
     _host = h
     return h
 

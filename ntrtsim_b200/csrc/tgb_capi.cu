@@ -265,6 +265,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
         a.cpg_n_couplings = w->cpg.n_couplings; a.cpg_n_pairs = w->cpg.n_pairs; a.cpg_max_steps = w->cpg.max_steps;
         a.cpg_score_body = w->cpg.score_body;
         a.cpg_topo = w->d_cpg_topo; a.cpg_imp = w->d_cpg_imp; a.cpg_state = w->d_cpg_state;
+        a.cpg_cable_control = w->cpg.cable_control; a.cpg_pid[0] = w->cpg.pid_kp; a.cpg_pid[1] = w->cpg.pid_ki; a.cpg_pid[2] = w->cpg.pid_kd;
         a.cpg_r_const = w->cpg.r_const; a.cpg_d_min = w->cpg.d_min; a.cpg_d_max = w->cpg.d_max; a.cpg_desc = w->cpg.descending_command;
         a.cpg_control_time = w->cpg.control_time; a.cpg_cable_step = w->cpg.cable_control_step;
         a.cpg_height_lo = w->cpg.height_lo; a.cpg_height_hi = w->cpg.height_hi;
@@ -637,7 +638,9 @@ tgb_status tgb_set_cpg_controller(tgb_world* w, const tgb_cpg_desc* d, const dou
         return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: one CPG node per cable is required");
     if (params_per_env != 2 + 2 * d->n_pairs) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: params_per_env must be 2 + 2 * n_pairs");
     if (d->score_body < 0 || d->score_body >= w->R) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: score body out of range");
-    if (!(d->control_time >= 0.0) || !(d->cable_control_step >= 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "control time is negative.");
+    if (!(d->control_time >= 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "control time is negative.");
+    if (!(d->cable_control_step >= 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "Negative control step"); /* tgCPGCableControl.cpp:41-44 */
+    if (d->cable_control != 0 && d->cable_control != 1) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: unknown cable control");
     if (d->coupling_begin[0] != 0 || d->coupling_begin[d->n_nodes] != d->n_couplings) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: bad CSR offsets");
     for (int i = 0; i < d->n_couplings; ++i)
         if (d->coupling_target[i] < 0 || d->coupling_target[i] >= d->n_nodes || d->coupling_pair[i] < 0 || d->coupling_pair[i] >= d->n_pairs)
@@ -660,7 +663,7 @@ tgb_status tgb_set_cpg_controller(tgb_world* w, const tgb_cpg_desc* d, const dou
     TGB_CUDA(cudaMemcpy(w->d_cpg_topo, topo.data(), topo.size() * sizeof(int), cudaMemcpyHostToDevice));
     TGB_CUDA(cudaMalloc(&w->d_cpg_imp, (size_t)4 * d->n_nodes * sizeof(double)));
     TGB_CUDA(cudaMemcpy(w->d_cpg_imp, d->impedance, (size_t)4 * d->n_nodes * sizeof(double), cudaMemcpyHostToDevice));
-    const size_t stateDoubles = (size_t)3 * w->C + 2;
+    const size_t stateDoubles = (size_t)TGB_CPG_STATE_DOUBLES(w->C);
     if (fresh || w->ctrlStride != params_per_env) {
         if (w->d_ctrl) { cudaFree(w->d_ctrl); w->d_ctrl = nullptr; }
         TGB_CUDA(cudaMalloc(&w->d_ctrl, (size_t)n * params_per_env * sizeof(double)));
@@ -702,7 +705,7 @@ tgb_status tgb_get_cpg_state(tgb_world* w, int32_t env_begin, int32_t env_count,
     if (w->ctrlKind != TGB_CTRL_CPG_IMPEDANCE || !w->d_cpg_state) return fail(TGB_ERR_STATE, "tgb_get_cpg_state: no CPG controller installed");
     if (env_count == 0) return TGB_OK;
     TGB_CUDA(cudaStreamSynchronize(w->stream));
-    const size_t stride = (size_t)3 * w->C + 2;
+    const size_t stride = (size_t)TGB_CPG_STATE_DOUBLES(w->C);
     TGB_CUDA(cudaMemcpy2D(out, (size_t)3 * w->C * sizeof(double), w->d_cpg_state + (size_t)env_begin * stride, stride * sizeof(double),
                           (size_t)3 * w->C * sizeof(double), env_count, cudaMemcpyDeviceToHost));
     return TGB_OK;

@@ -61,6 +61,8 @@ enum { FR_O = 0, FR_V = 3, FR_CTRLTIME = 6, FR_SPARE = 7, TGB_NFR = 8 };
 #define TGB_STATUS_NONFINITE 1
 #define TGB_STATUS_HEIGHT 2
 #define TGB_STATUS_CPG_INEFFICIENT 4
+/* doubles of CPG controller state per environment */
+#define TGB_CPG_STATE_DOUBLES(C) (6 * (C) + 2)
 
 struct tgb_step_args {
     void* state;          /* T[n_env][stride] */
@@ -94,7 +96,10 @@ struct tgb_step_args {
     int cpg_n_couplings, cpg_n_pairs, cpg_max_steps, cpg_score_body;
     const int* cpg_topo;      /* begin[C + 1], target[n_couplings], pair[n_couplings] */
     const double* cpg_imp;    /* [C][4] offset tension, length stiffness, velocity stiffness, control length */
-    double* cpg_state;        /* [n_env][3 C + 2]: (phase, radius, radius rate) per node, update time, cable control time */
+    double* cpg_state;        /* [n_env][6 C + 2]: (phase, radius, radius rate) per node, update time, cable control time, then per
+                                 cable the tgPIDController state (previous error, integrated error) and the last commanded tension */
+    int cpg_cable_control;    /* tgb_cpg_desc.cable_control */
+    double cpg_pid[3];        /* kP, kI, kD */
     double cpg_r_const, cpg_d_min, cpg_d_max, cpg_desc, cpg_control_time, cpg_cable_step, cpg_height_lo, cpg_height_hi;
 };
 

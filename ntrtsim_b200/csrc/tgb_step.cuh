@@ -239,7 +239,7 @@ struct CableRegs {
 __host__ __device__ inline int tgb_group_double_words(const tgb_step_args& a) {
     int n = a.ctrl_stride + 8;
     if (a.ctrl_kind == TGB_CTRL_ESCAPE_SINE) n += TGB_SINE_REC * 24 + 2 * 8; /* per cable (sin, cos[, amplitude, offset]) of the phase, per cluster (cos, sin) of the phase step */
-    if (a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) n += 3 * a.cpg_n_pairs + (3 + 3 + 3 + 21 + 1) * a.C;
+    if (a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) n += 3 * a.cpg_n_pairs + (3 + 3 + 3 + 21 + 1 + 3) * a.C;
     return (n + 1) & ~1; /* even: the int region behind the doubles stays 16-byte aligned */
 }
 
@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     double* sTrig = sXt + 3 * C;
     double* sK = sTrig + 3 * C;                /* [7][3 C] */
     double* sNodeValue = sK + 21 * C;
+    double* sPid = sNodeValue + C;             /* [C][3] tgPIDController previous error, integrated error; last commanded tension */
     int* sModelI = reinterpret_cast<int*>(reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) +
                                           groupsPerBlock * groupDWords);
 
@@ -413,7 +414,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
     double cpgUpdateTime = 0.0, cpgCableTime = 0.0;
     if (cpgOn) {
-        const double* cs = a.cpg_state + (size_t)env * (3 * C + 2);
+        const double* cs = a.cpg_state + (size_t)env * TGB_CPG_STATE_DOUBLES(C);
+        for (int i = lane; i < 3 * C; i += LPE) sPid[i] = cs[3 * C + 2 + i];
         for (int i = lane; i < 3 * C; i += LPE) sX[i] = cs[i];
         cpgUpdateTime = cs[3 * C];
         cpgCableTime = cs[3 * C + 1];
@@ -1109,10 +1111,10 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 #pragma unroll
                 for (int u = 0; u < CU; ++u) {
                     CableRegs<T>& q = cr[u];
+                    const double* g = a.cpg_imp + 4 * q.c;
                     if (q.actuator == TGB_ACT_BASIC) {
                         if (cpgCableControl) {
                             /* tgImpedanceController::controlTension(tgBasicActuator&, ...), tgImpedanceController.cpp:163-185 */
-                            const double* g = a.cpg_imp + 4 * q.c;
                             const T vel = q.motorVel; /* velocity slot of a basic actuator = the cable's m_velocity */
                             T setTension = (T)g[0] + (T)g[1] * (q.L - (T)g[3]) + (T)g[2] * (vel - (T)sNodeValue[q.c]);
                             setTension = setTension > T(0) ? setTension : T(0);
@@ -1124,10 +1126,32 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                             T newLength = q.rest - diff;
                             newLength = newLength < T(0.1) ? T(0.1) : newLength;
                             q.pref = newLength;
-                            q.moveMotors((T)cpgCableDt);
+                            /* tgCPGActuatorControl passes the accumulated control time, tgCPGCableControl the step's dt */
+                            q.moveMotors(a.cpg_cable_control == 1 ? dt : (T)cpgCableDt);
                         } else {
                             q.moveMotors(dt);
                         }
+                    } else if (q.actuator == TGB_ACT_KINEMATIC && a.cpg_cable_control == 1 && q.valid) {
+                        /* tgCPGCableControl::onStep with a tgPIDController, tgCPGCableControl.cpp:63-98 */
+                        double* pid = sPid + 3 * q.c;
+                        T tension = (q.L - q.rest) * q.k;
+                        tension = tension < T(0) ? T(0) : tension;
+                        T setPoint = (T)pid[2];
+                        if (cpgCableControl) {
+                            /* tgImpedanceController::controlTension(tgBasicController&, ...), tgImpedanceController.cpp:118-150;
+                               the actuator's velocity is motor velocity x radius (tgKinematicActuator.cpp:181-184) */
+                            const T vel = q.motorVel * M.cable(CF_MRADIUS, q.c);
+                            setPoint = (T)g[0] + (T)g[1] * (q.L - (T)g[3]) + (T)g[2] * (vel - (T)sNodeValue[q.c]);
+                            setPoint = setPoint > T(0) ? setPoint : T(0);
+                            pid[2] = (double)setPoint;
+                        }
+                        /* tgPIDController::control(dt, setPoint, sensorData), tgPIDController.cpp:80-109 */
+                        const T prevError = (T)pid[0];
+                        const T error = setPoint - tension;
+                        const T intError = (T)pid[1] + (error + prevError) / T(2) * dt;
+                        const T dError = (error - prevError) / dt;
+                        q.desiredTorque = (T)a.cpg_pid[0] * error + (T)a.cpg_pid[1] * intError + (T)a.cpg_pid[2] * dError;
+                        pid[0] = (double)error; pid[1] = (double)intError;
                     }
                 }
             }
@@ -1302,8 +1326,8 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         const vec_t* ss = reinterpret_cast<const vec_t*>(sState);
         for (int i = lane; i < a.stride / VN; i += LPE) gs[i] = ss[i];
         if (cpgOn) {
-            double* cs = a.cpg_state + (size_t)env * (3 * C + 2);
-            for (int i = lane; i < 3 * C; i += LPE) cs[i] = sX[i];
+            double* cs = a.cpg_state + (size_t)env * TGB_CPG_STATE_DOUBLES(C);
+            for (int i = lane; i < 3 * C; i += LPE) { cs[i] = sX[i]; cs[3 * C + 2 + i] = sPid[i]; }
             if (lane == 0) { cs[3 * C] = cpgUpdateTime; cs[3 * C + 1] = cpgCableTime; }
         }
         if (lane == 0) {

@@ -9,7 +9,7 @@ from . import _capi as capi
 from .world import FlatModel
 
 EXAMPLES = ("3_prism", "3_prism_noground", "SUPERball", "SUPERball_flat", "Escape", "Escape_c3", "tsTestRig_basic",
-            "tsTestRig_kinematic", "TetraSpine")
+            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3")
 
 
 def build_example(name):
@@ -62,7 +62,7 @@ class CpgController(object):
     """Static part of a CPG + impedance controller (a ctypes tgb_cpg_desc plus the arrays it points to)."""
 
     def __init__(self, begin, target, pair, n_pairs, impedance, r_const, d_min, d_max, descending_command, control_time,
-                 cable_control_step, max_steps, score_body, height_lo, height_hi):
+                 cable_control_step, max_steps, score_body, height_lo, height_hi, cable_control=0, pid=(0.0, 0.0, 0.0)):
         self.begin = np.ascontiguousarray(begin, dtype=np.int32)
         self.target = np.ascontiguousarray(target, dtype=np.int32)
         self.pair = np.ascontiguousarray(pair, dtype=np.int32)
@@ -71,7 +71,8 @@ class CpgController(object):
         self.n_nodes, self.n_pairs = len(self.begin) - 1, int(n_pairs)
         self.desc = capi.CpgDesc(self.n_nodes, len(self.target), self.begin.ctypes.data_as(i32p), self.target.ctypes.data_as(i32p),
                                  self.pair.ctypes.data_as(i32p), self.n_pairs, int(max_steps), self.impedance.ctypes.data_as(dp), r_const, d_min,
-                                 d_max, descending_command, control_time, cable_control_step, int(score_body), 0, height_lo, height_hi)
+                                 d_max, descending_command, control_time, cable_control_step, int(score_body), int(cable_control), height_lo, height_hi,
+                                 float(pid[0]), float(pid[1]), float(pid[2]))
 
     @property
     def params_per_env(self):
@@ -100,6 +101,56 @@ def tetraspine_cpg():
         if rc != 0:
             raise ValueError(h.tgh_last_error().decode())
         return CpgController(begin, target, pair, npairs.value, imp, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], int(it[0]), int(it[1]), sc[6], sc[7])
+    finally:
+        h.tgh_free(m)
+
+
+def flemons_cpg(name="FlemonsSpine"):
+    """The controller of the kinematic tetrahedral-complex spine (KinematicSpineCPGControl with the Config of
+    test_integration/SpineTests/WorldConf_Spines_test.cpp:110-147; tgCPGCableControl + tgPIDController(5000, 0, 10, tension control) on
+    every tgKinematicActuator), flattened by the C++ host code for tgb_set_cpg_controller (cable_control = 1)."""
+    h = capi.load_host()
+    m = h.tgh_build_example(name.encode())
+    if not m:
+        raise ValueError(h.tgh_last_error().decode())
+    try:
+        nn, nc, npairs = C.c_int(), C.c_int(), C.c_int()
+        if h.tgh_flemons_cpg(m, C.byref(nn), C.byref(nc), C.byref(npairs), None, None, None, None, None, None) != 0:
+            raise ValueError(h.tgh_last_error().decode())
+        begin = np.zeros(nn.value + 1, dtype=np.int32)
+        target = np.zeros(nc.value, dtype=np.int32)
+        pair = np.zeros(nc.value, dtype=np.int32)
+        imp = np.zeros((nn.value, 4))
+        sc = np.zeros(11)
+        it = np.zeros(2, dtype=np.int32)
+        vp = C.c_void_p
+        rc = h.tgh_flemons_cpg(m, C.byref(nn), C.byref(nc), C.byref(npairs), begin.ctypes.data_as(vp), target.ctypes.data_as(vp),
+                               pair.ctypes.data_as(vp), imp.ctypes.data_as(vp), sc.ctypes.data_as(vp), it.ctypes.data_as(vp))
+        if rc != 0:
+            raise ValueError(h.tgh_last_error().decode())
+        return CpgController(begin, target, pair, npairs.value, imp, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5], int(it[0]), int(it[1]), sc[6], sc[7],
+                             cable_control=1, pid=(sc[8], sc[9], sc[10]))
+    finally:
+        h.tgh_free(m)
+
+
+def flemons_param_rows(node_actions, edge_actions, name="FlemonsSpine"):
+    """scaleNodeActions + scaleEdgeActions for the kinematic tetrahedral-complex spine: node_actions [P, 2], edge_actions [P, 100, 2] in
+    [0, 1] (resources/src/learningSpines/TetrahedralComplex/logs/bestParameters-default_*.nnw) -> rows [P, 2 + 2 * 192]."""
+    h = capi.load_host()
+    m = h.tgh_build_example(name.encode())
+    if not m:
+        raise ValueError(h.tgh_last_error().decode())
+    try:
+        na = np.ascontiguousarray(node_actions, dtype=np.float64).reshape(-1, 2)
+        ea = np.ascontiguousarray(edge_actions, dtype=np.float64).reshape(na.shape[0], -1, 2)
+        rows = np.zeros((na.shape[0], 2 + 2 * 192))
+        vp = C.c_void_p
+        for i in range(na.shape[0]):
+            used = h.tgh_flemons_param_row(m, na[i].ctypes.data_as(vp), ea[i].ctypes.data_as(vp), ea.shape[1], rows[i].ctypes.data_as(vp))
+            if used != ea.shape[1]:
+                raise ValueError("scaleEdgeActions consumed %d of %d edge actions" % (used, ea.shape[1]))
+        return rows
     finally:
         h.tgh_free(m)
 

@@ -271,6 +271,72 @@ void TetraSpineLearningModel::teardown() {
     m_allSegments.clear();
 }
 
+/* ---- tetrahedral complex spine, kinematic actuators ----------------------------------------------------------------- */
+FlemonsSpineModelLearning::FlemonsSpineModelLearning(std::size_t segments) : m_segments(segments) {}
+void FlemonsSpineModelLearning::setup(tgWorld& world) {
+    /* FlemonsSpineModelLearning.cpp:62-92 */
+    const double density = 4.2 / 300.0, radius = 0.5, friction = 0.5, rollFriction = 0.0, restitution = 0.0;
+    const tgRod::Config rodConfig(radius, density, friction, rollFriction, restitution);
+    const double elasticity = 1000.0, damping = 10.0, pretension = 0.0, maxTens = 7000.0, maxSpeed = 12.0;
+    const double mRad = 1.0, motorFriction = 10.0, motorInertia = 1.0;
+    const bool backDrivable = false, history = false;
+    tgKinematicActuator::Config motorConfig(elasticity, damping, pretension, mRad, motorFriction, motorInertia, backDrivable, history, maxTens,
+                                            maxSpeed);
+    const double v_size = 10.0;
+    tgStructure tetra;
+    tetra.addNode(0.0, 0.0, 0.0);             /* center */
+    tetra.addNode(v_size, v_size, v_size);    /* front */
+    tetra.addNode(v_size, -v_size, -v_size);  /* right */
+    tetra.addNode(-v_size, v_size, -v_size);  /* back */
+    tetra.addNode(-v_size, -v_size, v_size);  /* left */
+    const char* rodTags[4] = {"front rod", "right rod", "back rod", "left rod"};
+    for (int i = 0; i < 4; ++i) tetra.addPair(0, i + 1, rodTags[i]);
+    tetra.move(btVector3(0.0, 15.0, 100.0));
+
+    tgStructure snake;
+    const btVector3 offset(0.0, 0.0, -v_size * 1.15);
+    for (std::size_t i = 0; i < m_segments; ++i) {
+        tgStructure* const p = new tgStructure(tetra);
+        p->addTags(numbered("segment num", (int)i + 1));
+        p->move((btScalar)(i + 1.0) * offset);
+        snake.addChild(p);
+    }
+    const std::vector<tgStructure*>& children = snake.getChildren();
+    for (std::size_t i = 1; i < children.size(); ++i) {
+        const tgNodes& n0 = children[i - 1]->getNodes();
+        const tgNodes& n1 = children[i]->getNodes();
+        const std::string seg = numbered(" seg", (int)i - 1) + numbered(" seg", (int)i);
+        snake.addPair(n0[1], n1[1], "outer front muscle" + seg);
+        snake.addPair(n0[2], n1[2], "outer right muscle" + seg);
+        snake.addPair(n0[3], n1[3], "outer back muscle" + seg);
+        snake.addPair(n0[4], n1[4], "outer top muscle" + seg);
+        snake.addPair(n0[2], n1[1], "inner front muscle" + seg);
+        snake.addPair(n0[2], n1[4], "inner right muscle" + seg);
+        snake.addPair(n0[3], n1[1], "inner left muscle" + seg);
+        snake.addPair(n0[3], n1[4], "inner back muscle" + seg);
+    }
+    tgBuildSpec spec;
+    spec.addBuilder("rod", new tgRodInfo(rodConfig));
+    spec.addBuilder("muscle", new tgKinematicActuatorInfo(motorConfig));
+    tgStructureInfo structureInfo(snake, spec);
+    structureInfo.buildInto(*this, world);
+
+    m_allMuscles = tgCast::filter<tgModel, tgSpringCableActuator>(getDescendants());
+    m_allSegments = find<tgModel>(std::string("segment"));
+    notifySetup();
+    tgModel::setup(world);
+}
+void FlemonsSpineModelLearning::step(double dt) {
+    notifyStep(dt);
+    tgModel::step(dt);
+}
+void FlemonsSpineModelLearning::teardown() {
+    notifyTeardown();
+    tgModel::teardown();
+    m_allMuscles.clear();
+    m_allSegments.clear();
+}
+
 tgbSpineControlConfig::tgbSpineControlConfig(int ss, int tm, int om, int param, int segnum, double ct)
     : segmentSpan(ss), theirMuscles(tm), ourMuscles(om), params(param), segmentNumber(segnum), controlTime(ct), lowAmp(0), highAmp(30),
       lowPhase(-1 * M_PI), highPhase(M_PI), lowFreq(0.0), highFreq(30.0) {

@@ -79,6 +79,25 @@ private:
     std::vector<tgModel*> m_allSegments;
 };
 
+/* 12-segment tetrahedral-complex ("Flemons") spine on kinematic actuators: every vertebra's 4 rods (centre to the corners of a
+   tetrahedron) auto-compound into one body, 8 tgKinematicActuator cables between consecutive vertebrae
+   (src/examples/learningSpines/TetrahedralComplex/FlemonsSpineModelLearning.cpp:51-206, USE_KINEMATIC) */
+class FlemonsSpineModelLearning : public tgSubject<FlemonsSpineModelLearning>, public tgModel {
+public:
+    explicit FlemonsSpineModelLearning(std::size_t segments);
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt);
+    virtual void teardown();
+    virtual bool stepsOnHost() const { return numObservers() > 0; }
+    const std::vector<tgSpringCableActuator*>& getAllMuscles() const { return m_allMuscles; }
+    std::size_t getSegments() const { return m_segments; }
+    const std::vector<tgModel*>& getAllSegments() const { return m_allSegments; }
+private:
+    std::size_t m_segments;
+    std::vector<tgSpringCableActuator*> m_allMuscles;
+    std::vector<tgModel*> m_allSegments;
+};
+
 /* ---- CPG + impedance control of the spine examples, flattened for tgb_set_cpg_controller ------------------------- */
 /* BaseSpineCPGControl::Config (BaseSpineCPGControl.h:60-77) with its defaults */
 struct tgbSpineControlConfig {

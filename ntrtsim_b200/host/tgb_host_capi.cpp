@@ -58,6 +58,12 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
             e->world = new tgWorld(tgWorld::Config(981));
             e->dt = 0.001;
             e->model = new TetraSpineLearningModel(3);
+        } else if (name == "FlemonsSpine" || name == "FlemonsSpine3") {
+            /* WorldConf_Spines_test.cpp:85-108 / AppFlemonsSpineLearning: tgWorld(Config(981)), default box ground, dt = 1e-3, 12
+               segments ("FlemonsSpine3": the same vertebrae, 3 segments, for small tests) */
+            e->world = new tgWorld(tgWorld::Config(981));
+            e->dt = 0.001;
+            e->model = new FlemonsSpineModelLearning(name == "FlemonsSpine" ? 12 : 3);
         } else {
             g_error = "unknown example: " + name;
             delete e;
@@ -189,6 +195,63 @@ int tgh_tetraspine_cpg(const tgh_model* m, int* n_nodes, int* n_couplings, int* 
     }
     if (ints) { ints[0] = 200; ints[1] = cfg.segmentNumber; }
     return 0;
+}
+
+/* The controller of the kinematic tetrahedral-complex spine, flattened for tgb_set_cpg_controller with cable_control = 1:
+   KinematicSpineCPGControl with the Config of WorldConf_Spines_test.cpp:110-147 (segmentSpan 3, 8 muscles, 2 params, scored segment 6 --
+   clamped to the last segment of a shorter spine --, controlTime .01, amplitude and frequency ranges [-30, 30], impedance gains
+   kt 0 / kp 1000 / kv 210 with the default control length = each muscle's start length), tgCPGCableControl(tgPIDController::Config(5000,
+   0, 10, true), controlTime) per muscle (KinematicSpineCPGControl.cpp:69-76).  scalars additionally carry the PID gains [8..10]. */
+static tgbSpineControlConfig flemonsControlConfig(std::size_t segments) {
+    tgbSpineControlConfig cfg(3, 8, 8, 2, segments > 6 ? 6 : (int)segments - 1, .01);
+    cfg.lowAmp = -30.0; cfg.highAmp = 30.0; cfg.lowFreq = -30.0; cfg.highFreq = 30.0;
+    return cfg;
+}
+int tgh_flemons_cpg(const tgh_model* m, int* n_nodes, int* n_couplings, int* n_pairs, int32_t* begin, int32_t* target, int32_t* pair,
+                    double* impedance, double* scalars /* r_const, d_min, d_max, desc, control_time, cable_step, lo, hi, kP, kI, kD */,
+                    int* ints /* max_steps, score_body */) {
+    const Example* e = reinterpret_cast<const Example*>(m);
+    if (!e) return 1;
+    const FlemonsSpineModelLearning* model = dynamic_cast<const FlemonsSpineModelLearning*>(e->model);
+    if (!model) { g_error = "not a FlemonsSpineModelLearning"; return 1; }
+    const tgWorldB200Impl& w = e->world->b200();
+    const tgbSpineControlConfig cfg = flemonsControlConfig(model->getSegments());
+    std::vector<int32_t> b, t, p;
+    try {
+        tgbSpineCpgTopology(w.cables(), cfg, b, t, p);
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        return 5;
+    }
+    *n_nodes = (int)w.cables().size();
+    *n_couplings = (int)t.size();
+    *n_pairs = cfg.tablePairs();
+    if (begin) std::memcpy(begin, b.data(), b.size() * sizeof(int32_t));
+    if (target) std::memcpy(target, t.data(), t.size() * sizeof(int32_t));
+    if (pair) std::memcpy(pair, p.data(), p.size() * sizeof(int32_t));
+    if (impedance) {
+        const std::vector<tgSpringCableActuator*>& muscles = model->getAllMuscles();
+        for (std::size_t i = 0; i < muscles.size(); ++i) {
+            double* g = impedance + 4 * muscles[i]->cableIndex();
+            g[0] = 0.0; g[1] = 1000.0; g[2] = 210.0;
+            g[3] = muscles[i]->getStartLength(); /* tgCPGActuatorControl::onAttach, tgCPGActuatorControl.cpp:64-66 */
+        }
+    }
+    if (scalars) {
+        scalars[0] = 20.0; scalars[1] = 0.0; scalars[2] = 5.0; scalars[3] = 2.0; scalars[4] = cfg.controlTime; scalars[5] = cfg.controlTime;
+        scalars[6] = 1.0; scalars[7] = 25.0;
+        scalars[8] = -5000.0; scalars[9] = -0.0; scalars[10] = -10.0; /* tension control inverts the gains, tgPIDController.cpp:34-43 */
+    }
+    if (ints) { ints[0] = 200; ints[1] = cfg.segmentNumber; }
+    return 0;
+}
+int tgh_flemons_param_row(const tgh_model* m, const double* node_actions, const double* edge_actions, int n_edge, double* row) {
+    const Example* e = reinterpret_cast<const Example*>(m);
+    const FlemonsSpineModelLearning* model = e ? dynamic_cast<const FlemonsSpineModelLearning*>(e->model) : 0;
+    if (!model) return -1;
+    const tgbSpineControlConfig cfg = flemonsControlConfig(model->getSegments());
+    tgbSpineScaleNodeActions(node_actions, cfg, row);
+    return tgbSpineScaleEdgeActions(edge_actions, n_edge, cfg, row + 2);
 }
 
 /* scaleNodeActions + scaleEdgeActions for the TetraSpine configuration: node_actions[2], edge_actions[n_edge][2] in [0,1]

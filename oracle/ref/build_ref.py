@@ -27,6 +27,7 @@ REFERENCE_SOURCES = [
     "src/controllers/tgBasicController.cpp",
     "src/controllers/tgTensionController.cpp",
     "src/controllers/tgImpedanceController.cpp",
+    "src/controllers/tgPIDController.cpp",
     "src/util/CPGNode.cpp",
     "src/util/CPGEquations.cpp",
 ]
@@ -39,6 +40,9 @@ def build():
     os.makedirs(OUT, exist_ok=True)
     srcs = [os.path.join(REF, s) for s in REFERENCE_SOURCES if os.path.exists(os.path.join(REF, s))]
     cmd = ["g++", "-std=c++11", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-DBT_USE_DOUBLE_PRECISION",
+           # bind the reference's symbols inside this library: the host mirror (libtgb_host.so, loaded RTLD_GLOBAL) defines classes of
+           # the same names and must not interpose on them
+           "-Wl,-Bsymbolic",
            "-I", os.path.join(HERE, "shim"), "-I", os.path.join(ROOT, "ntrtsim_b200", "host"), "-I", os.path.join(REF, "src"),
            "-o", os.path.join(OUT, "libntrt_ref.so"), os.path.join(HERE, "ref_harness.cpp")] + srcs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)

@@ -59,7 +59,65 @@ def sample_steps(steps):
     return sorted(set(list(range(0, 20)) + list(range(20, steps, 10)) + [steps - 1]))
 
 
+def flemons_golden():
+    """Kinematic tetrahedral-complex spine: CPGEquations + tgImpedanceController + tgPIDController + tgKinematicActuator (all reference
+    code) under the tgCPGCableControl timing (tgCPGCableControl.cpp:63-98), for the 3-segment and the 12-segment spine."""
+    res = os.path.join(os.environ.get("NTRT_REFERENCE", "/root/reference"), "resources", "src", "learningSpines", "TetrahedralComplex", "logs")
+
+    def nnw(name):
+        return [float(x) for x in open(os.path.join(res, name)).read().strip().split(",")]
+    node_actions = np.array(nnw("bestParameters-default_node-0.nnw"))
+    edge_actions = np.array([nnw("bestParameters-default_edge-%d.nnw" % i) for i in range(100)])
+    for name, steps in (("FlemonsSpine3", 400), ("FlemonsSpine", 300)):
+        m = nt.build_example(name)
+        ctl = nt.flemons_cpg(name)
+        row = nt.flemons_param_rows(node_actions[None], edge_actions[None], name)[0]
+        d = ctl.desc
+        cpg = ref_py.RefCPG(d.max_steps)
+        nC = m.n_cables
+        for _ in range(nC):
+            cpg.add_node([row[0], row[0], row[1], row[1], d.r_const, d.d_min, d.d_max])                    # assignNodeNumber
+        for i in range(nC):                                                                                # setConnectivity
+            ks = range(ctl.begin[i], ctl.begin[i + 1])
+            cpg.define_connections(i, [ctl.target[k] for k in ks], [row[2 + 2 * ctl.pair[k]] for k in ks], [row[3 + 2 * ctl.pair[k]] for k in ks])
+        st = {"update": 0.0, "cable": [0.0] * nC, "commanded": [0.0] * nC, "bogus": False, "cpg": [], "made": False}
+
+        def spine(ref, s, dt_, st=st, ctl=ctl, d=d, cpg=cpg, nC=nC):
+            if not st["made"]:                                         # tgCPGCableControl::onSetup
+                for i in range(nC):
+                    assert ref.pid_create(i, 5000.0, 0.0, 10.0, True) == 0
+                st["made"] = True
+            st["update"] += dt_                                        # BaseSpineCPGControl::onStep
+            if st["update"] >= d.control_time:
+                assert cpg.update([d.descending_command] * nC, st["update"]) == 0
+                st["update"] = 0.0
+            h = ref.get_bodies()[d.score_body, 1]
+            if h > d.height_hi or h < d.height_lo:
+                st["bogus"] = True
+            vals = cpg.values()
+            for i in range(nC):                                        # tgCPGCableControl::onStep (usePID)
+                st["cable"][i] += dt_
+                if st["cable"][i] >= d.cable_control_step:
+                    g = ctl.impedance[i]
+                    st["commanded"][i] = ref.impedance_control_pid(i, dt_, g[0], g[1], g[2], g[3], vals[i])
+                    st["cable"][i] = 0.0
+                else:
+                    ref.pid_control(i, dt_, st["commanded"][i])
+            st["cpg"].append(cpg.state())
+        keep = sample_steps(steps)
+        ts, rods, cabs = hybrid_rollout(m, 0.0, m.initial_rod_state(), 1e-3, steps, spine, keep=keep)
+        np.savez_compressed(os.path.join(OUT, "%s_kinematic_cpg.npz" % name.lower()), rods0=m.initial_rod_state(), dt=1e-3, steps=ts, rods=rods,
+                            cables=cabs, node_actions=node_actions, edge_actions=edge_actions, param_row=row,
+                            cpg_states=np.array(st["cpg"])[keep], bogus=st["bogus"])
+        print(name, "hybrid rollout done: bogus", st["bogus"], "max tension", cabs[..., 3].max(), "rest range", cabs[..., 0].min(), cabs[..., 0].max())
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "flemons":
+        if not ref_py.available():
+            build_ref.build()
+        flemons_golden()
+        return
     if not ref_py.available():
         build_ref.build()
     os.makedirs(OUT, exist_ok=True)
@@ -201,6 +259,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "tetraspine_cpg.npz"), rods0=m.initial_rod_state(), dt=1e-3, steps=ts, rods=rods, cables=cabs,
                         node_actions=node_actions, edge_actions=edge_actions, param_row=row, cpg_states=np.array(st["cpg"])[keep],
                         bogus=st["bogus"])
+    flemons_golden()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-28s %6d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -11,6 +11,7 @@
 #include "core/tgSpringCableActuator.h"
 #include "controllers/tgTensionController.h"
 #include "controllers/tgImpedanceController.h"
+#include "controllers/tgPIDController.h"
 #include "util/CPGEquations.h"
 #include "BulletDynamics/Dynamics/btRigidBody.h"
 
@@ -23,9 +24,11 @@ struct ref_world {
     std::vector<tgSpringCableActuator*> actuators;
     std::vector<tgBulletSpringCable*> cables;
     std::vector<tgTensionController*> tensionControllers;
+    std::vector<tgPIDController*> pids;
     std::vector<int> kinds;
     ~ref_world() {
         for (size_t i = 0; i < tensionControllers.size(); ++i) delete tensionControllers[i];
+        for (size_t i = 0; i < pids.size(); ++i) delete pids[i];
         for (size_t i = 0; i < actuators.size(); ++i) delete actuators[i]; /* deletes its cable and the anchors */
         for (size_t i = 0; i < bodies.size(); ++i) delete bodies[i];
     }
@@ -92,6 +95,7 @@ int ref_add_cable(ref_world* w, int a, int b, const double* worldA, const double
         w->actuators.push_back(act);
         w->kinds.push_back(kind);
         w->tensionControllers.push_back(kind == 1 ? new tgTensionController(static_cast<tgBasicActuator*>(act), 0.0) : 0);
+        w->pids.push_back(0);
         return (int)w->actuators.size() - 1;
     } catch (const std::exception& e) {
         g_err = e.what();
@@ -139,6 +143,25 @@ int ref_tension_control(ref_world* w, int c, double dt, double setPoint) {
 double ref_impedance_control(ref_world* w, int c, double dt, double T0, double Kp, double Kv, double newPosition, double offsetVel) {
     tgImpedanceController ic(T0, Kp, Kv);
     return ic.control(*static_cast<tgBasicActuator*>(w->actuators[c]), dt, newPosition, offsetVel);
+}
+/* tgCPGCableControl::onSetup: m_PID = new tgPIDController(&subject, Config(p, i, d, tensControl)) (tgCPGCableControl.cpp:52-61) */
+int ref_pid_create(ref_world* w, int c, double p, double i, double d, int tensControl) {
+    try {
+        delete w->pids[c];
+        w->pids[c] = new tgPIDController(w->actuators[c], tgPIDController::Config(p, i, d, tensControl != 0));
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+/* tgImpedanceController(T0, Kp, Kv).control(tgBasicController& = the cable's tgPIDController, dt, newPosition, offsetVel)
+   (tgCPGCableControl.cpp:73); returns the set tension */
+double ref_impedance_control_pid(ref_world* w, int c, double dt, double T0, double Kp, double Kv, double newPosition, double offsetVel) {
+    tgImpedanceController ic(T0, Kp, Kv);
+    return ic.control(*w->pids[c], dt, newPosition, offsetVel);
+}
+/* m_PID->control(dt, commandedTension, currentTension) with currentTension = subject.getTension() (tgCPGCableControl.cpp:83-87) */
+void ref_pid_control(ref_world* w, int c, double dt, double setPoint) {
+    const double currentTension = w->actuators[c]->getTension();
+    w->pids[c]->control(dt, setPoint, currentTension);
 }
 /* tgModel::step over the connectors: every actuator's step(dt) in creation order; 1 = std::invalid_argument */
 int ref_step_actuators(ref_world* w, double dt) {

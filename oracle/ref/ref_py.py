@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(os.path.dirname(HERE), "_ref", "libntrt_ref.so")
+LIB = os.environ.get("NTRT_REF_LIB", os.path.join(os.path.dirname(HERE), "_ref", "libntrt_ref.so"))
 _lib = None
 
 
@@ -34,6 +34,10 @@ def load():
         lib.ref_impedance_control.argtypes = [vp, i, d, d, d, d, d, d]
         lib.ref_impedance_control.restype = d
         lib.ref_step_actuators.argtypes = [vp, d]
+        lib.ref_pid_create.argtypes = [vp, i, d, d, d, i]
+        lib.ref_impedance_control_pid.argtypes = [vp, i, d, d, d, d, d, d]
+        lib.ref_impedance_control_pid.restype = d
+        lib.ref_pid_control.argtypes = [vp, i, d, d]
         lib.ref_cpg_create.restype = vp
         lib.ref_cpg_create.argtypes = [i]
         lib.ref_cpg_destroy.argtypes = [vp]
@@ -118,6 +122,15 @@ class RefModels(object):
 
     def impedance_control(self, c, dt, T0, Kp, Kv, new_position, offset_vel):
         return self.lib.ref_impedance_control(self.h, c, dt, T0, Kp, Kv, new_position, offset_vel)
+
+    def pid_create(self, c, p, i, d, tension_control=True):
+        return self.lib.ref_pid_create(self.h, c, p, i, d, 1 if tension_control else 0)
+
+    def impedance_control_pid(self, c, dt, T0, Kp, Kv, new_position, offset_vel):
+        return self.lib.ref_impedance_control_pid(self.h, c, dt, T0, Kp, Kv, new_position, offset_vel)
+
+    def pid_control(self, c, dt, set_point):
+        self.lib.ref_pid_control(self.h, c, dt, set_point)
 
     def step_actuators(self, dt):
         return self.lib.ref_step_actuators(self.h, dt)

@@ -232,6 +232,10 @@ struct tgo_world {
         double updateTime = 0;
         std::vector<double> cableTime;   /* tgCPGActuatorControl::m_controlTime of every cable */
         int numSteps = 0;
+        /* tgCPGCableControl (cable_control 1): tgPIDController gains and state, last commanded tension of every cable */
+        int cableControl = 0;
+        double kP = 0, kI = 0, kD = 0;
+        std::vector<double> pidPrevError, pidIntError, commandedTension;
     } cpg;
 
     /* CPGNode::nodeEquation, CPGNode.cpp:90-101 */
@@ -272,13 +276,42 @@ struct tgo_world {
         for (int i = 0; i < cpg.nNodes; ++i) cpg.nodeValue[i] = cpg.x[3 * i + 1] * std::cos(cpg.x[3 * i]); /* CPGNode::updateNodeValues */
         if (cpg.numSteps > cpg.maxSteps) status |= 4; /* "Inefficient CPG Parameters" */
     }
-    /* tgCPGActuatorControl::onStep (tgCPGActuatorControl.cpp:79-100) for cable i */
+    /* tgPIDController::control(dt, setPoint, sensorData), tgPIDController.cpp:80-109; the controllable is a tgKinematicActuator,
+       whose setControlInput stores the desired torque (tgKinematicActuator.cpp:227-230) */
+    void pidControl(int i, double dt, double setPoint, double sensorData) {
+        const double error = setPoint - sensorData;
+        cpg.pidIntError[i] += (error + cpg.pidPrevError[i]) / 2.0 * dt;
+        const double dError = (error - cpg.pidPrevError[i]) / dt;
+        const double result = cpg.kP * error + cpg.kI * cpg.pidIntError[i] + cpg.kD * dError;
+        cables[i].desiredTorque = result;
+        cpg.pidPrevError[i] = error;
+    }
+
+    /* tgCPGActuatorControl::onStep (tgCPGActuatorControl.cpp:79-100) / tgCPGCableControl::onStep (tgCPGCableControl.cpp:63-98)
+       for cable i */
     void cpgCableControl(int i, double dt) {
         Cable& c = cables[i];
         cpg.cableTime[i] += dt;
+        const double* g = &cpg.impedance[4 * i];
+        if (c.actuator == TGB_ACT_KINEMATIC) { /* tgCPGCableControl with usePID */
+            if (cpg.cableTime[i] >= cpg.cableStep) {
+                /* tgImpedanceController::controlTension(tgBasicController&, ...), tgImpedanceController.cpp:118-150 */
+                const double actualLength = cableLength(c);
+                const double vel = c.motorVel * c.mRadius; /* tgKinematicActuator::getVelocity, tgKinematicActuator.cpp:181-184 */
+                const double setTension = std::max(0.0, g[0] + g[1] * (actualLength - g[3]) + g[2] * (vel - cpg.nodeValue[i]));
+                const double currentTension = cableTension(c);
+                pidControl(i, dt, setTension, currentTension);
+                cpg.commandedTension[i] = setTension;
+                cpg.cableTime[i] = 0;
+            } else {
+                const double currentTension = cableTension(c);
+                pidControl(i, dt, cpg.commandedTension[i], currentTension);
+            }
+            return;
+        }
         if (cpg.cableTime[i] >= cpg.cableStep) {
-            const double ct = cpg.cableTime[i];
-            const double* g = &cpg.impedance[4 * i];
+            /* tgCPGActuatorControl hands the accumulated control time to the controller, tgCPGCableControl the step's dt */
+            const double ct = cpg.cableControl == 1 ? dt : cpg.cableTime[i];
             /* tgImpedanceController::controlTension(tgBasicActuator&, ...), tgImpedanceController.cpp:163-185 */
             const double actualLength = cableLength(c);
             const double vel = c.velocity;
@@ -291,6 +324,7 @@ struct tgo_world {
             double newLength = c.rest - diff;
             newLength = newLength < 0.1 ? 0.1 : newLength;
             setControlInput(c, newLength, ct);
+            cpg.commandedTension[i] = setTension;
             cpg.cableTime[i] = 0;
         } else {
             moveMotors(c, dt);
@@ -442,7 +476,8 @@ struct tgo_world {
         controllersStep(dt);
         for (size_t i = 0; i < cables.size(); ++i) {
             Cable& c = cables[i];
-            if (ctrlKind == TGB_CTRL_CPG_IMPEDANCE && c.actuator == TGB_ACT_BASIC) cpgCableControl((int)i, dt); /* notifyStep of the actuator */
+            if (ctrlKind == TGB_CTRL_CPG_IMPEDANCE && (c.actuator == TGB_ACT_BASIC || (c.actuator == TGB_ACT_KINEMATIC && cpg.cableControl == 1)))
+                cpgCableControl((int)i, dt); /* notifyStep of the actuator */
             if (c.actuator == TGB_ACT_KINEMATIC) {
                 integrateRestLength(c, dt);
                 cableForce(c, dt);
@@ -825,6 +860,8 @@ int tgo_set_cpg_controller(tgo_world* w, const tgb_cpg_desc* d, const double* pa
     c.x.assign(3 * d->n_nodes, 0.0);
     c.nodeValue.assign(d->n_nodes, 0.0);
     c.cableTime.assign(d->n_nodes, 0.0);
+    c.cableControl = d->cable_control; c.kP = d->pid_kp; c.kI = d->pid_ki; c.kD = d->pid_kd;
+    c.pidPrevError.assign(d->n_nodes, 0.0); c.pidIntError.assign(d->n_nodes, 0.0); c.commandedTension.assign(d->n_nodes, 0.0);
     w->ctrlKind = TGB_CTRL_CPG_IMPEDANCE;
     w->status = 0;
     w->episodeStartCom = w->scoreCom();

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.tgb_abi_version() == 1
+    assert lib.tgb_abi_version() == 2  # 2: tgb_cpg_desc gained cable_control and the PID gains
 
 
 def test_create_fails_loudly_without_a_gpu():

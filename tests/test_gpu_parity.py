@@ -437,6 +437,79 @@ def test_tetraspine_cpg_f32_short_horizon():
     assert perr[0] < F32_REL and perr[1] < F32_REL and lerr < F32_REL and rerr < F32_REL
 
 
+def flemons_inputs(example, n_env, seed=13):
+    """controller rows for a population of the kinematic tetrahedral-complex spine: the shipped parameters, mutated like
+    NeuroEvoMember::mutate (member 0 = the shipped parameters)"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "%s_kinematic_cpg.npz" % example.lower()))
+    rng = np.random.default_rng(seed)
+    node = np.clip(g["node_actions"][None] + rng.normal(0, 0.03, size=(n_env, 2)), 0, 1)
+    edge = np.clip(g["edge_actions"][None] + rng.normal(0, 0.03, size=(n_env, 100, 2)), 0, 1)
+    node[0], edge[0] = g["node_actions"], g["edge_actions"]
+    return nt.flemons_param_rows(node, edge, example)
+
+
+@pytest.mark.parametrize("example,steps", [("FlemonsSpine3", 1), ("FlemonsSpine3", 60), ("FlemonsSpine", 60)])
+def test_flemons_kinematic_cpg_pid_f64(example, steps):
+    """tgKinematicActuator cables driven by CPG -> impedance -> tgPIDController (cable_control 1), 3 and 12
+    vertebrae (12 compound bodies of 4 cylinders, 88 cables, 16 lanes per environment): double path vs the oracle."""
+    model, ctl = nt.build_example(example), nt.flemons_cpg(example)
+    n_env = 9
+    rows = flemons_inputs(example, n_env)
+    rods, cab = np.tile(model.initial_rod_state(), (n_env, 1, 1)), tiled_cables(model, n_env)
+    w = nt.BatchedWorld(model, n_env, precision="f64")
+    w.set_cpg_controller(ctl, rows)
+    w.step(model.dt, steps)
+    rd, cd, x = w.get_rod_state(), w.get_cable_obs(), w.get_cpg_state()
+    sc, st = w.scores(), w.status()
+    w.close()
+    ro, co, so, sto = oracle_py.rollout_batch(model, capi.WorldCfg, rods, cab, model.dt, steps, capi.TGB_CTRL_CPG_IMPEDANCE, rows,
+                                              cpg_desc=ctl.desc, want_scores=True, n_threads=8)
+    xo = []
+    for e in range(n_env):
+        o = oracle_py.OracleWorld(model, capi.WorldCfg)
+        o.set_cpg_controller(ctl.desc, rows[e])
+        o.step(model.dt, steps)
+        xo.append(o.cpg_state())
+    print("%s f64 %d steps: rods %s, cables %.2e, cpg %.2e" % (example, steps, rod_errors(rd, ro, 1.0), np.abs(cd - co).max(),
+                                                               np.abs(x - np.array(xo)).max()))
+    assert np.abs(x - np.array(xo)).max() < 1e-9
+    assert max(rod_errors(rd, ro, 1.0)) < 1e-6       # the PID loop amplifies round-off ~10x / 20 steps (tests/test_golden.py)
+    assert tension_rel_error(cd, co, floor=10.0) < 1e-6
+    assert np.abs(cd[..., 3] - co[..., 3]).max() < 1e-6   # motor velocity
+    assert np.abs(sc - so).max() < 1e-6 and np.array_equal(st & 6, sto & 6)
+
+
+def test_flemons_kinematic_cpg_pid_f32_short_horizon():
+    """Single precision on the PID-controlled kinematic spine.  tgPIDController differentiates the tension error over dt = 1e-3 with
+    kD = 10 (and kP = 5000): the tension (length - rest) * k carries the single-precision resolution of a length of ~11 on k = 1000,
+    ~1e-3, which the derivative term turns into torque noise of the order of 10 and the non-backdrivable motor's switching logic into
+    per-environment divergence as soon as the cables go taut (step ~21; measured: motor velocity off by 5 at step 25).  The stated
+    FP32 tolerance is therefore only meaningful until then -- 20 steps here; the double-precision instantiation is the one to use
+    for this controller (tests above).  Later steps are checked for sanity only: finite state, rest lengths within the motor limits."""
+    example = "FlemonsSpine"
+    model, ctl = nt.build_example(example), nt.flemons_cpg(example)
+    n_env, steps = 32, 20
+    rows = flemons_inputs(example, n_env)
+    rods, cab = np.tile(model.initial_rod_state(), (n_env, 1, 1)), tiled_cables(model, n_env)
+    w = nt.BatchedWorld(model, n_env, precision="f32")
+    w.set_cpg_controller(ctl, rows)
+    w.step(model.dt, steps)
+    rd, cd = w.get_rod_state(), w.get_cable_obs()
+    ro, co = oracle_py.rollout_batch(model, capi.WorldCfg, rods, cab, model.dt, steps, capi.TGB_CTRL_CPG_IMPEDANCE, rows, cpg_desc=ctl.desc,
+                                     n_threads=8)
+    perr = rod_errors(rd, ro, 20.0)
+    lerr = np.abs(cd[..., 1] - co[..., 1]).max() / 20.0
+    rerr = np.abs(cd[..., 0] - co[..., 0]).max() / 20.0
+    print("flemons f32 %d steps: rods %s length %.2e rest %.2e" % (steps, perr, lerr, rerr))
+    assert perr[0] < F32_REL and perr[1] < F32_REL and lerr < F32_REL and rerr < F32_REL
+    w.step(model.dt, 180)
+    rd, cd, st = w.get_rod_state(), w.get_cable_obs(), w.status()
+    w.close()
+    assert np.isfinite(rd).all() and np.isfinite(cd).all() and not (st & 1).any()
+    assert cd[..., 0].min() >= 0.1 - 1e-6 and cd[..., 0].max() < 40.0        # rest length: floor minRestLength, no runaway
+    assert np.abs(cd[..., 3]).max() <= 12.0 * 1.5                           # motor velocity stays of the order of the target velocity
+
+
 def test_population_evaluation_matches_oracle_scores():
     """NeuroEvo-style evaluate(params) -> scores on the device vs the oracle, incl. a member that leaves the height window."""
     from ntrtsim_b200.neuroevo import evaluate_population
