@@ -61,6 +61,23 @@ def build_workload(name, n_env, seed):
         model = nt.build_example("3_prism_noground")
         rods = random_poses(model, n_env, seed=seed)
         params, ctrl, p_ctrl = None, capi.TGB_CTRL_NONE, 0
+    elif name in ("tetraspine", "flemons"):
+        # NeuroEvo population evaluation (BASELINE config 4 / SURVEY 8f rank 1): every environment is one population member, the
+        # shipped parameters mutated like NeuroEvoMember::mutate (N(0, 0.03), clipped to [0, 1]); all members start from the model pose
+        example = "TetraSpine" if name == "tetraspine" else "FlemonsSpine"
+        model = nt.build_example(example)
+        g = np.load(os.path.join(ROOT, "tests", "golden", "tetraspine_cpg.npz" if name == "tetraspine" else "flemonsspine_kinematic_cpg.npz"))
+        rng = np.random.default_rng(seed + 1)
+        n_edge = g["edge_actions"].shape[0]
+        node = np.clip(g["node_actions"][None] + rng.normal(0, 0.03, size=(n_env, 2)), 0, 1)
+        edge = np.clip(g["edge_actions"][None] + rng.normal(0, 0.03, size=(n_env, n_edge, 2)), 0, 1)
+        if name == "tetraspine":
+            model.cpg, params = nt.tetraspine_cpg(), nt.tetraspine_param_rows(node, edge)
+        else:
+            model.cpg, params = nt.flemons_cpg(example), nt.flemons_param_rows(node, edge, example)
+        rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+        ctrl = capi.TGB_CTRL_CPG_IMPEDANCE
+        p_ctrl = 2 * 3 * model.n_cables   # CPG node state (phase, radius, radius rate) read and written every step
     else:
         raise ValueError(name)
     cab = np.tile(model.initial_cable_state(), (n_env, 1, 1))
@@ -68,10 +85,21 @@ def build_workload(name, n_env, seed):
     return model, rods, cab, ctrl, params, b_alg
 
 
+def install_controller(w, model, ctrl, params):
+    from ntrtsim_b200 import _capi as capi
+    if ctrl == capi.TGB_CTRL_CPG_IMPEDANCE:
+        w.set_cpg_controller(model.cpg, params)
+    elif ctrl:
+        w.set_controller(ctrl, params)
+
+
 def workload_desc(name, n_env, H, n_gpus):
     what = {"superball_noground": "SUPERball + sine controller, NO ground, zero gravity (tuning aid)",
             "superball": "SUPERball (EscapeModel: 6 rods, 24 basic-actuator cables) + EscapeController sine, flat box ground, g=98.1",
-            "prism": "3-prism (3 rods, 9 cables), no ground, g=981 (contact-free drop)"}[name]
+            "prism": "3-prism (3 rods, 9 cables), no ground, g=981 (contact-free drop)",
+            "tetraspine": "TetraSpine (3 compound bodies, 12 basic-actuator cables) + CPG/impedance control, population evaluation, box ground, g=981",
+            "flemons": "kinematic tetrahedral-complex spine (12 compound bodies, 88 kinematic-actuator cables) + CPG/impedance/PID control, "
+                       "population evaluation, box ground, g=981"}[name]
     return "%s; %d envs/GPU x %d GPU; dt=1e-3; %d sim steps per launch" % (what, n_env, n_gpus, H)
 
 
@@ -150,7 +178,8 @@ def cpu_port_rate(model, rods, cab, ctrl, params, H, n_env_sample, threads):
     from ntrtsim_b200 import _capi as capi
     p = None if params is None else params[:n_env_sample]
     t0 = time.perf_counter()
-    oracle_py.rollout_batch(model, capi.WorldCfg, rods[:n_env_sample], cab[:n_env_sample], model.dt, H, ctrl, p, n_threads=threads)
+    oracle_py.rollout_batch(model, capi.WorldCfg, rods[:n_env_sample], cab[:n_env_sample], model.dt, H, ctrl, p, n_threads=threads,
+                            cpg_desc=model.cpg.desc if ctrl == capi.TGB_CTRL_CPG_IMPEDANCE else None)
     dt = time.perf_counter() - t0
     return n_env_sample * H / dt, dt
 
@@ -195,7 +224,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--sim-steps", type=int, default=1000, help="simulation steps per launch (H)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--workload", default="superball", choices=["superball", "prism", "superball_noground"])
+    ap.add_argument("--workload", default="superball", choices=["superball", "prism", "superball_noground", "tetraspine", "flemons"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -232,8 +261,7 @@ def main():
     w = nt.BatchedWorld(model, n_env, precision=args.precision, device=local_rank, lanes_per_env=args.lanes, block_threads=args.threads)
     w.set_rod_state(rods)
     w.set_cable_state(cab)
-    if ctrl:
-        w.set_controller(ctrl, params)
+    install_controller(w, model, ctrl, params)
     lanes, block, grid = w.launch_geometry()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -305,8 +333,7 @@ def main():
     # controller time, and every call's inputs are the previous call's outputs (rod records; cable rest length and length),
     # handed over on the host.  Warm-up calls = the warm-up episodes above, so timed call i simulates the same second of
     # each rollout as timed step i above.  Each timed call moves that step's inputs host->device and its results back.
-    if ctrl:
-        w.set_controller(ctrl, params)
+    install_controller(w, model, ctrl, params)
 
     def hand_over():
         rods_p[...] = rod_out

@@ -153,9 +153,9 @@ TGB_D float sinPhase(double arg, float) {
    rods lying flat).  Inlined: a real call here costs more on the hot path (register shuffling around the call site; measured
    -5% on B200) than the cold code costs in instruction-cache footprint. */
 template <typename T>
-__device__ __forceinline__ void pgsSharedRows(T* ct, int laneStride, int nc, int iterations, bool anyPen, V3<T> gn, T invMass, T mu,
+__device__ __forceinline__ void pgsSharedRows(T* ct, int rowStride, int nc, int iterations, bool anyPen, V3<T> gn, T invMass, T mu,
                                            V3<T>& dLin, V3<T>& dAng, V3<T>& push, V3<T>& turn) {
-#define CTG(slot, f) ct[((slot) * TGB_NCT + (f)) * laneStride]
+#define CTG(slot, f) ct[(slot) * rowStride + (f)]
     if (anyPen)
         for (int it = 0; it < iterations; ++it) {
             for (int c = 0; c < nc; ++c) {
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
        list][body lane] of two float4 planes, so that the gather of a body lane is a run of 128-bit loads at consecutive addresses
        across lanes: no index loads, no bank conflicts. */
     const int jWords = kFast ? a.max_inc * LPE * 8 : 3 * C;
-    const int ctWords = a.cap_contacts * TGB_NCT * LPE;
+    const int ctWords = a.cap_contacts * TGB_NCT * R; /* rows [slot][body][TGB_NCT]: 23 words apart across lanes, conflict-free */
     /* the contact rows (live from contact generation to the end of the solver) and the cable impulses (live from the cable
        phase to the impulse gather) share one region: shared memory per environment decides how many CTAs an SM holds */
     const int exchangeWords = TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     T* sState = sGroupT;                       /* env record: bodies then cables */
     T* sPose = sState + a.stride;              /* [LPE][12] : pos3, basis9 of each body, one 16-byte aligned record per body */
     T* sJ = sPose + poseWords;                 /* [C][3] */
-    T* sCt = TGB_EXCHANGE_UNION ? sJ : sJ + jWords; /* [cap][TGB_NCT][LPE], same region */
+    T* sCt = TGB_EXCHANGE_UNION ? sJ : sJ + jWords; /* [cap][R][TGB_NCT], same region */
     constexpr bool cpgOn = CLASS == TGB_CLASS_CPG;
     constexpr bool sineOn = CLASS == TGB_CLASS_SINE;
     constexpr bool simpleOn = CLASS == TGB_CLASS_SIMPLE;
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     /* a frame tied to a static body never moves: static bodies then stay bit-exactly in place */
     const bool frameMoves = M.body(BF_INVMASS, a.frame_body) != T(0);
 
-#define CT(slot, f) sCt[((slot) * TGB_NCT + (f)) * LPE + lane]
+#define CT(slot, f) sCt[((slot) * R + bidx) * TGB_NCT + (f)]
 
     /* ---- CPG: CPGNode::updateDTs for this lane's nodes (CPGNode.cpp:71-88). Every lane of the warp calls this the same
        number of times (it synchronises); `act` masks groups that have nothing to do. sin(phi_j - phi_i - theta) is
@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                     }
                 }
             } else if (nc > 0) {
-                pgsSharedRows<T>(sCt + lane, LPE, nc, a.iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
+                pgsSharedRows<T>(sCt + bidx * TGB_NCT, R * TGB_NCT, nc, a.iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
             }
 
             /* ---- write back, split-impulse correction, integrateTransforms ---- */
@@ -1348,7 +1348,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
     const int groupsPerBlock = threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
-    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * TGB_NCT * lpe;
+    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * TGB_NCT * a.R;
     int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords);
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
