@@ -212,10 +212,32 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL prints its version banner) write to stdout: hand them stderr and keep the real stdout for the one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -399,7 +421,7 @@ def main():
                                     "sample": "%d envs x %d sim steps of the same workload, %d threads, %.1f s (FP64 CPU restatement of the "
                                               "NTRTsim/Bullet-2.82 path; Bullet is absent so the reference cannot be built)"
                                               % (sample_env, H * reps, cores, secs)}
-        print(json.dumps(line))
+        emit(line)
     w.close()
     if dist is not None:
         dist.destroy_process_group()
