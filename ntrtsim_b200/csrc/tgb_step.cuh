@@ -213,6 +213,144 @@ __device__ __forceinline__ void pgsSharedRows(T* ct, int rowStride, int nc, int 
 #undef CTG
 }
 
+/* Contact solve of a body with two or more contact points (a rod lying on a rim line, a compound body): rare next to the
+   single-point case, so it lives out of line -- the step loop's hot instructions stay within the instruction cache.
+   ct = row 0 of this body, rowStride = words between consecutive rows of one body. */
+template <typename T> struct ContactSolveOut { V3<T> dLin, dAng, push, turn; };
+template <typename T, bool kFast>
+__device__ __noinline__ ContactSolveOut<T> solveContactsGeneral(T* ct, int rowStride, int nc, int iterations, bool anyPen, V3<T> gn, T invMass,
+                                                                 T mu) {
+    V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
+    if (nc <= 2) {
+        /* one or two contact points (a rod touching with one rim point or lying on a rim line): the rows are read into
+           registers once and all iterations run there; same operations in the same order as the general path below */
+        T rxn[2][3], angN[2][3], invDiagN[2], rhsN[2], rhsPen[2], lamN[2], lamPush[2];
+        T tt[2][3], rxt[2][3], angT[2][3], invDiagT[2], rhsT[2], lamT[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int cc = c < nc ? c : 0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                rxn[c][j] = ct[(cc) * rowStride + (CT_RXN + j)]; angN[c][j] = ct[(cc) * rowStride + (CT_ANGN + j)];
+                tt[c][j] = ct[(cc) * rowStride + (CT_T + j)]; rxt[c][j] = ct[(cc) * rowStride + (CT_RXT + j)]; angT[c][j] = ct[(cc) * rowStride + (CT_ANGT + j)];
+            }
+            invDiagN[c] = ct[(cc) * rowStride + (CT_INVDIAGN)]; rhsN[c] = ct[(cc) * rowStride + (CT_RHSN)]; rhsPen[c] = ct[(cc) * rowStride + (CT_RHSPEN)];
+            invDiagT[c] = ct[(cc) * rowStride + (CT_INVDIAGT)]; rhsT[c] = ct[(cc) * rowStride + (CT_RHST)];
+            lamN[c] = T(0); lamPush[c] = T(0); lamT[c] = T(0);
+        }
+        if (anyPen)
+            for (int it = 0; it < iterations; ++it) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c >= nc || rhsPen[c] == T(0)) continue;
+                    T delta = rhsPen[c];
+                    const T dv = gn.dot(push) + (rxn[c][0] * turn.x + rxn[c][1] * turn.y + rxn[c][2] * turn.z);
+                    delta -= dv * invDiagN[c];
+                    const T sum = lamPush[c] + delta;
+                    if (sum < T(0)) { delta = -lamPush[c]; lamPush[c] = T(0); }
+                    else lamPush[c] = sum;
+                    push += gn * (invMass * delta);
+                    turn += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
+                }
+            }
+        if (kFast && TGB_MATRIX_PGS) {
+            /* Single precision: the same projected Gauss-Seidel in matrix form.  With A[r][s] = J_r M^-1 J_s^T over the
+               rows (N0, N1, T0, T1) the relative velocity change dv_r of every row is carried along and updated by one
+               multiply-add per applied impulse, instead of being re-formed from the body's velocity change by two dot
+               products: the dependent chain per row drops from ~10 to ~5 operations and the instruction count by ~4x.
+               Equal in exact arithmetic to the sequential-impulse form (kept for double precision, the parity path). */
+            T jl[4][3], ja[4][3], bl[4][3], ba[4][3], A[4][4], dv[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                jl[c][0] = gn.x; jl[c][1] = gn.y; jl[c][2] = gn.z;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    ja[c][j] = rxn[c][j]; ba[c][j] = angN[c][j]; bl[c][j] = jl[c][j] * invMass;
+                    jl[2 + c][j] = tt[c][j]; ja[2 + c][j] = rxt[c][j]; ba[2 + c][j] = angT[c][j]; bl[2 + c][j] = tt[c][j] * invMass;
+                }
+            }
+            const bool two = nc > 1;
+            /* A is symmetric: the upper triangle is computed (only the rows of the first contact when there is one) */
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = r; q < 4; ++q) {
+                    T v = T(0);
+                    if (two || ((r & 1) == 0 && (q & 1) == 0))
+                        v = (jl[r][0] * bl[q][0] + jl[r][1] * bl[q][1] + jl[r][2] * bl[q][2]) +
+                            (ja[r][0] * ba[q][0] + ja[r][1] * ba[q][1] + ja[r][2] * ba[q][2]);
+                    A[r][q] = v;
+                    A[q][r] = v;
+                }
+            for (int it = 0; it < iterations; ++it) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c == 1 && !two) continue;
+                    T delta = rhsN[c] - dv[c] * invDiagN[c];
+                    const T sum = lamN[c] + delta;
+                    if (sum < T(0)) { delta = -lamN[c]; lamN[c] = T(0); }
+                    else lamN[c] = sum;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) dv[r] += A[r][c] * delta;
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if ((c == 1 && !two) || !(lamN[c] > T(0))) continue;
+                    const T lo = -mu * lamN[c], hi = mu * lamN[c];
+                    T delta = rhsT[c] - dv[2 + c] * invDiagT[c];
+                    const T sum = lamT[c] + delta;
+                    if (sum < lo) { delta = lo - lamT[c]; lamT[c] = lo; }
+                    else if (sum > hi) { delta = hi - lamT[c]; lamT[c] = hi; }
+                    else lamT[c] = sum;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) dv[r] += A[r][2 + c] * delta;
+                }
+            }
+            /* the body's velocity change from the accumulated impulses */
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c == 1 && !two) continue;
+                dLin += V3<T>(bl[c][0], bl[c][1], bl[c][2]) * lamN[c] + V3<T>(bl[2 + c][0], bl[2 + c][1], bl[2 + c][2]) * lamT[c];
+                dAng += V3<T>(ba[c][0], ba[c][1], ba[c][2]) * lamN[c] + V3<T>(ba[2 + c][0], ba[2 + c][1], ba[2 + c][2]) * lamT[c];
+            }
+        } else
+        for (int it = 0; it < iterations; ++it) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c >= nc) continue;
+                T delta = rhsN[c];
+                const T dv = gn.dot(dLin) + (rxn[c][0] * dAng.x + rxn[c][1] * dAng.y + rxn[c][2] * dAng.z);
+                delta -= dv * invDiagN[c];
+                const T sum = lamN[c] + delta;
+                if (sum < T(0)) { delta = -lamN[c]; lamN[c] = T(0); }
+                else lamN[c] = sum;
+                dLin += gn * (invMass * delta);
+                dAng += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (c >= nc || !(lamN[c] > T(0))) continue;
+                const V3<T> t(tt[c][0], tt[c][1], tt[c][2]);
+                const T lo = -mu * lamN[c], hi = mu * lamN[c];
+                T delta = rhsT[c];
+                const T dv = t.dot(dLin) + (rxt[c][0] * dAng.x + rxt[c][1] * dAng.y + rxt[c][2] * dAng.z);
+                delta -= dv * invDiagT[c];
+                const T sum = lamT[c] + delta;
+                if (sum < lo) { delta = lo - lamT[c]; lamT[c] = lo; }
+                else if (sum > hi) { delta = hi - lamT[c]; lamT[c] = hi; }
+                else lamT[c] = sum;
+                dLin += t * (invMass * delta);
+                dAng += V3<T>(angT[c][0], angT[c][1], angT[c][2]) * delta;
+            }
+        }
+    } else {
+        pgsSharedRows<T>(ct, rowStride, nc, iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
+    }
+    ContactSolveOut<T> o;
+    o.dLin = dLin; o.dAng = dAng; o.push = push; o.turn = turn;
+    return o;
+}
+
 /* One cable's working set in registers (the cable phase keeps several of these in flight per lane). */
 template <typename T>
 struct CableRegs {
@@ -786,130 +924,9 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 }
                 dLin = bn * lamN + bt * lamT;
                 dAng = angN * lamN + angT * lamT;
-            } else if (nc > 0 && nc <= 2) {
-                /* one or two contact points (a rod touching with one rim point or lying on a rim line): the rows are read into
-                   registers once and all iterations run there; same operations in the same order as the general path below */
-                T rxn[2][3], angN[2][3], invDiagN[2], rhsN[2], rhsPen[2], lamN[2], lamPush[2];
-                T tt[2][3], rxt[2][3], angT[2][3], invDiagT[2], rhsT[2], lamT[2];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int cc = c < nc ? c : 0;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        rxn[c][j] = CT(cc, CT_RXN + j); angN[c][j] = CT(cc, CT_ANGN + j);
-                        tt[c][j] = CT(cc, CT_T + j); rxt[c][j] = CT(cc, CT_RXT + j); angT[c][j] = CT(cc, CT_ANGT + j);
-                    }
-                    invDiagN[c] = CT(cc, CT_INVDIAGN); rhsN[c] = CT(cc, CT_RHSN); rhsPen[c] = CT(cc, CT_RHSPEN);
-                    invDiagT[c] = CT(cc, CT_INVDIAGT); rhsT[c] = CT(cc, CT_RHST);
-                    lamN[c] = T(0); lamPush[c] = T(0); lamT[c] = T(0);
-                }
-                if (anyPen)
-                    for (int it = 0; it < a.iterations; ++it) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            if (c >= nc || rhsPen[c] == T(0)) continue;
-                            T delta = rhsPen[c];
-                            const T dv = gn.dot(push) + (rxn[c][0] * turn.x + rxn[c][1] * turn.y + rxn[c][2] * turn.z);
-                            delta -= dv * invDiagN[c];
-                            const T sum = lamPush[c] + delta;
-                            if (sum < T(0)) { delta = -lamPush[c]; lamPush[c] = T(0); }
-                            else lamPush[c] = sum;
-                            push += gn * (invMass * delta);
-                            turn += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
-                        }
-                    }
-                if (kFast && TGB_MATRIX_PGS) {
-                    /* Single precision: the same projected Gauss-Seidel in matrix form.  With A[r][s] = J_r M^-1 J_s^T over the
-                       rows (N0, N1, T0, T1) the relative velocity change dv_r of every row is carried along and updated by one
-                       multiply-add per applied impulse, instead of being re-formed from the body's velocity change by two dot
-                       products: the dependent chain per row drops from ~10 to ~5 operations and the instruction count by ~4x.
-                       Equal in exact arithmetic to the sequential-impulse form (kept for double precision, the parity path). */
-                    T jl[4][3], ja[4][3], bl[4][3], ba[4][3], A[4][4], dv[4] = {T(0), T(0), T(0), T(0)};
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        jl[c][0] = gn.x; jl[c][1] = gn.y; jl[c][2] = gn.z;
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) {
-                            ja[c][j] = rxn[c][j]; ba[c][j] = angN[c][j]; bl[c][j] = jl[c][j] * invMass;
-                            jl[2 + c][j] = tt[c][j]; ja[2 + c][j] = rxt[c][j]; ba[2 + c][j] = angT[c][j]; bl[2 + c][j] = tt[c][j] * invMass;
-                        }
-                    }
-                    const bool two = nc > 1;
-                    /* A is symmetric: the upper triangle is computed (only the rows of the first contact when there is one) */
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int q = r; q < 4; ++q) {
-                            T v = T(0);
-                            if (two || ((r & 1) == 0 && (q & 1) == 0))
-                                v = (jl[r][0] * bl[q][0] + jl[r][1] * bl[q][1] + jl[r][2] * bl[q][2]) +
-                                    (ja[r][0] * ba[q][0] + ja[r][1] * ba[q][1] + ja[r][2] * ba[q][2]);
-                            A[r][q] = v;
-                            A[q][r] = v;
-                        }
-                    for (int it = 0; it < a.iterations; ++it) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            if (c == 1 && !two) continue;
-                            T delta = rhsN[c] - dv[c] * invDiagN[c];
-                            const T sum = lamN[c] + delta;
-                            if (sum < T(0)) { delta = -lamN[c]; lamN[c] = T(0); }
-                            else lamN[c] = sum;
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) dv[r] += A[r][c] * delta;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            if ((c == 1 && !two) || !(lamN[c] > T(0))) continue;
-                            const T lo = -mu * lamN[c], hi = mu * lamN[c];
-                            T delta = rhsT[c] - dv[2 + c] * invDiagT[c];
-                            const T sum = lamT[c] + delta;
-                            if (sum < lo) { delta = lo - lamT[c]; lamT[c] = lo; }
-                            else if (sum > hi) { delta = hi - lamT[c]; lamT[c] = hi; }
-                            else lamT[c] = sum;
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) dv[r] += A[r][2 + c] * delta;
-                        }
-                    }
-                    /* the body's velocity change from the accumulated impulses */
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        if (c == 1 && !two) continue;
-                        dLin += V3<T>(bl[c][0], bl[c][1], bl[c][2]) * lamN[c] + V3<T>(bl[2 + c][0], bl[2 + c][1], bl[2 + c][2]) * lamT[c];
-                        dAng += V3<T>(ba[c][0], ba[c][1], ba[c][2]) * lamN[c] + V3<T>(ba[2 + c][0], ba[2 + c][1], ba[2 + c][2]) * lamT[c];
-                    }
-                } else
-                for (int it = 0; it < a.iterations; ++it) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        if (c >= nc) continue;
-                        T delta = rhsN[c];
-                        const T dv = gn.dot(dLin) + (rxn[c][0] * dAng.x + rxn[c][1] * dAng.y + rxn[c][2] * dAng.z);
-                        delta -= dv * invDiagN[c];
-                        const T sum = lamN[c] + delta;
-                        if (sum < T(0)) { delta = -lamN[c]; lamN[c] = T(0); }
-                        else lamN[c] = sum;
-                        dLin += gn * (invMass * delta);
-                        dAng += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * delta;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        if (c >= nc || !(lamN[c] > T(0))) continue;
-                        const V3<T> t(tt[c][0], tt[c][1], tt[c][2]);
-                        const T lo = -mu * lamN[c], hi = mu * lamN[c];
-                        T delta = rhsT[c];
-                        const T dv = t.dot(dLin) + (rxt[c][0] * dAng.x + rxt[c][1] * dAng.y + rxt[c][2] * dAng.z);
-                        delta -= dv * invDiagT[c];
-                        const T sum = lamT[c] + delta;
-                        if (sum < lo) { delta = lo - lamT[c]; lamT[c] = lo; }
-                        else if (sum > hi) { delta = hi - lamT[c]; lamT[c] = hi; }
-                        else lamT[c] = sum;
-                        dLin += t * (invMass * delta);
-                        dAng += V3<T>(angT[c][0], angT[c][1], angT[c][2]) * delta;
-                    }
-                }
             } else if (nc > 0) {
-                pgsSharedRows<T>(sCt + bidx * TGB_NCT, R * TGB_NCT, nc, a.iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
+                const ContactSolveOut<T> o = solveContactsGeneral<T, kFast>(sCt + bidx * TGB_NCT, R * TGB_NCT, nc, a.iterations, anyPen, gn, invMass, mu);
+                dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
             }
 
             /* ---- write back, split-impulse correction, integrateTransforms ---- */
