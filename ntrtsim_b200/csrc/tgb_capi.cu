@@ -778,7 +778,8 @@ tgb_status tgb_rollout_host(tgb_world* w, const double* rod_state_in, const doub
     /* Environments are independent, so a large batch is cut into chunks that run on their own streams: the host-to-device copy
        and packing of one chunk, the steps of another and the device-to-host copy of a third overlap (TGB_ROLLOUT_CHUNKS=1..4
        overrides the choice for batches of at least 1024 environments). */
-    int chunks = n >= 16384 ? (int)tgb_world::kPipe : 1; /* below that the copies are a few percent of the steps: one launch */
+    /* measured on B200, SUPERball, 1000 steps per call: 4096 envs 8.79e8 / 8.93e8 / 8.62e8 env-steps/s for 1 / 2 / 4 chunks */
+    int chunks = n >= 16384 ? (int)tgb_world::kPipe : n >= 4096 ? 2 : 1;
     {
         const char* envChunks = std::getenv("TGB_ROLLOUT_CHUNKS");
         if (envChunks && n >= 1024) chunks = std::max(1, std::min((int)tgb_world::kPipe, std::atoi(envChunks)));
