@@ -95,13 +95,21 @@ typedef struct {
     int32_t reserved;
 } tgb_body_desc;
 
-/* One collision primitive of a body: flat-ended cylinder along its local Y (tgRodInfo.cpp:105-106). */
+typedef enum {
+    TGB_SHAPE_CYLINDER = 0, /* btCylinderShape: flat-ended cylinder along its local Y (tgRodInfo.cpp:105-106) */
+    TGB_SHAPE_SPHERE = 1    /* btSphereShape (tgSphereInfo.cpp:100-115): a point with collision margin = radius; set
+                               half_length = margin = radius */
+} tgb_shape_kind;
+
+/* One collision primitive of a body. */
 typedef struct {
     double radius;
     double half_length;
-    double margin;         /* Bullet setSafeMargin: min(0.04, 0.1*min(radius, half_length)) */
+    double margin;         /* cylinder: Bullet setSafeMargin, min(0.04, 0.1*min(radius, half_length)); sphere: the radius */
     double pos[3];         /* child transform in the body frame */
     double quat[4];
+    int32_t kind;          /* tgb_shape_kind */
+    int32_t reserved;
 } tgb_shape_desc;
 
 typedef enum {

@@ -216,6 +216,7 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         const double wx = q * xs, wy = q * ys, wz = q * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
         const double m[9] = {1.0 - (yy + zz), xy - wz, xz + wy, xy + wz, 1.0 - (xx + zz), yz - wx, xz - wy, yz + wx, 1.0 - (xx + yy)};
         for (int k = 0; k < 9; ++k) st[(SF_ROT0 + k) * S + s] = (T)m[k];
+        st[SF_KIND * S + s] = (T)d.kind;
     }
     for (int c = 0; c < C; ++c) {
         const tgb_cable_desc& d = w->cables[c];
@@ -382,6 +383,10 @@ tgb_status tgb_add_model_flat(tgb_world* w, const tgb_body_desc* bodies, int32_t
         if (c.actuator < TGB_ACT_PASSIVE || c.actuator > TGB_ACT_KINEMATIC) return fail(TGB_ERR_INVALID_ARGUMENT, "unknown actuator kind");
         if (!(c.rest_length > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "Pretension causes string to shorten past rest length!");
     }
+    for (int i = 0; i < n_shapes; ++i) {
+        if (shapes[i].kind != TGB_SHAPE_CYLINDER && shapes[i].kind != TGB_SHAPE_SPHERE) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_model_flat: unknown shape kind");
+        if (shapes[i].radius < 0.0 || shapes[i].half_length < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "Negative radius");
+    }
     for (int i = 0; i < n_shapes; ++i) w->shapes.push_back(shapes[i]);
     for (int i = 0; i < n_bodies; ++i) {
         tgb_body_desc b = bodies[i];
@@ -473,10 +478,12 @@ tgb_status tgb_finalize(tgb_world* w) {
     TGB_CUDA(cudaMalloc(&w->d_scores, (size_t)n * 2 * sizeof(float)));
     TGB_CUDA(cudaMemset(w->d_scores, 0, (size_t)n * 2 * sizeof(float)));
 
-    /* the step kernel must fit its shared memory */
+    /* the step kernel must fit its shared memory: a CTA holds threads / lanes environments, so a model with many collision
+       shapes per body (contact rows) gets more lanes per environment until a CTA fits */
     {
         tgb_step_args a = stepArgs(w, 1e-3, 1);
         a.ctrl_stride = std::max(w->C, TGB_ESCAPE_PARAMS);
+        while (w->ops->step_smem(a, w->lanes, w->threads) > 227 * 1024 && w->lanes < 32 && !w->lanesOverride) w->lanes *= 2;
         const size_t smem = w->ops->step_smem(a, w->lanes, w->threads);
         if (smem > 227 * 1024) return fail(TGB_ERR_UNSUPPORTED, "tgb_finalize: model too large for one CTA's shared memory");
     }

@@ -400,6 +400,7 @@ template <typename T>
 struct ShapeConst {
     T radius, halfLen, margin;
     V3<T> spos, r0, r1; /* position, columns 0 and 1 of the rotation */
+    bool sphere;        /* a point with margin = radius: one candidate contact point instead of eight rim points */
 };
 
 /* Controller classes a kernel is compiled for (the controller kind inside a class is a warp-uniform run-time switch):
@@ -728,6 +729,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         sc.spos = V3<T>(M.shape(SF_POSX, si), M.shape(SF_POSY, si), M.shape(SF_POSZ, si));
         sc.r0 = V3<T>(M.shape(SF_ROT0 + 0, si), M.shape(SF_ROT0 + 3, si), M.shape(SF_ROT0 + 6, si));
         sc.r1 = V3<T>(M.shape(SF_ROT0 + 1, si), M.shape(SF_ROT0 + 4, si), M.shape(SF_ROT0 + 7, si));
+        sc.sphere = M.shape(SF_KIND, si) != T(0);
         return sc;
     };
     const ShapeConst<T> shape0 = loadShape(shapeCount > 0 ? shapeBegin : 0);
@@ -821,6 +823,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                             if (!(hk > skipAbove)) candidates |= 1u << (e * 4 + k);
                         }
                     }
+                    if (sc.sphere) candidates &= 1u; /* all eight candidates coincide with the centre */
                     int count = 0;
                     while (candidates != 0 && count < 4) {
                         const int slot = __ffs(candidates) - 1;

@@ -9,7 +9,7 @@ from . import _capi as capi
 from .world import FlatModel
 
 EXAMPLES = ("3_prism", "3_prism_noground", "SUPERball", "SUPERball_flat", "Escape", "Escape_c3", "tsTestRig_basic",
-            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3")
+            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3", "TetraSpineStatic_hf")
 
 
 def build_example(name):

@@ -286,6 +286,64 @@ tgModel* tgRodInfo::createModel(tgWorldB200Impl& world) {
     return new tgRod(&world, body, world.bodies().at(body).mass, getTags(), getLength());
 }
 
+/* ---- sphere at a node ------------------------------------------------------------------------------------ */
+tgSphereInfo::tgSphereInfo(const tgSphere::Config& config) : m_config(config) {}
+tgSphereInfo::tgSphereInfo(const tgSphere::Config& config, const tgTags& tags, const tgNode& node)
+    : tgRigidInfo(tags + node.getTags()), m_node(node), m_config(config) {}
+tgRigidInfo* tgSphereInfo::createRigidInfo(const tgNode& node, const tgTagSearch& search) const {
+    if (!search.matches(node.getTags())) return 0;
+    return new tgSphereInfo(m_config, getTags(), node);
+}
+double tgSphereInfo::getMass() const {
+    /* tgSphereInfo.cpp:117-123 */
+    const double radius = m_config.radius;
+    const double volume = 4.0 / 3.0 * M_PI * radius * radius * radius;
+    return volume * m_config.density;
+}
+btTransform tgSphereInfo::getTransform() const {
+    /* tgSphereInfo.h: identity rotation at the node */
+    btTransform t;
+    t.setIdentity();
+    t.setOrigin(m_node);
+    return t;
+}
+/* tgSphereInfo.cpp:133-163: the surface point toward the destination */
+btVector3 tgSphereInfo::getConnectionPoint(const btVector3& referencePoint, const btVector3& destinationPoint, double) const {
+    if (referencePoint == destinationPoint) throw std::invalid_argument("Destination point is the reference point.");
+    const btVector3 refToDest = (destinationPoint - referencePoint).normalize();
+    return m_node + refToDest * m_config.radius;
+}
+void tgSphereInfo::appendShapes(const btVector3& bodyOrigin, std::vector<tgb_shape_desc>& out) const {
+    tgb_shape_desc s = tgb_shape_desc();
+    s.kind = TGB_SHAPE_SPHERE;
+    s.radius = m_config.radius;
+    s.half_length = m_config.radius; /* btSphereShape: a point with collision margin = radius */
+    s.margin = m_config.radius;
+    const btVector3 o = m_node - bodyOrigin;
+    s.pos[0] = o.x(); s.pos[1] = o.y(); s.pos[2] = o.z();
+    s.quat[3] = 1.0;
+    out.push_back(s);
+}
+tgb_body_desc tgSphereInfo::describeBody(std::vector<tgb_shape_desc>& shapes) const {
+    tgb_body_desc b = tgb_body_desc();
+    fillCommonBody(b, getMass(), getTransform());
+    appendShapes(m_node, shapes);
+    if (b.mass != 0.0) {
+        /* btSphereShape::calculateLocalInertia: 0.4 m r^2 on every axis */
+        const double e = 0.4 * b.mass * m_config.radius * m_config.radius;
+        b.inertia[0] = e; b.inertia[1] = e; b.inertia[2] = e;
+    }
+    b.friction = m_config.friction;
+    b.rolling_friction = m_config.rollFriction;
+    b.restitution = m_config.restitution;
+    return b;
+}
+tgModel* tgSphereInfo::createModel(tgWorldB200Impl& world) {
+    initRigidBody(world);
+    const int body = getBodyIndex();
+    return new tgSphere(&world, body, world.bodies().at(body).mass, getTags());
+}
+
 double tgCompoundRigidInfo::getMass() const {
     double m = 0.0;
     for (std::size_t i = 0; i < m_rigids.size(); ++i) m += m_rigids[i]->getMass();
@@ -351,17 +409,15 @@ tgb_body_desc tgCompoundRigidInfo::describeBody(std::vector<tgb_shape_desc>& sha
         b.inertia[1] = b.mass / 12.0 * (lx * lx + lz * lz);
         b.inertia[2] = b.mass / 12.0 * (lx * lx + ly * ly);
     }
-    /* material: every member of a shipped compound shares one tgRod::Config; take the first rod's */
-    for (std::size_t i = 0; i < m_rigids.size(); ++i) {
-        const tgRodInfo* r = dynamic_cast<const tgRodInfo*>(m_rigids[i]);
-        if (r) {
-            b.friction = r->getConfig().friction;
-            b.rolling_friction = r->getConfig().rollFriction;
-            b.restitution = r->getConfig().restitution;
-            break;
-        }
-    }
+    getMaterial(b.friction, b.rolling_friction, b.restitution);
     return b;
+}
+/* Every leaf's initRigidBody sets friction / rolling friction / restitution on the shared btRigidBody after creating it
+   (tgRodInfo.cpp:72-79, tgSphereInfo.cpp:71-78), in the order the structure info initialises its rigids, so the last member's
+   Config is the one that stays. */
+void tgCompoundRigidInfo::getMaterial(double& friction, double& rollFriction, double& restitution) const {
+    friction = 0.5; rollFriction = 0.0; restitution = 0.0;
+    if (!m_rigids.empty()) m_rigids.back()->getMaterial(friction, rollFriction, restitution);
 }
 tgModel* tgCompoundRigidInfo::createModel(tgWorldB200Impl&) { return 0; } /* leaves create their own tgRod wrappers */
 
@@ -494,6 +550,17 @@ void tgStructureInfo::addRigidsAndConnectors() {
     const std::vector<tgBuildSpec::RigidAgent>& ra = m_buildSpec.getRigidAgents();
     const std::vector<tgBuildSpec::ConnectorAgent>& ca = m_buildSpec.getConnectorAgents();
     const tgPairs& pairs = m_structure.getPairs();
+    /* nodes first (tgStructureInfo.cpp:128-135): a tagged node becomes a rigid if a rigid agent answers for nodes */
+    const tgNodes& nodes = m_structure.getNodes();
+    for (std::size_t n = 0; n < nodes.size(); ++n) {
+        tgRigidInfo* rigid = 0;
+        for (int i = (int)ra.size() - 1; i >= 0 && !rigid; --i) {
+            tgTagSearch s = ra[i].tagSearch;
+            s.remove(getTags());
+            rigid = ra[i].infoFactory->createRigidInfo(nodes[n], s);
+        }
+        if (rigid) m_rigids.push_back(rigid);
+    }
     for (std::size_t p = 0; p < pairs.size(); ++p) {
         tgRigidInfo* rigid = 0;
         for (int i = (int)ra.size() - 1; i >= 0 && !rigid; --i) {

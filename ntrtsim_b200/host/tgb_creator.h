@@ -110,8 +110,12 @@ public:
     tgRigidInfo() : m_group(0), m_body(-1) {}
     explicit tgRigidInfo(const tgTags& tags) : tgTaggable(tags), m_group(0), m_body(-1) {}
     virtual ~tgRigidInfo() {}
-    /* factory side: NULL when the search does not match the pair's tags */
-    virtual tgRigidInfo* createRigidInfo(const tgPair& pair, const tgTagSearch& search) const = 0;
+    /* factory side: NULL when the search does not match the pair's / node's tags (tgRigidInfo.h:105-117: a factory answers for
+       pairs or for nodes, the other default is NULL) */
+    virtual tgRigidInfo* createRigidInfo(const tgPair& pair, const tgTagSearch& search) const { (void)pair; (void)search; return 0; }
+    virtual tgRigidInfo* createRigidInfo(const tgNode& node, const tgTagSearch& search) const { (void)node; (void)search; return 0; }
+    /* friction, rolling friction, restitution of this rigid's Config */
+    virtual void getMaterial(double& friction, double& rollFriction, double& restitution) const = 0;
     virtual double getMass() const = 0;
     virtual btVector3 getCenterOfMass() const = 0;
     virtual btTransform getTransform() const = 0;
@@ -139,6 +143,9 @@ public:
     explicit tgRodInfo(const tgRod::Config& config);
     tgRodInfo(const tgRod::Config& config, const tgTags& tags, const tgPair& pair);
     tgRigidInfo* createRigidInfo(const tgPair& pair, const tgTagSearch& search) const;
+    void getMaterial(double& friction, double& rollFriction, double& restitution) const {
+        friction = m_config.friction; rollFriction = m_config.rollFriction; restitution = m_config.restitution;
+    }
     const btVector3& getFrom() const { return m_pair.getFrom(); }
     const btVector3& getTo() const { return m_pair.getTo(); }
     double getLength() const { return getFrom().distance(getTo()); }
@@ -157,12 +164,37 @@ private:
     tgRod::Config m_config;
 };
 
+/* A sphere at a tagged node (tgSphereInfo.cpp:45-200). */
+class tgSphereInfo : public tgRigidInfo {
+public:
+    explicit tgSphereInfo(const tgSphere::Config& config);
+    tgSphereInfo(const tgSphere::Config& config, const tgTags& tags, const tgNode& node);
+    tgRigidInfo* createRigidInfo(const tgNode& node, const tgTagSearch& search) const;
+    void getMaterial(double& friction, double& rollFriction, double& restitution) const {
+        friction = m_config.friction; rollFriction = m_config.rollFriction; restitution = m_config.restitution;
+    }
+    const btVector3& getNode() const { return m_node; }
+    double getMass() const;
+    btVector3 getCenterOfMass() const { return m_node; }
+    btTransform getTransform() const;
+    bool containsNode(const btVector3& node) const { return m_node == node; }
+    std::vector<btVector3> getContainedNodes() const { return std::vector<btVector3>(1, m_node); }
+    btVector3 getConnectionPoint(const btVector3& referencePoint, const btVector3& destinationPoint, double rotation) const;
+    void appendShapes(const btVector3& bodyOrigin, std::vector<tgb_shape_desc>& out) const;
+    tgb_body_desc describeBody(std::vector<tgb_shape_desc>& shapes) const;
+    tgModel* createModel(tgWorldB200Impl& world);
+    const tgSphere::Config& getConfig() const { return m_config; }
+private:
+    tgNode m_node;
+    tgSphere::Config m_config;
+};
+
 /* Several rigids that share nodes, welded into one body (tgCompoundRigidInfo.cpp:47-112). */
 class tgCompoundRigidInfo : public tgRigidInfo {
 public:
     tgCompoundRigidInfo() {}
     void addRigid(tgRigidInfo& r) { m_rigids.push_back(&r); }
-    tgRigidInfo* createRigidInfo(const tgPair&, const tgTagSearch&) const { return 0; }
+    void getMaterial(double& friction, double& rollFriction, double& restitution) const;
     double getMass() const;
     btVector3 getCenterOfMass() const;
     btTransform getTransform() const;

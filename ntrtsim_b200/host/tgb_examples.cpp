@@ -271,6 +271,94 @@ void TetraSpineLearningModel::teardown() {
     m_allSegments.clear();
 }
 
+/* ---- hardware-faithful tetrahedral spine (rods + point masses) ----------------------------------------------------- */
+TetraSpineStaticModel_hf::TetraSpineStaticModel_hf(std::size_t segments) : m_segments(segments) {}
+void TetraSpineStaticModel_hf::setup(tgWorld& world) {
+    const double edge = 38;
+    const double height = round5(std::sqrt(3.0) / 2 * edge);
+    tgStructure tetra;
+    /* addNodes, TetraSpineStaticModel_hf.cpp:62-90 */
+    tetra.addNode(-edge / 2.0, 0, 0, "base");                               /* right */
+    tetra.addNode(edge / 2.0, 0, 0, "base");                                /* left */
+    tetra.addNode(0, height, 0, "base");                                    /* top */
+    tetra.addNode(0, edge / 2.0 * std::tan(M_PI / 6.0), 25.0, "tip");       /* front */
+    {
+        const tgNodes& old = tetra.getNodes();
+        tgNode nn1((old[0] + old[2]) / 2.0);                                /* 4 mid */
+        nn1.addTags(std::string("PCB"));
+        tgNode nn2((old[1] + old[2]) / 2.0);                                /* 5 mid */
+        nn2.addTags(std::string("PCB"));
+        tetra.addNode(nn1);
+        tetra.addNode(nn2);
+    }
+    /* addPairs, :92-102 */
+    tetra.addPair(0, 1, "back bottom rod");
+    tetra.addPair(0, 4, "back rightBottom rod");
+    tetra.addPair(4, 2, "back rightTop rod");
+    tetra.addPair(0, 3, "front right rod");
+    tetra.addPair(1, 5, "back leftBottom rod");
+    tetra.addPair(5, 2, "back leftTop rod");
+    tetra.addPair(1, 3, "front left rod");
+    tetra.addPair(2, 3, "front top rod");
+    tetra.move(btVector3(0.0, 2.0, 100.0));
+
+    tgStructure snake;
+    const btVector3 offset(0, 0, -23.0);
+    for (std::size_t i = 0; i < m_segments; ++i) {
+        tgStructure* const t = new tgStructure(tetra);
+        t->addTags(numbered("segment num", (int)i)); /* num0, num1, num2 select the point-mass builders below */
+        t->move((btScalar)(i + 1) * offset);
+        snake.addChild(t);
+    }
+    const std::vector<tgStructure*>& children = snake.getChildren();
+    for (std::size_t i = 1; i < children.size(); ++i) {
+        const tgNodes& n0 = children[i - 1]->getNodes();
+        const tgNodes& n1 = children[i]->getNodes();
+        snake.addPair(n0[0], n1[0], numbered("outer right muscle seg", (int)i));
+        snake.addPair(n0[1], n1[1], numbered("outer left muscle seg", (int)i));
+        snake.addPair(n0[2], n1[2], numbered("outer top muscle seg", (int)i));
+        snake.addPair(n0[0], n1[3], numbered("inner right muscle seg", (int)i));
+        snake.addPair(n0[1], n1[3], numbered("inner left muscle seg", (int)i));
+        snake.addPair(n0[2], n1[3], numbered("inner top muscle seg", (int)i));
+    }
+
+    /* :262-313 */
+    const double radius = 0.635 / 2.0;
+    const double density = 0.0201 / (std::pow(radius, 2) * M_PI * edge);
+    const double friction = 0.15;
+    const tgRod::Config rodConfig(radius, density, friction);
+    tgBuildSpec spec;
+    spec.addBuilder("rod", new tgRodInfo(rodConfig));
+    const double sphereVolume = 1000.0 * 4.0 / 3.0 * M_PI * std::pow(radius, 3); /* 1000 so that the numbers below are grams */
+    struct { const char* tags; double grams; } masses[9] = {{"num0 base", 140.0}, {"num1 base", 180.0}, {"num2 base", 100.0},
+                                                            {"num0 tip", 40.0},   {"num1 tip", 120.0},  {"num2 tip", 120.0},
+                                                            {"PCB num0", 70.0},   {"PCB num1", 70.0},   {"PCB num2", 95.0}};
+    for (int i = 0; i < 9; ++i) spec.addBuilder(masses[i].tags, new tgSphereInfo(tgSphere::Config(radius, masses[i].grams / sphereVolume, friction)));
+    tgSpringCableActuator::Config muscleConfig(229.16, 20, 2000.0, true, 5000, 7.0, 1.0, 1.0);
+    tgSpringCableActuator::Config muscleConfig2(229.16, 20, 700.0, true, 5000, 7.0, 1.0, 1.0);
+    spec.addBuilder("top muscle", new tgBasicActuatorInfo(muscleConfig));
+    spec.addBuilder("left muscle", new tgBasicActuatorInfo(muscleConfig2));
+    spec.addBuilder("right muscle", new tgBasicActuatorInfo(muscleConfig2));
+    tgStructureInfo structureInfo(snake, spec);
+    structureInfo.buildInto(*this, world);
+
+    m_allMuscles = find<tgSpringCableActuator>(std::string("muscle"));
+    m_allSegments = find<tgModel>(std::string("segment"));
+    notifySetup();
+    tgModel::setup(world);
+}
+void TetraSpineStaticModel_hf::step(double dt) {
+    if (dt < 0.0) throw std::invalid_argument("dt is not positive");
+    notifyStep(dt);
+    tgModel::step(dt);
+}
+void TetraSpineStaticModel_hf::teardown() {
+    notifyTeardown();
+    tgModel::teardown();
+    m_allMuscles.clear();
+    m_allSegments.clear();
+}
+
 /* ---- tetrahedral complex spine, kinematic actuators ----------------------------------------------------------------- */
 FlemonsSpineModelLearning::FlemonsSpineModelLearning(std::size_t segments) : m_segments(segments) {}
 void FlemonsSpineModelLearning::setup(tgWorld& world) {

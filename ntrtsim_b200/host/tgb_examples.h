@@ -98,6 +98,26 @@ private:
     std::vector<tgModel*> m_allSegments;
 };
 
+/* Hardware-faithful 3-segment tetrahedral spine of the ICRA 2015 hardware comparison: every segment is a compound of 8 rods and 6
+   point masses (spheres at the tagged nodes: corners, tip, PCBs), 6 tgBasicActuator cables between consecutive segments with
+   pretension 2000 (top) / 700 (left, right) (src/examples/IROS_2015/TetraSpineStatic/TetraSpineStaticModel_hf.cpp:51-330,
+   test_integration/ICRA2015Tests/ICRA2015_test.cpp:77-101) */
+class TetraSpineStaticModel_hf : public tgSubject<TetraSpineStaticModel_hf>, public tgModel {
+public:
+    explicit TetraSpineStaticModel_hf(std::size_t segments);
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt);
+    virtual void teardown();
+    virtual bool stepsOnHost() const { return numObservers() > 0; }
+    const std::vector<tgSpringCableActuator*>& getAllMuscles() const { return m_allMuscles; }
+    std::size_t getSegments() const { return m_segments; }
+    const std::vector<tgModel*>& getAllSegments() const { return m_allSegments; }
+private:
+    std::size_t m_segments;
+    std::vector<tgSpringCableActuator*> m_allMuscles;
+    std::vector<tgModel*> m_allSegments;
+};
+
 /* ---- CPG + impedance control of the spine examples, flattened for tgb_set_cpg_controller ------------------------- */
 /* BaseSpineCPGControl::Config (BaseSpineCPGControl.h:60-77) with its defaults */
 struct tgbSpineControlConfig {

@@ -375,6 +375,20 @@ private:
     double m_length;
 };
 
+/* A sphere at a node (src/core/tgSphere.h:52-88, tgSphere.cpp:36-72) */
+class tgSphere : public tgBaseRigid {
+public:
+    struct Config {
+        Config(double r = 0.5, double d = 1.0, double f = 1.0, double rf = 0.0, double res = 0.2);
+        const double radius;
+        const double density;
+        const double friction;
+        const double rollFriction;
+        const double restitution;
+    };
+    tgSphere(tgWorldB200Impl* world, int body, double mass, const tgTags& tags);
+};
+
 /* ------------------------------------------------------------------------------------------------
  * Cables and actuators  (src/core/tgSpringCableActuator.h:51-266, tgBasicActuator.h, tgKinematicActuator.h)
  * ---------------------------------------------------------------------------------------------- */

@@ -58,6 +58,11 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
             e->world = new tgWorld(tgWorld::Config(981));
             e->dt = 0.001;
             e->model = new TetraSpineLearningModel(3);
+        } else if (name == "TetraSpineStatic_hf") {
+            /* ICRA2015_test.cpp:77-101: tgWorld(Config(981)) with the default box ground, dt = 1e-3, 3 segments */
+            e->world = new tgWorld(tgWorld::Config(981));
+            e->dt = 0.001;
+            e->model = new TetraSpineStaticModel_hf(3);
         } else if (name == "FlemonsSpine" || name == "FlemonsSpine3") {
             /* WorldConf_Spines_test.cpp:85-108 / AppFlemonsSpineLearning: tgWorld(Config(981)), default box ground, dt = 1e-3, 12
                segments ("FlemonsSpine3": the same vertebrae, 3 segments, for small tests) */

@@ -115,6 +115,7 @@ struct M3 {
 static V3 vecMat(const V3& v, const M3& m) { return V3(m.col(0).dot(v), m.col(1).dot(v), m.col(2).dot(v)); }
 
 struct Shape {
+    int kind; /* tgb_shape_kind */
     double radius, halfLen, margin;
     V3 pos;
     M3 rot;
@@ -514,9 +515,11 @@ struct tgo_world {
                 else u = R.col(0);
                 V3 w = a.cross(u);
                 int count = 0;
-                for (int e = 0; e < 2 && count < 4; ++e) {
+                /* btSphereShape = a point with margin radius (rc = hc = 0): one contact point */
+                const int nEnds = s.kind == TGB_SHAPE_SPHERE ? 1 : 2, nDirs = s.kind == TGB_SHAPE_SPHERE ? 1 : 4;
+                for (int e = 0; e < nEnds && count < 4; ++e) {
                     V3 ce = c + a * (e == 0 ? -hc : hc);
-                    for (int k = 0; k < 4 && count < 4; ++k) {
+                    for (int k = 0; k < nDirs && count < 4; ++k) {
                         V3 dir = (k == 0) ? u : (k == 1) ? w : (k == 2) ? -u : -w;
                         V3 pc = ce + dir * rc;
                         double dist = n.dot(pc) - ground.offset - s.margin;
@@ -712,6 +715,7 @@ int tgo_add_model_flat(tgo_world* w, const tgb_body_desc* bodies, int n_bodies, 
     const int shape0 = (int)w->shapes.size();
     for (int i = 0; i < n_shapes; ++i) {
         Shape s;
+        s.kind = shapes[i].kind;
         s.radius = shapes[i].radius; s.halfLen = shapes[i].half_length; s.margin = shapes[i].margin;
         s.pos = V3(shapes[i].pos[0], shapes[i].pos[1], shapes[i].pos[2]);
         s.rot = M3::fromQuat(Q4(shapes[i].quat[0], shapes[i].quat[1], shapes[i].quat[2], shapes[i].quat[3]));
