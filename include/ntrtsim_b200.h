@@ -148,8 +148,20 @@ typedef enum {
        tgCPGActuatorControl::onStep (tgCPGActuatorControl.cpp:79-100) -> tgImpedanceController::control
        (controllers/tgImpedanceController.cpp:151-185) -> tgTensionController::control (tgTensionController.cpp:90-114);
        or, with tgb_cpg_desc.cable_control = 1, tgCPGCableControl::onStep -> tgPIDController -> tgKinematicActuator */
-    TGB_CTRL_CPG_IMPEDANCE = 5
+    TGB_CTRL_CPG_IMPEDANCE = 5,
+    /* SerializedSpineControl of the ICRA 2015 hardware comparison (src/examples/IROS_2015/TetraSpineStatic/SerializedSpineControl.cpp:
+       174-205 applyImpedanceControlGeneric, :262-371 onStep): every step, every tgBasicActuator cable runs
+       tgImpedanceController::controlTension(actuator, dt, control length, offset tension, target velocity) with the target velocity
+       offset_speed + cpg_amplitude * sin(simTime * cpg_frequency + phase), simTime advancing in jumps of 1 / update_frequency; then a
+       load is applied to up to three bodies at markers (btRigidBody::applyForce, consumed by the next world step): a force vector
+       scaled by a ramp (0 before t0, linear up to t1, constant to t2, linear down to t3).  params per env, TGB_SPINE_HEADER + 5 C:
+         [0..3]  offset_speed, cpg_amplitude, cpg_frequency, update_frequency
+         [4..7]  t0, t1, t2, t3 of the load ramp       [8..10] load vector at full scale      [11] number of loaded bodies (<= 3)
+         [12..26] per loaded body: body index, marker offset in the body frame (3), factor on the load vector
+         then per cable: offset tension, length stiffness, velocity stiffness, control length, phase */
+    TGB_CTRL_SERIALIZED_SPINE = 6
 } tgb_controller_kind;
+#define TGB_SPINE_HEADER 27
 
 /* Static part of a CPG + impedance controller: one CPG node per cable (node i drives cable i, the order of
    tgCPGActuatorControl::assignNodeNumber), the coupling lists of tgCPGActuatorControl::setConnectivity in CSR form, and the
@@ -195,6 +207,12 @@ typedef struct tgb_world tgb_world;
 int          tgb_abi_version(void);
 const char*  tgb_last_error(void);
 int          tgb_device_count(void);
+
+/* tgSpringCableActuator::Config::hist = true for every cable (tgSpringCableActuator.h:104-108, tgBasicActuator.cpp:227-241): keep the
+   running maximum of the tension logged after every step -- the quantity BaseSpineModelLearning::getStringMaxTensions reads from the
+   tension history (ICRA2015_test.cpp:119).  Enabling (or tgb_mark_episode_start) clears it.  out: [env_count][n_cables] doubles. */
+tgb_status tgb_track_max_tension(tgb_world* w, int32_t enable);
+tgb_status tgb_get_max_tension(tgb_world* w, int32_t env_begin, int32_t env_count, double* out);
 
 tgb_status tgb_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, tgb_world** out);
 tgb_status tgb_destroy(tgb_world* w);

@@ -6,4 +6,4 @@ host/   C++ mirror of the reference's tgStructure / tgBuildSpec / tgModel / tgSi
 from . import _capi as capi  # noqa: F401
 from .world import BatchedWorld, FlatModel  # noqa: F401
 from .examples import (build_example, escape_transform_actions, tree_counts, EXAMPLES, CpgController, tetraspine_cpg,  # noqa: F401
-                       tetraspine_param_rows, flemons_cpg, flemons_param_rows)
+                       tetraspine_param_rows, flemons_cpg, flemons_param_rows, serialized_spine_params)

@@ -11,7 +11,8 @@ TGB_OK, TGB_ERR_INVALID_ARGUMENT, TGB_ERR_STATE, TGB_ERR_CUDA, TGB_ERR_UNSUPPORT
 TGB_F32, TGB_F64 = 0, 1
 TGB_GROUND_EMPTY, TGB_GROUND_BOX, TGB_GROUND_PLANE = 0, 1, 2
 TGB_ACT_PASSIVE, TGB_ACT_BASIC, TGB_ACT_KINEMATIC = 0, 1, 2
-TGB_CTRL_NONE, TGB_CTRL_SETPOINT, TGB_CTRL_TENSION, TGB_CTRL_ESCAPE_SINE, TGB_CTRL_TORQUE, TGB_CTRL_CPG_IMPEDANCE = range(6)
+TGB_CTRL_NONE, TGB_CTRL_SETPOINT, TGB_CTRL_TENSION, TGB_CTRL_ESCAPE_SINE, TGB_CTRL_TORQUE, TGB_CTRL_CPG_IMPEDANCE, TGB_CTRL_SERIALIZED_SPINE = range(7)
+TGB_SPINE_HEADER = 27
 TGB_ESCAPE_PARAMS = 33
 ROD_STATE_DOUBLES = 13
 CABLE_OBS_DOUBLES = 4
@@ -66,7 +67,7 @@ ABI_SYMBOLS = [
     "tgb_abi_version", "tgb_last_error", "tgb_device_count", "tgb_create", "tgb_destroy", "tgb_add_model_flat",
     "tgb_finalize", "tgb_set_cpg_controller", "tgb_get_cpg_state", "tgb_num_bodies", "tgb_num_cables", "tgb_num_envs", "tgb_set_rod_state", "tgb_get_rod_state",
     "tgb_set_cable_state", "tgb_get_cable_obs", "tgb_set_controller", "tgb_set_control_input", "tgb_step", "tgb_step_world", "tgb_step_models", "tgb_sync",
-    "tgb_rollout_host", "tgb_get_time", "tgb_get_status", "tgb_mark_episode_start", "tgb_get_scores",
+    "tgb_rollout_host", "tgb_track_max_tension", "tgb_get_max_tension", "tgb_get_time", "tgb_get_status", "tgb_mark_episode_start", "tgb_get_scores",
     "tgb_scores_device_ptr", "tgb_step_timed", "tgb_launch_count", "tgb_launch_geometry", "tgb_set_lanes_per_env",
     "tgb_set_block_threads", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
 ]
@@ -117,6 +118,8 @@ def load():
     lib.tgb_sync.argtypes = [_vp]
     lib.tgb_step_world.argtypes = [_vp, C.c_double]
     lib.tgb_step_models.argtypes = [_vp, C.c_double]
+    lib.tgb_track_max_tension.argtypes = [_vp, _i32]
+    lib.tgb_get_max_tension.argtypes = [_vp, _i32, _i32, _vp]
     lib.tgb_rollout_host.argtypes = [_vp, _vp, _vp, C.c_double, _i32, _vp, _vp]
     lib.tgb_get_time.argtypes = [_vp, _dp]
     lib.tgb_get_status.argtypes = [_vp, _i32, _i32, _vp]

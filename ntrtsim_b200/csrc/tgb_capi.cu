@@ -55,6 +55,7 @@ struct tgb_world {
     void* d_state = nullptr;
     double* d_frame = nullptr;
     double* d_ctrl = nullptr;
+    void* d_max_tension = nullptr; /* tgb_track_max_tension */
     double* d_sine = nullptr;   /* sine controller phase pairs, see tgb_step_args::sine_state */
     double* d_com0 = nullptr;
     int* d_status = nullptr;
@@ -116,6 +117,7 @@ struct tgb_world {
         if (d_frame) cudaFree(d_frame);
         if (d_ctrl) cudaFree(d_ctrl);
         if (d_sine) cudaFree(d_sine);
+        if (d_max_tension) cudaFree(d_max_tension);
         if (d_com0) cudaFree(d_com0);
         if (d_status) cudaFree(d_status);
         if (d_model_t) cudaFree(d_model_t);
@@ -246,6 +248,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     std::memset(&a, 0, sizeof(a));
     a.state = w->d_state; a.frame = w->d_frame; a.ctrl = w->ctrlKind != TGB_CTRL_NONE ? w->d_ctrl : nullptr; a.status = w->d_status;
     a.sine_state = w->ctrlKind == TGB_CTRL_ESCAPE_SINE ? w->d_sine : nullptr;
+    a.max_tension = w->d_max_tension;
     a.model_t = w->d_model_t; a.model_i = w->d_model_i;
     a.n_env = w->cfg.n_env; a.n_steps = nSteps;
     a.stats = w->d_stats;
@@ -598,11 +601,22 @@ tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, 
     case TGB_CTRL_SETPOINT: case TGB_CTRL_TORQUE: need = w->C; break;
     case TGB_CTRL_TENSION: need = 1; break;
     case TGB_CTRL_ESCAPE_SINE: need = TGB_ESCAPE_PARAMS; break;
+    case TGB_CTRL_SERIALIZED_SPINE: need = TGB_SPINE_HEADER + 5 * w->C; break;
     case TGB_CTRL_CPG_IMPEDANCE: return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: use tgb_set_cpg_controller for the CPG controller");
     default: return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: unknown controller kind");
     }
     if (kind == TGB_CTRL_NONE) { w->ctrlKind = TGB_CTRL_NONE; return TGB_OK; }
     if (!params || params_per_env != need) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: wrong parameter count for this controller");
+    if (kind == TGB_CTRL_SERIALIZED_SPINE) {
+        const int rows = broadcast ? 1 : env_count;
+        for (int e = 0; e < rows; ++e) {
+            const double* P = params + (size_t)e * need;
+            if (!(P[3] > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: update frequency must be positive");
+            if (P[11] < 0.0 || P[11] > 3.0) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: at most three loaded bodies");
+            for (int k = 0; k < (int)P[11]; ++k)
+                if (P[12 + 5 * k] < 0.0 || P[12 + 5 * k] >= (double)w->R) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: loaded body out of range");
+        }
+    }
     const int n = w->cfg.n_env;
     if (w->ctrlKind != kind) {
         /* one controller kind per world: switching kinds needs parameters for every environment */
@@ -871,7 +885,36 @@ tgb_status tgb_mark_episode_start(tgb_world* w) {
     TGB_NEED_FINAL(w);
     TGB_CUDA(w->ops->com(w->ioArgs(0, w->cfg.n_env), 0, nullptr, nullptr, w->stream));
     TGB_CUDA(cudaMemsetAsync(w->d_status, 0, (size_t)w->cfg.n_env * sizeof(int), w->stream));
+    if (w->d_max_tension) TGB_CUDA(cudaMemsetAsync(w->d_max_tension, 0, (size_t)w->cfg.n_env * std::max(1, w->C) * w->scalarBytes, w->stream));
     TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_track_max_tension(tgb_world* w, int32_t enable) {
+    TGB_NEED_FINAL(w);
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    if (!enable) {
+        if (w->d_max_tension) { cudaFree(w->d_max_tension); w->d_max_tension = nullptr; }
+        return TGB_OK;
+    }
+    const size_t bytes = (size_t)w->cfg.n_env * std::max(1, w->C) * w->scalarBytes;
+    if (!w->d_max_tension) TGB_CUDA(cudaMalloc(&w->d_max_tension, bytes));
+    TGB_CUDA(cudaMemset(w->d_max_tension, 0, bytes));
+    return TGB_OK;
+}
+
+tgb_status tgb_get_max_tension(tgb_world* w, int32_t env_begin, int32_t env_count, double* out) {
+    TGB_NEED_FINAL(w);
+    if (!out || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_max_tension: bad range or NULL buffer");
+    if (!w->d_max_tension) return fail(TGB_ERR_STATE, "tgb_get_max_tension: tension history is off (tgb_track_max_tension)");
+    if (env_count == 0 || w->C == 0) return TGB_OK;
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    const size_t n = (size_t)env_count * w->C;
+    std::vector<unsigned char> tmp(n * w->scalarBytes);
+    TGB_CUDA(cudaMemcpy(tmp.data(), (const unsigned char*)w->d_max_tension + (size_t)env_begin * w->C * w->scalarBytes, tmp.size(),
+                        cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i)
+        out[i] = w->scalarBytes == 4 ? (double)reinterpret_cast<const float*>(tmp.data())[i] : reinterpret_cast<const double*>(tmp.data())[i];
     return TGB_OK;
 }
 

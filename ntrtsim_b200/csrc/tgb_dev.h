@@ -73,6 +73,7 @@ struct tgb_step_args {
     int* status;          /* [n_env] */
     const void* model_t;  /* packed T fields */
     const int* model_i;   /* packed int fields */
+    void* max_tension;    /* T[n_env][C] running maximum of the logged tension (tgb_track_max_tension), or NULL */
     unsigned long long* stats; /* instrumentation variant only (-DTGB_STATS, tools/), else unused */
     int n_env, n_steps;   /* a launch covers environments [env_begin, n_env) */
     int env_begin;

@@ -749,8 +749,31 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         /* =============================== world step (tgSimulation.cpp:205) =============================== */
         if (dynamic && doWorld) {
             /* applyGravity + solver-body external impulses */
+            V3<T> totalForce(T(0), gfy, T(0)), totalTorque(T(0), T(0), T(0));
+            if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) {
+                /* the load SerializedSpineControl::onStep applied after the previous step (SerializedSpineControl.cpp:336-370):
+                   btRigidBody::applyForce(force, marker relative position) adds to the total force and torque of this step */
+                const double t = ctrlTime;
+                double scale = 0.0;
+                if (t > sCtrl[4] && t < sCtrl[5]) scale = (t - sCtrl[4]) / (sCtrl[5] - sCtrl[4]);
+                else if (t >= sCtrl[5] && t < sCtrl[6]) scale = 1.0;
+                else if (t >= sCtrl[6] && t < sCtrl[7]) scale = (sCtrl[7] - t) / (sCtrl[7] - sCtrl[6]);
+                const int nLoaded = (int)sCtrl[11];
+                for (int k = 0; k < nLoaded; ++k) {
+                    const double* m = sCtrl + 12 + 5 * k;
+                    if ((int)m[0] != lane) continue;
+                    const V3<T> f((T)((sCtrl[8] * scale) * m[4]), (T)((sCtrl[9] * scale) * m[4]), (T)((sCtrl[10] * scale) * m[4]));
+                    const V3<T> rel = b.B * V3<T>((T)m[1], (T)m[2], (T)m[3]); /* abstractMarker::getRelativePosition */
+                    totalForce += f;
+                    totalTorque += rel.cross(f);
+                }
+            }
             V3<T> extLin(T(0), (gfy * invMass) * dt, T(0));
             V3<T> extAng(T(0), T(0), T(0));
+            if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) {
+                extLin = (totalForce * invMass) * dt;
+                extAng = b.Iinv.tmul(totalTorque) * dt;
+            }
             if (gyro) {
                 /* btRigidBody::computeGyroscopicForce, explicit, clamped at maxGyroscopicForce */
                 if (kFast) {
@@ -975,6 +998,11 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         /* =============================== models step (tgSimulation.cpp:208-211) =============================== */
         if (!doModels) continue; /* warp-uniform: a world-half-only launch (host observers run between the halves) */
         if (sineOn) ctrlTime += a.dt; /* EscapeController::m_totalTime */
+        if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) {
+            /* SerializedSpineControl::onStep, SerializedSpineControl.cpp:264-278: simTime advances in jumps of 1 / updateFrequency */
+            frameSpare += a.dt;
+            if (frameSpare >= 1.0 / sCtrl[3]) { ctrlTime += frameSpare; frameSpare = 0.0; }
+        }
         bool cpgCableControl = false;
         double cpgCableDt = 0.0;
         if (cpgOn) {
@@ -1079,6 +1107,30 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 #pragma unroll
                 for (int u = 0; u < CU; ++u)
                     if (cr[u].actuator == TGB_ACT_KINEMATIC) cr[u].desiredTorque = (T)sCtrl[cr[u].c];
+            } else if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) {
+#pragma unroll
+                for (int u = 0; u < CU; ++u) {
+                    CableRegs<T>& q = cr[u];
+                    if (q.actuator == TGB_ACT_BASIC) {
+                        /* SerializedSpineControl::applyImpedanceControlGeneric, SerializedSpineControl.cpp:174-205 */
+                        const double* g = sCtrl + TGB_SPINE_HEADER + 5 * q.c;
+                        const T cycle = sinPhase(ctrlTime * sCtrl[2] + g[4], T(0));
+                        const T target = (T)sCtrl[0] + cycle * (T)sCtrl[1];
+                        /* tgImpedanceController::controlTension(tgBasicActuator&, ...), tgImpedanceController.cpp:163-185 */
+                        const T vel = q.motorVel; /* velocity slot of a basic actuator = the cable's m_velocity */
+                        T setTension = (T)g[0] + (T)g[1] * (q.L - (T)g[3]) + (T)g[2] * (vel - target);
+                        setTension = setTension > T(0) ? setTension : T(0);
+                        /* static tgTensionController::control(sca, dt, setPoint), tgTensionController.cpp:90-114 */
+                        T tension = (q.L - q.rest) * q.k;
+                        tension = tension < T(0) ? T(0) : tension;
+                        const T delta = setTension - tension;
+                        const T diff = delta / q.k;
+                        T newLength = q.rest - diff;
+                        newLength = newLength < T(0.1) ? T(0.1) : newLength;
+                        q.pref = newLength;
+                        q.moveMotors(dt);
+                    }
+                }
             } else if (simpleOn && ctrlKind == TGB_CTRL_TENSION) {
                 const T setPoint = (T)sCtrl[0];
 #pragma unroll
@@ -1235,6 +1287,13 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
                 } else {
                     sJ[c * 3 + 0] = J.x; sJ[c * 3 + 1] = J.y; sJ[c * 3 + 2] = J.z;
                 }
+                if (a.max_tension != nullptr && live) {
+                    /* logHistory with hist = true: the tension after this cable's step; only the running maximum is kept */
+                    T tensionNow = (q.L - q.rest) * q.k;
+                    tensionNow = tensionNow < T(0) ? T(0) : tensionNow;
+                    T* mx = reinterpret_cast<T*>(a.max_tension) + (size_t)env * C + c;
+                    if (tensionNow > *mx) *mx = tensionNow;
+                }
 #if TGB_VEC_CS
                 T cs[TGB_NCS];
                 cs[CS_REST] = q.rest; cs[CS_PREV] = q.prev; cs[CS_PREF] = q.pref;
@@ -1356,6 +1415,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             f[FR_V] = Vx; f[FR_V + 1] = Vy; f[FR_V + 2] = Vz;
             f[FR_CTRLTIME] = ctrlTime;
             if (sineRecurrence && doModels) f[FR_SPARE] = 1.0;
+            if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) f[FR_SPARE] = frameSpare;
         }
         if (sineRecurrence && doModels) {
             double* gsine = a.sine_state + (size_t)env * 48;

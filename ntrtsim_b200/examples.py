@@ -168,3 +168,53 @@ def tetraspine_param_rows(node_actions, edge_actions):
         if used != ea.shape[1]:
             raise ValueError("scaleEdgeActions consumed %d of %d edge actions" % (used, ea.shape[1]))
     return rows
+
+
+# resources/src/ICRA2015/static/controlVars.json of the reference, the file SerializedSpineControl::Config reads
+# (SerializedSpineControl.cpp:51-163); values only, keyed like the file
+ICRA2015_STATIC_CONTROL_VARS = {
+    "inside_imp_ten": 0.0, "inside_imp_pos": 100.0, "inside_imp_vel": 100.0,
+    "outside_imp_ten": 1000.0, "outside_imp_pos": 100.0, "outside_imp_vel": 100.0,
+    "top_imp_ten": 1200.0, "top_imp_pos": 500.0, "top_imp_vel": 150.0,
+    "in_top_tens": (2800.0, 1000.0), "in_left_tens": (1500.0, 1000.0), "in_right_tens": (1800.0, 800.0),
+    "out_top_tens": (1500.0, 600.0), "out_left_tens": (1100.0, 800.0), "out_right_tens": (1000.0, 400.0),
+    "in_top_length": (19.0, 18.0), "in_left_length": (21.5, 22.5), "in_right_length": (21.5, 22.5),
+    "out_top_length": (18.5, 19.8), "out_left_length": (19.2, 18.8), "out_right_length": (19.3, 19.2),
+    "offset_speed": 0.0, "cpg_amplitude": 0.0, "cpg_frequency": 2.51, "bodyWaves": 0.5,
+    "top_offset": 0.0, "left_offset": 0.0, "right_offset": 0.0, "updateFrequency": 20.0,
+}
+
+
+def serialized_spine_params(model, cfg=None):
+    """The TGB_CTRL_SERIALIZED_SPINE parameter row of SerializedSpineControl on TetraSpineStaticModel_hf
+    (src/examples/IROS_2015/TetraSpineStatic/SerializedSpineControl.cpp:174-205,262-371): per-cable impedance gains / offset tension /
+    control length by muscle group (cables are created per segment pair in the order outer right, outer left, outer top, inner right,
+    inner left, inner top: TetraSpineStaticModel_hf.cpp:123-142), and the 2.3 kg load pulled on the front tip between simTime 30 and
+    45 with 0.45 / 0.55 of it held back at the other two tips (markers 1, 2 and 5: TetraSpineStaticModel_hf.cpp:160-205)."""
+    import math
+    c = dict(ICRA2015_STATIC_CONTROL_VARS if cfg is None else cfg)
+    C, R = model.n_cables, model.n_bodies
+    segments = R
+    row = np.zeros(capi.TGB_SPINE_HEADER + 5 * C)
+    row[0:4] = [c["offset_speed"], c["cpg_amplitude"], c["cpg_frequency"], c["updateFrequency"]]
+    row[4:8] = [30.0, 35.0, 40.0, 45.0]
+    row[8:11] = [0.0, 0.0, 2.3 * 981.0]
+    row[11] = 3
+    # the tip node of segment s: (0, edge / 2 * tan(pi / 6), 25) moved by (0, 2, 100) + (s + 1) * (0, 0, -23)
+    edge = 38.0
+    for k, (body, factor) in enumerate(((0, 1.0), (1, -1.0 / 2.0 * 0.9), (2, -1.0 / 2.0 * 1.1))):
+        tip = np.array([0.0, edge / 2.0 * math.tan(math.pi / 6.0) + 2.0, 25.0 + 100.0 - 23.0 * (body + 1)])
+        local = tip - np.array(model.bodies[body].pos)          # compound bodies start with identity rotation
+        row[12 + 5 * k: 12 + 5 * k + 5] = [body, local[0], local[1], local[2], factor]
+    groups = ["out_right", "out_left", "out_top", "in_right", "in_left", "in_top"]
+    gains = {"out_right": ("outside", 2), "out_left": ("outside", 1), "out_top": ("top", 0),
+             "in_right": ("inside", 2), "in_left": ("inside", 1), "in_top": ("top", 0)}
+    offsets = [c["top_offset"], c["left_offset"], c["right_offset"]]
+    for cable in range(C):
+        pair, g = divmod(cable, 6)          # pair = index of the string inside its group (stringList[i])
+        name = groups[g]
+        ctl, phase = gains[name]
+        row[capi.TGB_SPINE_HEADER + 5 * cable: capi.TGB_SPINE_HEADER + 5 * cable + 5] = [
+            c[name + "_tens"][pair], c[ctl + "_imp_pos"], c[ctl + "_imp_vel"], c[name + "_length"][pair],
+            2 * c["bodyWaves"] * math.pi * pair / segments + offsets[phase]]
+    return row

@@ -110,6 +110,16 @@ class BatchedWorld(object):
         capi.check(self._lib.tgb_set_cpg_controller(self._h, C.byref(desc.desc), _ptr(params), params.shape[-1], env_begin, n,
                                                     1 if broadcast else 0))
 
+    def track_max_tension(self, enable=True):
+        """hist = true for every cable: keep the running maximum of the tension history (BaseSpineModelLearning::getStringMaxTensions)"""
+        capi.check(self._lib.tgb_track_max_tension(self._h, 1 if enable else 0))
+
+    def max_tension(self, env_begin=0, env_count=None):
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.zeros((n, self.C))
+        capi.check(self._lib.tgb_get_max_tension(self._h, env_begin, n, _ptr(out)))
+        return out
+
     def get_cpg_state(self, env_begin=0, env_count=None):
         n = self.n_env - env_begin if env_count is None else env_count
         out = np.empty((n, self.C, 3))

@@ -42,6 +42,8 @@ def load():
     lib.tgo_set_cpg_controller.argtypes = [vp, vp, vp, i]
     lib.tgo_get_status.argtypes = [vp]
     lib.tgo_get_cpg_state.argtypes = [vp, vp]
+    lib.tgo_track_max_tension.argtypes = [vp, i]
+    lib.tgo_get_max_tension.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -91,6 +93,14 @@ class OracleWorld(object):
     def set_controller(self, kind, params):
         params = np.ascontiguousarray(params, dtype=np.float64)
         self._lib.tgo_set_controller(self._h, kind, _p(params), params.size)
+
+    def track_max_tension(self, enable=True):
+        self._lib.tgo_track_max_tension(self._h, 1 if enable else 0)
+
+    def max_tension(self):
+        out = np.zeros(self.C)
+        self._lib.tgo_get_max_tension(self._h, _p(out))
+        return out
 
     def set_control_input(self, inputs, dt):
         inputs = np.ascontiguousarray(inputs, dtype=np.float64)

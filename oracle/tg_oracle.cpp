@@ -214,7 +214,10 @@ struct tgo_world {
     int ctrlKind = TGB_CTRL_NONE;
     std::vector<double> ctrlParams;
     double time = 0.0;     /* tgSimView-style accumulated time */
-    double ctrlTime = 0.0; /* EscapeController::m_totalTime */
+    double ctrlTime = 0.0; /* EscapeController::m_totalTime; SerializedSpineControl::simTime */
+    double spineUpdateTime = 0.0; /* SerializedSpineControl::updateTime */
+    bool trackMaxTension = false;
+    std::vector<double> maxTension; /* running maximum of the tension history (hist = true) */
     V3 episodeStartCom;
     int iterations = 10;
     int status = 0;
@@ -458,6 +461,51 @@ struct tgo_world {
             for (int i = 0; i < C; ++i) moveMotors(cables[i], dt); /* EscapeController.cpp:108-116 */
             break;
         }
+        case TGB_CTRL_SERIALIZED_SPINE: { /* SerializedSpineControl::onStep, SerializedSpineControl.cpp:262-371 */
+            const double* P = ctrlParams.data();
+            spineUpdateTime += dt;
+            if (spineUpdateTime >= 1.0 / P[3]) {
+                ctrlTime += spineUpdateTime;
+                spineUpdateTime = 0.0;
+            }
+            for (int i = 0; i < C; ++i) {
+                Cable& c = cables[i];
+                if (c.actuator != TGB_ACT_BASIC) continue;
+                const double* g = P + TGB_SPINE_HEADER + 5 * i;
+                /* applyImpedanceControlGeneric, :174-205 */
+                const double cycle = std::sin(ctrlTime * P[2] + g[4]);
+                const double target = P[0] + cycle * P[1];
+                /* tgImpedanceController::controlTension(tgBasicActuator&, ...), tgImpedanceController.cpp:163-185 */
+                const double actualLength = cableLength(c);
+                const double vel = c.velocity;
+                const double setTension = std::max(0.0, g[0] + g[1] * (actualLength - g[3]) + g[2] * (vel - target));
+                /* static tgTensionController::control(sca, dt, setPoint), tgTensionController.cpp:90-114 */
+                const double currentTension = cableTension(c);
+                const double delta = setTension - currentTension;
+                const double diff = delta / c.k;
+                double newLength = c.rest - diff;
+                newLength = newLength < 0.1 ? 0.1 : newLength;
+                setControlInput(c, newLength, dt);
+            }
+            /* the load, :336-370: btRigidBody::applyForce(force, marker relative position) accumulates total force and torque,
+               which the next world step turns into external impulses and clears */
+            const double t = ctrlTime;
+            double scale = 0.0;
+            if (t > P[4] && t < P[5]) scale = (t - P[4]) / (P[5] - P[4]);
+            else if (t >= P[5] && t < P[6]) scale = 1.0;
+            else if (t >= P[6] && t < P[7]) scale = (P[7] - t) / (P[7] - P[6]);
+            const V3 force(P[8] * scale, P[9] * scale, P[10] * scale);
+            const int nLoaded = (int)P[11];
+            for (int k = 0; k < nLoaded; ++k) {
+                const double* m = P + 12 + 5 * k;
+                Body& b = bodies[(int)m[0]];
+                const V3 f = force * m[4];
+                const V3 rel = b.basis * V3(m[1], m[2], m[3]); /* abstractMarker::getRelativePosition */
+                b.totalForce += f;
+                b.totalTorque += rel.cross(f);
+            }
+            break;
+        }
         case TGB_CTRL_CPG_IMPEDANCE: { /* BaseSpineCPGControl::onStep, BaseSpineCPGControl.cpp:253-279 */
             cpg.updateTime += dt;
             if (cpg.updateTime >= cpg.controlTime) {
@@ -486,6 +534,8 @@ struct tgo_world {
             } else {
                 cableForce(c, dt);
             }
+            /* logHistory (hist = true): the tension after the cable's step joins the history; only its maximum is kept */
+            if (trackMaxTension) maxTension[i] = std::max(maxTension[i], cableTension(c));
         }
     }
 
@@ -804,10 +854,19 @@ void tgo_get_cable_obs(const tgo_world* w, double* o) {
 }
 
 int tgo_set_controller(tgo_world* w, int kind, const double* params, int n_params) {
+    if (kind == TGB_CTRL_SERIALIZED_SPINE && n_params != TGB_SPINE_HEADER + 5 * (int)w->cables.size()) return TGB_ERR_INVALID_ARGUMENT;
     w->ctrlKind = kind;
     w->ctrlParams.assign(params, params + n_params);
     w->ctrlTime = 0.0;
+    w->spineUpdateTime = 0.0;
     return 0;
+}
+void tgo_track_max_tension(tgo_world* w, int enable) {
+    w->trackMaxTension = enable != 0;
+    w->maxTension.assign(w->cables.size(), 0.0);
+}
+void tgo_get_max_tension(const tgo_world* w, double* out) {
+    for (size_t i = 0; i < w->cables.size(); ++i) out[i] = i < w->maxTension.size() ? w->maxTension[i] : 0.0;
 }
 
 int tgo_set_control_input(tgo_world* w, const double* input, double dt) {

@@ -52,6 +52,8 @@ void tgo_set_cable_state(tgo_world* w, const double* rest_prev); /* [n_cables][2
 void tgo_get_cable_obs(const tgo_world* w, double* obs4);        /* [n_cables][4] */
 
 int  tgo_set_controller(tgo_world* w, int kind, const double* params, int n_params);
+void tgo_track_max_tension(tgo_world* w, int enable);
+void tgo_get_max_tension(const tgo_world* w, double* out);
 int  tgo_set_control_input(tgo_world* w, const double* input, double dt); /* [n_cables] */
 /* CPG + impedance controller of the learningSpines examples; params = one row as in tgb_set_cpg_controller */
 int  tgo_set_cpg_controller(tgo_world* w, const tgb_cpg_desc* desc, const double* params, int n_params);
