@@ -327,16 +327,47 @@ def main():
     barrier()
     t_wall0 = time.perf_counter()
     ms_kernel, ms_gather = [], []
-    for _ in range(args.steps):
-        flush_l2()
-        ms_kernel.append(w.step_timed(model.dt, H, 1)[0])
-        if dist is not None:
-            ms_gather.append(gather_scores())
+    if dist is None:
+        for _ in range(args.steps):
+            flush_l2()
+            ms_kernel.append(w.step_timed(model.dt, H, 1)[0])
+        total_ms = sum(ms_kernel)
+    else:
+        # N > 1: one device-side bracket around the K steps (L2 flushes included).  The all-gather of step k is issued
+        # asynchronously as soon as step k's scores exist and overlaps step k+1; it is waited for before its source buffer is
+        # rewritten (one step later) and, for the last step, before the bracket closes -- every collective completes inside
+        # the timed region.  Ranks therefore only have to stay within one step of each other instead of meeting after every step.
+        ws = torch.cuda.ExternalStream(w.stream_handle())
+        ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pending = None
+        ev_start.record(ws)
+        for k in range(args.steps):
+            flush.fill_(rank & 0xff)
+            fl = torch.cuda.Event()
+            fl.record()
+            ws.wait_event(fl)
+            ev_k0.record(ws)
+            w.step(model.dt, H)                       # asynchronous on the world's stream
+            ev_k1.record(ws)
+            if pending is not None:                   # gather k-1 has had the whole flush + launch to finish
+                pending.wait()
+                torch.cuda.current_stream().synchronize()
+            ptr, nbytes = w.scores_device_ptr()       # scores of step k (synchronises the world's stream)
+            ms_kernel.append(ev_k0.elapsed_time(ev_k1))
+
+            class _Wrap(object):
+                __cuda_array_interface__ = {"shape": (n_env * 2,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+            local = torch.as_tensor(_Wrap(), device="cuda")
+            pending = dist.all_gather_into_tensor(scores_all, local, async_op=True)
+        pending.wait()
+        ev_end.record()
+        ev_end.synchronize()
+        total_ms = ev_start.elapsed_time(ev_end)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
     launches = w.launch_count() - launches0
-    total_ms = sum(ms_kernel) + sum(ms_gather)
     status_bad = int((w.status() & 1).sum())
 
     # ---- end to end through the C ABI with pinned host buffers ---------------------------------------------------
@@ -407,7 +438,8 @@ def main():
                          "note": "effective figure: env state stays on chip for the H fused steps, real DRAM traffic is ~1/H of it"},
         }
         if world_size > 1:
-            line["config"]["allgather_ms_per_step"] = float(np.mean(ms_gather))
+            line["config"]["allgather"] = "scores all-gather of step k issued asynchronously, overlapping step k+1, completed inside the timed bracket"
+            line["config"]["timing"] = "one CUDA-event bracket around the K steps incl. the L2 flushes; max over ranks"
         if world_size == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             # calibrate, then size the sample (whole batch, H x reps sim steps) for ~10-15 s of CPU work

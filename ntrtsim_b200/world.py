@@ -190,6 +190,12 @@ class BatchedWorld(object):
         capi.check(self._lib.tgb_scores_device_ptr(self._h, C.byref(p), C.byref(nbytes)))
         return p.value, nbytes.value
 
+    def stream_handle(self):
+        """the CUDA stream (cudaStream_t as an integer) all work of this world is issued on"""
+        p = C.c_void_p()
+        capi.check(self._lib.tgb_stream_handle(self._h, C.byref(p)))
+        return p.value or 0
+
     def launch_count(self):
         n = C.c_int64()
         capi.check(self._lib.tgb_launch_count(self._h, C.byref(n)))
