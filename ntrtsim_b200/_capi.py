@@ -165,6 +165,8 @@ def load_host():
     h.tgh_run_example.restype = C.c_int
     h.tgh_run_example_stepwise.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp]
     h.tgh_run_example_stepwise.restype = C.c_int
+    h.tgh_run_example_logged.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_double, C.c_int, C.c_char_p, C.c_int]
+    h.tgh_run_example_logged.restype = C.c_int
     h.tgh_tetraspine_cpg.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _vp, _vp, _vp, _vp]
     h.tgh_tetraspine_param_row.argtypes = [_vp, _vp, C.c_int, _vp]
     h.tgh_flemons_cpg.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _vp, _vp, _vp, _vp]

@@ -3,6 +3,7 @@
  * Reference behaviour followed is cited per function (paths relative to the NTRTsim tree).
  */
 #include "tgb_host.h"
+#include "tgb_sensors.h"
 
 #include <algorithm>
 #include <cmath>
@@ -354,6 +355,10 @@ std::string tgModel::toString(std::string prefix) const {
     for (std::size_t i = 0; i < m_children.size(); ++i) os << "\n" << m_children[i]->toString(prefix + "  ");
     return os.str();
 }
+std::vector<tgSenseable*> tgModel::getSenseableDescendants() const {
+    const std::vector<tgModel*> d = getDescendants();
+    return std::vector<tgSenseable*>(d.begin(), d.end());
+}
 std::vector<tgModel*> tgModel::getDescendants() const {
     std::vector<tgModel*> out;
     for (std::size_t i = 0; i < m_children.size(); ++i) {
@@ -514,6 +519,12 @@ tgSimulation::~tgSimulation() {
     teardown();
     m_view.releaseFromSimulation();
     for (std::size_t i = 0; i < m_models.size(); ++i) delete m_models[i];
+    for (std::size_t i = 0; i < m_dataManagers.size(); ++i) delete m_dataManagers[i];
+}
+void tgSimulation::addDataManager(tgDataManager* pDataManager) {
+    if (pDataManager == 0) throw std::invalid_argument("NULL pointer to tgDataManager");
+    pDataManager->setup();
+    m_dataManagers.push_back(pDataManager);
 }
 void tgSimulation::addModel(tgModel* pModel) {
     if (pModel == 0) throw std::invalid_argument("NULL pointer to tgModel");
@@ -541,7 +552,7 @@ bool tgSimulation::hasHostObservers() const {
 bool tgSimulation::hasHostStepCode() const {
     for (std::size_t i = 0; i < m_models.size(); ++i)
         if (m_models[i]->stepsOnHost()) return true;
-    return false;
+    return !m_dataManagers.empty(); /* loggers sample the state on the host after every step */
 }
 void tgSimulation::step(double dt) const {
     if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
@@ -553,6 +564,8 @@ void tgSimulation::step(double dt) const {
     /* ... then the cable forces of every actuator's step on the device. A cable force depends only on body poses and its own
        rest length, so evaluating all of them after all observers equals the reference's per-actuator interleaving. */
     m_view.world().b200().stepModels(dt);
+    /* data managers last (tgSimulation.cpp:213-216): loggers see the state after the complete step */
+    for (std::size_t i = 0; i < m_dataManagers.size(); ++i) m_dataManagers[i]->step(dt);
 }
 void tgSimulation::runFused(double dt, int steps) const {
     if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
@@ -562,9 +575,12 @@ void tgSimulation::run() const { m_view.run(); }
 void tgSimulation::run(int steps) const { m_view.run(steps); }
 void tgSimulation::teardown() {
     for (std::size_t i = 0; i < m_models.size(); ++i) m_models[i]->teardown();
+    for (std::size_t i = 0; i < m_dataManagers.size(); ++i) m_dataManagers[i]->teardown();
 }
 void tgSimulation::reset() {
     teardown();
     m_view.world().reset();
     for (std::size_t i = 0; i < m_models.size(); ++i) m_models[i]->setup(m_view.world());
+    /* after the models: the sensors are created from the rebuilt model tree (tgSimulation.cpp:147-156) */
+    for (std::size_t i = 0; i < m_dataManagers.size(); ++i) m_dataManagers[i]->setup();
 }

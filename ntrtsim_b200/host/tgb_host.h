@@ -279,7 +279,14 @@ private:
  * ---------------------------------------------------------------------------------------------- */
 class tgModelVisitor;
 
-class tgModel : public tgTaggable {
+/* Anything a sensor can be attached to (src/core/tgSenseable.h:41-66). */
+class tgSenseable {
+public:
+    virtual ~tgSenseable() {}
+    virtual std::vector<tgSenseable*> getSenseableDescendants() const { return std::vector<tgSenseable*>(); }
+};
+
+class tgModel : public tgTaggable, public tgSenseable {
 public:
     tgModel();
     explicit tgModel(const tgTags& tags);
@@ -294,6 +301,7 @@ public:
     void addChild(tgModel* pChild); /* takes ownership; NULL -> std::invalid_argument */
     virtual std::string toString(std::string prefix = "") const;
     std::vector<tgModel*> getDescendants() const;
+    virtual std::vector<tgSenseable*> getSenseableDescendants() const; /* tgModel.cpp:191-201 */
     const std::vector<tgModel*>& getChildren() const { return m_children; }
     template <typename T>
     std::vector<T*> find(const tgTagSearch& tagSearch) const {
@@ -507,6 +515,8 @@ protected:
     bool m_initialized;
 };
 
+class tgDataManager;
+
 class tgSimulation {
 public:
     explicit tgSimulation(tgSimView& view);
@@ -515,6 +525,8 @@ public:
     void run() const;
     void run(int steps) const;
     void addModel(tgModel* pModel); /* takes ownership; calls pModel->setup(world) */
+    /* takes ownership; calls setup(); stepped after the models in every step (tgSimulation.cpp:104-116,213-216) */
+    void addDataManager(tgDataManager* pDataManager);
     void reset();
     tgWorld& getWorld() const;
     /* True when any model-level or actuator-level host observer is attached (forces per-step host round trips). */
@@ -526,6 +538,7 @@ private:
     void teardown();
     tgSimView& m_view;
     std::vector<tgModel*> m_models;
+    std::vector<tgDataManager*> m_dataManagers;
 };
 
 #endif /* TGB_HOST_H */

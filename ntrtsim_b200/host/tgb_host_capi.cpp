@@ -5,6 +5,7 @@
  * apps: AppPrismModel.cpp:46-80, AppSUPERball.cpp:45-91, AppEscape.cpp:61-151, MotorTimestep_test.cpp:81-215.
  */
 #include "tgb_examples.h"
+#include "tgb_sensors.h"
 
 #include <cstring>
 #include <string>
@@ -149,6 +150,38 @@ int tgh_run_example_stepwise(const char* name, int n_env, int precision, int ste
         if (st == TGB_OK && cable_obs_out) st = tgb_get_cable_obs(w.handle(), 0, n_env, cable_obs_out);
         delete e;
         return st;
+    } catch (const std::invalid_argument& ex) {
+        g_error = ex.what();
+        delete e;
+        return TGB_ERR_INVALID_ARGUMENT;
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        delete e;
+        return TGB_ERR_RUNTIME;
+    }
+}
+
+/* An example app with a tgDataLogger2 attached the way the reference apps do it (e.g. src/examples/3_prism/AppPrismModel.cpp with
+   tgDataLogger2 + tgRodSensorInfo + tgSpringCableActuatorSensorInfo): `steps` steps through tgSimulation::run, one CSV line per
+   sample of environment `env`.  The name of the written file is returned through file_name_out. */
+int tgh_run_example_logged(const char* name, int n_env, int precision, int steps, const char* log_prefix, double time_interval, int env,
+                           char* file_name_out, int file_name_cap) {
+    Example* e = 0;
+    try {
+        e = build(name ? name : "", n_env, precision);
+        if (!e) return TGB_ERR_INVALID_ARGUMENT;
+        tgDataLogger2* logger = new tgDataLogger2(log_prefix ? log_prefix : "", time_interval, env);
+        logger->addSenseable(e->model);
+        logger->addSensorInfo(new tgRodSensorInfo());
+        logger->addSensorInfo(new tgSpringCableActuatorSensorInfo());
+        e->sim->addDataManager(logger);
+        e->sim->run(steps);
+        if (file_name_out && file_name_cap > 0) {
+            std::strncpy(file_name_out, logger->getFileName().c_str(), (size_t)file_name_cap - 1);
+            file_name_out[file_name_cap - 1] = 0;
+        }
+        delete e;
+        return TGB_OK;
     } catch (const std::invalid_argument& ex) {
         g_error = ex.what();
         delete e;

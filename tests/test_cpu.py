@@ -272,3 +272,31 @@ def test_oracle_batch_rollout_matches_single():
         o.set_controller(capi.TGB_CTRL_ESCAPE_SINE, params[e])
         o.step(1e-3, 100)
         assert np.array_equal(o.get_rod_state(), ro[e]) and np.array_equal(o.get_cable_obs(), co[e])
+
+
+def test_data_logger_schema_and_errors(tmp_path):
+    """tgDataLogger2 + tgRodSensorInfo + tgSpringCableActuatorSensorInfo of the host API write the reference's CSV schema
+    (src/sensors/tgDataLogger2.cpp:107-170, tgRodSensor.cpp:73-119, tgSpringCableActuatorSensor.cpp:60-85): one line of free text, then
+    "time,<sensor index>_<type>(<tags>).<field>,..." -- checked without a device (zero steps), with the reference's exceptions."""
+    import ctypes as C
+    h = capi.load_host()
+    buf = C.create_string_buffer(512)
+    rc = h.tgh_run_example_logged(b"3_prism", 1, 0, 0, str(tmp_path / "prism").encode(), 0.0, 0, buf, 512)
+    assert rc == 0, h.tgh_last_error()
+    name = buf.value.decode()
+    assert re.match(r".*/prism_\d{8}_\d{6}\.txt$", name)
+    lines = open(name).read().split("\n")
+    assert re.match(r"tgDataLogger2 started logging at time \d{8}_\d{6}, with 12 sensors on 1 senseable objects\.$", lines[0])
+    cols = lines[1].split(",")
+    assert cols[0] == "time" and cols[-1] == ""               # every field ends with a comma
+    assert cols[1:8] == ["0_rod(rod).X", "0_rod(rod).Y", "0_rod(rod).Z", "0_rod(rod).Euler1", "0_rod(rod).Euler2", "0_rod(rod).Euler3",
+                         "0_rod(rod).mass"]
+    assert cols[22:25] == ["3_SCA(muscle).RestLen", "3_SCA(muscle).CurrLen", "3_SCA(muscle).Tension"]
+    assert len(cols) == 1 + 3 * 7 + 9 * 3 + 1
+    assert lines[2:] == [""]                                   # no samples before the first step
+    assert h.tgh_run_example_logged(b"3_prism", 1, 0, 0, b"", 0.0, 0, buf, 512) == capi.TGB_ERR_INVALID_ARGUMENT
+    assert b"File name cannot be the empty string" in h.tgh_last_error()
+    assert h.tgh_run_example_logged(b"3_prism", 1, 0, 0, str(tmp_path / "x").encode(), -1.0, 0, buf, 512) == capi.TGB_ERR_INVALID_ARGUMENT
+    assert b"Time interval must be nonnegative" in h.tgh_last_error()
+    assert h.tgh_run_example_logged(b"3_prism", 1, 0, 0, b"/nonexistent_dir/x", 0.0, 0, buf, 512) == capi.TGB_ERR_RUNTIME
+    assert b"Log file could not be opened" in h.tgh_last_error()

@@ -667,3 +667,31 @@ def test_icra2015_hardware_comparison(precision):
     # two outer cables are reached during the loaded phase, after 35 s): the maxima agree to 0.5 N
     print("oracle max tensions", np.round(o.max_tension()[:6] / 100.0, 2))
     assert np.abs(o.max_tension()[:6] / 100.0 - sim).max() < 0.5
+
+
+def test_data_logger_samples_match_the_device_state(tmp_path):
+    """tgDataLogger2 through tgSimulation::run on the device: one CSV line per step (time interval 0), the reference's default
+    stream formatting (6 significant digits); the last line equals the final state read through the C ABI, for a chosen environment."""
+    import ctypes as C
+    h = capi.load_host()
+    buf = C.create_string_buffer(512)
+    steps, n_env = 40, 3
+    rc = h.tgh_run_example_logged(b"3_prism", n_env, capi.TGB_F64, steps, str(tmp_path / "prism").encode(), 0.0, 2, buf, 512)
+    assert rc == 0, h.tgh_last_error()
+    lines = [ln for ln in open(buf.value.decode()).read().split("\n") if ln]
+    assert len(lines) == 2 + steps
+    n_cols = len(lines[1].split(","))
+    rows = np.array([[float(x) for x in ln.split(",")[:-1]] for ln in lines[2:]])
+    assert rows.shape == (steps, n_cols - 1)
+    assert np.allclose(rows[:, 0], 1e-3 * np.arange(1, steps + 1), rtol=1e-5)
+    model = nt.build_example("3_prism")
+    rods = np.empty((n_env, model.n_bodies, 13))
+    cab = np.empty((n_env, model.n_cables, 4))
+    assert h.tgh_run_example_stepwise(b"3_prism", n_env, capi.TGB_F64, steps, rods.ctypes.data_as(C.c_void_p), cab.ctypes.data_as(C.c_void_p)) == 0
+    last = rows[-1]
+    for b in range(model.n_bodies):
+        assert np.allclose(last[1 + 7 * b: 4 + 7 * b], rods[2, b, 0:3], rtol=2e-5, atol=1e-6)       # centre of mass
+        assert abs(last[7 + 7 * b] - model.bodies[b].mass) < 1e-5 * model.bodies[b].mass           # mass
+    for c in range(model.n_cables):
+        o = 1 + 7 * model.n_bodies + 3 * c
+        assert np.allclose(last[o: o + 3], cab[2, c, 0:3], rtol=2e-5, atol=1e-6)                    # rest length, length, tension
