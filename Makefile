@@ -30,7 +30,7 @@ $(BUILD)/tgb_capi.o: $(CSRC)/tgb_capi.cu $(DEV_HDRS) | $(BUILD)
 $(LIBDIR)/libntrtsim_b200.so: $(BUILD)/tgb_step_f32.o $(BUILD)/tgb_step_f64.o $(STEP_OBJS) $(BUILD)/tgb_capi.o | $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $^
 
-HOST_SRCS := $(HOST)/tgb_host.cpp $(HOST)/tgb_creator.cpp $(HOST)/tgb_sensors.cpp $(HOST)/tgb_examples.cpp $(HOST)/tgb_host_capi.cpp
+HOST_SRCS := $(HOST)/tgb_host.cpp $(HOST)/tgb_creator.cpp $(HOST)/tgb_sensors.cpp $(HOST)/tgb_yaml.cpp $(HOST)/tgb_examples.cpp $(HOST)/tgb_host_capi.cpp
 $(LIBDIR)/libtgb_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libntrtsim_b200.so | $(LIBDIR)
 	$(CXX) -std=c++17 -O2 -fPIC -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lntrtsim_b200 -Wl,-rpath,'$$ORIGIN'
 

@@ -33,6 +33,23 @@ def build_example(name):
         h.tgh_free(m)
 
 
+def build_yaml(path, gravity=98.1, dt=0.001):
+    """A structure file of the YAML front-end (src/yamlbuilder/TensegrityModel.cpp) built by the C++ host API in the world of the
+    reference's yamlbuilder app (BuildTensegrityModel.cpp:44-79: gravity 98.1, default box ground, dt 1e-3) -> FlatModel."""
+    return build_example("yaml:%s@%r@%r" % (path, float(gravity), float(dt)))
+
+
+def yaml_to_json(text):
+    """The host YAML reader's parse of `text` as a JSON string (scalars as strings); ValueError on malformed input."""
+    h = capi.load_host()
+    n = h.tgh_yaml_to_json(text.encode(), None, 0)
+    if n < 0:
+        raise ValueError(h.tgh_last_error().decode())
+    buf = C.create_string_buffer(n + 1)
+    h.tgh_yaml_to_json(text.encode(), buf, n + 1)
+    return buf.value.decode()
+
+
 def tree_counts(name):
     """(number of tgRod, number of tgSpringCableActuator) descendants of the built tgModel tree."""
     h = capi.load_host()

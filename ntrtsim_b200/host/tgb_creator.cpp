@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <sstream>
 #include <queue>
 
 /* ---- tgUtil ---------------------------------------------------------------------------------------- */
@@ -162,6 +163,54 @@ void tgStructure::addChild(tgStructure* child) {
     if (child) m_children.push_back(child);
 }
 void tgStructure::addChild(const tgStructure& child) { m_children.push_back(new tgStructure(child)); }
+tgNode& tgStructure::findNode(const std::string& tags) {
+    std::vector<tgStructure*> q(1, this);
+    for (std::size_t head = 0; head < q.size(); ++head) {
+        tgStructure* s = q[head];
+        for (std::size_t i = 0; i < s->m_nodes.size(); ++i)
+            if (s->m_nodes[i].hasAllTags(tags)) return s->m_nodes[i];
+        q.insert(q.end(), s->m_children.begin(), s->m_children.end());
+    }
+    throw std::invalid_argument("Node not found: " + tags);
+}
+tgStructure& tgStructure::findChild(const std::string& tags) {
+    std::vector<tgStructure*> q(m_children);
+    for (std::size_t head = 0; head < q.size(); ++head) {
+        tgStructure* s = q[head];
+        if (s->hasAllTags(tags)) return *s;
+        q.insert(q.end(), s->m_children.begin(), s->m_children.end());
+    }
+    throw std::invalid_argument("Child structure not found: " + tags);
+}
+tgPair& tgStructure::findPair(const btVector3& from, const btVector3& to) {
+    std::vector<tgStructure*> q(1, this);
+    for (std::size_t head = 0; head < q.size(); ++head) {
+        tgStructure* s = q[head];
+        for (std::size_t i = 0; i < s->m_pairs.size(); ++i) {
+            const tgPair& p = s->m_pairs[i];
+            if ((p.getFrom() == from && p.getTo() == to) || (p.getFrom() == to && p.getTo() == from)) return s->m_pairs[i];
+        }
+        q.insert(q.end(), s->m_children.begin(), s->m_children.end());
+    }
+    std::ostringstream os;
+    os << "Pair not found: (" << from.x() << ", " << from.y() << ", " << from.z() << "), (" << to.x() << ", " << to.y() << ", " << to.z() << ")";
+    throw std::invalid_argument(os.str());
+}
+void tgPairs::removePair(const tgPair& p) {
+    const btVector3 from = p.getFrom(), to = p.getTo(); /* p may live in this very vector */
+    std::size_t w = 0;
+    for (std::size_t i = 0; i < m_pairs.size(); ++i)
+        if (!(m_pairs[i].getFrom() == from && m_pairs[i].getTo() == to)) {
+            if (w != i) m_pairs[w] = m_pairs[i];
+            ++w;
+        }
+    m_pairs.resize(w);
+}
+void tgStructure::removePair(const tgPair& pair) {
+    const tgPair copy(pair);
+    m_pairs.removePair(copy);
+    for (std::size_t i = 0; i < m_children.size(); ++i) m_children[i]->removePair(copy);
+}
 btVector3 tgStructure::getCentroid() const {
     btVector3 c(0, 0, 0);
     int n = 0;

@@ -61,6 +61,8 @@ private:
 class tgPairs {
 public:
     void addPair(const tgPair& p) { m_pairs.push_back(p); }
+    /* erases every pair with the same end points, tags not compared (tgPair.h:110-113, tgTaggables.h:191-193) */
+    void removePair(const tgPair& p);
     std::size_t size() const { return m_pairs.size(); }
     tgPair& operator[](std::size_t i) { return m_pairs.at(i); }
     const tgPair& operator[](std::size_t i) const { return m_pairs.at(i); }
@@ -96,6 +98,13 @@ public:
     void addChild(const tgStructure& child);  /* copies */
     btVector3 getCentroid() const;
     const tgNodes& getNodes() const { return m_nodes; }
+    /* breadth-first over this structure and its children; not found -> std::invalid_argument (tgStructure.cpp:206-267) */
+    tgNode& findNode(const std::string& tags);
+    tgStructure& findChild(const std::string& tags);
+    /* either direction; not found -> std::invalid_argument (tgStructure.cpp:226-247) */
+    tgPair& findPair(const btVector3& from, const btVector3& to);
+    /* here and in every child (tgStructure.cpp:101-106) */
+    void removePair(const tgPair& pair);
     const tgPairs& getPairs() const { return m_pairs; }
     const std::vector<tgStructure*>& getChildren() const { return m_children; }
 private:

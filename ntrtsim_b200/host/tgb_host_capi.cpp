@@ -6,6 +6,7 @@
  */
 #include "tgb_examples.h"
 #include "tgb_sensors.h"
+#include "tgb_yaml.h"
 
 #include <cstring>
 #include <string>
@@ -70,6 +71,22 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
             e->world = new tgWorld(tgWorld::Config(981));
             e->dt = 0.001;
             e->model = new FlemonsSpineModelLearning(name == "FlemonsSpine" ? 12 : 3);
+        } else if (name.size() > 5 && name.compare(0, 5, "yaml:") == 0) {
+            /* "yaml:<path>[@gravity[@dt]]": a structure file of the YAML front-end in the world of the reference's yamlbuilder app
+               (src/yamlbuilder/BuildTensegrityModel.cpp:44-79: gravity 98.1, default box ground, dt = 1e-3) */
+            std::string path = name.substr(5);
+            double gravity = 98.1, dt = 0.001;
+            std::size_t at = path.find('@');
+            if (at != std::string::npos) {
+                std::string rest = path.substr(at + 1);
+                path = path.substr(0, at);
+                gravity = std::atof(rest.c_str());
+                at = rest.find('@');
+                if (at != std::string::npos) dt = std::atof(rest.substr(at + 1).c_str());
+            }
+            e->world = new tgWorld(tgWorld::Config(gravity));
+            e->dt = dt;
+            e->model = new TensegrityModel(path);
         } else {
             g_error = "unknown example: " + name;
             delete e;
@@ -298,6 +315,56 @@ int tgh_tetraspine_param_row(const double* node_actions, const double* edge_acti
     const tgbSpineControlConfig cfg(3, 6, 6, 2, 1, .001);
     tgbSpineScaleNodeActions(node_actions, cfg, row);
     return tgbSpineScaleEdgeActions(edge_actions, n_edge, cfg, row + 2);
+}
+
+/* The YAML reader's view of a document as JSON (all scalars as strings, null as null): lets the tests compare the reader with a full
+   YAML parser on the structure-file subset.  Returns the length needed (without the terminator), or -1 with tgh_last_error set. */
+static void yamToJson(const Yam& y, std::string& out) {
+    switch (y.type()) {
+    case Yam::Null: out += "null"; break;
+    case Yam::Scalar: {
+        out += '"';
+        for (std::size_t i = 0; i < y.str().size(); ++i) {
+            const char c = y.str()[i];
+            if (c == '"' || c == '\\') out += '\\';
+            out += c;
+        }
+        out += '"';
+        break;
+    }
+    case Yam::Sequence:
+        out += '[';
+        for (std::size_t i = 0; i < y.elements().size(); ++i) {
+            if (i) out += ", ";
+            yamToJson(y.elements()[i], out);
+        }
+        out += ']';
+        break;
+    case Yam::Map:
+        out += '{';
+        for (std::size_t i = 0; i < y.items().size(); ++i) {
+            if (i) out += ", ";
+            yamToJson(Yam::load("\"" + y.items()[i].first + "\""), out);
+            out += ": ";
+            yamToJson(y.items()[i].second, out);
+        }
+        out += '}';
+        break;
+    }
+}
+int tgh_yaml_to_json(const char* text, char* out, int cap) {
+    try {
+        std::string json;
+        yamToJson(Yam::load(text ? text : ""), json);
+        if (out && cap > 0) {
+            std::strncpy(out, json.c_str(), (size_t)cap - 1);
+            out[cap - 1] = 0;
+        }
+        return (int)json.size();
+    } catch (const std::exception& ex) {
+        g_error = ex.what();
+        return -1;
+    }
 }
 
 /* Drop-in demonstration: the example app's main loop on the device through the host API only

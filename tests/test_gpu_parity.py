@@ -695,3 +695,27 @@ def test_data_logger_samples_match_the_device_state(tmp_path):
     for c in range(model.n_cables):
         o = 1 + 7 * model.n_bodies + 3 * c
         assert np.allclose(last[o: o + 3], cab[2, c, 0:3], rtol=2e-5, atol=1e-6)                    # rest length, length, tension
+
+
+# ------------------------------------------------------------------------------------------------ YAML front-end (8f rank 3)
+@pytest.mark.parametrize("precision,steps", [("f64", 300), ("f32", 60)])
+def test_yaml_built_tower_matches_oracle(tmp_path, precision, steps):
+    """A structure file of the reference's YAML format (three prisms joined by node_edge bonds: 9 rods, 27 strings) built by
+    TensegrityModel, replicated with random poses, dropped on the box ground of the yamlbuilder app's world."""
+    from test_yaml import BASE_PRISM, TOWER, write
+    from ntrtsim_b200 import examples
+    write(tmp_path, "base/Prism.yaml", BASE_PRISM)
+    model = examples.build_yaml(write(tmp_path, "tower.yaml", TOWER))
+    n_env = 32
+    rods = random_poses(model, n_env, seed=77, translate=0.5, lift=(0.0, 2.0), yaw_only=True)
+    cab = tiled_cables(model, n_env)
+    rd, cd, st = device_rollout(model, rods, cab, steps, precision)
+    ro, co = oracle_rollout(model, rods, cab, steps)
+    e = rod_errors(rd, ro, 24.0 if precision == "f32" else 1.0)
+    terr = tension_rel_error(cd, co, floor=100.0)
+    print("yaml tower %s %d steps: rods %s tension %.2e, min height %.3f" % (precision, steps, e, terr, ro[:, :, 1].min()))
+    assert not st.any()
+    if precision == "f64":
+        assert max(e) < 1e-7 and terr < 1e-7
+    else:
+        assert e[0] < F32_REL and e[1] < F32_REL and terr < 5 * F32_REL
