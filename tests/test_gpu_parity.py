@@ -707,7 +707,7 @@ def test_yaml_built_tower_matches_oracle(tmp_path, precision, steps):
     write(tmp_path, "base/Prism.yaml", BASE_PRISM)
     model = examples.build_yaml(write(tmp_path, "tower.yaml", TOWER))
     n_env = 32
-    rods = random_poses(model, n_env, seed=77, translate=0.5, lift=(0.0, 2.0), yaw_only=True)
+    rods = random_poses(model, n_env, seed=77, translate=0.5, lift=(-1.2, 0.5), yaw_only=True)
     cab = tiled_cables(model, n_env)
     rd, cd, st = device_rollout(model, rods, cab, steps, precision)
     ro, co = oracle_rollout(model, rods, cab, steps)
