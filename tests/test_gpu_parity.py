@@ -698,10 +698,12 @@ def test_data_logger_samples_match_the_device_state(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ YAML front-end (8f rank 3)
-@pytest.mark.parametrize("precision,steps", [("f64", 300), ("f32", 60)])
+@pytest.mark.parametrize("precision,steps", [("f64", 150), ("f32", 60)])
 def test_yaml_built_tower_matches_oracle(tmp_path, precision, steps):
     """A structure file of the reference's YAML format (three prisms joined by node_edge bonds: 9 rods, 27 strings) built by
-    TensegrityModel, replicated with random poses, dropped on the box ground of the yamlbuilder app's world."""
+    TensegrityModel, replicated with random poses, dropped on the box ground of the yamlbuilder app's world (the lowest rod ends touch
+    from the first steps on).  The chattering resting contact amplifies a 1e-13 perturbation to 1e-11 after 150 steps, 1e-8 after 200
+    and 1e-3 after 300 (measured on the oracle), hence the horizon."""
     from test_yaml import BASE_PRISM, TOWER, write
     from ntrtsim_b200 import examples
     write(tmp_path, "base/Prism.yaml", BASE_PRISM)
