@@ -308,6 +308,13 @@ tgb_status tgb_set_lanes_per_env(tgb_world* w, int32_t lanes);
    (also settable through the environment variable TGB_BLOCK_THREADS). */
 tgb_status tgb_set_block_threads(tgb_world* w, int32_t threads);
 
+/* Layout of the step kernel: 0 = one group of lanes per environment does bodies and cables (best when the device is full of warps),
+   1 = CTAs of four warps that hold 32 / lanes environments -- warp 0 runs the bodies, all four share the cables, 4 x lanes per
+   environment (shortens a step when the kernel is latency bound: a few thousand environments per GPU), -1 = automatic (default;
+   the environment variable TGB_WIDE=0/1 overrides the automatic choice).  Lanes per env must be 4 or 8 and the controller not the
+   CPG one, else the narrow layout is used.  Results are bit-identical in both layouts.  May be called at any time. */
+tgb_status tgb_set_wide_layout(tgb_world* w, int32_t mode);
+
 /* Bytes of device state per environment (the HBM traffic of one launch is 2x this per env). */
 tgb_status tgb_state_bytes_per_env(const tgb_world* w, size_t* out);
 

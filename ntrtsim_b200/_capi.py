@@ -69,7 +69,7 @@ ABI_SYMBOLS = [
     "tgb_set_cable_state", "tgb_get_cable_obs", "tgb_set_controller", "tgb_set_control_input", "tgb_step", "tgb_step_world", "tgb_step_models", "tgb_sync",
     "tgb_rollout_host", "tgb_track_max_tension", "tgb_get_max_tension", "tgb_get_time", "tgb_get_status", "tgb_mark_episode_start", "tgb_get_scores",
     "tgb_scores_device_ptr", "tgb_step_timed", "tgb_launch_count", "tgb_launch_geometry", "tgb_set_lanes_per_env",
-    "tgb_set_block_threads", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
+    "tgb_set_block_threads", "tgb_set_wide_layout", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -131,6 +131,7 @@ def load():
     lib.tgb_launch_geometry.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]
     lib.tgb_set_lanes_per_env.argtypes = [_vp, _i32]
     lib.tgb_set_block_threads.argtypes = [_vp, _i32]
+    lib.tgb_set_wide_layout.argtypes = [_vp, _i32]
     lib.tgb_state_bytes_per_env.argtypes = [_vp, C.POINTER(C.c_size_t)]
     lib.tgb_set_height_window.argtypes = [_vp, C.c_double, C.c_double]
     lib.tgb_stream_handle.argtypes = [_vp, C.POINTER(_vp)]

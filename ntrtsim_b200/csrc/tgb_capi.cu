@@ -50,7 +50,9 @@ struct tgb_world {
     const tgb_ops* ops = nullptr;
     size_t scalarBytes = 4;
     int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0, maxInc = 0;
-    int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0;
+    int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0, wideMode = -1;
+    mutable int wideCtasPerSm[2] = {-1, -1}; /* by controller class (simple, sine); -1 = not asked yet */
+    int smCount = 148;
     cudaStream_t stream = nullptr;
     void* d_state = nullptr;
     double* d_frame = nullptr;
@@ -243,6 +245,34 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
     std::memcpy(tbytes.data(), t.data(), tbytes.size());
 }
 
+/* The four-warp layout of the step kernel (tgb_step.cuh, WIDE) shortens a step by ~28 % (an environment's cables run in one round)
+   but holds four times the threads per environment: it pays while all its CTAs are resident at once (registers decide: 3 CTAs = 12
+   SUPERball environments per SM, ~1800 per B200; measured at 4096 environments: 5.8e8 env-steps/s against 9.6e8, the grid then runs
+   in 2.3 waves).  Automatic choice: wide when the whole grid is resident.  tgb_set_wide_layout / TGB_WIDE=0|1 override. */
+bool wideLayout(const tgb_world* w) {
+    if (w->ctrlKind == TGB_CTRL_CPG_IMPEDANCE) return false;
+    if (w->lanes != 4 && w->lanes != 8) return false;
+    if (w->wideMode >= 0) return w->wideMode != 0;
+    static const char* envWide = std::getenv("TGB_WIDE");
+    if (envWide) return std::atoi(envWide) != 0;
+    const int cls = w->ctrlKind == TGB_CTRL_ESCAPE_SINE ? 1 : 0;
+    if (w->wideCtasPerSm[cls] < 0) {
+        tgb_step_args a;
+        std::memset(&a, 0, sizeof(a));
+        a.R = w->R; a.C = w->C; a.S = w->S; a.max_inc = w->maxInc; a.stride = w->stride; a.cap_contacts = w->capContacts;
+        a.ctrl_kind = w->ctrlKind; a.ctrl_stride = std::max(w->C, TGB_ESCAPE_PARAMS); a.ground_kind = w->ground.kind;
+        a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
+        int ctas = 0;
+        if (w->ops->wide_ctas_per_sm(a, w->lanes, &ctas) != cudaSuccess) { cudaGetLastError(); ctas = 0; }
+        w->wideCtasPerSm[cls] = ctas;
+    }
+    /* without ground the narrow layout already keeps three cables per lane in flight: no gain measured (3-prism, 256..1024 envs) */
+    if (w->ground.kind == TGB_GROUND_EMPTY) return false;
+    const int envsPerCta = 32 / w->lanes;
+    const long long ctas = ((long long)w->cfg.n_env + envsPerCta - 1) / envsPerCta;
+    return ctas <= (long long)w->wideCtasPerSm[cls] * w->smCount;
+}
+
 tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     tgb_step_args a;
     std::memset(&a, 0, sizeof(a));
@@ -253,6 +283,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.n_env = w->cfg.n_env; a.n_steps = nSteps;
     a.stats = w->d_stats;
     a.phases = 3;
+    a.wide = wideLayout(w) ? 1 : 0;
     a.R = w->R; a.C = w->C; a.S = w->S; a.n_inc = w->nInc; a.max_inc = w->maxInc;
     a.stride = w->stride; a.cap_contacts = w->capContacts; a.frame_body = w->frameBody;
     a.ctrl_kind = w->ctrlKind; a.ctrl_stride = w->ctrlKind != TGB_CTRL_NONE ? w->ctrlStride : 0;
@@ -329,6 +360,7 @@ tgb_status tgb_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, t
     w->ground = *ground;
     w->ops = cfg->precision == TGB_F64 ? tgb_ops_f64() : tgb_ops_f32();
     w->scalarBytes = w->ops->scalar_bytes;
+    { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sms > 0) w->smCount = sms; }
     e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
@@ -410,6 +442,13 @@ tgb_status tgb_set_lanes_per_env(tgb_world* w, int32_t lanes) {
     if (lanes != 0 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
         return fail(TGB_ERR_INVALID_ARGUMENT, "lanes per env must be 0 (automatic), 2, 4, 8, 16 or 32");
     w->lanesOverride = lanes;
+    return TGB_OK;
+}
+
+tgb_status tgb_set_wide_layout(tgb_world* w, int32_t mode) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (mode < -1 || mode > 1) return fail(TGB_ERR_INVALID_ARGUMENT, "layout mode must be -1 (automatic), 0 (narrow) or 1 (wide)");
+    w->wideMode = mode;
     return TGB_OK;
 }
 
@@ -966,9 +1005,10 @@ tgb_status tgb_launch_count(const tgb_world* w, int64_t* out) {
 tgb_status tgb_launch_geometry(const tgb_world* w, int32_t* lanes_per_env, int32_t* block, int32_t* grid) {
     if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
     if (!w->finalized) return fail(TGB_ERR_STATE, "world is not finalized");
-    const int groups = w->threads / w->lanes;
+    const bool wide = wideLayout(w);
+    const int groups = wide ? 32 / w->lanes : w->threads / w->lanes;
     if (lanes_per_env) *lanes_per_env = w->lanes;
-    if (block) *block = w->threads;
+    if (block) *block = wide ? 128 : w->threads;
     if (grid) *grid = (w->cfg.n_env + groups - 1) / groups;
     return TGB_OK;
 }

@@ -78,6 +78,7 @@ struct tgb_step_args {
     int n_env, n_steps;   /* a launch covers environments [env_begin, n_env) */
     int env_begin;
     int phases;           /* bit0: world half of tgSimulation::step, bit1: models half (controllers, motors, cable forces) */
+    int wide;             /* 1: the four-warp layout (body warp + shared cable phase, tgb_step.cuh); CTAs of 128 threads hold 32 / lanes environments */
     int R, C, S, n_inc;
     int max_inc;          /* longest incidence list of a body */
     int stride;           /* T words per env record */

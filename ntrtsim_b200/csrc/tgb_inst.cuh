@@ -6,21 +6,24 @@
 #include "tgb_ops.h"
 #include "tgb_step.cuh"
 
-cudaError_t TGB_STEP_SIMPLE(const tgb_step_args& a, int lpe, int threads, cudaStream_t s);
-cudaError_t TGB_STEP_SINE(const tgb_step_args& a, int lpe, int threads, cudaStream_t s);
-cudaError_t TGB_STEP_CPG(const tgb_step_args& a, int lpe, int threads, cudaStream_t s);
+cudaError_t TGB_STEP_SIMPLE(const tgb_step_args& a, int lpe, int threads, cudaStream_t s, int* wide_ctas);
+cudaError_t TGB_STEP_SINE(const tgb_step_args& a, int lpe, int threads, cudaStream_t s, int* wide_ctas);
+cudaError_t TGB_STEP_CPG(const tgb_step_args& a, int lpe, int threads, cudaStream_t s, int* wide_ctas);
 
 namespace {
 
 typedef TGB_SCALAR scalar_t;
 
-cudaError_t step(const tgb_step_args& a, int lpe, int threads, cudaStream_t s) {
+cudaError_t stepOrQuery(const tgb_step_args& a, int lpe, int threads, cudaStream_t s, int* wide_ctas) {
     switch (tgb::tgb_ctrl_class(a.ctrl_kind)) {
-    case tgb::TGB_CLASS_CPG: return TGB_STEP_CPG(a, lpe, threads, s);
-    case tgb::TGB_CLASS_SINE: return TGB_STEP_SINE(a, lpe, threads, s);
-    default: return TGB_STEP_SIMPLE(a, lpe, threads, s);
+    case tgb::TGB_CLASS_CPG: return TGB_STEP_CPG(a, lpe, threads, s, wide_ctas);
+    case tgb::TGB_CLASS_SINE: return TGB_STEP_SINE(a, lpe, threads, s, wide_ctas);
+    default: return TGB_STEP_SIMPLE(a, lpe, threads, s, wide_ctas);
     }
 }
+cudaError_t step(const tgb_step_args& a, int lpe, int threads, cudaStream_t s) { return stepOrQuery(a, lpe, threads, s, nullptr); }
+/* CTAs of the four-warp layout per SM for this controller class / lanes / ground; 0 when that layout is not compiled for them */
+cudaError_t wide_ctas_per_sm(const tgb_step_args& a, int lpe, int* out) { return stepOrQuery(a, lpe, 128, nullptr, out); }
 
 size_t step_smem(const tgb_step_args& a, int lpe, int threads) { return tgb::tgb_step_smem_bytes(a, lpe, threads, sizeof(scalar_t)); }
 
@@ -62,7 +65,7 @@ cudaError_t com(const tgb::tgb_io_args& a, int mode, double* scores, float* scor
     return cudaGetLastError();
 }
 
-const tgb_ops kOps = {sizeof(scalar_t), step, step_smem, pack_rods, unpack_rods, pack_cables, cable_obs, control_input, com};
+const tgb_ops kOps = {sizeof(scalar_t), step, wide_ctas_per_sm, step_smem, pack_rods, unpack_rods, pack_cables, cable_obs, control_input, com};
 
 } // namespace
 

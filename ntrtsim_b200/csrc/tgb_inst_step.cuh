@@ -27,22 +27,67 @@ cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+/* the four-warp layout: 128 threads, 32 / LPE environments per CTA */
+template <int LPE, bool GROUND, int NW>
+cudaError_t launch_wide(const tgb_step_args& a, cudaStream_t s) {
+    const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, 128, sizeof(scalar_t));
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, NW>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int groupsPerBlock = 32 / LPE;
+    const int grid = (a.n_env - a.env_begin + groupsPerBlock - 1) / groupsPerBlock;
+    if (grid <= 0) return cudaSuccess;
+    tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, NW><<<grid, 32 * NW, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+/* CTAs of the four-warp layout one SM holds (registers and shared memory decide) */
+template <int LPE, bool GROUND>
+cudaError_t wide_ctas_per_sm(const tgb_step_args& a, int* out) {
+    tgb_step_args aw = a;
+    aw.wide = 1;
+    const size_t smem = tgb::tgb_step_smem_bytes(aw, LPE, 128, sizeof(scalar_t));
+    cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 4>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 4>, 128, smem);
+}
+
 template <int LPE>
-cudaError_t launch(const tgb_step_args& a, int threads, cudaStream_t s) {
+cudaError_t launch(const tgb_step_args& a, int threads, cudaStream_t s, int* wide_ctas) {
+    if (wide_ctas) {
+        *wide_ctas = 0;
+        if constexpr (TGB_STEP_CLASS != tgb::TGB_CLASS_CPG && (LPE == 4 || LPE == 8)) {
+            if (a.ground_kind == TGB_GROUND_EMPTY) return wide_ctas_per_sm<LPE, false>(a, wide_ctas);
+            return wide_ctas_per_sm<LPE, true>(a, wide_ctas);
+        }
+        return cudaSuccess;
+    }
+    if constexpr (TGB_STEP_CLASS != tgb::TGB_CLASS_CPG && (LPE == 4 || LPE == 8)) {
+        if (a.wide) {
+            if (a.ground_kind == TGB_GROUND_EMPTY) return launch_wide<LPE, false, 4>(a, s);
+            return launch_wide<LPE, true, 4>(a, s);
+        }
+    }
+    if (a.wide) return cudaErrorInvalidValue;
     if (a.ground_kind == TGB_GROUND_EMPTY) return launch_impl<LPE, false>(a, threads, s);
     return launch_impl<LPE, true>(a, threads, s);
 }
 
 } // namespace
 
-cudaError_t TGB_STEP_FN(const tgb_step_args& a, int lpe, int threads, cudaStream_t s) {
+cudaError_t TGB_STEP_FN(const tgb_step_args& a, int lpe, int threads, cudaStream_t s, int* wide_ctas) {
     if (threads < 32 || threads > 128 || (threads % 32) != 0) return cudaErrorInvalidValue;
     switch (lpe) {
-    case 2: return launch<2>(a, threads, s);
-    case 4: return launch<4>(a, threads, s);
-    case 8: return launch<8>(a, threads, s);
-    case 16: return launch<16>(a, threads, s);
-    case 32: return launch<32>(a, threads, s);
+    case 2: return launch<2>(a, threads, s, wide_ctas);
+    case 4: return launch<4>(a, threads, s, wide_ctas);
+    case 8: return launch<8>(a, threads, s, wide_ctas);
+    case 16: return launch<16>(a, threads, s, wide_ctas);
+    case 32: return launch<32>(a, threads, s, wide_ctas);
     default: return cudaErrorInvalidValue;
     }
 }

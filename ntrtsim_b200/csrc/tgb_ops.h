@@ -16,6 +16,7 @@ struct tgb_ops {
     size_t scalar_bytes;
     /* returns cudaErrorInvalidValue for an unsupported lanes-per-env value */
     cudaError_t (*step)(const tgb_step_args& a, int lanes_per_env, int threads, cudaStream_t s);
+    cudaError_t (*wide_ctas_per_sm)(const tgb_step_args& a, int lanes_per_env, int* out);
     size_t (*step_smem)(const tgb_step_args& a, int lanes_per_env, int threads);
     cudaError_t (*pack_rods)(const tgb::tgb_io_args& a, const double* src, int broadcast, cudaStream_t s);
     cudaError_t (*unpack_rods)(const tgb::tgb_io_args& a, double* dst, cudaStream_t s);

@@ -413,8 +413,18 @@ TGB_HOST_DEVICE_INLINE int tgb_ctrl_class(int kind) {
     return kind == TGB_CTRL_CPG_IMPEDANCE ? TGB_CLASS_CPG : kind == TGB_CTRL_ESCAPE_SINE ? TGB_CLASS_SINE : TGB_CLASS_SIMPLE;
 }
 
-template <typename T, int LPE, int CLASS, bool GROUND>
-__global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
+/* WIDE = true is the layout for few environments (the machine is latency bound: ~1.7 warps per scheduler at 4096 environments): a
+   CTA of four warps holds 32 / LPE environments; warp 0 is the body warp (lane j of a group of LPE = body j, as in the narrow
+   layout) and all four warps share the cable phase with 4 LPE lanes per environment, so that the cables of an environment run in
+   one round instead of C / LPE rounds.  The two per-step warp barriers become CTA barriers.  The arithmetic of a body / cable does
+   not depend on the lane that runs it: results are bit-identical to the narrow layout. */
+/* Register budgets: the narrow layout is capped by shared memory at 8 one-warp CTAs per SM, so its lanes may take what ptxas wants
+   (minBlocks 1: 209 registers instead of 163, +3.3 % on B200); the four-warp layout needs three CTAs per SM (168 registers). */
+#ifndef TGB_NARROW_MINBLOCKS
+#define TGB_NARROW_MINBLOCKS 1
+#endif
+template <typename T, int LPE, int CLASS, bool GROUND, int WIDE = 0 /* 0 or 4 warps */>
+__global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step_kernel(const tgb_step_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename Vec16<T>::type vec_t;
     const int VN = Vec16<T>::N;
@@ -422,11 +432,19 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
     const int tid = threadIdx.x;
     const int lane = tid % LPE;
-    const int grp = tid / LPE;
-    const int groupsPerBlock = blockDim.x / LPE;
+    const bool bodyWarp = !WIDE || tid < 32; /* WIDE: warps 1..3 shadow the groups of warp 0 in the body role and never store */
+    const int grp = WIDE ? (tid & 31) / LPE : tid / LPE;
+    const int groupsPerBlock = WIDE ? 32 / LPE : blockDim.x / LPE;
     const int envRaw = a.env_begin + blockIdx.x * groupsPerBlock + grp;
-    const bool live = envRaw < a.n_env;
-    const int env = live ? envRaw : a.n_env - 1; /* tail groups shadow the last env and never store */
+    const bool live = bodyWarp && envRaw < a.n_env;
+    const int env = envRaw < a.n_env ? envRaw : a.n_env - 1; /* tail groups shadow the last env and never store */
+    /* cable role: the lanes that share an environment's cables */
+    constexpr int CL = WIDE ? WIDE * LPE : LPE;
+    const int cLane = WIDE ? tid % CL : lane;
+    const int cGrp = WIDE ? tid / CL : grp;
+    const int cEnvRaw = a.env_begin + blockIdx.x * groupsPerBlock + cGrp;
+    const bool cLive = cEnvRaw < a.n_env;
+    const int cEnv = cLive ? cEnvRaw : a.n_env - 1;
     /* lanes of this group inside the warp, for shuffles */
     const unsigned fullMask = 0xffffffffu;
     const int warpLane = tid & 31;
@@ -465,6 +483,14 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     constexpr int CU = TGB_CABLE_UNROLL ? TGB_CABLE_UNROLL : (GROUND ? 1 : 3);
     const int groupDWords = tgb_group_double_words(a);
     double* sD = reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) + grp * groupDWords;
+    /* the same regions of the cable role's environment */
+    T* cStateP = sModelT + modelTWords + cGrp * groupTWords;
+    T* cPoseP = cStateP + a.stride;
+    T* cJP = cPoseP + poseWords;
+    double* cCtrlP = reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) + cGrp * groupDWords;
+    double* cCumP = cCtrlP + a.ctrl_stride;
+    double* cSineP = cCumP + 8;
+    double* cRotP = cSineP + TGB_SINE_REC * 24;
     double* sCtrl = sD;                        /* controller parameter row */
     double* sCum = sD + a.ctrl_stride;         /* sine controller: cumulative phase per cluster */
     /* CPG: pair table (weight, cos phase, sin phase), state x, stage state, published (sin, cos, r), k1..k7, node values */
@@ -571,7 +597,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
     int statusAcc = 0;
 
     /* ---- body state into registers ------------------------------------------------------------------------ */
-    const bool hasBody = lane < R;
+    const bool hasBody = bodyWarp && lane < R;
     const int bidx = hasBody ? lane : 0;
     BodyReg<T> b;
     {
@@ -605,7 +631,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
     };
     publishPose();
-    __syncwarp();
+    if (WIDE) __syncthreads(); else __syncwarp();
     /* a frame tied to a static body never moves: static bodies then stay bit-exactly in place */
     const bool frameMoves = M.body(BF_INVMASS, a.frame_body) != T(0);
 
@@ -965,7 +991,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
 
         /* ---- env frame: advance the origin with the frame velocity, then re-centre on the frame body ---- */
-        if (frameMoves && doWorld) {
+        if (frameMoves && doWorld && bodyWarp) {
             Ox += Vx * a.dt; Oy += Vy * a.dt; Oz += Vz * a.dt;
             const int src = groupLane0 + a.frame_body;
             const T sx = __shfl_sync(fullMask, b.x.x, src), sy = __shfl_sync(fullMask, b.x.y, src), sz = __shfl_sync(fullMask, b.x.z, src);
@@ -976,7 +1002,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
             b.v -= V3<T>(svx, svy, svz);
         }
         publishPose();
-        __syncwarp();
+        if (WIDE) __syncthreads(); else __syncwarp();
 #ifdef TGB_STATS
         if (a.stats) {
             /* per warp and step: [0..8] histogram of the largest contact count of a lane, [16..48] histogram of the number of
@@ -1023,12 +1049,17 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
         /* Cables of this lane are processed CU at a time in three passes (loads, arithmetic, stores) over independent
            register sets, so that the loads and the dependent chains of different cables overlap instead of queueing. */
-        for (int c0 = lane; c0 < C; c0 += CU * LPE) {
+        {
+        /* the cable role's view of its environment (identical to the body role's in the narrow layout) */
+        T* const sState = cStateP; T* const sPose = cPoseP; T* const sJ = cJP;
+        double* const sCtrl = cCtrlP; double* const sCum = cCumP; double* const sSine = cSineP; double* const sRot = cRotP;
+        const int env = cEnv; const bool live = cLive;
+        for (int c0 = cLane; c0 < C; c0 += CU * CL) {
             CableRegs<T> cr[CU];
 #pragma unroll
             for (int u = 0; u < CU; ++u) {
                 CableRegs<T>& q = cr[u];
-                const int cu = c0 + u * LPE;
+                const int cu = c0 + u * CL;
                 q.valid = cu < C;
                 const int c = q.valid ? cu : c0; /* an idle slot shadows cable c0 and never stores */
                 q.c = c;
@@ -1308,7 +1339,9 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 #endif
             }
         }
-        __syncwarp();
+        (void)sCtrl; (void)sCum; (void)sSine; (void)sRot; (void)env; (void)live; (void)sPose; (void)sState; (void)sJ;
+        }
+        if (WIDE) __syncthreads(); else __syncwarp();
 #ifdef TGB_STATS
         const long long statC = clock64();
 #endif
@@ -1399,7 +1432,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
         }
         if (live && lane == 0 && st != 0) a.status[env] |= st;
     }
-    __syncwarp();
+    if (WIDE) __syncthreads(); else __syncwarp();
     if (live) {
         vec_t* gs = reinterpret_cast<vec_t*>(reinterpret_cast<T*>(a.state) + (size_t)env * a.stride);
         const vec_t* ss = reinterpret_cast<const vec_t*>(sState);
@@ -1426,7 +1459,7 @@ __global__ void __launch_bounds__(128) tgb_step_kernel(const tgb_step_args a) {
 
 /* Shared memory a launch of this kernel needs; mirrors the carve-up above. */
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
-    const int groupsPerBlock = threads / lpe;
+    const int groupsPerBlock = a.wide ? 32 / lpe : threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
     const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * TGB_NCT * a.R;
     int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords);

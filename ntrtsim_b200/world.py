@@ -39,7 +39,7 @@ class FlatModel(object):
 
 
 class BatchedWorld(object):
-    def __init__(self, model, n_env, precision="f32", device=0, solver_iterations=0, lanes_per_env=0, block_threads=0):
+    def __init__(self, model, n_env, precision="f32", device=0, solver_iterations=0, lanes_per_env=0, block_threads=0, wide=None):
         self._lib = capi.load()
         self.model = model
         self.n_env = int(n_env)
@@ -55,6 +55,8 @@ class BatchedWorld(object):
                 capi.check(self._lib.tgb_set_lanes_per_env(h, lanes_per_env))
             if block_threads:
                 capi.check(self._lib.tgb_set_block_threads(h, block_threads))
+            if wide is not None:
+                capi.check(self._lib.tgb_set_wide_layout(h, 1 if wide else 0))
             capi.check(self._lib.tgb_finalize(h))
         except Exception:
             self.close()

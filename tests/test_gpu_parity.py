@@ -300,10 +300,34 @@ def test_bit_identical_across_launch_geometry(precision):
     model = nt.build_example("Escape_c3")
     n_env, steps = 70, 120
     rods, cab, params = escape_inputs(model, n_env, seed=5)
-    ref = device_rollout(model, rods, cab, steps, precision, capi.TGB_CTRL_ESCAPE_SINE, params)
-    for kw in (dict(lanes_per_env=16), dict(lanes_per_env=32, block_threads=64), dict(block_threads=128), dict(chunks=7)):
+    ref = device_rollout(model, rods, cab, steps, precision, capi.TGB_CTRL_ESCAPE_SINE, params, wide=False)
+    for kw in (dict(lanes_per_env=16, wide=False), dict(lanes_per_env=32, block_threads=64), dict(block_threads=128, wide=False), dict(chunks=7, wide=False),
+               dict(wide=True), dict(wide=True, chunks=7)):
         got = device_rollout(model, rods, cab, steps, precision, capi.TGB_CTRL_ESCAPE_SINE, params, **kw)
         assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), kw
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("example,ctrl", [("3_prism_noground", 0), ("3_prism", 0), ("SUPERball", capi.TGB_CTRL_TENSION),
+                                          ("tsTestRig_kinematic", capi.TGB_CTRL_TORQUE)])
+def test_wide_layout_is_bit_identical(precision, example, ctrl):
+    """The four-warp layout (body warp + shared cable phase; tgb_set_wide_layout) against the narrow one: 4 and 8 lanes per
+    environment, with and without ground, environment counts that leave tail groups, a launch cut in chunks."""
+    model = nt.build_example(example)
+    n_env, steps = 37, 150
+    rods = random_poses(model, n_env, seed=9, translate=0.5, lift=(0.0, 1.0), yaw_only=True)
+    cab = tiled_cables(model, n_env)
+    params = None
+    if ctrl == capi.TGB_CTRL_TENSION:
+        params = np.full((n_env, 1), 1000.0)
+    elif ctrl == capi.TGB_CTRL_TORQUE:
+        params = np.random.default_rng(4).uniform(-2.0, 2.0, size=(n_env, model.n_cables))
+    kw = dict(lanes_per_env=4) if model.n_bodies <= 2 else {}
+    ref = device_rollout(model, rods, cab, steps, precision, ctrl, params, wide=False, **kw)
+    for extra in (dict(), dict(chunks=4)):
+        got = device_rollout(model, rods, cab, steps, precision, ctrl, params, wide=True, **kw, **extra)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2]), extra
+    assert np.isfinite(ref[0]).all()
 
 
 def test_scores_and_status():
