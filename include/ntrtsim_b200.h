@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define TGB_ABI_VERSION 2
+#define TGB_ABI_VERSION 3
 
 typedef enum {
     TGB_OK = 0,
@@ -97,19 +97,22 @@ typedef struct {
 
 typedef enum {
     TGB_SHAPE_CYLINDER = 0, /* btCylinderShape: flat-ended cylinder along its local Y (tgRodInfo.cpp:105-106) */
-    TGB_SHAPE_SPHERE = 1    /* btSphereShape (tgSphereInfo.cpp:100-115): a point with collision margin = radius; set
+    TGB_SHAPE_SPHERE = 1,   /* btSphereShape (tgSphereInfo.cpp:100-115): a point with collision margin = radius; set
                                half_length = margin = radius */
+    TGB_SHAPE_BOX = 2       /* btBoxShape(width, length / 2, height) (tgBoxInfo.cpp:100-118): half extents radius (local X),
+                               half_length (local Y, the pair's axis) and half_extent_z */
 } tgb_shape_kind;
 
 /* One collision primitive of a body. */
 typedef struct {
     double radius;
     double half_length;
-    double margin;         /* cylinder: Bullet setSafeMargin, min(0.04, 0.1*min(radius, half_length)); sphere: the radius */
+    double margin;         /* cylinder, box: Bullet setSafeMargin, min(0.04, 0.1 * smallest half extent); sphere: the radius */
     double pos[3];         /* child transform in the body frame */
     double quat[4];
     int32_t kind;          /* tgb_shape_kind */
     int32_t reserved;
+    double half_extent_z;  /* box only (ABI version 3) */
 } tgb_shape_desc;
 
 typedef enum {

@@ -36,7 +36,7 @@ class BodyDesc(C.Structure):
 
 class ShapeDesc(C.Structure):
     _fields_ = [("radius", C.c_double), ("half_length", C.c_double), ("margin", C.c_double), ("pos", C.c_double * 3),
-                ("quat", C.c_double * 4), ("kind", C.c_int32), ("reserved", C.c_int32)]
+                ("quat", C.c_double * 4), ("kind", C.c_int32), ("reserved", C.c_int32), ("half_extent_z", C.c_double)]
 
 
 class CableDesc(C.Structure):

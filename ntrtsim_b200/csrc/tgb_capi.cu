@@ -221,6 +221,7 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         const double m[9] = {1.0 - (yy + zz), xy - wz, xz + wy, xy + wz, 1.0 - (xx + zz), yz - wx, xz - wy, yz + wx, 1.0 - (xx + yy)};
         for (int k = 0; k < 9; ++k) st[(SF_ROT0 + k) * S + s] = (T)m[k];
         st[SF_KIND * S + s] = (T)d.kind;
+        st[SF_HALFZ * S + s] = (T)d.half_extent_z;
     }
     for (int c = 0; c < C; ++c) {
         const tgb_cable_desc& d = w->cables[c];
@@ -419,7 +420,7 @@ tgb_status tgb_add_model_flat(tgb_world* w, const tgb_body_desc* bodies, int32_t
         if (!(c.rest_length > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "Pretension causes string to shorten past rest length!");
     }
     for (int i = 0; i < n_shapes; ++i) {
-        if (shapes[i].kind != TGB_SHAPE_CYLINDER && shapes[i].kind != TGB_SHAPE_SPHERE) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_model_flat: unknown shape kind");
+        if (shapes[i].kind < TGB_SHAPE_CYLINDER || shapes[i].kind > TGB_SHAPE_BOX) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_model_flat: unknown shape kind");
         if (shapes[i].radius < 0.0 || shapes[i].half_length < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "Negative radius");
     }
     for (int i = 0; i < n_shapes; ++i) w->shapes.push_back(shapes[i]);

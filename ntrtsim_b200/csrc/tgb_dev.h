@@ -31,7 +31,7 @@ enum { BF_INVMASS = 0, BF_GFY, BF_INVIX, BF_INVIY, BF_INVIZ, BF_IX, BF_IY, BF_IZ
 /* body int-fields */
 enum { BI_SHAPE_BEGIN = 0, BI_SHAPE_COUNT, BI_INC_BEGIN, BI_INC_COUNT, BI_GYRO, TGB_NBI };
 /* shape T-fields */
-enum { SF_RADIUS = 0, SF_HALFLEN, SF_MARGIN, SF_POSX, SF_POSY, SF_POSZ, SF_ROT0, SF_KIND = SF_ROT0 + 9 /* 0 cylinder, 1 sphere */, TGB_NSF };
+enum { SF_RADIUS = 0, SF_HALFLEN, SF_MARGIN, SF_POSX, SF_POSY, SF_POSZ, SF_ROT0, SF_KIND = SF_ROT0 + 9 /* tgb_shape_kind */, SF_HALFZ /* box */, TGB_NSF };
 /* cable T-fields */
 enum {
     CF_LAX = 0, CF_LAY, CF_LAZ, CF_LBX, CF_LBY, CF_LBZ, CF_K, CF_C, CF_MAXTENS, CF_TVEL, CF_MINAL, CF_MINRL,

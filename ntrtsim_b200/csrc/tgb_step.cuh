@@ -401,6 +401,8 @@ struct ShapeConst {
     T radius, halfLen, margin;
     V3<T> spos, r0, r1; /* position, columns 0 and 1 of the rotation */
     bool sphere;        /* a point with margin = radius: one candidate contact point instead of eight rim points */
+    bool box;           /* half extents (radius, halfLen, halfZ): the eight corners of the core box instead of rim points */
+    T halfZ;
 };
 
 /* Controller classes a kernel is compiled for (the controller kind inside a class is a warp-uniform run-time switch):
@@ -755,7 +757,9 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         sc.spos = V3<T>(M.shape(SF_POSX, si), M.shape(SF_POSY, si), M.shape(SF_POSZ, si));
         sc.r0 = V3<T>(M.shape(SF_ROT0 + 0, si), M.shape(SF_ROT0 + 3, si), M.shape(SF_ROT0 + 6, si));
         sc.r1 = V3<T>(M.shape(SF_ROT0 + 1, si), M.shape(SF_ROT0 + 4, si), M.shape(SF_ROT0 + 7, si));
-        sc.sphere = M.shape(SF_KIND, si) != T(0);
+        sc.sphere = M.shape(SF_KIND, si) == T(TGB_SHAPE_SPHERE);
+        sc.box = M.shape(SF_KIND, si) == T(TGB_SHAPE_BOX);
+        sc.halfZ = M.shape(SF_HALFZ, si);
         return sc;
     };
     const ShapeConst<T> shape0 = loadShape(shapeCount > 0 ? shapeBegin : 0);
@@ -847,20 +851,36 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     const T na = gn.dot(axisDir);
                     const V3<T> perp = -(gn - axisDir * na);
                     const T pl = perp.length();
-                    /* the lowest rim point is at n.c - |n.a| hc - rc |perp| (exact arithmetic): a shape clearly above the
-                       contact band contributes nothing (the 1e-3 slack covers round-off; no result changes) */
-                    if (((gn.dot(c) + originHeight) - margin) - tabs(na) * hc - rc * pl > SolverConst<T>::breakingThreshold() + T(1e-3)) continue;
+                    /* the lowest rim point is at n.c - |n.a| hc - rc |perp| (exact arithmetic; a box: minus the lowest corner's
+                       offset in the face instead of rc |perp|): a shape clearly above the contact band contributes nothing (the
+                       1e-3 slack covers round-off; no result changes) */
+                    T faceDrop = rc * pl;
+                    V3<T> boxU, boxW;
+                    if (sc.box) {
+                        /* the corners of the core box: around each face of the local-Y pair, starting at the corner lowest along the
+                           normal.  (boxU, boxW) are the halves of the face diagonals: corner k = 0 is +boxU, 1 is +boxW, 2 is -boxU,
+                           3 is -boxW, so that the candidate loop below is shared with the cylinder's rim points */
+                        const V3<T> ez = col0.cross(axisDir);
+                        const T hx = rc, hz = sc.halfZ - margin;
+                        const V3<T> bu = gn.dot(col0) > T(0) ? -col0 : col0, bw = gn.dot(ez) > T(0) ? -ez : ez;
+                        boxU = bu * hx + bw * hz;
+                        boxW = bw * hz - bu * hx;
+                        faceDrop = -gn.dot(boxU);
+                    }
+                    if (((gn.dot(c) + originHeight) - margin) - tabs(na) * hc - faceDrop > SolverConst<T>::breakingThreshold() + T(1e-3)) continue;
                     V3<T> u;
                     if (pl > T(1e-9)) u = perp / pl;
                     else u = col0;
-                    const V3<T> wdir = axisDir.cross(u);
+                    V3<T> wdir = axisDir.cross(u);
+                    T rr = rc; /* candidate k sits at ce +- rr u or ce +- rr wdir */
+                    if (sc.box) { u = boxU; wdir = boxW; rr = T(1); }
                     /* heights of the eight rim points in closed form (two end caps x four directions), used only to drop points
                        that are clearly out of the contact band before any vector work (same 1e-3 slack as above; a candidate
                        still has to pass the exact test).  The candidates are collected in a bit mask, then visited in the
                        manifold's order (end cap major, direction minor): lanes whose contacts sit at different rim points
                        run the row set-up below together instead of one candidate slot after the other. */
                     const T hCentre = (gn.dot(c) + originHeight) - margin;
-                    const T hu = rc * gn.dot(u), hw = rc * gn.dot(wdir);
+                    const T hu = rr * gn.dot(u), hw = rr * gn.dot(wdir);
                     const T skipAbove = SolverConst<T>::breakingThreshold() + T(1e-3);
                     unsigned candidates = 0;
 #pragma unroll
@@ -881,7 +901,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                         {
                             const V3<T> ce = c + axisDir * (e == 0 ? -hc : hc);
                             const V3<T> dir = (k == 0) ? u : (k == 1) ? wdir : (k == 2) ? -u : -wdir;
-                            const V3<T> pc = ce + dir * rc;
+                            const V3<T> pc = ce + dir * rr;
                             const T dist = (gn.dot(pc) + originHeight) - margin;
                             if (dist <= SolverConst<T>::breakingThreshold()) {
                                 /* ---- setupContactConstraint / setupFrictionConstraint for this point ---- */

@@ -335,6 +335,84 @@ tgModel* tgRodInfo::createModel(tgWorldB200Impl& world) {
     return new tgRod(&world, body, world.bodies().at(body).mass, getTags(), getLength());
 }
 
+/* ---- box between two nodes ------------------------------------------------------------------------------- */
+tgBoxInfo::tgBoxInfo(const tgBox::Config& config) : m_config(config) {}
+tgBoxInfo::tgBoxInfo(const tgBox::Config& config, const tgTags& tags, const tgPair& pair)
+    : tgRigidInfo(tags + pair.getTags()), m_pair(pair), m_config(config) {}
+tgRigidInfo* tgBoxInfo::createRigidInfo(const tgPair& pair, const tgTagSearch& search) const {
+    if (!search.matches(pair.getTags())) return 0;
+    return new tgBoxInfo(m_config, getTags(), pair);
+}
+double tgBoxInfo::getMass() const {
+    /* tgBoxInfo.cpp:120-133: width and height are half extents, the volume is that of the full box */
+    const double volume = getLength() * (m_config.width * 2) * (m_config.height * 2);
+    return volume * m_config.density;
+}
+std::vector<btVector3> tgBoxInfo::getContainedNodes() const {
+    std::vector<btVector3> v;
+    v.push_back(getFrom());
+    v.push_back(getTo());
+    return v;
+}
+/* tgBoxInfo.cpp:142-185: like a rod of radius `width` */
+btVector3 tgBoxInfo::getConnectionPoint(const btVector3& referencePoint, const btVector3& destinationPoint, double rotation) const {
+    if (referencePoint == destinationPoint) throw std::invalid_argument("Destination point is the reference point.");
+    const btVector3 axis = (getTo() - getFrom()).normalize();
+    const btVector3 refToDest = (referencePoint - destinationPoint).normalize();
+    btVector3 rotationAxis = axis.cross(refToDest);
+    if (rotationAxis.length() == 0.0) {
+        btScalar a = axis[0], b = axis[1], c = axis[2];
+        rotationAxis = btVector3(b - c, -a, a).normalize();
+    }
+    const btVector3 directional = axis.rotate(rotationAxis, -M_PI / 2.0).normalize();
+    const btVector3 surfaceVector = directional.rotate(axis, rotation).normalize() * m_config.width;
+    return referencePoint + surfaceVector;
+}
+tgb_shape_desc tgBoxInfo::shape() const {
+    tgb_shape_desc s = tgb_shape_desc();
+    s.kind = TGB_SHAPE_BOX;
+    s.radius = m_config.width;          /* half extent along local X */
+    s.half_length = getLength() / 2.0;  /* along local Y = the pair's axis */
+    s.half_extent_z = m_config.height;
+    /* btBoxShape: setSafeMargin(boxHalfExtents), btBoxShape.cpp / btConvexInternalShape.h */
+    const double m = 0.1 * std::min(s.radius, std::min(s.half_length, s.half_extent_z));
+    s.margin = m < 0.04 ? m : 0.04;
+    s.quat[3] = 1.0;
+    return s;
+}
+void tgBoxInfo::appendShapes(const btVector3& bodyOrigin, std::vector<tgb_shape_desc>& out) const {
+    tgb_shape_desc s = shape();
+    btTransform t = getTransform();
+    btVector3 o = t.getOrigin() - bodyOrigin;
+    btQuaternion q = t.getRotation();
+    s.pos[0] = o.x(); s.pos[1] = o.y(); s.pos[2] = o.z();
+    s.quat[0] = q.x(); s.quat[1] = q.y(); s.quat[2] = q.z(); s.quat[3] = q.w();
+    out.push_back(s);
+}
+tgb_body_desc tgBoxInfo::describeBody(std::vector<tgb_shape_desc>& shapes) const {
+    tgb_body_desc b = tgb_body_desc();
+    fillCommonBody(b, getMass(), getTransform());
+    const tgb_shape_desc s = shape();
+    shapes.push_back(s);
+    if (b.mass != 0.0) {
+        /* btBoxShape::calculateLocalInertia: the box of the half extents with margin */
+        const double lx = 2.0 * ((s.radius - s.margin) + s.margin), ly = 2.0 * ((s.half_length - s.margin) + s.margin),
+                     lz = 2.0 * ((s.half_extent_z - s.margin) + s.margin);
+        b.inertia[0] = b.mass / 12.0 * (ly * ly + lz * lz);
+        b.inertia[1] = b.mass / 12.0 * (lx * lx + lz * lz);
+        b.inertia[2] = b.mass / 12.0 * (lx * lx + ly * ly);
+    }
+    b.friction = m_config.friction;
+    b.rolling_friction = m_config.rollFriction;
+    b.restitution = m_config.restitution;
+    return b;
+}
+tgModel* tgBoxInfo::createModel(tgWorldB200Impl& world) {
+    initRigidBody(world);
+    const int body = getBodyIndex();
+    return new tgBox(&world, body, world.bodies().at(body).mass, getTags(), getLength());
+}
+
 /* ---- sphere at a node ------------------------------------------------------------------------------------ */
 tgSphereInfo::tgSphereInfo(const tgSphere::Config& config) : m_config(config) {}
 tgSphereInfo::tgSphereInfo(const tgSphere::Config& config, const tgTags& tags, const tgNode& node)
@@ -443,7 +521,8 @@ tgb_body_desc tgCompoundRigidInfo::describeBody(std::vector<tgb_shape_desc>& sha
         const tgb_shape_desc& s = shapes[i];
         btMatrix3x3 R(btQuaternion(s.quat[0], s.quat[1], s.quat[2], s.quat[3]));
         btMatrix3x3 A = R.absolute();
-        btVector3 he((s.radius - s.margin) + s.margin, (s.half_length - s.margin) + s.margin, (s.radius - s.margin) + s.margin);
+        const double hz = s.kind == TGB_SHAPE_BOX ? s.half_extent_z : s.radius;
+        btVector3 he((s.radius - s.margin) + s.margin, (s.half_length - s.margin) + s.margin, (hz - s.margin) + s.margin);
         btVector3 ext = he.dot3(A[0], A[1], A[2]);
         btVector3 c(s.pos[0], s.pos[1], s.pos[2]);
         for (int k = 0; k < 3; ++k) {

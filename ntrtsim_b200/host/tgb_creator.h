@@ -173,6 +173,34 @@ private:
     tgRod::Config m_config;
 };
 
+/* A box between the two points of a pair: btBoxShape(width, length / 2, height) in the pair's frame (tgBoxInfo.cpp:72-200). */
+class tgBoxInfo : public tgRigidInfo {
+public:
+    explicit tgBoxInfo(const tgBox::Config& config);
+    tgBoxInfo(const tgBox::Config& config, const tgTags& tags, const tgPair& pair);
+    tgRigidInfo* createRigidInfo(const tgPair& pair, const tgTagSearch& search) const;
+    void getMaterial(double& friction, double& rollFriction, double& restitution) const {
+        friction = m_config.friction; rollFriction = m_config.rollFriction; restitution = m_config.restitution;
+    }
+    const btVector3& getFrom() const { return m_pair.getFrom(); }
+    const btVector3& getTo() const { return m_pair.getTo(); }
+    double getLength() const { return getFrom().distance(getTo()); }
+    double getMass() const;
+    btVector3 getCenterOfMass() const { return tgUtil::center(getFrom(), getTo()); }
+    btTransform getTransform() const { return tgUtil::getTransform(getFrom(), getTo()); }
+    bool containsNode(const btVector3& node) const { return getFrom() == node || getTo() == node; }
+    std::vector<btVector3> getContainedNodes() const;
+    btVector3 getConnectionPoint(const btVector3& referencePoint, const btVector3& destinationPoint, double rotation) const;
+    void appendShapes(const btVector3& bodyOrigin, std::vector<tgb_shape_desc>& out) const;
+    tgb_body_desc describeBody(std::vector<tgb_shape_desc>& shapes) const;
+    tgModel* createModel(tgWorldB200Impl& world);
+    const tgBox::Config& getConfig() const { return m_config; }
+private:
+    tgb_shape_desc shape() const;
+    tgPair m_pair;
+    tgBox::Config m_config;
+};
+
 /* A sphere at a tagged node (tgSphereInfo.cpp:45-200). */
 class tgSphereInfo : public tgRigidInfo {
 public:

@@ -391,6 +391,19 @@ tgRod::Config::Config(double r, double d, double f, double rf, double res) : rad
 tgRod::tgRod(tgWorldB200Impl* world, int body, double mass, const tgTags& tags, double length)
     : tgBaseRigid(world, body, mass, tags), m_length(length) {}
 
+tgBox::Config::Config(double w, double h, double d, double f, double rf, double res)
+    : width(w), height(h), density(d), friction(f), rollFriction(rf), restitution(res) {
+    if (density < 0.0) throw std::range_error("Negative density");
+    if (width < 0.0) throw std::range_error("Negative width");
+    if (height < 0.0) throw std::range_error("Negative height");
+    if (friction < 0.0) throw std::range_error("Negative friction");
+    if (rollFriction < 0.0) throw std::range_error("Negative roll friction");
+    if (restitution < 0.0) throw std::range_error("Negative restitution");
+    if (restitution > 1.0) throw std::range_error("Restitution > 1");
+}
+tgBox::tgBox(tgWorldB200Impl* world, int body, double mass, const tgTags& tags, double length)
+    : tgBaseRigid(world, body, mass, tags), m_length(length) {}
+
 tgSphere::Config::Config(double r, double d, double f, double rf, double res) : radius(r), density(d), friction(f), rollFriction(rf), restitution(res) {
     if (density < 0.0) throw std::range_error("Negative density");
     if (radius < 0.0) throw std::range_error("Negative radius");

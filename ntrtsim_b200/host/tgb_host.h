@@ -383,6 +383,24 @@ private:
     double m_length;
 };
 
+/* A box between two points (src/core/tgBox.h:43-118, tgBox.cpp:36-64): `width` and `height` are HALF extents across the axis */
+class tgBox : public tgBaseRigid {
+public:
+    struct Config {
+        Config(double w = 1.0, double h = 1.0, double d = 1.0, double f = 1.0, double rf = 0.0, double res = 0.2);
+        const double width;
+        const double height;
+        const double density;
+        const double friction;
+        const double rollFriction;
+        const double restitution;
+    };
+    tgBox(tgWorldB200Impl* world, int body, double mass, const tgTags& tags, double length);
+    double length() const { return m_length; }
+private:
+    double m_length;
+};
+
 /* A sphere at a node (src/core/tgSphere.h:52-88, tgSphere.cpp:36-72) */
 class tgSphere : public tgBaseRigid {
 public:

@@ -221,11 +221,11 @@ TensegrityModel::~TensegrityModel() {}
 
 void TensegrityModel::setup(tgWorld& world) {
     tgBuildSpec spec;
-    /* default builders for the tags rod / string / sphere, overwritten by the file's own builders (TensegrityModel.cpp:89-95;
-       the reference also installs a tgBoxInfo default for "box", which this build does not have) */
+    /* default builders for the tags rod / string / box / sphere, overwritten by the file's own builders (TensegrityModel.cpp:89-95) */
     const Yam emptyYam;
     addRodBuilder("tgRodInfo", "rod", emptyYam, spec);
     addBasicActuatorBuilder("tgBasicActuatorInfo", "string", emptyYam, spec);
+    addBoxBuilder("tgBoxInfo", "box", emptyYam, spec);
     addSphereBuilder("tgSphereInfo", "sphere", emptyYam, spec);
 
     tgStructure structure;
@@ -529,7 +529,8 @@ void TensegrityModel::addBuilders(tgBuildSpec& spec, const Yam& builders) {
         else if (builderClass == "tgBasicActuatorInfo") addBasicActuatorBuilder(builderClass, tagMatch, parameters, spec);
         else if (builderClass == "tgKinematicActuatorInfo") addKinematicActuatorBuilder(builderClass, tagMatch, parameters, spec);
         else if (builderClass == "tgSphereInfo") addSphereBuilder(builderClass, tagMatch, parameters, spec);
-        else if (builderClass == "tgBasicContactCableInfo" || builderClass == "tgKinematicContactCableInfo" || builderClass == "tgBoxInfo")
+        else if (builderClass == "tgBoxInfo") addBoxBuilder(builderClass, tagMatch, parameters, spec);
+        else if (builderClass == "tgBasicContactCableInfo" || builderClass == "tgKinematicContactCableInfo")
             throw std::invalid_argument("Unsupported builder class in this build: " + builderClass);
         else throw std::invalid_argument("Unsupported builder class: " + builderClass);
     }
@@ -578,6 +579,13 @@ void TensegrityModel::addKinematicActuatorBuilder(const std::string& builderClas
                                                                                        k["motor_friction"], k["motor_inertia"], k["back_drivable"] != 0.0,
                                                                                        k["history"] != 0.0, k["max_tension"], k["target_velocity"],
                                                                                        k["min_actual_length"], k["min_rest_length"], k["rotation"])));
+}
+void TensegrityModel::addBoxBuilder(const std::string& builderClass, const std::string& tagMatch, const Yam& parameters, tgBuildSpec& spec) {
+    std::map<std::string, double> bp;
+    bp["width"] = boxWidth; bp["height"] = boxHeight; bp["density"] = boxDensity; bp["friction"] = boxFriction;
+    bp["roll_friction"] = boxRollFriction; bp["restitution"] = boxRestitution;
+    overwrite(bp, parameters, builderClass);
+    spec.addBuilder(tagMatch, new tgBoxInfo(tgBox::Config(bp["width"], bp["height"], bp["density"], bp["friction"], bp["roll_friction"], bp["restitution"])));
 }
 void TensegrityModel::addSphereBuilder(const std::string& builderClass, const std::string& tagMatch, const Yam& parameters, tgBuildSpec& spec) {
     std::map<std::string, double> sp;

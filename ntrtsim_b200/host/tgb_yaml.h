@@ -3,7 +3,7 @@
  * files (resources/YamlStructures/...) with the key names, defaults, tag rules and error messages of
  * src/yamlbuilder/TensegrityModel.{h,cpp}.  The reference parses with yaml-cpp; this repo carries its own reader for the YAML subset
  * those files use (block mappings and sequences by indentation, flow sequences, plain / quoted scalars, comments).
- * Not built here: tgBoxInfo and contact-cable builders (std::invalid_argument says so).
+ * Not built here: contact-cable builders (std::invalid_argument says so).
  */
 #ifndef TGB_YAML_H
 #define TGB_YAML_H
@@ -52,6 +52,7 @@ public:
 
     /* defaults of TensegrityModel.h:69-187 */
     static constexpr double rodRadius = 0.5, rodDensity = 1.0, rodFriction = 1.0, rodRollFriction = 0.0, rodRestitution = 0.2;
+    static constexpr double boxWidth = 1.0, boxHeight = 1.0, boxDensity = 1.0, boxFriction = 1.0, boxRollFriction = 0.0, boxRestitution = 0.2;
     static constexpr double sphereRadius = 0.5, sphereDensity = 1.0, sphereFriction = 1.0, sphereRollFriction = 0.0, sphereRestitution = 0.2;
     static constexpr double stringStiffness = 1000.0, stringDamping = 10.0, stringPretension = 0.0, stringRadius = 1.0,
                             stringMotorFriction = 0.0, stringMotorInertia = 1.0, stringBackDrivable = 0, stringHistory = 0,
@@ -82,6 +83,7 @@ private:
     void addRodBuilder(const std::string& builderClass, const std::string& tagMatch, const Yam& parameters, tgBuildSpec& spec);
     void addBasicActuatorBuilder(const std::string& builderClass, const std::string& tagMatch, const Yam& parameters, tgBuildSpec& spec);
     void addKinematicActuatorBuilder(const std::string& builderClass, const std::string& tagMatch, const Yam& parameters, tgBuildSpec& spec);
+    void addBoxBuilder(const std::string& builderClass, const std::string& tagMatch, const Yam& parameters, tgBuildSpec& spec);
     void addSphereBuilder(const std::string& builderClass, const std::string& tagMatch, const Yam& parameters, tgBuildSpec& spec);
     void yamlContainsOnly(const Yam& yam, const std::string& structurePath, const std::vector<std::string>& keys);
     void yamlNoDuplicates(const Yam& yam, const std::string& structurePath);

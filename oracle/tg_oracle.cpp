@@ -117,6 +117,7 @@ static V3 vecMat(const V3& v, const M3& m) { return V3(m.col(0).dot(v), m.col(1)
 struct Shape {
     int kind; /* tgb_shape_kind */
     double radius, halfLen, margin;
+    double halfZ; /* box: third half extent */
     V3 pos;
     M3 rot;
 };
@@ -565,6 +566,36 @@ struct tgo_world {
                 else u = R.col(0);
                 V3 w = a.cross(u);
                 int count = 0;
+                if (s.kind == TGB_SHAPE_BOX) {
+                    /* btBoxShape: the eight corners of the margin-shrunk core box, the face pair along local Y first ("end caps"),
+                       around each face starting at the corner lowest along the normal; same distance test and cap of 4 */
+                    const V3 ex = R.col(0), ez = ex.cross(a);
+                    const double hx = s.radius - s.margin, hz = s.halfZ - s.margin;
+                    const V3 bu = n.dot(ex) > 0.0 ? -ex : ex, bw = n.dot(ez) > 0.0 ? -ez : ez;
+                    /* halves of the face diagonals: corner k = 0 is +d0 (lowest), 1 is +d1, 2 is -d0, 3 is -d1 */
+                    const V3 d0 = bu * hx + bw * hz, d1 = bw * hz - bu * hx;
+                    for (int e = 0; e < 2 && count < 4; ++e) {
+                        V3 ce = c + a * (e == 0 ? -hc : hc);
+                        for (int k = 0; k < 4 && count < 4; ++k) {
+                            V3 pc = ce + ((k == 0) ? d0 : (k == 1) ? d1 : (k == 2) ? -d0 : -d1);
+                            double dist = n.dot(pc) - ground.offset - s.margin;
+                            if (dist <= kBreakingThreshold) {
+                                Contact ct;
+                                ct.body = (int)bi;
+                                ct.n = n;
+                                ct.r = (pc - n * s.margin) - b.pos;
+                                ct.dist = dist;
+                                double mu = b.friction * ground.friction;
+                                if (mu < -10.0) mu = -10.0;
+                                if (mu > 10.0) mu = 10.0;
+                                ct.mu = mu;
+                                contacts.push_back(ct);
+                                ++count;
+                            }
+                        }
+                    }
+                    continue;
+                }
                 /* btSphereShape = a point with margin radius (rc = hc = 0): one contact point */
                 const int nEnds = s.kind == TGB_SHAPE_SPHERE ? 1 : 2, nDirs = s.kind == TGB_SHAPE_SPHERE ? 1 : 4;
                 for (int e = 0; e < nEnds && count < 4; ++e) {
@@ -767,6 +798,7 @@ int tgo_add_model_flat(tgo_world* w, const tgb_body_desc* bodies, int n_bodies, 
         Shape s;
         s.kind = shapes[i].kind;
         s.radius = shapes[i].radius; s.halfLen = shapes[i].half_length; s.margin = shapes[i].margin;
+        s.halfZ = shapes[i].half_extent_z;
         s.pos = V3(shapes[i].pos[0], shapes[i].pos[1], shapes[i].pos[2]);
         s.rot = M3::fromQuat(Q4(shapes[i].quat[0], shapes[i].quat[1], shapes[i].quat[2], shapes[i].quat[3]));
         w->shapes.push_back(s);

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.tgb_abi_version() == 2  # 2: tgb_cpg_desc gained cable_control and the PID gains
+    assert lib.tgb_abi_version() == 3  # 2: tgb_cpg_desc gained cable_control and the PID gains; 3: box shapes (tgb_shape_desc.half_extent_z)
 
 
 def test_create_fails_loudly_without_a_gpu():
@@ -217,6 +217,43 @@ def test_oracle_rod_rests_on_the_ground():
         ends = [s[b, 0:3] + axis * sh.half_length, s[b, 0:3] - axis * sh.half_length]
         lows.append(min(e[1] for e in ends) - sh.radius * math.sqrt(max(0.0, 1 - axis[1] ** 2)))
     assert min(lows) > 1.5 - 0.1 and min(lows) < 1.5 + 0.1, lows
+
+
+def test_oracle_box_comes_to_rest_on_a_face(tmp_path):
+    """A tgBox dropped slightly tilted: it lands on corners, tips onto its lowest face and stays there with
+    the face's four corners as the manifold, its centre one half extent (the smallest: height 0.5) above the surface."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_yaml import write
+    from ntrtsim_b200 import examples
+    path = write(tmp_path, "box.yaml", """
+nodes:
+  p0: [0, 2.4, -1.5]
+  p1: [0.2, 2.5, 1.5]
+pair_groups:
+  box:
+    - [p0, p1]
+builders:
+  box:
+    class: tgBoxInfo
+    parameters:
+      width: 0.8
+      height: 0.5
+      density: 0.3
+      friction: 0.7
+      restitution: 0.0
+""")
+    m = examples.build_yaml(path)
+    o = _oracle(m)
+    o.step(1e-3, 3000)
+    s = o.get_rod_state()
+    assert np.abs(s[0, 7:13]).max() < 0.05, s[0, 7:13]
+    assert o.num_contacts() == 4
+    # the local axes: Y along the pair, X = width, Z = height; at rest one of them points up
+    up = [abs(quat_rotate(s[0, 3:7], np.eye(3)[k])[1]) for k in range(3)]
+    k = int(np.argmax(up))
+    assert up[k] > 0.999
+    half = [0.8, 1.5, 0.5][k]
+    assert abs(s[0, 1] - (1.5 + half)) < 0.05, (s[0, 1], half)
 
 
 @pytest.mark.parametrize("kind,command", [("basic", 5.0), ("kinematic", -580.0)])

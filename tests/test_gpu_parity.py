@@ -745,3 +745,44 @@ def test_yaml_built_tower_matches_oracle(tmp_path, precision, steps):
         assert max(e) < 1e-7 and terr < 1e-7
     else:
         assert e[0] < F32_REL and e[1] < F32_REL and terr < 5 * F32_REL
+
+
+def box_cart_inputs(model, n_env, seed=88):
+    """Random yaw, a small random tilt about a horizontal axis (no two corners of a box at the same height: a tie at the contact
+    threshold would be decided by round-off) and a height that leaves the box 0.05 .. 0.3 above the ground."""
+    from helpers import quat_mul, quat_rotate
+    rods = random_poses(model, n_env, seed=seed, translate=0.5, lift=(-0.48, -0.3), yaw_only=True)
+    rng = np.random.default_rng(seed + 1)
+    ang = rng.uniform(0.01, 0.05, size=n_env) * rng.choice([-1.0, 1.0], size=n_env)
+    az = rng.uniform(0, 2 * np.pi, size=n_env)
+    tilt = np.stack([np.sin(ang / 2) * np.cos(az), np.zeros(n_env), np.sin(ang / 2) * np.sin(az), np.cos(ang / 2)], axis=1)
+    centre = rods[:, :, 0:3].mean(axis=1, keepdims=True)
+    tb = np.broadcast_to(tilt[:, None, :], (n_env, model.n_bodies, 4))
+    rods[:, :, 0:3] = quat_rotate(tb, rods[:, :, 0:3] - centre) + centre
+    rods[:, :, 3:7] = quat_mul(tb, rods[:, :, 3:7])
+    return rods
+
+
+@pytest.mark.parametrize("precision,steps", [("f64", 80), ("f32", 45)])
+def test_box_shapes_match_oracle(tmp_path, precision, steps):
+    """SURVEY.md 8(f) rank 2 (second part): tgBoxInfo bodies.  A box with two rods tied to it by four pretensioned strings, built
+    from a structure file; the box lands on a corner within the first 30..60 steps and tips onto an edge and a face while the strings
+    pull the rods in.  Corner contacts switching on and off make this the most sensitive scenario of the suite: a 1e-13 perturbation
+    of the oracle's input grows to 1e-12 after 60 steps, 2e-9 after 90 and 7e-4 after 120, hence the horizons."""
+    from test_yaml import BOX_CART, write
+    from ntrtsim_b200 import examples
+    model = examples.build_yaml(write(tmp_path, "cart.yaml", BOX_CART))
+    assert sum(1 for s in model.shapes if s.kind == 2) == 1
+    n_env = 48
+    rods = box_cart_inputs(model, n_env)
+    cab = tiled_cables(model, n_env)
+    rd, cd, st = device_rollout(model, rods, cab, steps, precision)
+    ro, co = oracle_rollout(model, rods, cab, steps)
+    e = rod_errors(rd, ro, 6.0 if precision == "f32" else 1.0)
+    terr = tension_rel_error(cd, co, floor=50.0)
+    print("box cart %s %d steps: rods %s tension %.2e, min height %.3f" % (precision, steps, e, terr, ro[:, :, 1].min()))
+    assert not st.any()
+    if precision == "f64":
+        assert max(e) < 1e-7 and terr < 1e-7
+    else:
+        assert e[0] < F32_REL and e[1] < F32_REL and terr < 5 * F32_REL

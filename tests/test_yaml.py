@@ -250,10 +250,76 @@ bond_groups:
         assert 4 - 2 * 0.2 - 0.125 - 1e-9 <= c.rest_length <= 4 - 0.125 + 1e-9
 
 
+BOX_CART = """
+# a box body hung between two rods by four strings; boxes and rods sharing no nodes stay separate bodies
+nodes:
+  a0: [-3, 4, -2]
+  a1: [-3, 4, 2]
+  c0: [3, 4, -2]
+  c1: [3, 4, 2]
+  p0: [0, 2.6, -1.5]
+  p1: [0, 2.6, 1.5]
+pair_groups:
+  rod:
+    - [a0, a1]
+    - [c0, c1]
+  box:
+    - [p0, p1]
+  string:
+    - [a0, p0]
+    - [a1, p1]
+    - [c0, p0]
+    - [c1, p1]
+builders:
+  rod:
+    class: tgRodInfo
+    parameters:
+      radius: 0.3
+      density: 0.4
+  box:
+    class: tgBoxInfo
+    parameters:
+      width: 0.8
+      height: 0.5
+      density: 0.3
+      friction: 0.7
+      restitution: 0.1
+  string:
+    class: tgBasicActuatorInfo
+    parameters:
+      stiffness: 500
+      pretension: 50
+"""
+
+
+def test_box_builder(tmp_path):
+    """tgBoxInfo: btBoxShape(width, length / 2, height) -- width and height are half extents --, mass of the full box, box inertia of
+    the half extents with margin (tgBoxInfo.cpp:100-133)."""
+    m = examples.build_yaml(write(tmp_path, "cart.yaml", BOX_CART))
+    assert (m.n_bodies, m.n_cables) == (3, 4)
+    box = [i for i, b in enumerate(m.bodies) if m.shapes[b.shape_begin].kind == 2]
+    assert len(box) == 1
+    bi = box[0]
+    b = m.bodies[bi]
+    s = m.shapes[b.shape_begin]
+    assert (s.radius, s.half_length, s.half_extent_z, s.margin) == (0.8, 1.5, 0.5, 0.04)
+    mass = float(np.float32(3.0 * 1.6 * 1.0 * 0.3))
+    assert abs(b.mass - mass) < 1e-12
+    lx, ly, lz = 1.6, 3.0, 1.0
+    want = np.array([ly * ly + lz * lz, lx * lx + lz * lz, lx * lx + ly * ly]) * mass / 12.0
+    assert np.allclose(list(b.inertia), want, rtol=1e-12)
+    assert (b.friction, b.restitution) == (0.7, 0.1)
+    # the strings end `width` off the box axis, on the side of the rods (tgBoxInfo::getConnectionPoint)
+    for c in m.cables:
+        end = np.array(c.local_b if c.body_b == bi else c.local_a)
+        assert abs(np.hypot(end[0], end[2]) - 0.8) < 1e-9
+
+
 @pytest.mark.parametrize("text,msg", [
     ("nodez:\n  a: [0, 0, 0]\n", "contains invalid key: nodez"),
     ("nodes:\n  a: [0, 0, 0]\n  a: [1, 0, 0]\n", "contains duplicate key: a"),
-    ("builders:\n  rod:\n    class: tgBoxInfo\n", "Unsupported builder class"),
+    ("builders:\n  rod:\n    class: tgBasicContactCableInfo\n", "Unsupported builder class in this build"),
+    ("builders:\n  rod:\n    class: tgFooInfo\n", "Unsupported builder class: tgFooInfo"),
     ("builders:\n  rod:\n    parameters:\n      radius: 1\n", "Builder class not supplied for tag: rod"),
     ("builders:\n  rod:\n    class: tgRodInfo\n    parameters:\n      radios: 1\n", "Unsupported tgRodInfo parameter: radios"),
     ("nodes:\n  a: [0, 0, 0]\npair_groups:\n  rod:\n    - [a, b]\n", "Node not found: b"),
