@@ -333,36 +333,50 @@ def main():
             ms_kernel.append(w.step_timed(model.dt, H, 1)[0])
         total_ms = sum(ms_kernel)
     else:
-        # N > 1: one device-side bracket around the K steps (L2 flushes included).  The all-gather of step k is issued
-        # asynchronously as soon as step k's scores exist and overlaps step k+1; it is waited for before its source buffer is
-        # rewritten (one step later) and, for the last step, before the bracket closes -- every collective completes inside
-        # the timed region.  Ranks therefore only have to stay within one step of each other instead of meeting after every step.
+        # N > 1: one device-side bracket around the K steps (L2 flushes included); the host queues everything and never blocks
+        # inside it.  Stream order per step k: [torch stream] wait for step k-1, flush L2; [world stream] wait for the flush,
+        # H steps, wait for all-gather k-1 (its source buffer is about to be rewritten), refresh the score buffer;
+        # [collective stream] wait for the refresh, all-gather k.  The all-gather of step k thus overlaps step k+1 and ranks
+        # only have to stay within one step of each other; every collective completes before the bracket closes.
         ws = torch.cuda.ExternalStream(w.stream_handle())
+        cs = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
         ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev_k0, ev_k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pending = None
+        ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        gather_done, step_done, keep = None, None, []
         ev_start.record(ws)
         for k in range(args.steps):
+            if step_done is not None:
+                cur.wait_event(step_done)
             flush.fill_(rank & 0xff)
             fl = torch.cuda.Event()
-            fl.record()
+            fl.record(cur)
             ws.wait_event(fl)
-            ev_k0.record(ws)
+            ev_k0[k].record(ws)
             w.step(model.dt, H)                       # asynchronous on the world's stream
-            ev_k1.record(ws)
-            if pending is not None:                   # gather k-1 has had the whole flush + launch to finish
-                pending.wait()
-                torch.cuda.current_stream().synchronize()
-            ptr, nbytes = w.scores_device_ptr()       # scores of step k (synchronises the world's stream)
-            ms_kernel.append(ev_k0.elapsed_time(ev_k1))
+            ev_k1[k].record(ws)
+            if gather_done is not None:
+                ws.wait_event(gather_done)
+            ptr, nbytes = w.scores_refresh_async()    # scores of step k, queued on the world's stream
+            step_done = torch.cuda.Event()
+            step_done.record(ws)
 
             class _Wrap(object):
                 __cuda_array_interface__ = {"shape": (n_env * 2,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-            local = torch.as_tensor(_Wrap(), device="cuda")
-            pending = dist.all_gather_into_tensor(scores_all, local, async_op=True)
-        pending.wait()
-        ev_end.record()
+            with torch.cuda.stream(cs):
+                cs.wait_event(step_done)
+                local = torch.as_tensor(_Wrap(), device="cuda")
+                work = dist.all_gather_into_tensor(scores_all, local, async_op=True)
+                work.wait()                           # orders the collective stream after NCCL's; does not block the host
+                gather_done = torch.cuda.Event()
+                gather_done.record(cs)
+            keep.append((local, work, fl))
+        ws.wait_event(gather_done)
+        ev_end.record(ws)
         ev_end.synchronize()
+        torch.cuda.synchronize()
+        ms_kernel = [a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)]
         total_ms = ev_start.elapsed_time(ev_end)
     barrier()
     t_wall = time.perf_counter() - t_wall0

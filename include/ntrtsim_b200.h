@@ -295,6 +295,10 @@ tgb_status tgb_get_scores(tgb_world* w, int32_t env_begin, int32_t env_count, do
 /* Device-resident score buffer (float[n_env][2]) for NCCL allgather without a host hop. */
 tgb_status tgb_scores_device_ptr(tgb_world* w, void** ptr, size_t* bytes);
 
+/* The same without synchronising: the refresh is queued on the world's stream (tgb_stream_handle); order the consumer after it with
+   an event on that stream.  For pipelines that overlap the all-gather of one episode chunk with the next chunk's steps. */
+tgb_status tgb_scores_refresh_async(tgb_world* w, void** device_ptr, size_t* bytes);
+
 /* Timing helper: run `reps` launches of n_steps each, bracketed by CUDA events on the world's stream;
    ms_out[reps]. Used by bench.py because torch.cuda.Event only sees torch's current stream. */
 tgb_status tgb_step_timed(tgb_world* w, double dt, int32_t n_steps, int32_t reps, float* ms_out);

@@ -68,7 +68,7 @@ ABI_SYMBOLS = [
     "tgb_finalize", "tgb_set_cpg_controller", "tgb_get_cpg_state", "tgb_num_bodies", "tgb_num_cables", "tgb_num_envs", "tgb_set_rod_state", "tgb_get_rod_state",
     "tgb_set_cable_state", "tgb_get_cable_obs", "tgb_set_controller", "tgb_set_control_input", "tgb_step", "tgb_step_world", "tgb_step_models", "tgb_sync",
     "tgb_rollout_host", "tgb_track_max_tension", "tgb_get_max_tension", "tgb_get_time", "tgb_get_status", "tgb_mark_episode_start", "tgb_get_scores",
-    "tgb_scores_device_ptr", "tgb_step_timed", "tgb_launch_count", "tgb_launch_geometry", "tgb_set_lanes_per_env",
+    "tgb_scores_device_ptr", "tgb_scores_refresh_async", "tgb_step_timed", "tgb_launch_count", "tgb_launch_geometry", "tgb_set_lanes_per_env",
     "tgb_set_block_threads", "tgb_set_wide_layout", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
 ]
 
@@ -126,6 +126,7 @@ def load():
     lib.tgb_mark_episode_start.argtypes = [_vp]
     lib.tgb_get_scores.argtypes = [_vp, _i32, _i32, _vp]
     lib.tgb_scores_device_ptr.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]
+    lib.tgb_scores_refresh_async.argtypes = [_vp, C.POINTER(_vp), C.POINTER(C.c_size_t)]
     lib.tgb_step_timed.argtypes = [_vp, C.c_double, _i32, _i32, C.POINTER(C.c_float)]
     lib.tgb_launch_count.argtypes = [_vp, C.POINTER(C.c_int64)]
     lib.tgb_launch_geometry.argtypes = [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]

@@ -982,6 +982,15 @@ tgb_status tgb_scores_device_ptr(tgb_world* w, void** ptr, size_t* bytes) {
     return TGB_OK;
 }
 
+tgb_status tgb_scores_refresh_async(tgb_world* w, void** ptr, size_t* bytes) {
+    TGB_NEED_FINAL(w);
+    if (!ptr || !bytes) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    TGB_CUDA(w->ops->com(w->ioArgs(0, w->cfg.n_env), 1, nullptr, w->d_scores, w->stream));
+    *ptr = w->d_scores;
+    *bytes = (size_t)w->cfg.n_env * 2 * sizeof(float);
+    return TGB_OK;
+}
+
 tgb_status tgb_step_timed(tgb_world* w, double dt, int32_t n_steps, int32_t reps, float* ms_out) {
     TGB_NEED_FINAL(w);
     if (!(dt > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "dt is not positive");

@@ -15,6 +15,15 @@ namespace tgb {
 
 TGB_D float tsqrt(float x) { return sqrtf(x); }
 TGB_D double tsqrt(double x) { return sqrt(x); }
+/* Square root without the library routine's special-case branch (it ends a basic block, which keeps ptxas from overlapping the
+   dependent chains of independent cables): MUFU.RSQ, one Newton step, zero handled by a select; within 1 ulp of sqrtf. */
+TGB_D float tsqrtNoBranch(float x) {
+    const float r = rsqrtf(x);
+    const float s = x * r;
+    const float t = fmaf(fmaf(-s, s, x), 0.5f * r, s);
+    return x > 0.0f ? t : 0.0f;
+}
+TGB_D double tsqrtNoBranch(double x) { return sqrt(x); }
 TGB_D float tabs(float x) { return fabsf(x); }
 TGB_D double tabs(double x) { return fabs(x); }
 TGB_D float tsin(float x) { return sinf(x); }

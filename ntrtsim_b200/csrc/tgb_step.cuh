@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 q.ra = Ba * la; q.rb = Bb * lb;
                 const V3<T> p1 = q.ra + xa, p2 = q.rb + xb;
                 q.dist = p2 - p1;
-                q.L = q.dist.length();
+                q.L = kFast ? tsqrtNoBranch(q.dist.length2()) : q.dist.length();
 #if TGB_VEC_CS
                 T cs[TGB_NCS];
                 {

@@ -192,6 +192,12 @@ class BatchedWorld(object):
         capi.check(self._lib.tgb_scores_device_ptr(self._h, C.byref(p), C.byref(nbytes)))
         return p.value, nbytes.value
 
+    def scores_refresh_async(self):
+        """scores_device_ptr without the synchronisation: the refresh is queued on the world's stream"""
+        p, nbytes = C.c_void_p(), C.c_size_t()
+        capi.check(self._lib.tgb_scores_refresh_async(self._h, C.byref(p), C.byref(nbytes)))
+        return p.value, nbytes.value
+
     def stream_handle(self):
         """the CUDA stream (cudaStream_t as an integer) all work of this world is issued on"""
         p = C.c_void_p()
