@@ -786,3 +786,99 @@ def test_box_shapes_match_oracle(tmp_path, precision, steps):
         assert max(e) < 1e-7 and terr < 1e-7
     else:
         assert e[0] < F32_REL and e[1] < F32_REL and terr < 5 * F32_REL
+
+
+# ------------------------------------------------------------------------------------------------ sizes and edge cases
+def tall_tower_yaml(n_prisms):
+    names = "/".join("p%d" % (i + 1) for i in range(n_prisms))
+    return """
+substructures:
+  %s:
+    path: base/Prism.yaml
+    offset: [0, 12, 0]
+    translation: [0, 3, 0]
+bond_groups:
+  prism_string:
+    %s/node_edge:
+      - [top1, bottom1/bottom2]
+      - [top2, bottom2/bottom3]
+      - [top3, bottom3/bottom1]
+""" % (names, names)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_largest_supported_structure(tmp_path, precision):
+    """32 rigid bodies per environment is the limit of the step kernel (one lane per body): ten bonded prisms = 30 rods and 90
+    strings through the YAML front-end, one warp per environment, environment counts that do not fill the last CTA."""
+    from test_yaml import BASE_PRISM, write
+    from ntrtsim_b200 import examples
+    write(tmp_path, "base/Prism.yaml", BASE_PRISM)
+    model = examples.build_yaml(write(tmp_path, "tower10.yaml", tall_tower_yaml(10)))
+    assert (model.n_bodies, model.n_cables) == (30, 90)
+    n_env, steps = 5, 60
+    rods = random_poses(model, n_env, seed=3, translate=0.3, lift=(-1.2, 0.0), yaw_only=True)
+    cab = tiled_cables(model, n_env)
+    rd, cd, st = device_rollout(model, rods, cab, steps, precision)
+    ro, co = oracle_rollout(model, rods, cab, steps)
+    e = rod_errors(rd, ro, 90.0 if precision == "f32" else 1.0)
+    terr = tension_rel_error(cd, co, floor=100.0)
+    print("tower of 10 %s: rods %s tension %.2e" % (precision, e, terr))
+    assert not st.any()
+    if precision == "f64":
+        assert max(e) < 1e-7 and terr < 1e-7
+    else:
+        assert e[0] < F32_REL and e[1] < F32_REL and terr < 5 * F32_REL
+    # one body more than a warp has lanes is refused, loudly
+    too_big = examples.build_yaml(write(tmp_path, "tower11.yaml", tall_tower_yaml(11)))
+    with pytest.raises(capi.TgbError, match="more than 32 rigid bodies"):
+        nt.BatchedWorld(too_big, 1)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_single_body_without_cables_and_single_environment(tmp_path, precision):
+    """Degenerate sizes: one compound body (three rods welded at a node, no cables at all), one environment, and a zero-step call."""
+    from test_yaml import write
+    from ntrtsim_b200 import examples
+    model = examples.build_yaml(write(tmp_path, "tripod.yaml", """
+nodes:
+  hub: [0, 4, 0]
+  f1: [2, 2.2, 0]
+  f2: [-1, 2.2, 1.7]
+  f3: [-1, 2.3, -1.7]
+pair_groups:
+  rod:
+    - [hub, f1]
+    - [hub, f2]
+    - [hub, f3]
+builders:
+  rod:
+    class: tgRodInfo
+    parameters:
+      radius: 0.2
+      density: 0.5
+"""))
+    assert (model.n_bodies, model.n_cables, len(model.shapes)) == (1, 0, 3)
+    rods = model.initial_rod_state()[None].copy()
+    cab = np.zeros((1, 0, 2))
+    w = nt.BatchedWorld(model, 1, precision=precision)
+    try:
+        w.set_rod_state(rods)
+        w.step(model.dt, 0)  # a zero-step call changes nothing
+        w.sync()
+        before = w.get_rod_state()
+        with pytest.raises(capi.TgbError):
+            w.step(model.dt, -1)
+        w.step(model.dt, 150)  # impact at step ~100, at rest by 160; the resting chatter amplifies round-off from there on
+        w.sync()
+        rd = w.get_rod_state()
+        assert w.get_cable_obs().shape == (1, 0, capi.CABLE_OBS_DOUBLES)
+    finally:
+        w.close()
+    assert np.allclose(before, rods, atol=1e-6 if precision == "f32" else 0)
+    ro, _ = oracle_rollout(model, rods, cab, 150)
+    e = rod_errors(rd, ro, 4.0 if precision == "f32" else 1.0)
+    print("tripod %s: %s, height %.3f" % (precision, e, ro[0, 0, 1]))
+    if precision == "f64":
+        assert max(e) < 1e-7
+    else:
+        assert e[0] < 5 * F32_REL and e[1] < 5 * F32_REL   # 50 steps of impact and a three-point stance in single precision
