@@ -173,6 +173,8 @@ def load_host():
     h.tgh_tetraspine_param_row.argtypes = [_vp, _vp, C.c_int, _vp]
     h.tgh_flemons_cpg.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _vp, _vp, _vp, _vp, _vp]
     h.tgh_flemons_param_row.argtypes = [_vp, _vp, _vp, C.c_int, _vp]
+    h.tgh_quaternion_between.argtypes = [_vp, _vp, _vp, _vp, _vp]
+    h.tgh_quaternion_between.restype = None
     h.tgh_yaml_to_json.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     h.tgh_yaml_to_json.restype = C.c_int
     _host = h

@@ -317,6 +317,15 @@ int tgh_tetraspine_param_row(const double* node_actions, const double* edge_acti
     return tgbSpineScaleEdgeActions(edge_actions, n_edge, cfg, row + 2);
 }
 
+/* tgUtil::getQuaternionBetween (src/tgcreator/tgUtil.h:199-238) and btVector3::rotate, for the test that mirrors
+   test/tgcreator/tgUtil_test.cpp:72-97.  q_out = (x, y, z, w); rotated_out = v rotated by that quaternion's axis and angle. */
+void tgh_quaternion_between(const double* a, const double* b, const double* v, double* q_out, double* rotated_out) {
+    const btQuaternion q = tgUtil::getQuaternionBetween(btVector3(a[0], a[1], a[2]), btVector3(b[0], b[1], b[2]));
+    q_out[0] = q.x(); q_out[1] = q.y(); q_out[2] = q.z(); q_out[3] = q.w();
+    const btVector3 r = btVector3(v[0], v[1], v[2]).rotate(q.getAxis(), q.getAngle());
+    rotated_out[0] = r.x(); rotated_out[1] = r.y(); rotated_out[2] = r.z();
+}
+
 /* The YAML reader's view of a document as JSON (all scalars as strings, null as null): lets the tests compare the reader with a full
    YAML parser on the structure-file subset.  Returns the length needed (without the terminator), or -1 with tgh_last_error set. */
 static void yamToJson(const Yam& y, std::string& out) {

@@ -131,6 +131,27 @@ def _oracle(model, rods=None, cab=None):
     return o
 
 
+def test_tgutil_quaternion_between_opposite_vectors():
+    """test/tgcreator/tgUtil_test.cpp:72-97 (tgUtilTest.testQuaternion) on the host API's tgUtil: rotating by the quaternion between two
+    opposite vectors maps one onto the other, for the up / down pair btTransforms are defined against and for an arbitrary pair;
+    the reference's pass mark is btVector3::fuzzyZero, |d|^2 < SIMD_EPSILON (double build: DBL_EPSILON)."""
+    h = capi.load_host()
+
+    def between(a, b, v):
+        a, b, v = (np.array(x, dtype=np.float64) for x in (a, b, v))
+        q, r = np.zeros(4), np.zeros(3)
+        vp = C.c_void_p
+        h.tgh_quaternion_between(a.ctypes.data_as(vp), b.ctypes.data_as(vp), v.ctypes.data_as(vp), q.ctypes.data_as(vp), r.ctypes.data_as(vp))
+        return q, r
+    up, down = (0.0, 1.0, 0.0), (0.0, -1.0, 0.0)
+    q, result = between(down, up, down)
+    assert np.sum((np.array(up) - result) ** 2) < np.finfo(np.float64).eps
+    assert abs(np.linalg.norm(q) - 1.0) < 1e-15
+    start, end = (1.0, -1.0, 2.0), (-1.0, 1.0, -2.0)
+    q, result = between(start, end, end)
+    assert np.sum((np.array(start) - result) ** 2) < np.finfo(np.float64).eps
+
+
 def test_oracle_step_rejects_nonpositive_dt():
     o = _oracle(nt.build_example("3_prism"))
     assert o.step(0.0, 1) == capi.TGB_ERR_INVALID_ARGUMENT and o.step(-1.0, 1) == capi.TGB_ERR_INVALID_ARGUMENT
