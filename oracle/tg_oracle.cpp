@@ -164,6 +164,7 @@ struct Contact {
     /* friction row */
     V3 t, rxt, angT;
     double invDiagT, rhsT, lamT, mu;
+    double restitution; /* combined restitution of the pair (body x ground, or body x obstacle) */
 };
 
 /* Bullet 2.82 btContactSolverInfo defaults (tgWorldBulletPhysicsImpl.cpp:134-146 leaves them alone). */
@@ -545,8 +546,108 @@ struct tgo_world {
     /* Analytic cylinder-vs-plane manifold: per cylinder end cap, four rim points of the margin-shrunk core
        cylinder, starting at the rim point deepest along -n; a point is a contact when its distance (after both
        margins) is within the contact breaking threshold; at most 4 per cylinder (btPersistentManifold cap). */
+    /* Signed distance of a point to an oriented box (centre co, rotation Ro, half extents h) and the outward direction at the
+       closest surface point: outside, the vector from the closest point; inside, the axis of the nearest face (lowest index on
+       a tie). */
+    static double boxDistance(const V3& p, const V3& co, const M3& Ro, const V3& h, V3& nOut) {
+        const V3 d = p - co;
+        const double q[3] = {Ro.col(0).dot(d), Ro.col(1).dot(d), Ro.col(2).dot(d)};
+        const double hh[3] = {h.x, h.y, h.z};
+        double a[3], o[3], len2 = 0.0;
+        for (int i = 0; i < 3; ++i) {
+            a[i] = std::fabs(q[i]) - hh[i];
+            o[i] = a[i] > 0.0 ? a[i] : 0.0;
+            len2 += o[i] * o[i];
+        }
+        double nl[3] = {0.0, 0.0, 0.0}, sd;
+        if (len2 > 0.0) {
+            sd = std::sqrt(len2);
+            for (int i = 0; i < 3; ++i) nl[i] = (q[i] < 0.0 ? -o[i] : o[i]) / sd;
+        } else {
+            int k = 0;
+            if (a[1] > a[k]) k = 1;
+            if (a[2] > a[k]) k = 2;
+            sd = a[k];
+            nl[k] = q[k] < 0.0 ? -1.0 : 1.0;
+        }
+        nOut = Ro.col(0) * nl[0] + Ro.col(1) * nl[1] + Ro.col(2) * nl[2];
+        return sd;
+    }
+
+    /* Static obstacles (tgCraterDeep, tgBlockField, ... are static tgBox bodies): sample points of every
+       dynamic shape against every box shape of every static body.  Cylinder: five stations along the axis (both end caps, the
+       quarter points and the middle), at each the surface point of the core cylinder that faces the box; sphere: its centre;
+       box: its eight core corners.  A point is a contact when its distance (after the shape's margin; the obstacle counts with
+       its full half extents) is within the contact breaking threshold; at most 4 per pair of shapes, in sampling order. */
+    void generateObstacleContacts() {
+        for (size_t oi = 0; oi < bodies.size(); ++oi) {
+            const Body& ob = bodies[oi];
+            if (ob.invMass != 0.0) continue;
+            for (int osi = ob.shapeBegin; osi < ob.shapeBegin + ob.shapeCount; ++osi) {
+                const Shape& os = shapes[osi];
+                if (os.kind != TGB_SHAPE_BOX) continue;
+                const M3 Ro = ob.basis * os.rot;
+                const V3 co = ob.basis * os.pos + ob.pos;
+                const V3 h(os.radius, os.halfLen, os.halfZ);
+                for (size_t bi = 0; bi < bodies.size(); ++bi) {
+                    Body& b = bodies[bi];
+                    if (b.invMass == 0.0) continue;
+                    for (int si = b.shapeBegin; si < b.shapeBegin + b.shapeCount; ++si) {
+                        const Shape& s = shapes[si];
+                        const M3 R = b.basis * s.rot;
+                        const V3 c = b.basis * s.pos + b.pos;
+                        const V3 a = R.col(1);
+                        const double rc = s.radius - s.margin, hc = s.halfLen - s.margin;
+                        const int nPoints = s.kind == TGB_SHAPE_SPHERE ? 1 : s.kind == TGB_SHAPE_BOX ? 8 : 5;
+                        int count = 0;
+                        for (int k = 0; k < nPoints && count < 4; ++k) {
+                            V3 pc;
+                            if (s.kind == TGB_SHAPE_SPHERE) {
+                                pc = c;
+                            } else if (s.kind == TGB_SHAPE_BOX) {
+                                const V3 ex = R.col(0), ez = ex.cross(a);
+                                const double hx = rc, hz = s.halfZ - s.margin;
+                                pc = c + ex * ((k & 1) ? hx : -hx) + a * ((k & 2) ? hc : -hc) + ez * ((k & 4) ? hz : -hz);
+                            } else {
+                                const V3 pa = c + a * (hc * (0.5 * (double)(k - 2)));
+                                V3 g;
+                                boxDistance(pa, co, Ro, h, g);
+                                const V3 radial = g - a * a.dot(g);
+                                const double rl = radial.length();
+                                pc = rl > 1e-9 ? pa - radial * (rc / rl) : pa;
+                            }
+                            V3 n;
+                            const double dist = boxDistance(pc, co, Ro, h, n) - s.margin;
+                            if (dist <= kBreakingThreshold) {
+                                Contact ct;
+                                ct.body = (int)bi;
+                                ct.n = n;
+                                ct.r = (pc - n * s.margin) - b.pos;
+                                ct.dist = dist;
+                                double mu = b.friction * ob.friction;
+                                if (mu < -10.0) mu = -10.0;
+                                if (mu > 10.0) mu = 10.0;
+                                ct.mu = mu;
+                                ct.restitution = b.restitution * ob.restitution;
+                                contacts.push_back(ct);
+                                ++count;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
     void generateContacts() {
         contacts.clear();
+        generateGroundContacts();
+        generateObstacleContacts();
+        /* rows are solved body by body in the device kernel: keep the same order here (stable: ground first, then obstacles) */
+        std::stable_sort(contacts.begin(), contacts.end(), [](const Contact& x, const Contact& y) { return x.body < y.body; });
+    }
+
+    void generateGroundContacts() {
         if (ground.kind == TGB_GROUND_EMPTY) return;
         const V3 n(ground.normal[0], ground.normal[1], ground.normal[2]);
         for (size_t bi = 0; bi < bodies.size(); ++bi) {
@@ -589,6 +690,7 @@ struct tgo_world {
                                 if (mu < -10.0) mu = -10.0;
                                 if (mu > 10.0) mu = 10.0;
                                 ct.mu = mu;
+                                ct.restitution = b.restitution * ground.restitution;
                                 contacts.push_back(ct);
                                 ++count;
                             }
@@ -614,6 +716,7 @@ struct tgo_world {
                             if (mu < -10.0) mu = -10.0;
                             if (mu > 10.0) mu = 10.0;
                             ct.mu = mu;
+                            ct.restitution = b.restitution * ground.restitution;
                             contacts.push_back(ct);
                             ++count;
                         }
@@ -662,7 +765,7 @@ struct tgo_world {
             c.invDiagN = 1.0 / denom;
             V3 vel = b.linvel + b.angvel.cross(c.r);
             double relVel = c.n.dot(vel);
-            double combinedRestitution = b.restitution * ground.restitution;
+            double combinedRestitution = c.restitution;
             double restitution = combinedRestitution * -relVel;
             if (restitution <= 0.0) restitution = 0.0;
             /* friction direction from the lateral velocity, else btPlaneSpace1 */

@@ -277,6 +277,34 @@ builders:
     assert abs(s[0, 1] - (1.5 + half)) < 0.05, (s[0, 1], half)
 
 
+def test_oracle_bodies_rest_on_a_static_obstacle(tmp_path):
+    """Static tgBox obstacles (tgCraterDeep / tgBlockField are built from them): a rod and a ball dropped on a
+    block come to rest on its top face (y = 3.5) instead of falling through to the ground, the block itself never moves, and a
+    rod dropped beside the block slides off its side face and ends on the ground without entering the block."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_yaml import OBSTACLE_SCENE, write
+    from ntrtsim_b200 import examples
+    m = examples.build_yaml(write(tmp_path, "scene.yaml", OBSTACLE_SCENE))
+    static = [i for i, b in enumerate(m.bodies) if b.mass == 0.0]
+    assert len(static) == 1 and m.shapes[m.bodies[static[0]].shape_begin].kind == 2
+    moving = [i for i in range(m.n_bodies) if i not in static]
+    rods = [i for i in moving if m.shapes[m.bodies[i].shape_begin].kind == 0]
+    balls = [i for i in moving if m.shapes[m.bodies[i].shape_begin].kind == 1]
+    assert (len(rods), len(balls)) == (2, 1)
+    o = _oracle(m)
+    start = o.get_rod_state().copy()
+    o.step(1e-3, 3000)
+    s = o.get_rod_state()
+    assert np.array_equal(s[static[0]], start[static[0]])
+    top_rod = max(rods, key=lambda i: start[i, 1])
+    side_rod = min(rods, key=lambda i: start[i, 1])
+    assert abs(s[top_rod, 1] - (3.5 + 0.2)) < 0.03, s[top_rod, 0:3]          # lying on the top face
+    assert abs(s[balls[0], 1] - (3.5 + 0.5)) < 0.03, s[balls[0], 0:3]        # resting on the top face
+    assert np.abs(s[[top_rod, balls[0]], 7:13]).max() < 0.05
+    assert s[side_rod, 1] < 2.5 and abs(s[side_rod, 2]) > 1.0 + 0.2 - 0.05, s[side_rod, 0:3]  # beside the block, on the ground
+    assert np.isfinite(s).all()
+
+
 @pytest.mark.parametrize("kind,command", [("basic", 5.0), ("kinematic", -580.0)])
 def test_oracle_motor_timestep_independence(kind, command):
     """MotorTimestep_test.cpp:81-215: 1000 steps @1e-3 vs 500 @2e-3 vs 5000 @2e-4: rest length equal within 0.03."""

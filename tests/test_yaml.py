@@ -292,6 +292,49 @@ builders:
 """
 
 
+OBSTACLE_SCENE = """
+# a static block (density 0: tgBoxInfo like the obstacles of src/models/obstacles) lying on the ground, y 1.5 .. 3.5, x -3 .. 3, z -1 .. 1;
+# above it a rod parallel to the block, a ball, and a short rod that will hit the block's side face
+nodes:
+  k0: [-3, 2.5, 0]
+  k1: [3, 2.5, 0]
+  r0: [-2, 4.0, 0.3]
+  r1: [2, 4.1, 0.3]
+  ball: [0.5, 4.6, -0.4]
+  s0: [0, 2.4, 1.9]
+  s1: [0, 3.4, 3.2]
+pair_groups:
+  block:
+    - [k0, k1]
+  rod:
+    - [r0, r1]
+    - [s0, s1]
+builders:
+  block:
+    class: tgBoxInfo
+    parameters:
+      width: 1.0
+      height: 1.0
+      density: 0
+      friction: 0.8
+      restitution: 0.0
+  rod:
+    class: tgRodInfo
+    parameters:
+      radius: 0.2
+      density: 0.5
+      friction: 0.9
+      restitution: 0.0
+  ball:
+    class: tgSphereInfo
+    parameters:
+      radius: 0.5
+      density: 0.5
+      friction: 0.9
+      restitution: 0.0
+"""
+
+
 def test_box_builder(tmp_path):
     """tgBoxInfo: btBoxShape(width, length / 2, height) -- width and height are half extents --, mass of the full box, box inertia of
     the half extents with margin (tgBoxInfo.cpp:100-133)."""
