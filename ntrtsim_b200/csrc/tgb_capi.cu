@@ -49,7 +49,7 @@ struct tgb_world {
     bool finalized = false;
     const tgb_ops* ops = nullptr;
     size_t scalarBytes = 4;
-    int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0, maxInc = 0;
+    int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0, maxInc = 0, nObst = 0, modelObstOff = 0;
     int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0, wideMode = -1;
     mutable int wideCtasPerSm[2] = {-1, -1}; /* by controller class (simple, sine); -1 = not asked yet */
     int smCount = 148;
@@ -148,7 +148,8 @@ bool rangeOk(const tgb_world* w, int envBegin, int envCount) {
 }
 
 template <typename T>
-void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vector<int>& ints, int& nInc, int& crecOff, int& cirecOff, int& maxInc) {
+void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vector<int>& ints, int& nInc, int& crecOff, int& cirecOff, int& maxInc,
+               int& nObst, int& obstOff) {
     const int R = w->R, C = w->C, S = w->S;
     crecOff = (TGB_NBF * R + TGB_NSF * S + TGB_NCF * C + 3) & ~3;
     std::vector<T> t((size_t)crecOff + (size_t)TGB_CREC * C, T(0));
@@ -187,6 +188,7 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         bt[BF_MU * R + b] = (T)mu;
         bt[BF_RESTITUTION * R + b] = (T)d.restitution;
         bt[BF_MASS * R + b] = (T)d.mass;
+        bt[BF_FRICTION * R + b] = (T)d.friction;
         bi[BI_SHAPE_BEGIN * R + b] = d.shape_begin;
         bi[BI_SHAPE_COUNT * R + b] = d.shape_count;
         bi[BI_INC_BEGIN * R + b] = incPos;
@@ -242,6 +244,14 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         int* ri = ints.data() + cirecOff + (size_t)TGB_CIREC * c;
         ri[0] = d.body_a; ri[1] = d.body_b; ri[2] = d.actuator | (d.backdrivable ? 1 << 8 : 0); ri[3] = slotA[c] | (slotB[c] << 16);
     }
+    /* static obstacles: the box shapes of static bodies (tgBoxInfo with density 0, src/models/obstacles) */
+    obstOff = (int)ints.size();
+    nObst = 0;
+    for (int b = 0; b < R; ++b) {
+        if (w->bodies[b].mass != 0.0) continue;
+        for (int s = w->bodies[b].shape_begin; s < w->bodies[b].shape_begin + w->bodies[b].shape_count; ++s)
+            if (w->shapes[s].kind == TGB_SHAPE_BOX) { ints.push_back(b); ints.push_back(s); ++nObst; }
+    }
     tbytes.resize(t.size() * sizeof(T));
     std::memcpy(tbytes.data(), t.data(), tbytes.size());
 }
@@ -251,7 +261,7 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
    SUPERball environments per SM, ~1800 per B200; measured at 4096 environments: 5.8e8 env-steps/s against 9.6e8, the grid then runs
    in 2.3 waves).  Automatic choice: wide when the whole grid is resident.  tgb_set_wide_layout / TGB_WIDE=0|1 override. */
 bool wideLayout(const tgb_world* w) {
-    if (w->ctrlKind == TGB_CTRL_CPG_IMPEDANCE) return false;
+    if (w->ctrlKind == TGB_CTRL_CPG_IMPEDANCE || w->nObst > 0) return false;
     if (w->lanes != 4 && w->lanes != 8) return false;
     if (w->wideMode >= 0) return w->wideMode != 0;
     static const char* envWide = std::getenv("TGB_WIDE");
@@ -292,6 +302,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.ground_kind = w->ground.kind;
     a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
     a.model_crec_off = w->modelCrecOff; a.model_cirec_off = w->modelCirecOff;
+    a.n_obst = w->nObst; a.model_obst_off = w->modelObstOff;
     a.dt = dt;
     a.gn[0] = w->ground.normal[0]; a.gn[1] = w->ground.normal[1]; a.gn[2] = w->ground.normal[2];
     a.goff = w->ground.offset;
@@ -503,8 +514,10 @@ tgb_status tgb_finalize(tgb_world* w) {
 
     std::vector<unsigned char> tbytes;
     std::vector<int> ints;
-    if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc);
-    else packModel<float>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc);
+    if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff);
+    else packModel<float>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff);
+    /* obstacle contacts share the rows: room for those of up to three obstacles touched at once */
+    w->capContacts *= 1 + std::min(w->nObst, 3);
     w->modelTWords = (int)(tbytes.size() / w->scalarBytes);
     w->modelIWords = (int)ints.size();
     TGB_CUDA(cudaMalloc(&w->d_model_t, std::max<size_t>(tbytes.size(), 16)));

@@ -27,7 +27,7 @@
 #include <stdint.h>
 
 /* body T-fields */
-enum { BF_INVMASS = 0, BF_GFY, BF_INVIX, BF_INVIY, BF_INVIZ, BF_IX, BF_IY, BF_IZ, BF_MU, BF_RESTITUTION, BF_MASS, TGB_NBF };
+enum { BF_INVMASS = 0, BF_GFY, BF_INVIX, BF_INVIY, BF_INVIZ, BF_IX, BF_IY, BF_IZ, BF_MU, BF_RESTITUTION, BF_MASS, BF_FRICTION, TGB_NBF };
 /* body int-fields */
 enum { BI_SHAPE_BEGIN = 0, BI_SHAPE_COUNT, BI_INC_BEGIN, BI_INC_COUNT, BI_GYRO, TGB_NBI };
 /* shape T-fields */
@@ -53,7 +53,9 @@ enum { TGB_NBS = 13 };
 /* per-contact solver row words kept in shared memory */
 enum {
     CT_RXN = 0, CT_ANGN = 3, CT_INVDIAGN = 6, CT_RHSN, CT_RHSPEN, CT_LAMN, CT_LAMPUSH, CT_T = 11, CT_RXT = 14, CT_ANGT = 17,
-    CT_INVDIAGT = 20, CT_RHST, CT_LAMT, TGB_NCT
+    CT_INVDIAGT = 20, CT_RHST, CT_LAMT, TGB_NCT,
+    /* worlds with static obstacles: the row's own normal and friction coefficient behind the common part */
+    CT_NRM = TGB_NCT, CT_MU = CT_NRM + 3, TGB_NCT_OBST = CT_MU + 2 /* odd row stride: rows of neighbouring lanes on distinct banks */
 };
 /* frame doubles */
 enum { FR_O = 0, FR_V = 3, FR_CTRLTIME = 6, FR_SPARE = 7, TGB_NFR = 8 };
@@ -89,6 +91,7 @@ struct tgb_step_args {
     int ground_kind;
     int model_t_words, model_i_words;
     int model_crec_off, model_cirec_off; /* word offsets of the per-cable records inside model_t / model_i */
+    int n_obst, model_obst_off;          /* static obstacles: n_obst pairs (static body, its box shape) at this word offset of model_i */
     double dt;
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */
     double ground_restitution;

@@ -10,12 +10,12 @@ namespace {
 
 typedef TGB_SCALAR scalar_t;
 
-template <int LPE, bool GROUND>
+template <int LPE, bool GROUND, bool OBST = false>
 cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
     const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, threads, sizeof(scalar_t));
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND>,
+        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
@@ -23,7 +23,7 @@ cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
     const int groupsPerBlock = threads / LPE;
     const int grid = (a.n_env - a.env_begin + groupsPerBlock - 1) / groupsPerBlock;
     if (grid <= 0) return cudaSuccess;
-    tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND><<<grid, threads, smem, s>>>(a);
+    tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST><<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -74,6 +74,11 @@ cudaError_t launch(const tgb_step_args& a, int threads, cudaStream_t s, int* wid
         }
     }
     if (a.wide) return cudaErrorInvalidValue;
+    if (a.n_obst > 0) {
+        /* worlds with static obstacles: own instantiation (rows with normals); not compiled for the CPG class */
+        if constexpr (TGB_STEP_CLASS != tgb::TGB_CLASS_CPG) return launch_impl<LPE, true, true>(a, threads, s);
+        return cudaErrorNotSupported;
+    }
     if (a.ground_kind == TGB_GROUND_EMPTY) return launch_impl<LPE, false>(a, threads, s);
     return launch_impl<LPE, true>(a, threads, s);
 }

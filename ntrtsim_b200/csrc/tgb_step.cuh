@@ -213,6 +213,103 @@ __device__ __forceinline__ void pgsSharedRows(T* ct, int rowStride, int nc, int 
 #undef CTG
 }
 
+/* The same projected Gauss-Seidel for worlds with static obstacles: every row carries its own normal and friction coefficient
+   (CT_NRM, CT_MU).  Row order = generation order: ground points first, then obstacle by obstacle. */
+template <typename T>
+__device__ __noinline__ void pgsRowsWithNormals(T* ct, int rowStride, int nc, int iterations, bool anyPen, T invMass,
+                                                V3<T>& dLin, V3<T>& dAng, V3<T>& push, V3<T>& turn) {
+#define CTG(slot, f) ct[(slot) * rowStride + (f)]
+    if (anyPen)
+        for (int it = 0; it < iterations; ++it) {
+            for (int c = 0; c < nc; ++c) {
+                const T rhsPen = CTG(c, CT_RHSPEN);
+                if (rhsPen == T(0)) continue;
+                const V3<T> n(CTG(c, CT_NRM + 0), CTG(c, CT_NRM + 1), CTG(c, CT_NRM + 2));
+                const V3<T> rxn(CTG(c, CT_RXN + 0), CTG(c, CT_RXN + 1), CTG(c, CT_RXN + 2));
+                const V3<T> angN(CTG(c, CT_ANGN + 0), CTG(c, CT_ANGN + 1), CTG(c, CT_ANGN + 2));
+                const T invDiagN = CTG(c, CT_INVDIAGN);
+                T delta = rhsPen;
+                const T dv = n.dot(push) + rxn.dot(turn);
+                delta -= dv * invDiagN;
+                const T lam = CTG(c, CT_LAMPUSH);
+                const T sum = lam + delta;
+                if (sum < T(0)) { delta = -lam; CTG(c, CT_LAMPUSH) = T(0); }
+                else CTG(c, CT_LAMPUSH) = sum;
+                push += n * (invMass * delta);
+                turn += angN * delta;
+            }
+        }
+    for (int it = 0; it < iterations; ++it) {
+        for (int c = 0; c < nc; ++c) {
+            const V3<T> n(CTG(c, CT_NRM + 0), CTG(c, CT_NRM + 1), CTG(c, CT_NRM + 2));
+            const V3<T> rxn(CTG(c, CT_RXN + 0), CTG(c, CT_RXN + 1), CTG(c, CT_RXN + 2));
+            const V3<T> angN(CTG(c, CT_ANGN + 0), CTG(c, CT_ANGN + 1), CTG(c, CT_ANGN + 2));
+            const T invDiagN = CTG(c, CT_INVDIAGN);
+            T delta = CTG(c, CT_RHSN);
+            const T dv = n.dot(dLin) + rxn.dot(dAng);
+            delta -= dv * invDiagN;
+            const T lam = CTG(c, CT_LAMN);
+            const T sum = lam + delta;
+            if (sum < T(0)) { delta = -lam; CTG(c, CT_LAMN) = T(0); }
+            else CTG(c, CT_LAMN) = sum;
+            dLin += n * (invMass * delta);
+            dAng += angN * delta;
+        }
+        for (int c = 0; c < nc; ++c) {
+            const T lamN = CTG(c, CT_LAMN);
+            if (!(lamN > T(0))) continue;
+            const V3<T> t(CTG(c, CT_T + 0), CTG(c, CT_T + 1), CTG(c, CT_T + 2));
+            const V3<T> rxt(CTG(c, CT_RXT + 0), CTG(c, CT_RXT + 1), CTG(c, CT_RXT + 2));
+            const V3<T> angT(CTG(c, CT_ANGT + 0), CTG(c, CT_ANGT + 1), CTG(c, CT_ANGT + 2));
+            const T invDiagT = CTG(c, CT_INVDIAGT);
+            const T mu = CTG(c, CT_MU);
+            const T lo = -mu * lamN, hi = mu * lamN;
+            T delta = CTG(c, CT_RHST);
+            const T dv = t.dot(dLin) + rxt.dot(dAng);
+            delta -= dv * invDiagT;
+            const T lam = CTG(c, CT_LAMT);
+            const T sum = lam + delta;
+            if (sum < lo) { delta = lo - lam; CTG(c, CT_LAMT) = lo; }
+            else if (sum > hi) { delta = hi - lam; CTG(c, CT_LAMT) = hi; }
+            else CTG(c, CT_LAMT) = sum;
+            dLin += t * (invMass * delta);
+            dAng += angT * delta;
+        }
+    }
+#undef CTG
+}
+
+/* Signed distance of a point to an oriented box (centre co, axes e0 e1 e2, half extents h) and the outward direction at the closest
+   surface point: outside, the vector from the closest point; inside, the axis of the nearest face (lowest index on a tie). */
+template <typename T>
+TGB_D T boxDistance(const V3<T>& p, const V3<T>& co, const V3<T>& e0, const V3<T>& e1, const V3<T>& e2, const V3<T>& h, V3<T>& nOut) {
+    const V3<T> d = p - co;
+    const T q[3] = {e0.dot(d), e1.dot(d), e2.dot(d)};
+    const T hh[3] = {h.x, h.y, h.z};
+    T a[3], o[3], len2 = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        a[i] = tabs(q[i]) - hh[i];
+        o[i] = a[i] > T(0) ? a[i] : T(0);
+        len2 += o[i] * o[i];
+    }
+    T nl[3] = {T(0), T(0), T(0)}, sd;
+    if (len2 > T(0)) {
+        sd = tsqrt(len2);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) nl[i] = (q[i] < T(0) ? -o[i] : o[i]) / sd;
+    } else {
+        int k = 0;
+        if (a[1] > a[k]) k = 1;
+        if (a[2] > a[k]) k = 2;
+        sd = a[k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) nl[i] = i == k ? (q[i] < T(0) ? T(-1) : T(1)) : T(0);
+    }
+    nOut = e0 * nl[0] + e1 * nl[1] + e2 * nl[2];
+    return sd;
+}
+
 /* Contact solve of a body with two or more contact points (a rod lying on a rim line, a compound body): rare next to the
    single-point case, so it lives out of line -- the step loop's hot instructions stay within the instruction cache.
    ct = row 0 of this body, rowStride = words between consecutive rows of one body. */
@@ -425,7 +522,7 @@ TGB_HOST_DEVICE_INLINE int tgb_ctrl_class(int kind) {
 #ifndef TGB_NARROW_MINBLOCKS
 #define TGB_NARROW_MINBLOCKS 1
 #endif
-template <typename T, int LPE, int CLASS, bool GROUND, int WIDE = 0 /* 0 or 4 warps */>
+template <typename T, int LPE, int CLASS, bool GROUND, int WIDE = 0 /* 0 or 4 warps */, bool OBST = false /* static obstacles, narrow layout only */>
 __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step_kernel(const tgb_step_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename Vec16<T>::type vec_t;
@@ -464,7 +561,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
        list][body lane] of two float4 planes, so that the gather of a body lane is a run of 128-bit loads at consecutive addresses
        across lanes: no index loads, no bank conflicts. */
     const int jWords = kFast ? a.max_inc * LPE * 8 : 3 * C;
-    const int ctWords = a.cap_contacts * TGB_NCT * R; /* rows [slot][body][TGB_NCT]: 23 words apart across lanes, conflict-free */
+    constexpr int NCT = OBST ? (int)TGB_NCT_OBST : (int)TGB_NCT;
+    const int ctWords = a.cap_contacts * NCT * R; /* rows [slot][body][NCT]: 23 words apart across lanes, conflict-free */
     /* the contact rows (live from contact generation to the end of the solver) and the cable impulses (live from the cable
        phase to the impulse gather) share one region: shared memory per environment decides how many CTAs an SM holds */
     const int exchangeWords = TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords;
@@ -637,7 +735,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     /* a frame tied to a static body never moves: static bodies then stay bit-exactly in place */
     const bool frameMoves = M.body(BF_INVMASS, a.frame_body) != T(0);
 
-#define CT(slot, f) sCt[((slot) * R + bidx) * TGB_NCT + (f)]
+#define CT(slot, f) sCt[((slot) * R + bidx) * NCT + (f)]
 
     /* ---- CPG: CPGNode::updateDTs for this lane's nodes (CPGNode.cpp:71-88). Every lane of the warp calls this the same
        number of times (it synchronises); `act` masks groups that have nothing to do. sin(phi_j - phi_i - theta) is
@@ -828,7 +926,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             /* ---- ground contact manifold (analytic cylinder rim points against the ground surface) ---- */
             int nc = 0;
             bool anyPen = false;
-            if (GROUND) {
+            if (GROUND && (!OBST || a.ground_kind != TGB_GROUND_EMPTY)) {
                 /* signed height of the frame origin above the surface, formed in double */
                 const T originHeight = (T)(a.gn[0] * Ox + a.gn[1] * Oy + a.gn[2] * Oz - a.goff);
                 for (int si = shapeBegin; si < shapeBegin + shapeCount; ++si) {
@@ -946,6 +1044,9 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 CT(nc, CT_RXT + 0) = rxt.x; CT(nc, CT_RXT + 1) = rxt.y; CT(nc, CT_RXT + 2) = rxt.z;
                                 CT(nc, CT_ANGT + 0) = angT.x; CT(nc, CT_ANGT + 1) = angT.y; CT(nc, CT_ANGT + 2) = angT.z;
                                 CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = T(0);
+                                if constexpr (OBST) {
+                                    CT(nc, CT_NRM + 0) = gn.x; CT(nc, CT_NRM + 1) = gn.y; CT(nc, CT_NRM + 2) = gn.z; CT(nc, CT_MU) = mu;
+                                }
                                 ++nc;
                                 ++count;
                             }
@@ -954,12 +1055,111 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 }
             }
 
+            /* ---- static obstacles: sample points of this body's shapes against the box shapes of static bodies (same scheme as
+               the oracle's generateObstacleContacts: cylinder = five stations along the axis, at each the surface point facing the
+               box; sphere = centre; box = eight corners; at most 4 points per pair of shapes, rows capped at cap_contacts) ---- */
+            if constexpr (OBST) {
+                const int* obst = sModelI + a.model_obst_off;
+                const T bodyFriction = M.body(BF_FRICTION, bidx), bodyRestitution = M.body(BF_RESTITUTION, bidx);
+                for (int oi = 0; oi < a.n_obst; ++oi) {
+                    const int ob = obst[2 * oi], os = obst[2 * oi + 1];
+                    /* the obstacle's pose as its (static) body published it, frame-relative like this body's */
+                    const T* op = sPose + 12 * ob;
+                    const V3<T> ox(op[0], op[1], op[2]);
+                    M3<T> OB;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) OB.m[i][j] = op[3 + i * 3 + j];
+                    const ShapeConst<T> oc = loadShape(os);
+                    const V3<T> e0 = OB * oc.r0, e1 = OB * oc.r1, e2 = e0.cross(e1);
+                    const V3<T> co = OB * oc.spos + ox;
+                    const V3<T> oh(oc.radius, oc.halfLen, oc.halfZ);
+                    T obstMu = bodyFriction * M.body(BF_FRICTION, ob);
+                    obstMu = obstMu < T(-10) ? T(-10) : (obstMu > T(10) ? T(10) : obstMu);
+                    const T obstRestitution = bodyRestitution * M.body(BF_RESTITUTION, ob);
+                    for (int si = shapeBegin; si < shapeBegin + shapeCount; ++si) {
+                        const ShapeConst<T> sc = si == shapeBegin ? shape0 : loadShape(si);
+                        const V3<T> col0 = b.B * sc.r0, axisDir = b.B * sc.r1, c = b.B * sc.spos + b.x;
+                        const T margin = sc.margin, rc = sc.radius - margin, hc = sc.halfLen - margin;
+                        const int nPoints = sc.sphere ? 1 : sc.box ? 8 : 5;
+                        int count = 0;
+                        for (int k = 0; k < nPoints && count < 4 && nc < a.cap_contacts; ++k) {
+                            V3<T> pc;
+                            if (sc.sphere) {
+                                pc = c;
+                            } else if (sc.box) {
+                                const V3<T> ez = col0.cross(axisDir);
+                                const T hx = rc, hz = sc.halfZ - margin;
+                                pc = c + col0 * ((k & 1) ? hx : -hx) + axisDir * ((k & 2) ? hc : -hc) + ez * ((k & 4) ? hz : -hz);
+                            } else {
+                                const V3<T> pa = c + axisDir * (hc * (T(0.5) * (T)(k - 2)));
+                                V3<T> g;
+                                boxDistance(pa, co, e0, e1, e2, oh, g);
+                                const V3<T> radial = g - axisDir * axisDir.dot(g);
+                                const T rl = radial.length();
+                                pc = rl > T(1e-9) ? pa - radial * (rc / rl) : pa;
+                            }
+                            V3<T> n;
+                            const T dist = boxDistance(pc, co, e0, e1, e2, oh, n) - margin;
+                            if (dist <= SolverConst<T>::breakingThreshold()) {
+                                const V3<T> r = (pc - n * margin) - b.x;
+                                const V3<T> rxn = r.cross(n);
+                                const V3<T> angN = b.Iinv * rxn;
+                                const T denom = invMass + n.dot(angN.cross(r));
+                                const T invDiagN = T(1) / denom;
+                                const V3<T> vel = linvel + b.w.cross(r);
+                                const T relVel = n.dot(vel);
+                                T restitution = obstRestitution * -relVel;
+                                if (restitution <= T(0)) restitution = T(0);
+                                const V3<T> lat = vel - n * relVel;
+                                const T lat2 = lat.length2();
+                                V3<T> t;
+                                if (lat2 > epsilonOf<T>()) t = lat * (T(1) / tsqrt(lat2));
+                                else t = planeSpace1(n);
+                                const T velDotN = n.dot(linvel + extLin) + rxn.dot(b.w + extAng);
+                                T velocityError = restitution - velDotN;
+                                const T penetration = dist;
+                                T erp = SolverConst<T>::erp2();
+                                if (penetration > SolverConst<T>::splitThreshold()) erp = SolverConst<T>::erp();
+                                T positionalError = T(0);
+                                if (penetration > T(0)) velocityError -= penetration / dt;
+                                else positionalError = -penetration * erp / dt;
+                                const T penetrationImpulse = positionalError * invDiagN;
+                                const T velocityImpulse = velocityError * invDiagN;
+                                T rhsN, rhsPen;
+                                if (penetration > SolverConst<T>::splitThreshold()) { rhsN = penetrationImpulse + velocityImpulse; rhsPen = T(0); }
+                                else { rhsN = velocityImpulse; rhsPen = penetrationImpulse; anyPen = anyPen || rhsPen != T(0); }
+                                const V3<T> rxt = r.cross(t);
+                                const V3<T> angT = b.Iinv * rxt;
+                                const T denomT = invMass + t.dot(angT.cross(r));
+                                const T invDiagT = T(1) / denomT;
+                                const T relT = t.dot(linvel + extLin) + rxt.dot(b.w);
+                                const T rhsT = (T(0) - relT) * invDiagT;
+                                CT(nc, CT_RXN + 0) = rxn.x; CT(nc, CT_RXN + 1) = rxn.y; CT(nc, CT_RXN + 2) = rxn.z;
+                                CT(nc, CT_ANGN + 0) = angN.x; CT(nc, CT_ANGN + 1) = angN.y; CT(nc, CT_ANGN + 2) = angN.z;
+                                CT(nc, CT_INVDIAGN) = invDiagN; CT(nc, CT_RHSN) = rhsN; CT(nc, CT_RHSPEN) = rhsPen;
+                                CT(nc, CT_LAMN) = T(0); CT(nc, CT_LAMPUSH) = T(0);
+                                CT(nc, CT_T + 0) = t.x; CT(nc, CT_T + 1) = t.y; CT(nc, CT_T + 2) = t.z;
+                                CT(nc, CT_RXT + 0) = rxt.x; CT(nc, CT_RXT + 1) = rxt.y; CT(nc, CT_RXT + 2) = rxt.z;
+                                CT(nc, CT_ANGT + 0) = angT.x; CT(nc, CT_ANGT + 1) = angT.y; CT(nc, CT_ANGT + 2) = angT.z;
+                                CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = T(0);
+                                CT(nc, CT_NRM + 0) = n.x; CT(nc, CT_NRM + 1) = n.y; CT(nc, CT_NRM + 2) = n.z; CT(nc, CT_MU) = obstMu;
+                                ++nc;
+                                ++count;
+                            }
+                        }
+                    }
+                }
+            }
 #ifdef TGB_STATS
             statNc = nc; statPen = anyPen;
 #endif
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
-            if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
+            if (OBST) {
+                if (nc > 0) pgsRowsWithNormals<T>(sCt + bidx * NCT, R * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
+            } else if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
                 /* Single precision, one contact point (by far the commonest case: a rod end touching the ground): the matrix form
                    of the solver below for the two rows (normal, friction) of that point, straight-line and branch-free.  The
                    relative velocity change of each row is carried along: dvN = ANN lamN + ANT lamT, dvT = ANT lamN + ATT lamT. */
@@ -997,7 +1197,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 dLin = bn * lamN + bt * lamT;
                 dAng = angN * lamN + angT * lamT;
             } else if (nc > 0) {
-                const ContactSolveOut<T> o = solveContactsGeneral<T, kFast>(sCt + bidx * TGB_NCT, R * TGB_NCT, nc, a.iterations, anyPen, gn, invMass, mu);
+                const ContactSolveOut<T> o = solveContactsGeneral<T, kFast>(sCt + bidx * NCT, R * NCT, nc, a.iterations, anyPen, gn, invMass, mu);
                 dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
             }
 
@@ -1481,7 +1681,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
     const int groupsPerBlock = a.wide ? 32 / lpe : threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
-    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * TGB_NCT * a.R;
+    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST : (int)TGB_NCT) * a.R;
     int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords);
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }

@@ -9,7 +9,7 @@ from . import _capi as capi
 from .world import FlatModel
 
 EXAMPLES = ("3_prism", "3_prism_noground", "SUPERball", "SUPERball_flat", "Escape", "Escape_c3", "tsTestRig_basic",
-            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3", "TetraSpineStatic_hf")
+            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3", "TetraSpineStatic_hf", "Escape_crater", "Escape_crater_shallow")
 
 
 def build_example(name):

@@ -69,6 +69,34 @@ void PrismModel::teardown() {
     tgModel::teardown();
 }
 
+/* ---- crater obstacles -------------------------------------------------------------------------------- */
+tgCraterDeep::tgCraterDeep() : m_origin(0, 0, 0), m_halfSize(15.0) {}
+tgCraterDeep::tgCraterDeep(btVector3 center) : m_origin(center), m_halfSize(15.0) {}
+tgCraterDeep::tgCraterDeep(btVector3 center, double halfSize) : m_origin(center), m_halfSize(halfSize) {}
+void tgCraterDeep::setup(tgWorld& world) {
+    /* friction 1, rolling friction 0.01, restitution 0.2 like the rods they meet; density 0 makes the boxes static */
+    const tgBox::Config wallConfig(m_halfSize, m_halfSize, 0.0, 1.0, 0.01, 0.2);
+    tgStructure s;
+    for (int wall = 0; wall < 4; ++wall) {
+        /* every wall is entered at x = 20 and the structure so far is turned a quarter about the vertical through the origin
+           before the pair is made, so the four walls end up a quarter turn apart (tgCraterDeep.cpp:124-145) */
+        s.addNode(20.0, -10.0, 0.0, "node");
+        s.addNode(20.0, 25.0, 0.0, "node");
+        s.addRotation(m_origin, btVector3(0, 1, 0), M_PI / 2);
+        s.addPair(2 * wall, 2 * wall + 1, "box");
+    }
+    s.move(btVector3(0, -5, 0)); /* sunk into the ground */
+    tgBuildSpec spec;
+    spec.addBuilder("box", new tgBoxInfo(wallConfig));
+    tgStructureInfo structureInfo(s, spec);
+    structureInfo.buildInto(*this, world);
+    tgModel::setup(world);
+}
+void tgCraterDeep::step(double dt) {
+    if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
+    tgModel::step(dt);
+}
+
 /* ---- SUPERball (T6) ---------------------------------------------------------------------------------- */
 T6Model::T6Model() {}
 void T6Model::setup(tgWorld& world) {

@@ -47,6 +47,26 @@ private:
     std::vector<tgBasicActuator*> m_actuators;
 };
 
+/* Crater obstacles (src/models/obstacles/tgCraterDeep.cpp:40-169, tgCraterShallow.cpp): four static tgBox walls (density 0) standing
+   around `origin`, 20 from it, from 15 below to 20 above it; half width and half thickness 15 (deep) or 10 (shallow). */
+class tgCraterDeep : public tgModel {
+public:
+    tgCraterDeep();
+    explicit tgCraterDeep(btVector3 center);
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt); /* dt <= 0 -> std::invalid_argument */
+protected:
+    tgCraterDeep(btVector3 center, double halfSize);
+private:
+    btVector3 m_origin;
+    double m_halfSize;
+};
+class tgCraterShallow : public tgCraterDeep {
+public:
+    tgCraterShallow() : tgCraterDeep(btVector3(0, 0, 0), 10.0) {}
+    explicit tgCraterShallow(btVector3 center) : tgCraterDeep(center, 10.0) {}
+};
+
 /* Motor test rig: a static rod, a hanging rod, one cable (src/examples/motorModel/tsTestRig.cpp:53-199) */
 class tsTestRig : public tgSubject<tsTestRig>, public tgModel {
 public:

@@ -19,8 +19,9 @@ struct Example {
     tgSimView* view;
     tgSimulation* sim;
     tgModel* model; /* owned by sim */
+    tgModel* obstacle; /* a second model of the same world (owned by sim), or NULL */
     double dt;
-    Example() : world(0), view(0), sim(0), model(0), dt(0.001) {}
+    Example() : world(0), view(0), sim(0), model(0), obstacle(0), dt(0.001) {}
     ~Example() {
         delete sim;
         delete view;
@@ -42,6 +43,13 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
             e->world = new tgWorld(tgWorld::Config(98.1), new tgBoxGround(tgBoxGround::Config(btVector3(0.0, pitch, 0.0))));
             e->dt = 0.001;
             e->model = new T6Model();
+        } else if (name == "Escape_crater" || name == "Escape_crater_shallow") {
+            /* AppEscape.cpp:59-97 complete: EscapeModel and, as a second model of the same simulation, tgCraterDeep at the origin */
+            e->world = new tgWorld(tgWorld::Config(98.1),
+                                   new tgBoxGround(tgBoxGround::Config(btVector3(0, 0, 0), 0.5, 0.0, btVector3(10000.0, 2, 10000.0), btVector3(0, 0, 0))));
+            e->dt = 1.0 / 60.0 / 10.0;
+            e->model = new EscapeModel();
+            e->obstacle = name == "Escape_crater" ? new tgCraterDeep(btVector3(0, 0, 0)) : new tgCraterShallow(btVector3(0, 0, 0));
         } else if (name == "Escape" || name == "Escape_c3") {
             /* AppEscape: box ground half extents (10000, 2, 10000), dt = 1/600. "_c3" = BASELINE config 3:
                default box ground, dt = 1e-3. */
@@ -96,6 +104,7 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
         e->view = new tgSimView(*e->world, e->dt, 1.0 / 60.0 < e->dt ? e->dt : 1.0 / 60.0);
         e->sim = new tgSimulation(*e->view);
         e->sim->addModel(e->model);
+        if (e->obstacle) e->sim->addModel(e->obstacle);
     } catch (const std::exception& ex) {
         g_error = ex.what();
         delete e;

@@ -86,6 +86,8 @@ class BatchedWorld(object):
         return out
 
     def set_cable_state(self, rest_prev, env_begin=0):
+        if self.C == 0:
+            return  # a structure without cables has no cable state
         rest_prev = np.ascontiguousarray(rest_prev, dtype=np.float64).reshape(-1, self.C, 2)
         capi.check(self._lib.tgb_set_cable_state(self._h, env_begin, rest_prev.shape[0], _ptr(rest_prev)))
 

@@ -549,9 +549,9 @@ struct tgo_world {
     /* Signed distance of a point to an oriented box (centre co, rotation Ro, half extents h) and the outward direction at the
        closest surface point: outside, the vector from the closest point; inside, the axis of the nearest face (lowest index on
        a tie). */
-    static double boxDistance(const V3& p, const V3& co, const M3& Ro, const V3& h, V3& nOut) {
+    static double boxDistance(const V3& p, const V3& co, const V3 e[3], const V3& h, V3& nOut) {
         const V3 d = p - co;
-        const double q[3] = {Ro.col(0).dot(d), Ro.col(1).dot(d), Ro.col(2).dot(d)};
+        const double q[3] = {e[0].dot(d), e[1].dot(d), e[2].dot(d)};
         const double hh[3] = {h.x, h.y, h.z};
         double a[3], o[3], len2 = 0.0;
         for (int i = 0; i < 3; ++i) {
@@ -570,7 +570,7 @@ struct tgo_world {
             sd = a[k];
             nl[k] = q[k] < 0.0 ? -1.0 : 1.0;
         }
-        nOut = Ro.col(0) * nl[0] + Ro.col(1) * nl[1] + Ro.col(2) * nl[2];
+        nOut = e[0] * nl[0] + e[1] * nl[1] + e[2] * nl[2];
         return sd;
     }
 
@@ -580,13 +580,26 @@ struct tgo_world {
        box: its eight core corners.  A point is a contact when its distance (after the shape's margin; the obstacle counts with
        its full half extents) is within the contact breaking threshold; at most 4 per pair of shapes, in sampling order. */
     void generateObstacleContacts() {
+        /* the device kernel keeps at most cap rows per body (tgb_capi.cu: 4 per shape of the largest body, times 1 + the number of
+           obstacles up to three); the same cap here */
+        int maxShapes = 1, nObst = 0;
+        for (const Body& b : bodies) {
+            maxShapes = std::max(maxShapes, b.shapeCount);
+            if (b.invMass == 0.0)
+                for (int s = b.shapeBegin; s < b.shapeBegin + b.shapeCount; ++s) nObst += shapes[s].kind == TGB_SHAPE_BOX;
+        }
+        if (nObst == 0) return;
+        const int cap = 4 * maxShapes * (1 + std::min(nObst, 3));
+        std::vector<int> rows(bodies.size(), 0);
+        for (const Contact& c : contacts) rows[c.body] += 1;
         for (size_t oi = 0; oi < bodies.size(); ++oi) {
             const Body& ob = bodies[oi];
             if (ob.invMass != 0.0) continue;
             for (int osi = ob.shapeBegin; osi < ob.shapeBegin + ob.shapeCount; ++osi) {
                 const Shape& os = shapes[osi];
                 if (os.kind != TGB_SHAPE_BOX) continue;
-                const M3 Ro = ob.basis * os.rot;
+                const M3 Rm = ob.basis * os.rot;
+                const V3 Ro[3] = {Rm.col(0), Rm.col(1), Rm.col(0).cross(Rm.col(1))};
                 const V3 co = ob.basis * os.pos + ob.pos;
                 const V3 h(os.radius, os.halfLen, os.halfZ);
                 for (size_t bi = 0; bi < bodies.size(); ++bi) {
@@ -600,7 +613,7 @@ struct tgo_world {
                         const double rc = s.radius - s.margin, hc = s.halfLen - s.margin;
                         const int nPoints = s.kind == TGB_SHAPE_SPHERE ? 1 : s.kind == TGB_SHAPE_BOX ? 8 : 5;
                         int count = 0;
-                        for (int k = 0; k < nPoints && count < 4; ++k) {
+                        for (int k = 0; k < nPoints && count < 4 && rows[bi] < cap; ++k) {
                             V3 pc;
                             if (s.kind == TGB_SHAPE_SPHERE) {
                                 pc = c;
@@ -631,6 +644,7 @@ struct tgo_world {
                                 ct.restitution = b.restitution * ob.restitution;
                                 contacts.push_back(ct);
                                 ++count;
+                                rows[bi] += 1;
                             }
                         }
                     }

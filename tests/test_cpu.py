@@ -277,6 +277,23 @@ builders:
     assert abs(s[0, 1] - (1.5 + half)) < 0.05, (s[0, 1], half)
 
 
+def test_crater_obstacle_models():
+    """tgCraterDeep / tgCraterShallow (src/models/obstacles): four static boxes a quarter turn apart, 20 from the origin, sunk by 5;
+    as the second model of the AppEscape simulation they follow EscapeModel's six rods in the flattened world."""
+    for name, half in (("Escape_crater", 15.0), ("Escape_crater_shallow", 10.0)):
+        m = nt.build_example(name)
+        assert (m.n_bodies, m.n_cables) == (10, 24)
+        walls = [i for i, b in enumerate(m.bodies) if b.mass == 0.0]
+        assert walls == [6, 7, 8, 9]
+        pos = m.initial_rod_state()[walls, 0:3]
+        assert np.allclose(np.sort(np.abs(pos[:, [0, 2]]).max(axis=1)), 20.0) and np.allclose(pos[:, 1], 2.5)
+        assert np.allclose(np.abs(pos[:, [0, 2]]).min(axis=1), 0.0, atol=1e-12)
+        for i in walls:
+            s = m.shapes[m.bodies[i].shape_begin]
+            assert (s.kind, s.radius, s.half_length, s.half_extent_z) == (2, half, 17.5, half)
+            assert (m.bodies[i].friction, m.bodies[i].rolling_friction, m.bodies[i].restitution) == (1.0, 0.01, 0.2)
+
+
 def test_oracle_bodies_rest_on_a_static_obstacle(tmp_path):
     """Static tgBox obstacles (tgCraterDeep / tgBlockField are built from them): a rod and a ball dropped on a
     block come to rest on its top face (y = 3.5) instead of falling through to the ground, the block itself never moves, and a

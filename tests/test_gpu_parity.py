@@ -882,3 +882,74 @@ builders:
         assert max(e) < 1e-7
     else:
         assert e[0] < 5 * F32_REL and e[1] < 5 * F32_REL   # 50 steps of impact and a three-point stance in single precision
+
+
+# ------------------------------------------------------------------------------------------------ static obstacles (8f rank 2)
+@pytest.mark.parametrize("precision,steps", [("f64", 45), ("f32", 40)])
+def test_static_obstacle_contacts_match_oracle(tmp_path, precision, steps):
+    """A static block (tgBoxInfo, density 0) with a rod and a ball dropping on its top face and a rod hitting its side face: obstacle
+    contacts carry their own normal, friction and restitution through the solver.  The static body stays bit-exactly in place.
+    A rod landing flat on a face is a four-point contact that chatters: a 1e-13 perturbation of the oracle's input grows to 6e-10 after
+    60 steps and 7e-8 after 80, hence the horizons (first contacts: side face at step ~17, top face from step ~30)."""
+    from test_yaml import OBSTACLE_SCENE, write
+    from ntrtsim_b200 import examples
+    model = examples.build_yaml(write(tmp_path, "scene.yaml", OBSTACLE_SCENE))
+    static = [i for i, b in enumerate(model.bodies) if b.mass == 0.0]
+    n_env = 24
+    base = model.initial_rod_state()
+    rng = np.random.default_rng(123)
+    rods = np.tile(base, (n_env, 1, 1))
+    moving = [i for i in range(model.n_bodies) if i not in static]
+    # every moving body gets its own small random offset and initial velocity: contacts switch on at different steps (top rod and
+    # ball 0.05 .. 0.4 above the top face; the low rod 0.1 from the side face and moving towards it)
+    rods[:, moving, 0:3] += rng.uniform(-0.05, 0.05, size=(n_env, len(moving), 3)) + np.array([0.0, -0.25, 0.0])
+    rods[:, moving, 7:10] = rng.uniform(-0.5, 0.5, size=(n_env, len(moving), 3))
+    side = min((i for i in moving if model.shapes[model.bodies[i].shape_begin].kind == 0), key=lambda i: base[i, 1])
+    rods[:, side, 1] += 0.25
+    rods[:, side, 2] -= 0.6
+    rods[:, side, 9] = -6.0
+    cab = np.zeros((n_env, 0, 2))
+    rd, _, st = device_rollout(model, rods, cab, steps, precision)
+    ro, _ = oracle_rollout(model, rods, cab, steps)
+    e = rod_errors(rd, ro, 6.0 if precision == "f32" else 1.0)
+    print("obstacle scene %s %d steps: %s" % (precision, steps, e))
+    assert not st.any()
+    assert np.array_equal(rd[:, static], rods[:, static]) if precision == "f64" else np.allclose(rd[:, static], rods[:, static], atol=1e-6)
+    if precision == "f64":
+        assert max(e) < 1e-7
+    else:
+        assert e[0] < F32_REL and e[1] < F32_REL
+
+
+@pytest.mark.parametrize("precision,steps", [("f64", 300), ("f32", 150)])
+def test_escape_crater_app_matches_oracle(precision, steps):
+    """AppEscape complete (src/examples/craterEscape/AppEscape.cpp:59-97): EscapeModel with its sine controller and tgCraterDeep as a
+    second model of the same simulation -- four static tgBox walls around a 10 x 10 pit, rim at y = 20.  The balls are dropped from
+    just above the rim and land on the walls' top faces and inner edges (the 17-long rods do not fit into the pit)."""
+    model = nt.build_example("Escape_crater")
+    dyn = [i for i, b in enumerate(model.bodies) if b.mass != 0.0]
+    assert (model.n_bodies, len(dyn), model.n_cables) == (10, 6, 24)
+    assert all(model.shapes[model.bodies[i].shape_begin].kind == 2 for i in range(model.n_bodies) if i not in dyn)
+    n_env = 16
+    rng = np.random.default_rng(5)
+    rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+    rods[:, dyn, 0:3] += rng.uniform(-0.3, 0.3, size=(n_env, 1, 3)) + np.array([0.0, 14.0, 0.0])
+    cab = tiled_cables(model, n_env)
+    params = nt.escape_transform_actions(rng.uniform(size=(n_env, 32)), 9.0)
+    rd, cd, st = device_rollout(model, rods, cab, steps, precision, capi.TGB_CTRL_ESCAPE_SINE, params)
+    ro, co = oracle_rollout(model, rods, cab, steps, capi.TGB_CTRL_ESCAPE_SINE, params)
+    # per environment: the sampled surface point of a rod jumps when the obstacle feature closest to a station switches between a
+    # face and an edge, and an environment that sits on such a switch amplifies round-off at once (on the oracle alone a 1e-15
+    # perturbation of this very input moves one of the 16 environments by 5e-7 within 100 steps, the others by < 1e-10)
+    scale = 17.0 if precision == "f32" else 1.0
+    rda = align_quat_sign(rd, ro)
+    per_env = np.maximum(np.abs(rda[..., 0:3] - ro[..., 0:3]).reshape(n_env, -1).max(axis=1) / scale,
+                         np.abs(rda[..., 3:7] - ro[..., 3:7]).reshape(n_env, -1).max(axis=1))
+    tper = (np.abs(cd[..., 2] - co[..., 2]) / np.maximum(np.abs(co[..., 2]), 2452.0)).max(axis=1)
+    print("Escape + crater %s %d steps: pose error per env %s, tension %s, lowest rod centre %.2f"
+          % (precision, steps, np.sort(per_env)[[0, n_env // 2, -2, -1]], np.sort(tper)[[n_env // 2, -1]], ro[:, dyn, 1].min()))
+    assert not st.any()
+    assert ro[:, dyn, 1].min() > 20.0  # held up by the rim
+    tol = 1e-8 if precision == "f64" else F32_REL
+    assert np.sum(per_env < tol) >= n_env - 2 and per_env.max() < 1e-3
+    assert np.sum(tper < (1e-7 if precision == "f64" else 5 * F32_REL)) >= n_env - 2 and tper.max() < 1e-2
