@@ -9,7 +9,7 @@ from . import _capi as capi
 from .world import FlatModel
 
 EXAMPLES = ("3_prism", "3_prism_noground", "SUPERball", "SUPERball_flat", "Escape", "Escape_c3", "tsTestRig_basic",
-            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3", "TetraSpineStatic_hf", "Escape_crater", "Escape_crater_shallow")
+            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3", "TetraSpineStatic_hf", "Escape_crater", "Escape_crater_shallow", "SUPERball_stairs", "SUPERball_blocks", "SUPERball_wall")
 
 
 def build_example(name):

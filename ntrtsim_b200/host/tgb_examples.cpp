@@ -97,6 +97,92 @@ void tgCraterDeep::step(double dt) {
     tgModel::step(dt);
 }
 
+namespace {
+/* the common tail of the obstacle models: every pair tagged "box" becomes a static tgBox */
+void buildStaticBoxes(tgModel& self, tgStructure& s, const tgBox::Config& boxConfig, tgWorld& world) {
+    tgBuildSpec spec;
+    spec.addBuilder("box", new tgBoxInfo(boxConfig));
+    tgStructureInfo structureInfo(s, spec);
+    structureInfo.buildInto(self, world);
+}
+} // namespace
+
+tgStairs::Config::Config(btVector3 origin, btScalar friction, btScalar restitution, std::size_t nStairs, double stairWidth, double stepWidth,
+                         double stepHeight, double angle)
+    : m_origin(origin), m_friction(friction), m_restitution(restitution), m_nBlocks(nStairs), m_length(stairWidth), m_width(stepWidth),
+      m_height(stepHeight), m_angle(angle) {}
+tgStairs::tgStairs() {}
+tgStairs::tgStairs(const Config& config) : m_config(config) {}
+void tgStairs::setup(tgWorld& world) {
+    /* density and rolling friction zero; the Config's full sizes halved into tgBox half extents (tgStairs.cpp:82-84) */
+    const tgBox::Config boxConfig(m_config.m_width / 2.0, m_config.m_height / 2.0, 0.0, m_config.m_friction, 0.0, m_config.m_restitution);
+    tgStructure s;
+    tgNode from(0.0, 0.0, 0.0), to(0.0, 0.0, m_config.m_length);
+    const btVector3 rise(m_config.m_width, m_config.m_height, 0.0);
+    for (std::size_t i = 0; i < m_config.m_nBlocks; ++i) {
+        s.addNode(from);
+        s.addNode(to);
+        s.addPair((int)(2 * i), (int)(2 * i + 1), "box");
+        from += rise;
+        to += rise;
+    }
+    s.addRotation(btVector3(0.0, 0.0, 0.0), btVector3(0.0, 1.0, 0.0), m_config.m_angle);
+    s.move(m_config.m_origin);
+    buildStaticBoxes(*this, s, boxConfig, world);
+    tgModel::setup(world);
+}
+void tgStairs::step(double dt) {
+    if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
+    tgModel::step(dt);
+}
+
+tgBlockField::Config::Config(btVector3 origin, btScalar friction, btScalar restitution, btVector3 minPos, btVector3 maxPos, std::size_t nBlocks,
+                             double blockLength, double blockWidth, double blockHeight)
+    : m_origin(origin), m_friction(friction), m_restitution(restitution), m_minPos(minPos), m_maxPos(maxPos), m_nBlocks(nBlocks),
+      m_length(blockLength), m_width(blockWidth), m_height(blockHeight) {}
+tgBlockField::tgBlockField() {}
+tgBlockField::tgBlockField(const Config& config) : m_config(config) {}
+void tgBlockField::setup(tgWorld& world) {
+    const tgBox::Config boxConfig(m_config.m_width / 2.0, m_config.m_height / 2.0, 0.0, m_config.m_friction, 0.0, m_config.m_restitution);
+    tgStructure s;
+    const btVector3 fieldSize = m_config.m_maxPos - m_config.m_minPos;
+    for (std::size_t i = 0; i < m_config.m_nBlocks; ++i) {
+        /* three draws per block, x then y then z (tgBlockField.cpp:131-145) */
+        const double xOffset = fieldSize.getX() * rand() / RAND_MAX;
+        const double yOffset = fieldSize.getY() * rand() / RAND_MAX;
+        const double zOffset = fieldSize.getZ() * rand() / RAND_MAX;
+        tgNode position(m_config.m_minPos + btVector3(xOffset, yOffset, zOffset));
+        s.addNode(position);
+        position += btVector3(0.0, 0.0, m_config.m_length);
+        s.addNode(position);
+        s.addPair((int)(2 * i), (int)(2 * i + 1), "box");
+    }
+    s.move(m_config.m_origin);
+    buildStaticBoxes(*this, s, boxConfig, world);
+    tgModel::setup(world);
+}
+void tgBlockField::step(double dt) {
+    if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
+    tgModel::step(dt);
+}
+
+Wall::Wall() : m_origin(0, 0, 0) {}
+Wall::Wall(btVector3 origin) : m_origin(origin) {}
+void Wall::setup(tgWorld& world) {
+    const tgBox::Config boxConfig(5.0, 1.0, 0.0, 1.0, 0.01, 0.2);
+    tgStructure s;
+    s.addNode(-100.0, 0.0, 0.0, "node");
+    s.addNode(100.0, 0.0, 0.0, "node");
+    s.addPair(0, 1, "box");
+    s.move(m_origin);
+    buildStaticBoxes(*this, s, boxConfig, world);
+    tgModel::setup(world);
+}
+void Wall::step(double dt) {
+    if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
+    tgModel::step(dt);
+}
+
 /* ---- SUPERball (T6) ---------------------------------------------------------------------------------- */
 T6Model::T6Model() {}
 void T6Model::setup(tgWorld& world) {

@@ -67,6 +67,59 @@ public:
     explicit tgCraterShallow(btVector3 center) : tgCraterDeep(center, 10.0) {}
 };
 
+/* A flight of stairs (src/models/obstacles/tgStairs.{h,cpp}): nStairs static boxes, each `stepWidth` further and `stepHeight`
+   higher than the one before, turned by `angle` about the vertical and moved to `origin`. */
+class tgStairs : public tgModel {
+public:
+    struct Config {
+        Config(btVector3 origin = btVector3(0.0, 0.0, 0.0), btScalar friction = 0.5, btScalar restitution = 0.0, std::size_t nStairs = 10,
+               double stairWidth = 20.0, double stepWidth = 5.0, double stepHeight = 1.0, double angle = 0.0);
+        btVector3 m_origin;
+        btScalar m_friction, m_restitution;
+        std::size_t m_nBlocks;
+        double m_length, m_width, m_height, m_angle;
+    };
+    tgStairs();
+    explicit tgStairs(const Config& config);
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt); /* dt <= 0 -> std::invalid_argument */
+private:
+    Config m_config;
+};
+
+/* A field of static blocks at random places (src/models/obstacles/tgBlockField.{h,cpp}; positions from rand() like there). An
+   environment holds at most 32 bodies, so the reference's default of 500 blocks does not fit: pass a smaller nBlocks. */
+class tgBlockField : public tgModel {
+public:
+    struct Config {
+        Config(btVector3 origin = btVector3(0.0, 0.0, 0.0), btScalar friction = 0.5, btScalar restitution = 0.0,
+               btVector3 minPos = btVector3(-100.0, 0.0, -100.0), btVector3 maxPos = btVector3(100.0, 0.0, 100.0), std::size_t nBlocks = 500,
+               double blockLength = 5.0, double blockWidth = 5.0, double blockHeight = 5.0);
+        btVector3 m_origin;
+        btScalar m_friction, m_restitution;
+        btVector3 m_minPos, m_maxPos;
+        std::size_t m_nBlocks;
+        double m_length, m_width, m_height;
+    };
+    tgBlockField();
+    explicit tgBlockField(const Config& config);
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt);
+private:
+    Config m_config;
+};
+
+/* One long static box through `origin` (src/models/obstacles/tgWall.{h,cpp}: class Wall): 200 long, half extents 5 x 1. */
+class Wall : public tgModel {
+public:
+    Wall();
+    explicit Wall(btVector3 origin);
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt);
+private:
+    btVector3 m_origin;
+};
+
 /* Motor test rig: a static rod, a hanging rod, one cable (src/examples/motorModel/tsTestRig.cpp:53-199) */
 class tsTestRig : public tgSubject<tsTestRig>, public tgModel {
 public:

@@ -50,6 +50,20 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
             e->dt = 1.0 / 60.0 / 10.0;
             e->model = new EscapeModel();
             e->obstacle = name == "Escape_crater" ? new tgCraterDeep(btVector3(0, 0, 0)) : new tgCraterShallow(btVector3(0, 0, 0));
+        } else if (name == "SUPERball_stairs" || name == "SUPERball_blocks" || name == "SUPERball_wall") {
+            /* src/models/obstacles/AppObstacleTest.cpp-style scenes: the SUPERball on the default ground next to an obstacle model */
+            e->world = new tgWorld(tgWorld::Config(98.1));
+            e->dt = 0.001;
+            e->model = new T6Model();
+            if (name == "SUPERball_stairs") {
+                e->obstacle = new tgStairs(tgStairs::Config(btVector3(0.0, 2.0, -10.0), 0.5, 0.0, 6, 20.0, 5.0, 1.0, 0.0));
+            } else if (name == "SUPERball_blocks") {
+                srand(1); /* the reference draws the block positions from rand(); a fixed seed keeps the scene reproducible */
+                e->obstacle = new tgBlockField(tgBlockField::Config(btVector3(0.0, 1.5, 0.0), 0.5, 0.0, btVector3(-30.0, 0.0, -30.0),
+                                                                    btVector3(30.0, 0.0, 30.0), 20, 5.0, 5.0, 2.0));
+            } else {
+                e->obstacle = new Wall(btVector3(0.0, 2.5, 6.0));
+            }
         } else if (name == "Escape" || name == "Escape_c3") {
             /* AppEscape: box ground half extents (10000, 2, 10000), dt = 1/600. "_c3" = BASELINE config 3:
                default box ground, dt = 1e-3. */
