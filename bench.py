@@ -57,6 +57,16 @@ def build_workload(name, n_env, seed):
         params = nt.escape_transform_actions(rng.uniform(size=(n_env, 32)), 9.0)
         ctrl = capi.TGB_CTRL_ESCAPE_SINE
         p_ctrl = 32
+    elif name == "crater":
+        # AppEscape complete: the SUPERball dropped onto the rim of tgCraterDeep (four static box walls), sine controller
+        model = nt.build_example("Escape_crater")
+        dyn = [i for i, b in enumerate(model.bodies) if b.mass != 0.0]
+        rng = np.random.default_rng(seed)
+        rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+        rods[:, dyn, 0:3] += rng.uniform(-0.3, 0.3, size=(n_env, 1, 3)) + np.array([0.0, 14.0, 0.0])
+        params = nt.escape_transform_actions(rng.uniform(size=(n_env, 32)), 9.0)
+        ctrl = capi.TGB_CTRL_ESCAPE_SINE
+        p_ctrl = 32
     elif name == "prism":
         model = nt.build_example("3_prism_noground")
         rods = random_poses(model, n_env, seed=seed)
@@ -97,10 +107,11 @@ def workload_desc(name, n_env, H, n_gpus):
     what = {"superball_noground": "SUPERball + sine controller, NO ground, zero gravity (tuning aid)",
             "superball": "SUPERball (EscapeModel: 6 rods, 24 basic-actuator cables) + EscapeController sine, flat box ground, g=98.1",
             "prism": "3-prism (3 rods, 9 cables), no ground, g=981 (contact-free drop)",
+            "crater": "SUPERball (EscapeModel) + EscapeController sine on tgCraterDeep (4 static box walls), box ground, g=98.1 (AppEscape)",
             "tetraspine": "TetraSpine (3 compound bodies, 12 basic-actuator cables) + CPG/impedance control, population evaluation, box ground, g=981",
             "flemons": "kinematic tetrahedral-complex spine (12 compound bodies, 88 kinematic-actuator cables) + CPG/impedance/PID control, "
                        "population evaluation, box ground, g=981"}[name]
-    return "%s; %d envs/GPU x %d GPU; dt=1e-3; %d sim steps per launch" % (what, n_env, n_gpus, H)
+    return "%s; %d envs/GPU x %d GPU; dt=%s; %d sim steps per launch" % (what, n_env, n_gpus, "1/600" if name == "crater" else "1e-3", H)
 
 
 class ClockSampler(object):
@@ -246,7 +257,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--sim-steps", type=int, default=1000, help="simulation steps per launch (H)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--workload", default="superball", choices=["superball", "prism", "superball_noground", "tetraspine", "flemons"])
+    ap.add_argument("--workload", default="superball", choices=["superball", "prism", "superball_noground", "tetraspine", "flemons", "crater"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -493,8 +493,8 @@ tgb_status tgb_finalize(tgb_world* w) {
        bit-exactly in place), else the first body */
     w->frameBody = 0;
     for (int b = w->R - 1; b >= 0; --b) {
-        maxShapes = std::max(maxShapes, (int)w->bodies[b].shape_count);
         if (w->bodies[b].mass == 0.0) w->frameBody = b;
+        else maxShapes = std::max(maxShapes, (int)w->bodies[b].shape_count); /* contact rows exist for dynamic bodies only */
     }
     w->capContacts = 4 * maxShapes; /* at most 4 manifold points per collision shape */
     w->lanes = w->lanesOverride ? w->lanesOverride : std::max(2, nextPow2(w->R));
@@ -516,8 +516,8 @@ tgb_status tgb_finalize(tgb_world* w) {
     std::vector<int> ints;
     if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff);
     else packModel<float>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff);
-    /* obstacle contacts share the rows: room for those of up to three obstacles touched at once */
-    w->capContacts *= 1 + std::min(w->nObst, 3);
+    /* obstacle contacts share the rows: room for those of up to two obstacles touched at once */
+    w->capContacts *= 1 + std::min(w->nObst, 2);
     w->modelTWords = (int)(tbytes.size() / w->scalarBytes);
     w->modelIWords = (int)ints.size();
     TGB_CUDA(cudaMalloc(&w->d_model_t, std::max<size_t>(tbytes.size(), 16)));

@@ -283,30 +283,29 @@ __device__ __noinline__ void pgsRowsWithNormals(T* ct, int rowStride, int nc, in
    surface point: outside, the vector from the closest point; inside, the axis of the nearest face (lowest index on a tie). */
 template <typename T>
 TGB_D T boxDistance(const V3<T>& p, const V3<T>& co, const V3<T>& e0, const V3<T>& e1, const V3<T>& e2, const V3<T>& h, V3<T>& nOut) {
+    /* scalars and selects only: no indexed local arrays */
     const V3<T> d = p - co;
-    const T q[3] = {e0.dot(d), e1.dot(d), e2.dot(d)};
-    const T hh[3] = {h.x, h.y, h.z};
-    T a[3], o[3], len2 = T(0);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        a[i] = tabs(q[i]) - hh[i];
-        o[i] = a[i] > T(0) ? a[i] : T(0);
-        len2 += o[i] * o[i];
-    }
-    T nl[3] = {T(0), T(0), T(0)}, sd;
+    const T q0 = e0.dot(d), q1 = e1.dot(d), q2 = e2.dot(d);
+    const T a0 = tabs(q0) - h.x, a1 = tabs(q1) - h.y, a2 = tabs(q2) - h.z;
+    const T o0 = a0 > T(0) ? a0 : T(0), o1 = a1 > T(0) ? a1 : T(0), o2 = a2 > T(0) ? a2 : T(0);
+    const T len2 = (o0 * o0 + o1 * o1) + o2 * o2;
+    T n0, n1, n2, sd;
     if (len2 > T(0)) {
         sd = tsqrt(len2);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) nl[i] = (q[i] < T(0) ? -o[i] : o[i]) / sd;
+        n0 = (q0 < T(0) ? -o0 : o0) / sd;
+        n1 = (q1 < T(0) ? -o1 : o1) / sd;
+        n2 = (q2 < T(0) ? -o2 : o2) / sd;
     } else {
-        int k = 0;
-        if (a[1] > a[k]) k = 1;
-        if (a[2] > a[k]) k = 2;
-        sd = a[k];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) nl[i] = i == k ? (q[i] < T(0) ? T(-1) : T(1)) : T(0);
+        /* inside: the nearest face, lowest index on a tie */
+        const bool k1 = a1 > a0;
+        const T a01 = k1 ? a1 : a0;
+        const bool k2 = a2 > a01;
+        sd = k2 ? a2 : a01;
+        n0 = (!k1 && !k2) ? (q0 < T(0) ? T(-1) : T(1)) : T(0);
+        n1 = (k1 && !k2) ? (q1 < T(0) ? T(-1) : T(1)) : T(0);
+        n2 = k2 ? (q2 < T(0) ? T(-1) : T(1)) : T(0);
     }
-    nOut = e0 * nl[0] + e1 * nl[1] + e2 * nl[2];
+    nOut = e0 * n0 + e1 * n1 + e2 * n2;
     return sd;
 }
 
@@ -1083,6 +1082,15 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                         const V3<T> col0 = b.B * sc.r0, axisDir = b.B * sc.r1, c = b.B * sc.spos + b.x;
                         const T margin = sc.margin, rc = sc.radius - margin, hc = sc.halfLen - margin;
                         const int nPoints = sc.sphere ? 1 : sc.box ? 8 : 5;
+                        {
+                            /* every sample point lies within `reach` of the shape's centre and the distance to the box is
+                               1-Lipschitz: a pair whose centre is further than that from the contact band has no contact (1e-3 of
+                               slack for round-off; no result changes) */
+                            const T hz = sc.box ? sc.halfZ - margin : T(0);
+                            const T reach = sc.sphere ? T(0) : tsqrt(rc * rc + hc * hc + hz * hz);
+                            V3<T> unused;
+                            if (boxDistance(c, co, e0, e1, e2, oh, unused) - reach - margin > SolverConst<T>::breakingThreshold() + T(1e-3)) continue;
+                        }
                         int count = 0;
                         for (int k = 0; k < nPoints && count < 4 && nc < a.cap_contacts; ++k) {
                             V3<T> pc;

@@ -580,16 +580,16 @@ struct tgo_world {
        box: its eight core corners.  A point is a contact when its distance (after the shape's margin; the obstacle counts with
        its full half extents) is within the contact breaking threshold; at most 4 per pair of shapes, in sampling order. */
     void generateObstacleContacts() {
-        /* the device kernel keeps at most cap rows per body (tgb_capi.cu: 4 per shape of the largest body, times 1 + the number of
-           obstacles up to three); the same cap here */
+        /* the device kernel keeps at most cap rows per body (tgb_capi.cu: 4 per shape of the largest dynamic body, times 1 + the
+           number of obstacles up to two); the same cap here */
         int maxShapes = 1, nObst = 0;
         for (const Body& b : bodies) {
-            maxShapes = std::max(maxShapes, b.shapeCount);
-            if (b.invMass == 0.0)
+            if (b.invMass != 0.0) maxShapes = std::max(maxShapes, b.shapeCount);
+            else
                 for (int s = b.shapeBegin; s < b.shapeBegin + b.shapeCount; ++s) nObst += shapes[s].kind == TGB_SHAPE_BOX;
         }
         if (nObst == 0) return;
-        const int cap = 4 * maxShapes * (1 + std::min(nObst, 3));
+        const int cap = 4 * maxShapes * (1 + std::min(nObst, 2));
         std::vector<int> rows(bodies.size(), 0);
         for (const Contact& c : contacts) rows[c.body] += 1;
         for (size_t oi = 0; oi < bodies.size(); ++oi) {
