@@ -281,7 +281,7 @@ __device__ __noinline__ void pgsRowsWithNormals(T* ct, int rowStride, int nc, in
 
 /* Signed distance of a point to an oriented box (centre co, axes e0 e1 e2, half extents h) and the outward direction at the closest
    surface point: outside, the vector from the closest point; inside, the axis of the nearest face (lowest index on a tie). */
-template <typename T>
+template <typename T, bool kFast>
 TGB_D T boxDistance(const V3<T>& p, const V3<T>& co, const V3<T>& e0, const V3<T>& e1, const V3<T>& e2, const V3<T>& h, V3<T>& nOut) {
     /* scalars and selects only: no indexed local arrays */
     const V3<T> d = p - co;
@@ -291,10 +291,19 @@ TGB_D T boxDistance(const V3<T>& p, const V3<T>& co, const V3<T>& e0, const V3<T
     const T len2 = (o0 * o0 + o1 * o1) + o2 * o2;
     T n0, n1, n2, sd;
     if (len2 > T(0)) {
-        sd = tsqrt(len2);
-        n0 = (q0 < T(0) ? -o0 : o0) / sd;
-        n1 = (q1 < T(0) ? -o1 : o1) / sd;
-        n2 = (q2 < T(0) ? -o2 : o2) / sd;
+        if (kFast) {
+            /* single precision: one MUFU.RSQ instead of a square root and three divisions */
+            const T inv = trsqrt(len2);
+            sd = len2 * inv;
+            n0 = (q0 < T(0) ? -o0 : o0) * inv;
+            n1 = (q1 < T(0) ? -o1 : o1) * inv;
+            n2 = (q2 < T(0) ? -o2 : o2) * inv;
+        } else {
+            sd = tsqrt(len2);
+            n0 = (q0 < T(0) ? -o0 : o0) / sd;
+            n1 = (q1 < T(0) ? -o1 : o1) / sd;
+            n2 = (q2 < T(0) ? -o2 : o2) / sd;
+        }
     } else {
         /* inside: the nearest face, lowest index on a tie */
         const bool k1 = a1 > a0;
@@ -1089,7 +1098,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                             const T hz = sc.box ? sc.halfZ - margin : T(0);
                             const T reach = sc.sphere ? T(0) : tsqrt(rc * rc + hc * hc + hz * hz);
                             V3<T> unused;
-                            if (boxDistance(c, co, e0, e1, e2, oh, unused) - reach - margin > SolverConst<T>::breakingThreshold() + T(1e-3)) continue;
+                            if (boxDistance<T, kFast>(c, co, e0, e1, e2, oh, unused) - reach - margin > SolverConst<T>::breakingThreshold() + T(1e-3)) continue;
                         }
                         int count = 0;
                         for (int k = 0; k < nPoints && count < 4 && nc < a.cap_contacts; ++k) {
@@ -1103,19 +1112,24 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                             } else {
                                 const V3<T> pa = c + axisDir * (hc * (T(0.5) * (T)(k - 2)));
                                 V3<T> g;
-                                boxDistance(pa, co, e0, e1, e2, oh, g);
+                                boxDistance<T, kFast>(pa, co, e0, e1, e2, oh, g);
                                 const V3<T> radial = g - axisDir * axisDir.dot(g);
-                                const T rl = radial.length();
-                                pc = rl > T(1e-9) ? pa - radial * (rc / rl) : pa;
+                                if (kFast) {
+                                    const T rl2 = radial.length2();
+                                    pc = rl2 > T(1e-18) ? pa - radial * (rc * trsqrt(rl2)) : pa;
+                                } else {
+                                    const T rl = radial.length();
+                                    pc = rl > T(1e-9) ? pa - radial * (rc / rl) : pa;
+                                }
                             }
                             V3<T> n;
-                            const T dist = boxDistance(pc, co, e0, e1, e2, oh, n) - margin;
+                            const T dist = boxDistance<T, kFast>(pc, co, e0, e1, e2, oh, n) - margin;
                             if (dist <= SolverConst<T>::breakingThreshold()) {
                                 const V3<T> r = (pc - n * margin) - b.x;
                                 const V3<T> rxn = r.cross(n);
                                 const V3<T> angN = b.Iinv * rxn;
                                 const T denom = invMass + n.dot(angN.cross(r));
-                                const T invDiagN = T(1) / denom;
+                                const T invDiagN = kFast ? trcp(denom) : T(1) / denom;
                                 const V3<T> vel = linvel + b.w.cross(r);
                                 const T relVel = n.dot(vel);
                                 T restitution = obstRestitution * -relVel;
@@ -1123,7 +1137,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 const V3<T> lat = vel - n * relVel;
                                 const T lat2 = lat.length2();
                                 V3<T> t;
-                                if (lat2 > epsilonOf<T>()) t = lat * (T(1) / tsqrt(lat2));
+                                if (lat2 > epsilonOf<T>()) t = lat * (kFast ? trsqrt(lat2) : T(1) / tsqrt(lat2));
                                 else t = planeSpace1(n);
                                 const T velDotN = n.dot(linvel + extLin) + rxn.dot(b.w + extAng);
                                 T velocityError = restitution - velDotN;
@@ -1131,8 +1145,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 T erp = SolverConst<T>::erp2();
                                 if (penetration > SolverConst<T>::splitThreshold()) erp = SolverConst<T>::erp();
                                 T positionalError = T(0);
-                                if (penetration > T(0)) velocityError -= penetration / dt;
-                                else positionalError = -penetration * erp / dt;
+                                if (penetration > T(0)) velocityError -= tdiv(penetration, dt);
+                                else positionalError = tdiv(-penetration * erp, dt);
                                 const T penetrationImpulse = positionalError * invDiagN;
                                 const T velocityImpulse = velocityError * invDiagN;
                                 T rhsN, rhsPen;
@@ -1141,7 +1155,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 const V3<T> rxt = r.cross(t);
                                 const V3<T> angT = b.Iinv * rxt;
                                 const T denomT = invMass + t.dot(angT.cross(r));
-                                const T invDiagT = T(1) / denomT;
+                                const T invDiagT = kFast ? trcp(denomT) : T(1) / denomT;
                                 const T relT = t.dot(linvel + extLin) + rxt.dot(b.w);
                                 const T rhsT = (T(0) - relT) * invDiagT;
                                 CT(nc, CT_RXN + 0) = rxn.x; CT(nc, CT_RXN + 1) = rxn.y; CT(nc, CT_RXN + 2) = rxn.z;
