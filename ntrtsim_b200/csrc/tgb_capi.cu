@@ -303,6 +303,8 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
     a.model_crec_off = w->modelCrecOff; a.model_cirec_off = w->modelCirecOff;
     a.n_obst = w->nObst; a.model_obst_off = w->modelObstOff;
+    a.n_dyn = 0;
+    for (int b = 0; b < w->R; ++b) a.n_dyn += w->bodies[b].mass != 0.0;
     a.dt = dt;
     a.gn[0] = w->ground.normal[0]; a.gn[1] = w->ground.normal[1]; a.gn[2] = w->ground.normal[2];
     a.goff = w->ground.offset;

@@ -91,6 +91,7 @@ struct tgb_step_args {
     int ground_kind;
     int model_t_words, model_i_words;
     int model_crec_off, model_cirec_off; /* word offsets of the per-cable records inside model_t / model_i */
+    int n_dyn;                           /* bodies with mass: worlds with obstacles keep contact rows for these only */
     int n_obst, model_obst_off;          /* static obstacles: n_obst pairs (static body, its box shape) at this word offset of model_i */
     double dt;
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */

@@ -570,7 +570,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
        across lanes: no index loads, no bank conflicts. */
     const int jWords = kFast ? a.max_inc * LPE * 8 : 3 * C;
     constexpr int NCT = OBST ? (int)TGB_NCT_OBST : (int)TGB_NCT;
-    const int ctWords = a.cap_contacts * NCT * R; /* rows [slot][body][NCT]: 23 words apart across lanes, conflict-free */
+    const int rowBodies = OBST ? a.n_dyn : R;     /* worlds with obstacles: no rows for the static bodies */
+    const int ctWords = a.cap_contacts * NCT * rowBodies; /* rows [slot][body][NCT]: 23 words apart across lanes, conflict-free */
     /* the contact rows (live from contact generation to the end of the solver) and the cable impulses (live from the cable
        phase to the impulse gather) share one region: shared memory per environment decides how many CTAs an SM holds */
     const int exchangeWords = TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords;
@@ -743,7 +744,13 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     /* a frame tied to a static body never moves: static bodies then stay bit-exactly in place */
     const bool frameMoves = M.body(BF_INVMASS, a.frame_body) != T(0);
 
-#define CT(slot, f) sCt[((slot) * R + bidx) * NCT + (f)]
+    /* row column of this body: its index among the dynamic bodies of the environment when static ones have no rows */
+    int rowIdx = bidx;
+    if (OBST) {
+        const unsigned dynMask = __ballot_sync(fullMask, dynamic);
+        rowIdx = __popc(dynMask & ((1u << warpLane) - 1u) & ~((1u << groupLane0) - 1u));
+    }
+#define CT(slot, f) sCt[((slot) * rowBodies + rowIdx) * NCT + (f)]
 
     /* ---- CPG: CPGNode::updateDTs for this lane's nodes (CPGNode.cpp:71-88). Every lane of the warp calls this the same
        number of times (it synchronises); `act` masks groups that have nothing to do. sin(phi_j - phi_i - theta) is
@@ -1180,7 +1187,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
             if (OBST) {
-                if (nc > 0) pgsRowsWithNormals<T>(sCt + bidx * NCT, R * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
+                if (nc > 0) pgsRowsWithNormals<T>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
             } else if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
                 /* Single precision, one contact point (by far the commonest case: a rod end touching the ground): the matrix form
                    of the solver below for the two rows (normal, friction) of that point, straight-line and branch-free.  The
@@ -1219,7 +1226,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 dLin = bn * lamN + bt * lamT;
                 dAng = angN * lamN + angT * lamT;
             } else if (nc > 0) {
-                const ContactSolveOut<T> o = solveContactsGeneral<T, kFast>(sCt + bidx * NCT, R * NCT, nc, a.iterations, anyPen, gn, invMass, mu);
+                const ContactSolveOut<T> o = solveContactsGeneral<T, kFast>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, gn, invMass, mu);
                 dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
             }
 
@@ -1703,7 +1710,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
     const int groupsPerBlock = a.wide ? 32 / lpe : threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
-    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST : (int)TGB_NCT) * a.R;
+    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST * a.n_dyn : (int)TGB_NCT * a.R);
     int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords);
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
