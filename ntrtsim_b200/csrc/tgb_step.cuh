@@ -963,7 +963,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     const T rc = radius - margin, hc = halfLen - margin;
                     const T na = gn.dot(axisDir);
                     const V3<T> perp = -(gn - axisDir * na);
-                    const T pl = perp.length();
+                    const T pl = kFast ? tsqrtNoBranch(perp.length2()) : perp.length();
                     /* the lowest rim point is at n.c - |n.a| hc - rc |perp| (exact arithmetic; a box: minus the lowest corner's
                        offset in the face instead of rc |perp|): a shape clearly above the contact band contributes nothing (the
                        1e-3 slack covers round-off; no result changes) */
@@ -982,7 +982,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     }
                     if (((gn.dot(c) + originHeight) - margin) - tabs(na) * hc - faceDrop > SolverConst<T>::breakingThreshold() + T(1e-3)) continue;
                     V3<T> u;
-                    if (pl > T(1e-9)) u = perp / pl;
+                    if (pl > T(1e-9)) u = kFast ? perp * trcp(pl) : perp / pl;
                     else u = col0;
                     V3<T> wdir = axisDir.cross(u);
                     T rr = rc; /* candidate k sits at ce +- rr u or ce +- rr wdir */
