@@ -465,9 +465,13 @@ struct CableRegs {
     T L, k, damp, tVel, maxTens, maxStretch, minAL, minRL;
     T rest, prev, pref, motorVel, desiredTorque, velocity;
     /* tgBasicActuator::moveMotors, tgBasicActuator.cpp:170-225 */
-    TGB_D void moveMotors(T dtm, bool enable = true) {
-        /* written with selects only: the same values as the reference's branches, no divergence in the cable phase */
-        const T stepSize = tVel * dtm;
+    TGB_D void moveMotors(T dtm, bool enable = true, T stepScale = T(1)) {
+        /* written with selects only: the same values as the reference's branches, no divergence in the cable phase.
+           stepScale = 2 stands for two consecutive calls with the same preferred length (EscapeController moves every motor twice
+           per step): two clamped moves towards one target are one move clamped at twice the step -- the tension clamp of the
+           preferred length is idempotent, the sign of the remaining difference and the length test do not change between the
+           calls, and the minimum rest length clamps the sum the same way.  Equal in exact arithmetic; used in single precision. */
+        const T stepSize = tVel * dtm * stepScale;
         const T newPref = ((L - pref) * k > maxTens) ? L - maxStretch : pref;
         const T diff = newPref - rest;
         const T move = (tabs(diff) > stepSize) ? tcopysign(stepSize, diff) : diff; /* (diff / |diff|) * stepSize, exactly */
@@ -527,6 +531,9 @@ TGB_HOST_DEVICE_INLINE int tgb_ctrl_class(int kind) {
    not depend on the lane that runs it: results are bit-identical to the narrow layout. */
 /* Register budgets: the narrow layout is capped by shared memory at 8 one-warp CTAs per SM, so its lanes may take what ptxas wants
    (minBlocks 1: 209 registers instead of 163, +3.3 % on B200); the four-warp layout needs three CTAs per SM (168 registers). */
+#ifndef TGB_FUSE_DOUBLE_MOVE
+#define TGB_FUSE_DOUBLE_MOVE 1
+#endif
 #ifndef TGB_NARROW_MINBLOCKS
 #define TGB_NARROW_MINBLOCKS 1
 #endif
@@ -1455,6 +1462,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                         else if (newLength >= maxLength) newLength = maxLength;
                         const bool accept = !(newLength < T(0));
                         q.pref = accept ? newLength : q.pref;
+                        if (kFast && TGB_FUSE_DOUBLE_MOVE) {
+                            q.moveMotors(dt, true, accept ? T(2) : T(1)); /* both moves of this step in one */
+                            continue;
+                        }
                         q.moveMotors(dt, accept);
                     }
                     q.moveMotors(dt); /* EscapeController.cpp:108-116: every muscle's motors move a second time */
