@@ -100,7 +100,11 @@ typedef enum {
     TGB_SHAPE_SPHERE = 1,   /* btSphereShape (tgSphereInfo.cpp:100-115): a point with collision margin = radius; set
                                half_length = margin = radius */
     TGB_SHAPE_BOX = 2       /* btBoxShape(width, length / 2, height) (tgBoxInfo.cpp:100-118): half extents radius (local X),
-                               half_length (local Y, the pair's axis) and half_extent_z */
+                               half_length (local Y, the pair's axis) and half_extent_z.  A box shape of a STATIC body (mass 0: the
+                               obstacle models of src/models/obstacles are tgBoxInfo structures with density 0) is an obstacle:
+                               every dynamic body of the environment collides with it, with the friction and restitution of the
+                               two bodies multiplied.  Static cylinders / spheres only anchor cables (tsTestRig), nothing collides
+                               with them. */
 } tgb_shape_kind;
 
 /* One collision primitive of a body. */
