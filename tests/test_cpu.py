@@ -403,3 +403,122 @@ def test_data_logger_schema_and_errors(tmp_path):
     assert b"Time interval must be nonnegative" in h.tgh_last_error()
     assert h.tgh_run_example_logged(b"3_prism", 1, 0, 0, b"/nonexistent_dir/x", 0.0, 0, buf, 512) == capi.TGB_ERR_RUNTIME
     assert b"Log file could not be opened" in h.tgh_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ contact: analytic known answers
+# Bullet is not in the reference tree, so the contact half of the step cannot be pinned against it; these tests pin
+# it against mechanics instead: Coulomb friction, rolling without slipping, and the sliding threshold on an incline.
+BALL = """
+nodes:
+  ball: [0, 2.0, 0]
+builders:
+  ball:
+    class: tgSphereInfo
+    parameters:
+      radius: 0.5
+      density: 1.0
+      friction: 1.0
+      roll_friction: 0.0
+      restitution: 0.0
+"""
+
+BRICK = """
+nodes:
+  p0: [0, 0, -1]
+  p1: [0, 0, 1]
+pair_groups:
+  box:
+    - [p0, p1]
+builders:
+  box:
+    class: tgBoxInfo
+    parameters:
+      width: 0.6
+      height: 0.3
+      density: 1.0
+      friction: 0.9
+      roll_friction: 0.0
+      restitution: 0.0
+"""
+
+
+def _build_text(tmp_path, name, text):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_yaml import write
+    from ntrtsim_b200 import examples
+    return examples.build_yaml(write(tmp_path, name, text))
+
+
+def sliding_ball_expectations(model, v0=10.0):
+    mu = model.bodies[0].friction * model.ground.friction  # 1.0 x 0.5 (btBoxGround never applies its Config friction: Bullet default)
+    g = model.gravity
+    t_roll = 2.0 * v0 / (7.0 * mu * g)  # solid sphere (I = 2/5 m r^2): slipping ends when v = 5/7 v0
+    return mu, g, t_roll, 5.0 / 7.0 * v0
+
+
+def test_oracle_sliding_ball_ends_rolling_at_five_sevenths(tmp_path):
+    """A ball set sliding at v0 on the flat ground decelerates at mu g while it slips, spins up, and rolls without slipping at
+    5/7 v0 from t = 2 v0 / (7 mu g) on (rolling friction 0)."""
+    m = _build_text(tmp_path, "ball.yaml", BALL)
+    assert abs(m.bodies[0].inertia[0] - 0.4 * m.bodies[0].mass * 0.25) < 1e-12  # btSphereShape::calculateLocalInertia
+    mu, g, t_roll, v_roll = sliding_ball_expectations(m)
+    rods = m.initial_rod_state()
+    rods[0, 7] = 10.0
+    o = _oracle(m, rods)
+    n_mid = int(0.5 * t_roll / m.dt)
+    o.step(m.dt, n_mid)
+    s = o.get_rod_state()
+    assert abs(s[0, 7] - (10.0 - mu * g * n_mid * m.dt)) < 0.02 * 10.0          # Coulomb deceleration while slipping
+    assert abs(s[0, 12] - (-2.5 * mu * g * n_mid * m.dt / 0.5)) < 0.02 * 20.0   # spin-up: dw/dt = -(5/2) mu g / r about z
+    o.step(m.dt, int(2.0 * t_roll / m.dt))
+    s = o.get_rod_state()
+    assert abs(s[0, 7] - v_roll) < 0.01 * v_roll, s[0, 7:13]
+    assert abs(s[0, 12] + s[0, 7] / 0.5) < 0.01 * v_roll / 0.5                  # v = -w_z r: no slip
+    v_then = s[0, 7]
+    o.step(m.dt, 200)
+    assert abs(o.get_rod_state()[0, 7] - v_then) < 1e-3 * v_then                # and it keeps rolling
+    assert abs(o.get_rod_state()[0, 1] - 2.0) < 0.03
+
+
+def incline(model, theta):
+    """The model's ground turned into a slope of angle theta rising along +x, through the point (0, 1.5, 0)."""
+    model.ground.normal[0], model.ground.normal[1], model.ground.normal[2] = -math.sin(theta), math.cos(theta), 0.0
+    model.ground.offset = 1.5 * math.cos(theta)
+    return model
+
+
+def brick_on_incline_state(model, theta):
+    """The brick (half extents 0.6 across, 0.3 thick after the builder's frame: local Z = thickness) lying on the slope at rest."""
+    rods = model.initial_rod_state()
+    n = np.array([-math.sin(theta), math.cos(theta), 0.0])
+    # builder frame: local Y along the pair (world z), local X = width -> world x, local Z = height -> world -y; turn about z by theta
+    q_tilt = np.array([0.0, 0.0, math.sin(theta / 2), math.cos(theta / 2)])
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import quat_mul
+    rods[0, 3:7] = quat_mul(q_tilt[None], rods[0, 3:7][None])[0]
+    rods[0, 0:3] = np.array([0.0, 1.5, 0.0]) + n * (0.3 + 0.01)
+    return rods
+
+
+@pytest.mark.parametrize("theta,slides", [(0.30, False), (0.60, True)])
+def test_oracle_brick_on_incline_sticks_below_the_friction_angle(tmp_path, theta, slides):
+    """mu = 0.9 x 0.5 = 0.45 (friction angle 0.42 rad): a brick on a 0.30 rad slope stays put, on a 0.60 rad slope it slides down with
+    a = g (sin theta - mu cos theta)."""
+    m = incline(_build_text(tmp_path, "brick.yaml", BRICK), theta)
+    mu = m.bodies[0].friction * m.ground.friction
+    o = _oracle(m, brick_on_incline_state(m, theta))
+    o.step(m.dt, 100)  # settle onto the slope
+    s0 = o.get_rod_state().copy()
+    T = 0.2
+    o.step(m.dt, int(T / m.dt))
+    s1 = o.get_rod_state()
+    down = np.array([-math.cos(theta), -math.sin(theta), 0.0])
+    travelled = float(np.dot(s1[0, 0:3] - s0[0, 0:3], down))
+    v_down = float(np.dot(s1[0, 7:10], down))
+    if not slides:
+        # a velocity-level friction row without position correction creeps a little (3 mm here); frictionless it would travel 0.58
+        assert abs(travelled) < 0.01 and abs(v_down) < 0.05, (travelled, v_down)
+    else:
+        a = m.gravity * (math.sin(theta) - mu * math.cos(theta))
+        v_start = float(np.dot(s0[0, 7:10], down))
+        assert abs((v_down - v_start) - a * T) < 0.03 * a * T, (v_down - v_start, a * T)

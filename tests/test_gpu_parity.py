@@ -979,3 +979,43 @@ def test_obstacle_models_match_oracle(scene):
     # round-off level except for the environments that sit on a face / edge switch of the sampling scheme (the wall's top edge
     # under a rod: 3 of 12 environments at 1e-8 .. 4e-7 after 250 steps)
     assert np.sum(per_env < 1e-8) >= (2 * n_env) // 3 and per_env.max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ contact: analytic known answers
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_sliding_ball_and_incline_known_answers_on_device(tmp_path, precision):
+    """The analytic pins of the contact half (tests/test_cpu.py: Coulomb deceleration and 5/7 v0 rolling speed of a sliding ball; a brick
+    sticks below the friction angle and slides with g (sin theta - mu cos theta) above it) asked of the CUDA path itself."""
+    import math
+    from test_cpu import BALL, BRICK, _build_text, sliding_ball_expectations, incline, brick_on_incline_state
+    m = _build_text(tmp_path, "ball.yaml", BALL)
+    mu, g, t_roll, v_roll = sliding_ball_expectations(m)
+    n_env = 8
+    v0 = np.linspace(6.0, 13.0, n_env)  # every environment its own launch speed
+    rods = np.tile(m.initial_rod_state(), (n_env, 1, 1))
+    rods[:, 0, 7] = v0
+    steps = int(3.0 * (2.0 * v0.max() / (7.0 * mu * g)) / m.dt)
+    rd, _, st = device_rollout(m, rods, np.zeros((n_env, 0, 2)), steps, precision)
+    assert not st.any()
+    assert np.allclose(rd[:, 0, 7], 5.0 / 7.0 * v0, rtol=0.01)
+    assert np.allclose(rd[:, 0, 12], -rd[:, 0, 7] / 0.5, rtol=0.01)
+    for theta, slides in ((0.30, False), (0.60, True)):
+        b = incline(_build_text(tmp_path, "brick.yaml", BRICK), theta)
+        mub = b.bodies[0].friction * b.ground.friction
+        start = np.tile(brick_on_incline_state(b, theta), (4, 1, 1))
+        w = nt.BatchedWorld(b, 4, precision=precision)
+        try:
+            w.set_rod_state(start)
+            w.step(b.dt, 100)
+            s0 = w.get_rod_state()
+            w.step(b.dt, 200)
+            s1 = w.get_rod_state()
+        finally:
+            w.close()
+        down = np.array([-math.cos(theta), -math.sin(theta), 0.0])
+        dv = (s1[:, 0, 7:10] - s0[:, 0, 7:10]) @ down
+        if slides:
+            a = b.gravity * (math.sin(theta) - mub * math.cos(theta))
+            assert np.allclose(dv, a * 0.2, rtol=0.03), dv
+        else:
+            assert np.abs((s1[:, 0, 0:3] - s0[:, 0, 0:3]) @ down).max() < 0.01 and np.abs(s1[:, 0, 7:10] @ down).max() < 0.05
