@@ -522,3 +522,15 @@ def test_oracle_brick_on_incline_sticks_below_the_friction_angle(tmp_path, theta
         a = m.gravity * (math.sin(theta) - mu * math.cos(theta))
         v_start = float(np.dot(s0[0, 7:10], down))
         assert abs((v_down - v_start) - a * T) < 0.03 * a * T, (v_down - v_start, a * T)
+
+
+def test_oracle_hanging_rod_settles_at_weight_over_stiffness():
+    """The motor rig left alone (src/examples/motorModel/tsTestRig.cpp: a rod hanging from a static rod by one cable, k = 1000,
+    c = 10): at rest the cable carries the rod's weight, stretch = m g / k -- whatever the damping law does on the way."""
+    m = nt.build_example("tsTestRig_basic")
+    weight = [b.mass for b in m.bodies if b.mass != 0.0][0] * m.gravity
+    o = _oracle(m)
+    o.step(m.dt, 6000)
+    rest, length, tension, _ = o.get_cable_obs()[0]
+    assert abs(tension - weight) < 2e-3 * weight, (tension, weight)
+    assert abs((length - rest) - weight / m.cables[0].stiffness) < 2e-3 * weight / m.cables[0].stiffness
