@@ -482,6 +482,11 @@ struct CableRegs {
     }
 };
 
+/* CPG coupling lists of up to 512 words are staged into shared memory (see the kernel) */
+__host__ __device__ inline bool tgb_cpg_topo_staged(const tgb_step_args& a) {
+    return a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE && (a.C + 1) + 2 * a.cpg_n_couplings <= 512;
+}
+
 /* doubles of shared memory per env group: controller row, sine cumulative phases, CPG work space */
 __host__ __device__ inline int tgb_group_double_words(const tgb_step_args& a) {
     int n = a.ctrl_stride + 8;
@@ -762,15 +767,25 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     /* ---- CPG: CPGNode::updateDTs for this lane's nodes (CPGNode.cpp:71-88). Every lane of the warp calls this the same
        number of times (it synchronises); `act` masks groups that have nothing to do. sin(phi_j - phi_i - theta) is
        expanded over the published (sin phi, cos phi) of the nodes and the precomputed (cos theta, sin theta). */
-    const int* topoBegin = a.cpg_topo;
-    const int* topoTarget = a.cpg_topo + (C + 1);
+    /* the coupling lists are read in every stage of the integrator: short ones are staged into shared memory behind the model's
+       ints (TetraSpine: 205 words, +4 %); long ones stay in global memory / L1 -- for the 12-vertebra spine (several thousand words)
+       the extra shared memory costs resident CTAs: 9.7e6 -> 6.5e6 env-steps/s when staged */
+    int* sTopo = sModelI + ((a.model_i_words + 3) & ~3);
+    const bool stageTopo = cpgOn && tgb_cpg_topo_staged(a);
+    if (stageTopo) {
+        const int topoWords = (C + 1) + 2 * a.cpg_n_couplings;
+        for (int i = tid; i < topoWords; i += blockDim.x) sTopo[i] = a.cpg_topo[i];
+        __syncthreads();
+    }
+    const int* topoBegin = stageTopo ? sTopo : a.cpg_topo;
+    const int* topoTarget = topoBegin + (C + 1);
     const int* topoPair = topoTarget + a.cpg_n_couplings;
     auto cpgRhs = [&](const double* xin, double* kout, bool act) {
         if (act)
             for (int i = lane; i < C; i += LPE) {
                 double sn, cn;
                 sincos(xin[3 * i], &sn, &cn);
-                sTrig[3 * i] = sn; sTrig[3 * i + 1] = cn; sTrig[3 * i + 2] = xin[3 * i + 1];
+                sTrig[i] = sn; sTrig[C + i] = cn; sTrig[2 * C + i] = xin[3 * i + 1]; /* planes: no bank conflicts in the gather below */
             }
         __syncwarp();
         if (act) {
@@ -779,11 +794,11 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             const double freq = inRange ? sCtrl[0] * d + sCtrl[0] : 0.0;   /* nodeEquation(d, c0, c1) with c0 = c1 */
             const double radius = inRange ? sCtrl[1] * d + sCtrl[1] : 0.0;
             for (int i = lane; i < C; i += LPE) {
-                const double si = sTrig[3 * i], ci = sTrig[3 * i + 1];
+                const double si = sTrig[i], ci = sTrig[C + i];
                 double phiDot = 2 * 3.14159265358979323846 * freq;
                 for (int k = topoBegin[i]; k < topoBegin[i + 1]; ++k) {
                     const int j = topoTarget[k], p = topoPair[k];
-                    const double sj = sTrig[3 * j], cj = sTrig[3 * j + 1], rj = sTrig[3 * j + 2];
+                    const double sj = sTrig[j], cj = sTrig[C + j], rj = sTrig[2 * C + j];
                     const double sd = sj * ci - cj * si, cd = cj * ci + sj * si;
                     phiDot += sPair[3 * p] * rj * (sd * sPair[3 * p + 1] - cd * sPair[3 * p + 2]);
                 }
@@ -1729,7 +1744,8 @@ inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, 
     size_t bytes = (size_t)(modelTWords + groupsPerBlock * groupTWords) * sizeofT;
     bytes = (bytes + 7) & ~(size_t)7;
     bytes += (size_t)groupsPerBlock * groupDWords * sizeof(double);
-    bytes += (size_t)a.model_i_words * sizeof(int);
+    bytes += (size_t)((a.model_i_words + 3) & ~3) * sizeof(int);
+    if (tgb_cpg_topo_staged(a)) bytes += (size_t)((a.C + 1) + 2 * a.cpg_n_couplings) * sizeof(int);
     return bytes + 16;
 }
 
