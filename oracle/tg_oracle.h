@@ -28,8 +28,10 @@
  * own sources compiled in place (oracle/_ref, see oracle/ref/README.md) through tests/golden/.
  * Piece (3) rigid-body integration is pinned by analytic invariants; piece (4) contact has no per-step
  * pin ("parity unpinned" step by step): Bullet's GJK/persistent-manifold narrowphase and its Dantzig LCP
- * solver are replaced here by an analytic cylinder-rim / sphere manifold and fixed-iteration projected
- * Gauss-Seidel.  The whole path, contact included, is pinned at the level of a percent by the reference
+ * solver are replaced here by an analytic cylinder-rim / sphere / box-corner manifold against the ground, a
+ * sample-point manifold against the box shapes of static bodies (obstacles), and fixed-iteration projected
+ * Gauss-Seidel; its friction and normal rows are checked against mechanics (sliding ball, brick on an incline:
+ * tests/test_cpu.py).  The whole path, contact included, is pinned at the level of a percent by the reference
  * suite's own known-answer test test_integration/ICRA2015Tests/ICRA2015_test.cpp (maxima of six cable
  * tensions over 60000 steps against hardware, with the reference simulator's own errors as bounds):
  * tests/test_golden.py::test_icra2015_hardware_comparison_of_the_reference_test_suite.
