@@ -407,3 +407,52 @@ def test_shipped_structure_files_load():
         if rel in want:
             assert (m.n_bodies, m.n_cables) == want[rel], rel
     assert seen >= 27
+
+
+def test_scale_kinematic_actuators_and_spheres(tmp_path):
+    """`scale` of a substructure (about its own centroid), tgKinematicActuatorInfo parameters and tgSphereInfo at tagged nodes."""
+    write(tmp_path, "base/Prism.yaml", BASE_PRISM)
+    path = write(tmp_path, "scaled.yaml", """
+substructures:
+  big:
+    path: base/Prism.yaml
+    scale: 2
+    translation: [0, 10, 0]
+nodes:
+  weight: [0, 30, 0]
+pair_groups:
+  motor:
+    - [weight, big.top1]
+builders:
+  weight:
+    class: tgSphereInfo
+    parameters:
+      radius: 0.75
+      density: 2.0
+  motor:
+    class: tgKinematicActuatorInfo
+    parameters:
+      stiffness: 1500
+      damping: 20
+      radius: 0.05
+      motor_inertia: 0.8
+      motor_friction: 0.1
+      back_drivable: 1
+      max_tension: 900
+      target_velocity: 50
+""")
+    m = examples.build_yaml(path)
+    assert (m.n_bodies, m.n_cables) == (4, 10)
+    rods = m.initial_rod_state()
+    lengths = sorted(2 * m.shapes[b.shape_begin].half_length for b in m.bodies if m.shapes[b.shape_begin].kind == 0)
+    base = np.sqrt(6.0 ** 2 + 8.0 ** 2 + 3.4641016151377544 ** 2)  # bottom1 (4,0,0) -> top1 (-2,8,3.46)
+    assert np.allclose(lengths, 2 * base)
+    ball = [b for b in m.bodies if m.shapes[b.shape_begin].kind == 1][0]
+    assert abs(ball.mass - float(np.float32(4.0 / 3.0 * np.pi * 0.75 ** 3 * 2.0))) < 1e-9
+    motor = [c for c in m.cables if c.actuator == 2]
+    assert len(motor) == 1
+    c = motor[0]
+    assert (c.stiffness, c.damping, c.motor_radius, c.motor_inertia, c.motor_friction, c.backdrivable, c.max_tension, c.target_velocity) == \
+        (1500.0, 20.0, 0.05, 0.8, 0.1, 1, 900.0, 50.0)
+    # the scaled prism is centred where the unscaled one was (centroid (0, 4, 0)) before the translation by 10
+    assert np.allclose(rods[[i for i, b in enumerate(m.bodies) if m.shapes[b.shape_begin].kind == 0], 0:3].mean(axis=0), [0, 14, 0], atol=1e-9)
