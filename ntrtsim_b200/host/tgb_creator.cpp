@@ -740,7 +740,19 @@ void tgStructureInfo::autoCompoundRigids() {
         } else {
             std::sort(group.begin(), group.end());
             tgCompoundRigidInfo* c = new tgCompoundRigidInfo();
+            /* every member carries the tag "compound_" + six characters of [0-9A-Za-z] by which tgCompoundRigidSensorInfo finds the
+               members of one compound (tgRigidAutoCompound.cpp:146-157; the reference draws the characters from a random device,
+               here a counter-seeded generator: tags are unique per process and reproducible) */
+            static unsigned long long compoundCounter = 0;
+            unsigned long long h = (++compoundCounter) * 6364136223846793005ULL + 1442695040888963407ULL;
+            static const char alphanum[] = "0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz";
+            std::string compoundTag = "compound_";
+            for (int k = 0; k < 6; ++k) {
+                h = h * 6364136223846793005ULL + 1442695040888963407ULL;
+                compoundTag += alphanum[(h >> 33) % 62];
+            }
             for (std::size_t g = 0; g < group.size(); ++g) {
+                all[group[g]]->addTags(compoundTag);
                 c->addRigid(*all[group[g]]);
                 all[group[g]]->setRigidInfoGroup(c);
             }

@@ -375,6 +375,7 @@ tgBaseRigid::tgBaseRigid(tgWorldB200Impl* world, int body, double mass, const tg
     if (!world || body < 0) throw std::invalid_argument("tgBaseRigid: no body");
 }
 btVector3 tgBaseRigid::centerOfMass(int env) const { return m_world->bodyPosition(m_body, env); }
+btQuaternion tgBaseRigid::orientationQuaternion(int env) const { return m_world->bodyOrientation(m_body, env); }
 btVector3 tgBaseRigid::orientation(int env) const {
     btMatrix3x3 rot(m_world->bodyOrientation(m_body, env));
     btScalar yaw = 0, pitch = 0, roll = 0;

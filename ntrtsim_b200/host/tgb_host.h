@@ -359,6 +359,7 @@ public:
     /* yaw, pitch, roll of the body (tgBaseRigid.cpp:92-103) */
     virtual btVector3 orientation() const { return orientation(0); }
     btVector3 orientation(int env) const;
+    btQuaternion orientationQuaternion(int env = 0) const; /* btRigidBody::getOrientation */
     int bodyIndex() const { return m_body; }
 protected:
     tgBaseRigid(tgWorldB200Impl* world, int body, double mass, const tgTags& tags);

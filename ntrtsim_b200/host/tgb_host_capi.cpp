@@ -214,6 +214,7 @@ int tgh_run_example_logged(const char* name, int n_env, int precision, int steps
         logger->addSenseable(e->model);
         logger->addSensorInfo(new tgRodSensorInfo());
         logger->addSensorInfo(new tgSpringCableActuatorSensorInfo());
+        logger->addSensorInfo(new tgCompoundRigidSensorInfo()); /* as in src/examples/.../AppHorizontalSpine.cpp */
         e->sim->addDataManager(logger);
         e->sim->run(steps);
         if (file_name_out && file_name_cap > 0) {

@@ -3,6 +3,9 @@
  */
 #include "tgb_sensors.h"
 
+#include <algorithm>
+#include <cctype>
+#include <cmath>
 #include <cstdlib>
 #include <ctime>
 #include <iostream>
@@ -85,6 +88,105 @@ bool tgSpringCableActuatorSensorInfo::isThisMySenseable(tgSenseable* pSenseable)
 std::vector<tgSensor*> tgSpringCableActuatorSensorInfo::createSensorsIfAppropriate(tgSenseable* pSenseable) {
     if (!isThisMySenseable(pSenseable)) throw std::invalid_argument("pSenseable is NOT a tgSpringCableActuator, inside tgSpringCableActuatorSensorInfo.");
     return std::vector<tgSensor*>(1, new tgSpringCableActuatorSensor(dynamic_cast<tgSpringCableActuator*>(pSenseable)));
+}
+
+/* ---- compound rigid bodies --------------------------------------------------------------------------------- */
+tgCompoundRigidSensor::tgCompoundRigidSensor(tgModel* pModel) : tgSensor(pModel) {
+    throw std::invalid_argument("Called the constructor for tgCompoundRigidSensor with only a pointer, NOT a tag. That's not allowed, a specific compound tag must be passed in also.");
+}
+tgCompoundRigidSensor::tgCompoundRigidSensor(tgModel* pModel, std::string tag) : tgSensor(pModel), m_tag(tag) {
+    if (pModel == 0) throw std::invalid_argument("Pointer to pModel is NULL inside tgCompoundRigidSensor.");
+    m_rigids = pModel->find<tgBaseRigid>(m_tag);
+    if (m_rigids.empty()) throw std::runtime_error("tgCompoundRigidSensor found no rigid bodies with its tag - something is wrong (inside constructor.)");
+    origOrientQuatInv = m_rigids[0]->orientationQuaternion(0).inverse();
+}
+btVector3 tgCompoundRigidSensor::getCenterOfMass() {
+    btVector3 com(0.0, 0.0, 0.0);
+    for (std::size_t i = 0; i < m_rigids.size(); ++i) com += m_rigids[i]->centerOfMass(m_env);
+    com /= (btScalar)m_rigids.size();
+    return com;
+}
+btVector3 tgCompoundRigidSensor::getOrientation() {
+    const btQuaternion diff = m_rigids[0]->orientationQuaternion(m_env) * origOrientQuatInv;
+    btMatrix3x3 rot(diff);
+    btScalar yaw = 0.0, pitch = 0.0, roll = 0.0;
+    rot.getEulerYPR(yaw, pitch, roll);
+    return btVector3(180 / M_PI * yaw, 180 / M_PI * pitch, 180 / M_PI * roll);
+}
+double tgCompoundRigidSensor::getMass() {
+    double mass = 0;
+    for (std::size_t i = 0; i < m_rigids.size(); ++i) mass += m_rigids[i]->mass();
+    return mass;
+}
+std::vector<std::string> tgCompoundRigidSensor::getSensorDataHeadings() {
+    const std::string prefix = "compound(" + m_tag;
+    const char* fields[7] = {").X", ").Y", ").Z", ").YawDegrees", ").PitchDegrees", ").RollDegrees", ").mass"};
+    std::vector<std::string> headings;
+    for (int i = 0; i < 7; ++i) headings.push_back(prefix + fields[i]);
+    return headings;
+}
+std::vector<std::string> tgCompoundRigidSensor::getSensorData() {
+    const btVector3 com = getCenterOfMass(), orient = getOrientation();
+    std::vector<std::string> data;
+    for (int i = 0; i < 3; ++i) data.push_back(number(com[i]));
+    for (int i = 0; i < 3; ++i) data.push_back(number(orient[i]));
+    data.push_back(number(getMass()));
+    return data;
+}
+namespace {
+/* "compound_" followed by six word characters */
+bool findCompoundTag(const std::string& tags, std::string& matched) {
+    const std::string prefix = "compound_";
+    for (std::size_t pos = tags.find(prefix); pos != std::string::npos; pos = tags.find(prefix, pos + prefix.size())) {
+        if (tags.size() < pos + prefix.size() + 6) continue;
+        bool ok = true;
+        for (std::size_t i = 0; i < 6; ++i) {
+            const unsigned char ch = (unsigned char)tags[pos + prefix.size() + i];
+            ok = ok && (std::isalnum(ch) || ch == '_');
+        }
+        if (ok) { matched = tags.substr(pos, prefix.size() + 6); return true; }
+    }
+    return false;
+}
+} // namespace
+std::map<std::string, int> tgCompoundRigidSensorInfo::getCompoundTags(tgModel* pModel) {
+    std::map<std::string, int> compounds;
+    std::vector<tgModel*> descendants = pModel->getDescendants();
+    for (std::size_t i = 0; i < descendants.size(); ++i) {
+        std::string matched;
+        if (!findCompoundTag(joinTags(descendants[i]->getTags()), matched)) continue;
+        if (dynamic_cast<tgBaseRigid*>(descendants[i]) == 0)
+            throw std::runtime_error("A tgModel that is NOT a rigid body has a compound tag attached to it. Only rigid bodies should have compound tags.");
+        compounds[matched] += 1;
+    }
+    return compounds;
+}
+bool tgCompoundRigidSensorInfo::isThisMySenseable(tgSenseable* pSenseable) {
+    if (pSenseable == 0) throw std::invalid_argument("pSenseable was NULL inside tgCompoundRigidSensorInfo.");
+    tgModel* pModel = dynamic_cast<tgModel*>(pSenseable);
+    if (pModel == 0) return false;
+    const std::map<std::string, int> compounds = getCompoundTags(pModel);
+    for (std::map<std::string, int>::const_iterator it = compounds.begin(); it != compounds.end(); ++it) {
+        if (it->second >= 2) {
+            if (std::find(blacklist.begin(), blacklist.end(), it->first) == blacklist.end()) return true;
+        } else if (it->second == 1) {
+            throw std::runtime_error("There is only one object with a compound tag. That's not possible, compound tgModels should be at least two objects. Exiting.");
+        }
+    }
+    return false;
+}
+std::vector<tgSensor*> tgCompoundRigidSensorInfo::createSensorsIfAppropriate(tgSenseable* pSenseable) {
+    if (!isThisMySenseable(pSenseable))
+        throw std::invalid_argument("pSenseable is NOT a valid tgModel or does not have non-blacklisted compound rigid bodies, inside tgCompoundRigidSensorInfo.");
+    tgModel* pModel = dynamic_cast<tgModel*>(pSenseable);
+    std::map<std::string, int> compounds = getCompoundTags(pModel);
+    for (std::size_t i = 0; i < blacklist.size(); ++i) compounds.erase(blacklist[i]);
+    std::vector<tgSensor*> sensors;
+    for (std::map<std::string, int>::const_iterator it = compounds.begin(); it != compounds.end(); ++it) {
+        sensors.push_back(new tgCompoundRigidSensor(pModel, it->first));
+        blacklist.push_back(it->first);
+    }
+    return sensors;
 }
 
 /* ---- data manager ------------------------------------------------------------------------------------------ */

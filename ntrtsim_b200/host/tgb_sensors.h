@@ -11,6 +11,7 @@
 #include "tgb_host.h"
 
 #include <fstream>
+#include <map>
 
 /* One sensor on one senseable object (tgSensor.h:44-104): headings "type(tags).field", data as strings. */
 class tgSensor {
@@ -57,6 +58,34 @@ class tgSpringCableActuatorSensorInfo : public tgSensorInfo {
 public:
     bool isThisMySenseable(tgSenseable* pSenseable);
     std::vector<tgSensor*> createSensorsIfAppropriate(tgSenseable* pSenseable);
+};
+
+/* compound(tag).X Y Z YawDegrees PitchDegrees RollDegrees mass for the rigids that share one "compound_XXXXXX" tag
+   (tgCompoundRigidSensor.cpp:59-262): position = mean of the members' centres of mass, orientation = the first member's rotation
+   since the sensor was made, mass = sum of the members' mass() -- each of which is the mass of the shared body, as in the reference. */
+class tgCompoundRigidSensor : public tgSensor {
+public:
+    explicit tgCompoundRigidSensor(tgModel* pModel);               /* always std::invalid_argument: a tag is required */
+    tgCompoundRigidSensor(tgModel* pModel, std::string tag);      /* no rigid with the tag -> std::runtime_error */
+    std::vector<std::string> getSensorDataHeadings();
+    std::vector<std::string> getSensorData();
+    btVector3 getCenterOfMass();
+    btVector3 getOrientation();
+    double getMass();
+private:
+    std::string m_tag;
+    std::vector<tgBaseRigid*> m_rigids;
+    btQuaternion origOrientQuatInv;
+};
+/* One sensor per compound tag found among a model's descendants; tags already served are blacklisted so that the same compound is not
+   sensed again through a child model (tgCompoundRigidSensorInfo.cpp:93-230). */
+class tgCompoundRigidSensorInfo : public tgSensorInfo {
+public:
+    bool isThisMySenseable(tgSenseable* pSenseable);
+    std::vector<tgSensor*> createSensorsIfAppropriate(tgSenseable* pSenseable);
+private:
+    std::map<std::string, int> getCompoundTags(tgModel* pModel);
+    std::vector<std::string> blacklist;
 };
 
 /* Owns sensor infos and sensors; setup() creates the sensors of every senseable and its descendants (tgDataManager.cpp:86-139). */

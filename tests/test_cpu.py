@@ -405,6 +405,30 @@ def test_data_logger_schema_and_errors(tmp_path):
     assert b"Log file could not be opened" in h.tgh_last_error()
 
 
+def test_data_logger_compound_rigid_sensors(tmp_path):
+    """tgCompoundRigidSensorInfo (src/sensors/tgCompoundRigidSensor{,Info}.cpp): the members of an auto-compounded body share a tag
+    "compound_XXXXXX" (tgRigidAutoCompound.cpp:146-157) and the logger gets one compound sensor per tag -- TetraSpine: 3 segments of 6
+    rods -- with the headings compound(tag).X ... .mass, next to the 18 rod and 12 cable sensors."""
+    import ctypes as C
+    h = capi.load_host()
+    buf = C.create_string_buffer(512)
+    rc = h.tgh_run_example_logged(b"TetraSpine", 1, 0, 0, str(tmp_path / "spine").encode(), 0.0, 0, buf, 512)
+    assert rc == 0, h.tgh_last_error()
+    lines = open(buf.value.decode()).read().split("\n")
+    assert re.match(r".* with 33 sensors on 1 senseable objects\.$", lines[0]), lines[0]
+    cols = lines[1].split(",")[1:-1]
+    compound = [c for c in cols if "_compound(" in c]
+    tags = sorted(set(re.findall(r"compound\((compound_\w{6})\)", " ".join(compound))))
+    assert len(tags) == 3 and len(compound) == 3 * 7
+    first = [c.split(".", 1)[1] for c in compound[:7]]
+    assert first == ["X", "Y", "Z", "YawDegrees", "PitchDegrees", "RollDegrees", "mass"]
+    # every rod of a segment carries its segment's compound tag
+    rods = [c for c in cols if "_rod(" in c and c.endswith(".X")]
+    assert len(rods) == 18
+    for t in tags:
+        assert sum(1 for c in rods if t in c) == 6
+
+
 # ------------------------------------------------------------------------------------------------ contact: analytic known answers
 # Bullet is not in the reference tree, so the contact half of the step cannot be pinned against it (DESIGN.md section 4); these tests pin
 # it against mechanics instead: Coulomb friction, rolling without slipping, and the sliding threshold on an incline.
