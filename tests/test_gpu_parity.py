@@ -721,6 +721,36 @@ def test_data_logger_samples_match_the_device_state(tmp_path):
         assert np.allclose(last[o: o + 3], cab[2, c, 0:3], rtol=2e-5, atol=1e-6)                    # rest length, length, tension
 
 
+def test_data_logger_compound_samples_match_the_device_state(tmp_path):
+    """tgCompoundRigidSensor on the device: the logged position of every TetraSpine segment is its body's centre of mass, its mass
+    column the sum of its six members' mass() (each the whole body's, as in the reference), its yaw / pitch / roll the rotation since
+    the logger was set up."""
+    import ctypes as C
+    import re
+    h = capi.load_host()
+    buf = C.create_string_buffer(512)
+    steps = 25
+    rc = h.tgh_run_example_logged(b"TetraSpine", 2, capi.TGB_F64, steps, str(tmp_path / "spine").encode(), 0.0, 1, buf, 512)
+    assert rc == 0, h.tgh_last_error()
+    lines = [ln for ln in open(buf.value.decode()).read().split("\n") if ln]
+    cols = lines[1].split(",")[:-1]
+    last = [float(x) for x in lines[-1].split(",")[:-1]]
+    model = nt.build_example("TetraSpine")
+    rods = np.empty((2, model.n_bodies, 13))
+    assert h.tgh_run_example_stepwise(b"TetraSpine", 2, capi.TGB_F64, steps, rods.ctypes.data_as(C.c_void_p), None) == 0
+    xs = [i for i, c in enumerate(cols) if re.search(r"_compound\(compound_\w{6}\)\.X$", c)]
+    assert len(xs) == 3
+    seen = set()
+    for i in xs:
+        com = np.array(last[i: i + 3])
+        body = int(np.argmin(np.abs(rods[1, :, 0:3] - com).max(axis=1)))
+        seen.add(body)
+        assert np.allclose(com, rods[1, body, 0:3], rtol=2e-5, atol=1e-6)
+        assert abs(last[i + 6] - 6 * model.bodies[body].mass) < 1e-5 * 6 * model.bodies[body].mass
+        assert all(abs(a) < 30.0 for a in last[i + 3: i + 6])  # a few degrees of settling, not radians or garbage
+    assert seen == {0, 1, 2}
+
+
 # ------------------------------------------------------------------------------------------------ YAML front-end (8f rank 3)
 @pytest.mark.parametrize("precision,steps", [("f64", 150), ("f32", 60)])
 def test_yaml_built_tower_matches_oracle(tmp_path, precision, steps):
