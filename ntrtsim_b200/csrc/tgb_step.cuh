@@ -1141,7 +1141,9 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                             } else {
                                 const V3<T> pa = c + axisDir * (hc * (T(0.5) * (T)(k - 2)));
                                 V3<T> g;
-                                boxDistance<T, kFast>(pa, co, e0, e1, e2, oh, g);
+                                /* the surface point lies rc from the station and the distance is 1-Lipschitz: a station further
+                                   than that from the contact band has no contact (1e-3 of slack; no result changes) */
+                                if (boxDistance<T, kFast>(pa, co, e0, e1, e2, oh, g) - rc - margin > SolverConst<T>::breakingThreshold() + T(1e-3)) continue;
                                 const V3<T> radial = g - axisDir * axisDir.dot(g);
                                 if (kFast) {
                                     const T rl2 = radial.length2();
