@@ -1210,9 +1210,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 #endif
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
-            if (OBST) {
-                if (nc > 0) pgsRowsWithNormals<T>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
-            } else if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
+            if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
+                /* in worlds with obstacles the single row carries its own normal and friction coefficient */
+                const V3<T> gn1 = OBST ? V3<T>(CT(0, CT_NRM + 0), CT(0, CT_NRM + 1), CT(0, CT_NRM + 2)) : gn;
+                const T mu1 = OBST ? CT(0, CT_MU) : mu;
                 /* Single precision, one contact point (by far the commonest case: a rod end touching the ground): the matrix form
                    of the solver below for the two rows (normal, friction) of that point, straight-line and branch-free.  The
                    relative velocity change of each row is carried along: dvN = ANN lamN + ANT lamT, dvT = ANT lamN + ATT lamT. */
@@ -1223,14 +1224,14 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 const V3<T> angT(CT(0, CT_ANGT + 0), CT(0, CT_ANGT + 1), CT(0, CT_ANGT + 2));
                 const T invDiagN = CT(0, CT_INVDIAGN), rhsN = CT(0, CT_RHSN), rhsPen = CT(0, CT_RHSPEN);
                 const T invDiagT = CT(0, CT_INVDIAGT), rhsT = CT(0, CT_RHST);
-                const V3<T> bn = gn * invMass, bt = t * invMass;
+                const V3<T> bn = gn1 * invMass, bt = t * invMass;
                 /* With one point the two rows couple through ANT = J_N M^-1 J_T^T only, and 1 / invDiag is the row's own diagonal
                    entry, so an iteration  lam += rhs - (A lam)_row * invDiag  collapses to
                        lamN <- max(0, rhsN - kN lamT),   lamT <- clamp(rhsT - kT lamN, -mu lamN, mu lamN)
                    with kN = ANT invDiagN, kT = ANT invDiagT: the same fixed-point iteration in exact arithmetic with a dependent
                    chain of five operations per iteration instead of eleven.  The split-impulse row is alone in its system:
                    every iteration leaves it at max(0, rhsPen). */
-                const T ANT = gn.dot(bt) + rxn.dot(angT);
+                const T ANT = gn1.dot(bt) + rxn.dot(angT);
                 const T kN = ANT * invDiagN, kT = ANT * invDiagT;
                 if (rhsPen != T(0) && a.iterations > 0) {
                     const T lamPush = rhsPen > T(0) ? rhsPen : T(0);
@@ -1242,13 +1243,15 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     const T sumN = rhsN - kN * lamT;
                     lamN = sumN < T(0) ? T(0) : sumN;
                     /* friction row: skipped (impulse kept) while the normal impulse is zero */
-                    const T hi = mu * lamN;
+                    const T hi = mu1 * lamN;
                     T sumT = rhsT - kT * lamN;
                     sumT = sumT < -hi ? -hi : (sumT > hi ? hi : sumT);
                     lamT = lamN > T(0) ? sumT : lamT;
                 }
                 dLin = bn * lamN + bt * lamT;
                 dAng = angN * lamN + angT * lamT;
+            } else if (OBST) {
+                if (nc > 0) pgsRowsWithNormals<T>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
             } else if (nc > 0) {
                 const ContactSolveOut<T> o = solveContactsGeneral<T, kFast>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, gn, invMass, mu);
                 dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
