@@ -558,3 +558,59 @@ def test_oracle_hanging_rod_settles_at_weight_over_stiffness():
     rest, length, tension, _ = o.get_cable_obs()[0]
     assert abs(tension - weight) < 2e-3 * weight, (tension, weight)
     assert abs((length - rest) - weight / m.cables[0].stiffness) < 2e-3 * weight / m.cables[0].stiffness
+
+
+# ------------------------------------------------------------------------------------------------ learning outer loop
+def test_neuroevolution_population_bookkeeping(tmp_path):
+    """Ordering, the lenient maximum, the int-truncated average, mutation of the worst by copies of the best, and the .nnw format with
+    the loader's dropped last value (src/learning/NeuroEvolution/*.cpp)."""
+    from ntrtsim_b200.neuroevo import NeuroEvoPopulation, load_nnw
+    rng = np.random.default_rng(0)
+    pop = NeuroEvoPopulation(6, 10, rng, compare_average_scores=False, leniency_coef=0.5)
+    assert pop.params.shape == (6, 10) and (pop.params >= 0).all() and (pop.params <= 1).all()
+    for m, s in enumerate([3.0, 9.0, 1.0, 7.0, 5.0, 2.0]):
+        pop.update_scores(m, (s, 0.0))
+    pop.update_scores(1, (4.0, 0.0))           # a worse repeat: max decays to 0.5 * 9 + 0.5 * 4
+    assert pop.max_score[1] == 6.5 and pop.max_score1[1] == 9.0
+    before = pop.params.copy()
+    order = pop.order()
+    assert list(order) == [3, 1, 4, 0, 5, 2]   # by maximum: 7, 6.5, 5, 3, 2, 1
+    assert np.array_equal(pop.params, before[order])
+    pop2 = NeuroEvoPopulation(2, 3, rng, compare_average_scores=True)
+    for s in (0.9, 0.9, 0.9):
+        pop2.update_scores(0, (s, 0.0))
+    pop2.update_scores(1, (1.2, 0.0))
+    pop2.order()
+    assert pop2.average_score[0] == 1.0 and pop2.average_score[1] == 0.0   # int accumulator: 0.9 + 0.9 + 0.9 -> 0; 1.2 -> 1
+    best = pop.params[:2].copy()
+    pop.mutate(2)
+    changed = pop.params[[5, 4]] != best
+    assert (np.abs(pop.params[[5, 4]] - best) <= 0.2).all() and (pop.params >= 0).all() and (pop.params <= 1).all()
+    assert changed.mean() < 0.75               # each parameter moves with probability 1/4 overall
+    with pytest.raises(ValueError):
+        pop.mutate(4)
+    path = str(tmp_path / "best.nnw")
+    pop.save_best(path)
+    assert open(path).read().count(",") == 9
+    loaded = load_nnw(path, 10, defaults=np.full(10, -1.0))
+    assert np.allclose(loaded[:9], pop.params[0, :9], rtol=1e-5) and loaded[9] == -1.0   # the last value is never read
+
+
+def test_neuroevolution_generation_loop_improves_a_known_fitness():
+    """The batched generation loop on a fitness with a known optimum: first generation tests everybody, later ones only the renewed
+    members; the leader's score never decreases when every member keeps a single score."""
+    from ntrtsim_b200.neuroevo import NeuroEvolution
+    target = np.linspace(0.1, 0.9, 8)
+    calls = []
+
+    def evaluate(rows):
+        calls.append(len(rows))
+        return np.stack([10.0 - np.abs(rows - target).sum(axis=1), np.zeros(len(rows))], axis=1)
+    evo = NeuroEvolution(n_params=8, population_size=40, number_of_elements_to_mutate=20, seed=3, leniency_coef=0.0)
+    leaders = []
+    for _ in range(60):
+        evo.step(evaluate)
+        leaders.append(evo.population.max_score[0])
+    assert calls[0] == 40 and set(calls[1:]) == {20}
+    assert leaders[-1] > leaders[0] + 0.3 and leaders[-1] > 9.0
+    assert evo.log[-1][0] == 60 * 20 and len(evo.log) == 60

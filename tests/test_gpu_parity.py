@@ -1049,3 +1049,27 @@ def test_sliding_ball_and_incline_known_answers_on_device(tmp_path, precision):
             assert np.allclose(dv, a * 0.2, rtol=0.03), dv
         else:
             assert np.abs((s1[:, 0, 0:3] - s0[:, 0, 0:3]) @ down).max() < 0.01 and np.abs(s1[:, 0, 7:10] @ down).max() < 0.05
+
+
+def test_neuroevolution_generations_on_device():
+    """The learning outer loop end to end: a population of TetraSpine controllers (2 node + 57 x 2 edge actions in
+    [0, 1]) evolved for three generations, every generation's episodes evaluated in one batched launch sequence."""
+    from ntrtsim_b200.neuroevo import NeuroEvolution, evaluate_population
+    model, ctl = nt.build_example("TetraSpine"), nt.tetraspine_cpg()
+    sizes = []
+
+    def evaluate(rows):
+        sizes.append(len(rows))
+        params = nt.tetraspine_param_rows(rows[:, :2], rows[:, 2:].reshape(len(rows), 57, 2))
+        scores, status = evaluate_population(model, ctl, params, n_steps=400)
+        assert np.isfinite(scores).all()
+        return scores
+    evo = NeuroEvolution(n_params=2 + 114, population_size=24, number_of_elements_to_mutate=8, seed=11)
+    first = evo.step(evaluate)
+    best0 = evo.population.max_score[0]
+    assert best0 == first[:, 0].max()
+    evo.step(evaluate)
+    evo.step(evaluate)
+    assert sizes == [24, 8, 8]
+    assert evo.population.max_score[0] >= best0 or evo.population.max_score[0] >= 0.5 * (best0 + first[:, 0].min())
+    assert len(evo.log) == 3 and evo.log[0][0] == 24
