@@ -185,3 +185,42 @@ class NeuroEvolution(object):
         pop.mutate(self.num_mutate)
         self.first = len(pop) - self.num_mutate
         return scores
+
+
+def read_configuration(path):
+    """The key = value files of the learning examples (Config.ini, nodeConfig.ini, edgeConfig.ini), read like
+    src/learning/Configuration/configuration.cpp:77-118: blank lines and lines starting with '#' or ';' are skipped, keys and values
+    are trimmed, later keys overwrite earlier ones; a missing file yields an empty configuration (the reference only warns)."""
+    data = {}
+    try:
+        lines = open(path).read().split("\n")
+    except IOError:
+        print("Warning! Config.ini file not found!")
+        return data
+    for s in lines:
+        t = s.lstrip(" \f\t\v")
+        if not t or t[0] in "#;":
+            continue
+        key, _, value = t.partition("=")
+        key = key.rstrip(" \f\t\v")
+        if not key:
+            continue
+        data[key] = value.strip(" \f\n\r\t\v")
+    return data
+
+
+def neuroevolution_from_configuration(path, n_params, seed=None):
+    """A NeuroEvolution set up from an .ini of the learning examples: populationSize, numberOfElementsToMutate, leniencyCoef,
+    compareAverageScores, clearScoresBetweenGenerations, startSeed (NeuroEvolution.cpp:70-110, NeuroEvoPopulation.cpp:40-52); missing
+    integer keys read as 0 like configuration::getintvalue."""
+    c = read_configuration(path)
+
+    def geti(k):
+        try:
+            return int(float(c.get(k, 0)))
+        except ValueError:
+            return 0
+    return NeuroEvolution(n_params, geti("populationSize"), geti("numberOfElementsToMutate"),
+                          seed=geti("startSeed") if seed is None else seed, compare_average_scores=geti("compareAverageScores") != 0,
+                          clear_scores_between_generations=geti("clearScoresBetweenGenerations") != 0,
+                          leniency_coef=float(c.get("leniencyCoef", 0.0) or 0.0))

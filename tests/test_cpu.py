@@ -614,3 +614,21 @@ def test_neuroevolution_generation_loop_improves_a_known_fitness():
     assert calls[0] == 40 and set(calls[1:]) == {20}
     assert leaders[-1] > leaders[0] + 0.3 and leaders[-1] > 9.0
     assert evo.log[-1][0] == 60 * 20 and len(evo.log) == 60
+
+
+def test_learning_configuration_files(tmp_path):
+    """configuration::readFile semantics and a NeuroEvolution set up from such a file; the shipped TetraSpine node configuration when
+    the reference tree is here."""
+    from ntrtsim_b200.neuroevo import read_configuration, neuroevolution_from_configuration
+    p = tmp_path / "Config.ini"
+    p.write_text("#config file\n; also a comment\n\nlearning=1\n  populationSize = 10 \nnumberOfElementsToMutate=4\nleniencyCoef=0.25\n"
+                 "compareAverageScores=1\n=nokey\npopulationSize=12\n")
+    c = read_configuration(str(p))
+    assert c == {"learning": "1", "populationSize": "12", "numberOfElementsToMutate": "4", "leniencyCoef": "0.25", "compareAverageScores": "1"}
+    evo = neuroevolution_from_configuration(str(p), n_params=5)
+    assert len(evo.population) == 12 and evo.num_mutate == 4 and evo.population.leniency == 0.25 and evo.population.compare_average_scores
+    assert read_configuration(str(tmp_path / "missing.ini")) == {}
+    shipped = "/root/reference/resources/src/learningSpines/TetraSpine/nodeConfig.ini"
+    if os.path.exists(shipped):
+        evo = neuroevolution_from_configuration(shipped, n_params=2)
+        assert len(evo.population) == 2 and evo.num_mutate == 1 and evo.population.leniency == 1.0
