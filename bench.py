@@ -17,6 +17,10 @@ registers/shared memory for the H steps; HBM is touched at the launch boundaries
                 so the reference itself cannot be built: kind "port") on all host cores, bounded sample
 
 python bench.py --impl reference times that CPU port alone, all host threads, same workload/metric.
+
+Other workloads (--workload prism | tetraspine | flemons | crater | superball_noground, --envs, --precision f64) are side lines for
+DESIGN.md / profiles/; under torchrun (--gpus N) every rank runs its own 4096 environments and the per-rollout scores are all-gathered
+once per bench step, overlapping the next step (see the N > 1 branch below).
 """
 import argparse
 import json
