@@ -673,33 +673,46 @@ tgb_status tgb_set_controller(tgb_world* w, int32_t kind, const double* params, 
         }
     }
     const int n = w->cfg.n_env;
+    if (kind == TGB_CTRL_ESCAPE_SINE && w->C < 24)
+        return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: the sine controller drives the 24 muscles of the SUPERball cluster map (EscapeController.cpp:245-291)");
+    /* tgb_step is asynchronous on the world's stream: nothing of the controller may change under a step kernel in flight */
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
     if (w->ctrlKind != kind) {
-        /* one controller kind per world: switching kinds needs parameters for every environment */
+        /* one controller kind per world: switching kinds needs parameters for every environment.  Everything that can fail is done
+           on temporaries; the world's controller (buffer, stride, kind) changes only once all of it succeeded. */
         if (!(env_begin == 0 && env_count == n)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_controller: a new controller kind must cover all environments");
-        if (w->d_ctrl) { cudaFree(w->d_ctrl); w->d_ctrl = nullptr; }
-        TGB_CUDA(cudaMalloc(&w->d_ctrl, (size_t)n * need * sizeof(double)));
-        w->ctrlStride = need;
-        if (kind == TGB_CTRL_ESCAPE_SINE && !w->d_sine) TGB_CUDA(cudaMalloc(&w->d_sine, (size_t)n * 48 * sizeof(double)));
         {
             tgb_step_args a = stepArgs(w, 1e-3, 1);
             a.ctrl_stride = need;
             a.ctrl_kind = kind;
             if (w->ops->step_smem(a, w->lanes, w->threads) > 227 * 1024) return fail(TGB_ERR_UNSUPPORTED, "controller parameters do not fit in shared memory");
         }
+        double* newCtrl = nullptr;
+        TGB_CUDA(cudaMalloc(&newCtrl, (size_t)n * need * sizeof(double)));
+        if (kind == TGB_CTRL_ESCAPE_SINE && !w->d_sine) {
+            cudaError_t e = cudaMalloc(&w->d_sine, (size_t)n * 48 * sizeof(double));
+            if (e != cudaSuccess) { cudaFree(newCtrl); w->d_sine = nullptr; return cudaFail(e, "tgb_set_controller: sine state"); }
+        }
+        if (w->d_ctrl) cudaFree(w->d_ctrl);
+        w->d_ctrl = newCtrl;
+        w->ctrlStride = need;
+        w->ctrlKind = kind;
     }
     if (env_count > 0) {
+        /* stream-ordered behind anything still queued (the stream is idle here, see above) */
         if (broadcast) {
             std::vector<double> rows((size_t)env_count * need);
             for (int e = 0; e < env_count; ++e) std::memcpy(&rows[(size_t)e * need], params, need * sizeof(double));
-            TGB_CUDA(cudaMemcpy(w->d_ctrl + (size_t)env_begin * need, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice));
+            TGB_CUDA(cudaMemcpyAsync(w->d_ctrl + (size_t)env_begin * need, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+            TGB_CUDA(cudaStreamSynchronize(w->stream)); /* `rows` goes out of scope */
         } else {
-            TGB_CUDA(cudaMemcpy(w->d_ctrl + (size_t)env_begin * need, params, (size_t)env_count * need * sizeof(double), cudaMemcpyHostToDevice));
+            TGB_CUDA(cudaMemcpyAsync(w->d_ctrl + (size_t)env_begin * need, params, (size_t)env_count * need * sizeof(double), cudaMemcpyHostToDevice, w->stream));
         }
         /* controller time restarts (EscapeController::onSetup: m_totalTime = 0); the spare word after it is cleared too: the
            sine phases of these environments start again from exact values */
-        TGB_CUDA(cudaStreamSynchronize(w->stream));
         static_assert(FR_SPARE == FR_CTRLTIME + 1, "controller time and spare word are adjacent");
-        TGB_CUDA(cudaMemset2D(w->d_frame + (size_t)env_begin * TGB_NFR + FR_CTRLTIME, TGB_NFR * sizeof(double), 0, 2 * sizeof(double), env_count));
+        TGB_CUDA(cudaMemset2DAsync(w->d_frame + (size_t)env_begin * TGB_NFR + FR_CTRLTIME, TGB_NFR * sizeof(double), 0, 2 * sizeof(double), env_count, w->stream));
+        TGB_CUDA(cudaStreamSynchronize(w->stream));
     }
     w->ctrlKind = kind;
     return TGB_OK;
@@ -727,6 +740,8 @@ tgb_status tgb_set_cpg_controller(tgb_world* w, const tgb_cpg_desc* d, const dou
     const bool fresh = w->ctrlKind != TGB_CTRL_CPG_IMPEDANCE;
     if (fresh && !(env_begin == 0 && env_count == n))
         return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: a new controller kind must cover all environments");
+    if (!fresh && w->ctrlStride != params_per_env && !(env_begin == 0 && env_count == n))
+        return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: a change of params_per_env must cover all environments");
     TGB_CUDA(cudaStreamSynchronize(w->stream));
     /* static part */
     std::vector<int> topo;
@@ -741,8 +756,13 @@ tgb_status tgb_set_cpg_controller(tgb_world* w, const tgb_cpg_desc* d, const dou
     TGB_CUDA(cudaMemcpy(w->d_cpg_imp, d->impedance, (size_t)4 * d->n_nodes * sizeof(double), cudaMemcpyHostToDevice));
     const size_t stateDoubles = (size_t)TGB_CPG_STATE_DOUBLES(w->C);
     if (fresh || w->ctrlStride != params_per_env) {
-        if (w->d_ctrl) { cudaFree(w->d_ctrl); w->d_ctrl = nullptr; }
-        TGB_CUDA(cudaMalloc(&w->d_ctrl, (size_t)n * params_per_env * sizeof(double)));
+        /* a different row length reallocates the parameter rows of every environment: the call must bring all of them */
+        if (!(env_begin == 0 && env_count == n))
+            return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_cpg_controller: a change of params_per_env must cover all environments");
+        double* newCtrl = nullptr;
+        TGB_CUDA(cudaMalloc(&newCtrl, (size_t)n * params_per_env * sizeof(double)));
+        if (w->d_ctrl) cudaFree(w->d_ctrl);
+        w->d_ctrl = newCtrl;
         w->ctrlStride = params_per_env;
     }
     if (!w->d_cpg_state) TGB_CUDA(cudaMalloc(&w->d_cpg_state, (size_t)n * stateDoubles * sizeof(double)));

@@ -6,19 +6,42 @@
 #include "tgb_ops.h"
 #include "tgb_step.cuh"
 
+#include <mutex>
+
 namespace {
 
 typedef TGB_SCALAR scalar_t;
 
+/* cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute of a kernel: remember the largest size set
+   so far per device ordinal, never lower it (a smaller world must not take the room away from a larger one created earlier), and
+   serialise the bookkeeping (worlds of different host threads share these kernels). */
+struct SmemAttrCache {
+    enum { kMaxDevices = 64 };
+    size_t configured[kMaxDevices] = {};
+    std::mutex lock;
+    template <typename Kernel>
+    cudaError_t ensure(Kernel kernel, size_t smem) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        std::lock_guard<std::mutex> g(lock);
+        if (smem > configured[dev]) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured[dev] = smem;
+        }
+        return cudaSuccess;
+    }
+};
+
 template <int LPE, bool GROUND, bool OBST = false>
 cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
     const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, threads, sizeof(scalar_t));
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static SmemAttrCache cache;
+    {
+        cudaError_t e = cache.ensure(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST>, smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const int groupsPerBlock = threads / LPE;
     const int grid = (a.n_env - a.env_begin + groupsPerBlock - 1) / groupsPerBlock;
@@ -27,16 +50,20 @@ cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+/* one cache per instantiation of the four-warp layout, shared by its launch and its occupancy query */
+template <int LPE, bool GROUND, int NW>
+SmemAttrCache& wideCache() {
+    static SmemAttrCache cache;
+    return cache;
+}
+
 /* the four-warp layout: 128 threads, 32 / LPE environments per CTA */
 template <int LPE, bool GROUND, int NW>
 cudaError_t launch_wide(const tgb_step_args& a, cudaStream_t s) {
     const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, 128, sizeof(scalar_t));
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, NW>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = wideCache<LPE, GROUND, NW>().ensure(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, NW>, smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const int groupsPerBlock = 32 / LPE;
     const int grid = (a.n_env - a.env_begin + groupsPerBlock - 1) / groupsPerBlock;
@@ -51,8 +78,7 @@ cudaError_t wide_ctas_per_sm(const tgb_step_args& a, int* out) {
     tgb_step_args aw = a;
     aw.wide = 1;
     const size_t smem = tgb::tgb_step_smem_bytes(aw, LPE, 128, sizeof(scalar_t));
-    cudaError_t e = cudaFuncSetAttribute(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 4>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = wideCache<LPE, GROUND, 4>().ensure(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 4>, smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 4>, 128, smem);
 }

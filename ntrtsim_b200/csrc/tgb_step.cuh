@@ -1462,7 +1462,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 for (int u = 0; u < CU; ++u) {
                     CableRegs<T>& q = cr[u];
                     const int c = q.c;
-                    if (c < 24) {
+                    if (c < 24 && q.valid) { /* an idle unroll slot shadows cable c0: it must not advance c0's phase a second time */
                         /* EscapeController::setPreferredMuscleLengths, EscapeController.cpp:245-291 */
                         const int cluster = c < 16 ? (c >> 2) : 4 + ((c - 16) >> 1);
                         T newLength;

@@ -11,6 +11,31 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _host_buffer(a, shape, what, writable=False):
+    """A C-contiguous float64 array of exactly `shape`: the C ABI reads / writes raw doubles, so anything else is an error here
+    rather than garbage there.  Inputs are converted; output buffers must already be right (a converted copy would be lost)."""
+    if writable:
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable and a.size == int(np.prod(shape))):
+            raise ValueError("%s must be a writable C-contiguous float64 array of %d elements" % (what, int(np.prod(shape))))
+        return a
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.size != int(np.prod(shape)):
+        raise ValueError("%s has %d elements, expected %s" % (what, a.size, "x".join(str(int(x)) for x in shape)))
+    return a
+
+
+def _rows(params, n, broadcast, what):
+    """env_count of a parameter array: one row when broadcast, else exactly one row per environment of the range"""
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    rows = 1 if params.ndim == 1 else int(np.prod(params.shape[:-1]))
+    if broadcast:
+        if rows != 1:
+            raise ValueError("%s: a broadcast takes one parameter row, got %d" % (what, rows))
+    elif rows != n:
+        raise ValueError("%s: %d parameter rows for %d environments" % (what, rows, n))
+    return params
+
+
 class FlatModel(object):
     """The flattened descriptors of one model: what tgStructureInfo::buildInto hands to the world
     (reference: src/tgcreator/tgStructureInfo.cpp:277-289) plus the world settings of its app."""
@@ -103,14 +128,14 @@ class BatchedWorld(object):
         if params is None:
             capi.check(self._lib.tgb_set_controller(self._h, kind, None, 0, env_begin, n, 0))
             return
-        params = np.ascontiguousarray(params, dtype=np.float64)
+        params = _rows(params, n, broadcast, "set_controller")
         per_env = params.shape[-1]
         capi.check(self._lib.tgb_set_controller(self._h, kind, _ptr(params), per_env, env_begin, n, 1 if broadcast else 0))
 
     def set_cpg_controller(self, desc, params, env_begin=0, env_count=None, broadcast=False):
         """desc: a CpgController (ntrtsim_b200.examples.tetraspine_cpg); params: [n, 2 + 2 * n_pairs] rows"""
         n = self.n_env - env_begin if env_count is None else env_count
-        params = np.ascontiguousarray(params, dtype=np.float64)
+        params = _rows(params, n, broadcast, "set_cpg_controller")
         capi.check(self._lib.tgb_set_cpg_controller(self._h, C.byref(desc.desc), _ptr(params), params.shape[-1], env_begin, n,
                                                     1 if broadcast else 0))
 
@@ -134,6 +159,8 @@ class BatchedWorld(object):
         n = self.n_env - env_begin if env_count is None else env_count
         inputs = np.ascontiguousarray(inputs, dtype=np.float64)
         broadcast = 1 if inputs.ndim == 1 else 0
+        if inputs.size != (1 if broadcast else n) * self.C:
+            raise ValueError("set_control_input: %d values for %d environments x %d cables" % (inputs.size, 1 if broadcast else n, self.C))
         capi.check(self._lib.tgb_set_control_input(self._h, env_begin, n, _ptr(inputs), broadcast, dt))
 
     # ---- stepping ----------------------------------------------------------------------------------------
@@ -160,6 +187,12 @@ class BatchedWorld(object):
             rod_out = np.empty((self.n_env, self.R, capi.ROD_STATE_DOUBLES))
         if cable_out is None:
             cable_out = np.empty((self.n_env, self.C, capi.CABLE_OBS_DOUBLES))
+        if rod_in is not None:
+            rod_in = _host_buffer(rod_in, (self.n_env, self.R, capi.ROD_STATE_DOUBLES), "rod_in")
+        if cable_in is not None:
+            cable_in = _host_buffer(cable_in, (self.n_env, self.C, 2), "cable_in")
+        rod_out = _host_buffer(rod_out, (self.n_env, self.R, capi.ROD_STATE_DOUBLES), "rod_out", writable=True)
+        cable_out = _host_buffer(cable_out, (self.n_env, self.C, capi.CABLE_OBS_DOUBLES), "cable_out", writable=True)
         capi.check(self._lib.tgb_rollout_host(self._h, _ptr(rod_in) if rod_in is not None else None,
                                               _ptr(cable_in) if cable_in is not None else None, dt, n_steps,
                                               _ptr(rod_out), _ptr(cable_out)))
