@@ -38,6 +38,12 @@ def load():
     lib.tgo_mark_episode_start.argtypes = [vp]
     lib.tgo_get_scores.argtypes = [vp, vp]
     lib.tgo_num_contacts.argtypes = [vp]
+    lib.tgo_num_pair_contacts.argtypes = [vp]
+    lib.tgo_set_pair_contact_cap.argtypes = [vp, i]
+    lib.tgo_set_default_pair_contact_cap.argtypes = [i]
+    lib.tgo_get_min_clearance.restype = dbl
+    lib.tgo_get_min_clearance.argtypes = [vp]
+    lib.tgo_reset_min_clearance.argtypes = [vp]
     lib.tgo_rollout_batch.argtypes = [vp, vp, vp, i, vp, i, vp, i, i, vp, i, vp, dbl, i, vp, vp, dbl, i, i, vp, vp, vp, vp, vp]
     lib.tgo_set_cpg_controller.argtypes = [vp, vp, vp, i]
     lib.tgo_get_status.argtypes = [vp]
@@ -112,6 +118,20 @@ class OracleWorld(object):
     def num_contacts(self):
         return self._lib.tgo_num_contacts(self._h)
 
+    def num_pair_contacts(self):
+        """rows between two bodies in the last world step"""
+        return self._lib.tgo_num_pair_contacts(self._h)
+
+    def set_pair_contact_cap(self, cap):
+        self._lib.tgo_set_pair_contact_cap(self._h, int(cap))
+
+    def min_clearance(self, reset=False):
+        """smallest surface distance between two bodies' shapes seen by any world step so far"""
+        v = self._lib.tgo_get_min_clearance(self._h)
+        if reset:
+            self._lib.tgo_reset_min_clearance(self._h)
+        return v
+
     def scores(self):
         out = np.empty(2)
         self._lib.tgo_get_scores(self._h, _p(out))
@@ -134,6 +154,11 @@ class OracleWorld(object):
         out = np.empty((self.C, 3))
         self._lib.tgo_get_cpg_state(self._h, _p(out))
         return out
+
+
+def set_default_pair_contact_cap(cap):
+    """pair-contact row cap of oracle worlds created from now on (rollout_batch creates its own worlds); 0 = bodies do not collide"""
+    load().tgo_set_default_pair_contact_cap(int(cap))
 
 
 def rollout_batch(model, cfg_cls, rod_in, cable_in, dt, n_steps, ctrl_kind=0, ctrl_params=None, setup_input=None, setup_dt=0.0,

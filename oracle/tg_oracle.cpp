@@ -155,8 +155,11 @@ struct Cable {
 
 struct Contact {
     int body;
+    int bodyB = -1; /* body pairs: the second body (the normal points from B to A, Bullet's m_normalWorldOnB); -1 = the static world */
     V3 n;        /* ground -> rod */
     V3 r;        /* contact point on the rod relative to its centre of mass */
+    V3 rB;       /* body pairs: contact point on B relative to B's centre of mass */
+    V3 rxnB, angNB, rxtB, angTB; /* B's side of the two rows */
     double dist;
     /* normal row */
     V3 rxn, angN;
@@ -223,6 +226,9 @@ struct tgo_world {
     V3 episodeStartCom;
     int iterations = 10;
     int status = 0;
+    int pairCap = 6;            /* rows of body-pair contacts per environment (tgb_set_pair_contact_cap); 0 = bodies do not collide */
+    int pairRows = 0;           /* body-pair rows of the last world step */
+    double minClearance = 1e30; /* smallest surface distance of two bodies' shapes seen by any world step */
 
     /* ---- CPG + impedance controller (TGB_CTRL_CPG_IMPEDANCE) ---------------------------------------------- */
     struct Cpg {
@@ -659,6 +665,104 @@ struct tgo_world {
         generateObstacleContacts();
         /* rows are solved body by body in the device kernel: keep the same order here (stable: ground first, then obstacles) */
         std::stable_sort(contacts.begin(), contacts.end(), [](const Contact& x, const Contact& y) { return x.body < y.body; });
+        /* rows between two bodies come last, in pair order: every iteration of the solver visits the rows of the static world
+           first (body by body), then the pair rows */
+        generateBodyPairContacts();
+    }
+
+    /* ---- contacts between bodies (tgWorldBulletPhysicsImpl.cpp:82-107: btAxisSweep3 + btDefaultCollisionConfiguration collide
+       every pair of bodies of the world; tgRodInfo.cpp:99-113 btCylinderShape, tgSphereInfo.cpp:100-115 btSphereShape).
+       Bullet runs GJK/EPA on the convex pair and keeps a persistent manifold; here, as for the ground, an analytic manifold: a
+       cylinder counts as the capsule inscribed in it (its axis segment shortened by the radius at both ends, swept by the
+       radius), a sphere as a segment of length zero.  One contact at the closest points of the two segments; two (at the ends of
+       the overlap) when the segments are parallel within kParallel and overlap.  A point is a contact when the surface distance
+       is within the contact breaking threshold.  At most 4 rows per pair of bodies and pairCap rows per environment, in the
+       order (body A < body B, shape of A, shape of B, point).  Boxes take no part (static boxes are obstacles, see above). */
+    struct Segment { V3 p, d; double h, r; };
+    static bool shapeSegment(const Body& b, const Shape& s, Segment& g) {
+        if (s.kind == TGB_SHAPE_BOX) return false;
+        const M3 R = b.basis * s.rot;
+        g.p = b.basis * s.pos + b.pos;
+        g.d = R.col(1);
+        g.r = s.radius;
+        g.h = s.kind == TGB_SHAPE_SPHERE ? 0.0 : (s.halfLen - s.radius > 0.0 ? s.halfLen - s.radius : 0.0);
+        return true;
+    }
+    static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+    /* closest points A(s) = pa + s da, B(t) = pb + t db of two segments given by centre, unit direction, half length */
+    static void closestSegmentParams(const Segment& A, const Segment& B, double& sOut, double& tOut, double& bOut, double& cOut, double& fOut) {
+        const V3 r = A.p - B.p;
+        const double b = A.d.dot(B.d), c = A.d.dot(r), f = B.d.dot(r);
+        const double denom = 1.0 - b * b;
+        double s = 0.0, t = 0.0;
+        if (A.h > 0.0 && denom > 1e-12) s = clampd((b * f - c) / denom, -A.h, A.h);
+        t = b * s + f;
+        if (t < -B.h) { t = -B.h; s = clampd(b * t - c, -A.h, A.h); }
+        else if (t > B.h) { t = B.h; s = clampd(b * t - c, -A.h, A.h); }
+        sOut = s; tOut = t; bOut = b; cOut = c; fOut = f;
+    }
+    void generateBodyPairContacts() {
+        pairRows = 0; /* with pairCap == 0 the clearance is still measured, no row is generated */
+        const double kParallel = 1e-4; /* 1 - cos^2 of the angle between the axes below which the overlap's two ends are used */
+        const int nb = (int)bodies.size();
+        for (int ia = 0; ia < nb; ++ia)
+            for (int ib = ia + 1; ib < nb; ++ib) {
+                Body& A = bodies[ia];
+                Body& B = bodies[ib];
+                if (A.invMass == 0.0 && B.invMass == 0.0) continue;
+                int count = 0;
+                for (int sa = A.shapeBegin; sa < A.shapeBegin + A.shapeCount; ++sa)
+                    for (int sb = B.shapeBegin; sb < B.shapeBegin + B.shapeCount; ++sb) {
+                        Segment ga, gb;
+                        if (!shapeSegment(A, shapes[sa], ga) || !shapeSegment(B, shapes[sb], gb)) continue;
+                        double s0, t0, b, c, f;
+                        closestSegmentParams(ga, gb, s0, t0, b, c, f);
+                        double sp[2] = {s0, s0}, tp[2] = {t0, t0};
+                        int np = 1;
+                        if (ga.h > 0.0 && gb.h > 0.0 && 1.0 - b * b < kParallel) {
+                            /* B's end points in A's axis parameter: s(t) = t b - c */
+                            const double e0 = -gb.h * b - c, e1 = gb.h * b - c;
+                            const double lo = std::max(-ga.h, std::min(e0, e1)), hi = std::min(ga.h, std::max(e0, e1));
+                            if (hi - lo > 1e-9) {
+                                np = 2;
+                                sp[0] = lo; tp[0] = clampd(b * lo + f, -gb.h, gb.h);
+                                sp[1] = hi; tp[1] = clampd(b * hi + f, -gb.h, gb.h);
+                            }
+                        }
+                        for (int k = 0; k < np; ++k) {
+                            const V3 ca = ga.p + ga.d * sp[k], cb = gb.p + gb.d * tp[k];
+                            const V3 dv = ca - cb;
+                            const double d2 = dv.length2();
+                            const double d = std::sqrt(d2);
+                            const double dist = d - ga.r - gb.r;
+                            if (dist < minClearance) minClearance = dist;
+                            if (dist > kBreakingThreshold) continue;
+                            if (count >= 4 || pairRows >= pairCap) continue;
+                            V3 n;
+                            if (d > 1e-9) n = dv * (1.0 / d);
+                            else {
+                                /* the axes meet: any direction perpendicular to both */
+                                const V3 x = ga.d.cross(gb.d);
+                                const double xl = x.length();
+                                n = xl > 1e-9 ? x * (1.0 / xl) : planeSpace1(ga.d);
+                            }
+                            Contact ct;
+                            ct.body = ia; ct.bodyB = ib;
+                            ct.n = n;
+                            ct.r = (ca - n * ga.r) - A.pos;
+                            ct.rB = (cb + n * gb.r) - B.pos;
+                            ct.dist = dist;
+                            double mu = A.friction * B.friction;
+                            if (mu < -10.0) mu = -10.0;
+                            if (mu > 10.0) mu = 10.0;
+                            ct.mu = mu;
+                            ct.restitution = A.restitution * B.restitution;
+                            contacts.push_back(ct);
+                            ++count;
+                            ++pairRows;
+                        }
+                    }
+            }
     }
 
     void generateGroundContacts() {
@@ -776,8 +880,18 @@ struct tgo_world {
             c.rxn = c.r.cross(c.n);
             c.angN = b.invInertiaWorld * c.rxn;
             double denom = b.invMass + c.n.dot(c.angN.cross(c.r));
-            c.invDiagN = 1.0 / denom;
             V3 vel = b.linvel + b.angvel.cross(c.r);
+            const bool pair = c.bodyB >= 0;
+            const int j = pair ? c.bodyB : i;
+            Body& bB = bodies[j];
+            if (pair) {
+                /* the second body of the row: Jacobian (-n, -(rB x n)); setupContactConstraint adds both bodies' terms */
+                c.rxnB = c.rB.cross(c.n);
+                c.angNB = bB.invInertiaWorld * c.rxnB;
+                denom = denom + (bB.invMass + c.n.dot(c.angNB.cross(c.rB)));
+                vel = vel - (bB.linvel + bB.angvel.cross(c.rB));
+            }
+            c.invDiagN = 1.0 / denom;
             double relVel = c.n.dot(vel);
             double combinedRestitution = c.restitution;
             double restitution = combinedRestitution * -relVel;
@@ -789,6 +903,7 @@ struct tgo_world {
             else c.t = planeSpace1(c.n);
             c.lamN = 0.0; c.lamPush = 0.0; c.lamT = 0.0; /* no persistent manifold => no warm start */
             double velDotN = c.n.dot(b.linvel + extLin[i]) + c.rxn.dot(b.angvel + extAng[i]);
+            if (pair) velDotN = velDotN - (c.n.dot(bB.linvel + extLin[j]) + c.rxnB.dot(bB.angvel + extAng[j]));
             double velocityError = restitution - velDotN;
             double penetration = c.dist;
             double erp = kErp2;
@@ -804,8 +919,14 @@ struct tgo_world {
             c.rxt = c.r.cross(c.t);
             c.angT = b.invInertiaWorld * c.rxt;
             double denomT = b.invMass + c.t.dot(c.angT.cross(c.r));
-            c.invDiagT = 1.0 / denomT;
             double relT = c.t.dot(b.linvel + extLin[i]) + c.rxt.dot(b.angvel);
+            if (pair) {
+                c.rxtB = c.rB.cross(c.t);
+                c.angTB = bB.invInertiaWorld * c.rxtB;
+                denomT = denomT + (bB.invMass + c.t.dot(c.angTB.cross(c.rB)));
+                relT = relT - (c.t.dot(bB.linvel + extLin[j]) + c.rxtB.dot(bB.angvel));
+            }
+            c.invDiagT = 1.0 / denomT;
             c.rhsT = (0.0 - relT) * c.invDiagT;
         }
 
@@ -817,12 +938,17 @@ struct tgo_world {
                 const int i = c.body;
                 double delta = c.rhsPen;
                 double dv = c.n.dot(push[i]) + c.rxn.dot(turn[i]);
+                if (c.bodyB >= 0) dv = dv - (c.n.dot(push[c.bodyB]) + c.rxnB.dot(turn[c.bodyB]));
                 delta -= dv * c.invDiagN;
                 double sum = c.lamPush + delta;
                 if (sum < 0.0) { delta = -c.lamPush; c.lamPush = 0.0; }
                 else c.lamPush = sum;
                 push[i] += c.n * (b.invMass * delta);
                 turn[i] += c.angN * delta;
+                if (c.bodyB >= 0) {
+                    push[c.bodyB] -= c.n * (bodies[c.bodyB].invMass * delta);
+                    turn[c.bodyB] -= c.angNB * delta;
+                }
             }
         }
         for (int it = 0; it < iterations; ++it) {
@@ -831,12 +957,17 @@ struct tgo_world {
                 const int i = c.body;
                 double delta = c.rhsN;
                 double dv = c.n.dot(dLin[i]) + c.rxn.dot(dAng[i]);
+                if (c.bodyB >= 0) dv = dv - (c.n.dot(dLin[c.bodyB]) + c.rxnB.dot(dAng[c.bodyB]));
                 delta -= dv * c.invDiagN;
                 double sum = c.lamN + delta;
                 if (sum < 0.0) { delta = -c.lamN; c.lamN = 0.0; }
                 else c.lamN = sum;
                 dLin[i] += c.n * (b.invMass * delta);
                 dAng[i] += c.angN * delta;
+                if (c.bodyB >= 0) {
+                    dLin[c.bodyB] -= c.n * (bodies[c.bodyB].invMass * delta);
+                    dAng[c.bodyB] -= c.angNB * delta;
+                }
             }
             for (Contact& c : contacts) {
                 if (!(c.lamN > 0.0)) continue;
@@ -845,6 +976,7 @@ struct tgo_world {
                 double lo = -c.mu * c.lamN, hi = c.mu * c.lamN;
                 double delta = c.rhsT;
                 double dv = c.t.dot(dLin[i]) + c.rxt.dot(dAng[i]);
+                if (c.bodyB >= 0) dv = dv - (c.t.dot(dLin[c.bodyB]) + c.rxtB.dot(dAng[c.bodyB]));
                 delta -= dv * c.invDiagT;
                 double sum = c.lamT + delta;
                 if (sum < lo) { delta = lo - c.lamT; c.lamT = lo; }
@@ -852,6 +984,10 @@ struct tgo_world {
                 else c.lamT = sum;
                 dLin[i] += c.t * (b.invMass * delta);
                 dAng[i] += c.angT * delta;
+                if (c.bodyB >= 0) {
+                    dLin[c.bodyB] -= c.t * (bodies[c.bodyB].invMass * delta);
+                    dAng[c.bodyB] -= c.angTB * delta;
+                }
             }
         }
 
@@ -895,10 +1031,15 @@ struct tgo_world {
     }
 };
 
+static int g_defaultPairCap = 6;
+
 extern "C" {
+
+void tgo_set_default_pair_contact_cap(int cap) { g_defaultPairCap = cap < 0 ? 0 : cap; }
 
 tgo_world* tgo_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground) {
     tgo_world* w = new tgo_world();
+    w->pairCap = g_defaultPairCap;
     w->cfg = *cfg;
     w->ground = *ground;
     w->iterations = cfg->solver_iterations > 0 ? cfg->solver_iterations : 10;
@@ -1080,6 +1221,10 @@ int tgo_set_cpg_controller(tgo_world* w, const tgb_cpg_desc* d, const double* pa
     return 0;
 }
 int tgo_num_contacts(const tgo_world* w) { return (int)w->contacts.size(); }
+int tgo_num_pair_contacts(const tgo_world* w) { return w->pairRows; }
+void tgo_set_pair_contact_cap(tgo_world* w, int cap) { w->pairCap = cap < 0 ? 0 : cap; }
+double tgo_get_min_clearance(const tgo_world* w) { return w->minClearance; }
+void tgo_reset_min_clearance(tgo_world* w) { w->minClearance = 1e30; }
 
 int tgo_rollout_batch(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, const tgb_body_desc* bodies, int n_bodies,
                       const tgb_shape_desc* shapes, int n_shapes, const tgb_cable_desc* cables, int n_cables, int ctrl_kind,

@@ -82,6 +82,13 @@ double tgo_get_time(const tgo_world* w);
 void   tgo_mark_episode_start(tgo_world* w);
 void   tgo_get_scores(const tgo_world* w, double* scores2);
 int    tgo_num_contacts(const tgo_world* w);      /* contacts generated in the last world step */
+int    tgo_num_pair_contacts(const tgo_world* w); /* of which rows between two bodies */
+/* rows of body-pair contacts kept per environment (same meaning as tgb_set_pair_contact_cap; default 6, 0 = bodies do not collide) */
+void   tgo_set_pair_contact_cap(tgo_world* w, int cap);
+void   tgo_set_default_pair_contact_cap(int cap);  /* for worlds created afterwards (tgo_rollout_batch creates its own) */
+/* smallest surface distance between the collision shapes of two different bodies seen by any world step so far */
+double tgo_get_min_clearance(const tgo_world* w);
+void   tgo_reset_min_clearance(tgo_world* w);
 
 /* Batched convenience for tests and the CPU baseline: run `n_env` independent environments that share one
    model, each from its own rod state / cable state / controller row, for n_steps; OpenMP-free, `n_threads`

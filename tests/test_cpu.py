@@ -560,6 +560,150 @@ def test_oracle_hanging_rod_settles_at_weight_over_stiffness():
     assert abs((length - rest) - weight / m.cables[0].stiffness) < 2e-3 * weight / m.cables[0].stiffness
 
 
+# ------------------------------------------------------------------------------------------------ contact between bodies
+# tgWorldBulletPhysicsImpl.cpp:82-107 collides every pair of bodies of the world (rod x rod, vertebra x vertebra).  Known answers:
+# crossed rods rest on each other one diameter apart, a rod-rod impact without gravity conserves momentum, and a 3-prism under its
+# own pretension folds until its rods touch (they used to pass through each other).
+CROSSED_RODS = """
+nodes:
+  a0: [-3, 0.5, 0]
+  a1: [3, 0.5, 0]
+  b0: [0.3, 2.0, -3]
+  b1: [0.3, 2.0, 3]
+pair_groups:
+  rod:
+    - [a0, a1]
+    - [b0, b1]
+builders:
+  rod:
+    class: tgRodInfo
+    parameters:
+      radius: 0.5
+      density: 1.0
+      friction: 1.0
+      roll_friction: 0.0
+      restitution: 0.0
+"""
+
+
+def segment_distance(p1, q1, p2, q2):
+    """distance between the segments p1-q1 and p2-q2 (dense sampling; test-side check, independent of the oracle's closed form)"""
+    s = np.linspace(0.0, 1.0, 801)
+    a = p1[None] + (q1 - p1)[None] * s[:, None]
+    b = p2[None] + (q2 - p2)[None] * s[:, None]
+    return np.sqrt(((a[:, None, :] - b[None, :, :]) ** 2).sum(-1)).min()
+
+
+def rod_axes(model, rods):
+    from helpers import quat_rotate
+    out = []
+    for i, b in enumerate(model.bodies):
+        sh = model.shapes[b.shape_begin]
+        ax = quat_rotate(rods[i, 3:7][None], np.array([[0.0, 1.0, 0.0]]))[0]
+        out.append((rods[i, 0:3] - ax * sh.half_length, rods[i, 0:3] + ax * sh.half_length, sh.radius))
+    return out
+
+
+RAILS = """
+nodes:
+  a0: [-3, 2.0, -1.5]
+  a1: [3, 2.0, -1.5]
+  c0: [-3, 2.0, 1.5]
+  c1: [3, 2.0, 1.5]
+  b0: [0.3, 3.5, -3]
+  b1: [0.3, 3.5, 3]
+pair_groups:
+  rail:
+    - [a0, a1]
+    - [c0, c1]
+  rod:
+    - [b0, b1]
+builders:
+  rail:
+    class: tgRodInfo
+    parameters:
+      radius: 0.5
+      density: 0.0
+      friction: 1.0
+      restitution: 0.0
+  rod:
+    class: tgRodInfo
+    parameters:
+      radius: 0.5
+      density: 1.0
+      friction: 1.0
+      roll_friction: 0.0
+      restitution: 0.0
+"""
+
+
+def test_oracle_crossed_rods_rest_one_diameter_apart(tmp_path):
+    """a rod dropped across two static rods (rails) comes to rest on them, axes one diameter apart"""
+    m = _build_text(tmp_path, "rails.yaml", RAILS)
+    assert len(m.bodies) == 3 and [b.mass == 0.0 for b in m.bodies] == [True, True, False]
+    o = _oracle(m)
+    o.step(m.dt, 1500)
+    s = o.get_rod_state()
+    assert np.abs(s[2, 7:13]).max() < 0.05, s[2, 7:13]           # at rest
+    axes = rod_axes(m, s)
+    for rail in (0, 1):
+        gap = segment_distance(axes[rail][0], axes[rail][1], axes[2][0], axes[2][1]) - axes[rail][2] - axes[2][2]
+        assert -0.045 < gap < 0.021, gap                          # within the contact band of the solver (slop 0.04, breaking threshold 0.02)
+    assert abs(s[2, 1] - 3.0) < 0.05                              # on top of the rails (the ground's top face is at y = 1.5)
+    assert o.num_pair_contacts() == 2 and o.min_clearance() > -0.1
+    # with the pair contacts switched off it falls through the static rods onto the ground
+    o2 = _oracle(m)
+    o2.set_pair_contact_cap(0)
+    o2.step(m.dt, 1500)
+    assert abs(o2.get_rod_state()[2, 1] - 2.0) < 0.05
+
+
+def test_oracle_rod_rod_impact_conserves_momentum(tmp_path):
+    m = _build_text(tmp_path, "crossed.yaml", CROSSED_RODS)
+    m.ground.kind = capi.TGB_GROUND_EMPTY
+    m.gravity = 0.0
+    rods = m.initial_rod_state()
+    rods[1, 8] = -8.0                                              # the upper rod flies down onto the lower one, off centre
+    o = _oracle(m, rods)
+    mass = np.array([b.mass for b in m.bodies])
+
+    def momenta(s):
+        lin = (mass[:, None] * s[:, 7:10]).sum(0)
+        from helpers import quat_rotate
+        ang = np.zeros(3)
+        for i, b in enumerate(m.bodies):
+            wl = quat_rotate(s[i, 3:7][None] * np.array([-1, -1, -1, 1.0]), s[i, 10:13][None])[0]
+            Lw = quat_rotate(s[i, 3:7][None], (np.array(list(b.inertia)) * wl)[None])[0]
+            ang += Lw + mass[i] * np.cross(s[i, 0:3], s[i, 7:10])
+        return lin, ang
+    lin0, ang0 = momenta(o.get_rod_state())
+    touched = False
+    for _ in range(400):
+        o.step(m.dt, 1)
+        touched = touched or o.num_pair_contacts() > 0
+    s = o.get_rod_state()
+    lin1, ang1 = momenta(s)
+    assert touched and s[0, 8] < -1.0 and s[1, 8] > -7.0, s[:, 8]  # the struck rod moves off, the striker slows down
+    assert np.abs(lin1 - lin0).max() < 1e-9 * np.abs(lin0).max()
+    # the gyroscopic term is integrated explicitly (btRigidBody::computeGyroscopicForce): angular momentum drifts at its order only
+    assert np.abs(ang1 - ang0).max() < 2e-3 * max(1.0, np.abs(ang0).max()), (ang0, ang1)
+    (p1, q1, r1), (p2, q2, r2) = rod_axes(m, s)
+    assert segment_distance(p1, q1, p2, q2) - r1 - r2 > -0.05      # and they did not pass through each other
+
+
+def test_oracle_prism_rods_touch_instead_of_passing_through():
+    """3_prism without ground: the pretensioned strings fold the prism until its rods meet (step ~180 of the golden drop)."""
+    m = nt.build_example("3_prism_noground")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "prism_drop.npz"))
+    o = _oracle(m, g["rods0"])
+    o.step(m.dt, 600)
+    assert o.min_clearance() > -0.08, o.min_clearance()
+    o2 = _oracle(m, g["rods0"])
+    o2.set_pair_contact_cap(0)
+    o2.step(m.dt, 600)
+    assert o2.min_clearance() < -0.3, o2.min_clearance()          # without pair contacts the rods interpenetrate deeply
+
+
 # ------------------------------------------------------------------------------------------------ learning outer loop (SURVEY 3.5)
 def test_neuroevolution_population_bookkeeping(tmp_path):
     """Ordering, the lenient maximum, the int-truncated average, mutation of the worst by copies of the best, and the .nnw format with
