@@ -398,6 +398,14 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = w.launch_count() - launches0
     status_bad = int((w.status() & 1).sum())
+    # contact between bodies (rod x rod): the smallest surface distance between two rods every environment has seen over the warm-up and
+    # timed launches, measured by the step kernel itself on every step
+    clr = w.min_clearance()
+    radius = float(model.shapes[0].radius)
+    body_body = {"pair_contacts": "on (tgb_pairs.cuh: every pair of bodies tested every step)", "min_clearance": float(clr.min()),
+                 "envs_touching": int((clr <= 0.02).sum()), "envs_deeper_than_solver_slop": int((clr < -0.1).sum()),
+                 "envs_deeper_than_one_radius": int((clr < -radius).sum()), "envs": int(n_env),
+                 "sim_steps_seen": int(H * (args.steps + args.warmup))}
 
     # ---- end to end through the C ABI with pinned host buffers ---------------------------------------------------
     def pinned(a):
@@ -459,6 +467,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_total / args.steps, "checksum_mean_tension": e2e_checksum},
             "gpu_launches": int(launches),
+            "body_body": body_body,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(args.workload, H), "kernel": "tgb_step_kernel<%s,%d>" % (args.precision, lanes),

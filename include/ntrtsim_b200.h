@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define TGB_ABI_VERSION 3
+#define TGB_ABI_VERSION 4
 
 typedef enum {
     TGB_OK = 0,
@@ -314,6 +314,21 @@ tgb_status tgb_launch_count(const tgb_world* w, int64_t* out);
 tgb_status tgb_launch_geometry(const tgb_world* w, int32_t* lanes_per_env, int32_t* block, int32_t* grid);
 /* Override lanes per env (1,2,4,8,16,32) before tgb_finalize; 0 = automatic. */
 tgb_status tgb_set_lanes_per_env(tgb_world* w, int32_t lanes);
+
+/* Contact between the bodies of an environment (ABI version 4).  The reference's world collides every pair of rigid bodies
+   (src/core/tgWorldBulletPhysicsImpl.cpp:82-107: btAxisSweep3 + btDefaultCollisionConfiguration; rods are btCylinderShape,
+   src/tgcreator/tgRodInfo.cpp:99-113): rods of a tensegrity that fold onto each other, vertebrae of a spine that meet.  Here every pair
+   of bodies with at least one dynamic member is tested on every step (cylinders as the capsules inscribed in them, spheres; boxes
+   take no part) and a pair within the contact breaking threshold gets rows that couple the two bodies in the contact solver.
+   `cap` = rows of this kind kept per environment (default TGB_DEFAULT_PAIR_CONTACT_CAP, at most 4 per pair of bodies); 0 switches
+   the contact between bodies off (bodies then pass through each other, as in ABI version <= 3).  Before tgb_finalize. */
+#define TGB_DEFAULT_PAIR_CONTACT_CAP 6
+tgb_status tgb_set_pair_contact_cap(tgb_world* w, int32_t cap);
+
+/* out[env_count]: the smallest surface distance between the collision shapes (capsules, spheres) of two different bodies of the
+   environment that any step has seen since tgb_finalize or the last call with reset != 0 (1e30: no pair has come near; measured for
+   pairs whose bounding spheres overlap).  Negative = the shapes overlap by that much. */
+tgb_status tgb_get_min_clearance(tgb_world* w, int32_t env_begin, int32_t env_count, double* out, int32_t reset);
 
 /* Threads per CTA of the step kernel (32, 64, 96, 128; a multiple of lanes per env); 0 = automatic
    (also settable through the environment variable TGB_BLOCK_THREADS). */

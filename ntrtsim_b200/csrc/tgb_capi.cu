@@ -50,6 +50,8 @@ struct tgb_world {
     const tgb_ops* ops = nullptr;
     size_t scalarBytes = 4;
     int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0, maxInc = 0, nObst = 0, modelObstOff = 0;
+    int nPairs = 0, modelPairOff = 0, pairCap = TGB_DEFAULT_PAIR_CONTACT_CAP; /* contact between bodies (tgb_pairs.cuh) */
+    float* d_min_clearance = nullptr;
     int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0, wideMode = -1;
     mutable int wideCtasPerSm[2] = {-1, -1}; /* by controller class (simple, sine); -1 = not asked yet */
     int smCount = 148;
@@ -127,6 +129,7 @@ struct tgb_world {
         if (d_stage) cudaFree(d_stage);
         if (h_stage) cudaFreeHost(h_stage);
         if (d_scores) cudaFree(d_scores);
+        if (d_min_clearance) cudaFree(d_min_clearance);
         if (d_cpg_topo) cudaFree(d_cpg_topo);
         if (d_cpg_imp) cudaFree(d_cpg_imp);
         if (d_cpg_state) cudaFree(d_cpg_state);
@@ -149,7 +152,7 @@ bool rangeOk(const tgb_world* w, int envBegin, int envCount) {
 
 template <typename T>
 void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vector<int>& ints, int& nInc, int& crecOff, int& cirecOff, int& maxInc,
-               int& nObst, int& obstOff) {
+               int& nObst, int& obstOff, int& nPairs, int& pairOff) {
     const int R = w->R, C = w->C, S = w->S;
     crecOff = (TGB_NBF * R + TGB_NSF * S + TGB_NCF * C + 3) & ~3;
     std::vector<T> t((size_t)crecOff + (size_t)TGB_CREC * C, T(0));
@@ -189,6 +192,17 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         bt[BF_RESTITUTION * R + b] = (T)d.restitution;
         bt[BF_MASS * R + b] = (T)d.mass;
         bt[BF_FRICTION * R + b] = (T)d.friction;
+        {
+            /* every capsule of the body (tgb_pairs.cuh) lies within this radius of the body origin */
+            double bound = 0.0;
+            for (int sI = d.shape_begin; sI < d.shape_begin + d.shape_count; ++sI) {
+                const tgb_shape_desc& sh = w->shapes[sI];
+                if (sh.kind == TGB_SHAPE_BOX) continue;
+                const double segH = sh.kind == TGB_SHAPE_SPHERE ? 0.0 : std::max(0.0, sh.half_length - sh.radius);
+                bound = std::max(bound, std::sqrt(sh.pos[0] * sh.pos[0] + sh.pos[1] * sh.pos[1] + sh.pos[2] * sh.pos[2]) + segH + sh.radius);
+            }
+            bt[BF_BOUND * R + b] = (T)(bound * (1.0 + 1e-6));
+        }
         bi[BI_SHAPE_BEGIN * R + b] = d.shape_begin;
         bi[BI_SHAPE_COUNT * R + b] = d.shape_count;
         bi[BI_INC_BEGIN * R + b] = incPos;
@@ -224,6 +238,7 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         for (int k = 0; k < 9; ++k) st[(SF_ROT0 + k) * S + s] = (T)m[k];
         st[SF_KIND * S + s] = (T)d.kind;
         st[SF_HALFZ * S + s] = (T)d.half_extent_z;
+        st[SF_SEGH * S + s] = d.kind == TGB_SHAPE_CYLINDER ? (T)std::max(0.0, d.half_length - d.radius) : T(0);
     }
     for (int c = 0; c < C; ++c) {
         const tgb_cable_desc& d = w->cables[c];
@@ -252,6 +267,22 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
         for (int s = w->bodies[b].shape_begin; s < w->bodies[b].shape_begin + w->bodies[b].shape_count; ++s)
             if (w->shapes[s].kind == TGB_SHAPE_BOX) { ints.push_back(b); ints.push_back(s); ++nObst; }
     }
+    /* pairs of bodies that can collide: at least one of them dynamic, both with a shape that is not a box */
+    pairOff = (int)ints.size();
+    nPairs = 0;
+    {
+        std::vector<char> hasCapsule(R, 0);
+        for (int b = 0; b < R; ++b)
+            for (int sI = w->bodies[b].shape_begin; sI < w->bodies[b].shape_begin + w->bodies[b].shape_count; ++sI)
+                if (w->shapes[sI].kind != TGB_SHAPE_BOX) hasCapsule[b] = 1;
+        for (int ia = 0; ia < R; ++ia)
+            for (int ib = ia + 1; ib < R; ++ib) {
+                if (w->bodies[ia].mass == 0.0 && w->bodies[ib].mass == 0.0) continue;
+                if (!hasCapsule[ia] || !hasCapsule[ib]) continue;
+                ints.push_back(ia + 32 * ib);
+                ++nPairs;
+            }
+    }
     tbytes.resize(t.size() * sizeof(T));
     std::memcpy(tbytes.data(), t.data(), tbytes.size());
 }
@@ -273,6 +304,7 @@ bool wideLayout(const tgb_world* w) {
         a.R = w->R; a.C = w->C; a.S = w->S; a.max_inc = w->maxInc; a.stride = w->stride; a.cap_contacts = w->capContacts;
         a.ctrl_kind = w->ctrlKind; a.ctrl_stride = std::max(w->C, TGB_ESCAPE_PARAMS); a.ground_kind = w->ground.kind;
         a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
+        a.n_pairs = w->pairCap > 0 ? w->nPairs : 0; a.pair_cap = w->pairCap;
         int ctas = 0;
         if (w->ops->wide_ctas_per_sm(a, w->lanes, &ctas) != cudaSuccess) { cudaGetLastError(); ctas = 0; }
         w->wideCtasPerSm[cls] = ctas;
@@ -303,6 +335,8 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
     a.model_crec_off = w->modelCrecOff; a.model_cirec_off = w->modelCirecOff;
     a.n_obst = w->nObst; a.model_obst_off = w->modelObstOff;
+    a.n_pairs = w->pairCap > 0 ? w->nPairs : 0; a.model_pair_off = w->modelPairOff; a.pair_cap = w->pairCap;
+    a.min_clearance = w->d_min_clearance;
     a.n_dyn = 0;
     for (int b = 0; b < w->R; ++b) a.n_dyn += w->bodies[b].mass != 0.0;
     a.dt = dt;
@@ -466,6 +500,32 @@ tgb_status tgb_set_wide_layout(tgb_world* w, int32_t mode) {
     return TGB_OK;
 }
 
+tgb_status tgb_set_pair_contact_cap(tgb_world* w, int32_t cap) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (w->finalized) return fail(TGB_ERR_STATE, "tgb_set_pair_contact_cap: world already finalized");
+    if (cap < 0 || cap > 64) return fail(TGB_ERR_INVALID_ARGUMENT, "pair contact cap must be 0 (bodies do not collide) .. 64");
+    w->pairCap = cap;
+    return TGB_OK;
+}
+
+tgb_status tgb_get_min_clearance(tgb_world* w, int32_t env_begin, int32_t env_count, double* out, int32_t reset) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (!w->finalized) return fail(TGB_ERR_STATE, "world is not finalized");
+    TGB_CUDA(cudaSetDevice(w->cfg.device));
+    if (!out || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_min_clearance: bad range or NULL buffer");
+    if (env_count == 0) return TGB_OK;
+    std::vector<float> tmp((size_t)env_count);
+    TGB_CUDA(cudaMemcpyAsync(tmp.data(), w->d_min_clearance + env_begin, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    for (int i = 0; i < env_count; ++i) out[i] = (double)tmp[i];
+    if (reset) {
+        for (int i = 0; i < env_count; ++i) tmp[i] = 1e30f;
+        TGB_CUDA(cudaMemcpyAsync(w->d_min_clearance + env_begin, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
+        TGB_CUDA(cudaStreamSynchronize(w->stream));
+    }
+    return TGB_OK;
+}
+
 tgb_status tgb_set_block_threads(tgb_world* w, int32_t threads) {
     if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
     if (threads != 0 && threads != 32 && threads != 64 && threads != 96 && threads != 128)
@@ -516,8 +576,8 @@ tgb_status tgb_finalize(tgb_world* w) {
 
     std::vector<unsigned char> tbytes;
     std::vector<int> ints;
-    if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff);
-    else packModel<float>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff);
+    if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff, w->nPairs, w->modelPairOff);
+    else packModel<float>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff, w->nPairs, w->modelPairOff);
     /* obstacle contacts share the rows: room for those of up to two obstacles touched at once */
     w->capContacts *= 1 + std::min(w->nObst, 2);
     w->modelTWords = (int)(tbytes.size() / w->scalarBytes);
@@ -533,6 +593,11 @@ tgb_status tgb_finalize(tgb_world* w) {
     TGB_CUDA(cudaMalloc(&w->d_com0, (size_t)n * 3 * sizeof(double)));
     TGB_CUDA(cudaMalloc(&w->d_status, (size_t)n * sizeof(int)));
     TGB_CUDA(cudaMemset(w->d_status, 0, (size_t)n * sizeof(int)));
+    {
+        std::vector<float> far((size_t)n, 1e30f);
+        TGB_CUDA(cudaMalloc(&w->d_min_clearance, (size_t)n * sizeof(float)));
+        TGB_CUDA(cudaMemcpy(w->d_min_clearance, far.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    }
     TGB_CUDA(cudaMalloc(&w->d_scores, (size_t)n * 2 * sizeof(float)));
     TGB_CUDA(cudaMemset(w->d_scores, 0, (size_t)n * 2 * sizeof(float)));
 

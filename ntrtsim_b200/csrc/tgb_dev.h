@@ -27,11 +27,13 @@
 #include <stdint.h>
 
 /* body T-fields */
-enum { BF_INVMASS = 0, BF_GFY, BF_INVIX, BF_INVIY, BF_INVIZ, BF_IX, BF_IY, BF_IZ, BF_MU, BF_RESTITUTION, BF_MASS, BF_FRICTION, TGB_NBF };
+enum { BF_INVMASS = 0, BF_GFY, BF_INVIX, BF_INVIY, BF_INVIZ, BF_IX, BF_IY, BF_IZ, BF_MU, BF_RESTITUTION, BF_MASS, BF_FRICTION,
+       BF_BOUND /* radius about the body origin that holds every capsule of the body (body-pair culling) */, TGB_NBF };
 /* body int-fields */
 enum { BI_SHAPE_BEGIN = 0, BI_SHAPE_COUNT, BI_INC_BEGIN, BI_INC_COUNT, BI_GYRO, TGB_NBI };
 /* shape T-fields */
-enum { SF_RADIUS = 0, SF_HALFLEN, SF_MARGIN, SF_POSX, SF_POSY, SF_POSZ, SF_ROT0, SF_KIND = SF_ROT0 + 9 /* tgb_shape_kind */, SF_HALFZ /* box */, TGB_NSF };
+enum { SF_RADIUS = 0, SF_HALFLEN, SF_MARGIN, SF_POSX, SF_POSY, SF_POSZ, SF_ROT0, SF_KIND = SF_ROT0 + 9 /* tgb_shape_kind */, SF_HALFZ /* box */,
+       SF_SEGH /* half length of the capsule core segment of the body-pair manifold: max(0, half length - radius), 0 for a sphere */, TGB_NSF };
 /* cable T-fields */
 enum {
     CF_LAX = 0, CF_LAY, CF_LAZ, CF_LBX, CF_LBY, CF_LBZ, CF_K, CF_C, CF_MAXTENS, CF_TVEL, CF_MINAL, CF_MINRL,
@@ -56,6 +58,14 @@ enum {
     CT_INVDIAGT = 20, CT_RHST, CT_LAMT, TGB_NCT,
     /* worlds with static obstacles: the row's own normal and friction coefficient behind the common part */
     CT_NRM = TGB_NCT, CT_MU = CT_NRM + 3, TGB_NCT_OBST = CT_MU + 2 /* odd row stride: rows of neighbouring lanes on distinct banks */
+};
+/* Row of a contact between two bodies (tgb_pairs.cuh), T words in shared memory.  The two sides' Jacobian blocks are not stored: each
+   side's lane re-forms r x n, Iinv (r x n) from its own r and the inverse inertia in its registers.  Between detection and row
+   set-up PR_RA / PR_RB hold the contact points on the two surfaces (frame-relative), PR_LAMN the distance, PR_LAMPUSH the
+   combined restitution. */
+enum {
+    PR_N = 0, PR_RA = 3, PR_RB = 6, PR_T = 9, PR_INVDIAGN = 12, PR_RHSN, PR_RHSPEN, PR_LAMN, PR_LAMPUSH, PR_INVDIAGT, PR_RHST, PR_LAMT,
+    PR_MU, PR_IDS /* body A + 32 * body B */, TGB_NPR
 };
 /* frame doubles */
 enum { FR_O = 0, FR_V = 3, FR_CTRLTIME = 6, FR_SPARE = 7, TGB_NFR = 8 };
@@ -93,6 +103,9 @@ struct tgb_step_args {
     int model_crec_off, model_cirec_off; /* word offsets of the per-cable records inside model_t / model_i */
     int n_dyn;                           /* bodies with mass: worlds with obstacles keep contact rows for these only */
     int n_obst, model_obst_off;          /* static obstacles: n_obst pairs (static body, its box shape) at this word offset of model_i */
+    int n_pairs, model_pair_off;         /* pairs of bodies that can collide (at least one dynamic): body A + 32 * body B, A < B, at this word offset of model_i */
+    int pair_cap;                        /* rows of body-pair contacts per environment; 0 = bodies do not collide with each other */
+    float* min_clearance;                /* [n_env] running minimum of the surface distance between two bodies' capsules, or NULL */
     double dt;
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */
     double ground_restitution;

@@ -20,8 +20,10 @@
  *                                     list; deterministic, no atomics), then the whole world step of that body:
  *                                     gravity + gyroscopic term, ground contact manifold, projected Gauss-Seidel,
  *                                     transform integration; publish the new pose
- * Bodies only interact through cables, and the ground is static, so the contact solve of each body is independent
- * and a body never leaves its lane.  Two __syncwarp() per step, no block-level barrier inside the step loop.
+ * Bodies interact through cables and, when two of them come within the contact band, through rows between two bodies
+ * (tgb_pairs.cuh).  Without such a row -- the common case, checked every step -- the ground is the only partner, the contact
+ * solve of each body is independent and never leaves its lane.  Two __syncwarp() per step, no block-level barrier inside
+ * the step loop.
  * HBM is touched only at launch boundaries: the CTA's environment records are one contiguous span that is moved
  * with 128-bit accesses into shared memory and back.
  *
@@ -31,6 +33,7 @@
 #include "../../include/ntrtsim_b200.h"
 #include "tgb_dev.h"
 #include "tgb_math.cuh"
+#include "tgb_pairs.cuh"
 
 #include <type_traits>
 
@@ -321,7 +324,6 @@ TGB_D T boxDistance(const V3<T>& p, const V3<T>& co, const V3<T>& e0, const V3<T
 /* Contact solve of a body with two or more contact points (a rod lying on a rim line, a compound body): rare next to the
    single-point case, so it lives out of line -- the step loop's hot instructions stay within the instruction cache.
    ct = row 0 of this body, rowStride = words between consecutive rows of one body. */
-template <typename T> struct ContactSolveOut { V3<T> dLin, dAng, push, turn; };
 template <typename T, bool kFast>
 __device__ __noinline__ ContactSolveOut<T> solveContactsGeneral(T* ct, int rowStride, int nc, int iterations, bool anyPen, V3<T> gn, T invMass,
                                                                  T mu) {
@@ -583,7 +585,9 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     const int jWords = kFast ? a.max_inc * LPE * 8 : 3 * C;
     constexpr int NCT = OBST ? (int)TGB_NCT_OBST : (int)TGB_NCT;
     const int rowBodies = OBST ? a.n_dyn : R;     /* worlds with obstacles: no rows for the static bodies */
-    const int ctWords = a.cap_contacts * NCT * rowBodies; /* rows [slot][body][NCT]: 23 words apart across lanes, conflict-free */
+    const int ctOnlyWords = a.cap_contacts * NCT * rowBodies; /* rows [slot][body][NCT]: 23 words apart across lanes, conflict-free */
+    const int pairWords = a.n_pairs > 0 ? a.pair_cap * (int)TGB_NPR : 0; /* rows between two bodies, behind the contact rows */
+    const int ctWords = ctOnlyWords + pairWords;
     /* the contact rows (live from contact generation to the end of the solver) and the cable impulses (live from the cable
        phase to the impulse gather) share one region: shared memory per environment decides how many CTAs an SM holds */
     const int exchangeWords = TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords;
@@ -596,6 +600,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     T* sPose = sState + a.stride;              /* [LPE][12] : pos3, basis9 of each body, one 16-byte aligned record per body */
     T* sJ = sPose + poseWords;                 /* [C][3] */
     T* sCt = TGB_EXCHANGE_UNION ? sJ : sJ + jWords; /* [cap][R][TGB_NCT], same region */
+    T* sPairRows = sCt + ctOnlyWords;               /* [pair_cap][TGB_NPR] */
     constexpr bool cpgOn = CLASS == TGB_CLASS_CPG;
     constexpr bool sineOn = CLASS == TGB_CLASS_SINE;
     constexpr bool simpleOn = CLASS == TGB_CLASS_SIMPLE;
@@ -903,6 +908,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                shape0.r1.x == T(0) && shape0.r1.y == T(1) && shape0.r1.z == T(0);
 
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
+    T pairClearance = T(1e30); /* smallest surface distance of two bodies' capsules this lane has seen */
 #ifdef TGB_STATS
     const long long statT0 = clock64();
 #endif
@@ -912,7 +918,36 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         const long long statA = clock64();
 #endif
         /* =============================== world step (tgSimulation.cpp:205) =============================== */
-        if (dynamic && doWorld) {
+        if (doWorld) { /* warp-uniform */
+        V3<T> extLin(T(0), T(0), T(0)), extAng(T(0), T(0), T(0)), linvel(T(0), T(0), T(0));
+        int nc = 0;
+        bool anyPen = false;
+        /* ---- contact between bodies: detection from the published poses (tgb_pairs.cuh).  Every lane of the body warp takes part; the
+           lanes of a group take the environment's body pairs round robin.  nPairRows stays 0 unless a pair is within the contact band. */
+        int nPairRows = 0;
+        if (a.n_pairs > 0 && a.pair_cap > 0 && bodyWarp) {
+            const unsigned groupMaskP = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
+            const int* pairTable = sModelI + a.model_pair_off;
+            for (int p0 = 0; p0 < a.n_pairs; p0 += LPE) {
+                const int p = p0 + lane;
+                int ia = 0, ib = 0;
+                bool near = false;
+                if (p < a.n_pairs) {
+                    const int code = pairTable[p];
+                    ia = code & 31; ib = code >> 5;
+                    near = pairNear<T>(M, sPose, ia, ib, pairClearance);
+                }
+                unsigned nearMask = __ballot_sync(fullMask, near) & groupMaskP;
+                while (nearMask != 0u) { /* rare; group-uniform */
+                    const int L = __ffs(nearMask) - 1;
+                    nearMask &= nearMask - 1u;
+                    int cnt = 0;
+                    if (warpLane == L) cnt = emitPairRows<T>(M, sPose, ia, ib, sPairRows, nPairRows, a.pair_cap);
+                    nPairRows += __shfl_sync(groupMaskP, cnt, L);
+                }
+            }
+        }
+        if (dynamic) {
             /* applyGravity + solver-body external impulses */
             V3<T> totalForce(T(0), gfy, T(0)), totalTorque(T(0), T(0), T(0));
             if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) {
@@ -933,8 +968,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     totalTorque += rel.cross(f);
                 }
             }
-            V3<T> extLin(T(0), (gfy * invMass) * dt, T(0));
-            V3<T> extAng(T(0), T(0), T(0));
+            extLin = V3<T>(T(0), (gfy * invMass) * dt, T(0));
             if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) {
                 extLin = (totalForce * invMass) * dt;
                 extAng = b.Iinv.tmul(totalTorque) * dt;
@@ -958,11 +992,9 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 }
             }
             const V3<T> Vf((T)Vx, (T)Vy, (T)Vz);
-            const V3<T> linvel = b.v + Vf; /* world linear velocity */
+            linvel = b.v + Vf; /* world linear velocity */
 
             /* ---- ground contact manifold (analytic cylinder rim points against the ground surface) ---- */
-            int nc = 0;
-            bool anyPen = false;
             if (GROUND && (!OBST || a.ground_kind != TGB_GROUND_EMPTY)) {
                 /* signed height of the frame origin above the surface, formed in double */
                 const T originHeight = (T)(a.gn[0] * Ox + a.gn[1] * Oy + a.gn[2] * Oz - a.goff);
@@ -1208,9 +1240,22 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 #ifdef TGB_STATS
             statNc = nc; statPen = anyPen;
 #endif
+        } /* dynamic: external impulses and the rows against the static world */
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
-            if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
+            if (nPairRows > 0) {
+                /* group-uniform: this environment has rows between two bodies; all its lanes solve together (tgb_pairs.cuh) */
+                const unsigned groupMaskP = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
+                __syncwarp(groupMaskP); /* the pair rows and every body's own rows are in shared memory */
+                const bool mine = dynamic;
+                const M3<T> IinvP = b.Iinv;
+                const ContactSolveOut<T> o = solveCoupled<T, kFast, OBST>(
+                    sCt + rowIdx * NCT, rowBodies * NCT, mine ? nc : 0, mine && anyPen, gn, mu, sPairRows, nPairRows, lane, groupLane0, groupMaskP, b.x,
+                    IinvP, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt, a.iterations);
+                dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
+            } else if (!dynamic) {
+                /* nothing to solve */
+            } else if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
                 /* in worlds with obstacles the single row carries its own normal and friction coefficient */
                 const V3<T> gn1 = OBST ? V3<T>(CT(0, CT_NRM + 0), CT(0, CT_NRM + 1), CT(0, CT_NRM + 2)) : gn;
                 const T mu1 = OBST ? CT(0, CT_MU) : mu;
@@ -1258,13 +1303,15 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             }
 
             /* ---- write back, split-impulse correction, integrateTransforms ---- */
-            b.v = (b.v + dLin) + extLin;
-            b.w = (b.w + dAng) + extAng;
-            if (push.nonzero() || turn.nonzero()) integrateTransform(b.x, b.q, push, turn * SolverConst<T>::turnErp(), dt);
-            integrateTransform(b.x, b.q, b.v, b.w, dt);
-            b.B = M3<T>::fromQuat(b.q);
-            b.Iinv = b.B.conjugateDiag(invI);
-        }
+            if (dynamic) {
+                b.v = (b.v + dLin) + extLin;
+                b.w = (b.w + dAng) + extAng;
+                if (push.nonzero() || turn.nonzero()) integrateTransform(b.x, b.q, push, turn * SolverConst<T>::turnErp(), dt);
+                integrateTransform(b.x, b.q, b.v, b.w, dt);
+                b.B = M3<T>::fromQuat(b.q);
+                b.Iinv = b.B.conjugateDiag(invI);
+            }
+        } /* doWorld */
 
         /* ---- env frame: advance the origin with the frame velocity, then re-centre on the frame body ---- */
         if (frameMoves && doWorld && bodyWarp) {
@@ -1711,6 +1758,12 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             if (!(h > a.height_lo && h < a.height_hi)) st |= TGB_STATUS_HEIGHT;
         }
         if (live && lane == 0 && st != 0) a.status[env] |= st;
+        if (a.min_clearance != nullptr) {
+            float clr = (float)pairClearance;
+#pragma unroll
+            for (int off = LPE / 2; off > 0; off >>= 1) clr = fminf(clr, __shfl_xor_sync(fullMask, clr, off));
+            if (live && lane == 0 && clr < a.min_clearance[env]) a.min_clearance[env] = clr;
+        }
     }
     if (WIDE) __syncthreads(); else __syncwarp();
     if (live) {
@@ -1741,7 +1794,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
     const int groupsPerBlock = a.wide ? 32 / lpe : threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
-    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C, ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST * a.n_dyn : (int)TGB_NCT * a.R);
+    const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C;
+    const int ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST * a.n_dyn : (int)TGB_NCT * a.R) + (a.n_pairs > 0 ? a.pair_cap * (int)TGB_NPR : 0);
     int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords);
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }

@@ -64,7 +64,8 @@ class FlatModel(object):
 
 
 class BatchedWorld(object):
-    def __init__(self, model, n_env, precision="f32", device=0, solver_iterations=0, lanes_per_env=0, block_threads=0, wide=None):
+    def __init__(self, model, n_env, precision="f32", device=0, solver_iterations=0, lanes_per_env=0, block_threads=0, wide=None,
+                 pair_contact_cap=None):
         self._lib = capi.load()
         self.model = model
         self.n_env = int(n_env)
@@ -82,6 +83,8 @@ class BatchedWorld(object):
                 capi.check(self._lib.tgb_set_block_threads(h, block_threads))
             if wide is not None:
                 capi.check(self._lib.tgb_set_wide_layout(h, 1 if wide else 0))
+            if pair_contact_cap is not None:
+                capi.check(self._lib.tgb_set_pair_contact_cap(h, int(pair_contact_cap)))
             capi.check(self._lib.tgb_finalize(h))
         except Exception:
             self.close()
@@ -208,6 +211,13 @@ class BatchedWorld(object):
         n = self.n_env - env_begin if env_count is None else env_count
         out = np.empty(n, dtype=np.int32)
         capi.check(self._lib.tgb_get_status(self._h, env_begin, n, _ptr(out)))
+        return out
+
+    def min_clearance(self, env_begin=0, env_count=None, reset=False):
+        """smallest surface distance between two bodies' collision shapes seen by any step so far, per environment"""
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.empty(n)
+        capi.check(self._lib.tgb_get_min_clearance(self._h, env_begin, n, _ptr(out), 1 if reset else 0))
         return out
 
     def set_height_window(self, lo, hi):

@@ -717,6 +717,12 @@ struct tgo_world {
                         if (!shapeSegment(A, shapes[sa], ga) || !shapeSegment(B, shapes[sb], gb)) continue;
                         double s0, t0, b, c, f;
                         closestSegmentParams(ga, gb, s0, t0, b, c, f);
+                        {
+                            /* the surface distance of the pair = the distance at the closest points */
+                            const V3 dv0 = (ga.p + ga.d * s0) - (gb.p + gb.d * t0);
+                            const double clearance = std::sqrt(dv0.length2()) - ga.r - gb.r;
+                            if (clearance < minClearance) minClearance = clearance;
+                        }
                         double sp[2] = {s0, s0}, tp[2] = {t0, t0};
                         int np = 1;
                         if (ga.h > 0.0 && gb.h > 0.0 && 1.0 - b * b < kParallel) {
@@ -735,7 +741,6 @@ struct tgo_world {
                             const double d2 = dv.length2();
                             const double d = std::sqrt(d2);
                             const double dist = d - ga.r - gb.r;
-                            if (dist < minClearance) minClearance = dist;
                             if (dist > kBreakingThreshold) continue;
                             if (count >= 4 || pairRows >= pairCap) continue;
                             V3 n;

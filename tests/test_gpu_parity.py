@@ -1073,3 +1073,153 @@ def test_neuroevolution_generations_on_device():
     assert sizes == [24, 8, 8]
     assert evo.population.max_score[0] >= best0 or evo.population.max_score[0] >= 0.5 * (best0 + first[:, 0].min())
     assert len(evo.log) == 3 and evo.log[0][0] == 24
+
+
+# ------------------------------------------------------------------------------------------------ contact between bodies
+# tgWorldBulletPhysicsImpl.cpp:82-107: every pair of bodies of the world collides.  tgb_pairs.cuh against the oracle's
+# generateBodyPairContacts, and the known answers of tests/test_cpu.py asked of the CUDA path.
+def _text_model(tmp_path, name, text):
+    from test_cpu import _build_text
+    return _build_text(tmp_path, name, text)
+
+
+@pytest.mark.parametrize("precision,steps", [("f64", 400), ("f32", 150)])
+def test_rod_on_static_rods_matches_oracle(tmp_path, precision, steps):
+    """a rod dropped across two static rods: dynamic x static pair rows next to nothing else (the rod never reaches the ground)"""
+    from test_cpu import RAILS
+    model = _text_model(tmp_path, "rails.yaml", RAILS)
+    n_env = 8
+    rng = np.random.default_rng(7)
+    rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+    rods[:, 2, 0] += rng.uniform(-0.5, 0.5, size=n_env)   # where it crosses the rails
+    rods[:, 2, 1] += rng.uniform(0.0, 1.0, size=n_env)
+    cab = np.zeros((n_env, 0, 2))
+    w = nt.BatchedWorld(model, n_env, precision=precision)
+    w.set_rod_state(rods)
+    w.step(model.dt, steps)
+    rd, clr = w.get_rod_state(), w.min_clearance()
+    w.close()
+    ro = np.empty_like(rd)
+    clr_o = np.empty(n_env)
+    for e in range(n_env):
+        o = oracle_py.OracleWorld(model, capi.WorldCfg)
+        o.set_rod_state(rods[e])
+        o.step(model.dt, steps)
+        ro[e], clr_o[e] = o.get_rod_state(), o.min_clearance()
+    e = rod_errors(rd, ro, 1.0)
+    print("rod on rails %s %d steps: %s clearance dev %s oracle %s" % (precision, steps, e, clr, clr_o))
+    tol = 1e-7 if precision == "f64" else 2e-3
+    assert max(e[0], e[1]) < tol and max(e[2], e[3]) < tol * 100, e
+    assert np.abs(clr - clr_o).max() < (1e-6 if precision == "f64" else 1e-3)
+    assert (ro[:, 2, 1] > 2.9).all() and (rd[:, 2, 1] > 2.9).all()   # resting on the rails (ground top face at 1.5, rails at 2.0)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_rod_rod_impact_conserves_momentum_on_device(tmp_path, precision):
+    from test_cpu import CROSSED_RODS
+    model = _text_model(tmp_path, "crossed.yaml", CROSSED_RODS)
+    model.ground.kind = capi.TGB_GROUND_EMPTY
+    model.gravity = 0.0
+    n_env = 5
+    rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+    rods[:, 1, 8] = -8.0
+    rods[:, 1, 0] += np.linspace(-1.0, 1.0, n_env)         # hit at different places
+    mass = np.array([b.mass for b in model.bodies])
+    w = nt.BatchedWorld(model, n_env, precision=precision)
+    w.set_rod_state(rods)
+    w.step(model.dt, 400)
+    rd, clr = w.get_rod_state(), w.min_clearance()
+    w.close()
+    p0 = (mass[None, :, None] * rods[:, :, 7:10]).sum(1)
+    p1 = (mass[None, :, None] * rd[:, :, 7:10]).sum(1)
+    print("rod-rod impact %s: momentum drift %.3e, clearance %s" % (precision, np.abs(p1 - p0).max(), clr))
+    assert np.abs(p1 - p0).max() < (1e-9 if precision == "f64" else 2e-4) * np.abs(p0).max()
+    assert (rd[:, 0, 8] < -1.0).all() and (rd[:, 1, 8] > -7.0).all()   # the struck rod moves off, the striker slows down
+    assert (clr < 0.021).all() and (clr > -0.06).all()                # they touched and did not pass through each other
+    if precision == "f64":
+        ro = np.stack([_oracle_states(model, rods[e], 400) for e in range(n_env)])
+        assert max(rod_errors(rd, ro, 1.0)) < 1e-7
+
+
+def _oracle_states(model, rods, steps, cab=None, ctrl=0, params=None, cap=None):
+    o = oracle_py.OracleWorld(model, capi.WorldCfg)
+    if cap is not None:
+        o.set_pair_contact_cap(cap)
+    o.set_rod_state(rods)
+    if cab is not None:
+        o.set_cable_state(cab)
+    if ctrl:
+        o.set_controller(ctrl, params)
+    o.step(model.dt, steps)
+    return o.get_rod_state()
+
+
+def test_prism_rods_meet_f64():
+    """config 2 beyond the contact-free part: the pretensioned strings fold the 3-prism until its rods meet (step ~180 for the model
+    pose); the double path follows the oracle through the rod-rod contact, and the clearance never goes below the solver's slop."""
+    model = nt.build_example("3_prism_noground")
+    n_env, steps = 24, 450
+    rods, cab = random_poses(model, n_env, seed=1234), tiled_cables(model, n_env)
+    w = nt.BatchedWorld(model, n_env, precision="f64")
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    w.step(model.dt, steps)
+    rd, cd, clr = w.get_rod_state(), w.get_cable_obs(), w.min_clearance()
+    w.close()
+    ro, co = oracle_rollout(model, rods, cab, steps)
+    e = rod_errors(rd, ro, 1.0)
+    print("prism rods meet f64: %s cables %.3e clearance min %.4f max %.4f" % (e, np.abs(cd - co).max(), clr.min(), clr.max()))
+    assert (clr < 0.02).all() and (clr > -0.08).all()
+    assert max(e) < 1e-6, e
+    # switched off (ABI <= 3 behaviour) the rods pass through each other
+    w = nt.BatchedWorld(model, n_env, precision="f64", pair_contact_cap=0)
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    w.step(model.dt, steps)
+    r0 = w.get_rod_state()
+    w.close()
+    ro0 = np.stack([_oracle_states(model, rods[e], steps, cab[e], cap=0) for e in range(n_env)])
+    assert max(rod_errors(r0, ro0, 1.0)) < 1e-7
+
+
+def test_bench_workload_rods_keep_their_clearance():
+    """on the benchmark workload (seed 2345) rods used to pass through each other in ~8 % of the environments within
+    one launch of 1000 steps.  With the pair contacts no environment goes deeper than the solver's slop, in single precision at the
+    benchmark's own settings; the double path agrees with the oracle on the environments that had a rod-rod contact."""
+    sys.path.insert(0, ROOT)
+    import bench
+    n_env, steps = 256, 1000
+    model, rods, cab, ctrl, params, _ = bench.build_workload("superball", n_env, bench.SEED)
+    w = nt.BatchedWorld(model, n_env, precision="f32")
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    w.set_controller(ctrl, params)
+    w.step(model.dt, steps)
+    clr32 = w.min_clearance()
+    w.close()
+    w = nt.BatchedWorld(model, n_env, precision="f32", pair_contact_cap=0)
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    w.set_controller(ctrl, params)
+    w.step(model.dt, steps)
+    clr_off = w.min_clearance()
+    w.close()
+    print("bench workload, %d envs x %d steps: clearance < 0 in %d envs (pairs on) / %d (off); deepest %.3f / %.3f"
+          % (n_env, steps, (clr32 < 0).sum(), (clr_off < 0).sum(), clr32.min(), clr_off.min()))
+    assert clr32.min() > -0.1
+    assert (clr_off < -0.4).sum() >= 5      # the hole this closes: rods more than a radius inside each other
+    # double precision against the oracle on the environments whose rods met within the first 400 steps
+    steps64 = 400
+    w = nt.BatchedWorld(model, n_env, precision="f64")
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    w.set_controller(ctrl, params)
+    w.step(model.dt, steps64)
+    rd, clr64 = w.get_rod_state(), w.min_clearance()
+    w.close()
+    met = np.where(clr64 < 0.02)[0]
+    assert len(met) >= 3, len(met)
+    ro = np.stack([_oracle_states(model, rods[e], steps64, cab[e], ctrl, params[e]) for e in met])
+    e = rod_errors(rd[met], ro, 1.0)
+    print("bench workload f64, %d envs with a rod-rod contact within %d steps: %s" % (len(met), steps64, e))
+    assert max(e) < 1e-6, e
