@@ -321,7 +321,8 @@ tgb_status tgb_set_lanes_per_env(tgb_world* w, int32_t lanes);
    of bodies with at least one dynamic member is tested on every step (cylinders as the capsules inscribed in them, spheres; boxes
    take no part) and a pair within the contact breaking threshold gets rows that couple the two bodies in the contact solver.
    `cap` = rows of this kind kept per environment (default TGB_DEFAULT_PAIR_CONTACT_CAP, at most 4 per pair of bodies); 0 switches
-   the contact between bodies off (bodies then pass through each other, as in ABI version <= 3).  Before tgb_finalize. */
+   the contact between bodies off (bodies then pass through each other, as in ABI version <= 3); -1 keeps the test but generates no row
+   (tgb_get_min_clearance then measures how far bodies would interpenetrate).  Before tgb_finalize. */
 #define TGB_DEFAULT_PAIR_CONTACT_CAP 6
 tgb_status tgb_set_pair_contact_cap(tgb_world* w, int32_t cap);
 

@@ -202,6 +202,17 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
                 bound = std::max(bound, std::sqrt(sh.pos[0] * sh.pos[0] + sh.pos[1] * sh.pos[1] + sh.pos[2] * sh.pos[2]) + segH + sh.radius);
             }
             bt[BF_BOUND * R + b] = (T)(bound * (1.0 + 1e-6));
+            /* a plain rod / ball: one shape that is not a box, sitting in the body frame */
+            bt[BF_SEGH * R + b] = T(-1); bt[BF_SEGR * R + b] = T(0);
+            if (d.shape_count == 1) {
+                const tgb_shape_desc& sh = w->shapes[d.shape_begin];
+                const bool aligned = sh.pos[0] == 0.0 && sh.pos[1] == 0.0 && sh.pos[2] == 0.0 && sh.quat[0] == 0.0 && sh.quat[1] == 0.0 &&
+                                     sh.quat[2] == 0.0 && sh.quat[3] != 0.0;
+                if (aligned && sh.kind != TGB_SHAPE_BOX) {
+                    bt[BF_SEGH * R + b] = sh.kind == TGB_SHAPE_SPHERE ? T(0) : (T)std::max(0.0, sh.half_length - sh.radius);
+                    bt[BF_SEGR * R + b] = (T)sh.radius;
+                }
+            }
         }
         bi[BI_SHAPE_BEGIN * R + b] = d.shape_begin;
         bi[BI_SHAPE_COUNT * R + b] = d.shape_count;
@@ -304,7 +315,7 @@ bool wideLayout(const tgb_world* w) {
         a.R = w->R; a.C = w->C; a.S = w->S; a.max_inc = w->maxInc; a.stride = w->stride; a.cap_contacts = w->capContacts;
         a.ctrl_kind = w->ctrlKind; a.ctrl_stride = std::max(w->C, TGB_ESCAPE_PARAMS); a.ground_kind = w->ground.kind;
         a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
-        a.n_pairs = w->pairCap > 0 ? w->nPairs : 0; a.pair_cap = w->pairCap;
+        a.n_pairs = w->pairCap != 0 ? w->nPairs : 0; a.pair_cap = w->pairCap;
         int ctas = 0;
         if (w->ops->wide_ctas_per_sm(a, w->lanes, &ctas) != cudaSuccess) { cudaGetLastError(); ctas = 0; }
         w->wideCtasPerSm[cls] = ctas;
@@ -335,7 +346,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
     a.model_crec_off = w->modelCrecOff; a.model_cirec_off = w->modelCirecOff;
     a.n_obst = w->nObst; a.model_obst_off = w->modelObstOff;
-    a.n_pairs = w->pairCap > 0 ? w->nPairs : 0; a.model_pair_off = w->modelPairOff; a.pair_cap = w->pairCap;
+    a.n_pairs = w->pairCap != 0 ? w->nPairs : 0; a.model_pair_off = w->modelPairOff; a.pair_cap = w->pairCap;
     a.min_clearance = w->d_min_clearance;
     a.n_dyn = 0;
     for (int b = 0; b < w->R; ++b) a.n_dyn += w->bodies[b].mass != 0.0;
@@ -503,7 +514,7 @@ tgb_status tgb_set_wide_layout(tgb_world* w, int32_t mode) {
 tgb_status tgb_set_pair_contact_cap(tgb_world* w, int32_t cap) {
     if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
     if (w->finalized) return fail(TGB_ERR_STATE, "tgb_set_pair_contact_cap: world already finalized");
-    if (cap < 0 || cap > 64) return fail(TGB_ERR_INVALID_ARGUMENT, "pair contact cap must be 0 (bodies do not collide) .. 64");
+    if (cap < -1 || cap > 64) return fail(TGB_ERR_INVALID_ARGUMENT, "pair contact cap must be -1 (measure the clearance only), 0 (off) .. 64");
     w->pairCap = cap;
     return TGB_OK;
 }
@@ -574,6 +585,11 @@ tgb_status tgb_finalize(tgb_world* w) {
     if (threads % 32 || threads < 32 || threads > 128) return fail(TGB_ERR_INVALID_ARGUMENT, "bad block size");
     w->threads = threads;
 
+    {
+        /* tuning aid: TGB_PAIR_CAP overrides the pair contact cap (0 = off, -1 = detection only: pairs are tested, no row is emitted) */
+        const char* envCap = std::getenv("TGB_PAIR_CAP");
+        if (envCap) w->pairCap = std::max(-1, std::min(64, std::atoi(envCap)));
+    }
     std::vector<unsigned char> tbytes;
     std::vector<int> ints;
     if (w->cfg.precision == TGB_F64) packModel<double>(w, tbytes, ints, w->nInc, w->modelCrecOff, w->modelCirecOff, w->maxInc, w->nObst, w->modelObstOff, w->nPairs, w->modelPairOff);

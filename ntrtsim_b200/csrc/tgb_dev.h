@@ -28,7 +28,9 @@
 
 /* body T-fields */
 enum { BF_INVMASS = 0, BF_GFY, BF_INVIX, BF_INVIY, BF_INVIZ, BF_IX, BF_IY, BF_IZ, BF_MU, BF_RESTITUTION, BF_MASS, BF_FRICTION,
-       BF_BOUND /* radius about the body origin that holds every capsule of the body (body-pair culling) */, TGB_NBF };
+       BF_BOUND /* radius about the body origin that holds every capsule of the body (body-pair culling) */,
+       BF_SEGH /* a body that is one cylinder or sphere in the body frame (a plain rod): half length of its core segment; else -1 */,
+       BF_SEGR /* and its radius */, TGB_NBF };
 /* body int-fields */
 enum { BI_SHAPE_BEGIN = 0, BI_SHAPE_COUNT, BI_INC_BEGIN, BI_INC_COUNT, BI_GYRO, TGB_NBI };
 /* shape T-fields */

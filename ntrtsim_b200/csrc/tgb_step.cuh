@@ -586,12 +586,14 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     constexpr int NCT = OBST ? (int)TGB_NCT_OBST : (int)TGB_NCT;
     const int rowBodies = OBST ? a.n_dyn : R;     /* worlds with obstacles: no rows for the static bodies */
     const int ctOnlyWords = a.cap_contacts * NCT * rowBodies; /* rows [slot][body][NCT]: 23 words apart across lanes, conflict-free */
-    const int pairWords = a.n_pairs > 0 ? a.pair_cap * (int)TGB_NPR : 0; /* rows between two bodies, behind the contact rows */
+    const int pairWords = (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap * (int)TGB_NPR : 0; /* rows between two bodies, behind the contact rows */
     const int ctWords = ctOnlyWords + pairWords;
     /* the contact rows (live from contact generation to the end of the solver) and the cable impulses (live from the cable
        phase to the impulse gather) share one region: shared memory per environment decides how many CTAs an SM holds */
     const int exchangeWords = TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords;
-    int groupTWords = a.stride + poseWords + exchangeWords;
+    /* body pairs: per pair the slack left before it has to be tested again, per body the motion bound of the last step (tgb_pairs.cuh) */
+    const int pairKeepWords = a.n_pairs > 0 ? a.n_pairs + LPE : 0;
+    int groupTWords = a.stride + poseWords + exchangeWords + pairKeepWords;
     groupTWords = (groupTWords + 3) & ~3;
     /* keep group regions LPE banks apart so that the groups of one warp do not collide */
     if (LPE < 32) { while ((groupTWords & 31) != (LPE < 4 ? 4 : LPE)) groupTWords += 4; }
@@ -601,6 +603,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     T* sJ = sPose + poseWords;                 /* [C][3] */
     T* sCt = TGB_EXCHANGE_UNION ? sJ : sJ + jWords; /* [cap][R][TGB_NCT], same region */
     T* sPairRows = sCt + ctOnlyWords;               /* [pair_cap][TGB_NPR] */
+    T* sPairSlack = sJ + exchangeWords;             /* [n_pairs], then [LPE] motion bounds */
+    T* sMotion = sPairSlack + a.n_pairs;
     constexpr bool cpgOn = CLASS == TGB_CLASS_CPG;
     constexpr bool sineOn = CLASS == TGB_CLASS_SINE;
     constexpr bool simpleOn = CLASS == TGB_CLASS_SIMPLE;
@@ -757,6 +761,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         }
     };
     publishPose();
+    if (a.n_pairs > 0 && bodyWarp) {
+        /* every pair is tested on the first step of a launch */
+        for (int i = lane; i < a.n_pairs + LPE; i += LPE) sPairSlack[i] = T(0);
+    }
     if (WIDE) __syncthreads(); else __syncwarp();
     /* a frame tied to a static body never moves: static bodies then stay bit-exactly in place */
     const bool frameMoves = M.body(BF_INVMASS, a.frame_body) != T(0);
@@ -925,7 +933,11 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         /* ---- contact between bodies: detection from the published poses (tgb_pairs.cuh).  Every lane of the body warp takes part; the
            lanes of a group take the environment's body pairs round robin.  nPairRows stays 0 unless a pair is within the contact band. */
         int nPairRows = 0;
-        if (a.n_pairs > 0 && a.pair_cap > 0 && bodyWarp) {
+#ifdef TGB_STATS
+        const long long statP0 = clock64();
+        int statTests = 0, statEmits = 0;
+#endif
+        if (a.n_pairs > 0 && bodyWarp) {
             const unsigned groupMaskP = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
             const int* pairTable = sModelI + a.model_pair_off;
             for (int p0 = 0; p0 < a.n_pairs; p0 += LPE) {
@@ -935,18 +947,50 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 if (p < a.n_pairs) {
                     const int code = pairTable[p];
                     ia = code & 31; ib = code >> 5;
-                    near = pairNear<T>(M, sPose, ia, ib, pairClearance);
                 }
+                /* no point of either body has moved further than its published bound since the pair's distance was taken: the pair
+                   cannot be within the contact band before its slack is used up.  When a lane of the warp has to test its pair, the
+                   others test theirs as well -- the instructions are issued anyway, and their next test moves further away. */
+                T slack = T(1);
+                if (p < a.n_pairs) slack = sPairSlack[p] - (sMotion[ia] + sMotion[ib]);
+                if (__any_sync(fullMask, !(slack > T(0)))) {
+                    if (p < a.n_pairs) {
+#ifdef TGB_STATS
+                        ++statTests;
+#endif
+                        T dist;
+                        near = pairNear<T>(M, sPose, ia, ib, pairClearance, dist);
+                        slack = (dist - pairBreakingThreshold<T>() - T(4e-3)) * T(0.999);
+                    }
+                }
+                if (p < a.n_pairs) sPairSlack[p] = slack;
                 unsigned nearMask = __ballot_sync(fullMask, near) & groupMaskP;
+                if (a.pair_cap < 0) nearMask = 0u; /* tuning aid: detection only */
                 while (nearMask != 0u) { /* rare; group-uniform */
                     const int L = __ffs(nearMask) - 1;
                     nearMask &= nearMask - 1u;
                     int cnt = 0;
                     if (warpLane == L) cnt = emitPairRows<T>(M, sPose, ia, ib, sPairRows, nPairRows, a.pair_cap);
+#ifdef TGB_STATS
+                    ++statEmits;
+#endif
                     nPairRows += __shfl_sync(groupMaskP, cnt, L);
                 }
             }
         }
+#ifdef TGB_STATS
+        if (a.stats) {
+            /* [103] cycles of the pair detection, [58] pair tests (lane count), [59] emissions */
+            const long long statP1 = clock64();
+            int tests = statTests;
+            for (int off = 16; off > 0; off >>= 1) tests += __shfl_xor_sync(fullMask, tests, off);
+            if (warpLane == 0) {
+                atomicAdd(a.stats + 103, (unsigned long long)(statP1 - statP0));
+                atomicAdd(a.stats + 58, (unsigned long long)tests);
+                atomicAdd(a.stats + 59, (unsigned long long)statEmits);
+            }
+        }
+#endif
         if (dynamic) {
             /* applyGravity + solver-body external impulses */
             V3<T> totalForce(T(0), gfy, T(0)), totalTorque(T(0), T(0), T(0));
@@ -1243,16 +1287,60 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         } /* dynamic: external impulses and the rows against the static world */
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
-            if (nPairRows > 0) {
-                /* group-uniform: this environment has rows between two bodies; all its lanes solve together (tgb_pairs.cuh) */
+            bool solved = false;
+            if (a.n_pairs > 0 && bodyWarp && __any_sync(fullMask, nPairRows > 0)) {
+                /* warp-uniform: environments of this warp have rows between two bodies.  Their lanes solve together (tgb_pairs.cuh);
+                   the other environments keep their per-lane solvers below. */
                 const unsigned groupMaskP = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
-                __syncwarp(groupMaskP); /* the pair rows and every body's own rows are in shared memory */
                 const bool mine = dynamic;
-                const M3<T> IinvP = b.Iinv;
-                const ContactSolveOut<T> o = solveCoupled<T, kFast, OBST>(
-                    sCt + rowIdx * NCT, rowBodies * NCT, mine ? nc : 0, mine && anyPen, gn, mu, sPairRows, nPairRows, lane, groupLane0, groupMaskP, b.x,
-                    IinvP, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt, a.iterations);
-                dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
+                const int ncMine = mine ? nc : 0;
+                const bool coupled = nPairRows > 0; /* uniform within the environment's group */
+                /* which solver: decided by the environment's own rows only */
+                const bool own2 = (__ballot_sync(fullMask, ncMine > 1) & groupMaskP) != 0u;
+                const bool own3 = (__ballot_sync(fullMask, ncMine > 2) & groupMaskP) != 0u;
+                const bool inReg1 = coupled && !own2 && nPairRows <= 1;
+                const bool inReg2 = coupled && !inReg1 && !own3 && nPairRows <= TGB_PAIR_REG_ROWS;
+                const unsigned coupledMask = __ballot_sync(fullMask, coupled);
+                const unsigned reg1Mask = __ballot_sync(fullMask, inReg1), reg2Mask = __ballot_sync(fullMask, inReg2);
+                const unsigned memMask = coupledMask & ~(reg1Mask | reg2Mask);
+                __syncwarp(); /* the pair rows and every body's own rows are in shared memory */
+#ifdef TGB_STATS
+                const long long statS0 = clock64();
+#endif
+                if (coupled) {
+                    ContactSolveOut<T> o;
+                    if (inReg1) {
+                        o = solveCoupledReg<T, kFast, OBST, 1, 1>(reg1Mask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine, mine && anyPen, gn, mu,
+                                                                  sPairRows, nPairRows, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0),
+                                                                  kFast ? b.v : linvel, b.w, extLin, extAng, dt, a.iterations);
+                    } else if (inReg2) {
+                        o = solveCoupledReg<T, kFast, OBST, 2, TGB_PAIR_REG_ROWS>(reg2Mask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine,
+                                                                                  mine && anyPen, gn, mu, sPairRows, nPairRows, lane, groupLane0, b.x,
+                                                                                  b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin,
+                                                                                  extAng, dt, a.iterations);
+                    } else {
+                        setupPairRows<T, kFast>(memMask, sPairRows, nPairRows, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0),
+                                                kFast ? b.v : linvel, b.w, extLin, extAng, dt);
+                        o = solveCoupledMem<T, kFast, OBST>(memMask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine, mine && anyPen, gn, mu,
+                                                            sPairRows, nPairRows, lane, groupLane0, b.Iinv, mine ? invMass : T(0), a.iterations);
+                    }
+                    dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
+                    solved = true;
+                }
+#ifdef TGB_STATS
+                __syncwarp();
+                if (a.stats && warpLane == 0) {
+                    /* [55] warp-steps with a coupled environment, [56] of which with one in the shared-memory solver, [57] coupled
+                       environments summed over warp-steps, [104] cycles of the coupled solve */
+                    atomicAdd(a.stats + 55, 1ULL);
+                    if (memMask) atomicAdd(a.stats + 56, 1ULL);
+                    atomicAdd(a.stats + 57, (unsigned long long)(__popc(coupledMask) / LPE));
+                    atomicAdd(a.stats + 104, (unsigned long long)(clock64() - statS0));
+                }
+#endif
+            }
+            if (solved) {
+                /* done above */
             } else if (!dynamic) {
                 /* nothing to solve */
             } else if (kFast && TGB_SINGLE_CONTACT_PGS && nc == 1) {
@@ -1310,6 +1398,13 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 integrateTransform(b.x, b.q, b.v, b.w, dt);
                 b.B = M3<T>::fromQuat(b.q);
                 b.Iinv = b.B.conjugateDiag(invI);
+                if (a.n_pairs > 0) {
+                    /* how far a point of this body's shapes can have moved in this step, relative to the env frame: translation by
+                       (v + push) dt, rotation by at most (|w| + turnErp |turn|) dt about the body origin (1-norms of the rare split-impulse terms: upper bounds) */
+                    const T lin1 = tsqrtNoBranch(b.v.length2()) + (tabs(push.x) + tabs(push.y) + tabs(push.z));
+                    const T ang1 = tsqrtNoBranch(b.w.length2()) + SolverConst<T>::turnErp() * (tabs(turn.x) + tabs(turn.y) + tabs(turn.z));
+                    sMotion[lane] = (lin1 + M.body(BF_BOUND, bidx) * ang1) * (dt * T(1.001));
+                }
             }
         } /* doWorld */
 
@@ -1795,8 +1890,8 @@ inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, 
     const int groupsPerBlock = a.wide ? 32 / lpe : threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
     const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C;
-    const int ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST * a.n_dyn : (int)TGB_NCT * a.R) + (a.n_pairs > 0 ? a.pair_cap * (int)TGB_NPR : 0);
-    int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords);
+    const int ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST * a.n_dyn : (int)TGB_NCT * a.R) + ((a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap * (int)TGB_NPR : 0);
+    int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords) + (a.n_pairs > 0 ? a.n_pairs + lpe : 0);
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
     const int groupDWords = tgb_group_double_words(a);

@@ -4,4 +4,10 @@ for line in open(sys.argv[1]):
         v=[int(x) for x in line.split()[1:]]
         ws=v[50]
         print('warp-steps %d body %.0f cable %.0f gather %.0f cycles/warp-step; total/warp %.0f'%(ws, v[100]/ws, v[101]/ws, v[102]/ws, v[51]/max(1,v[54])/1000))
+        print('  per-warp cycles/step: mean %.0f  slowest %.0f  fastest %.0f' % (v[51]/max(1,v[54])/1000, v[52]/1000, v[53]/1000))
+        print('  pair detection %.0f cycles/warp-step, %.2f pair tests/warp-step, %.3f emissions/warp-step' % (v[103]/ws, v[58]/ws, v[59]/ws))
+        cs = max(1, v[55])
+        print('  coupled warp-steps %.1f%% (%.1f%% of them with the shared-memory solver), %.2f coupled envs per coupled warp-step, %.0f cycles per coupled solve'
+              % (100.0*v[55]/ws, 100.0*v[56]/cs, v[57]/cs, v[104]/cs))
+        print('  contact-count histogram (max nc of a lane per warp-step):', [round(100.0*x/ws,1) for x in v[0:9]])
     elif line.startswith('episodes'): print(line.strip())
