@@ -425,8 +425,9 @@ tgb_status tgb_create(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, t
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
     if (e != cudaSuccess) { w->release(); delete w; return cudaFail(e, "tgb_create: stream/event creation"); }
     if (std::getenv("TGB_STATS")) {
-        if (cudaMalloc(&w->d_stats, 128 * sizeof(unsigned long long)) == cudaSuccess) {
-            cudaMemset(w->d_stats, 0, 128 * sizeof(unsigned long long));
+        /* 128 global counters, then 8 per CTA (first warp) for up to 4096 CTAs: see the TGB_STATS blocks of tgb_step.cuh */
+        if (cudaMalloc(&w->d_stats, (128 + 8 * 4096) * sizeof(unsigned long long)) == cudaSuccess) {
+            cudaMemset(w->d_stats, 0, (128 + 8 * 4096) * sizeof(unsigned long long));
             cudaMemset(w->d_stats + 53, 0xff, sizeof(unsigned long long));
         }
     }
@@ -439,11 +440,18 @@ tgb_status tgb_destroy(tgb_world* w) {
     cudaSetDevice(w->cfg.device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     if (w->d_stats) {
-        unsigned long long h[128];
-        if (cudaMemcpy(h, w->d_stats, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        std::vector<unsigned long long> h(128 + 8 * 4096);
+        if (cudaMemcpy(h.data(), w->d_stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
             std::fprintf(stderr, "TGB_STATS");
             for (int i = 0; i < 128; ++i) std::fprintf(stderr, " %llu", h[i]);
             std::fprintf(stderr, "\n");
+            /* per CTA: total cycles, coupled warp-steps, cycles in the coupled solve, cycles in the pair detection, warp-steps with the
+               shared-memory solver, warp-steps with a lane of three or more contact points, cycles in the cable phase, spare */
+            for (int c = 0; c < 4096; ++c) {
+                const unsigned long long* r = h.data() + 128 + 8 * c;
+                if (r[0] == 0) continue;
+                std::fprintf(stderr, "TGB_CTA %d %llu %llu %llu %llu %llu %llu %llu %llu\n", c, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+            }
         }
         cudaFree(w->d_stats);
     }

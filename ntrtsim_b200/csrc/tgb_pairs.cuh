@@ -30,6 +30,13 @@
 
 namespace tgb {
 
+#ifdef TGB_STATS
+/* instrumentation builds: per-section cycles of solveCoupledReg, added to stats[105..] by the first lane of the mask */
+#define TGB_PAIR_TICK(slot) do { if (statsP && warpLane == 0) { const long long now_ = clock64(); atomicAdd(statsP + (slot), (unsigned long long)(now_ - tick_)); tick_ = now_; } } while (0)
+#else
+#define TGB_PAIR_TICK(slot) do { } while (0)
+#endif
+
 template <typename T> struct ContactSolveOut { V3<T> dLin, dAng, push, turn; };
 
 template <typename T> TGB_D T pairBreakingThreshold() { return T(0.02); }
@@ -137,76 +144,69 @@ TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance
     return near;
 }
 
-/* Emission (rare): the contacts of bodies (ia, ib) as rows base, base + 1, ... of the environment's pair rows; returns the number
-   written.  Mirrors the oracle's generateBodyPairContacts expression by expression. */
+/* The contacts of one pair of capsules (bodies ia < ib) as rows base + count, ... of the environment's pair rows; `count` counts the rows
+   of this pair of bodies (at most 4).  Mirrors the oracle's generateBodyPairContacts expression by expression. */
+template <typename T>
+TGB_D void emitCapsulePair(const CoreSegment<T>& ga, const CoreSegment<T>& gb, int ia, int ib, T mu, T restitution, T* rows, int base, int cap,
+                           int& count) {
+    T s0, t0, b, c, f;
+    closestSegmentParams<T>(ga, gb, s0, t0, b, c, f);
+    T sp[2] = {s0, s0}, tp[2] = {t0, t0};
+    int np = 1;
+    if (ga.h > T(0) && gb.h > T(0) && T(1) - b * b < pairParallel<T>()) {
+        /* B's end points in A's axis parameter: s(t) = t b - c */
+        const T e0 = -gb.h * b - c, e1 = gb.h * b - c;
+        const T emin = e0 < e1 ? e0 : e1, emax = e0 < e1 ? e1 : e0;
+        const T lo = -ga.h > emin ? -ga.h : emin, hi = ga.h < emax ? ga.h : emax;
+        if (hi - lo > T(1e-9)) {
+            np = 2;
+            sp[0] = lo; tp[0] = clampT(b * lo + f, -gb.h, gb.h);
+            sp[1] = hi; tp[1] = clampT(b * hi + f, -gb.h, gb.h);
+        }
+    }
+    for (int k = 0; k < np; ++k) {
+        const V3<T> ca = ga.p + ga.d * sp[k], cb = gb.p + gb.d * tp[k];
+        const V3<T> dv = ca - cb;
+        const T d = tsqrt(dv.length2());
+        const T dist = d - ga.r - gb.r;
+        if (dist > pairBreakingThreshold<T>()) continue;
+        if (count >= 4 || base + count >= cap) continue;
+        V3<T> n;
+        if (d > T(1e-9)) n = dv * trcp(d); /* double: 1 / d, the oracle's */
+        else {
+            /* the axes meet: any direction perpendicular to both */
+            const V3<T> x = ga.d.cross(gb.d);
+            const T xl = x.length();
+            if (xl > T(1e-9)) n = x * (T(1) / xl);
+            else {
+                /* btPlaneSpace1 of A's axis */
+                const V3<T> a = ga.d;
+                if (tabs(a.z) > T(0.7071067811865475244008443621048490)) {
+                    const T kk = T(1) / tsqrt(a.y * a.y + a.z * a.z);
+                    n = V3<T>(T(0), -a.z * kk, a.y * kk);
+                } else {
+                    const T kk = T(1) / tsqrt(a.x * a.x + a.y * a.y);
+                    n = V3<T>(-a.y * kk, a.x * kk, T(0));
+                }
+            }
+        }
+        const V3<T> pA = ca - n * ga.r, pB = cb + n * gb.r; /* the contact points on the two surfaces */
+        T* row = rows + (base + count) * TGB_NPR;
+        row[PR_N + 0] = n.x; row[PR_N + 1] = n.y; row[PR_N + 2] = n.z;
+        row[PR_RA + 0] = pA.x; row[PR_RA + 1] = pA.y; row[PR_RA + 2] = pA.z;
+        row[PR_RB + 0] = pB.x; row[PR_RB + 1] = pB.y; row[PR_RB + 2] = pB.z;
+        row[PR_LAMN] = dist; row[PR_LAMPUSH] = restitution;
+        row[PR_MU] = mu; row[PR_IDS] = (T)(ia + 32 * ib);
+        ++count;
+    }
+}
+
+/* Emission for bodies made of several shapes (compound bodies); out of line. */
 template <typename T, typename Model>
-__device__ __noinline__ int emitPairRows(const Model M, const T* sPose, int ia, int ib, T* rows, int base, int cap) {
+__device__ __noinline__ int emitCompoundPairRows(const Model M, const T* sPose, int ia, int ib, T mu, T restitution, T* rows, int base, int cap) {
     const T* pa = sPose + 12 * ia;
     const T* pb = sPose + 12 * ib;
     int count = 0;
-    T mu = M.body(BF_FRICTION, ia) * M.body(BF_FRICTION, ib);
-    mu = mu < T(-10) ? T(-10) : (mu > T(10) ? T(10) : mu);
-    const T restitution = M.body(BF_RESTITUTION, ia) * M.body(BF_RESTITUTION, ib);
-    /* the contacts of one pair of capsules */
-    auto emitFor = [&](const CoreSegment<T>& ga, const CoreSegment<T>& gb) {
-        T s0, t0, b, c, f;
-        closestSegmentParams<T>(ga, gb, s0, t0, b, c, f);
-        T sp[2] = {s0, s0}, tp[2] = {t0, t0};
-        int np = 1;
-        if (ga.h > T(0) && gb.h > T(0) && T(1) - b * b < pairParallel<T>()) {
-            /* B's end points in A's axis parameter: s(t) = t b - c */
-            const T e0 = -gb.h * b - c, e1 = gb.h * b - c;
-            const T emin = e0 < e1 ? e0 : e1, emax = e0 < e1 ? e1 : e0;
-            const T lo = -ga.h > emin ? -ga.h : emin, hi = ga.h < emax ? ga.h : emax;
-            if (hi - lo > T(1e-9)) {
-                np = 2;
-                sp[0] = lo; tp[0] = clampT(b * lo + f, -gb.h, gb.h);
-                sp[1] = hi; tp[1] = clampT(b * hi + f, -gb.h, gb.h);
-            }
-        }
-        for (int k = 0; k < np; ++k) {
-            const V3<T> ca = ga.p + ga.d * sp[k], cb = gb.p + gb.d * tp[k];
-            const V3<T> dv = ca - cb;
-            const T d = tsqrt(dv.length2());
-            const T dist = d - ga.r - gb.r;
-            if (dist > pairBreakingThreshold<T>()) continue;
-            if (count >= 4 || base + count >= cap) continue;
-            V3<T> n;
-            if (d > T(1e-9)) n = dv * trcp(d); /* double: 1 / d, the oracle's */
-            else {
-                /* the axes meet: any direction perpendicular to both */
-                const V3<T> x = ga.d.cross(gb.d);
-                const T xl = x.length();
-                if (xl > T(1e-9)) n = x * (T(1) / xl);
-                else {
-                    /* btPlaneSpace1 of A's axis */
-                    const V3<T> a = ga.d;
-                    if (tabs(a.z) > T(0.7071067811865475244008443621048490)) {
-                        const T kk = T(1) / tsqrt(a.y * a.y + a.z * a.z);
-                        n = V3<T>(T(0), -a.z * kk, a.y * kk);
-                    } else {
-                        const T kk = T(1) / tsqrt(a.x * a.x + a.y * a.y);
-                        n = V3<T>(-a.y * kk, a.x * kk, T(0));
-                    }
-                }
-            }
-            const V3<T> pA = ca - n * ga.r, pB = cb + n * gb.r; /* the contact points on the two surfaces */
-            T* row = rows + (base + count) * TGB_NPR;
-            row[PR_N + 0] = n.x; row[PR_N + 1] = n.y; row[PR_N + 2] = n.z;
-            row[PR_RA + 0] = pA.x; row[PR_RA + 1] = pA.y; row[PR_RA + 2] = pA.z;
-            row[PR_RB + 0] = pB.x; row[PR_RB + 1] = pB.y; row[PR_RB + 2] = pB.z;
-            row[PR_LAMN] = dist; row[PR_LAMPUSH] = restitution;
-            row[PR_MU] = mu; row[PR_IDS] = (T)(ia + 32 * ib);
-            ++count;
-        }
-    };
-    if (M.body(BF_SEGH, ia) >= T(0) && M.body(BF_SEGH, ib) >= T(0)) {
-        CoreSegment<T> ga, gb;
-        coreSegmentOfRod<T>(M, pa, ia, ga);
-        coreSegmentOfRod<T>(M, pb, ib, gb);
-        emitFor(ga, gb);
-        return count;
-    }
     const int sa0 = M.bodyi(BI_SHAPE_BEGIN, ia), sa1 = sa0 + M.bodyi(BI_SHAPE_COUNT, ia);
     const int sb0 = M.bodyi(BI_SHAPE_BEGIN, ib), sb1 = sb0 + M.bodyi(BI_SHAPE_COUNT, ib);
     for (int sa = sa0; sa < sa1; ++sa) {
@@ -215,10 +215,28 @@ __device__ __noinline__ int emitPairRows(const Model M, const T* sPose, int ia, 
         for (int sb = sb0; sb < sb1; ++sb) {
             CoreSegment<T> gb;
             if (!coreSegment<T>(M, pb, sb, gb)) continue;
-            emitFor(ga, gb);
+            emitCapsulePair<T>(ga, gb, ia, ib, mu, restitution, rows, base, cap, count);
         }
     }
     return count;
+}
+
+/* Emission: the contacts of bodies (ia, ib) as rows base, base + 1, ... of the environment's pair rows; returns the number written.
+   Two plain rods / balls in line, compound bodies out of line. */
+template <typename T, typename Model>
+TGB_D int emitPairRows(const Model& M, const T* sPose, int ia, int ib, T* rows, int base, int cap) {
+    T mu = M.body(BF_FRICTION, ia) * M.body(BF_FRICTION, ib);
+    mu = mu < T(-10) ? T(-10) : (mu > T(10) ? T(10) : mu);
+    const T restitution = M.body(BF_RESTITUTION, ia) * M.body(BF_RESTITUTION, ib);
+    if (M.body(BF_SEGH, ia) >= T(0) && M.body(BF_SEGH, ib) >= T(0)) {
+        CoreSegment<T> ga, gb;
+        coreSegmentOfRod<T>(M, sPose + 12 * ia, ia, ga);
+        coreSegmentOfRod<T>(M, sPose + 12 * ib, ib, gb);
+        int count = 0;
+        emitCapsulePair<T>(ga, gb, ia, ib, mu, restitution, rows, base, cap, count);
+        return count;
+    }
+    return emitCompoundPairRows<T>(M, sPose, ia, ib, mu, restitution, rows, base, cap);
 }
 
 /* solveCoupledReg is compiled for (own contact points per lane, pair rows per environment) = (1, 1) -- a rod end on the ground, one
@@ -335,11 +353,21 @@ TGB_D bool groupHasPenetration(unsigned groupMask, bool anyPenOwn, const T* pr, 
    W_ij = J_i M^-1 J_j^T formed once -- the dependent chain of a row visit is 5 operations instead of ~12, and a pair row adds one
    shuffle (the two sides' parts of its relative velocity).  Equal to the velocity-space iteration in exact arithmetic. */
 template <typename T, bool kFast, bool OBST, int NC, int PM>
-__device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsigned groupMask, T* ct, int rowStride, int nc, bool anyPenOwn, V3<T> gn,
+__device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T* ct, int rowStride, int nc, bool anyPenOwn, V3<T> gn,
                                                             T muGround, const T* pr, int nPairRows, int lane, int groupLane0, V3<T> x, M3<T> Iinv,
-                                                            T invMass, V3<T> vel, V3<T> w, V3<T> extLin, V3<T> extAng, T dt, int iterations) {
+                                                            T invMass, V3<T> vel, V3<T> w, V3<T> extLin, V3<T> extAng, T dt, int iterations
+#ifdef TGB_STATS
+                                                            , unsigned long long* statsP
+#endif
+                                                            ) {
     constexpr int PMAX = PM;
+    /* All 32 lanes of the warp are here (lanes of environments that take another solver pass nc = 0, nPairRows = 0 and ignore the
+       result): with the constant full mask a shuffle is one instruction, without the convergence check a run-time mask costs. */
+    constexpr unsigned mask = 0xffffffffu;
     const int warpLane = groupLane0 + lane;
+#ifdef TGB_STATS
+    long long tick_ = clock64();
+#endif
     const int maxP = __reduce_max_sync(mask, nPairRows);
     /* ---- own rows (up to two contact points against the static world), as the step kernel set them up ---- */
     V3<T> on[NC], orxn[NC], oangN[NC], ot[NC], orxt[NC], oangT[NC];
@@ -357,6 +385,7 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsign
         oInvT[c] = TGB_CTG(cc, CT_INVDIAGT); oRhsT[c] = TGB_CTG(cc, CT_RHST);
         oMu[c] = OBST ? TGB_CTG(cc, CT_MU) : muGround;
     }
+    TGB_PAIR_TICK(105);
     /* ---- this lane's side of its environment's pair rows (setupContactConstraint / setupFrictionConstraint with two bodies):
        sign +1 (body A), -1 (body B) or 0 (not its row) ---- */
     V3<T> pn[PMAX], prxn[PMAX], pangN[PMAX], pt[PMAX], prxt[PMAX], pangT[PMAX];
@@ -384,7 +413,7 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsign
         const T vdn = n.dot(vel + extLin) + rxn.dot(w + extAng);
         T o_dN = dN, o_vdn = vdn;
         V3<T> o_vp = vp;
-        if (p < maxP) { /* uniform over the lanes of `mask` */
+        if (PM == 1 || p < maxP) { /* uniform over the lanes of `mask` */
             o_dN = __shfl_sync(mask, dN, src); o_vdn = __shfl_sync(mask, vdn, src);
             o_vp = V3<T>(__shfl_sync(mask, vp.x, src), __shfl_sync(mask, vp.y, src), __shfl_sync(mask, vp.z, src));
         }
@@ -423,7 +452,7 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsign
         const T dT = invMass + t.dot(angT.cross(r));
         const T rT = t.dot(vel + extLin) + rxt.dot(w);
         T o_dT = dT, o_rT = rT;
-        if (p < maxP) { o_dT = __shfl_sync(mask, dT, src); o_rT = __shfl_sync(mask, rT, src); }
+        if (PM == 1 || p < maxP) { o_dT = __shfl_sync(mask, dT, src); o_rT = __shfl_sync(mask, rT, src); }
         const T denomT = (isB ? o_dT : dT) + (isB ? dT : o_dT);
         const T relT = (isB ? o_rT : rT) - (isB ? rT : o_rT);
         const T invDiagT = kFast ? trcp(denomT) : T(1) / denomT;
@@ -435,6 +464,7 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsign
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) penHere = penHere || pRhsPen[p] != T(0);
     const bool anyPen = __any_sync(mask, penHere);
+    TGB_PAIR_TICK(106);
 
     V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
     if constexpr (kFast) {
@@ -474,89 +504,86 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsign
                 const T v = jl[i].dot(bl[j]) + ja[i].dot(ba[j]);
                 W[i][j] = v; W[j][i] = v;
             }
-        T lam[K], dv[K];
+        TGB_PAIR_TICK(107);
+        /* A row visit, written for the shortest dependent chain (dv -> fma -> max/min -> subtract -> fma into the next row's dv):
+           new impulse = clamp(lam + rhs - dv invD) with lam + rhs kept ready from the row's previous visit. */
+        T lam[K], dv[K], base[K];
 #pragma unroll
-        for (int i = 0; i < K; ++i) { lam[i] = T(0); dv[i] = T(0); }
+        for (int i = 0; i < K; ++i) { lam[i] = T(0); dv[i] = T(0); base[i] = rhs[i]; }
         if (anyPen) {
-            /* split impulse: the normal rows alone, their own impulses and relative velocities */
+            /* split impulse: the normal rows alone, their own impulses and relative velocities; a row without it has rhsP = 0 and stays 0 */
             T lamP[K], dvP[K];
 #pragma unroll
             for (int i = 0; i < K; ++i) { lamP[i] = T(0); dvP[i] = T(0); }
             for (int it = 0; it < iterations; ++it) {
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {
-                    T delta = rhsP[c] - dvP[c] * invD[c];
-                    const T sum = lamP[c] + delta;
-                    if (sum < T(0)) delta = -lamP[c];
-                    if (rhsP[c] == T(0)) delta = T(0);
-                    lamP[c] += delta;
+                    const T nl = rhsP[c] != T(0) ? fmaxf(fmaf(-dvP[c], invD[c], lamP[c] + rhsP[c]), T(0)) : T(0);
+                    const T delta = nl - lamP[c];
+                    lamP[c] = nl;
 #pragma unroll
-                    for (int i = 0; i < K; ++i) dvP[i] += W[i][c] * delta;
+                    for (int i = 0; i < K; ++i) dvP[i] = fmaf(W[i][c], delta, dvP[i]);
                 }
 #pragma unroll
                 for (int p = 0; p < PMAX; ++p)
-                    if (p < maxP) {
+                    if (PM == 1 || p < maxP) {
                         const int r_ = PN + p;
                         const T total = dvP[r_] + __shfl_sync(mask, dvP[r_], pSrc[p]);
-                        T delta = rhsP[r_] - total * invD[r_];
-                        const T sum = lamP[r_] + delta;
-                        if (sum < T(0)) delta = -lamP[r_];
-                        if (rhsP[r_] == T(0)) delta = T(0);
-                        lamP[r_] += delta;
+                        const T nl = rhsP[r_] != T(0) ? fmaxf(fmaf(-total, invD[r_], lamP[r_] + rhsP[r_]), T(0)) : T(0);
+                        const T delta = nl - lamP[r_];
+                        lamP[r_] = nl;
 #pragma unroll
-                        for (int i = 0; i < K; ++i) dvP[i] += W[i][r_] * delta;
+                        for (int i = 0; i < K; ++i) dvP[i] = fmaf(W[i][r_], delta, dvP[i]);
                     }
             }
 #pragma unroll
             for (int i = 0; i < K; ++i) { push += bl[i] * lamP[i]; turn += ba[i] * lamP[i]; }
         }
+        TGB_PAIR_TICK(108);
         for (int it = 0; it < iterations; ++it) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                T delta = rhs[c] - dv[c] * invD[c];
-                const T sum = lam[c] + delta;
-                if (sum < T(0)) delta = -lam[c];
-                lam[c] += delta;
+                const T nl = fmaxf(fmaf(-dv[c], invD[c], base[c]), T(0));
+                const T delta = nl - lam[c];
+                lam[c] = nl; base[c] = nl + rhs[c];
 #pragma unroll
-                for (int i = 0; i < K; ++i) dv[i] += W[i][c] * delta;
+                for (int i = 0; i < K; ++i) dv[i] = fmaf(W[i][c], delta, dv[i]);
             }
 #pragma unroll
             for (int p = 0; p < PMAX; ++p)
-                if (p < maxP) {
+                if (PM == 1 || p < maxP) {
                     const int r_ = PN + p;
                     const T total = dv[r_] + __shfl_sync(mask, dv[r_], pSrc[p]);
-                    T delta = rhs[r_] - total * invD[r_];
-                    const T sum = lam[r_] + delta;
-                    if (sum < T(0)) delta = -lam[r_];
-                    lam[r_] += delta;
+                    const T nl = fmaxf(fmaf(-total, invD[r_], base[r_]), T(0));
+                    const T delta = nl - lam[r_];
+                    lam[r_] = nl; base[r_] = nl + rhs[r_];
 #pragma unroll
-                    for (int i = 0; i < K; ++i) dv[i] += W[i][r_] * delta;
+                    for (int i = 0; i < K; ++i) dv[i] = fmaf(W[i][r_], delta, dv[i]);
                 }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const int r_ = NC + c;
                 const T hi = oMu[c] * lam[c];
-                T sum = lam[r_] + (rhs[r_] - dv[r_] * invD[r_]);
-                sum = sum < -hi ? -hi : (sum > hi ? hi : sum);
-                const T delta = lam[c] > T(0) ? sum - lam[r_] : T(0); /* skipped (impulse kept) while the normal impulse is zero */
-                lam[r_] += delta;
+                const T nl = fminf(fmaxf(fmaf(-dv[r_], invD[r_], base[r_]), -hi), hi);
+                const T delta = lam[c] > T(0) ? nl - lam[r_] : T(0); /* skipped (impulse kept) while the normal impulse is zero */
+                lam[r_] += delta; base[r_] = lam[r_] + rhs[r_];
 #pragma unroll
-                for (int i = 0; i < K; ++i) dv[i] += W[i][r_] * delta;
+                for (int i = 0; i < K; ++i) dv[i] = fmaf(W[i][r_], delta, dv[i]);
             }
 #pragma unroll
             for (int p = 0; p < PMAX; ++p)
-                if (p < maxP) {
+                if (PM == 1 || p < maxP) {
                     const int r_ = PT + p;
                     const T total = dv[r_] + __shfl_sync(mask, dv[r_], pSrc[p]);
                     const T hi = pMu[p] * lam[PN + p];
-                    T sum = lam[r_] + (rhs[r_] - total * invD[r_]);
-                    sum = sum < -hi ? -hi : (sum > hi ? hi : sum);
-                    const T delta = lam[PN + p] > T(0) ? sum - lam[r_] : T(0);
-                    lam[r_] += delta;
+                    const T nl = fminf(fmaxf(fmaf(-total, invD[r_], base[r_]), -hi), hi);
+                    const T delta = lam[PN + p] > T(0) ? nl - lam[r_] : T(0);
+                    lam[r_] += delta; base[r_] = lam[r_] + rhs[r_];
 #pragma unroll
-                    for (int i = 0; i < K; ++i) dv[i] += W[i][r_] * delta;
+                    for (int i = 0; i < K; ++i) dv[i] = fmaf(W[i][r_], delta, dv[i]);
                 }
         }
+        TGB_PAIR_TICK(109);
 #pragma unroll
         for (int i = 0; i < K; ++i) { dLin += bl[i] * lam[i]; dAng += ba[i] * lam[i]; }
     } else {
@@ -602,7 +629,7 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsign
                     if (c < nc && oRhsPen[c] != T(0)) ownNormal(c, oRhsPen[c], oLamPush[c], push, turn);
 #pragma unroll
                 for (int p = 0; p < PMAX; ++p)
-                    if (p < maxP) pairNormalReg(p, pRhsPen[p], pLamPush[p], push, turn, pRhsPen[p] != T(0));
+                    if (PM == 1 || p < maxP) pairNormalReg(p, pRhsPen[p], pLamPush[p], push, turn, pRhsPen[p] != T(0));
             }
         for (int it = 0; it < iterations; ++it) {
 #pragma unroll
@@ -610,7 +637,7 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsign
                 if (c < nc) ownNormal(c, oRhsN[c], oLamN[c], dLin, dAng);
 #pragma unroll
             for (int p = 0; p < PMAX; ++p)
-                if (p < maxP) pairNormalReg(p, pRhsN[p], pLamN[p], dLin, dAng, pSign[p] != T(0));
+                if (PM == 1 || p < maxP) pairNormalReg(p, pRhsN[p], pLamN[p], dLin, dAng, pSign[p] != T(0));
 #pragma unroll
             for (int c = 0; c < NC; ++c)
                 if (c < nc && oLamN[c] > T(0)) {
@@ -627,7 +654,7 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned mask, unsign
                 }
 #pragma unroll
             for (int p = 0; p < PMAX; ++p)
-                if (p < maxP) {
+                if (PM == 1 || p < maxP) {
                     const T dvOwn = pt[p].dot(dLin) + prxt[p].dot(dAng);
                     const T dvOther = __shfl_sync(mask, dvOwn, pSrc[p]);
                     const bool isB = pSign[p] < T(0);

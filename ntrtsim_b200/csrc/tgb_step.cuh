@@ -919,6 +919,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     T pairClearance = T(1e30); /* smallest surface distance of two bodies' capsules this lane has seen */
 #ifdef TGB_STATS
     const long long statT0 = clock64();
+    unsigned long long wCoupled = 0, wCoupledCyc = 0, wDetectCyc = 0, wMem = 0, wMany = 0, wCableCyc = 0;
 #endif
     for (int step = 0; step < a.n_steps; ++step) {
 #ifdef TGB_STATS
@@ -984,6 +985,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             const long long statP1 = clock64();
             int tests = statTests;
             for (int off = 16; off > 0; off >>= 1) tests += __shfl_xor_sync(fullMask, tests, off);
+            wDetectCyc += (unsigned long long)(statP1 - statP0);
             if (warpLane == 0) {
                 atomicAdd(a.stats + 103, (unsigned long long)(statP1 - statP0));
                 atomicAdd(a.stats + 58, (unsigned long long)tests);
@@ -1307,28 +1309,44 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 #ifdef TGB_STATS
                 const long long statS0 = clock64();
 #endif
+                /* The register solvers are entered by the whole warp (full-mask shuffles); lanes of environments that are not theirs
+                   come along with no rows and drop the result. */
+                ContactSolveOut<T> o;
+                if (reg1Mask != 0u) {
+                    const ContactSolveOut<T> o1 = solveCoupledReg<T, kFast, OBST, 1, 1>(
+                        groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, inReg1 ? ncMine : 0, inReg1 && mine && anyPen, gn, mu, sPairRows,
+                        inReg1 ? nPairRows : 0, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt,
+                        a.iterations
+#ifdef TGB_STATS
+                        , a.stats
+#endif
+                        );
+                    if (inReg1) o = o1;
+                }
+                if (reg2Mask != 0u) {
+                    const ContactSolveOut<T> o2 = solveCoupledReg<T, kFast, OBST, 2, TGB_PAIR_REG_ROWS>(
+                        groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, inReg2 ? ncMine : 0, inReg2 && mine && anyPen, gn, mu, sPairRows,
+                        inReg2 ? nPairRows : 0, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt,
+                        a.iterations
+#ifdef TGB_STATS
+                        , a.stats
+#endif
+                        );
+                    if (inReg2) o = o2;
+                }
+                if (coupled && !inReg1 && !inReg2) {
+                    setupPairRows<T, kFast>(memMask, sPairRows, nPairRows, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0),
+                                            kFast ? b.v : linvel, b.w, extLin, extAng, dt);
+                    o = solveCoupledMem<T, kFast, OBST>(memMask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine, mine && anyPen, gn, mu,
+                                                        sPairRows, nPairRows, lane, groupLane0, b.Iinv, mine ? invMass : T(0), a.iterations);
+                }
                 if (coupled) {
-                    ContactSolveOut<T> o;
-                    if (inReg1) {
-                        o = solveCoupledReg<T, kFast, OBST, 1, 1>(reg1Mask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine, mine && anyPen, gn, mu,
-                                                                  sPairRows, nPairRows, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0),
-                                                                  kFast ? b.v : linvel, b.w, extLin, extAng, dt, a.iterations);
-                    } else if (inReg2) {
-                        o = solveCoupledReg<T, kFast, OBST, 2, TGB_PAIR_REG_ROWS>(reg2Mask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine,
-                                                                                  mine && anyPen, gn, mu, sPairRows, nPairRows, lane, groupLane0, b.x,
-                                                                                  b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin,
-                                                                                  extAng, dt, a.iterations);
-                    } else {
-                        setupPairRows<T, kFast>(memMask, sPairRows, nPairRows, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0),
-                                                kFast ? b.v : linvel, b.w, extLin, extAng, dt);
-                        o = solveCoupledMem<T, kFast, OBST>(memMask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine, mine && anyPen, gn, mu,
-                                                            sPairRows, nPairRows, lane, groupLane0, b.Iinv, mine ? invMass : T(0), a.iterations);
-                    }
                     dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
                     solved = true;
                 }
 #ifdef TGB_STATS
                 __syncwarp();
+                wCoupled += 1; wCoupledCyc += (unsigned long long)(clock64() - statS0); wMem += memMask ? 1 : 0;
                 if (a.stats && warpLane == 0) {
                     /* [55] warp-steps with a coupled environment, [56] of which with one in the shared-memory solver, [57] coupled
                        environments summed over warp-steps, [104] cycles of the coupled solve */
@@ -1336,6 +1354,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     if (memMask) atomicAdd(a.stats + 56, 1ULL);
                     atomicAdd(a.stats + 57, (unsigned long long)(__popc(coupledMask) / LPE));
                     atomicAdd(a.stats + 104, (unsigned long long)(clock64() - statS0));
+                    atomicAdd(a.stats + 110, (unsigned long long)(statS0 - statA)); /* body phase before the coupled solve, coupled warp-steps only */
                 }
 #endif
             }
@@ -1429,6 +1448,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(fullMask, mx, off));
             const int touching = __popc(__ballot_sync(fullMask, statNc > 0));
             const bool pen = __any_sync(fullMask, statPen);
+            wMany += mx >= 3 ? 1 : 0;
             if (warpLane == 0) {
                 atomicAdd(a.stats + min(mx, 8), 1ULL);
                 atomicAdd(a.stats + 16 + touching, 1ULL);
@@ -1804,6 +1824,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             /* cycles of this warp in the body phase, the cable phase and the gather */
             atomicAdd(a.stats + 100, (unsigned long long)(statB - statA));
             atomicAdd(a.stats + 101, (unsigned long long)(statC - statB));
+            wCableCyc += (unsigned long long)(statC - statB);
             atomicAdd(a.stats + 102, (unsigned long long)(clock64() - statC));
         }
 #endif
@@ -1816,6 +1837,11 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         atomicAdd(a.stats + 51, cyc); atomicMax(a.stats + 52, cyc); atomicMin(a.stats + 53, cyc); atomicAdd(a.stats + 54, 1ULL);
         const int bucket = (int)min(31ULL, cyc * 16ULL / (unsigned long long)(a.n_steps * 14000LL)); /* cycles per step / 14000 * 16 */
         atomicAdd(a.stats + 64 + bucket, 1ULL);
+        if (blockIdx.x < 4096 && tid < 32) {
+            unsigned long long* r = a.stats + 128 + 8 * blockIdx.x;
+            atomicAdd(r + 0, cyc); atomicAdd(r + 1, wCoupled); atomicAdd(r + 2, wCoupledCyc); atomicAdd(r + 3, wDetectCyc);
+            atomicAdd(r + 4, wMem); atomicAdd(r + 5, wMany); atomicAdd(r + 6, wCableCyc);
+        }
     }
 #endif
     /* ---- store: bodies back into the record, record back to HBM, frame, status ---------------------------- */

@@ -1,5 +1,18 @@
 import sys,re
+ctas = []
+def flush_ctas():
+    global ctas
+    if not ctas: return
+    ctas.sort(key=lambda r: -r[1])
+    tot = sorted(r[1] for r in ctas)
+    print('  per-CTA total cycles: median %.3g, p90 %.3g, p99 %.3g, max %.3g' % (tot[len(tot)//2], tot[int(len(tot)*0.9)], tot[int(len(tot)*0.99)], tot[-1]))
+    print('  slowest CTAs: id total | coupled steps, coupled-solve cycles, detection cycles, mem-solver steps, steps with >=3 contacts, cable cycles')
+    for r in ctas[:8]: print('   ', r)
+    ctas = []
 for line in open(sys.argv[1]):
+    if line.startswith('TGB_CTA'):
+        ctas.append([int(x) for x in line.split()[1:]]); continue
+    if line.startswith('episodes'): flush_ctas()
     if line.startswith('TGB_STATS'):
         v=[int(x) for x in line.split()[1:]]
         ws=v[50]
@@ -9,5 +22,9 @@ for line in open(sys.argv[1]):
         cs = max(1, v[55])
         print('  coupled warp-steps %.1f%% (%.1f%% of them with the shared-memory solver), %.2f coupled envs per coupled warp-step, %.0f cycles per coupled solve'
               % (100.0*v[55]/ws, 100.0*v[56]/cs, v[57]/cs, v[104]/cs))
+        print('  coupled solve sections (cycles per coupled solve): own rows %.0f, pair set-up %.0f, W %.0f, split impulse %.0f, iterations %.0f; body phase before it %.0f'
+              % (v[105]/cs, v[106]/cs, v[107]/cs, v[108]/cs, v[109]/cs, v[110]/cs))
         print('  contact-count histogram (max nc of a lane per warp-step):', [round(100.0*x/ws,1) for x in v[0:9]])
     elif line.startswith('episodes'): print(line.strip())
+
+flush_ctas()
