@@ -331,68 +331,74 @@ def main():
         return e0.elapsed_time(e1)
 
     # ---- warm-up ---------------------------------------------------------------------------------------------
+    flush_l2()  # the first use of torch's fill kernel loads it (~20 ms on the host): not inside the timed bracket
     for _ in range(args.warmup):
         w.step_timed(model.dt, H, 1)
         if dist is not None:
             gather_scores()
 
     # ---- timed region: device-resident state ---------------------------------------------------------------------
+    # The same method at every N: ONE CUDA-event bracket on the world's stream around the K steps, L2 flushes included; the host
+    # queues everything and never blocks inside it.  Stream order per step k: [torch stream] wait for step k-1, flush L2;
+    # [world stream] wait for the flush, H sim steps (events around the launch give the kernel's own duration), and for N > 1:
+    # wait for all-gather k-1 (its source buffer is about to be rewritten), refresh the score buffer; [collective stream] wait
+    # for the refresh, all-gather k.  The all-gather of step k thus overlaps step k+1, ranks only have to stay within one step of
+    # each other, and every collective completes before the bracket closes.
     launches0 = w.launch_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     t_wall0 = time.perf_counter()
-    ms_kernel, ms_gather = [], []
-    if dist is None:
-        for _ in range(args.steps):
-            flush_l2()
-            ms_kernel.append(w.step_timed(model.dt, H, 1)[0])
-        total_ms = sum(ms_kernel)
-    else:
-        # N > 1: one device-side bracket around the K steps (L2 flushes included); the host queues everything and never blocks
-        # inside it.  Stream order per step k: [torch stream] wait for step k-1, flush L2; [world stream] wait for the flush,
-        # H steps, wait for all-gather k-1 (its source buffer is about to be rewritten), refresh the score buffer;
-        # [collective stream] wait for the refresh, all-gather k.  The all-gather of step k thus overlaps step k+1 and ranks
-        # only have to stay within one step of each other; every collective completes before the bracket closes.
-        ws = torch.cuda.ExternalStream(w.stream_handle())
-        cs = torch.cuda.Stream()
-        cur = torch.cuda.current_stream()
-        ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-        gather_done, step_done, keep = None, None, []
-        ev_start.record(ws)
-        for k in range(args.steps):
-            if step_done is not None:
-                cur.wait_event(step_done)
-            flush.fill_(rank & 0xff)
-            fl = torch.cuda.Event()
-            fl.record(cur)
-            ws.wait_event(fl)
-            ev_k0[k].record(ws)
-            w.step(model.dt, H)                       # asynchronous on the world's stream
-            ev_k1[k].record(ws)
-            if gather_done is not None:
-                ws.wait_event(gather_done)
-            ptr, nbytes = w.scores_refresh_async()    # scores of step k, queued on the world's stream
+    ws = torch.cuda.ExternalStream(w.stream_handle())
+    cs = torch.cuda.Stream() if dist is not None else None
+    cur = torch.cuda.current_stream()
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_g0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_g1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    gather_done, step_done, keep = None, None, []
+    ev_start.record(ws)
+    for k in range(args.steps):
+        if step_done is not None:
+            cur.wait_event(step_done)
+        flush.fill_(rank & 0xff)
+        fl = torch.cuda.Event()
+        fl.record(cur)
+        ws.wait_event(fl)
+        ev_k0[k].record(ws)
+        w.step(model.dt, H)                       # asynchronous on the world's stream
+        ev_k1[k].record(ws)
+        if dist is None:
             step_done = torch.cuda.Event()
             step_done.record(ws)
+            keep.append(fl)
+            continue
+        if gather_done is not None:
+            ws.wait_event(gather_done)
+        ptr, nbytes = w.scores_refresh_async()    # scores of step k, queued on the world's stream
+        step_done = torch.cuda.Event()
+        step_done.record(ws)
 
-            class _Wrap(object):
-                __cuda_array_interface__ = {"shape": (n_env * 2,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-            with torch.cuda.stream(cs):
-                cs.wait_event(step_done)
-                local = torch.as_tensor(_Wrap(), device="cuda")
-                work = dist.all_gather_into_tensor(scores_all, local, async_op=True)
-                work.wait()                           # orders the collective stream after NCCL's; does not block the host
-                gather_done = torch.cuda.Event()
-                gather_done.record(cs)
-            keep.append((local, work, fl))
+        class _Wrap(object):
+            __cuda_array_interface__ = {"shape": (n_env * 2,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        with torch.cuda.stream(cs):
+            cs.wait_event(step_done)
+            local = torch.as_tensor(_Wrap(), device="cuda")
+            ev_g0[k].record(cs)
+            work = dist.all_gather_into_tensor(scores_all, local, async_op=True)
+            work.wait()                           # orders the collective stream after NCCL's; does not block the host
+            ev_g1[k].record(cs)
+            gather_done = torch.cuda.Event()
+            gather_done.record(cs)
+        keep.append((local, work, fl))
+    if gather_done is not None:
         ws.wait_event(gather_done)
-        ev_end.record(ws)
-        ev_end.synchronize()
-        torch.cuda.synchronize()
-        ms_kernel = [a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)]
-        total_ms = ev_start.elapsed_time(ev_end)
+    ev_end.record(ws)
+    ev_end.synchronize()
+    torch.cuda.synchronize()
+    ms_kernel = [a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)]
+    ms_gather = [a.elapsed_time(b) for a, b in zip(ev_g0, ev_g1)] if dist is not None else []
+    total_ms = ev_start.elapsed_time(ev_end)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
@@ -444,8 +450,16 @@ def main():
     e2e_total = sum(e2e_s)
     e2e_checksum = float(np.abs(cab_out[..., 2]).mean())
 
-    # max over ranks
+    # max over ranks; the per-rank kernel durations travel too, so that the line names what limits the scaling
+    per_rank_kernel = [ms_kernel]
+    per_rank_total = [total_ms]
     if dist is not None:
+        mine = torch.tensor(ms_kernel + [total_ms, float(np.mean(ms_gather))], dtype=torch.float64, device="cuda")
+        everyone = [torch.empty_like(mine) for _ in range(world_size)]
+        dist.all_gather(everyone, mine)
+        per_rank_kernel = [[float(x) for x in t[:args.steps]] for t in everyone]
+        per_rank_total = [float(t[args.steps]) for t in everyone]
+        per_rank_gather = [float(t[args.steps + 1]) for t in everyone]
         t = torch.tensor([total_ms, e2e_total, float(launches), float(status_bad)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_total = float(t[0]), float(t[1])
@@ -475,9 +489,16 @@ def main():
                          "peak_source": peak_src,
                          "note": "effective figure: env state stays on chip for the H fused steps, real DRAM traffic is ~1/H of it"},
         }
+        line["config"]["timing"] = "one CUDA-event bracket on the world's stream around the K steps incl. the L2 flushes, same at every N; max over ranks"
+        allk = np.array(per_rank_kernel)
+        line["per_rank_kernel_ms"] = {"min": float(allk.min()), "median": float(np.median(allk)), "max": float(allk.max()),
+                                      "mean_by_rank": [float(x) for x in allk.mean(axis=1)],
+                                      "sum_of_step_max_over_ranks": float(allk.max(axis=0).sum()),
+                                      "bracket_ms_by_rank": per_rank_total}
         if world_size > 1:
             line["config"]["allgather"] = "scores all-gather of step k issued asynchronously, overlapping step k+1, completed inside the timed bracket"
-            line["config"]["timing"] = "one CUDA-event bracket around the K steps incl. the L2 flushes; max over ranks"
+            line["allgather_ms"] = {"mean_by_rank": per_rank_gather, "bytes_per_rank": int(n_env * 2 * 4),
+                                    "note": "device time of the collective on its own stream; overlaps the next step's kernel"}
         if world_size == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             # calibrate, then size the sample (whole batch, H x reps sim steps) for ~10-15 s of CPU work
