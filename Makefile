@@ -32,7 +32,7 @@ $(LIBDIR)/libntrtsim_b200.so: $(BUILD)/tgb_step_f32.o $(BUILD)/tgb_step_f64.o $(
 
 HOST_SRCS := $(HOST)/tgb_host.cpp $(HOST)/tgb_creator.cpp $(HOST)/tgb_sensors.cpp $(HOST)/tgb_yaml.cpp $(HOST)/tgb_examples.cpp $(HOST)/tgb_host_capi.cpp
 $(LIBDIR)/libtgb_host.so: $(HOST_SRCS) $(HOST_HDRS) $(LIBDIR)/libntrtsim_b200.so | $(LIBDIR)
-	$(CXX) -std=c++17 -O2 -fPIC -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lntrtsim_b200 -Wl,-rpath,'$$ORIGIN'
+	$(CXX) -std=c++17 -O2 -fPIC -shared -o $@ $(HOST_SRCS) -L$(LIBDIR) -lntrtsim_b200 -ldl -Wl,-rpath,'$$ORIGIN'
 
 # test infrastructure, never linked into the libraries above
 oracle/liboracle.so: oracle/tg_oracle.cpp oracle/tg_oracle.h include/ntrtsim_b200.h

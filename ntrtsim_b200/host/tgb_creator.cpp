@@ -5,6 +5,9 @@
  */
 #include "tgb_creator.h"
 
+#include <cstdlib>
+#include <ctime>
+
 #include <algorithm>
 #include <cmath>
 #include <sstream>
@@ -798,4 +801,19 @@ void tgStructureInfo::buildInto(tgModel& model, tgWorld& world) {
     initRigidBodies(impl);
     initConnectors(impl);
     buildIntoHelper(model, impl, *this);
+}
+
+/* tgUtil.cpp:54-62 */
+void tgUtil::seedRandom() { srand((unsigned)time(0)); }
+void tgUtil::seedRandom(int seed) { srand((unsigned)seed); }
+
+std::ostream& operator<<(std::ostream& os, const tgStructure& structure) {
+    os << "tgStructure(" << structure.getNodes().size() << " nodes, " << structure.getPairs().size() << " pairs, " << structure.getChildren().size()
+       << " children) tags: " << structure.getTags();
+    return os;
+}
+
+std::ostream& operator<<(std::ostream& os, const tgStructureInfo& info) {
+    os << "tgStructureInfo(" << info.getRigids().size() << " rigids, " << info.getConnectors().size() << " connectors)";
+    return os;
 }

@@ -10,6 +10,8 @@
 
 #include "tgb_host.h"
 
+#include <cmath>
+
 /* geometry helpers with the reference's arithmetic (src/tgcreator/tgUtil.h:92-311) */
 struct tgUtil {
     static btVector3 upVector() { return btVector3(0.0, 1.0, 0.0); }
@@ -19,13 +21,39 @@ struct tgUtil {
     static btTransform getTransform(const btVector3& start, const btVector3& end);
     static void addRotation(btVector3& v, const btVector3& fixedPoint, const btVector3& axis, double angle);
     static void addRotation(btVector3& v, const btVector3& fixedPoint, const btQuaternion& rotation);
+    static void addRotation(btVector3& v, const btVector3& fixedPoint, const btVector3& fromOrientation, const btVector3& toOrientation) {
+        addRotation(v, fixedPoint, getQuaternionBetween(fromOrientation, toOrientation));
+    }
+    /* tgUtil.h:324-365: unit conversion, rounding to `precision` decimals, the C library's generator seeded (from the clock / a number) */
+    static double rad2deg(double radians) { return radians * 180.0 / M_PI; }
+    static double deg2rad(double degrees) { return degrees * (M_PI / 180.0); }
+    static double round(double d, int precision = 5) {
+        const int m = static_cast<int>(pow(10.0, precision));
+        return floor(d * m + 0.5) / m;
+    }
+    static void seedRandom();
+    static void seedRandom(int seed);
 };
+
+/* src/core/tgString.h: a name with a number appended ("segment", 3 -> "segment3") */
+inline std::string tgString(std::string s, int i) {
+    std::ostringstream ss;
+    ss << s << i;
+    return ss.str();
+}
 
 /* A tagged point (tgNode.h). */
 class tgNode : public btVector3, public tgTaggable {
 public:
     tgNode(const btVector3& v = btVector3(), const std::string& tags = "") : btVector3(v), tgTaggable(tgTags(tags)) {}
     tgNode(double x, double y, double z, const std::string& tags = "") : btVector3(x, y, z), tgTaggable(tgTags(tags)) {}
+    /* tgNode.h:62-92: turn the node about a fixed point */
+    void addRotation(const btVector3& fixedPoint, const btVector3& axis, double angle) { tgUtil::addRotation(*this, fixedPoint, axis, angle); }
+    void addRotation(const btVector3& fixedPoint, const btQuaternion& rotation) { addRotation(fixedPoint, rotation.getAxis(), rotation.getAngle()); }
+    void addRotation(const btVector3& fixedPoint, const btVector3& fromOrientation, const btVector3& toOrientation) {
+        addRotation(fixedPoint, tgUtil::getQuaternionBetween(fromOrientation, toOrientation));
+    }
+    bool operator==(const tgNode& other) const { return x() == other.x() && y() == other.y() && z() == other.z(); }
 };
 
 /* A tagged pair of points (tgPair.h). */
@@ -337,5 +365,9 @@ private:
     std::vector<tgStructureInfo*> m_children;
     std::vector<tgRigidInfo*> m_compounds;
 };
+
+/* the reference's model files print their structure info while they build (tgStructureInfo.h:141-147, tgStructure.h:211-273) */
+std::ostream& operator<<(std::ostream& os, const tgStructureInfo& info);
+std::ostream& operator<<(std::ostream& os, const tgStructure& structure);
 
 #endif /* TGB_CREATOR_H */

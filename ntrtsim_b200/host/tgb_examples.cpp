@@ -97,6 +97,36 @@ void tgCraterDeep::step(double dt) {
     tgModel::step(dt);
 }
 
+tgCraterShallow::tgCraterShallow() : m_origin(0, 0, 0) {}
+tgCraterShallow::tgCraterShallow(btVector3 center) : m_origin(center) {}
+void tgCraterShallow::setup(tgWorld& world) {
+    const tgBox::Config rampConfig(10.0, 10.0, 0.0, 1.0, 0.01, 0.2); /* density 0: static */
+    /* one ramp: the two ends of a box diagonal, 20 + half a width out in x and z and half a height + 2 up and down, both turned an
+       eighth about the vertical through the point half way between them measured from zero (tgCraterShallow.cpp:141-167) */
+    const double reach = 20.0 + 10.0 / 2.0, rise = 10.0 / 2.0 + 2.0;
+    const btVector3 pivot((reach + reach) / 2, (rise + rise) / 2, (reach + reach) / 2);
+    tgNode low(-reach, -rise, -reach, "node"), high(reach, rise, reach, "node");
+    low.addRotation(pivot, btVector3(0, 1, 0), M_PI / 4);
+    high.addRotation(pivot, btVector3(0, 1, 0), M_PI / 4);
+    tgStructure s;
+    for (int ramp = 0; ramp < 4; ++ramp) {
+        s.addNode(low);
+        s.addNode(high);
+        s.addRotation(m_origin, btVector3(0, 1, 0), M_PI / 2); /* everything entered so far turns a quarter */
+        s.addPair(2 * ramp, 2 * ramp + 1, "box");
+    }
+    s.move(btVector3(0, -5, 0)); /* sunk into the ground */
+    tgBuildSpec spec;
+    spec.addBuilder("box", new tgBoxInfo(rampConfig));
+    tgStructureInfo structureInfo(s, spec);
+    structureInfo.buildInto(*this, world);
+    tgModel::setup(world);
+}
+void tgCraterShallow::step(double dt) {
+    if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
+    tgModel::step(dt);
+}
+
 namespace {
 /* the common tail of the obstacle models: every pair tagged "box" becomes a static tgBox */
 void buildStaticBoxes(tgModel& self, tgStructure& s, const tgBox::Config& boxConfig, tgWorld& world) {

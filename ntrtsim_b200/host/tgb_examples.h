@@ -48,7 +48,7 @@ private:
 };
 
 /* Crater obstacles (src/models/obstacles/tgCraterDeep.cpp:40-169, tgCraterShallow.cpp): four static tgBox walls (density 0) standing
-   around `origin`, 20 from it, from 15 below to 20 above it; half width and half thickness 15 (deep) or 10 (shallow). */
+   around `origin`, 20 from it, from 15 below to 20 above it; half width and half thickness 15. */
 class tgCraterDeep : public tgModel {
 public:
     tgCraterDeep();
@@ -61,10 +61,18 @@ private:
     btVector3 m_origin;
     double m_halfSize;
 };
-class tgCraterShallow : public tgCraterDeep {
+/* tgCraterShallow (src/models/obstacles/tgCraterShallow.cpp:72-168) is not a smaller tgCraterDeep: its four static boxes (half width
+   and half thickness 10) run along the DIAGONAL from (-25, -7, -25) to (25, 7, 25), turned an eighth about the vertical through
+   (25, 7, 25); the structure so far is turned a quarter about the vertical through `origin` after each, and all sink 5 into the ground --
+   low ramps leaning outwards instead of walls.  (tests/test_reference_sources.py holds this against the reference's own source.) */
+class tgCraterShallow : public tgModel {
 public:
-    tgCraterShallow() : tgCraterDeep(btVector3(0, 0, 0), 10.0) {}
-    explicit tgCraterShallow(btVector3 center) : tgCraterDeep(center, 10.0) {}
+    tgCraterShallow();
+    explicit tgCraterShallow(btVector3 center);
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt); /* dt <= 0 -> std::invalid_argument */
+private:
+    btVector3 m_origin;
 };
 
 /* A flight of stairs (src/models/obstacles/tgStairs.{h,cpp}): nStairs static boxes, each `stepWidth` further and `stepHeight`

@@ -46,7 +46,6 @@ std::string tgTags::joinTags(const std::string& sep) const {
 std::ostream& operator<<(std::ostream& os, const tgTags& t) { return os << t.joinTags(" "); }
 
 tgTagSearch::tgTagSearch(const std::string& expr) { parse(expr); }
-tgTagSearch::tgTagSearch(const char* expr) { parse(expr ? expr : ""); }
 void tgTagSearch::parse(const std::string& expr) {
     std::size_t start = 0;
     while (start <= expr.size()) {

@@ -16,8 +16,15 @@
 #include "../../include/ntrtsim_b200.h"
 #include "LinearMath/btTransform.h"
 
+/* the standard headers the reference's core headers bring along (src/core/tgTaggable.h:29-35, tgModel.h:35-36): model sources
+   written against them rely on assert, atoi, std::cout ... being declared */
+#include <assert.h>
+#include <stdlib.h>
+#include <algorithm>
 #include <cstddef>
+#include <cstdio>
 #include <deque>
+#include <iostream>
 #include <set>
 #include <sstream>
 #include <stdexcept>
@@ -59,8 +66,8 @@ std::ostream& operator<<(std::ostream& os, const tgTags& t);
 class tgTagSearch {
 public:
     tgTagSearch() {}
-    tgTagSearch(const std::string& expr);
-    tgTagSearch(const char* expr);
+    tgTagSearch(const std::string& expr); /* the only converting constructor, as in src/core/tgTagSearch.h:54: find<T>("tag") then picks
+                                             the std::string overload of tgModel::find instead of being ambiguous */
     bool matches(const tgTags& tags) const;
     void remove(const tgTags& tags);
 private:
@@ -318,6 +325,9 @@ public:
 private:
     std::vector<tgModel*> m_children;
 };
+
+/* tgModel.h:227-237: a model prints as its toString() */
+inline std::ostream& operator<<(std::ostream& os, const tgModel& obj) { return os << obj.toString(); }
 
 class tgModelVisitor {
 public:

@@ -11,8 +11,22 @@
 #include <cstring>
 #include <string>
 
+#include <dlfcn.h>
+
 namespace {
 thread_local std::string g_error;
+
+/* "ref:<shared library>@<example>": the world of <example>, but the model objects come from `tgModel* tgb_make_model(const char*
+   which)` of the library -- tests/ref_models builds one from the reference's own, unchanged model sources compiled against this
+   host API (ntrtsim_b200/host/compat), which is what "the existing tgModel / tgStructure / tgBuildSpec API stays in place" means. */
+typedef tgModel* (*ModelFactory)(const char*);
+thread_local ModelFactory g_factory = 0;
+tgModel* fromFactory(const std::string& which) {
+    tgModel* m = g_factory(which.c_str());
+    if (!m) throw std::invalid_argument("the model library has no model for " + which);
+    return m;
+}
+#define TGB_MODEL(which, expr) (g_factory ? fromFactory(which) : static_cast<tgModel*>(expr))
 
 struct Example {
     tgWorld* world;
@@ -30,6 +44,19 @@ struct Example {
 };
 
 Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) {
+    if (name.compare(0, 4, "ref:") == 0) {
+        const std::size_t at = name.rfind('@');
+        if (at == std::string::npos) { g_error = "ref:<library>@<example> expected"; return 0; }
+        const std::string lib = name.substr(4, at - 4), base = name.substr(at + 1);
+        void* h = dlopen(lib.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!h) { g_error = std::string("cannot load the model library: ") + dlerror(); return 0; }
+        ModelFactory f = reinterpret_cast<ModelFactory>(dlsym(h, "tgb_make_model"));
+        if (!f) { g_error = "the model library does not export tgb_make_model"; return 0; }
+        g_factory = f;
+        Example* e = build(base, n_env, precision);
+        g_factory = 0;
+        return e; /* the library stays loaded: the model's code lives in it */
+    }
     Example* e = new Example();
     try {
         if (name == "3_prism" || name == "3_prism_noground") {
@@ -37,26 +64,27 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
                                                  : static_cast<tgGround*>(new tgEmptyGround());
             e->world = new tgWorld(tgWorld::Config(981), ground);
             e->dt = 0.001;
-            e->model = new PrismModel();
+            e->model = TGB_MODEL(name, new PrismModel());
         } else if (name == "SUPERball" || name == "SUPERball_flat") {
             const double pitch = name == "SUPERball" ? M_PI / 15.0 : 0.0;
             e->world = new tgWorld(tgWorld::Config(98.1), new tgBoxGround(tgBoxGround::Config(btVector3(0.0, pitch, 0.0))));
             e->dt = 0.001;
-            e->model = new T6Model();
+            e->model = TGB_MODEL(name, new T6Model());
         } else if (name == "Escape_crater" || name == "Escape_crater_shallow") {
             /* AppEscape.cpp:59-97 complete: EscapeModel and, as a second model of the same simulation, tgCraterDeep at the origin */
             e->world = new tgWorld(tgWorld::Config(98.1),
                                    new tgBoxGround(tgBoxGround::Config(btVector3(0, 0, 0), 0.5, 0.0, btVector3(10000.0, 2, 10000.0), btVector3(0, 0, 0))));
             e->dt = 1.0 / 60.0 / 10.0;
-            e->model = new EscapeModel();
-            e->obstacle = name == "Escape_crater" ? new tgCraterDeep(btVector3(0, 0, 0)) : new tgCraterShallow(btVector3(0, 0, 0));
+            e->model = TGB_MODEL(name, new EscapeModel());
+            e->obstacle = TGB_MODEL(name + ":obstacle", name == "Escape_crater" ? static_cast<tgModel*>(new tgCraterDeep(btVector3(0, 0, 0)))
+                                                                                : static_cast<tgModel*>(new tgCraterShallow(btVector3(0, 0, 0))));
         } else if (name == "SUPERball_stairs" || name == "SUPERball_blocks" || name == "SUPERball_wall") {
             /* src/models/obstacles/AppObstacleTest.cpp-style scenes: the SUPERball on the default ground next to an obstacle model */
             e->world = new tgWorld(tgWorld::Config(98.1));
             e->dt = 0.001;
-            e->model = new T6Model();
+            e->model = TGB_MODEL(name, new T6Model());
             if (name == "SUPERball_stairs") {
-                e->obstacle = new tgStairs(tgStairs::Config(btVector3(0.0, 2.0, -10.0), 0.5, 0.0, 6, 20.0, 5.0, 1.0, 0.0));
+                e->obstacle = TGB_MODEL(name + ":obstacle", new tgStairs(tgStairs::Config(btVector3(0.0, 2.0, -10.0), 0.5, 0.0, 6, 20.0, 5.0, 1.0, 0.0)));
             } else if (name == "SUPERball_blocks") {
                 srand(1); /* the reference draws the block positions from rand(); a fixed seed keeps the scene reproducible */
                 e->obstacle = new tgBlockField(tgBlockField::Config(btVector3(0.0, 1.5, 0.0), 0.5, 0.0, btVector3(-30.0, 0.0, -30.0),
@@ -72,16 +100,16 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
                                          : tgBoxGround::Config();
             e->world = new tgWorld(tgWorld::Config(98.1), new tgBoxGround(gc));
             e->dt = name == "Escape" ? 1.0 / 60.0 / 10.0 : 0.001;
-            e->model = new EscapeModel();
+            e->model = TGB_MODEL(name, new EscapeModel());
         } else if (name == "tsTestRig_basic" || name == "tsTestRig_kinematic") {
             e->world = new tgWorld(tgWorld::Config(981)); /* MotorTimestep_test: default ground */
             e->dt = 0.001;
-            e->model = new tsTestRig(name == "tsTestRig_kinematic");
+            e->model = TGB_MODEL(name, new tsTestRig(name == "tsTestRig_kinematic"));
         } else if (name == "TetraSpine") {
             /* AppTetraSpineLearning.cpp:48-109: tgWorld(Config(981)) with the default box ground, dt = 1e-3, 3 segments */
             e->world = new tgWorld(tgWorld::Config(981));
             e->dt = 0.001;
-            e->model = new TetraSpineLearningModel(3);
+            e->model = TGB_MODEL(name, new TetraSpineLearningModel(3));
         } else if (name == "TetraSpineStatic_hf") {
             /* ICRA2015_test.cpp:77-101: tgWorld(Config(981)) with the default box ground, dt = 1e-3, 3 segments */
             e->world = new tgWorld(tgWorld::Config(981));
@@ -92,7 +120,7 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
                segments ("FlemonsSpine3": the same vertebrae, 3 segments, for small tests) */
             e->world = new tgWorld(tgWorld::Config(981));
             e->dt = 0.001;
-            e->model = new FlemonsSpineModelLearning(name == "FlemonsSpine" ? 12 : 3);
+            e->model = TGB_MODEL(name, new FlemonsSpineModelLearning(name == "FlemonsSpine" ? 12 : 3));
         } else if (name.size() > 5 && name.compare(0, 5, "yaml:") == 0) {
             /* "yaml:<path>[@gravity[@dt]]": a structure file of the YAML front-end in the world of the reference's yamlbuilder app
                (src/yamlbuilder/BuildTensegrityModel.cpp:44-79: gravity 98.1, default box ground, dt = 1e-3) */
