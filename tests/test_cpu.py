@@ -279,20 +279,34 @@ builders:
 
 
 def test_crater_obstacle_models():
-    """tgCraterDeep / tgCraterShallow (src/models/obstacles): four static boxes a quarter turn apart, 20 from the origin, sunk by 5;
-    as the second model of the AppEscape simulation they follow EscapeModel's six rods in the flattened world."""
-    for name, half in (("Escape_crater", 15.0), ("Escape_crater_shallow", 10.0)):
-        m = nt.build_example(name)
-        assert (m.n_bodies, m.n_cables) == (10, 24)
-        walls = [i for i, b in enumerate(m.bodies) if b.mass == 0.0]
-        assert walls == [6, 7, 8, 9]
-        pos = m.initial_rod_state()[walls, 0:3]
-        assert np.allclose(np.sort(np.abs(pos[:, [0, 2]]).max(axis=1)), 20.0) and np.allclose(pos[:, 1], 2.5)
-        assert np.allclose(np.abs(pos[:, [0, 2]]).min(axis=1), 0.0, atol=1e-12)
-        for i in walls:
-            s = m.shapes[m.bodies[i].shape_begin]
-            assert (s.kind, s.radius, s.half_length, s.half_extent_z) == (2, half, 17.5, half)
-            assert (m.bodies[i].friction, m.bodies[i].rolling_friction, m.bodies[i].restitution) == (1.0, 0.01, 0.2)
+    """tgCraterDeep / tgCraterShallow (src/models/obstacles): four static boxes a quarter turn apart, sunk by 5; as the second model of
+    the AppEscape simulation they follow EscapeModel's six rods in the flattened world.  Deep: walls 20 from the origin.  Shallow
+    (tgCraterShallow.cpp:124-168): boxes along the diagonal between (-25, -7, -25) and (25, 7, 25) turned an eighth -- low ramps; the
+    exact descriptors are held against the reference's own source in tests/test_reference_sources.py."""
+    m = nt.build_example("Escape_crater")
+    assert (m.n_bodies, m.n_cables) == (10, 24)
+    walls = [i for i, b in enumerate(m.bodies) if b.mass == 0.0]
+    assert walls == [6, 7, 8, 9]
+    pos = m.initial_rod_state()[walls, 0:3]
+    assert np.allclose(np.sort(np.abs(pos[:, [0, 2]]).max(axis=1)), 20.0) and np.allclose(pos[:, 1], 2.5)
+    assert np.allclose(np.abs(pos[:, [0, 2]]).min(axis=1), 0.0, atol=1e-12)
+    for i in walls:
+        s = m.shapes[m.bodies[i].shape_begin]
+        assert (s.kind, s.radius, s.half_length, s.half_extent_z) == (2, 15.0, 17.5, 15.0)
+        assert (m.bodies[i].friction, m.bodies[i].rolling_friction, m.bodies[i].restitution) == (1.0, 0.01, 0.2)
+    m = nt.build_example("Escape_crater_shallow")
+    assert (m.n_bodies, m.n_cables) == (10, 24)
+    ramps = [i for i, b in enumerate(m.bodies) if b.mass == 0.0]
+    assert ramps == [6, 7, 8, 9]
+    pos = m.initial_rod_state()[ramps, 0:3]
+    half_diagonal = 0.5 * math.sqrt(50.0 ** 2 + 14.0 ** 2 + 50.0 ** 2)
+    assert np.allclose(pos[:, 1], -5.0)                                                       # centred 5 below the origin's height
+    assert np.allclose(pos.sum(axis=0)[[0, 2]], 0.0, atol=1e-9)                               # a quarter turn apart about the vertical
+    assert np.allclose(np.hypot(pos[:, 0], pos[:, 2]), np.hypot(pos[0, 0], pos[0, 2]))
+    for i in ramps:
+        s = m.shapes[m.bodies[i].shape_begin]
+        assert (s.kind, s.radius, s.half_extent_z) == (2, 10.0, 10.0) and abs(s.half_length - half_diagonal) < 1e-9
+        assert (m.bodies[i].friction, m.bodies[i].rolling_friction, m.bodies[i].restitution) == (1.0, 0.01, 0.2)
 
 
 def test_oracle_bodies_rest_on_a_static_obstacle(tmp_path):
