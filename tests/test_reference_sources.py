@@ -68,7 +68,7 @@ def test_reference_model_source_unmodified_runs_through_tgb(name, ctrl):
     if ctrl == capi.TGB_CTRL_ESCAPE_SINE:
         params = nt.escape_transform_actions(np.random.default_rng(4).uniform(size=(n_env, 32)), 9.0)
     elif ctrl == capi.TGB_CTRL_TENSION:
-        params = np.full((n_env, 1), 300.0)
+        params = np.full((n_env, 1), 1000.0)  # AppSUPERball.cpp: T6TensionController(1000)
     w = nt.BatchedWorld(model, n_env, precision="f64")
     w.set_rod_state(rods)
     w.set_cable_state(cab)
