@@ -41,6 +41,7 @@ def load():
     lib.tgo_num_pair_contacts.argtypes = [vp]
     lib.tgo_set_pair_contact_cap.argtypes = [vp, i]
     lib.tgo_set_default_pair_contact_cap.argtypes = [i]
+    lib.tgo_set_warm_start.argtypes = [vp, dbl]
     lib.tgo_get_min_clearance.restype = dbl
     lib.tgo_get_min_clearance.argtypes = [vp]
     lib.tgo_reset_min_clearance.argtypes = [vp]
@@ -124,6 +125,10 @@ class OracleWorld(object):
 
     def set_pair_contact_cap(self, cap):
         self._lib.tgo_set_pair_contact_cap(self._h, int(cap))
+
+    def set_warm_start(self, factor):
+        """warm starting factor of the contact solver (Bullet: 0.85); 0 = no persistent manifold"""
+        self._lib.tgo_set_warm_start(self._h, float(factor))
 
     def min_clearance(self, reset=False):
         """smallest surface distance between two bodies' shapes seen by any world step so far"""

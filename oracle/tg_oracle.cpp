@@ -155,6 +155,7 @@ struct Cable {
 
 struct Contact {
     int body;
+    long long key = -1; /* identity of the manifold point across steps (persistent manifold): see warmStartKey */
     int bodyB = -1; /* body pairs: the second body (the normal points from B to A, Bullet's m_normalWorldOnB); -1 = the static world */
     V3 n;        /* ground -> rod */
     V3 r;        /* contact point on the rod relative to its centre of mass */
@@ -226,6 +227,13 @@ struct tgo_world {
     V3 episodeStartCom;
     int iterations = 10;
     int status = 0;
+    /* Persistent manifold + warm starting (btPersistentManifold keeps a point's applied impulses from step to step;
+       btSequentialImpulseConstraintSolver starts the next solve from them scaled by btContactSolverInfo::m_warmstartingFactor = 0.85,
+       SOLVER_USE_WARMSTARTING is on by default).  A point keeps its identity through its slot: (shape, rim point) against the ground,
+       (obstacle shape, shape, sample) against an obstacle, (shape, shape, point) between two bodies.  0 = every solve starts from zero. */
+    double warmStart = 0.85;
+    struct Cached { double lamN, lamT; };
+    std::vector<std::pair<long long, Cached> > manifoldCache; /* of the last step, keyed (key, body) packed */
     int pairCap = 6;            /* rows of body-pair contacts per environment (tgb_set_pair_contact_cap); 0 = bodies do not collide */
     int pairRows = 0;           /* body-pair rows of the last world step */
     double minClearance = 1e30; /* smallest surface distance of two bodies' shapes seen by any world step */
@@ -648,6 +656,7 @@ struct tgo_world {
                                 if (mu > 10.0) mu = 10.0;
                                 ct.mu = mu;
                                 ct.restitution = b.restitution * ob.restitution;
+                                ct.key = (((long long)1 << 40) | ((long long)osi << 24) | ((long long)si << 8) | (long long)k);
                                 contacts.push_back(ct);
                                 ++count;
                                 rows[bi] += 1;
@@ -762,6 +771,7 @@ struct tgo_world {
                             if (mu > 10.0) mu = 10.0;
                             ct.mu = mu;
                             ct.restitution = A.restitution * B.restitution;
+                            ct.key = (((long long)2 << 40) | ((long long)sa << 24) | ((long long)sb << 8) | (long long)k);
                             contacts.push_back(ct);
                             ++count;
                             ++pairRows;
@@ -814,6 +824,7 @@ struct tgo_world {
                                 if (mu > 10.0) mu = 10.0;
                                 ct.mu = mu;
                                 ct.restitution = b.restitution * ground.restitution;
+                                ct.key = ((long long)si << 8) | (long long)(e * 4 + k);
                                 contacts.push_back(ct);
                                 ++count;
                             }
@@ -840,6 +851,7 @@ struct tgo_world {
                             if (mu > 10.0) mu = 10.0;
                             ct.mu = mu;
                             ct.restitution = b.restitution * ground.restitution;
+                            ct.key = ((long long)si << 8) | (long long)(e * 4 + k);
                             contacts.push_back(ct);
                             ++count;
                         }
@@ -906,7 +918,7 @@ struct tgo_world {
             double lat2 = lat.length2();
             if (lat2 > DBL_EPSILON) c.t = lat * (1.0 / std::sqrt(lat2));
             else c.t = planeSpace1(c.n);
-            c.lamN = 0.0; c.lamPush = 0.0; c.lamT = 0.0; /* no persistent manifold => no warm start */
+            c.lamN = 0.0; c.lamPush = 0.0; c.lamT = 0.0; /* warm start: applied below, once the row is complete */
             double velDotN = c.n.dot(b.linvel + extLin[i]) + c.rxn.dot(b.angvel + extAng[i]);
             if (pair) velDotN = velDotN - (c.n.dot(bB.linvel + extLin[j]) + c.rxnB.dot(bB.angvel + extAng[j]));
             double velocityError = restitution - velDotN;
@@ -933,6 +945,23 @@ struct tgo_world {
             }
             c.invDiagT = 1.0 / denomT;
             c.rhsT = (0.0 - relT) * c.invDiagT;
+            if (warmStart > 0.0) {
+                /* setupContactConstraint / setFrictionConstraintImpulse: the point's impulses of the last step, scaled, are the starting
+                   point of this solve and act on the bodies' velocity changes straight away (the friction impulse along the NEW direction) */
+                const long long id = (c.key << 12) | ((long long)c.body << 6) | (long long)(c.bodyB < 0 ? 63 : c.bodyB);
+                for (const auto& e : manifoldCache)
+                    if (e.first == id) {
+                        c.lamN = e.second.lamN * warmStart;
+                        c.lamT = e.second.lamT * warmStart;
+                        dLin[i] += c.n * (b.invMass * c.lamN) + c.t * (b.invMass * c.lamT);
+                        dAng[i] += c.angN * c.lamN + c.angT * c.lamT;
+                        if (pair) {
+                            dLin[j] -= c.n * (bB.invMass * c.lamN) + c.t * (bB.invMass * c.lamT);
+                            dAng[j] -= c.angNB * c.lamN + c.angTB * c.lamT;
+                        }
+                        break;
+                    }
+            }
         }
 
         /* split-impulse iterations, then velocity iterations (fixed-iteration PGS in place of Dantzig) */
@@ -996,6 +1025,13 @@ struct tgo_world {
             }
         }
 
+        if (warmStart > 0.0) {
+            manifoldCache.clear();
+            for (const Contact& c : contacts) {
+                const long long id = (c.key << 12) | ((long long)c.body << 6) | (long long)(c.bodyB < 0 ? 63 : c.bodyB);
+                manifoldCache.push_back(std::make_pair(id, Cached{c.lamN, c.lamT}));
+            }
+        }
         /* write back + split-impulse transform correction */
         for (size_t i = 0; i < nb; ++i) {
             Body& b = bodies[i];
@@ -1108,6 +1144,7 @@ int tgo_num_bodies(const tgo_world* w) { return (int)w->bodies.size(); }
 int tgo_num_cables(const tgo_world* w) { return (int)w->cables.size(); }
 
 void tgo_set_rod_state(tgo_world* w, const double* s) {
+    /* (the persistent manifolds survive: the hybrid reference rollouts hand the state over every step) */
     for (size_t i = 0; i < w->bodies.size(); ++i, s += 13) {
         Body& b = w->bodies[i];
         b.pos = V3(s[0], s[1], s[2]);
@@ -1228,6 +1265,7 @@ int tgo_set_cpg_controller(tgo_world* w, const tgb_cpg_desc* d, const double* pa
 int tgo_num_contacts(const tgo_world* w) { return (int)w->contacts.size(); }
 int tgo_num_pair_contacts(const tgo_world* w) { return w->pairRows; }
 void tgo_set_pair_contact_cap(tgo_world* w, int cap) { w->pairCap = cap < 0 ? 0 : cap; }
+void tgo_set_warm_start(tgo_world* w, double factor) { w->warmStart = factor; w->manifoldCache.clear(); }
 double tgo_get_min_clearance(const tgo_world* w) { return w->minClearance; }
 void tgo_reset_min_clearance(tgo_world* w) { w->minClearance = 1e30; }
 

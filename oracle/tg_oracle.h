@@ -85,7 +85,10 @@ int    tgo_num_contacts(const tgo_world* w);      /* contacts generated in the l
 int    tgo_num_pair_contacts(const tgo_world* w); /* of which rows between two bodies */
 /* rows of body-pair contacts kept per environment (same meaning as tgb_set_pair_contact_cap; default 6, 0 = bodies do not collide) */
 void   tgo_set_pair_contact_cap(tgo_world* w, int cap);
-void   tgo_set_default_pair_contact_cap(int cap);  /* for worlds created afterwards (tgo_rollout_batch creates its own) */
+void   tgo_set_default_pair_contact_cap(int cap);
+/* warm starting factor of the contact solver (btContactSolverInfo::m_warmstartingFactor, 0.85): every manifold point starts a solve
+   from its impulses of the previous step times this; 0 = every solve starts from zero (no persistent manifold). */
+void   tgo_set_warm_start(tgo_world* w, double factor);  /* for worlds created afterwards (tgo_rollout_batch creates its own) */
 /* smallest surface distance between the collision shapes of two different bodies seen by any world step so far */
 double tgo_get_min_clearance(const tgo_world* w);
 void   tgo_reset_min_clearance(tgo_world* w);

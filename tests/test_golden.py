@@ -183,8 +183,10 @@ def test_icra2015_hardware_comparison_of_the_reference_test_suite():
     SerializedSpineControl (controlVars.json of resources/src/ICRA2015/static) for 60000 steps of 1 ms, ground contact and the 2.3 kg
     load ramp included; the maxima of the six front cables' tension histories against the tensions measured on the robot.  This is
     the one test of the reference suite that exercises the whole path with a quantitative answer.  Its bounds are the reference
-    simulator's own errors plus a hair; the oracle meets four of the six and misses outer front left (0.3554 vs 0.3501) and inner
-    front top (0.06004 vs 0.06): asserted here is every bound widened by one percentage point, and the four outright."""
+    simulator's own errors plus a hair, so meeting all six says the maxima agree with NTRTsim/Bullet to about half a percent.
+    They are asserted as the reference asserts them (EXPECT_LE, no widening).  What it took (round 2): the persistent manifold with
+    warm starting at Bullet's factor 0.85 -- without it the resting contacts of the feet chatter and two bounds are missed by 0.5 and
+    0.02 percentage points (checked below as well, so that the dependence stays visible)."""
     hardware = np.array([14.1811, 15.5914, 24.6800, 22.0161, 18.0986, 34.3954])
     bound = np.array([0.2251, 0.3501, 0.19, 0.0601, 0.0715, 0.06])
     model = nt.build_example("TetraSpineStatic_hf")
@@ -197,5 +199,12 @@ def test_icra2015_hardware_comparison_of_the_reference_test_suite():
     sim = mt[:6] / 100.0
     err = np.abs((hardware - sim) / hardware)
     print("ICRA2015 (oracle): max tensions %s N, error vs hardware %s" % (np.round(sim, 2), np.round(err, 4)))
-    assert np.all(err <= bound + 0.01), err
-    assert np.all(err[[0, 2, 3, 4]] <= bound[[0, 2, 3, 4]]), err
+    assert np.all(err <= bound), err
+    cold = oracle_py.OracleWorld(model, capi.WorldCfg)
+    cold.set_warm_start(0.0)
+    cold.set_controller(capi.TGB_CTRL_SERIALIZED_SPINE, nt.serialized_spine_params(model))
+    cold.track_max_tension(True)
+    cold.step(model.dt, 60000)
+    err_cold = np.abs((hardware - cold.max_tension()[:6] / 100.0) / hardware)
+    print("ICRA2015 (oracle, every solve from zero): error vs hardware %s" % np.round(err_cold, 4))
+    assert np.all(err_cold <= bound + 0.01) and not np.all(err_cold <= bound)
