@@ -326,6 +326,19 @@ tgb_status tgb_set_lanes_per_env(tgb_world* w, int32_t lanes);
 #define TGB_DEFAULT_PAIR_CONTACT_CAP 6
 tgb_status tgb_set_pair_contact_cap(tgb_world* w, int32_t cap);
 
+/* Persistent contact manifolds with warm starting (ABI version 4).  Bullet keeps a manifold point's applied impulses from step to step
+   (btPersistentManifold) and its sequential-impulse solver starts every solve from them scaled by
+   btContactSolverInfo::m_warmstartingFactor = 0.85 (SOLVER_USE_WARMSTARTING is on by default; the world of
+   src/core/tgWorldBulletPhysicsImpl.cpp:134-146 leaves both alone).  Here a point keeps its identity through its slot -- (shape, rim
+   point) against the ground, (obstacle, shape, sample) against an obstacle, (shape, shape, point) between two bodies -- and the
+   impulses travel with the environment between launches.  0 = every solve starts from zero.  Changing the factor empties the
+   manifolds.  Default TGB_DEFAULT_WARM_STARTING = 0 (off): NTRTsim's world solves contacts with btMLCPSolver(btDantzigSolver), a direct
+   solve that does not depend on a starting point, and on the reference suite's one quantitative whole-path test (ICRA2015_test.cpp) an
+   ensemble of perturbed runs gives the same error distribution with and without warm starting, while the
+   persistent manifolds cost ~20 % of the step's throughput.  Pass 0.85 for the behaviour of Bullet's own sequential-impulse solver. */
+#define TGB_DEFAULT_WARM_STARTING 0.0
+tgb_status tgb_set_warm_starting(tgb_world* w, double factor);
+
 /* out[env_count]: the smallest surface distance between the collision shapes (capsules, spheres) of two different bodies of the
    environment that any step has seen since tgb_finalize or the last call with reset != 0 (1e30: no pair has come near; measured for
    pairs whose bounding spheres overlap).  Negative = the shapes overlap by that much. */

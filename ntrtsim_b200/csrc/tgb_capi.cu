@@ -52,6 +52,9 @@ struct tgb_world {
     int R = 0, C = 0, S = 0, stride = 0, capContacts = 0, frameBody = 0, nInc = 0, maxInc = 0, nObst = 0, modelObstOff = 0;
     int nPairs = 0, modelPairOff = 0, pairCap = TGB_DEFAULT_PAIR_CONTACT_CAP; /* contact between bodies (tgb_pairs.cuh) */
     float* d_min_clearance = nullptr;
+    void* d_warm = nullptr;        /* persistent manifolds between launches: T[n_env][warmWords] (tgb_dev.h TGB_WARM_*) */
+    int warmWords = 0;
+    double warmFactor = TGB_DEFAULT_WARM_STARTING; /* btContactSolverInfo::m_warmstartingFactor */
     int lanes = 0, threads = 0, lanesOverride = 0, threadsOverride = 0, wideMode = -1;
     mutable int wideCtasPerSm[2] = {-1, -1}; /* by controller class (simple, sine); -1 = not asked yet */
     int smCount = 148;
@@ -130,6 +133,7 @@ struct tgb_world {
         if (h_stage) cudaFreeHost(h_stage);
         if (d_scores) cudaFree(d_scores);
         if (d_min_clearance) cudaFree(d_min_clearance);
+        if (d_warm) cudaFree(d_warm);
         if (d_cpg_topo) cudaFree(d_cpg_topo);
         if (d_cpg_imp) cudaFree(d_cpg_imp);
         if (d_cpg_state) cudaFree(d_cpg_state);
@@ -316,6 +320,8 @@ bool wideLayout(const tgb_world* w) {
         a.ctrl_kind = w->ctrlKind; a.ctrl_stride = std::max(w->C, TGB_ESCAPE_PARAMS); a.ground_kind = w->ground.kind;
         a.model_t_words = w->modelTWords; a.model_i_words = w->modelIWords;
         a.n_pairs = w->pairCap != 0 ? w->nPairs : 0; a.pair_cap = w->pairCap;
+        a.warm = w->warmFactor > 0.0 ? w->d_warm : nullptr; a.n_dyn = 0;
+        for (int b = 0; b < w->R; ++b) a.n_dyn += w->bodies[b].mass != 0.0;
         int ctas = 0;
         if (w->ops->wide_ctas_per_sm(a, w->lanes, &ctas) != cudaSuccess) { cudaGetLastError(); ctas = 0; }
         w->wideCtasPerSm[cls] = ctas;
@@ -348,6 +354,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.n_obst = w->nObst; a.model_obst_off = w->modelObstOff;
     a.n_pairs = w->pairCap != 0 ? w->nPairs : 0; a.model_pair_off = w->modelPairOff; a.pair_cap = w->pairCap;
     a.min_clearance = w->d_min_clearance;
+    a.warm = w->warmFactor > 0.0 ? w->d_warm : nullptr; a.warm_factor = w->warmFactor;
     a.n_dyn = 0;
     for (int b = 0; b < w->R; ++b) a.n_dyn += w->bodies[b].mass != 0.0;
     a.dt = dt;
@@ -527,6 +534,37 @@ tgb_status tgb_set_pair_contact_cap(tgb_world* w, int32_t cap) {
     return TGB_OK;
 }
 
+tgb_status tgb_set_warm_starting(tgb_world* w, double factor) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (!(factor >= 0.0 && factor <= 1.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "warm starting factor must be in [0, 1]");
+    if (w->finalized && factor > 0.0) {
+        /* the persistent manifolds take shared memory in the step kernel: refuse rather than fail at the next launch */
+        const double before = w->warmFactor;
+        w->warmFactor = factor;
+        tgb_step_args a = stepArgs(w, 1e-3, 1);
+        if (a.ctrl_stride == 0) a.ctrl_stride = std::max(w->C, TGB_ESCAPE_PARAMS);
+        if (w->ops->step_smem(a, w->lanes, w->threads) > 227 * 1024) {
+            w->warmFactor = before;
+            return fail(TGB_ERR_UNSUPPORTED, "tgb_set_warm_starting: the persistent manifolds do not fit in shared memory for this model");
+        }
+    }
+    w->warmFactor = factor;
+    if (w->finalized && w->d_warm) {
+        /* a new factor starts from empty manifolds */
+        TGB_CUDA(cudaSetDevice(w->cfg.device));
+        TGB_CUDA(cudaStreamSynchronize(w->stream));
+        const size_t words = (size_t)w->cfg.n_env * w->warmWords;
+        if (w->scalarBytes == 4) {
+            std::vector<float> empty(words, -1.0f);
+            TGB_CUDA(cudaMemcpy(w->d_warm, empty.data(), words * sizeof(float), cudaMemcpyHostToDevice));
+        } else {
+            std::vector<double> empty(words, -1.0);
+            TGB_CUDA(cudaMemcpy(w->d_warm, empty.data(), words * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    return TGB_OK;
+}
+
 tgb_status tgb_get_min_clearance(tgb_world* w, int32_t env_begin, int32_t env_count, double* out, int32_t reset) {
     if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
     if (!w->finalized) return fail(TGB_ERR_STATE, "world is not finalized");
@@ -621,6 +659,23 @@ tgb_status tgb_finalize(tgb_world* w) {
         std::vector<float> far((size_t)n, 1e30f);
         TGB_CUDA(cudaMalloc(&w->d_min_clearance, (size_t)n * sizeof(float)));
         TGB_CUDA(cudaMemcpy(w->d_min_clearance, far.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    {
+        /* persistent manifolds: empty (key -1) */
+        int nDyn = 0;
+        for (int b = 0; b < w->R; ++b) nDyn += w->bodies[b].mass != 0.0;
+        const int rowBodies = w->nObst > 0 ? nDyn : w->R;
+        const int pairCapRows = (w->pairCap > 0 && w->nPairs > 0) ? w->pairCap : 0;
+        w->warmWords = TGB_WARM_STATE_WORDS(w->capContacts, rowBodies, pairCapRows);
+        const size_t words = (size_t)n * w->warmWords;
+        TGB_CUDA(cudaMalloc(&w->d_warm, std::max<size_t>(words * w->scalarBytes, 16)));
+        if (w->scalarBytes == 4) {
+            std::vector<float> empty(words, -1.0f);
+            TGB_CUDA(cudaMemcpy(w->d_warm, empty.data(), words * sizeof(float), cudaMemcpyHostToDevice));
+        } else {
+            std::vector<double> empty(words, -1.0);
+            TGB_CUDA(cudaMemcpy(w->d_warm, empty.data(), words * sizeof(double), cudaMemcpyHostToDevice));
+        }
     }
     TGB_CUDA(cudaMalloc(&w->d_scores, (size_t)n * 2 * sizeof(float)));
     TGB_CUDA(cudaMemset(w->d_scores, 0, (size_t)n * 2 * sizeof(float)));

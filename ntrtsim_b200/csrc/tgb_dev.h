@@ -57,17 +57,26 @@ enum { TGB_NBS = 13 };
 /* per-contact solver row words kept in shared memory */
 enum {
     CT_RXN = 0, CT_ANGN = 3, CT_INVDIAGN = 6, CT_RHSN, CT_RHSPEN, CT_LAMN, CT_LAMPUSH, CT_T = 11, CT_RXT = 14, CT_ANGT = 17,
-    CT_INVDIAGT = 20, CT_RHST, CT_LAMT, TGB_NCT,
+    CT_INVDIAGT = 20, CT_RHST, CT_LAMT,
+    CT_KEY /* identity of the manifold point across steps (persistent manifold, warm starting): see TGB_WARM_* */,
+    TGB_NCT = 25 /* odd row stride: rows of neighbouring lanes on distinct banks */,
     /* worlds with static obstacles: the row's own normal and friction coefficient behind the common part */
-    CT_NRM = TGB_NCT, CT_MU = CT_NRM + 3, TGB_NCT_OBST = CT_MU + 2 /* odd row stride: rows of neighbouring lanes on distinct banks */
+    CT_NRM = CT_KEY + 1, CT_MU = CT_NRM + 3, TGB_NCT_OBST = 29
 };
+/* Persistent manifold: per environment and dynamic body the (key, normal impulse, friction impulse) of every row of the last world
+   step, [cap_contacts][row bodies][3], then [pair_cap][3] for the rows between two bodies; key < 0 = empty.  A point keeps its
+   identity through its slot: ground: (shape of the body, rim point / corner); obstacle: TGB_WARM_OBST + (obstacle, shape, sample);
+   pair: (body A + 32 body B, shape of A, shape of B, point).  In shared memory during a launch, in HBM (tgb_step_args.warm) between
+   launches, so that results do not depend on how an episode is cut into launches. */
+enum { TGB_WARM_WORDS = 3, TGB_WARM_OBST = 4096 };
+#define TGB_WARM_STATE_WORDS(cap, rowBodies, pairCap) (TGB_WARM_WORDS * ((cap) * (rowBodies) + (pairCap)))
 /* Row of a contact between two bodies (tgb_pairs.cuh), T words in shared memory.  The two sides' Jacobian blocks are not stored: each
    side's lane re-forms r x n, Iinv (r x n) from its own r and the inverse inertia in its registers.  Between detection and row
    set-up PR_RA / PR_RB hold the contact points on the two surfaces (frame-relative), PR_LAMN the distance, PR_LAMPUSH the
-   combined restitution. */
+   combined restitution, PR_INVDIAGT / PR_RHST the point's warm-start impulses (normal, friction; already scaled). */
 enum {
     PR_N = 0, PR_RA = 3, PR_RB = 6, PR_T = 9, PR_INVDIAGN = 12, PR_RHSN, PR_RHSPEN, PR_LAMN, PR_LAMPUSH, PR_INVDIAGT, PR_RHST, PR_LAMT,
-    PR_MU, PR_IDS /* body A + 32 * body B */, TGB_NPR
+    PR_MU, PR_IDS /* body A + 32 * body B */, PR_KEY /* identity of the point across steps (warm starting) */, TGB_NPR
 };
 /* frame doubles */
 enum { FR_O = 0, FR_V = 3, FR_CTRLTIME = 6, FR_SPARE = 7, TGB_NFR = 8 };
@@ -107,6 +116,8 @@ struct tgb_step_args {
     int n_obst, model_obst_off;          /* static obstacles: n_obst pairs (static body, its box shape) at this word offset of model_i */
     int n_pairs, model_pair_off;         /* pairs of bodies that can collide (at least one dynamic): body A + 32 * body B, A < B, at this word offset of model_i */
     int pair_cap;                        /* rows of body-pair contacts per environment; 0 = bodies do not collide with each other */
+    void* warm;                          /* T[n_env][TGB_WARM_STATE_WORDS]: the persistent manifolds between launches, or NULL */
+    double warm_factor;                  /* btContactSolverInfo::m_warmstartingFactor (0.85); 0 = every solve starts from zero */
     float* min_clearance;                /* [n_env] running minimum of the surface distance between two bodies' capsules, or NULL */
     double dt;
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */

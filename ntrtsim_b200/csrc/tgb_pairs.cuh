@@ -146,9 +146,17 @@ TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance
 
 /* The contacts of one pair of capsules (bodies ia < ib) as rows base + count, ... of the environment's pair rows; `count` counts the rows
    of this pair of bodies (at most 4).  Mirrors the oracle's generateBodyPairContacts expression by expression. */
+/* where emission finds the persistent manifold of the environment's pair rows (tgb_dev.h TGB_WARM_*); entries == nullptr: no warm start */
 template <typename T>
-TGB_D void emitCapsulePair(const CoreSegment<T>& ga, const CoreSegment<T>& gb, int ia, int ib, T mu, T restitution, T* rows, int base, int cap,
-                           int& count) {
+struct PairWarm {
+    const T* entries; /* [cap][TGB_WARM_WORDS] */
+    int cap;
+    T factor;
+};
+
+template <typename T>
+TGB_D void emitCapsulePair(const CoreSegment<T>& ga, const CoreSegment<T>& gb, int ia, int ib, int saLocal, int sbLocal, T mu, T restitution,
+                           const PairWarm<T>& warm, T* rows, int base, int cap, int& count) {
     T s0, t0, b, c, f;
     closestSegmentParams<T>(ga, gb, s0, t0, b, c, f);
     T sp[2] = {s0, s0}, tp[2] = {t0, t0};
@@ -197,13 +205,23 @@ TGB_D void emitCapsulePair(const CoreSegment<T>& ga, const CoreSegment<T>& gb, i
         row[PR_RB + 0] = pB.x; row[PR_RB + 1] = pB.y; row[PR_RB + 2] = pB.z;
         row[PR_LAMN] = dist; row[PR_LAMPUSH] = restitution;
         row[PR_MU] = mu; row[PR_IDS] = (T)(ia + 32 * ib);
+        /* the point's impulses at the end of the last step, scaled (0 when the point is new) */
+        const T key = (T)((((ia + 32 * ib) * 64 + saLocal) * 64 + sbLocal) * 2 + k);
+        T wN = T(0), wT = T(0);
+        if (warm.entries != nullptr)
+            for (int j = 0; j < warm.cap; ++j) {
+                const T* e = warm.entries + j * TGB_WARM_WORDS;
+                if (e[0] == key) { wN = e[1] * warm.factor; wT = e[2] * warm.factor; }
+            }
+        row[PR_KEY] = key; row[PR_INVDIAGT] = wN; row[PR_RHST] = wT;
         ++count;
     }
 }
 
 /* Emission for bodies made of several shapes (compound bodies); out of line. */
 template <typename T, typename Model>
-__device__ __noinline__ int emitCompoundPairRows(const Model M, const T* sPose, int ia, int ib, T mu, T restitution, T* rows, int base, int cap) {
+__device__ __noinline__ int emitCompoundPairRows(const Model M, const T* sPose, int ia, int ib, T mu, T restitution, const PairWarm<T> warm, T* rows,
+                                                 int base, int cap) {
     const T* pa = sPose + 12 * ia;
     const T* pb = sPose + 12 * ib;
     int count = 0;
@@ -215,7 +233,7 @@ __device__ __noinline__ int emitCompoundPairRows(const Model M, const T* sPose, 
         for (int sb = sb0; sb < sb1; ++sb) {
             CoreSegment<T> gb;
             if (!coreSegment<T>(M, pb, sb, gb)) continue;
-            emitCapsulePair<T>(ga, gb, ia, ib, mu, restitution, rows, base, cap, count);
+            emitCapsulePair<T>(ga, gb, ia, ib, sa - sa0, sb - sb0, mu, restitution, warm, rows, base, cap, count);
         }
     }
     return count;
@@ -224,7 +242,7 @@ __device__ __noinline__ int emitCompoundPairRows(const Model M, const T* sPose, 
 /* Emission: the contacts of bodies (ia, ib) as rows base, base + 1, ... of the environment's pair rows; returns the number written.
    Two plain rods / balls in line, compound bodies out of line. */
 template <typename T, typename Model>
-TGB_D int emitPairRows(const Model& M, const T* sPose, int ia, int ib, T* rows, int base, int cap) {
+TGB_D int emitPairRows(const Model& M, const T* sPose, int ia, int ib, const PairWarm<T>& warm, T* rows, int base, int cap) {
     T mu = M.body(BF_FRICTION, ia) * M.body(BF_FRICTION, ib);
     mu = mu < T(-10) ? T(-10) : (mu > T(10) ? T(10) : mu);
     const T restitution = M.body(BF_RESTITUTION, ia) * M.body(BF_RESTITUTION, ib);
@@ -233,10 +251,10 @@ TGB_D int emitPairRows(const Model& M, const T* sPose, int ia, int ib, T* rows, 
         coreSegmentOfRod<T>(M, sPose + 12 * ia, ia, ga);
         coreSegmentOfRod<T>(M, sPose + 12 * ib, ib, gb);
         int count = 0;
-        emitCapsulePair<T>(ga, gb, ia, ib, mu, restitution, rows, base, cap, count);
+        emitCapsulePair<T>(ga, gb, ia, ib, 0, 0, mu, restitution, warm, rows, base, cap, count);
         return count;
     }
-    return emitCompoundPairRows<T>(M, sPose, ia, ib, mu, restitution, rows, base, cap);
+    return emitCompoundPairRows<T>(M, sPose, ia, ib, mu, restitution, warm, rows, base, cap);
 }
 
 /* solveCoupledReg is compiled for (own contact points per lane, pair rows per environment) = (1, 1) -- a rod end on the ground, one
@@ -278,6 +296,7 @@ __device__ __noinline__ void setupPairRows(unsigned mask, T* pr, int nPairRows, 
         const int po = isB ? PR_RB : PR_RA;
         const V3<T> r = V3<T>(row[po + 0], row[po + 1], row[po + 2]) - x;
         const T dist = row[PR_LAMN], combinedRestitution = row[PR_LAMPUSH];
+        const T warmN = row[PR_INVDIAGT], warmT = row[PR_RHST];
         const V3<T> rxn = r.cross(n);
         const V3<T> angN = Iinv * rxn;
         const T dN = invMass + n.dot(angN.cross(r));
@@ -328,8 +347,8 @@ __device__ __noinline__ void setupPairRows(unsigned mask, T* pr, int nPairRows, 
         if (isA) {
             row[PR_RA + 0] = r.x; row[PR_RA + 1] = r.y; row[PR_RA + 2] = r.z;
             row[PR_T + 0] = t.x; row[PR_T + 1] = t.y; row[PR_T + 2] = t.z;
-            row[PR_INVDIAGN] = invDiagN; row[PR_RHSN] = rhsN; row[PR_RHSPEN] = rhsPen; row[PR_LAMN] = T(0); row[PR_LAMPUSH] = T(0);
-            row[PR_INVDIAGT] = invDiagT; row[PR_RHST] = rhsT; row[PR_LAMT] = T(0);
+            row[PR_INVDIAGN] = invDiagN; row[PR_RHSN] = rhsN; row[PR_RHSPEN] = rhsPen; row[PR_LAMN] = warmN; row[PR_LAMPUSH] = T(0);
+            row[PR_INVDIAGT] = invDiagT; row[PR_RHST] = rhsT; row[PR_LAMT] = warmT;
         }
         if (isB) { row[PR_RB + 0] = r.x; row[PR_RB + 1] = r.y; row[PR_RB + 2] = r.z; }
     }
@@ -354,8 +373,8 @@ TGB_D bool groupHasPenetration(unsigned groupMask, bool anyPenOwn, const T* pr, 
    shuffle (the two sides' parts of its relative velocity).  Equal to the velocity-space iteration in exact arithmetic. */
 template <typename T, bool kFast, bool OBST, int NC, int PM>
 __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T* ct, int rowStride, int nc, bool anyPenOwn, V3<T> gn,
-                                                            T muGround, const T* pr, int nPairRows, int lane, int groupLane0, V3<T> x, M3<T> Iinv,
-                                                            T invMass, V3<T> vel, V3<T> w, V3<T> extLin, V3<T> extAng, T dt, int iterations
+                                                            T muGround, const T* pr, T* warmPair, int nPairRows, int lane, int groupLane0, V3<T> x,
+                                                            M3<T> Iinv, T invMass, V3<T> vel, V3<T> w, V3<T> extLin, V3<T> extAng, T dt, int iterations
 #ifdef TGB_STATS
                                                             , unsigned long long* statsP
 #endif
@@ -371,7 +390,7 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
     const int maxP = __reduce_max_sync(mask, nPairRows);
     /* ---- own rows (up to two contact points against the static world), as the step kernel set them up ---- */
     V3<T> on[NC], orxn[NC], oangN[NC], ot[NC], orxt[NC], oangT[NC];
-    T oInvN[NC], oRhsN[NC], oRhsPen[NC], oInvT[NC], oRhsT[NC], oMu[NC];
+    T oInvN[NC], oRhsN[NC], oRhsPen[NC], oInvT[NC], oRhsT[NC], oMu[NC], oWarmN[NC], oWarmT[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const int cc = c < nc ? c : 0; /* a lane without that row reads row 0 (or stale words) and never uses the result */
@@ -384,12 +403,14 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
         oInvN[c] = TGB_CTG(cc, CT_INVDIAGN); oRhsN[c] = TGB_CTG(cc, CT_RHSN); oRhsPen[c] = TGB_CTG(cc, CT_RHSPEN);
         oInvT[c] = TGB_CTG(cc, CT_INVDIAGT); oRhsT[c] = TGB_CTG(cc, CT_RHST);
         oMu[c] = OBST ? TGB_CTG(cc, CT_MU) : muGround;
+        oWarmN[c] = c < nc ? TGB_CTG(cc, CT_LAMN) : T(0); oWarmT[c] = c < nc ? TGB_CTG(cc, CT_LAMT) : T(0);
     }
     TGB_PAIR_TICK(105);
     /* ---- this lane's side of its environment's pair rows (setupContactConstraint / setupFrictionConstraint with two bodies):
        sign +1 (body A), -1 (body B) or 0 (not its row) ---- */
     V3<T> pn[PMAX], prxn[PMAX], pangN[PMAX], pt[PMAX], prxt[PMAX], pangT[PMAX];
     T pInvN[PMAX], pRhsN[PMAX], pRhsPen[PMAX], pInvT[PMAX], pRhsT[PMAX], pMu[PMAX], pSign[PMAX];
+    T pWarmN[PMAX], pWarmT[PMAX], pKey[PMAX]; /* warm starting: the point's scaled impulses of the last step, its identity */
     int pSrc[PMAX];
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) {
@@ -406,6 +427,8 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
         const V3<T> r = V3<T>(row[po + 0], row[po + 1], row[po + 2]) - x;
         const T dist = row[PR_LAMN], combinedRestitution = row[PR_LAMPUSH];
         pMu[p] = row[PR_MU];
+        pWarmN[p] = (isA || isB) ? row[PR_INVDIAGT] : T(0); pWarmT[p] = (isA || isB) ? row[PR_RHST] : T(0);
+        pKey[p] = row[PR_KEY];
         const V3<T> rxn = r.cross(n);
         const V3<T> angN = Iinv * rxn;
         const T dN = invMass + n.dot(angN.cross(r));
@@ -508,8 +531,18 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
         /* A row visit, written for the shortest dependent chain (dv -> fma -> max/min -> subtract -> fma into the next row's dv):
            new impulse = clamp(lam + rhs - dv invD) with lam + rhs kept ready from the row's previous visit. */
         T lam[K], dv[K], base[K];
+        /* warm starting: the rows start from their scaled impulses of the last step; every row's relative velocity part follows */
 #pragma unroll
-        for (int i = 0; i < K; ++i) { lam[i] = T(0); dv[i] = T(0); base[i] = rhs[i]; }
+        for (int c = 0; c < NC; ++c) { lam[c] = oWarmN[c]; lam[NC + c] = oWarmT[c]; }
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) { lam[PN + p] = pWarmN[p]; lam[PT + p] = pWarmT[p]; }
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            T v = T(0);
+#pragma unroll
+            for (int j = 0; j < K; ++j) v = fmaf(W[i][j], lam[j], v);
+            dv[i] = v; base[i] = lam[i] + rhs[i];
+        }
         if (anyPen) {
             /* split impulse: the normal rows alone, their own impulses and relative velocities; a row without it has rhsP = 0 and stays 0 */
             T lamP[K], dvP[K];
@@ -586,14 +619,40 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
         TGB_PAIR_TICK(109);
 #pragma unroll
         for (int i = 0; i < K; ++i) { dLin += bl[i] * lam[i]; dAng += ba[i] * lam[i]; }
+        /* the final impulses: own rows back into the rows, pair rows into the persistent manifold (by the lane of body A) */
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (c < nc) { TGB_CTG(c, CT_LAMN) = lam[c]; TGB_CTG(c, CT_LAMT) = lam[NC + c]; }
+        if (warmPair != nullptr) {
+#pragma unroll
+            for (int p = 0; p < PMAX; ++p)
+                if (pSign[p] > T(0)) { warmPair[p * TGB_WARM_WORDS] = pKey[p]; warmPair[p * TGB_WARM_WORDS + 1] = lam[PN + p]; warmPair[p * TGB_WARM_WORDS + 2] = lam[PT + p]; }
+        }
     } else {
         /* ---- velocity space, the oracle's operations in the oracle's order ---- */
         T oLamN[NC], oLamT[NC], oLamPush[NC];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) { oLamN[c] = T(0); oLamT[c] = T(0); oLamPush[c] = T(0); }
         T pLamN[PMAX], pLamT[PMAX], pLamPush[PMAX];
+        /* warm starting: the rows' scaled impulses of the last step act on the body straight away, row by row in the oracle's order */
 #pragma unroll
-        for (int p = 0; p < PMAX; ++p) { pLamN[p] = T(0); pLamT[p] = T(0); pLamPush[p] = T(0); }
+        for (int c = 0; c < NC; ++c) {
+            oLamN[c] = oWarmN[c]; oLamT[c] = oWarmT[c]; oLamPush[c] = T(0);
+            if (c < nc) {
+                dLin += on[c] * (invMass * oLamN[c]) + ot[c] * (invMass * oLamT[c]);
+                dAng += oangN[c] * oLamN[c] + oangT[c] * oLamT[c];
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p) {
+            pLamN[p] = pWarmN[p]; pLamT[p] = pWarmT[p]; pLamPush[p] = T(0);
+            if (pSign[p] > T(0)) {
+                dLin += pn[p] * (invMass * pLamN[p]) + pt[p] * (invMass * pLamT[p]);
+                dAng += pangN[p] * pLamN[p] + pangT[p] * pLamT[p];
+            }
+            if (pSign[p] < T(0)) {
+                dLin -= pn[p] * (invMass * pLamN[p]) + pt[p] * (invMass * pLamT[p]);
+                dAng -= pangN[p] * pLamN[p] + pangT[p] * pLamT[p];
+            }
+        }
         /* one visit of a normal-type row of this lane's own */
         auto ownNormal = [&](int c, T rhsv, T& lamv, V3<T>& lin, V3<T>& ang) {
             T delta = rhsv;
@@ -674,6 +733,15 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
                     }
                 }
         }
+        /* the final impulses: own rows back into the rows, pair rows into the persistent manifold (by the lane of body A) */
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (c < nc) { TGB_CTG(c, CT_LAMN) = oLamN[c]; TGB_CTG(c, CT_LAMT) = oLamT[c]; }
+        if (warmPair != nullptr) {
+#pragma unroll
+            for (int p = 0; p < PMAX; ++p)
+                if (pSign[p] > T(0)) { warmPair[p * TGB_WARM_WORDS] = pKey[p]; warmPair[p * TGB_WARM_WORDS + 1] = pLamN[p]; warmPair[p * TGB_WARM_WORDS + 2] = pLamT[p]; }
+        }
     }
     ContactSolveOut<T> o;
     o.dLin = dLin; o.dAng = dAng; o.push = push; o.turn = turn;
@@ -682,12 +750,35 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
 
 template <typename T, bool kFast, bool OBST>
 __device__ __noinline__ ContactSolveOut<T> solveCoupledMem(unsigned mask, unsigned groupMask, T* ct, int rowStride, int nc, bool anyPenOwn, V3<T> gn,
-                                                            T muGround, T* pr, int nPairRows, int lane, int groupLane0, M3<T> Iinv, T invMass,
-                                                            int iterations) {
+                                                            T muGround, T* pr, T* warmPair, int nPairRows, int lane, int groupLane0, M3<T> Iinv,
+                                                            T invMass, int iterations) {
     const int warpLane = groupLane0 + lane;
     const int maxP = __reduce_max_sync(mask, nPairRows);
     const bool anyPen = __any_sync(mask, groupHasPenetration<T>(groupMask, anyPenOwn, pr, nPairRows));
     V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
+    /* warm starting: the rows' initial impulses (as the set-up left them in the rows) act on the bodies straight away */
+    for (int c = 0; c < nc; ++c) {
+        const T lamN0 = TGB_CTG(c, CT_LAMN), lamT0 = TGB_CTG(c, CT_LAMT);
+        const V3<T> n = OBST ? V3<T>(TGB_CTG(c, CT_NRM + 0), TGB_CTG(c, CT_NRM + 1), TGB_CTG(c, CT_NRM + 2)) : gn;
+        const V3<T> t(TGB_CTG(c, CT_T + 0), TGB_CTG(c, CT_T + 1), TGB_CTG(c, CT_T + 2));
+        const V3<T> angN(TGB_CTG(c, CT_ANGN + 0), TGB_CTG(c, CT_ANGN + 1), TGB_CTG(c, CT_ANGN + 2));
+        const V3<T> angT(TGB_CTG(c, CT_ANGT + 0), TGB_CTG(c, CT_ANGT + 1), TGB_CTG(c, CT_ANGT + 2));
+        dLin += n * (invMass * lamN0) + t * (invMass * lamT0);
+        dAng += angN * lamN0 + angT * lamT0;
+    }
+    for (int p = 0; p < nPairRows; ++p) {
+        const T* row = pr + p * TGB_NPR;
+        const int ids = (int)row[PR_IDS];
+        const bool isA = lane == (ids & 31), isB = lane == (ids >> 5);
+        if (!isA && !isB) continue;
+        const V3<T> n(row[PR_N + 0], row[PR_N + 1], row[PR_N + 2]), t(row[PR_T + 0], row[PR_T + 1], row[PR_T + 2]);
+        const int po = isB ? PR_RB : PR_RA;
+        const V3<T> r(row[po + 0], row[po + 1], row[po + 2]);
+        const T lamN0 = row[PR_LAMN], lamT0 = row[PR_LAMT];
+        const V3<T> lin = n * (invMass * lamN0) + t * (invMass * lamT0);
+        const V3<T> ang = (Iinv * r.cross(n)) * lamN0 + (Iinv * r.cross(t)) * lamT0;
+        if (isA) { dLin += lin; dAng += ang; } else { dLin -= lin; dAng -= ang; }
+    }
     auto pairVisit = [&](int p, int rhsField, int lamField, bool friction, V3<T>& lin, V3<T>& ang) {
         const bool have = p < nPairRows;
         T* row = pr + (have ? p : 0) * TGB_NPR;
@@ -785,6 +876,14 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledMem(unsigned mask, unsign
         for (int p = 0; p < maxP; ++p) pairVisit(p, PR_RHST, PR_LAMT, true, dLin, dAng);
         __syncwarp(mask);
     }
+    /* the pair rows' final impulses into the persistent manifold (by the lane of body A) */
+    if (warmPair != nullptr)
+        for (int p = 0; p < nPairRows; ++p) {
+            const T* row = pr + p * TGB_NPR;
+            if (lane == ((int)row[PR_IDS] & 31)) {
+                warmPair[p * TGB_WARM_WORDS] = row[PR_KEY]; warmPair[p * TGB_WARM_WORDS + 1] = row[PR_LAMN]; warmPair[p * TGB_WARM_WORDS + 2] = row[PR_LAMT];
+            }
+        }
     ContactSolveOut<T> o;
     o.dLin = dLin; o.dAng = dAng; o.push = push; o.turn = turn;
     return o;

@@ -159,6 +159,15 @@ template <typename T>
 __device__ __forceinline__ void pgsSharedRows(T* ct, int rowStride, int nc, int iterations, bool anyPen, V3<T> gn, T invMass, T mu,
                                            V3<T>& dLin, V3<T>& dAng, V3<T>& push, V3<T>& turn) {
 #define CTG(slot, f) ct[(slot) * rowStride + (f)]
+    /* warm starting: the rows' initial impulses (CT_LAMN / CT_LAMT as the row set-up left them) act on the body straight away */
+    for (int c = 0; c < nc; ++c) {
+        const T lamN0 = CTG(c, CT_LAMN), lamT0 = CTG(c, CT_LAMT);
+        const V3<T> t(CTG(c, CT_T + 0), CTG(c, CT_T + 1), CTG(c, CT_T + 2));
+        const V3<T> angN(CTG(c, CT_ANGN + 0), CTG(c, CT_ANGN + 1), CTG(c, CT_ANGN + 2));
+        const V3<T> angT(CTG(c, CT_ANGT + 0), CTG(c, CT_ANGT + 1), CTG(c, CT_ANGT + 2));
+        dLin += gn * (invMass * lamN0) + t * (invMass * lamT0);
+        dAng += angN * lamN0 + angT * lamT0;
+    }
     if (anyPen)
         for (int it = 0; it < iterations; ++it) {
             for (int c = 0; c < nc; ++c) {
@@ -222,6 +231,16 @@ template <typename T>
 __device__ __noinline__ void pgsRowsWithNormals(T* ct, int rowStride, int nc, int iterations, bool anyPen, T invMass,
                                                 V3<T>& dLin, V3<T>& dAng, V3<T>& push, V3<T>& turn) {
 #define CTG(slot, f) ct[(slot) * rowStride + (f)]
+    /* warm starting: the rows' initial impulses act on the body straight away */
+    for (int c = 0; c < nc; ++c) {
+        const T lamN0 = CTG(c, CT_LAMN), lamT0 = CTG(c, CT_LAMT);
+        const V3<T> n(CTG(c, CT_NRM + 0), CTG(c, CT_NRM + 1), CTG(c, CT_NRM + 2));
+        const V3<T> t(CTG(c, CT_T + 0), CTG(c, CT_T + 1), CTG(c, CT_T + 2));
+        const V3<T> angN(CTG(c, CT_ANGN + 0), CTG(c, CT_ANGN + 1), CTG(c, CT_ANGN + 2));
+        const V3<T> angT(CTG(c, CT_ANGT + 0), CTG(c, CT_ANGT + 1), CTG(c, CT_ANGT + 2));
+        dLin += n * (invMass * lamN0) + t * (invMass * lamT0);
+        dAng += angN * lamN0 + angT * lamT0;
+    }
     if (anyPen)
         for (int it = 0; it < iterations; ++it) {
             for (int c = 0; c < nc; ++c) {
@@ -343,7 +362,8 @@ __device__ __noinline__ ContactSolveOut<T> solveContactsGeneral(T* ct, int rowSt
             }
             invDiagN[c] = ct[(cc) * rowStride + (CT_INVDIAGN)]; rhsN[c] = ct[(cc) * rowStride + (CT_RHSN)]; rhsPen[c] = ct[(cc) * rowStride + (CT_RHSPEN)];
             invDiagT[c] = ct[(cc) * rowStride + (CT_INVDIAGT)]; rhsT[c] = ct[(cc) * rowStride + (CT_RHST)];
-            lamN[c] = T(0); lamPush[c] = T(0); lamT[c] = T(0);
+            /* warm starting: the initial impulses the row set-up left in the row */
+            lamN[c] = c < nc ? ct[(cc) * rowStride + (CT_LAMN)] : T(0); lamPush[c] = T(0); lamT[c] = c < nc ? ct[(cc) * rowStride + (CT_LAMT)] : T(0);
         }
         if (anyPen)
             for (int it = 0; it < iterations; ++it) {
@@ -389,6 +409,9 @@ __device__ __noinline__ ContactSolveOut<T> solveContactsGeneral(T* ct, int rowSt
                     A[r][q] = v;
                     A[q][r] = v;
                 }
+            /* warm starting: the rows' relative velocity changes under the initial impulses (rows N0, N1, T0, T1) */
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dv[r] = (A[r][0] * lamN[0] + A[r][1] * lamN[1]) + (A[r][2] * lamT[0] + A[r][3] * lamT[1]);
             for (int it = 0; it < iterations; ++it) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
@@ -420,7 +443,14 @@ __device__ __noinline__ ContactSolveOut<T> solveContactsGeneral(T* ct, int rowSt
                 dLin += V3<T>(bl[c][0], bl[c][1], bl[c][2]) * lamN[c] + V3<T>(bl[2 + c][0], bl[2 + c][1], bl[2 + c][2]) * lamT[c];
                 dAng += V3<T>(ba[c][0], ba[c][1], ba[c][2]) * lamN[c] + V3<T>(ba[2 + c][0], ba[2 + c][1], ba[2 + c][2]) * lamT[c];
             }
-        } else
+        } else {
+        /* warm starting: the initial impulses act on the body straight away (contact by contact, the oracle's order) */
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (c >= nc) continue;
+            dLin += gn * (invMass * lamN[c]) + V3<T>(tt[c][0], tt[c][1], tt[c][2]) * (invMass * lamT[c]);
+            dAng += V3<T>(angN[c][0], angN[c][1], angN[c][2]) * lamN[c] + V3<T>(angT[c][0], angT[c][1], angT[c][2]) * lamT[c];
+        }
         for (int it = 0; it < iterations; ++it) {
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -450,6 +480,11 @@ __device__ __noinline__ ContactSolveOut<T> solveContactsGeneral(T* ct, int rowSt
                 dAng += V3<T>(angT[c][0], angT[c][1], angT[c][2]) * delta;
             }
         }
+        }
+        /* the final impulses go back into the rows: the persistent manifold keeps them for the next step */
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (c < nc) { ct[c * rowStride + CT_LAMN] = lamN[c]; ct[c * rowStride + CT_LAMT] = lamT[c]; }
     } else {
         pgsSharedRows<T>(ct, rowStride, nc, iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
     }
@@ -593,7 +628,11 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     const int exchangeWords = TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords;
     /* body pairs: per pair the slack left before it has to be tested again, per body the motion bound of the last step (tgb_pairs.cuh) */
     const int pairKeepWords = a.n_pairs > 0 ? a.n_pairs + LPE : 0;
-    int groupTWords = a.stride + poseWords + exchangeWords + pairKeepWords;
+    /* persistent manifolds (warm starting): the rows' impulses of the last world step, see TGB_WARM_* in tgb_dev.h */
+    const bool warmOn = a.warm != nullptr && a.warm_factor > 0.0;
+    const int warmPairCap = (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap : 0;
+    const int warmWords = a.warm != nullptr ? TGB_WARM_STATE_WORDS(a.cap_contacts, rowBodies, warmPairCap) : 0;
+    int groupTWords = a.stride + poseWords + exchangeWords + pairKeepWords + warmWords;
     groupTWords = (groupTWords + 3) & ~3;
     /* keep group regions LPE banks apart so that the groups of one warp do not collide */
     if (LPE < 32) { while ((groupTWords & 31) != (LPE < 4 ? 4 : LPE)) groupTWords += 4; }
@@ -605,6 +644,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     T* sPairRows = sCt + ctOnlyWords;               /* [pair_cap][TGB_NPR] */
     T* sPairSlack = sJ + exchangeWords;             /* [n_pairs], then [LPE] motion bounds */
     T* sMotion = sPairSlack + a.n_pairs;
+    T* sWarm = sPairSlack + pairKeepWords;          /* [cap_contacts][row bodies][3], then [pair_cap][3] */
+    T* sWarmPair = sWarm + TGB_WARM_WORDS * a.cap_contacts * rowBodies;
     constexpr bool cpgOn = CLASS == TGB_CLASS_CPG;
     constexpr bool sineOn = CLASS == TGB_CLASS_SINE;
     constexpr bool simpleOn = CLASS == TGB_CLASS_SIMPLE;
@@ -647,6 +688,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         for (int i = lane; i < a.stride / VN; i += LPE) ss[i] = gs[i];
         if (a.ctrl != nullptr)
             for (int i = lane; i < a.ctrl_stride; i += LPE) sCtrl[i] = a.ctrl[(size_t)env * a.ctrl_stride + i];
+        if (a.warm != nullptr && bodyWarp) {
+            const T* gw = reinterpret_cast<const T*>(a.warm) + (size_t)env * warmWords;
+            for (int i = lane; i < warmWords; i += LPE) sWarm[i] = gw[i];
+        }
     }
     __syncthreads();
 
@@ -776,6 +821,16 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         rowIdx = __popc(dynMask & ((1u << warpLane) - 1u) & ~((1u << groupLane0) - 1u));
     }
 #define CT(slot, f) sCt[((slot) * rowBodies + rowIdx) * NCT + (f)]
+    /* the impulses this body's manifold point `key` ended the last world step with, scaled by the warm starting factor (0 when new) */
+    const T warmFactor = (T)a.warm_factor;
+    auto warmLookup = [&](T key, T& wN, T& wT) {
+        wN = T(0); wT = T(0);
+        if (!warmOn) return;
+        for (int j = 0; j < a.cap_contacts; ++j) {
+            const T* e = sWarm + (j * rowBodies + rowIdx) * TGB_WARM_WORDS;
+            if (e[0] == key) { wN = e[1] * warmFactor; wT = e[2] * warmFactor; }
+        }
+    };
 
     /* ---- CPG: CPGNode::updateDTs for this lane's nodes (CPGNode.cpp:71-88). Every lane of the warp calls this the same
        number of times (it synchronises); `act` masks groups that have nothing to do. sin(phi_j - phi_i - theta) is
@@ -917,6 +972,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
     T pairClearance = T(1e30); /* smallest surface distance of two bodies' capsules this lane has seen */
+    int prevNc = a.cap_contacts, prevPairRows = (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap : 0; /* rows of the last world step (upper bounds at launch) */
 #ifdef TGB_STATS
     const long long statT0 = clock64();
     unsigned long long wCoupled = 0, wCoupledCyc = 0, wDetectCyc = 0, wMem = 0, wMany = 0, wCableCyc = 0;
@@ -931,6 +987,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         V3<T> extLin(T(0), T(0), T(0)), extAng(T(0), T(0), T(0)), linvel(T(0), T(0), T(0));
         int nc = 0;
         bool anyPen = false;
+        bool anyWarm = false; /* a row of this body starts from a non-zero impulse */
         /* ---- contact between bodies: detection from the published poses (tgb_pairs.cuh).  Every lane of the body warp takes part; the
            lanes of a group take the environment's body pairs round robin.  nPairRows stays 0 unless a pair is within the contact band. */
         int nPairRows = 0;
@@ -971,7 +1028,11 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     const int L = __ffs(nearMask) - 1;
                     nearMask &= nearMask - 1u;
                     int cnt = 0;
-                    if (warpLane == L) cnt = emitPairRows<T>(M, sPose, ia, ib, sPairRows, nPairRows, a.pair_cap);
+                    if (warpLane == L) {
+                        PairWarm<T> pw;
+                        pw.entries = warmOn ? sWarmPair : nullptr; pw.cap = a.pair_cap; pw.factor = (T)a.warm_factor;
+                        cnt = emitPairRows<T>(M, sPose, ia, ib, pw, sPairRows, nPairRows, a.pair_cap);
+                    }
 #ifdef TGB_STATS
                     ++statEmits;
 #endif
@@ -1154,11 +1215,16 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 CT(nc, CT_RXN + 0) = rxn.x; CT(nc, CT_RXN + 1) = rxn.y; CT(nc, CT_RXN + 2) = rxn.z;
                                 CT(nc, CT_ANGN + 0) = angN.x; CT(nc, CT_ANGN + 1) = angN.y; CT(nc, CT_ANGN + 2) = angN.z;
                                 CT(nc, CT_INVDIAGN) = invDiagN; CT(nc, CT_RHSN) = rhsN; CT(nc, CT_RHSPEN) = rhsPen;
-                                CT(nc, CT_LAMN) = T(0); CT(nc, CT_LAMPUSH) = T(0);
+                                const T key = (T)((si - shapeBegin) * 8 + slot);
+                                T warmN, warmT;
+                                warmLookup(key, warmN, warmT);
+                                CT(nc, CT_LAMN) = warmN; CT(nc, CT_LAMPUSH) = T(0);
+                                if (warmOn) CT(nc, CT_KEY) = key;
                                 CT(nc, CT_T + 0) = t.x; CT(nc, CT_T + 1) = t.y; CT(nc, CT_T + 2) = t.z;
                                 CT(nc, CT_RXT + 0) = rxt.x; CT(nc, CT_RXT + 1) = rxt.y; CT(nc, CT_RXT + 2) = rxt.z;
                                 CT(nc, CT_ANGT + 0) = angT.x; CT(nc, CT_ANGT + 1) = angT.y; CT(nc, CT_ANGT + 2) = angT.z;
-                                CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = T(0);
+                                CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = warmT;
+                                anyWarm = anyWarm || warmN != T(0) || warmT != T(0);
                                 if constexpr (OBST) {
                                     CT(nc, CT_NRM + 0) = gn.x; CT(nc, CT_NRM + 1) = gn.y; CT(nc, CT_NRM + 2) = gn.z; CT(nc, CT_MU) = mu;
                                 }
@@ -1270,11 +1336,16 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 CT(nc, CT_RXN + 0) = rxn.x; CT(nc, CT_RXN + 1) = rxn.y; CT(nc, CT_RXN + 2) = rxn.z;
                                 CT(nc, CT_ANGN + 0) = angN.x; CT(nc, CT_ANGN + 1) = angN.y; CT(nc, CT_ANGN + 2) = angN.z;
                                 CT(nc, CT_INVDIAGN) = invDiagN; CT(nc, CT_RHSN) = rhsN; CT(nc, CT_RHSPEN) = rhsPen;
-                                CT(nc, CT_LAMN) = T(0); CT(nc, CT_LAMPUSH) = T(0);
+                                const T key = (T)(TGB_WARM_OBST + (oi * 64 + (si - shapeBegin)) * 8 + k);
+                                T warmN, warmT;
+                                warmLookup(key, warmN, warmT);
+                                CT(nc, CT_LAMN) = warmN; CT(nc, CT_LAMPUSH) = T(0);
+                                if (warmOn) CT(nc, CT_KEY) = key;
                                 CT(nc, CT_T + 0) = t.x; CT(nc, CT_T + 1) = t.y; CT(nc, CT_T + 2) = t.z;
                                 CT(nc, CT_RXT + 0) = rxt.x; CT(nc, CT_RXT + 1) = rxt.y; CT(nc, CT_RXT + 2) = rxt.z;
                                 CT(nc, CT_ANGT + 0) = angT.x; CT(nc, CT_ANGT + 1) = angT.y; CT(nc, CT_ANGT + 2) = angT.z;
-                                CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = T(0);
+                                CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = warmT;
+                                anyWarm = anyWarm || warmN != T(0) || warmT != T(0);
                                 CT(nc, CT_NRM + 0) = n.x; CT(nc, CT_NRM + 1) = n.y; CT(nc, CT_NRM + 2) = n.z; CT(nc, CT_MU) = obstMu;
                                 ++nc;
                                 ++count;
@@ -1315,7 +1386,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 if (reg1Mask != 0u) {
                     const ContactSolveOut<T> o1 = solveCoupledReg<T, kFast, OBST, 1, 1>(
                         groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, inReg1 ? ncMine : 0, inReg1 && mine && anyPen, gn, mu, sPairRows,
-                        inReg1 ? nPairRows : 0, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt,
+                        warmOn ? sWarmPair : nullptr, inReg1 ? nPairRows : 0, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt,
                         a.iterations
 #ifdef TGB_STATS
                         , a.stats
@@ -1326,7 +1397,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 if (reg2Mask != 0u) {
                     const ContactSolveOut<T> o2 = solveCoupledReg<T, kFast, OBST, 2, TGB_PAIR_REG_ROWS>(
                         groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, inReg2 ? ncMine : 0, inReg2 && mine && anyPen, gn, mu, sPairRows,
-                        inReg2 ? nPairRows : 0, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt,
+                        warmOn ? sWarmPair : nullptr, inReg2 ? nPairRows : 0, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt,
                         a.iterations
 #ifdef TGB_STATS
                         , a.stats
@@ -1338,7 +1409,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     setupPairRows<T, kFast>(memMask, sPairRows, nPairRows, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0),
                                             kFast ? b.v : linvel, b.w, extLin, extAng, dt);
                     o = solveCoupledMem<T, kFast, OBST>(memMask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine, mine && anyPen, gn, mu,
-                                                        sPairRows, nPairRows, lane, groupLane0, b.Iinv, mine ? invMass : T(0), a.iterations);
+                                                        sPairRows, warmOn ? sWarmPair : nullptr, nPairRows, lane, groupLane0, b.Iinv,
+                                                        mine ? invMass : T(0), a.iterations);
                 }
                 if (coupled) {
                     dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
@@ -1390,7 +1462,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     push = bn * lamPush;
                     turn = angN * lamPush;
                 }
+                /* warm starting: the normal row's own diagonal cancels its initial impulse out of the iteration above; the friction
+                   impulse enters through the first normal update (and stays if the normal impulse never becomes positive) */
                 T lamN = T(0), lamT = T(0);
+                if (warmOn) { lamN = CT(0, CT_LAMN); lamT = CT(0, CT_LAMT); }
                 for (int it = 0; it < a.iterations; ++it) {
                     const T sumN = rhsN - kN * lamT;
                     lamN = sumN < T(0) ? T(0) : sumN;
@@ -1402,6 +1477,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 }
                 dLin = bn * lamN + bt * lamT;
                 dAng = angN * lamN + angT * lamT;
+                if (warmOn) { CT(0, CT_LAMN) = lamN; CT(0, CT_LAMT) = lamT; }
             } else if (OBST) {
                 if (nc > 0) pgsRowsWithNormals<T>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
             } else if (nc > 0) {
@@ -1409,6 +1485,23 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
             }
 
+            /* ---- the persistent manifold of the next step: this step's rows with their final impulses (every solver above leaves them
+               in the rows); slots beyond them are emptied ---- */
+            if (warmOn) {
+                if (dynamic) {
+                    const int n = nc > prevNc ? nc : prevNc;
+                    for (int j = 0; j < n; ++j) {
+                        T* e = sWarm + (j * rowBodies + rowIdx) * TGB_WARM_WORDS;
+                        if (j < nc) { e[0] = CT(j, CT_KEY); e[1] = CT(j, CT_LAMN); e[2] = CT(j, CT_LAMT); }
+                        else e[0] = T(-1);
+                    }
+                    prevNc = nc;
+                }
+                if (a.n_pairs > 0 && bodyWarp) { /* nPairRows, prevPairRows: uniform within the group */
+                    for (int p = nPairRows + lane; p < prevPairRows; p += LPE) sWarmPair[p * TGB_WARM_WORDS] = T(-1);
+                    prevPairRows = nPairRows;
+                }
+            }
             /* ---- write back, split-impulse correction, integrateTransforms ---- */
             if (dynamic) {
                 b.v = (b.v + dLin) + extLin;
@@ -1891,6 +1984,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         vec_t* gs = reinterpret_cast<vec_t*>(reinterpret_cast<T*>(a.state) + (size_t)env * a.stride);
         const vec_t* ss = reinterpret_cast<const vec_t*>(sState);
         for (int i = lane; i < a.stride / VN; i += LPE) gs[i] = ss[i];
+        if (a.warm != nullptr && doWorld) {
+            T* gw = reinterpret_cast<T*>(a.warm) + (size_t)env * warmWords;
+            for (int i = lane; i < warmWords; i += LPE) gw[i] = sWarm[i];
+        }
         if (cpgOn) {
             double* cs = a.cpg_state + (size_t)env * TGB_CPG_STATE_DOUBLES(C);
             for (int i = lane; i < 3 * C; i += LPE) { cs[i] = sX[i]; cs[3 * C + 2 + i] = sPid[i]; }
@@ -1917,7 +2014,8 @@ inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, 
     const int modelTWords = (a.model_t_words + 3) & ~3;
     const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C;
     const int ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST * a.n_dyn : (int)TGB_NCT * a.R) + ((a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap * (int)TGB_NPR : 0);
-    int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords) + (a.n_pairs > 0 ? a.n_pairs + lpe : 0);
+    int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords) + (a.n_pairs > 0 ? a.n_pairs + lpe : 0) +
+                      (a.warm != nullptr ? TGB_WARM_STATE_WORDS(a.cap_contacts, a.n_obst > 0 ? a.n_dyn : a.R, (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap : 0) : 0);
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
     const int groupDWords = tgb_group_double_words(a);

@@ -231,7 +231,7 @@ struct tgo_world {
        btSequentialImpulseConstraintSolver starts the next solve from them scaled by btContactSolverInfo::m_warmstartingFactor = 0.85,
        SOLVER_USE_WARMSTARTING is on by default).  A point keeps its identity through its slot: (shape, rim point) against the ground,
        (obstacle shape, shape, sample) against an obstacle, (shape, shape, point) between two bodies.  0 = every solve starts from zero. */
-    double warmStart = 0.85;
+    double warmStart = 0.0; /* same default as the device library (TGB_DEFAULT_WARM_STARTING, see include/ntrtsim_b200.h for why) */
     struct Cached { double lamN, lamT; };
     std::vector<std::pair<long long, Cached> > manifoldCache; /* of the last step, keyed (key, body) packed */
     int pairCap = 6;            /* rows of body-pair contacts per environment (tgb_set_pair_contact_cap); 0 = bodies do not collide */
