@@ -308,6 +308,7 @@ void packModel(const tgb_world* w, std::vector<unsigned char>& tbytes, std::vect
    in 2.3 waves).  Automatic choice: wide when the whole grid is resident.  tgb_set_wide_layout / TGB_WIDE=0|1 override. */
 bool wideLayout(const tgb_world* w) {
     if (w->ctrlKind == TGB_CTRL_CPG_IMPEDANCE || w->nObst > 0) return false;
+    if (w->warmFactor > 0.0) return false; /* the persistent manifolds are compiled for the narrow layout only */
     if (w->lanes != 4 && w->lanes != 8) return false;
     if (w->wideMode >= 0) return w->wideMode != 0;
     static const char* envWide = std::getenv("TGB_WIDE");

@@ -35,19 +35,26 @@ struct SmemAttrCache {
     }
 };
 
-template <int LPE, bool GROUND, bool OBST = false>
-cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
+template <int LPE, bool GROUND, bool OBST, bool WARM>
+cudaError_t launch_inst(const tgb_step_args& a, int threads, cudaStream_t s) {
     const size_t smem = tgb::tgb_step_smem_bytes(a, LPE, threads, sizeof(scalar_t));
     static SmemAttrCache cache;
     {
-        cudaError_t e = cache.ensure(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST>, smem);
+        cudaError_t e = cache.ensure(tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST, WARM>, smem);
         if (e != cudaSuccess) return e;
     }
     const int groupsPerBlock = threads / LPE;
     const int grid = (a.n_env - a.env_begin + groupsPerBlock - 1) / groupsPerBlock;
     if (grid <= 0) return cudaSuccess;
-    tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST><<<grid, threads, smem, s>>>(a);
+    tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST, WARM><<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+/* the persistent-manifold instantiation only when the world asks for warm starting (tgb_step_args.warm) */
+template <int LPE, bool GROUND, bool OBST = false>
+cudaError_t launch_impl(const tgb_step_args& a, int threads, cudaStream_t s) {
+    if (a.warm != nullptr) return launch_inst<LPE, GROUND, OBST, true>(a, threads, s);
+    return launch_inst<LPE, GROUND, OBST, false>(a, threads, s);
 }
 
 /* one cache per instantiation of the four-warp layout, shared by its launch and its occupancy query */

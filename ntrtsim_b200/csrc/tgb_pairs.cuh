@@ -38,6 +38,8 @@ namespace tgb {
 #endif
 
 template <typename T> struct ContactSolveOut { V3<T> dLin, dAng, push, turn; };
+/* result of solveCoupledWarp: `solved` = the lane's environment was coupled and `o` is its result; statMem: instrumentation only */
+template <typename T> struct CoupledOut { ContactSolveOut<T> o; bool solved; bool statMem; };
 
 template <typename T> TGB_D T pairBreakingThreshold() { return T(0.02); }
 template <typename T> TGB_D T pairParallel() { return T(1e-4); }
@@ -96,8 +98,18 @@ TGB_D void closestSegmentParams(const CoreSegment<T>& A, const CoreSegment<T>& B
 /* Detection: the smallest surface distance `dist` between the capsules of bodies (ia, ib) (a lower bound from the bounding spheres
    when those are apart); returns whether a pair of shapes is within the contact band (1e-3 of slack for round-off: emitPairRows
    applies the exact test).  Also folds the distance into the running minimum `clearance`. */
+/* A contact found by the detection itself (two plain rods / balls, one point): what emitCapsulePair would compute again.  valid = false:
+   the pair takes emitPairRows (compound bodies, the two-point manifold of parallel rods, axes that meet). */
+template <typename T>
+struct PairRecord {
+    bool valid;
+    V3<T> n, pA, pB;
+    T dist;
+};
+
 template <typename T, typename Model>
-TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance, T& dist) {
+TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance, T& dist, PairRecord<T>& rec) {
+    rec.valid = false;
     const T* pa = sPose + 12 * ia;
     const T* pb = sPose + 12 * ib;
     {
@@ -115,11 +127,21 @@ TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance
         coreSegmentOfRod<T>(M, pb, ib, gb);
         T s, t, b, c, f;
         closestSegmentParams<T>(ga, gb, s, t, b, c, f);
-        const V3<T> dv = (ga.p + ga.d * s) - (gb.p + gb.d * t);
-        const T dd = tsqrtNoBranch(dv.length2()) - ga.r - gb.r;
+        const V3<T> ca = ga.p + ga.d * s, cb = gb.p + gb.d * t;
+        const V3<T> dv = ca - cb;
+        const T d = tsqrtNoBranch(dv.length2()); /* double: sqrt, as in emitCapsulePair */
+        const T dd = d - ga.r - gb.r;
         clearance = dd < clearance ? dd : clearance;
         dist = dd;
-        return dd <= pairBreakingThreshold<T>() + T(1e-3);
+        const bool near = dd <= pairBreakingThreshold<T>() + T(1e-3);
+        if (near && d > T(1e-9) && !(ga.h > T(0) && gb.h > T(0) && T(1) - b * b < pairParallel<T>())) {
+            /* the one contact of this pair, with emitCapsulePair's operations */
+            rec.valid = true;
+            rec.n = dv * trcp(d);
+            rec.pA = ca - rec.n * ga.r; rec.pB = cb + rec.n * gb.r;
+            rec.dist = dd;
+        }
+        return near;
     }
     bool near = false;
     T best = T(1e30);
@@ -218,6 +240,29 @@ TGB_D void emitCapsulePair(const CoreSegment<T>& ga, const CoreSegment<T>& gb, i
     }
 }
 
+/* Emission of the contact the detection already holds (PairRecord): row `base` of the environment's pair rows; returns the rows written */
+template <typename T, typename Model>
+TGB_D int emitRecordedPair(const Model& M, const PairRecord<T>& rec, int ia, int ib, const PairWarm<T>& warm, T* rows, int base, int cap) {
+    if (rec.dist > pairBreakingThreshold<T>() || base >= cap) return 0;
+    T mu = M.body(BF_FRICTION, ia) * M.body(BF_FRICTION, ib);
+    mu = mu < T(-10) ? T(-10) : (mu > T(10) ? T(10) : mu);
+    T* row = rows + base * TGB_NPR;
+    row[PR_N + 0] = rec.n.x; row[PR_N + 1] = rec.n.y; row[PR_N + 2] = rec.n.z;
+    row[PR_RA + 0] = rec.pA.x; row[PR_RA + 1] = rec.pA.y; row[PR_RA + 2] = rec.pA.z;
+    row[PR_RB + 0] = rec.pB.x; row[PR_RB + 1] = rec.pB.y; row[PR_RB + 2] = rec.pB.z;
+    row[PR_LAMN] = rec.dist; row[PR_LAMPUSH] = M.body(BF_RESTITUTION, ia) * M.body(BF_RESTITUTION, ib);
+    row[PR_MU] = mu; row[PR_IDS] = (T)(ia + 32 * ib);
+    const T key = (T)((((ia + 32 * ib) * 64) * 64) * 2);
+    T wN = T(0), wT = T(0);
+    if (warm.entries != nullptr)
+        for (int j = 0; j < warm.cap; ++j) {
+            const T* e = warm.entries + j * TGB_WARM_WORDS;
+            if (e[0] == key) { wN = e[1] * warm.factor; wT = e[2] * warm.factor; }
+        }
+    row[PR_KEY] = key; row[PR_INVDIAGT] = wN; row[PR_RHST] = wT;
+    return 1;
+}
+
 /* Emission for bodies made of several shapes (compound bodies); out of line. */
 template <typename T, typename Model>
 __device__ __noinline__ int emitCompoundPairRows(const Model M, const T* sPose, int ia, int ib, T mu, T restitution, const PairWarm<T> warm, T* rows,
@@ -257,6 +302,37 @@ TGB_D int emitPairRows(const Model& M, const T* sPose, int ia, int ib, const Pai
     return emitCompoundPairRows<T>(M, sPose, ia, ib, mu, restitution, warm, rows, base, cap);
 }
 
+/* World inverse inertia as the coupled solvers apply it: double keeps the matrix (the oracle's operations), single precision the factored
+   form B (invI o (B^T v)) of the step kernel -- the nine words of the matrix are not held in registers there. */
+template <typename T>
+struct InvInertia {
+    M3<T> B;      /* basis (single precision) or the world inverse inertia matrix itself (double) */
+    V3<T> invI;   /* local inverse inertia (single precision) */
+    bool factored;
+    TGB_D V3<T> operator*(const V3<T>& v) const {
+        if (factored) {
+            const V3<T> l = B.tmul(v);
+            return B * V3<T>(invI.x * l.x, invI.y * l.y, invI.z * l.z);
+        }
+        return B * v;
+    }
+};
+
+/* What the coupled solvers need of the lane's body (they are inlined into the step kernel: these are the kernel's registers).  A lane
+   without a dynamic body of its own takes part with zero inverse mass and inertia. */
+template <typename T>
+struct CoupledBody {
+    V3<T> pos, gnv;
+    InvInertia<T> inertia;
+    T invMassV, muV;
+    bool mine;
+    TGB_D V3<T> x() const { return pos; }
+    TGB_D T invMass() const { return invMassV; }
+    TGB_D T mu() const { return muV; }
+    TGB_D V3<T> normal() const { return gnv; }
+    TGB_D InvInertia<T> Iinv() const { return inertia; }
+};
+
 /* solveCoupledReg is compiled for (own contact points per lane, pair rows per environment) = (1, 1) -- a rod end on the ground, one
    rod-rod contact: the commonest case by far -- and (2, 2); environments beyond that take solveCoupledMem.  A single warp issues
    roughly one instruction every four cycles here (dependent chains), so the executed instruction count of a coupled step is what
@@ -281,8 +357,11 @@ TGB_D int emitPairRows(const Model& M, const T* sPose, int ia, int ib, const Pai
    by the two lanes that own its bodies: each forms its side J_side . dV of the relative velocity from its registers, one shuffle
    brings the other side over, both lanes compute the same impulse and apply it to their own body. */
 template <typename T, bool kFast>
-__device__ __noinline__ void setupPairRows(unsigned mask, T* pr, int nPairRows, int lane, int groupLane0, V3<T> x, M3<T> Iinv, T invMass, V3<T> vel,
+__device__ __forceinline__ void setupPairRows(unsigned mask, T* pr, int nPairRows, int lane, int groupLane0, const CoupledBody<T>& body, V3<T> vel,
                                            V3<T> w, V3<T> extLin, V3<T> extAng, T dt) {
+    const V3<T> x = body.x();
+    const InvInertia<T> Iinv = body.Iinv();
+    const T invMass = body.invMass();
     const int warpLane = groupLane0 + lane;
     const int maxP = __reduce_max_sync(mask, nPairRows);
     for (int p = 0; p < maxP; ++p) {
@@ -372,9 +451,9 @@ TGB_D bool groupHasPenetration(unsigned groupMask, bool anyPenOwn, const T* pr, 
    W_ij = J_i M^-1 J_j^T formed once -- the dependent chain of a row visit is 5 operations instead of ~12, and a pair row adds one
    shuffle (the two sides' parts of its relative velocity).  Equal to the velocity-space iteration in exact arithmetic. */
 template <typename T, bool kFast, bool OBST, int NC, int PM>
-__device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T* ct, int rowStride, int nc, bool anyPenOwn, V3<T> gn,
-                                                            T muGround, const T* pr, T* warmPair, int nPairRows, int lane, int groupLane0, V3<T> x,
-                                                            M3<T> Iinv, T invMass, V3<T> vel, V3<T> w, V3<T> extLin, V3<T> extAng, T dt, int iterations
+__device__ __forceinline__ ContactSolveOut<T> solveCoupledReg(T* ct, int rowStride, int nc, bool anyPenOwn, const T* pr, T* warmPair, int nPairRows,
+                                                            int lane, int groupLane0, const CoupledBody<T>& body, V3<T> vel, V3<T> w, V3<T> extLin,
+                                                            V3<T> extAng, T dt, int iterations
 #ifdef TGB_STATS
                                                             , unsigned long long* statsP
 #endif
@@ -384,6 +463,9 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
        result): with the constant full mask a shuffle is one instruction, without the convergence check a run-time mask costs. */
     constexpr unsigned mask = 0xffffffffu;
     const int warpLane = groupLane0 + lane;
+    const V3<T> x = body.x(), gn = body.normal();
+    const InvInertia<T> Iinv = body.Iinv();
+    const T invMass = body.invMass(), muGround = body.mu();
 #ifdef TGB_STATS
     long long tick_ = clock64();
 #endif
@@ -749,9 +831,12 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledReg(unsigned groupMask, T
 }
 
 template <typename T, bool kFast, bool OBST>
-__device__ __noinline__ ContactSolveOut<T> solveCoupledMem(unsigned mask, unsigned groupMask, T* ct, int rowStride, int nc, bool anyPenOwn, V3<T> gn,
-                                                            T muGround, T* pr, T* warmPair, int nPairRows, int lane, int groupLane0, M3<T> Iinv,
-                                                            T invMass, int iterations) {
+__device__ __forceinline__ ContactSolveOut<T> solveCoupledMem(unsigned mask, unsigned groupMask, T* ct, int rowStride, int nc, bool anyPenOwn, T* pr,
+                                                            T* warmPair, int nPairRows, int lane, int groupLane0, const CoupledBody<T>& body,
+                                                            int iterations) {
+    const V3<T> gn = body.normal();
+    const InvInertia<T> Iinv = body.Iinv();
+    const T invMass = body.invMass(), muGround = body.mu();
     const int warpLane = groupLane0 + lane;
     const int maxP = __reduce_max_sync(mask, nPairRows);
     const bool anyPen = __any_sync(mask, groupHasPenetration<T>(groupMask, anyPenOwn, pr, nPairRows));
@@ -889,5 +974,63 @@ __device__ __noinline__ ContactSolveOut<T> solveCoupledMem(unsigned mask, unsign
     return o;
 }
 #undef TGB_CTG
+
+/* The one call the step kernel makes when a warp has coupled environments (a single call site keeps the hot loop's register
+   allocation away from the argument marshalling of four): decides per environment which solver it takes -- by the environment's own
+   rows only -- and runs them.  Entered by all 32 lanes of the body warp.  `solved` tells the lane whether its result is in the
+   return value (its environment is coupled) or its per-lane solver still has to run. */
+template <typename T, bool kFast, bool OBST, int LPE>
+__device__ __forceinline__ CoupledOut<T> solveCoupledWarp(T* ct, int rowStride, int nc, bool anyPenOwn, T* pr, T* warmPair, int nPairRows, int lane,
+                                                        int groupLane0, const CoupledBody<T>& body, V3<T> vel, V3<T> w, V3<T> extLin, V3<T> extAng, T dt,
+                                                        int iterations
+#ifdef TGB_STATS
+                                                        , unsigned long long* statsP
+#endif
+                                                        ) {
+    const unsigned fullMask = 0xffffffffu;
+    const unsigned groupMaskP = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
+    const int ncMine = body.mine ? nc : 0;
+    const bool penMine = body.mine && anyPenOwn;
+    const bool coupled = nPairRows > 0; /* uniform within the environment's group */
+    const bool own2 = (__ballot_sync(fullMask, ncMine > 1) & groupMaskP) != 0u;
+    const bool own3 = (__ballot_sync(fullMask, ncMine > 2) & groupMaskP) != 0u;
+    const bool inReg1 = coupled && !own2 && nPairRows <= 1;
+    const bool inReg2 = coupled && !inReg1 && !own3 && nPairRows <= TGB_PAIR_REG_ROWS;
+    const unsigned coupledMask = __ballot_sync(fullMask, coupled);
+    const unsigned reg1Mask = __ballot_sync(fullMask, inReg1), reg2Mask = __ballot_sync(fullMask, inReg2);
+    const unsigned memMask = coupledMask & ~(reg1Mask | reg2Mask);
+    __syncwarp(); /* the pair rows and every body's own rows are in shared memory */
+    ContactSolveOut<T> o;
+    o.dLin = V3<T>(T(0), T(0), T(0)); o.dAng = o.dLin; o.push = o.dLin; o.turn = o.dLin;
+    /* the register solvers are entered by the whole warp (full-mask shuffles); lanes of environments that are not theirs come along with
+       no rows and drop the result */
+    if (reg1Mask != 0u) {
+        const ContactSolveOut<T> o1 = solveCoupledReg<T, kFast, OBST, 1, 1>(ct, rowStride, inReg1 ? ncMine : 0, inReg1 && penMine, pr, warmPair,
+                                                                            inReg1 ? nPairRows : 0, lane, groupLane0, body, vel, w, extLin, extAng, dt,
+                                                                            iterations
+#ifdef TGB_STATS
+                                                                            , statsP
+#endif
+                                                                            );
+        if (inReg1) o = o1;
+    }
+    if (reg2Mask != 0u) {
+        const ContactSolveOut<T> o2 = solveCoupledReg<T, kFast, OBST, 2, TGB_PAIR_REG_ROWS>(ct, rowStride, inReg2 ? ncMine : 0, inReg2 && penMine, pr,
+                                                                                            warmPair, inReg2 ? nPairRows : 0, lane, groupLane0, body, vel,
+                                                                                            w, extLin, extAng, dt, iterations
+#ifdef TGB_STATS
+                                                                                            , statsP
+#endif
+                                                                                            );
+        if (inReg2) o = o2;
+    }
+    if (coupled && !inReg1 && !inReg2) {
+        setupPairRows<T, kFast>(memMask, pr, nPairRows, lane, groupLane0, body, vel, w, extLin, extAng, dt);
+        o = solveCoupledMem<T, kFast, OBST>(memMask, groupMaskP, ct, rowStride, ncMine, penMine, pr, warmPair, nPairRows, lane, groupLane0, body, iterations);
+    }
+    CoupledOut<T> r;
+    r.o = o; r.solved = coupled; r.statMem = memMask != 0u;
+    return r;
+}
 
 } // namespace tgb

@@ -579,7 +579,9 @@ TGB_HOST_DEVICE_INLINE int tgb_ctrl_class(int kind) {
 #ifndef TGB_NARROW_MINBLOCKS
 #define TGB_NARROW_MINBLOCKS 1
 #endif
-template <typename T, int LPE, int CLASS, bool GROUND, int WIDE = 0 /* 0 or 4 warps */, bool OBST = false /* static obstacles, narrow layout only */>
+template <typename T, int LPE, int CLASS, bool GROUND, int WIDE = 0 /* 0 or 4 warps */, bool OBST = false /* static obstacles, narrow layout only */,
+          bool WARM = false /* persistent manifolds with warm starting (tgb_set_warm_starting), narrow layout only: compiled out of the default
+                               kernels -- even skipped at run time its code cost 6 % of the step (registers, instruction footprint) */>
 __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step_kernel(const tgb_step_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename Vec16<T>::type vec_t;
@@ -627,11 +629,11 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
        phase to the impulse gather) share one region: shared memory per environment decides how many CTAs an SM holds */
     const int exchangeWords = TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords;
     /* body pairs: per pair the slack left before it has to be tested again, per body the motion bound of the last step (tgb_pairs.cuh) */
-    const int pairKeepWords = a.n_pairs > 0 ? a.n_pairs + LPE : 0;
+    const int pairKeepWords = a.n_pairs > 0 ? a.n_pairs + LPE : 0; /* slack per pair, motion bound per body */
     /* persistent manifolds (warm starting): the rows' impulses of the last world step, see TGB_WARM_* in tgb_dev.h */
-    const bool warmOn = a.warm != nullptr && a.warm_factor > 0.0;
-    const int warmPairCap = (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap : 0;
-    const int warmWords = a.warm != nullptr ? TGB_WARM_STATE_WORDS(a.cap_contacts, rowBodies, warmPairCap) : 0;
+#define warmOn (WARM && a.warm != nullptr) /* the host passes the buffer only with a positive factor */
+#define warmPairCap ((a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap : 0)
+#define warmWords (warmOn ? TGB_WARM_STATE_WORDS(a.cap_contacts, rowBodies, warmPairCap) : 0)
     int groupTWords = a.stride + poseWords + exchangeWords + pairKeepWords + warmWords;
     groupTWords = (groupTWords + 3) & ~3;
     /* keep group regions LPE banks apart so that the groups of one warp do not collide */
@@ -644,8 +646,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     T* sPairRows = sCt + ctOnlyWords;               /* [pair_cap][TGB_NPR] */
     T* sPairSlack = sJ + exchangeWords;             /* [n_pairs], then [LPE] motion bounds */
     T* sMotion = sPairSlack + a.n_pairs;
-    T* sWarm = sPairSlack + pairKeepWords;          /* [cap_contacts][row bodies][3], then [pair_cap][3] */
-    T* sWarmPair = sWarm + TGB_WARM_WORDS * a.cap_contacts * rowBodies;
+#define sWarm (sPairSlack + pairKeepWords)         /* [cap_contacts][row bodies][3], then [pair_cap][3] */
+#define sWarmPair (sWarm + TGB_WARM_WORDS * a.cap_contacts * rowBodies)
     constexpr bool cpgOn = CLASS == TGB_CLASS_CPG;
     constexpr bool sineOn = CLASS == TGB_CLASS_SINE;
     constexpr bool simpleOn = CLASS == TGB_CLASS_SIMPLE;
@@ -688,7 +690,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         for (int i = lane; i < a.stride / VN; i += LPE) ss[i] = gs[i];
         if (a.ctrl != nullptr)
             for (int i = lane; i < a.ctrl_stride; i += LPE) sCtrl[i] = a.ctrl[(size_t)env * a.ctrl_stride + i];
-        if (a.warm != nullptr && bodyWarp) {
+        if (warmOn && bodyWarp) {
             const T* gw = reinterpret_cast<const T*>(a.warm) + (size_t)env * warmWords;
             for (int i = lane; i < warmWords; i += LPE) sWarm[i] = gw[i];
         }
@@ -793,7 +795,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     const int incBegin = M.bodyi(BI_INC_BEGIN, bidx), incCount = M.bodyi(BI_INC_COUNT, bidx);
     const bool gyro = M.bodyi(BI_GYRO, bidx) != 0;
     const bool dynamic = hasBody && invMass != T(0);
-    b.Iinv = b.B.conjugateDiag(invI);
+    if (!kFast) b.Iinv = b.B.conjugateDiag(invI);
 
     auto publishPose = [&]() {
         if (hasBody) {
@@ -804,6 +806,16 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 #pragma unroll
             for (int i = 0; i < 12 / VN; ++i) dst[i] = *reinterpret_cast<vec_t*>(&rec[i * VN]);
         }
+    };
+    /* world inverse inertia times a vector.  Double keeps the matrix (the oracle's operations); single precision applies it in factored
+       form, B (invI o (B^T v)), and does not hold the nine words of the matrix in registers across the step -- the kernel sits at the
+       255-register limit and every value kept alive there is a spilled loop invariant somewhere else. */
+    auto applyIinv = [&](const V3<T>& v) -> V3<T> {
+        if (kFast) {
+            const V3<T> l = b.B.tmul(v);
+            return b.B * V3<T>(invI.x * l.x, invI.y * l.y, invI.z * l.z);
+        }
+        return b.Iinv * v;
     };
     publishPose();
     if (a.n_pairs > 0 && bodyWarp) {
@@ -822,10 +834,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     }
 #define CT(slot, f) sCt[((slot) * rowBodies + rowIdx) * NCT + (f)]
     /* the impulses this body's manifold point `key` ended the last world step with, scaled by the warm starting factor (0 when new) */
-    const T warmFactor = (T)a.warm_factor;
     auto warmLookup = [&](T key, T& wN, T& wT) {
         wN = T(0); wT = T(0);
         if (!warmOn) return;
+        const T warmFactor = (T)a.warm_factor;
         for (int j = 0; j < a.cap_contacts; ++j) {
             const T* e = sWarm + (j * rowBodies + rowIdx) * TGB_WARM_WORDS;
             if (e[0] == key) { wN = e[1] * warmFactor; wT = e[2] * warmFactor; }
@@ -972,7 +984,6 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
     T pairClearance = T(1e30); /* smallest surface distance of two bodies' capsules this lane has seen */
-    int prevNc = a.cap_contacts, prevPairRows = (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap : 0; /* rows of the last world step (upper bounds at launch) */
 #ifdef TGB_STATS
     const long long statT0 = clock64();
     unsigned long long wCoupled = 0, wCoupledCyc = 0, wDetectCyc = 0, wMem = 0, wMany = 0, wCableCyc = 0;
@@ -987,7 +998,6 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         V3<T> extLin(T(0), T(0), T(0)), extAng(T(0), T(0), T(0)), linvel(T(0), T(0), T(0));
         int nc = 0;
         bool anyPen = false;
-        bool anyWarm = false; /* a row of this body starts from a non-zero impulse */
         /* ---- contact between bodies: detection from the published poses (tgb_pairs.cuh).  Every lane of the body warp takes part; the
            lanes of a group take the environment's body pairs round robin.  nPairRows stays 0 unless a pair is within the contact band. */
         int nPairRows = 0;
@@ -1002,6 +1012,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 const int p = p0 + lane;
                 int ia = 0, ib = 0;
                 bool near = false;
+                PairRecord<T> rec;
+                rec.valid = false;
                 if (p < a.n_pairs) {
                     const int code = pairTable[p];
                     ia = code & 31; ib = code >> 5;
@@ -1017,7 +1029,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                         ++statTests;
 #endif
                         T dist;
-                        near = pairNear<T>(M, sPose, ia, ib, pairClearance, dist);
+                        near = pairNear<T>(M, sPose, ia, ib, pairClearance, dist, rec);
                         slack = (dist - pairBreakingThreshold<T>() - T(4e-3)) * T(0.999);
                     }
                 }
@@ -1031,7 +1043,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     if (warpLane == L) {
                         PairWarm<T> pw;
                         pw.entries = warmOn ? sWarmPair : nullptr; pw.cap = a.pair_cap; pw.factor = (T)a.warm_factor;
-                        cnt = emitPairRows<T>(M, sPose, ia, ib, pw, sPairRows, nPairRows, a.pair_cap);
+                        cnt = rec.valid ? emitRecordedPair<T>(M, rec, ia, ib, pw, sPairRows, nPairRows, a.pair_cap)
+                                        : emitPairRows<T>(M, sPose, ia, ib, pw, sPairRows, nPairRows, a.pair_cap);
                     }
 #ifdef TGB_STATS
                     ++statEmits;
@@ -1078,7 +1091,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             extLin = V3<T>(T(0), (gfy * invMass) * dt, T(0));
             if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) {
                 extLin = (totalForce * invMass) * dt;
-                extAng = b.Iinv.tmul(totalTorque) * dt;
+                extAng = (kFast ? applyIinv(totalTorque) : b.Iinv.tmul(totalTorque)) * dt;
             }
             if (gyro) {
                 /* btRigidBody::computeGyroscopicForce, explicit, clamped at maxGyroscopicForce */
@@ -1181,7 +1194,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 /* ---- setupContactConstraint / setupFrictionConstraint for this point ---- */
                                 const V3<T> r = (pc - gn * margin) - b.x;
                                 const V3<T> rxn = r.cross(gn);
-                                const V3<T> angN = b.Iinv * rxn;
+                                const V3<T> angN = applyIinv(rxn);
                                 const T denom = invMass + gn.dot(angN.cross(r));
                                 const T invDiagN = trcp(denom);
                                 const V3<T> vel = linvel + b.w.cross(r);
@@ -1207,7 +1220,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 if (penetration > SolverConst<T>::splitThreshold()) { rhsN = penetrationImpulse + velocityImpulse; rhsPen = T(0); }
                                 else { rhsN = velocityImpulse; rhsPen = penetrationImpulse; anyPen = anyPen || rhsPen != T(0); }
                                 const V3<T> rxt = r.cross(t);
-                                const V3<T> angT = b.Iinv * rxt;
+                                const V3<T> angT = applyIinv(rxt);
                                 const T denomT = invMass + t.dot(angT.cross(r));
                                 const T invDiagT = trcp(denomT);
                                 const T relT = t.dot(linvel + extLin) + rxt.dot(b.w);
@@ -1224,7 +1237,6 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 CT(nc, CT_RXT + 0) = rxt.x; CT(nc, CT_RXT + 1) = rxt.y; CT(nc, CT_RXT + 2) = rxt.z;
                                 CT(nc, CT_ANGT + 0) = angT.x; CT(nc, CT_ANGT + 1) = angT.y; CT(nc, CT_ANGT + 2) = angT.z;
                                 CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = warmT;
-                                anyWarm = anyWarm || warmN != T(0) || warmT != T(0);
                                 if constexpr (OBST) {
                                     CT(nc, CT_NRM + 0) = gn.x; CT(nc, CT_NRM + 1) = gn.y; CT(nc, CT_NRM + 2) = gn.z; CT(nc, CT_MU) = mu;
                                 }
@@ -1302,7 +1314,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                             if (dist <= SolverConst<T>::breakingThreshold()) {
                                 const V3<T> r = (pc - n * margin) - b.x;
                                 const V3<T> rxn = r.cross(n);
-                                const V3<T> angN = b.Iinv * rxn;
+                                const V3<T> angN = applyIinv(rxn);
                                 const T denom = invMass + n.dot(angN.cross(r));
                                 const T invDiagN = kFast ? trcp(denom) : T(1) / denom;
                                 const V3<T> vel = linvel + b.w.cross(r);
@@ -1328,7 +1340,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 if (penetration > SolverConst<T>::splitThreshold()) { rhsN = penetrationImpulse + velocityImpulse; rhsPen = T(0); }
                                 else { rhsN = velocityImpulse; rhsPen = penetrationImpulse; anyPen = anyPen || rhsPen != T(0); }
                                 const V3<T> rxt = r.cross(t);
-                                const V3<T> angT = b.Iinv * rxt;
+                                const V3<T> angT = applyIinv(rxt);
                                 const T denomT = invMass + t.dot(angT.cross(r));
                                 const T invDiagT = kFast ? trcp(denomT) : T(1) / denomT;
                                 const T relT = t.dot(linvel + extLin) + rxt.dot(b.w);
@@ -1345,7 +1357,6 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                                 CT(nc, CT_RXT + 0) = rxt.x; CT(nc, CT_RXT + 1) = rxt.y; CT(nc, CT_RXT + 2) = rxt.z;
                                 CT(nc, CT_ANGT + 0) = angT.x; CT(nc, CT_ANGT + 1) = angT.y; CT(nc, CT_ANGT + 2) = angT.z;
                                 CT(nc, CT_INVDIAGT) = invDiagT; CT(nc, CT_RHST) = rhsT; CT(nc, CT_LAMT) = warmT;
-                                anyWarm = anyWarm || warmN != T(0) || warmT != T(0);
                                 CT(nc, CT_NRM + 0) = n.x; CT(nc, CT_NRM + 1) = n.y; CT(nc, CT_NRM + 2) = n.z; CT(nc, CT_MU) = obstMu;
                                 ++nc;
                                 ++count;
@@ -1364,67 +1375,39 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             if (a.n_pairs > 0 && bodyWarp && __any_sync(fullMask, nPairRows > 0)) {
                 /* warp-uniform: environments of this warp have rows between two bodies.  Their lanes solve together (tgb_pairs.cuh);
                    the other environments keep their per-lane solvers below. */
-                const unsigned groupMaskP = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
-                const bool mine = dynamic;
-                const int ncMine = mine ? nc : 0;
-                const bool coupled = nPairRows > 0; /* uniform within the environment's group */
-                /* which solver: decided by the environment's own rows only */
-                const bool own2 = (__ballot_sync(fullMask, ncMine > 1) & groupMaskP) != 0u;
-                const bool own3 = (__ballot_sync(fullMask, ncMine > 2) & groupMaskP) != 0u;
-                const bool inReg1 = coupled && !own2 && nPairRows <= 1;
-                const bool inReg2 = coupled && !inReg1 && !own3 && nPairRows <= TGB_PAIR_REG_ROWS;
-                const unsigned coupledMask = __ballot_sync(fullMask, coupled);
-                const unsigned reg1Mask = __ballot_sync(fullMask, inReg1), reg2Mask = __ballot_sync(fullMask, inReg2);
-                const unsigned memMask = coupledMask & ~(reg1Mask | reg2Mask);
-                __syncwarp(); /* the pair rows and every body's own rows are in shared memory */
 #ifdef TGB_STATS
                 const long long statS0 = clock64();
 #endif
-                /* The register solvers are entered by the whole warp (full-mask shuffles); lanes of environments that are not theirs
-                   come along with no rows and drop the result. */
-                ContactSolveOut<T> o;
-                if (reg1Mask != 0u) {
-                    const ContactSolveOut<T> o1 = solveCoupledReg<T, kFast, OBST, 1, 1>(
-                        groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, inReg1 ? ncMine : 0, inReg1 && mine && anyPen, gn, mu, sPairRows,
-                        warmOn ? sWarmPair : nullptr, inReg1 ? nPairRows : 0, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt,
-                        a.iterations
+                CoupledBody<T> cb;
+                cb.pos = b.x; cb.gnv = gn; cb.mine = dynamic; cb.invMassV = dynamic ? invMass : T(0); cb.muV = mu;
+                cb.inertia.factored = kFast;
+                cb.inertia.B = kFast ? b.B : b.Iinv;
+                cb.inertia.invI = dynamic ? invI : V3<T>(T(0), T(0), T(0));
+                if (!kFast && !dynamic) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) cb.inertia.B.m[i][j] = T(0);
+                }
+                const CoupledOut<T> co = solveCoupledWarp<T, kFast, OBST, LPE>(sCt + rowIdx * NCT, rowBodies * NCT, nc, anyPen, sPairRows,
+                                                                               warmOn ? sWarmPair : nullptr, nPairRows, lane, groupLane0, cb,
+                                                                               kFast ? b.v : linvel, b.w, extLin, extAng, dt, a.iterations
 #ifdef TGB_STATS
-                        , a.stats
+                                                                               , a.stats
 #endif
-                        );
-                    if (inReg1) o = o1;
-                }
-                if (reg2Mask != 0u) {
-                    const ContactSolveOut<T> o2 = solveCoupledReg<T, kFast, OBST, 2, TGB_PAIR_REG_ROWS>(
-                        groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, inReg2 ? ncMine : 0, inReg2 && mine && anyPen, gn, mu, sPairRows,
-                        warmOn ? sWarmPair : nullptr, inReg2 ? nPairRows : 0, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0), kFast ? b.v : linvel, b.w, extLin, extAng, dt,
-                        a.iterations
-#ifdef TGB_STATS
-                        , a.stats
-#endif
-                        );
-                    if (inReg2) o = o2;
-                }
-                if (coupled && !inReg1 && !inReg2) {
-                    setupPairRows<T, kFast>(memMask, sPairRows, nPairRows, lane, groupLane0, b.x, b.Iinv, mine ? invMass : T(0),
-                                            kFast ? b.v : linvel, b.w, extLin, extAng, dt);
-                    o = solveCoupledMem<T, kFast, OBST>(memMask, groupMaskP, sCt + rowIdx * NCT, rowBodies * NCT, ncMine, mine && anyPen, gn, mu,
-                                                        sPairRows, warmOn ? sWarmPair : nullptr, nPairRows, lane, groupLane0, b.Iinv,
-                                                        mine ? invMass : T(0), a.iterations);
-                }
-                if (coupled) {
-                    dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
-                    solved = true;
-                }
+                                                                               );
+                solved = co.solved;
+                if (solved) { dLin = co.o.dLin; dAng = co.o.dAng; push = co.o.push; turn = co.o.turn; }
 #ifdef TGB_STATS
                 __syncwarp();
-                wCoupled += 1; wCoupledCyc += (unsigned long long)(clock64() - statS0); wMem += memMask ? 1 : 0;
+                const unsigned long long statMem = co.statMem ? 1ULL : 0ULL;
+                wCoupled += 1; wCoupledCyc += (unsigned long long)(clock64() - statS0); wMem += statMem;
                 if (a.stats && warpLane == 0) {
                     /* [55] warp-steps with a coupled environment, [56] of which with one in the shared-memory solver, [57] coupled
                        environments summed over warp-steps, [104] cycles of the coupled solve */
                     atomicAdd(a.stats + 55, 1ULL);
-                    if (memMask) atomicAdd(a.stats + 56, 1ULL);
-                    atomicAdd(a.stats + 57, (unsigned long long)(__popc(coupledMask) / LPE));
+                    if (statMem) atomicAdd(a.stats + 56, 1ULL);
+                    atomicAdd(a.stats + 57, (unsigned long long)(__popc(__ballot_sync(fullMask, nPairRows > 0)) / LPE));
                     atomicAdd(a.stats + 104, (unsigned long long)(clock64() - statS0));
                     atomicAdd(a.stats + 110, (unsigned long long)(statS0 - statA)); /* body phase before the coupled solve, coupled warp-steps only */
                 }
@@ -1489,18 +1472,14 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                in the rows); slots beyond them are emptied ---- */
             if (warmOn) {
                 if (dynamic) {
-                    const int n = nc > prevNc ? nc : prevNc;
-                    for (int j = 0; j < n; ++j) {
+                    for (int j = 0; j < a.cap_contacts; ++j) {
                         T* e = sWarm + (j * rowBodies + rowIdx) * TGB_WARM_WORDS;
                         if (j < nc) { e[0] = CT(j, CT_KEY); e[1] = CT(j, CT_LAMN); e[2] = CT(j, CT_LAMT); }
                         else e[0] = T(-1);
                     }
-                    prevNc = nc;
                 }
-                if (a.n_pairs > 0 && bodyWarp) { /* nPairRows, prevPairRows: uniform within the group */
-                    for (int p = nPairRows + lane; p < prevPairRows; p += LPE) sWarmPair[p * TGB_WARM_WORDS] = T(-1);
-                    prevPairRows = nPairRows;
-                }
+                if (a.n_pairs > 0 && bodyWarp) /* nPairRows: uniform within the group */
+                    for (int p = nPairRows + lane; p < warmPairCap; p += LPE) sWarmPair[p * TGB_WARM_WORDS] = T(-1);
             }
             /* ---- write back, split-impulse correction, integrateTransforms ---- */
             if (dynamic) {
@@ -1509,7 +1488,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 if (push.nonzero() || turn.nonzero()) integrateTransform(b.x, b.q, push, turn * SolverConst<T>::turnErp(), dt);
                 integrateTransform(b.x, b.q, b.v, b.w, dt);
                 b.B = M3<T>::fromQuat(b.q);
-                b.Iinv = b.B.conjugateDiag(invI);
+                if (!kFast) b.Iinv = b.B.conjugateDiag(invI);
                 if (a.n_pairs > 0) {
                     /* how far a point of this body's shapes can have moved in this step, relative to the env frame: translation by
                        (v + push) dt, rotation by at most (|w| + turnErp |turn|) dt about the body origin (1-norms of the rare split-impulse terms: upper bounds) */
@@ -1895,7 +1874,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     sumT += V3<T>(t4.x, t4.y, t4.z);
                 }
                 b.v += sumJ * invMass;
-                b.w += b.Iinv * sumT;
+                b.w += applyIinv(sumT);
             } else {
                 for (int i = incBegin; i < incBegin + incCount; ++i) {
                     const int code = M.inc[i];
@@ -1984,7 +1963,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         vec_t* gs = reinterpret_cast<vec_t*>(reinterpret_cast<T*>(a.state) + (size_t)env * a.stride);
         const vec_t* ss = reinterpret_cast<const vec_t*>(sState);
         for (int i = lane; i < a.stride / VN; i += LPE) gs[i] = ss[i];
-        if (a.warm != nullptr && doWorld) {
+        if (warmOn && doWorld) {
             T* gw = reinterpret_cast<T*>(a.warm) + (size_t)env * warmWords;
             for (int i = lane; i < warmWords; i += LPE) gw[i] = sWarm[i];
         }
@@ -2007,6 +1986,12 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         }
     }
 }
+
+#undef warmOn
+#undef warmPairCap
+#undef warmWords
+#undef sWarm
+#undef sWarmPair
 
 /* Shared memory a launch of this kernel needs; mirrors the carve-up above. */
 inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, size_t sizeofT) {
