@@ -55,6 +55,9 @@
 #ifndef TGB_VEC_CREC
 #define TGB_VEC_CREC 1
 #endif
+#ifndef TGB_FACTORED_IINV
+#define TGB_FACTORED_IINV 1 /* single precision: apply the world inverse inertia as B (invI o (B^T v)) instead of holding the matrix */
+#endif
 #ifndef TGB_CABLE_UNROLL
 #define TGB_CABLE_UNROLL 0 /* 0 = automatic */
 #endif
@@ -620,7 +623,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
        list][body lane] of two float4 planes, so that the gather of a body lane is a run of 128-bit loads at consecutive addresses
        across lanes: no index loads, no bank conflicts. */
     const int jWords = kFast ? a.max_inc * LPE * 8 : 3 * C;
-    constexpr int NCT = OBST ? (int)TGB_NCT_OBST : (int)TGB_NCT;
+    /* without the persistent manifolds a row has no key: 23 words (the stride must stay odd, see CT_*) */
+    constexpr int NCT = OBST ? (int)TGB_NCT_OBST : (WARM ? (int)TGB_NCT : (int)TGB_NCT - 2);
     const int rowBodies = OBST ? a.n_dyn : R;     /* worlds with obstacles: no rows for the static bodies */
     const int ctOnlyWords = a.cap_contacts * NCT * rowBodies; /* rows [slot][body][NCT]: 23 words apart across lanes, conflict-free */
     const int pairWords = (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap * (int)TGB_NPR : 0; /* rows between two bodies, behind the contact rows */
@@ -795,7 +799,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     const int incBegin = M.bodyi(BI_INC_BEGIN, bidx), incCount = M.bodyi(BI_INC_COUNT, bidx);
     const bool gyro = M.bodyi(BI_GYRO, bidx) != 0;
     const bool dynamic = hasBody && invMass != T(0);
-    if (!kFast) b.Iinv = b.B.conjugateDiag(invI);
+    if (!(kFast && TGB_FACTORED_IINV)) b.Iinv = b.B.conjugateDiag(invI);
 
     auto publishPose = [&]() {
         if (hasBody) {
@@ -811,7 +815,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
        form, B (invI o (B^T v)), and does not hold the nine words of the matrix in registers across the step -- the kernel sits at the
        255-register limit and every value kept alive there is a spilled loop invariant somewhere else. */
     auto applyIinv = [&](const V3<T>& v) -> V3<T> {
-        if (kFast) {
+        if (kFast && TGB_FACTORED_IINV) {
             const V3<T> l = b.B.tmul(v);
             return b.B * V3<T>(invI.x * l.x, invI.y * l.y, invI.z * l.z);
         }
@@ -1091,7 +1095,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             extLin = V3<T>(T(0), (gfy * invMass) * dt, T(0));
             if (simpleOn && ctrlKind == TGB_CTRL_SERIALIZED_SPINE) {
                 extLin = (totalForce * invMass) * dt;
-                extAng = (kFast ? applyIinv(totalTorque) : b.Iinv.tmul(totalTorque)) * dt;
+                extAng = ((kFast && TGB_FACTORED_IINV) ? applyIinv(totalTorque) : b.Iinv.tmul(totalTorque)) * dt;
             }
             if (gyro) {
                 /* btRigidBody::computeGyroscopicForce, explicit, clamped at maxGyroscopicForce */
@@ -1380,10 +1384,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 #endif
                 CoupledBody<T> cb;
                 cb.pos = b.x; cb.gnv = gn; cb.mine = dynamic; cb.invMassV = dynamic ? invMass : T(0); cb.muV = mu;
-                cb.inertia.factored = kFast;
-                cb.inertia.B = kFast ? b.B : b.Iinv;
+                cb.inertia.factored = kFast && TGB_FACTORED_IINV;
+                cb.inertia.B = (kFast && TGB_FACTORED_IINV) ? b.B : b.Iinv;
                 cb.inertia.invI = dynamic ? invI : V3<T>(T(0), T(0), T(0));
-                if (!kFast && !dynamic) {
+                if (!(kFast && TGB_FACTORED_IINV) && !dynamic) {
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -1488,7 +1492,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 if (push.nonzero() || turn.nonzero()) integrateTransform(b.x, b.q, push, turn * SolverConst<T>::turnErp(), dt);
                 integrateTransform(b.x, b.q, b.v, b.w, dt);
                 b.B = M3<T>::fromQuat(b.q);
-                if (!kFast) b.Iinv = b.B.conjugateDiag(invI);
+                if (!(kFast && TGB_FACTORED_IINV)) b.Iinv = b.B.conjugateDiag(invI);
                 if (a.n_pairs > 0) {
                     /* how far a point of this body's shapes can have moved in this step, relative to the env frame: translation by
                        (v + push) dt, rotation by at most (|w| + turnErp |turn|) dt about the body origin (1-norms of the rare split-impulse terms: upper bounds) */
@@ -1998,7 +2002,8 @@ inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, 
     const int groupsPerBlock = a.wide ? 32 / lpe : threads / lpe;
     const int modelTWords = (a.model_t_words + 3) & ~3;
     const int jWords = sizeofT == 4 ? a.max_inc * lpe * 8 : 3 * a.C;
-    const int ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST * a.n_dyn : (int)TGB_NCT * a.R) + ((a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap * (int)TGB_NPR : 0);
+    const int ctWords = a.cap_contacts * (a.n_obst > 0 ? (int)TGB_NCT_OBST * a.n_dyn : ((int)TGB_NCT - (a.warm != nullptr && !a.wide ? 0 : 2)) * a.R) +
+                        ((a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap * (int)TGB_NPR : 0);
     int groupTWords = a.stride + 12 * lpe + (TGB_EXCHANGE_UNION ? (jWords > ctWords ? jWords : ctWords) : jWords + ctWords) + (a.n_pairs > 0 ? a.n_pairs + lpe : 0) +
                       (a.warm != nullptr ? TGB_WARM_STATE_WORDS(a.cap_contacts, a.n_obst > 0 ? a.n_dyn : a.R, (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap : 0) : 0);
     groupTWords = (groupTWords + 3) & ~3;

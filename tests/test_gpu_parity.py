@@ -93,7 +93,7 @@ def test_prism_first_step_damping_artefact():
 def test_prism_drop_f32_full_horizon():
     """config 2, single precision, full horizon H = 1000 steps (each env falls ~490 units): stated FP32 tolerance."""
     model = nt.build_example("3_prism_noground")
-    n_env, steps = 512, 1000
+    n_env, steps = 4096, 1000   # BASELINE config 2 at its full size
     rods, cab = random_poses(model, n_env, seed=1234), tiled_cables(model, n_env)
     rd, cd, st = device_rollout(model, rods, cab, steps, "f32", chunks=4)
     ro, co = oracle_rollout(model, rods, cab, steps)
@@ -1365,3 +1365,56 @@ def test_warm_starting_f32_and_layouts():
     per_env = np.abs(align_quat_sign(ref[0], ro)[..., 0:3] - ro[..., 0:3]).max(axis=(1, 2)) / 17.0
     print("warm starting f32: fraction within 1e-4 %.3f, worst %.3e" % (np.mean(per_env < F32_REL), per_env.max()))
     assert np.mean(per_env < F32_REL) >= 0.95 and per_env.max() < 1e-2   # 62 of 64 measured; the others are contacts switching a step apart
+
+
+def test_superball_f32_contact_parity_statistics_full_size():
+    """BASELINE config 3 at its full size (4096 environments, the benchmark's seed and controller draws), single precision against the
+    oracle: what fraction of the environments stays within the FP32 tolerance (1e-4 of the structure size / of max(|T|, 100)) after
+    200 steps and after the benchmark's 1000 steps per launch, and what the others have in common.  Contact makes trajectories
+    sensitive (a manifold point appearing a step earlier changes the impulses), so this is a statistic, asserted as such."""
+    sys.path.insert(0, ROOT)
+    import bench
+    n_env = 4096
+    model, rods, cab, ctrl, params, _ = bench.build_workload("superball", n_env, bench.SEED)
+    w = nt.BatchedWorld(model, n_env, precision="f32")
+    w.set_rod_state(rods)
+    w.set_cable_state(cab)
+    w.set_controller(ctrl, params)
+    out = {}
+    done = 0
+    for steps in (200, 1000):
+        w.step(model.dt, steps - done)
+        done = steps
+        out[steps] = (w.get_rod_state(), w.get_cable_obs(), w.min_clearance())
+    assert not (w.status() & 1).any()
+    w.close()
+    for steps in (200, 1000):
+        rd, cd, clr = out[steps]
+        ro, co = oracle_rollout(model, rods, cab, steps, ctrl, params, threads=os.cpu_count() or 8)
+        pos = np.abs(align_quat_sign(rd, ro)[..., 0:3] - ro[..., 0:3]).max(axis=(1, 2)) / 17.0
+        ten = (np.abs(cd[..., 2] - co[..., 2]) / np.maximum(np.abs(co[..., 2]), 100.0)).max(axis=1)
+        worst = np.maximum(pos, ten)
+        touched = clr < 0.02
+        frac = [float(np.mean(worst < t)) for t in (1e-4, 1e-3, 1e-2)]
+        print("config 3, 4096 envs, f32 vs oracle after %d steps: within 1e-4 %.4f, 1e-3 %.4f, 1e-2 %.4f; median %.2e; envs with a rod-rod "
+              "contact so far %d, of the %d envs beyond 1e-4 %d had one" % (steps, frac[0], frac[1], frac[2], np.median(worst), int(touched.sum()),
+                                                                           int((worst >= 1e-4).sum()), int((touched & (worst >= 1e-4)).sum())))
+        # the yardstick for the long horizon: the oracle against itself with its input moved by one single-precision ulp of the structure
+        # size (1e-6) -- what any single-precision computation of these trajectories can be expected to hold
+        pert = rods.copy()
+        pert[:, :, 0:3] += 1e-6 * np.random.default_rng(1).normal(size=pert[:, :, 0:3].shape)
+        rp, cp = oracle_rollout(model, pert, cab, steps, ctrl, params, threads=os.cpu_count() or 8)
+        pos_o = np.abs(align_quat_sign(rp, ro)[..., 0:3] - ro[..., 0:3]).max(axis=(1, 2)) / 17.0
+        ten_o = (np.abs(cp[..., 2] - co[..., 2]) / np.maximum(np.abs(co[..., 2]), 100.0)).max(axis=1)
+        own = np.maximum(pos_o, ten_o)
+        frac_own = [float(np.mean(own < t)) for t in (1e-4, 1e-3, 1e-2)]
+        print("    oracle vs oracle with its input moved by 1e-6: within 1e-4 %.4f, 1e-3 %.4f, 1e-2 %.4f; median %.2e"
+              % (frac_own[0], frac_own[1], frac_own[2], np.median(own)))
+        if steps == 200:
+            assert frac[0] >= 0.985 and frac[2] >= 0.999
+        else:
+            # The north star asks for the tolerance over a short horizon (above) and over the full horizon for contact-free rollouts
+            # (test_prism_drop_f32_full_horizon).  With contact the full horizon is a statistic: measured 48 % / 79 % / 98 % within
+            # 1e-4 / 1e-3 / 1e-2 (median 1.1e-4), against 79 % / 91 % / 99 % for the oracle after ONE perturbation of 1e-6 at the start --
+            # single precision perturbs every step.  Held here: the bulk stays bounded.
+            assert frac[1] >= 0.70 and frac[2] >= 0.95 and np.median(worst) < 5e-4
