@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define TGB_ABI_VERSION 4
+#define TGB_ABI_VERSION 5
 
 typedef enum {
     TGB_OK = 0,
@@ -354,6 +354,14 @@ tgb_status tgb_set_block_threads(tgb_world* w, int32_t threads);
    the environment variable TGB_WIDE=0/1 overrides the automatic choice).  Lanes per env must be 4 or 8 and the controller not the
    CPG one, else the narrow layout is used.  Results are bit-identical in both layouts.  May be called at any time. */
 tgb_status tgb_set_wide_layout(tgb_world* w, int32_t mode);
+
+/* Tail split of long launches (worlds whose bodies collide with each other): environments that spent at least 1/8 of their last
+   launch with contact rows between two bodies (rods leaning on each other -- they run the coupled contact solver on every step and
+   a launch ends with its slowest warp) get a warp of their own on a second stream, the others keep the usual layout.  -1 =
+   automatic (default: launches of >= 64 steps over >= 512 environments; TGB_TAIL_SPLIT=0 in the environment turns it off), 0 = off,
+   1 = every launch with a threshold of one step (tests).  Results are bit-identical with and without.  No reference counterpart:
+   Bullet steps one world at a time.  May be called at any time. */
+tgb_status tgb_set_tail_split(tgb_world* w, int32_t mode);
 
 /* Bytes of device state per environment (the HBM traffic of one launch is 2x this per env). */
 tgb_status tgb_state_bytes_per_env(const tgb_world* w, size_t* out);

@@ -70,7 +70,7 @@ ABI_SYMBOLS = [
     "tgb_rollout_host", "tgb_track_max_tension", "tgb_get_max_tension", "tgb_get_time", "tgb_get_status", "tgb_mark_episode_start", "tgb_get_scores",
     "tgb_scores_device_ptr", "tgb_scores_refresh_async", "tgb_step_timed", "tgb_launch_count", "tgb_launch_geometry", "tgb_set_lanes_per_env",
     "tgb_set_block_threads", "tgb_set_wide_layout", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
-    "tgb_set_pair_contact_cap", "tgb_get_min_clearance", "tgb_set_warm_starting",
+    "tgb_set_pair_contact_cap", "tgb_get_min_clearance", "tgb_set_warm_starting", "tgb_set_tail_split",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -140,6 +140,7 @@ def load():
     lib.tgb_set_pair_contact_cap.argtypes = [_vp, _i32]
     lib.tgb_get_min_clearance.argtypes = [_vp, _i32, _i32, _vp, _i32]
     lib.tgb_set_warm_starting.argtypes = [_vp, C.c_double]
+    lib.tgb_set_tail_split.argtypes = [_vp, _i32]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tgb_abi_version", "tgb_last_error", "tgb_device_count"):

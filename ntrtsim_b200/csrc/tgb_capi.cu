@@ -85,6 +85,17 @@ struct tgb_world {
     double heightLo = 1.0, heightHi = 0.0; /* disabled */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long* d_stats = nullptr; /* TGB_STATS=1 with a -DTGB_STATS build of the kernels (tools/) */
+    /* tail split (launchSplit below): steps per environment with rows between two bodies in its last launch, and per range of
+       environments in flight (slot 0: the whole world on `stream`; slot 1 + k: chunk k of tgb_rollout_host) the two lists of a launch */
+    enum { kSplitSlots = 5 };
+    int* d_coupled = nullptr;       /* [n_env] */
+    int* d_split_count = nullptr;   /* [kSplitSlots][2]: slow candidates, fast environments */
+    int* d_split_slow = nullptr;    /* [kSplitSlots][splitSlowCap] */
+    int* d_split_fast = nullptr;    /* [n_env]: a range's fast list sits at its env_begin */
+    int splitSlowCap = 0, splitMode = -1 /* -1 automatic, 0 off, 1 forced (tests) */, coupledLaunchSteps = 0;
+    cudaStream_t splitStream[kSplitSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t splitFork[kSplitSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t splitJoin[kSplitSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     /* tgb_rollout_host pipelines env chunks over these streams: the copies of one chunk overlap the steps of the others */
     enum { kPipe = 4 };
     cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr, nullptr};
@@ -133,6 +144,15 @@ struct tgb_world {
         if (h_stage) cudaFreeHost(h_stage);
         if (d_scores) cudaFree(d_scores);
         if (d_min_clearance) cudaFree(d_min_clearance);
+        if (d_coupled) cudaFree(d_coupled);
+        if (d_split_count) cudaFree(d_split_count);
+        if (d_split_slow) cudaFree(d_split_slow);
+        if (d_split_fast) cudaFree(d_split_fast);
+        for (int i = 0; i < kSplitSlots; ++i) {
+            if (splitStream[i]) cudaStreamDestroy(splitStream[i]);
+            if (splitFork[i]) cudaEventDestroy(splitFork[i]);
+            if (splitJoin[i]) cudaEventDestroy(splitJoin[i]);
+        }
         if (d_warm) cudaFree(d_warm);
         if (d_cpg_topo) cudaFree(d_cpg_topo);
         if (d_cpg_imp) cudaFree(d_cpg_imp);
@@ -355,6 +375,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.n_obst = w->nObst; a.model_obst_off = w->modelObstOff;
     a.n_pairs = w->pairCap != 0 ? w->nPairs : 0; a.model_pair_off = w->modelPairOff; a.pair_cap = w->pairCap;
     a.min_clearance = w->d_min_clearance;
+    a.coupled_steps = (a.n_pairs > 0 && a.pair_cap > 0) ? w->d_coupled : nullptr;
     a.warm = w->warmFactor > 0.0 ? w->d_warm : nullptr; a.warm_factor = w->warmFactor;
     a.n_dyn = 0;
     for (int b = 0; b < w->R; ++b) a.n_dyn += w->bodies[b].mass != 0.0;
@@ -375,24 +396,132 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     return a;
 }
 
+/* Tail split.  A launch ends with its slowest warp, and environments whose rods lean on each other take the coupled contact solver
+   (tgb_pairs.cuh) on every step for thousands of steps: a warp that holds one of them runs ~1.6x as long as the others (measured on
+   the bench workload: SMs active 62 % of the launch).  Such environments are few and they stay what they are from one launch to the
+   next, so a launch of many steps is cut in two by the count the last launch left per environment (tgb_step_args.coupled_steps):
+   the environments that were coupled for at least 1/8 of its steps (at most splitSlowCap of them -- all CTAs of both kernels have to
+   stay resident) get one warp each (32 lanes per environment: the cables run in one round instead of four, the body pairs are
+   tested in one, nothing of another environment's contact code is executed), on a second stream of higher priority; everything
+   else runs in the usual layout.  Both kernels take their environments from lists a small kernel writes (tgb_step_args.env_list).
+   Results do not depend on which lanes simulate an environment (tested bit for bit), so the split changes durations only. */
+__global__ void tgb_classify_envs_kernel(const int* coupled, int envBegin, int envCount, int threshold, int slowCap, int* count, int* slow,
+                                         int* fast) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= envCount) return;
+    const int env = envBegin + i;
+    if (coupled[env] >= threshold) {
+        const int k = atomicAdd(count, 1);
+        if (k < slowCap) { slow[k] = env; return; }
+    }
+    fast[atomicAdd(count + 1, 1)] = env;
+}
+
+bool splitWanted(const tgb_world* w, const tgb_step_args& a, int envCount) {
+    if (w->d_coupled == nullptr || a.coupled_steps == nullptr || a.phases != 3 || a.wide || w->lanes >= 32) return false;
+    if (w->ctrlKind == TGB_CTRL_CPG_IMPEDANCE) return false; /* the CPG class gives an environment as many lanes as it has nodes */
+    if (w->splitMode == 0) return false;
+    if (w->splitMode == 1) return true;
+    static const char* envSplit = std::getenv("TGB_TAIL_SPLIT");
+    if (envSplit && std::atoi(envSplit) == 0) return false;
+    /* one more kernel and two lists pay when a launch is long and the device is full enough for its slowest warp to matter */
+    return a.n_steps >= 64 && envCount >= 512 && w->coupledLaunchSteps > 0;
+}
+
+tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount, cudaStream_t s, int slot, int lastSteps) {
+    if (!w->splitStream[slot]) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        TGB_CUDA(cudaStreamCreateWithPriority(&w->splitStream[slot], cudaStreamNonBlocking, hi));
+        TGB_CUDA(cudaEventCreateWithFlags(&w->splitFork[slot], cudaEventDisableTiming));
+        TGB_CUDA(cudaEventCreateWithFlags(&w->splitJoin[slot], cudaEventDisableTiming));
+    }
+    int* count = w->d_split_count + 2 * slot;
+    int* slow = w->d_split_slow + (size_t)slot * w->splitSlowCap;
+    int* fast = w->d_split_fast + envBegin;
+    const int slowCap = w->splitMode == 1 ? std::min(w->splitSlowCap, envCount) : std::min(w->splitSlowCap, std::max(1, envCount / 20));
+    const int threshold = w->splitMode == 1 ? 1 : std::max(1, lastSteps / 8);
+    TGB_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(int), s));
+    tgb_classify_envs_kernel<<<(envCount + 255) / 256, 256, 0, s>>>(w->d_coupled, envBegin, envCount, threshold, slowCap, count, slow, fast);
+    TGB_CUDA(cudaGetLastError());
+    {
+        static const char* dbg = std::getenv("TGB_SPLIT_DEBUG"); /* tuning aid: synchronises */
+        if (dbg) {
+            int h[2] = {0, 0};
+            cudaMemcpyAsync(h, count, sizeof(h), cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            std::fprintf(stderr, "tgb tail split: %d environments coupled for >= %d of the last %d steps (cap %d), %d in the usual layout\n", h[0],
+                         threshold, lastSteps, slowCap, h[1]);
+        }
+    }
+    TGB_CUDA(cudaEventRecord(w->splitFork[slot], s));
+    TGB_CUDA(cudaStreamWaitEvent(w->splitStream[slot], w->splitFork[slot], 0));
+    tgb_step_args as = a;
+    as.env_list = slow; as.env_list_count = count; as.env_list_slots = slowCap;
+    cudaError_t e = w->ops->step(as, 32, 32, w->splitStream[slot]);
+    if (e != cudaSuccess) return cudaFail(e, "step kernel launch (coupled environments)");
+    TGB_CUDA(cudaEventRecord(w->splitJoin[slot], w->splitStream[slot]));
+    tgb_step_args af = a;
+    af.env_list = fast; af.env_list_count = count + 1; af.env_list_slots = envCount;
+    e = w->ops->step(af, w->lanes, w->threads, s);
+    if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
+    TGB_CUDA(cudaStreamWaitEvent(s, w->splitJoin[slot], 0));
+    w->launches += 3;
+    return TGB_OK;
+}
+
+/* Steps per launch while the tail split is on: which environments are coupled is only known from the launch before, so a call of
+   many steps is cut into launches of this many -- an environment whose rods come to rest on each other spends at most one of them in
+   a warp that it holds up.  (Results do not depend on how an episode is cut into launches: tested.) */
+int splitChunk(const tgb_world* w) {
+    static const char* envChunk = std::getenv("TGB_SPLIT_CHUNK");
+    if (envChunk && std::atoi(envChunk) > 0) return std::atoi(envChunk);
+    return w->splitMode == 1 ? 100 : (1 << 30); /* measured on B200 (bench workload, 1000 steps): launches of 125 / 250 / 500 / 1000 steps 8.0 / 6.9 / 6.4 / 6.4 ms */
+}
+
 tgb_status launchStep(tgb_world* w, double dt, int nSteps, int phases = 3) {
     tgb_step_args a = stepArgs(w, dt, nSteps);
     a.phases = phases;
-    cudaError_t e = w->ops->step(a, w->lanes, w->threads, w->stream);
-    if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
-    w->launches += 1;
+    if (splitWanted(w, a, w->cfg.n_env)) {
+        const int chunk = splitChunk(w);
+        for (int done = 0; done < nSteps; done += chunk) {
+            a.n_steps = std::min(chunk, nSteps - done);
+            tgb_status st = launchSplit(w, a, 0, w->cfg.n_env, w->stream, 0, w->coupledLaunchSteps);
+            if (st != TGB_OK) return st;
+            w->coupledLaunchSteps = a.n_steps;
+        }
+    } else {
+        cudaError_t e = w->ops->step(a, w->lanes, w->threads, w->stream);
+        if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
+        w->launches += 1;
+        if ((phases & 1) && a.coupled_steps) w->coupledLaunchSteps = nSteps;
+    }
     if (phases & 1) w->time += dt * nSteps;
     return TGB_OK;
 }
 
-/* the same for the environments [envBegin, envBegin + envCount) only, on stream s; does not advance the world's clock */
-tgb_status launchStepRange(tgb_world* w, double dt, int nSteps, int envBegin, int envCount, cudaStream_t s) {
+/* the same for the environments [envBegin, envBegin + envCount) only, on stream s; does not advance the world's clock.  slot: which
+   of the world's list buffers the range may use (1 + chunk of tgb_rollout_host) */
+tgb_status launchStepRange(tgb_world* w, double dt, int nSteps, int envBegin, int envCount, cudaStream_t s, int slot) {
     tgb_step_args a = stepArgs(w, dt, nSteps);
-    a.env_begin = envBegin;
-    a.n_env = envBegin + envCount;
-    cudaError_t e = w->ops->step(a, w->lanes, w->threads, s);
-    if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
-    w->launches += 1;
+    if (splitWanted(w, a, envCount)) {
+        const int chunk = splitChunk(w);
+        int lastSteps = w->coupledLaunchSteps;
+        for (int done = 0; done < nSteps; done += chunk) {
+            a.n_steps = std::min(chunk, nSteps - done);
+            tgb_status st = launchSplit(w, a, envBegin, envCount, s, slot, lastSteps);
+            if (st != TGB_OK) return st;
+            lastSteps = a.n_steps;
+        }
+        w->coupledLaunchSteps = std::min(chunk, nSteps); /* (the chunks of one call of tgb_rollout_host are cut alike) */
+    } else {
+        a.env_begin = envBegin;
+        a.n_env = envBegin + envCount;
+        cudaError_t e = w->ops->step(a, w->lanes, w->threads, s);
+        if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
+        w->launches += 1;
+        if (a.coupled_steps) w->coupledLaunchSteps = nSteps;
+    }
     return TGB_OK;
 }
 
@@ -524,6 +653,13 @@ tgb_status tgb_set_wide_layout(tgb_world* w, int32_t mode) {
     if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
     if (mode < -1 || mode > 1) return fail(TGB_ERR_INVALID_ARGUMENT, "layout mode must be -1 (automatic), 0 (narrow) or 1 (wide)");
     w->wideMode = mode;
+    return TGB_OK;
+}
+
+tgb_status tgb_set_tail_split(tgb_world* w, int32_t mode) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL world");
+    if (mode < -1 || mode > 1) return fail(TGB_ERR_INVALID_ARGUMENT, "tail split mode must be -1 (automatic), 0 (off) or 1 (every launch, any count)");
+    w->splitMode = mode;
     return TGB_OK;
 }
 
@@ -660,6 +796,16 @@ tgb_status tgb_finalize(tgb_world* w) {
         std::vector<float> far((size_t)n, 1e30f);
         TGB_CUDA(cudaMalloc(&w->d_min_clearance, (size_t)n * sizeof(float)));
         TGB_CUDA(cudaMemcpy(w->d_min_clearance, far.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (w->nPairs > 0 && w->pairCap > 0) {
+        /* tail split: all CTAs of both kernels of a launch have to be resident (8 one-warp CTAs per SM), so the environments that get a
+           warp of their own are capped at what the device has left over */
+        w->splitSlowCap = std::max(16, std::min(n, w->smCount));
+        TGB_CUDA(cudaMalloc(&w->d_coupled, (size_t)n * sizeof(int)));
+        TGB_CUDA(cudaMemset(w->d_coupled, 0, (size_t)n * sizeof(int)));
+        TGB_CUDA(cudaMalloc(&w->d_split_count, 2 * tgb_world::kSplitSlots * sizeof(int)));
+        TGB_CUDA(cudaMalloc(&w->d_split_slow, (size_t)tgb_world::kSplitSlots * w->splitSlowCap * sizeof(int)));
+        TGB_CUDA(cudaMalloc(&w->d_split_fast, (size_t)n * sizeof(int)));
     }
     {
         /* persistent manifolds: empty (key -1) */
@@ -1058,7 +1204,7 @@ tgb_status tgb_rollout_host(tgb_world* w, const double* rod_state_in, const doub
             TGB_CUDA(w->ops->pack_cables(io, dCabStage + off, 0, 0, s));
         }
         if (n_steps > 0) {
-            st = launchStepRange(w, dt, n_steps, b, cnt, s);
+            st = launchStepRange(w, dt, n_steps, b, cnt, s, chunks > 1 ? 1 + k : 0);
             if (st != TGB_OK) return st;
         }
         if (rod_state_out) {

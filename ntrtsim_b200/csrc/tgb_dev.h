@@ -119,6 +119,12 @@ struct tgb_step_args {
     void* warm;                          /* T[n_env][TGB_WARM_STATE_WORDS]: the persistent manifolds between launches, or NULL */
     double warm_factor;                  /* btContactSolverInfo::m_warmstartingFactor (0.85); 0 = every solve starts from zero */
     float* min_clearance;                /* [n_env] running minimum of the surface distance between two bodies' capsules, or NULL */
+    /* Launches over a list of environments (tgb_capi.cu, "tail split"): slot i of the grid simulates environment env_list[i] for
+       i < min(*env_list_count, env_list_slots); CTAs beyond the count leave at once.  NULL: slot i is environment env_begin + i. */
+    const int* env_list;
+    const int* env_list_count;
+    int env_list_slots;
+    int* coupled_steps;                  /* [n_env] steps of this launch in which the environment had rows between two bodies, or NULL */
     double dt;
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */
     double ground_restitution;

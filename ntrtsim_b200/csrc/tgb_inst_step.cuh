@@ -44,7 +44,8 @@ cudaError_t launch_inst(const tgb_step_args& a, int threads, cudaStream_t s) {
         if (e != cudaSuccess) return e;
     }
     const int groupsPerBlock = threads / LPE;
-    const int grid = (a.n_env - a.env_begin + groupsPerBlock - 1) / groupsPerBlock;
+    const int slots = a.env_list != nullptr ? a.env_list_slots : a.n_env - a.env_begin;
+    const int grid = (slots + groupsPerBlock - 1) / groupsPerBlock;
     if (grid <= 0) return cudaSuccess;
     tgb::tgb_step_kernel<scalar_t, LPE, TGB_STEP_CLASS, GROUND, 0, OBST, WARM><<<grid, threads, smem, s>>>(a);
     return cudaGetLastError();
@@ -100,6 +101,7 @@ cudaError_t launch(const tgb_step_args& a, int threads, cudaStream_t s, int* wid
         }
         return cudaSuccess;
     }
+    if (a.wide && a.env_list != nullptr) return cudaErrorInvalidValue; /* lists of environments: narrow layouts only */
     if constexpr (TGB_STEP_CLASS != tgb::TGB_CLASS_CPG && (LPE == 4 || LPE == 8)) {
         if (a.wide) {
             if (a.ground_kind == TGB_GROUND_EMPTY) return launch_wide<LPE, false, 4>(a, s);

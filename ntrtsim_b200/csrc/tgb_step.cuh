@@ -596,16 +596,27 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     const bool bodyWarp = !WIDE || tid < 32; /* WIDE: warps 1..3 shadow the groups of warp 0 in the body role and never store */
     const int grp = WIDE ? (tid & 31) / LPE : tid / LPE;
     const int groupsPerBlock = WIDE ? 32 / LPE : blockDim.x / LPE;
-    const int envRaw = a.env_begin + blockIdx.x * groupsPerBlock + grp;
+    /* launches over a list of environments: slot -> environment through env_list; CTAs beyond the list's length leave at once
+       (before any barrier), groups beyond it shadow the list's last environment */
+    int listCount = 0;
+    if (a.env_list != nullptr) {
+        listCount = *a.env_list_count;
+        if (listCount > a.env_list_slots) listCount = a.env_list_slots;
+        if ((int)blockIdx.x * groupsPerBlock >= listCount) return;
+    }
+    const int slotRaw = blockIdx.x * groupsPerBlock + grp;
+    const int envRaw = a.env_list != nullptr ? (slotRaw < listCount ? a.env_list[slotRaw] : a.n_env) : a.env_begin + slotRaw;
+    const int envShadow = a.env_list != nullptr ? a.env_list[listCount - 1] : a.n_env - 1;
     const bool live = bodyWarp && envRaw < a.n_env;
-    const int env = envRaw < a.n_env ? envRaw : a.n_env - 1; /* tail groups shadow the last env and never store */
+    const int env = envRaw < a.n_env ? envRaw : envShadow; /* tail groups shadow the last env and never store */
     /* cable role: the lanes that share an environment's cables */
     constexpr int CL = WIDE ? WIDE * LPE : LPE;
     const int cLane = WIDE ? tid % CL : lane;
     const int cGrp = WIDE ? tid / CL : grp;
-    const int cEnvRaw = a.env_begin + blockIdx.x * groupsPerBlock + cGrp;
+    const int cSlotRaw = blockIdx.x * groupsPerBlock + cGrp;
+    const int cEnvRaw = a.env_list != nullptr ? (cSlotRaw < listCount ? a.env_list[cSlotRaw] : a.n_env) : a.env_begin + cSlotRaw;
     const bool cLive = cEnvRaw < a.n_env;
-    const int cEnv = cLive ? cEnvRaw : a.n_env - 1;
+    const int cEnv = cLive ? cEnvRaw : envShadow;
     /* lanes of this group inside the warp, for shuffles */
     const unsigned fullMask = 0xffffffffu;
     const int warpLane = tid & 31;
@@ -988,6 +999,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
     T pairClearance = T(1e30); /* smallest surface distance of two bodies' capsules this lane has seen */
+    int coupledSteps = 0;      /* steps of this launch with rows between two bodies (uniform within the group) */
 #ifdef TGB_STATS
     const long long statT0 = clock64();
     unsigned long long wCoupled = 0, wCoupledCyc = 0, wDetectCyc = 0, wMem = 0, wMany = 0, wCableCyc = 0;
@@ -1071,6 +1083,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             }
         }
 #endif
+        coupledSteps += nPairRows > 0 ? 1 : 0;
         if (dynamic) {
             /* applyGravity + solver-body external impulses */
             V3<T> totalForce(T(0), gfy, T(0)), totalTorque(T(0), T(0), T(0));
@@ -1405,13 +1418,14 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 #ifdef TGB_STATS
                 __syncwarp();
                 const unsigned long long statMem = co.statMem ? 1ULL : 0ULL;
+                const unsigned statCoupledLanes = __ballot_sync(fullMask, nPairRows > 0); /* by every lane: lane 0 alone must not call it */
                 wCoupled += 1; wCoupledCyc += (unsigned long long)(clock64() - statS0); wMem += statMem;
                 if (a.stats && warpLane == 0) {
                     /* [55] warp-steps with a coupled environment, [56] of which with one in the shared-memory solver, [57] coupled
                        environments summed over warp-steps, [104] cycles of the coupled solve */
                     atomicAdd(a.stats + 55, 1ULL);
                     if (statMem) atomicAdd(a.stats + 56, 1ULL);
-                    atomicAdd(a.stats + 57, (unsigned long long)(__popc(__ballot_sync(fullMask, nPairRows > 0)) / LPE));
+                    atomicAdd(a.stats + 57, (unsigned long long)(__popc(statCoupledLanes) / LPE));
                     atomicAdd(a.stats + 104, (unsigned long long)(clock64() - statS0));
                     atomicAdd(a.stats + 110, (unsigned long long)(statS0 - statA)); /* body phase before the coupled solve, coupled warp-steps only */
                 }
@@ -1961,6 +1975,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             for (int off = LPE / 2; off > 0; off >>= 1) clr = fminf(clr, __shfl_xor_sync(fullMask, clr, off));
             if (live && lane == 0 && clr < a.min_clearance[env]) a.min_clearance[env] = clr;
         }
+        if (a.coupled_steps != nullptr && live && lane == 0 && doWorld) a.coupled_steps[env] = coupledSteps;
     }
     if (WIDE) __syncthreads(); else __syncwarp();
     if (live) {

@@ -65,7 +65,7 @@ class FlatModel(object):
 
 class BatchedWorld(object):
     def __init__(self, model, n_env, precision="f32", device=0, solver_iterations=0, lanes_per_env=0, block_threads=0, wide=None,
-                 pair_contact_cap=None, warm_starting=None):
+                 pair_contact_cap=None, warm_starting=None, tail_split=None):
         self._lib = capi.load()
         self.model = model
         self.n_env = int(n_env)
@@ -87,6 +87,8 @@ class BatchedWorld(object):
                 capi.check(self._lib.tgb_set_pair_contact_cap(h, int(pair_contact_cap)))
             if warm_starting is not None:
                 capi.check(self._lib.tgb_set_warm_starting(h, float(warm_starting)))
+            if tail_split is not None:
+                capi.check(self._lib.tgb_set_tail_split(h, int(tail_split)))
             capi.check(self._lib.tgb_finalize(h))
         except Exception:
             self.close()

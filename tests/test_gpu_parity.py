@@ -1487,3 +1487,45 @@ def test_population_members_vertebrae_contact_statistics():
           % (n_env, steps, int((clr < 0.02).sum()), int((clr < -0.1).sum()), worst, np.round(clr[worst], 3), np.round(clr_o, 3)))
     assert int((clr < -0.1).sum()) <= 3
     assert np.abs(clr[worst] - np.array(clr_o)).max() < 0.15
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_tail_split_is_bit_identical(precision):
+    """The tail split of long launches (tgb_set_tail_split: environments whose rods leaned on each other in the last launch get a warp
+    of their own on a second stream, the others run from a list in the usual layout) changes durations only: rod states, cable
+    observations, clearances and the world's status are bit for bit those of unsplit launches -- through tgb_step and through
+    tgb_rollout_host, in the forced mode (every launch, threshold of one step) and in the automatic one."""
+    sys.path.insert(0, ROOT)
+    import bench
+    n_env, steps = 640, 250
+    model, rods, cab, ctrl, params, _ = bench.build_workload("superball", n_env, bench.SEED)
+
+    def run(split, host):
+        w = nt.BatchedWorld(model, n_env, precision=precision, tail_split=split, wide=False)   # (the split is for the narrow layouts)
+        w.set_controller(ctrl, params)
+        if host:
+            r, c = rods.copy(), cab.copy()
+            for _ in range(3):
+                ro, co = w.rollout_host(r, c, model.dt, steps)
+                r = ro
+                c = np.ascontiguousarray(co[..., 0:2])
+        else:
+            w.set_rod_state(rods)
+            w.set_cable_state(cab)
+            for _ in range(3):
+                w.step(model.dt, steps)
+            ro, co = w.get_rod_state(), w.get_cable_obs()
+        # (the clearance is measured on the steps a pair is tested on; beyond the contact band those depend on the warp's other pairs)
+        out = (ro, co, np.minimum(w.min_clearance(), 0.02), w.status(), w.launch_count())
+        w.close()
+        return out
+
+    for host in (False, True):
+        ref = run(0, host)
+        assert (ref[2] <= 0.02).sum() >= 5          # rods do meet in this sample
+        for mode in (1, -1):
+            got = run(mode, host)
+            for a, b in zip(ref[:4], got[:4]):
+                assert np.array_equal(a, b)
+            if mode == 1:
+                assert got[4] > ref[4]               # the split launches ran: lists + two kernels per launch
