@@ -179,12 +179,17 @@ def ncu_traffic_per_launch(workload, H):
     if os.path.exists(path):
         try:
             d = json.load(open(path))
-            key = "%s_H%d" % (workload, H)
+            key = "%s_H%s" % (workload, H)
             if key in d:
                 return d[key]
         except Exception:
             pass
     return None
+
+
+def ncu_warp_instructions_per_launch(workload, H):
+    """warp instructions one launch of the step kernel executes (committed ncu capture of this configuration), or None"""
+    return ncu_traffic_per_launch(workload, "%d_warp_instructions" % H)
 
 
 def cpu_port_rate(model, rods, cab, ctrl, params, H, n_env_sample, threads):
@@ -489,6 +494,18 @@ def main():
                          "peak_source": peak_src,
                          "note": "effective figure: env state stays on chip for the H fused steps, real DRAM traffic is ~1/H of it"},
         }
+        # what actually binds this kernel: instruction issue.  warp instructions per env-step from the committed ncu capture of this
+        # configuration x measured env-steps/s against the SMs' issue rate (4 schedulers x 1 warp instruction per cycle per SM)
+        wi = ncu_warp_instructions_per_launch(args.workload, H)
+        if wi is not None and clocks and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            per_env_step = wi / float(n_env * H)
+            issue_peak = sms * 4 * clocks["sm_mhz"] * 1e6
+            rate = n_env * H / (k_ms * 1e-3)
+            line["roofline"]["issue"] = {"warp_instr_per_env_step": per_env_step, "issue_peak_warp_instr_per_s": issue_peak,
+                                         "achieved_warp_instr_per_s": per_env_step * rate, "frac": per_env_step * rate / issue_peak,
+                                         "note": "the binding limit (HBM carries ~1/H of the algorithmic bytes): fraction of the SMs' issue slots; "
+                                                 "instruction count from profiles/ (ncu, same command), rate measured here"}
         line["config"]["timing"] = "one CUDA-event bracket on the world's stream around the K steps incl. the L2 flushes, same at every N; max over ranks"
         allk = np.array(per_rank_kernel)
         line["per_rank_kernel_ms"] = {"min": float(allk.min()), "median": float(np.median(allk)), "max": float(allk.max()),

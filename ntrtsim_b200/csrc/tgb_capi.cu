@@ -405,12 +405,13 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
    tested in one, nothing of another environment's contact code is executed), on a second stream of higher priority; everything
    else runs in the usual layout.  Both kernels take their environments from lists a small kernel writes (tgb_step_args.env_list).
    Results do not depend on which lanes simulate an environment (tested bit for bit), so the split changes durations only. */
-__global__ void tgb_classify_envs_kernel(const int* coupled, int envBegin, int envCount, int threshold, int slowCap, int* count, int* slow,
-                                         int* fast) {
+__global__ void tgb_classify_envs_kernel(const int* coupled, int envBegin, int envCount, int threshold, int recentThreshold, int slowCap, int* count,
+                                         int* slow, int* fast) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= envCount) return;
     const int env = envBegin + i;
-    if (coupled[env] >= threshold) {
+    const int total = coupled[env] & 0xfffff, recent = coupled[env] >> 20;
+    if (total >= threshold || recent >= recentThreshold) {
         const int k = atomicAdd(count, 1);
         if (k < slowCap) { slow[k] = env; return; }
     }
@@ -441,8 +442,10 @@ tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount
     int* fast = w->d_split_fast + envBegin;
     const int slowCap = w->splitMode == 1 ? std::min(w->splitSlowCap, envCount) : std::min(w->splitSlowCap, std::max(1, envCount / 20));
     const int threshold = w->splitMode == 1 ? 1 : std::max(1, lastSteps / 8);
+    /* ... or for a quarter of its last 256 steps: an environment whose rods met late in the last launch is likely to start this one so */
+    const int recentThreshold = w->splitMode == 1 ? 1 : std::max(1, std::min(lastSteps, 256) / 4);
     TGB_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(int), s));
-    tgb_classify_envs_kernel<<<(envCount + 255) / 256, 256, 0, s>>>(w->d_coupled, envBegin, envCount, threshold, slowCap, count, slow, fast);
+    tgb_classify_envs_kernel<<<(envCount + 255) / 256, 256, 0, s>>>(w->d_coupled, envBegin, envCount, threshold, recentThreshold, slowCap, count, slow, fast);
     TGB_CUDA(cudaGetLastError());
     {
         static const char* dbg = std::getenv("TGB_SPLIT_DEBUG"); /* tuning aid: synchronises */
@@ -456,16 +459,29 @@ tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount
     }
     TGB_CUDA(cudaEventRecord(w->splitFork[slot], s));
     TGB_CUDA(cudaStreamWaitEvent(w->splitStream[slot], w->splitFork[slot], 0));
+    static const char* dbgT = std::getenv("TGB_SPLIT_DEBUG");
+    cudaEvent_t dbgEv[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (dbgT) { for (int i = 0; i < 4; ++i) cudaEventCreate(&dbgEv[i]); cudaEventRecord(dbgEv[0], w->splitStream[slot]); }
     tgb_step_args as = a;
     as.env_list = slow; as.env_list_count = count; as.env_list_slots = slowCap;
     cudaError_t e = w->ops->step(as, 32, 32, w->splitStream[slot]);
     if (e != cudaSuccess) return cudaFail(e, "step kernel launch (coupled environments)");
+    if (dbgT) cudaEventRecord(dbgEv[1], w->splitStream[slot]);
     TGB_CUDA(cudaEventRecord(w->splitJoin[slot], w->splitStream[slot]));
     tgb_step_args af = a;
     af.env_list = fast; af.env_list_count = count + 1; af.env_list_slots = envCount;
+    if (dbgT) cudaEventRecord(dbgEv[2], s);
     e = w->ops->step(af, w->lanes, w->threads, s);
     if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
+    if (dbgT) cudaEventRecord(dbgEv[3], s);
     TGB_CUDA(cudaStreamWaitEvent(s, w->splitJoin[slot], 0));
+    if (dbgT) {
+        cudaStreamSynchronize(s);
+        float ts = 0, tf = 0;
+        cudaEventElapsedTime(&ts, dbgEv[0], dbgEv[1]); cudaEventElapsedTime(&tf, dbgEv[2], dbgEv[3]);
+        std::fprintf(stderr, "tgb tail split: one warp per environment %.3f ms, usual layout %.3f ms\n", ts, tf);
+        for (int i = 0; i < 4; ++i) cudaEventDestroy(dbgEv[i]);
+    }
     w->launches += 3;
     return TGB_OK;
 }

@@ -124,7 +124,9 @@ struct tgb_step_args {
     const int* env_list;
     const int* env_list_count;
     int env_list_slots;
-    int* coupled_steps;                  /* [n_env] steps of this launch in which the environment had rows between two bodies, or NULL */
+    int* coupled_steps;                  /* [n_env] steps of this launch in which the environment had rows between two bodies or a body
+                                            with three or more contact points (the steps that hold a warp up) in the low 20 bits, those
+                                            among the launch's last 256 steps above them; or NULL */
     double dt;
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */
     double ground_restitution;

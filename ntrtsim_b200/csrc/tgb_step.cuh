@@ -343,6 +343,123 @@ TGB_D T boxDistance(const V3<T>& p, const V3<T>& co, const V3<T>& e0, const V3<T
     return sd;
 }
 
+/* Single precision, three or four contact points of one body (a rod lying flat on the ground, a vertebra on two rod ends): the same
+   projected Gauss-Seidel in matrix form, everything in registers.  With A[r][s] = J_r M^-1 J_s^T over the rows (N0..N3, T0..T3) the
+   relative velocity change dv_r of every row is carried along and updated by one multiply-add per applied impulse; a row visit is a
+   dependent chain of ~5 operations instead of two dot products over shared-memory operands plus the body update (~15 operations and
+   two shared-memory round trips).  Rows are visited in the order of pgsSharedRows (normals 0..nc-1, then frictions 0..nc-1): equal to
+   it in exact arithmetic.  Measured need: warps holding a flat-lying rod ran 40 % longer than the median warp (TGB_STATS, round 2) --
+   after the body pairs the second reason a launch waits for a few warps.  NORMALS: rows carry their own normal and friction
+   coefficient (worlds with static obstacles).  Out of line: its registers are its own. */
+template <typename T, bool NORMALS>
+__device__ __noinline__ ContactSolveOut<T> solveContactsMatrix4(T* ct, int rowStride, int nc, int iterations, bool anyPen, V3<T> gn, T invMass, T muBody) {
+    constexpr int M = 4, K = 8;
+#define CTG(slot, f) ct[(slot) * rowStride + (f)]
+    T A[K][K], rhs[K], invD[K], lam[K], rhsP[M], muv[M];
+    {
+        T jl[K][3], ja[K][3], bl[K][3], ba[K][3];
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            const bool has = c < nc;
+            const int cc = has ? c : 0;
+            const T z = has ? T(1) : T(0); /* rows this body does not have: zero Jacobian, nothing couples to them */
+            const V3<T> n = NORMALS ? V3<T>(CTG(cc, CT_NRM + 0), CTG(cc, CT_NRM + 1), CTG(cc, CT_NRM + 2)) : gn;
+            const T nn[3] = {n.x, n.y, n.z};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                jl[c][j] = nn[j] * z; ja[c][j] = CTG(cc, CT_RXN + j) * z; ba[c][j] = CTG(cc, CT_ANGN + j) * z; bl[c][j] = jl[c][j] * invMass;
+                jl[M + c][j] = CTG(cc, CT_T + j) * z; ja[M + c][j] = CTG(cc, CT_RXT + j) * z; ba[M + c][j] = CTG(cc, CT_ANGT + j) * z;
+                bl[M + c][j] = jl[M + c][j] * invMass;
+            }
+            rhs[c] = has ? CTG(cc, CT_RHSN) : T(0); invD[c] = has ? CTG(cc, CT_INVDIAGN) : T(0); rhsP[c] = has ? CTG(cc, CT_RHSPEN) : T(0);
+            rhs[M + c] = has ? CTG(cc, CT_RHST) : T(0); invD[M + c] = has ? CTG(cc, CT_INVDIAGT) : T(0);
+            lam[c] = has ? CTG(cc, CT_LAMN) : T(0); lam[M + c] = has ? CTG(cc, CT_LAMT) : T(0); /* warm starting: what the row set-up left */
+            muv[c] = NORMALS ? (has ? CTG(cc, CT_MU) : T(0)) : muBody;
+        }
+#pragma unroll
+        for (int r = 0; r < K; ++r)
+#pragma unroll
+            for (int q = r; q < K; ++q) {
+                const T v = (jl[r][0] * bl[q][0] + jl[r][1] * bl[q][1] + jl[r][2] * bl[q][2]) + (ja[r][0] * ba[q][0] + ja[r][1] * ba[q][1] + ja[r][2] * ba[q][2]);
+                A[r][q] = v;
+                A[q][r] = v;
+            }
+    }
+    V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
+    if (anyPen) {
+        /* split impulse: the normal rows alone, with their own impulses and relative velocities */
+        T lamP[M], dvP[M];
+#pragma unroll
+        for (int c = 0; c < M; ++c) { lamP[c] = T(0); dvP[c] = T(0); }
+        for (int it = 0; it < iterations; ++it) {
+#pragma unroll
+            for (int c = 0; c < M; ++c) {
+                if (c >= nc || rhsP[c] == T(0)) continue;
+                T delta = rhsP[c] - dvP[c] * invD[c];
+                const T sum = lamP[c] + delta;
+                if (sum < T(0)) { delta = -lamP[c]; lamP[c] = T(0); }
+                else lamP[c] = sum;
+#pragma unroll
+                for (int r = 0; r < M; ++r) dvP[r] += A[r][c] * delta;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            if (c >= nc) continue;
+            const V3<T> n = NORMALS ? V3<T>(CTG(c, CT_NRM + 0), CTG(c, CT_NRM + 1), CTG(c, CT_NRM + 2)) : gn;
+            push += n * (invMass * lamP[c]);
+            turn += V3<T>(CTG(c, CT_ANGN + 0), CTG(c, CT_ANGN + 1), CTG(c, CT_ANGN + 2)) * lamP[c];
+        }
+    }
+    T dv[K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        T v = T(0);
+#pragma unroll
+        for (int q = 0; q < K; ++q) v += A[r][q] * lam[q];
+        dv[r] = v;
+    }
+    for (int it = 0; it < iterations; ++it) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            if (c >= nc) continue;
+            T delta = rhs[c] - dv[c] * invD[c];
+            const T sum = lam[c] + delta;
+            if (sum < T(0)) { delta = -lam[c]; lam[c] = T(0); }
+            else lam[c] = sum;
+#pragma unroll
+            for (int r = 0; r < K; ++r) dv[r] += A[r][c] * delta;
+        }
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            if (c >= nc || !(lam[c] > T(0))) continue;
+            const T lo = -muv[c] * lam[c], hi = muv[c] * lam[c];
+            T delta = rhs[M + c] - dv[M + c] * invD[M + c];
+            const T sum = lam[M + c] + delta;
+            if (sum < lo) { delta = lo - lam[M + c]; lam[M + c] = lo; }
+            else if (sum > hi) { delta = hi - lam[M + c]; lam[M + c] = hi; }
+            else lam[M + c] = sum;
+#pragma unroll
+            for (int r = 0; r < K; ++r) dv[r] += A[r][M + c] * delta;
+        }
+    }
+    /* the body's velocity change from the accumulated impulses; the final impulses go back into the rows (persistent manifold) */
+#pragma unroll
+    for (int c = 0; c < M; ++c) {
+        if (c >= nc) continue;
+        const V3<T> n = NORMALS ? V3<T>(CTG(c, CT_NRM + 0), CTG(c, CT_NRM + 1), CTG(c, CT_NRM + 2)) : gn;
+        const V3<T> t(CTG(c, CT_T + 0), CTG(c, CT_T + 1), CTG(c, CT_T + 2));
+        dLin += n * (invMass * lam[c]) + t * (invMass * lam[M + c]);
+        dAng += V3<T>(CTG(c, CT_ANGN + 0), CTG(c, CT_ANGN + 1), CTG(c, CT_ANGN + 2)) * lam[c] +
+                V3<T>(CTG(c, CT_ANGT + 0), CTG(c, CT_ANGT + 1), CTG(c, CT_ANGT + 2)) * lam[M + c];
+        CTG(c, CT_LAMN) = lam[c]; CTG(c, CT_LAMT) = lam[M + c];
+    }
+#undef CTG
+    ContactSolveOut<T> o;
+    o.dLin = dLin; o.dAng = dAng; o.push = push; o.turn = turn;
+    return o;
+}
+
 /* Contact solve of a body with two or more contact points (a rod lying on a rim line, a compound body): rare next to the
    single-point case, so it lives out of line -- the step loop's hot instructions stay within the instruction cache.
    ct = row 0 of this body, rowStride = words between consecutive rows of one body. */
@@ -488,6 +605,8 @@ __device__ __noinline__ ContactSolveOut<T> solveContactsGeneral(T* ct, int rowSt
 #pragma unroll
         for (int c = 0; c < 2; ++c)
             if (c < nc) { ct[c * rowStride + CT_LAMN] = lamN[c]; ct[c * rowStride + CT_LAMT] = lamT[c]; }
+    } else if (kFast && TGB_MATRIX_PGS && nc <= 4) {
+        return solveContactsMatrix4<T, false>(ct, rowStride, nc, iterations, anyPen, gn, invMass, mu);
     } else {
         pgsSharedRows<T>(ct, rowStride, nc, iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
     }
@@ -528,11 +647,16 @@ __host__ __device__ inline bool tgb_cpg_topo_staged(const tgb_step_args& a) {
 }
 
 /* doubles of shared memory per env group: controller row, sine cumulative phases, CPG work space */
-__host__ __device__ inline int tgb_group_double_words(const tgb_step_args& a) {
+__host__ __device__ inline int tgb_group_double_words(const tgb_step_args& a, int lpe) {
     int n = a.ctrl_stride + 8;
     if (a.ctrl_kind == TGB_CTRL_ESCAPE_SINE) n += TGB_SINE_REC * 24 + 2 * 8; /* per cable (sin, cos[, amplitude, offset]) of the phase, per cluster (cos, sin) of the phase step */
     if (a.ctrl_kind == TGB_CTRL_CPG_IMPEDANCE) n += 3 * a.cpg_n_pairs + (3 + 3 + 3 + 21 + 1 + 3) * a.C;
-    return (n + 1) & ~1; /* even: the int region behind the doubles stays 16-byte aligned */
+    n = (n + 1) & ~1; /* even: the int region behind the doubles stays 16-byte aligned */
+    /* A 64-bit access of a warp goes through the banks half a warp at a time; lanes of a group read consecutive doubles (the sine
+       controller's phase pairs), so the groups that share a half warp must start lpe doubles apart modulo the 16 doubles of a bank
+       row (ncu, rounds 1 and 2: LDS.64 / STS.64 of the phase pairs at 50 % excessive wavefronts with the regions 176 doubles apart) */
+    if (lpe < 16 && a.ctrl_kind == TGB_CTRL_ESCAPE_SINE) while ((n & 15) != lpe) n += 2;
+    return n;
 }
 
 /* Views of the packed model in shared memory. */
@@ -669,7 +793,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     /* cables in flight per lane in the cable phase: 3 where the instruction footprint allows it (no contact code), else 1 --
        measured on B200: 3 is +7% without ground and -10% with ground (the hot loop then overflows the instruction cache) */
     constexpr int CU = TGB_CABLE_UNROLL ? TGB_CABLE_UNROLL : (GROUND ? 1 : 3);
-    const int groupDWords = tgb_group_double_words(a);
+    const int groupDWords = tgb_group_double_words(a, LPE);
     double* sD = reinterpret_cast<double*>(sModelT + modelTWords + groupsPerBlock * groupTWords) + grp * groupDWords;
     /* the same regions of the cable role's environment */
     T* cStateP = sModelT + modelTWords + cGrp * groupTWords;
@@ -999,7 +1123,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
     T pairClearance = T(1e30); /* smallest surface distance of two bodies' capsules this lane has seen */
-    int coupledSteps = 0;      /* steps of this launch with rows between two bodies (uniform within the group) */
+    int coupledSteps = 0, coupledRecent = 0; /* steps of this launch that hold a warp up (see below), in all and among the last 256; uniform within the group */
 #ifdef TGB_STATS
     const long long statT0 = clock64();
     unsigned long long wCoupled = 0, wCoupledCyc = 0, wDetectCyc = 0, wMem = 0, wMany = 0, wCableCyc = 0;
@@ -1083,7 +1207,6 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             }
         }
 #endif
-        coupledSteps += nPairRows > 0 ? 1 : 0;
         if (dynamic) {
             /* applyGravity + solver-body external impulses */
             V3<T> totalForce(T(0), gfy, T(0)), totalTorque(T(0), T(0), T(0));
@@ -1386,6 +1509,15 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             statNc = nc; statPen = anyPen;
 #endif
         } /* dynamic: external impulses and the rows against the static world */
+            /* a step that holds its warp up: rows between two bodies, or a body with three or more contact points (a rod standing on
+               an end cap) -- environments in which such steps last are given a warp of their own by the host (tgb_capi.cu, tail split) */
+            if (a.coupled_steps != nullptr) {
+                const unsigned groupMaskH = (LPE == 32) ? 0xffffffffu : (((1u << LPE) - 1u) << groupLane0);
+                const unsigned manyMask = __ballot_sync(fullMask, nc >= 3); /* (by every lane: not behind the || of a lane's own flag) */
+                const int heavy = (nPairRows > 0 || (manyMask & groupMaskH) != 0u) ? 1 : 0;
+                coupledSteps += heavy;
+                if (step >= a.n_steps - 256) coupledRecent += heavy; /* what the environment is like now says most about the next launch */
+            }
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
             bool solved = false;
@@ -1480,7 +1612,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 dAng = angN * lamN + angT * lamT;
                 if (warmOn) { CT(0, CT_LAMN) = lamN; CT(0, CT_LAMT) = lamT; }
             } else if (OBST) {
-                if (nc > 0) pgsRowsWithNormals<T>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
+                if (kFast && TGB_MATRIX_PGS && nc > 0 && nc <= 4) {
+                    const ContactSolveOut<T> o = solveContactsMatrix4<T, true>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, gn, invMass, mu);
+                    dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
+                } else if (nc > 0) pgsRowsWithNormals<T>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
             } else if (nc > 0) {
                 const ContactSolveOut<T> o = solveContactsGeneral<T, kFast>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, gn, invMass, mu);
                 dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
@@ -1975,7 +2110,8 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             for (int off = LPE / 2; off > 0; off >>= 1) clr = fminf(clr, __shfl_xor_sync(fullMask, clr, off));
             if (live && lane == 0 && clr < a.min_clearance[env]) a.min_clearance[env] = clr;
         }
-        if (a.coupled_steps != nullptr && live && lane == 0 && doWorld) a.coupled_steps[env] = coupledSteps;
+        if (a.coupled_steps != nullptr && live && lane == 0 && doWorld)
+            a.coupled_steps[env] = (coupledSteps < 0xfffff ? coupledSteps : 0xfffff) | (coupledRecent << 20);
     }
     if (WIDE) __syncthreads(); else __syncwarp();
     if (live) {
@@ -2023,7 +2159,7 @@ inline size_t tgb_step_smem_bytes(const tgb_step_args& a, int lpe, int threads, 
                       (a.warm != nullptr ? TGB_WARM_STATE_WORDS(a.cap_contacts, a.n_obst > 0 ? a.n_dyn : a.R, (a.n_pairs > 0 && a.pair_cap > 0) ? a.pair_cap : 0) : 0);
     groupTWords = (groupTWords + 3) & ~3;
     if (lpe < 32) { while ((groupTWords & 31) != (lpe < 4 ? 4 : lpe)) groupTWords += 4; }
-    const int groupDWords = tgb_group_double_words(a);
+    const int groupDWords = tgb_group_double_words(a, lpe);
     size_t bytes = (size_t)(modelTWords + groupsPerBlock * groupTWords) * sizeofT;
     bytes = (bytes + 7) & ~(size_t)7;
     bytes += (size_t)groupsPerBlock * groupDWords * sizeof(double);

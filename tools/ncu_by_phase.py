@@ -26,7 +26,7 @@ def main():
             if key in l and "/*" in l and not l.strip().startswith("*"):
                 bounds.append((i, name))
     bounds.sort()
-    loop_start = [i for i, l in enumerate(src, 1) if "for (int step = 0; step < a.n_steps" in l][0]
+    loop_start = [i for i, l in enumerate(src, 1) if "for (int step = 0; step < " in l][0]
 
     def phase_of(n):
         if n < loop_start:
