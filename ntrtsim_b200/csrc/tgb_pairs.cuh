@@ -108,7 +108,7 @@ struct PairRecord {
 };
 
 template <typename T, typename Model>
-TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance, T& dist, PairRecord<T>& rec) {
+TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance, T& dist, PairRecord<T>& rec, bool* deferCompound = nullptr) {
     rec.valid = false;
     const T* pa = sPose + 12 * ia;
     const T* pb = sPose + 12 * ib;
@@ -143,6 +143,12 @@ TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance
         }
         return near;
     }
+    if (deferCompound != nullptr) {
+        /* bodies of several shapes: the caller spreads the pairs of shapes over the lanes of the group (pairNearCompoundGroup) */
+        *deferCompound = true;
+        dist = T(0);
+        return false;
+    }
     bool near = false;
     T best = T(1e30);
     const int sa0 = M.bodyi(BI_SHAPE_BEGIN, ia), sa1 = sa0 + M.bodyi(BI_SHAPE_COUNT, ia);
@@ -164,6 +170,42 @@ TGB_D bool pairNear(const Model& M, const T* sPose, int ia, int ib, T& clearance
     clearance = best < clearance ? best : clearance;
     dist = best;
     return near;
+}
+
+/* The same test for two bodies made of several shapes, by all lanes of the environment's group together: the pairs of shapes go round
+   the lanes (a TetraSpine vertebra has six rods: 36 segment-segment tests per pair of bodies, which one lane used to walk alone while
+   the others waited -- the population evaluation lost half its rate to it), then the smallest distance and the near flag are reduced
+   over the group.  Same distances as pairNear's loop; the minimum of a set does not depend on the order. */
+template <typename T, typename Model, int LPE>
+TGB_D void pairNearCompoundGroup(const Model& M, const T* sPose, int ia, int ib, int lane, unsigned groupMask, T& bestOut, T& exactOut, bool& nearOut) {
+    const T* pa = sPose + 12 * ia;
+    const T* pb = sPose + 12 * ib;
+    const int sa0 = M.bodyi(BI_SHAPE_BEGIN, ia), na = M.bodyi(BI_SHAPE_COUNT, ia);
+    const int sb0 = M.bodyi(BI_SHAPE_BEGIN, ib), nb = M.bodyi(BI_SHAPE_COUNT, ib);
+    T best = T(1e30), exact = T(1e30);
+    bool near = false;
+    for (int t = lane; t < na * nb; t += LPE) {
+        const int sa = sa0 + t / nb, sb = sb0 + t % nb;
+        CoreSegment<T> ga, gb;
+        if (!coreSegment<T>(M, pa, sa, ga) || !coreSegment<T>(M, pb, sb, gb)) continue;
+        /* (no bounding test per pair of shapes: a lower bound from the spheres about two long rods is far below their distance and
+           would use the pair's slack up at once -- measured: the pairs were then tested on every step, 2.3e7 -> 1.4e7 env-steps/s) */
+        T s, tt, b, c, f;
+        closestSegmentParams<T>(ga, gb, s, tt, b, c, f);
+        const V3<T> dv = (ga.p + ga.d * s) - (gb.p + gb.d * tt);
+        const T dd = tsqrtNoBranch(dv.length2()) - ga.r - gb.r;
+        best = dd < best ? dd : best;
+        exact = dd < exact ? dd : exact;
+        near = near || dd <= pairBreakingThreshold<T>() + T(1e-3);
+    }
+#pragma unroll
+    for (int off = LPE / 2; off > 0; off >>= 1) {
+        const T ob = __shfl_xor_sync(groupMask, best, off), oe = __shfl_xor_sync(groupMask, exact, off);
+        best = ob < best ? ob : best;
+        exact = oe < exact ? oe : exact;
+    }
+    nearOut = (__ballot_sync(groupMask, near) & groupMask) != 0u;
+    bestOut = best; exactOut = exact;
 }
 
 /* The contacts of one pair of capsules (bodies ia < ib) as rows base + count, ... of the environment's pair rows; `count` counts the rows

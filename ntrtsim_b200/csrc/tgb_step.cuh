@@ -58,11 +58,29 @@
 #ifndef TGB_FACTORED_IINV
 #define TGB_FACTORED_IINV 1 /* single precision: apply the world inverse inertia as B (invI o (B^T v)) instead of holding the matrix */
 #endif
+#ifndef TGB_COOP_PAIRS
+#define TGB_COOP_PAIRS 1 /* bodies of several shapes: pairs of shapes spread over the group's lanes (pairNearCompoundGroup) */
+#endif
+#ifndef TGB_MATRIX4
+#define TGB_MATRIX4 0 /* three or four contact points of a body: matrix-form PGS in registers (solveContactsMatrix4).  Measured on B200,
+                         same box: SUPERball 6.05e8 without / 5.89e8 with, TetraSpine 2.35e7 / 1.89e7 -- forming the 36 couplings and the
+                         out-of-line call cost more than the shorter row visits save: off */
+#endif
 #ifndef TGB_CABLE_UNROLL
 #define TGB_CABLE_UNROLL 0 /* 0 = automatic */
 #endif
 
 namespace tgb {
+
+/* Dormand-Prince 5(4): row s = the coefficients of k1 .. k(s+1) in the state handed to stage s + 2; the last row is the fifth-order
+   solution (no k2 term) */
+static __constant__ double tgb_dopri_a[6][6] = {
+    {1.0 / 5.0, 0.0, 0.0, 0.0, 0.0, 0.0},
+    {3.0 / 40.0, 9.0 / 40.0, 0.0, 0.0, 0.0, 0.0},
+    {44.0 / 45.0, -56.0 / 15.0, 32.0 / 9.0, 0.0, 0.0, 0.0},
+    {19372.0 / 6561.0, -25360.0 / 2187.0, 64448.0 / 6561.0, -212.0 / 729.0, 0.0, 0.0},
+    {9017.0 / 3168.0, -355.0 / 33.0, 46732.0 / 5247.0, 49.0 / 176.0, -5103.0 / 18656.0, 0.0},
+    {35.0 / 384.0, 0.0, 500.0 / 1113.0, 125.0 / 192.0, -2187.0 / 6784.0, 11.0 / 84.0}};
 
 template <typename T> struct Vec16;
 template <> struct Vec16<float> { typedef float4 type; enum { N = 4 }; };
@@ -605,7 +623,7 @@ __device__ __noinline__ ContactSolveOut<T> solveContactsGeneral(T* ct, int rowSt
 #pragma unroll
         for (int c = 0; c < 2; ++c)
             if (c < nc) { ct[c * rowStride + CT_LAMN] = lamN[c]; ct[c * rowStride + CT_LAMT] = lamT[c]; }
-    } else if (kFast && TGB_MATRIX_PGS && nc <= 4) {
+    } else if (kFast && TGB_MATRIX_PGS && TGB_MATRIX4 && nc <= 4) {
         return solveContactsMatrix4<T, false>(ct, rowStride, nc, iterations, anyPen, gn, invMass, mu);
     } else {
         pgsSharedRows<T>(ct, rowStride, nc, iterations, anyPen, gn, invMass, mu, dLin, dAng, push, turn);
@@ -897,7 +915,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     if (cpgOn) {
         const double* cs = a.cpg_state + (size_t)env * TGB_CPG_STATE_DOUBLES(C);
         for (int i = lane; i < 3 * C; i += LPE) sPid[i] = cs[3 * C + 2 + i];
-        for (int i = lane; i < 3 * C; i += LPE) sX[i] = cs[i];
+        for (int i = lane; i < 3 * C; i += LPE) sX[(i % 3) * C + i / 3] = cs[i]; /* node-major in HBM, planes [variable][node] here */
         cpgUpdateTime = cs[3 * C];
         cpgCableTime = cs[3 * C + 1];
         for (int p = lane; p < a.cpg_n_pairs; p += LPE) {
@@ -908,7 +926,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             sPair[3 * p + 2] = sn;
         }
         __syncwarp();
-        for (int i = lane; i < C; i += LPE) sNodeValue[i] = sX[3 * i + 1] * cos(sX[3 * i]); /* CPGNode::updateNodeValues */
+        for (int i = lane; i < C; i += LPE) sNodeValue[i] = sX[C + i] * cos(sX[i]); /* CPGNode::updateNodeValues */
     }
     int statusAcc = 0;
 
@@ -999,12 +1017,14 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
     const int* topoBegin = stageTopo ? sTopo : a.cpg_topo;
     const int* topoTarget = topoBegin + (C + 1);
     const int* topoPair = topoTarget + a.cpg_n_couplings;
+    /* CPG state, stage state and the seven slopes live in planes [variable][node] (consecutive lanes on consecutive doubles: the
+       stride of three doubles of the node-major layout put LDS.64 / STS.64 at 50 % excessive wavefronts, ncu round 2) */
     auto cpgRhs = [&](const double* xin, double* kout, bool act) {
         if (act)
             for (int i = lane; i < C; i += LPE) {
                 double sn, cn;
-                sincos(xin[3 * i], &sn, &cn);
-                sTrig[i] = sn; sTrig[C + i] = cn; sTrig[2 * C + i] = xin[3 * i + 1]; /* planes: no bank conflicts in the gather below */
+                sincos(xin[i], &sn, &cn);
+                sTrig[i] = sn; sTrig[C + i] = cn; sTrig[2 * C + i] = xin[C + i];
             }
         __syncwarp();
         if (act) {
@@ -1021,22 +1041,26 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     const double sd = sj * ci - cj * si, cd = cj * ci + sj * si;
                     phiDot += sPair[3 * p] * rj * (sd * sPair[3 * p + 1] - cd * sPair[3 * p + 2]);
                 }
-                const double r = xin[3 * i + 1], rd = xin[3 * i + 2];
-                kout[3 * i] = phiDot;
-                kout[3 * i + 1] = rd;
-                kout[3 * i + 2] = a.cpg_r_const * (a.cpg_r_const / 4 * (radius - r) - rd);
+                const double r = xin[C + i], rd = xin[2 * C + i];
+                kout[i] = phiDot;
+                kout[C + i] = rd;
+                kout[2 * C + i] = a.cpg_r_const * (a.cpg_r_const / 4 * (radius - r) - rd);
             }
         }
         __syncwarp();
     };
     /* CPGEquations::update (CPGEquations.cpp:231-267) = Boost.Odeint integrate(): controlled Dormand-Prince 5(4), FSAL,
-       eps_abs = eps_rel = 1e-6 (see oracle/tg_odeint.h for the restated algorithm). `want` = this group updates now. */
+       eps_abs = eps_rel = 1e-6 (see oracle/tg_odeint.h for the restated algorithm). `want` = this group updates now.
+       The six stages run as a loop over the tableau (tgb_dopri_a) with ONE copy of the right-hand side: unrolled, the eight copies
+       of it (each with a double-precision sincos) made the kernel's loop larger than the instruction cache serves -- ncu round 2:
+       35 % of the stall samples of the TetraSpine population evaluation were "no instruction".  Same operations in the same order
+       (the fifth-order solution's k2 term, absent in odeint, is a product with 0 added to a finite sum: exact). */
     auto cpgUpdate = [&](double tEnd, bool want) {
         const double eps = 2.220446049250313e-16;
         double dtc = tEnd <= 0.1 ? tEnd : 0.1;
         double t = 0.0;
         int numSteps = 0;
-        double* k1 = sK; double* k2 = sK + 3 * C; double* k3 = sK + 6 * C; double* k4 = sK + 9 * C; double* k5 = sK + 12 * C;
+        double* k1 = sK; double* k3 = sK + 6 * C; double* k4 = sK + 9 * C; double* k5 = sK + 12 * C;
         double* k6 = sK + 15 * C; double* k7 = sK + 18 * C;
         cpgRhs(sX, k1, want);
         numSteps += 1;
@@ -1044,37 +1068,33 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         bool active = want && (tEnd - t > eps);
         while (__any_sync(fullMask, active)) {
             if (active && trials == 0 && (t + dtc) - tEnd > eps) dtc = tEnd - t;
-            const double b21 = 1.0 / 5.0, b31 = 3.0 / 40.0, b32 = 9.0 / 40.0, b41 = 44.0 / 45.0, b42 = -56.0 / 15.0, b43 = 32.0 / 9.0;
-            const double b51 = 19372.0 / 6561.0, b52 = -25360.0 / 2187.0, b53 = 64448.0 / 6561.0, b54 = -212.0 / 729.0;
-            const double b61 = 9017.0 / 3168.0, b62 = -355.0 / 33.0, b63 = 46732.0 / 5247.0, b64 = 49.0 / 176.0, b65 = -5103.0 / 18656.0;
+            for (int stg = 0; stg < 6; ++stg) {
+                if (active)
+                    for (int i = lane; i < C; i += LPE) {
+#pragma unroll
+                        for (int var = 0; var < 3; ++var) {
+                            const int v = var * C + i;
+                            double acc = 1.0 * sX[v];
+                            for (int j = 0; j <= stg; ++j) acc = acc + (dtc * tgb_dopri_a[stg][j]) * sK[3 * C * j + v];
+                            sXt[v] = acc;
+                        }
+                    }
+                cpgRhs(sXt, sK + 3 * C * (stg + 1), active);
+            }
             const double c1 = 35.0 / 384.0, c3 = 500.0 / 1113.0, c4 = 125.0 / 192.0, c5 = -2187.0 / 6784.0, c6 = 11.0 / 84.0;
             const double dc1 = c1 - 5179.0 / 57600.0, dc3 = c3 - 7571.0 / 16695.0, dc4 = c4 - 393.0 / 640.0,
                          dc5 = c5 - (-92097.0 / 339200.0), dc6 = c6 - 187.0 / 2100.0, dc7 = -1.0 / 40.0;
-            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
-                sXt[v] = 1.0 * sX[v] + (dtc * b21) * k1[v];
-            cpgRhs(sXt, k2, active);
-            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
-                sXt[v] = 1.0 * sX[v] + (dtc * b31) * k1[v] + (dtc * b32) * k2[v];
-            cpgRhs(sXt, k3, active);
-            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
-                sXt[v] = 1.0 * sX[v] + (dtc * b41) * k1[v] + (dtc * b42) * k2[v] + (dtc * b43) * k3[v];
-            cpgRhs(sXt, k4, active);
-            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
-                sXt[v] = 1.0 * sX[v] + (dtc * b51) * k1[v] + (dtc * b52) * k2[v] + (dtc * b53) * k3[v] + (dtc * b54) * k4[v];
-            cpgRhs(sXt, k5, active);
-            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
-                sXt[v] = 1.0 * sX[v] + (dtc * b61) * k1[v] + (dtc * b62) * k2[v] + (dtc * b63) * k3[v] + (dtc * b64) * k4[v] + (dtc * b65) * k5[v];
-            cpgRhs(sXt, k6, active);
-            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v)
-                sXt[v] = 1.0 * sX[v] + (dtc * c1) * k1[v] + (dtc * c3) * k3[v] + (dtc * c4) * k4[v] + (dtc * c5) * k5[v] + (dtc * c6) * k6[v];
-            cpgRhs(sXt, k7, active);
             if (active) numSteps += 6;
             /* error estimate, maximum over the group's nodes */
             double err = 0.0;
-            if (active) for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v) {
-                const double xe = (dtc * dc1) * k1[v] + (dtc * dc3) * k3[v] + (dtc * dc4) * k4[v] + (dtc * dc5) * k5[v] + (dtc * dc6) * k6[v] + (dtc * dc7) * k7[v];
-                const double e = fabs(xe) / (1e-6 + 1e-6 * (1.0 * fabs(sX[v]) + (1.0 * dtc) * fabs(k1[v])));
-                err = fmax(err, e);
+            if (active) for (int i = lane; i < C; i += LPE) {
+#pragma unroll
+                for (int var = 0; var < 3; ++var) {
+                    const int v = var * C + i;
+                    const double xe = (dtc * dc1) * k1[v] + (dtc * dc3) * k3[v] + (dtc * dc4) * k4[v] + (dtc * dc5) * k5[v] + (dtc * dc6) * k6[v] + (dtc * dc7) * k7[v];
+                    const double e = fabs(xe) / (1e-6 + 1e-6 * (1.0 * fabs(sX[v]) + (1.0 * dtc) * fabs(k1[v])));
+                    err = fmax(err, e);
+                }
             }
 #pragma unroll
             for (int off = LPE / 2; off > 0; off >>= 1) err = fmax(err, __shfl_xor_sync(fullMask, err, off));
@@ -1091,7 +1111,10 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     } else {
                         t += dtc;
                     }
-                    for (int i = lane; i < C; i += LPE) for (int v = 3 * i; v < 3 * i + 3; ++v) { sX[v] = sXt[v]; k1[v] = k7[v]; }
+                    for (int i = lane; i < C; i += LPE) {
+#pragma unroll
+                        for (int var = 0; var < 3; ++var) { const int v = var * C + i; sX[v] = sXt[v]; k1[v] = k7[v]; }
+                    }
                     trials = 0;
                     active = tEnd - t > eps;
                 }
@@ -1099,7 +1122,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             __syncwarp();
         }
         if (want) {
-            for (int i = lane; i < C; i += LPE) sNodeValue[i] = sX[3 * i + 1] * cos(sX[3 * i]);
+            for (int i = lane; i < C; i += LPE) sNodeValue[i] = sX[C + i] * cos(sX[i]);
             if (numSteps > a.cpg_max_steps) statusAcc |= TGB_STATUS_CPG_INEFFICIENT;
         }
         __syncwarp();
@@ -1164,13 +1187,29 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 T slack = T(1);
                 if (p < a.n_pairs) slack = sPairSlack[p] - (sMotion[ia] + sMotion[ib]);
                 if (__any_sync(fullMask, !(slack > T(0)))) {
+                    bool compound = false;
                     if (p < a.n_pairs) {
 #ifdef TGB_STATS
                         ++statTests;
 #endif
                         T dist;
-                        near = pairNear<T>(M, sPose, ia, ib, pairClearance, dist, rec);
+                        near = pairNear<T>(M, sPose, ia, ib, pairClearance, dist, rec, TGB_COOP_PAIRS ? &compound : nullptr);
                         slack = (dist - pairBreakingThreshold<T>() - T(4e-3)) * T(0.999);
+                    }
+                    /* bodies of several shapes: their pairs of shapes are tested by all lanes of the group together, pair after pair */
+                    unsigned compoundMask = __ballot_sync(fullMask, compound) & groupMaskP;
+                    while (compoundMask != 0u) { /* group-uniform */
+                        const int L = __ffs(compoundMask) - 1;
+                        compoundMask &= compoundMask - 1u;
+                        const int ja = __shfl_sync(groupMaskP, ia, L), jb = __shfl_sync(groupMaskP, ib, L);
+                        T best, exact;
+                        bool nr;
+                        pairNearCompoundGroup<T, ModelView<T>, LPE>(M, sPose, ja, jb, lane, groupMaskP, best, exact, nr);
+                        if (warpLane == L) {
+                            near = nr;
+                            pairClearance = exact < pairClearance ? exact : pairClearance;
+                            slack = (best - pairBreakingThreshold<T>() - T(4e-3)) * T(0.999);
+                        }
                     }
                 }
                 if (p < a.n_pairs) sPairSlack[p] = slack;
@@ -1612,7 +1651,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 dAng = angN * lamN + angT * lamT;
                 if (warmOn) { CT(0, CT_LAMN) = lamN; CT(0, CT_LAMT) = lamT; }
             } else if (OBST) {
-                if (kFast && TGB_MATRIX_PGS && nc > 0 && nc <= 4) {
+                if (kFast && TGB_MATRIX_PGS && TGB_MATRIX4 && nc > 0 && nc <= 4) {
                     const ContactSolveOut<T> o = solveContactsMatrix4<T, true>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, gn, invMass, mu);
                     dLin = o.dLin; dAng = o.dAng; push = o.push; turn = o.turn;
                 } else if (nc > 0) pgsRowsWithNormals<T>(sCt + rowIdx * NCT, rowBodies * NCT, nc, a.iterations, anyPen, invMass, dLin, dAng, push, turn);
@@ -2124,7 +2163,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         }
         if (cpgOn) {
             double* cs = a.cpg_state + (size_t)env * TGB_CPG_STATE_DOUBLES(C);
-            for (int i = lane; i < 3 * C; i += LPE) { cs[i] = sX[i]; cs[3 * C + 2 + i] = sPid[i]; }
+            for (int i = lane; i < 3 * C; i += LPE) { cs[i] = sX[(i % 3) * C + i / 3]; cs[3 * C + 2 + i] = sPid[i]; }
             if (lane == 0) { cs[3 * C] = cpgUpdateTime; cs[3 * C + 1] = cpgCableTime; }
         }
         if (lane == 0) {
