@@ -179,7 +179,7 @@ def ncu_traffic_per_launch(workload, H):
     if os.path.exists(path):
         try:
             d = json.load(open(path))
-            key = "%s_H%s" % (workload, H)
+            key = "%s_H%s" % (workload, H) if not str(H).startswith("_") else workload + str(H)
             if key in d:
                 return d[key]
         except Exception:
@@ -187,9 +187,9 @@ def ncu_traffic_per_launch(workload, H):
     return None
 
 
-def ncu_warp_instructions_per_launch(workload, H):
-    """warp instructions one launch of the step kernel executes (committed ncu capture of this configuration), or None"""
-    return ncu_traffic_per_launch(workload, "%d_warp_instructions" % H)
+def ncu_warp_instructions_per_env_step(workload):
+    """warp instructions of the step kernel per env-step (committed ncu capture of this workload at 4096 environments), or None"""
+    return ncu_traffic_per_launch(workload, "_warp_instructions_per_env_step")
 
 
 def cpu_port_rate(model, rods, cab, ctrl, params, H, n_env_sample, threads):
@@ -496,10 +496,9 @@ def main():
         }
         # what actually binds this kernel: instruction issue.  warp instructions per env-step from the committed ncu capture of this
         # configuration x measured env-steps/s against the SMs' issue rate (4 schedulers x 1 warp instruction per cycle per SM)
-        wi = ncu_warp_instructions_per_launch(args.workload, H)
-        if wi is not None and clocks and clocks.get("sm_mhz"):
+        per_env_step = ncu_warp_instructions_per_env_step(args.workload)
+        if per_env_step is not None and clocks and clocks.get("sm_mhz"):
             sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-            per_env_step = wi / float(n_env * H)
             issue_peak = sms * 4 * clocks["sm_mhz"] * 1e6
             rate = n_env * H / (k_ms * 1e-3)
             line["roofline"]["issue"] = {"warp_instr_per_env_step": per_env_step, "issue_peak_warp_instr_per_s": issue_peak,

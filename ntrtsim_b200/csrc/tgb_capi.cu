@@ -354,6 +354,19 @@ bool wideLayout(const tgb_world* w) {
     return ctas <= (long long)w->wideCtasPerSm[cls] * w->smCount;
 }
 
+/* thresholds of the tail split's classification (environment variables: tuning aids) */
+struct SplitTuning { int totalDiv, recentWindow, recentThreshold; };
+const SplitTuning& splitTuning() {
+    static const SplitTuning t = [] {
+        SplitTuning v = {8, 256, 64};
+        if (const char* e = std::getenv("TGB_SPLIT_TOTAL_DIV")) v.totalDiv = std::max(1, std::atoi(e));
+        if (const char* e = std::getenv("TGB_SPLIT_RECENT_WIN")) v.recentWindow = std::max(1, std::min(2047, std::atoi(e)));
+        if (const char* e = std::getenv("TGB_SPLIT_RECENT_THR")) v.recentThreshold = std::max(1, std::atoi(e));
+        return v;
+    }();
+    return t;
+}
+
 tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     tgb_step_args a;
     std::memset(&a, 0, sizeof(a));
@@ -376,6 +389,7 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.n_pairs = w->pairCap != 0 ? w->nPairs : 0; a.model_pair_off = w->modelPairOff; a.pair_cap = w->pairCap;
     a.min_clearance = w->d_min_clearance;
     a.coupled_steps = (a.n_pairs > 0 && a.pair_cap > 0) ? w->d_coupled : nullptr;
+    a.recent_window = splitTuning().recentWindow;
     a.warm = w->warmFactor > 0.0 ? w->d_warm : nullptr; a.warm_factor = w->warmFactor;
     a.n_dyn = 0;
     for (int b = 0; b < w->R; ++b) a.n_dyn += w->bodies[b].mass != 0.0;
@@ -441,9 +455,9 @@ tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount
     int* slow = w->d_split_slow + (size_t)slot * w->splitSlowCap;
     int* fast = w->d_split_fast + envBegin;
     const int slowCap = w->splitMode == 1 ? std::min(w->splitSlowCap, envCount) : std::min(w->splitSlowCap, std::max(1, envCount / 20));
-    const int threshold = w->splitMode == 1 ? 1 : std::max(1, lastSteps / 8);
+    const int threshold = w->splitMode == 1 ? 1 : std::max(1, lastSteps / splitTuning().totalDiv);
     /* ... or for a quarter of its last 256 steps: an environment whose rods met late in the last launch is likely to start this one so */
-    const int recentThreshold = w->splitMode == 1 ? 1 : std::max(1, std::min(lastSteps, 256) / 4);
+    const int recentThreshold = w->splitMode == 1 ? 1 : std::max(1, std::min(std::min(lastSteps, splitTuning().recentWindow), splitTuning().recentThreshold));
     TGB_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(int), s));
     tgb_classify_envs_kernel<<<(envCount + 255) / 256, 256, 0, s>>>(w->d_coupled, envBegin, envCount, threshold, recentThreshold, slowCap, count, slow, fast);
     TGB_CUDA(cudaGetLastError());
@@ -816,7 +830,9 @@ tgb_status tgb_finalize(tgb_world* w) {
     if (w->nPairs > 0 && w->pairCap > 0) {
         /* tail split: all CTAs of both kernels of a launch have to be resident (8 one-warp CTAs per SM), so the environments that get a
            warp of their own are capped at what the device has left over */
-        w->splitSlowCap = std::max(16, std::min(n, w->smCount));
+        /* (measured: with the cap of 148 reached the launch took twice as long -- not every CTA of the second kernel found a place
+           beside seven or eight of the first; half of that has always fitted) */
+        w->splitSlowCap = std::max(16, std::min(n, w->smCount / 2));
         TGB_CUDA(cudaMalloc(&w->d_coupled, (size_t)n * sizeof(int)));
         TGB_CUDA(cudaMemset(w->d_coupled, 0, (size_t)n * sizeof(int)));
         TGB_CUDA(cudaMalloc(&w->d_split_count, 2 * tgb_world::kSplitSlots * sizeof(int)));

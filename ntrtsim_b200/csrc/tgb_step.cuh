@@ -921,9 +921,9 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         for (int p = lane; p < a.cpg_n_pairs; p += LPE) {
             double sn, cn;
             sincos(sCtrl[2 + 2 * p + 1], &sn, &cn);
-            sPair[3 * p] = sCtrl[2 + 2 * p];
-            sPair[3 * p + 1] = cn;
-            sPair[3 * p + 2] = sn;
+            sPair[p] = sCtrl[2 + 2 * p];             /* planes [weight | cos | sin][pair]: lanes read consecutive pairs */
+            sPair[a.cpg_n_pairs + p] = cn;
+            sPair[2 * a.cpg_n_pairs + p] = sn;
         }
         __syncwarp();
         for (int i = lane; i < C; i += LPE) sNodeValue[i] = sX[C + i] * cos(sX[i]); /* CPGNode::updateNodeValues */
@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                     const int j = topoTarget[k], p = topoPair[k];
                     const double sj = sTrig[j], cj = sTrig[C + j], rj = sTrig[2 * C + j];
                     const double sd = sj * ci - cj * si, cd = cj * ci + sj * si;
-                    phiDot += sPair[3 * p] * rj * (sd * sPair[3 * p + 1] - cd * sPair[3 * p + 2]);
+                    phiDot += sPair[p] * rj * (sd * sPair[a.cpg_n_pairs + p] - cd * sPair[2 * a.cpg_n_pairs + p]);
                 }
                 const double r = xin[C + i], rd = xin[2 * C + i];
                 kout[i] = phiDot;
@@ -1555,7 +1555,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 const unsigned manyMask = __ballot_sync(fullMask, nc >= 3); /* (by every lane: not behind the || of a lane's own flag) */
                 const int heavy = (nPairRows > 0 || (manyMask & groupMaskH) != 0u) ? 1 : 0;
                 coupledSteps += heavy;
-                if (step >= a.n_steps - 256) coupledRecent += heavy; /* what the environment is like now says most about the next launch */
+                if (step >= a.n_steps - a.recent_window) coupledRecent += heavy; /* what the environment is like now says most about the next launch */
             }
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
