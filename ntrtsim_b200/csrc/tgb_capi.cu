@@ -355,12 +355,11 @@ bool wideLayout(const tgb_world* w) {
 }
 
 /* thresholds of the tail split's classification (environment variables: tuning aids) */
-struct SplitTuning { int totalDiv, recentWindow, recentThreshold; };
+struct SplitTuning { int totalDiv, recentThreshold; };
 const SplitTuning& splitTuning() {
     static const SplitTuning t = [] {
-        SplitTuning v = {8, 256, 64};
+        SplitTuning v = {8, 8};
         if (const char* e = std::getenv("TGB_SPLIT_TOTAL_DIV")) v.totalDiv = std::max(1, std::atoi(e));
-        if (const char* e = std::getenv("TGB_SPLIT_RECENT_WIN")) v.recentWindow = std::max(1, std::min(2047, std::atoi(e)));
         if (const char* e = std::getenv("TGB_SPLIT_RECENT_THR")) v.recentThreshold = std::max(1, std::atoi(e));
         return v;
     }();
@@ -389,7 +388,6 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
     a.n_pairs = w->pairCap != 0 ? w->nPairs : 0; a.model_pair_off = w->modelPairOff; a.pair_cap = w->pairCap;
     a.min_clearance = w->d_min_clearance;
     a.coupled_steps = (a.n_pairs > 0 && a.pair_cap > 0) ? w->d_coupled : nullptr;
-    a.recent_window = splitTuning().recentWindow;
     a.warm = w->warmFactor > 0.0 ? w->d_warm : nullptr; a.warm_factor = w->warmFactor;
     a.n_dyn = 0;
     for (int b = 0; b < w->R; ++b) a.n_dyn += w->bodies[b].mass != 0.0;
@@ -456,8 +454,10 @@ tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount
     int* fast = w->d_split_fast + envBegin;
     const int slowCap = w->splitMode == 1 ? std::min(w->splitSlowCap, envCount) : std::min(w->splitSlowCap, std::max(1, envCount / 20));
     const int threshold = w->splitMode == 1 ? 1 : std::max(1, lastSteps / splitTuning().totalDiv);
-    /* ... or for a quarter of its last 256 steps: an environment whose rods met late in the last launch is likely to start this one so */
-    const int recentThreshold = w->splitMode == 1 ? 1 : std::max(1, std::min(std::min(lastSteps, splitTuning().recentWindow), splitTuning().recentThreshold));
+    /* ... or on its last steps in a row: an environment whose rods met late in the last launch starts this one so (TGB_STATS, round 2:
+       launch after launch one warp of the usual layout held an environment that was coupled for 840 - 1000 of the 1000 steps and had
+       been for fewer than 125 of the launch before) */
+    const int recentThreshold = w->splitMode == 1 ? 1 : std::max(1, std::min(lastSteps, splitTuning().recentThreshold));
     TGB_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(int), s));
     tgb_classify_envs_kernel<<<(envCount + 255) / 256, 256, 0, s>>>(w->d_coupled, envBegin, envCount, threshold, recentThreshold, slowCap, count, slow, fast);
     TGB_CUDA(cudaGetLastError());
@@ -510,6 +510,10 @@ int splitChunk(const tgb_world* w) {
 }
 
 tgb_status launchStep(tgb_world* w, double dt, int nSteps, int phases = 3) {
+    if (w->d_stats && std::getenv("TGB_STATS_RESET")) { /* instrumentation: the counters of the last launch only */
+        cudaMemsetAsync(w->d_stats, 0, (128 + 8 * 4096) * sizeof(unsigned long long), w->stream);
+        cudaMemsetAsync(w->d_stats + 53, 0xff, sizeof(unsigned long long), w->stream);
+    }
     tgb_step_args a = stepArgs(w, dt, nSteps);
     a.phases = phases;
     if (splitWanted(w, a, w->cfg.n_env)) {

@@ -124,10 +124,9 @@ struct tgb_step_args {
     const int* env_list;
     const int* env_list_count;
     int env_list_slots;
-    int recent_window;                   /* steps at the end of a launch that count as recent in coupled_steps (<= 2047) */
     int* coupled_steps;                  /* [n_env] steps of this launch in which the environment had rows between two bodies or a body
                                             with three or more contact points (the steps that hold a warp up) in the low 20 bits, those
-                                            among the launch's last recent_window steps above them; or NULL */
+                                            the number of such steps in a row up to the launch's last step (capped at 2047) above them; or NULL */
     double dt;
     double gn[3], goff;   /* ground surface { x : gn.x = goff } */
     double ground_restitution;

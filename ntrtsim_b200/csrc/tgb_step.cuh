@@ -1146,7 +1146,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
 
     const bool doWorld = (a.phases & 1) != 0, doModels = (a.phases & 2) != 0;
     T pairClearance = T(1e30); /* smallest surface distance of two bodies' capsules this lane has seen */
-    int coupledSteps = 0, coupledRecent = 0; /* steps of this launch that hold a warp up (see below), in all and among the last 256; uniform within the group */
+    int coupledSteps = 0, coupledRecent = 0; /* steps of this launch that hold a warp up (see below): in all, and in a row up to the last one; uniform within the group */
 #ifdef TGB_STATS
     const long long statT0 = clock64();
     unsigned long long wCoupled = 0, wCoupledCyc = 0, wDetectCyc = 0, wMem = 0, wMany = 0, wCableCyc = 0;
@@ -1555,7 +1555,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
                 const unsigned manyMask = __ballot_sync(fullMask, nc >= 3); /* (by every lane: not behind the || of a lane's own flag) */
                 const int heavy = (nPairRows > 0 || (manyMask & groupMaskH) != 0u) ? 1 : 0;
                 coupledSteps += heavy;
-                if (step >= a.n_steps - a.recent_window) coupledRecent += heavy; /* what the environment is like now says most about the next launch */
+                coupledRecent = heavy ? coupledRecent + 1 : 0; /* heavy steps in a row up to now: what the environment is like at the end of the launch says most about the next one */
             }
             /* ---- projected Gauss-Seidel: split-impulse rows, then velocity rows ---- */
             V3<T> dLin(T(0), T(0), T(0)), dAng(T(0), T(0), T(0)), push(T(0), T(0), T(0)), turn(T(0), T(0), T(0));
@@ -2101,8 +2101,9 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
         atomicAdd(a.stats + 51, cyc); atomicMax(a.stats + 52, cyc); atomicMin(a.stats + 53, cyc); atomicAdd(a.stats + 54, 1ULL);
         const int bucket = (int)min(31ULL, cyc * 16ULL / (unsigned long long)(a.n_steps * 14000LL)); /* cycles per step / 14000 * 16 */
         atomicAdd(a.stats + 64 + bucket, 1ULL);
-        if (blockIdx.x < 4096 && tid < 32) {
-            unsigned long long* r = a.stats + 128 + 8 * blockIdx.x;
+        const int statCta = blockIdx.x + (a.env_list != nullptr && LPE == 32 ? 2048 : 0); /* tail split: the one-warp-per-environment launch apart */
+        if (statCta < 4096 && tid < 32) {
+            unsigned long long* r = a.stats + 128 + 8 * statCta;
             atomicAdd(r + 0, cyc); atomicAdd(r + 1, wCoupled); atomicAdd(r + 2, wCoupledCyc); atomicAdd(r + 3, wDetectCyc);
             atomicAdd(r + 4, wMem); atomicAdd(r + 5, wMany); atomicAdd(r + 6, wCableCyc);
         }
@@ -2150,7 +2151,7 @@ __global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step
             if (live && lane == 0 && clr < a.min_clearance[env]) a.min_clearance[env] = clr;
         }
         if (a.coupled_steps != nullptr && live && lane == 0 && doWorld)
-            a.coupled_steps[env] = (coupledSteps < 0xfffff ? coupledSteps : 0xfffff) | (coupledRecent << 20);
+            a.coupled_steps[env] = (coupledSteps < 0xfffff ? coupledSteps : 0xfffff) | ((coupledRecent < 2047 ? coupledRecent : 2047) << 20);
     }
     if (WIDE) __syncthreads(); else __syncwarp();
     if (live) {

@@ -63,6 +63,8 @@ def evaluate_population(model, controller, param_rows, n_steps, dt=None, precisi
             status = w.status()
         finally:
             w.close()
+    if world_size == 1:   # the whole population was evaluated here, whatever process group the caller may have initialised
+        return np.asarray(local, dtype=np.float64).reshape(-1, 2), status
     return allgather_scores(local, P, group=group), status
 
 

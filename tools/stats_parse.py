@@ -7,7 +7,12 @@ def flush_ctas():
     tot = sorted(r[1] for r in ctas)
     print('  per-CTA total cycles: median %.3g, p90 %.3g, p99 %.3g, max %.3g' % (tot[len(tot)//2], tot[int(len(tot)*0.9)], tot[int(len(tot)*0.99)], tot[-1]))
     print('  slowest CTAs: id total | coupled steps, coupled-solve cycles, detection cycles, mem-solver steps, steps with >=3 contacts, cable cycles')
-    for r in ctas[:8]: print('   ', r)
+    for r in ctas[:12]: print('   ', r)
+    slow = [r for r in ctas if r[0] >= 2048]
+    if slow:
+        print('  one-warp-per-environment launch (ids from 2048): %d CTAs, slowest %.3g, median %.3g' % (len(slow), max(r[1] for r in slow), sorted(r[1] for r in slow)[len(slow)//2]))
+        usual = sorted((r for r in ctas if r[0] < 2048), key=lambda r: -r[1])
+        print('  usual layout: slowest %.3g, p99 %.3g, median %.3g' % (usual[0][1], usual[len(usual)//100][1], usual[len(usual)//2][1]))
     ctas = []
 for line in open(sys.argv[1]):
     if line.startswith('TGB_CTA'):
