@@ -347,6 +347,10 @@ bool wideLayout(const tgb_world* w) {
         if (w->ops->wide_ctas_per_sm(a, w->lanes, &ctas) != cudaSuccess) { cudaGetLastError(); ctas = 0; }
         w->wideCtasPerSm[cls] = ctas;
     }
+    /* with contact between bodies compiled in, the four-warp kernel no longer pays (its 168 registers spill 632 bytes; capped at two CTAs
+       per SM instead it has 255 and still loses): 256 / 512 / 1024 / 1184 environments 3.9e7 / 7.8e7 / 1.49e8 / 1.73e8 against
+       3.8e7 / 1.12e8 / 1.98e8 / 2.27e8 for the narrow layout (round 2, same box).  Automatic choice: narrow; tgb_set_wide_layout(1) still forces it */
+    if (w->nPairs > 0 && w->pairCap != 0) return false;
     /* without ground the narrow layout already keeps three cables per lane in flight: no gain measured (3-prism, 256..1024 envs) */
     if (w->ground.kind == TGB_GROUND_EMPTY) return false;
     const int envsPerCta = 32 / w->lanes;

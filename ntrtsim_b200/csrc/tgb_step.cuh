@@ -721,13 +721,16 @@ TGB_HOST_DEVICE_INLINE int tgb_ctrl_class(int kind) {
 #ifndef TGB_FUSE_DOUBLE_MOVE
 #define TGB_FUSE_DOUBLE_MOVE 1
 #endif
+#ifndef TGB_WIDE_MINBLOCKS
+#define TGB_WIDE_MINBLOCKS 3
+#endif
 #ifndef TGB_NARROW_MINBLOCKS
 #define TGB_NARROW_MINBLOCKS 1
 #endif
 template <typename T, int LPE, int CLASS, bool GROUND, int WIDE = 0 /* 0 or 4 warps */, bool OBST = false /* static obstacles, narrow layout only */,
           bool WARM = false /* persistent manifolds with warm starting (tgb_set_warm_starting), narrow layout only: compiled out of the default
                                kernels -- even skipped at run time its code cost 6 % of the step (registers, instruction footprint) */>
-__global__ void __launch_bounds__(128, WIDE ? 3 : TGB_NARROW_MINBLOCKS) tgb_step_kernel(const tgb_step_args a) {
+__global__ void __launch_bounds__(128, WIDE ? TGB_WIDE_MINBLOCKS : TGB_NARROW_MINBLOCKS) tgb_step_kernel(const tgb_step_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef typename Vec16<T>::type vec_t;
     const int VN = Vec16<T>::N;

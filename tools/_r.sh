@@ -1,4 +1,6 @@
-(timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3)
-python bench.py > gpurun_out/bench_r02f.json 2> gpurun_out/bench_r02f.err; python -c "import json; d=json.load(open('gpurun_out/bench_r02f.json')); print('superball', d['value'], d['e2e']['value'], d['roofline']['kernel_ms'], d['roofline'].get('issue',{}).get('frac'), d['per_rank_kernel_ms'], d['cpu_baseline']['value'])"
-python bench.py --impl reference --steps 3 > gpurun_out/bench_r02f_reference.json 2>> gpurun_out/bench_r02f.err; cat gpurun_out/bench_r02f_reference.json | cut -c1-300
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+for e in 256 512 1024 1184; do
+for v in default wide2; do
+if [ $v = default ]; then unset TGB_LIB_DIR; else export TGB_LIB_DIR=$PWD/variants/$v; fi
+timeout 100 python bench.py --envs $e --no-cpu-baseline | python -c "import json,sys; d=json.load(sys.stdin); print('$e $v', '%.4g'%d['value'], d['roofline']['kernel_ms'], d['config']['block_threads'], d['config']['grid'])"
+TGB_WIDE=0 timeout 100 python bench.py --envs $e --no-cpu-baseline | python -c "import json,sys; d=json.load(sys.stdin); print('$e $v narrow', '%.4g'%d['value'], d['roofline']['kernel_ms'], d['config']['block_threads'], d['config']['grid'])"
+done; done
