@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define TGB_ABI_VERSION 5
+#define TGB_ABI_VERSION 6
 
 typedef enum {
     TGB_OK = 0,
@@ -343,6 +343,58 @@ tgb_status tgb_set_warm_starting(tgb_world* w, double factor);
    environment that any step has seen since tgb_finalize or the last call with reset != 0 (1e30: no pair has come near; measured for
    pairs whose bounding spheres overlap).  Negative = the shapes overlap by that much. */
 tgb_status tgb_get_min_clearance(tgb_world* w, int32_t env_begin, int32_t env_count, double* out, int32_t reset);
+
+/* ---- Contact cables (ABI version 6) --------------------------------------------------------------------------
+   tgBulletContactSpringCable (src/core/tgBulletContactSpringCable.cpp:97-190) as built by tgBasicContactCableInfo
+   (src/tgcreator/tgBasicContactCableInfo.cpp:86-131): a spring-cable between two permanent anchors that collides with the rigid bodies
+   of its world and bends around them over *sliding* anchors (src/core/tgBulletSpringCableAnchor.cpp:89-334).  Every step, in the models
+   half (tgBulletContactSpringCable::step, :97-125):
+     updateManifolds (:196-365)   contact points between the cable's segments (cylinders of radius `thickness` between consecutive
+                                  anchors) and every body; a point with negative distance proposes a sliding anchor at the point on the
+                                  body's surface, contact normal pointing from the cable into the body;
+     updateAnchorList (:367-482)  a proposal joins the anchor list behind its nearest past anchor unless it lies within `resolution` of
+                                  a sliding neighbour on the same body, the cable would have to push there (a neighbour lies behind
+                                  the contact plane), a same-body neighbour's normal opposes its own, or the cable would grow by more than
+                                  2 x resolution over the previous step's length;
+     pruneAnchors (:563-673)      anchors whose body no longer touches the cable go; the rest slide sideways along
+                                  ((back - forward) x normal) until the cable is straight in the tangent plane (updateAnchorPositions,
+                                  :484-561, accepted while a contact point of the body lies within 0.1 of the new position); anchors
+                                  closer than resolution / 2 to a neighbour or with a neighbour behind the contact plane go; repeated
+                                  until four passes in a row remove nothing;
+     calculateAndApplyForce (:127-194)  tension k (sum of segment lengths - rest length) >= 0 plus the clamped damping term; the end
+                                  anchors are pulled along their segments, a sliding anchor gets magnitude x (unit(forward - current)
+                                  + unit(back - current)); impulses force x dt at the anchors -- they sum to zero
+                                  (test_integration/MuscleNP/MuscleNP_test.cpp:108-112 pins the momentum).
+   Bullet's ghost object and persistent manifolds are restated geometrically, the way the contact between bodies is (see
+   tgb_set_pair_contact_cap): a cylinder counts as the capsule inscribed in it, a sphere as itself, boxes take no part; the "manifold" of
+   (cable, body) is the set of closest-point pairs of this step's segments with the body's shapes that are nearer than Bullet's contact
+   breaking threshold (0.02), evaluated at the poses of the cable's step (Bullet's are one world step old).  At most
+   TGB_CCABLE_MAX_SLIDING sliding anchors per cable: further proposals are dropped.  The actuator is tgBasicActuator with no control
+   input (its step is the cable's step, src/core/tgBasicActuator.cpp:227-241).  Worlds with contact cables run one launch of the step
+   kernel plus one of the contact-cable kernel per step. */
+#define TGB_CCABLE_MAX_SLIDING 6
+/* per-cable observation: rest length, actual length (over all anchors), tension, velocity, number of sliding anchors */
+#define TGB_CCABLE_OBS_DOUBLES 5
+/* per-anchor record of tgb_get_contact_cable_anchors: body index, world position (3), contact normal (3) */
+#define TGB_CCABLE_ANCHOR_DOUBLES 7
+typedef struct {
+    int32_t body_a, body_b;
+    double local_a[3], local_b[3]; /* the two permanent anchors in their bodies' frames */
+    double stiffness, damping;
+    double rest_length;    /* |p2 - p1| - pretension / k */
+    double prev_length;    /* == rest_length (tgBulletSpringCable.cpp:47, the first-step damping artefact) */
+    double thickness;      /* tgBulletContactSpringCable.h:89: 0.001 */
+    double resolution;     /* tgBulletContactSpringCable.h:90: 0.1 */
+} tgb_contact_cable_desc;
+
+/* Append contact cables (body indices relative to the model added LAST with tgb_add_model_flat).  Before tgb_finalize. */
+tgb_status tgb_add_contact_cables(tgb_world* w, const tgb_contact_cable_desc* cables, int32_t n_cables);
+tgb_status tgb_num_contact_cables(const tgb_world* w, int32_t* out);
+/* obs: [env_count][n_contact_cables][TGB_CCABLE_OBS_DOUBLES] */
+tgb_status tgb_get_contact_cable_obs(tgb_world* w, int32_t env_begin, int32_t env_count, double* obs);
+/* the sliding anchors of one contact cable, in order from anchor 1 to anchor 2: out[env_count][TGB_CCABLE_MAX_SLIDING][7], unused
+   slots zero with body index -1 (tgSpringCable::getAnchors without the two permanent ends) */
+tgb_status tgb_get_contact_cable_anchors(tgb_world* w, int32_t cable, int32_t env_begin, int32_t env_count, double* out);
 
 /* Threads per CTA of the step kernel (32, 64, 96, 128; a multiple of lanes per env); 0 = automatic
    (also settable through the environment variable TGB_BLOCK_THREADS). */

@@ -47,6 +47,17 @@ class CableDesc(C.Structure):
                 ("motor_radius", C.c_double), ("motor_friction", C.c_double), ("motor_inertia", C.c_double)]
 
 
+class ContactCableDesc(C.Structure):
+    _fields_ = [("body_a", C.c_int32), ("body_b", C.c_int32), ("local_a", C.c_double * 3), ("local_b", C.c_double * 3),
+                ("stiffness", C.c_double), ("damping", C.c_double), ("rest_length", C.c_double), ("prev_length", C.c_double),
+                ("thickness", C.c_double), ("resolution", C.c_double)]
+
+
+CCABLE_MAX_SLIDING = 6
+CCABLE_OBS_DOUBLES = 5
+CCABLE_ANCHOR_DOUBLES = 7
+
+
 class CpgDesc(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("n_couplings", C.c_int32), ("coupling_begin", C.POINTER(C.c_int32)),
                 ("coupling_target", C.POINTER(C.c_int32)), ("coupling_pair", C.POINTER(C.c_int32)), ("n_pairs", C.c_int32),
@@ -71,6 +82,7 @@ ABI_SYMBOLS = [
     "tgb_scores_device_ptr", "tgb_scores_refresh_async", "tgb_step_timed", "tgb_launch_count", "tgb_launch_geometry", "tgb_set_lanes_per_env",
     "tgb_set_block_threads", "tgb_set_wide_layout", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
     "tgb_set_pair_contact_cap", "tgb_get_min_clearance", "tgb_set_warm_starting", "tgb_set_tail_split",
+    "tgb_add_contact_cables", "tgb_num_contact_cables", "tgb_get_contact_cable_obs", "tgb_get_contact_cable_anchors",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -141,6 +153,10 @@ def load():
     lib.tgb_get_min_clearance.argtypes = [_vp, _i32, _i32, _vp, _i32]
     lib.tgb_set_warm_starting.argtypes = [_vp, C.c_double]
     lib.tgb_set_tail_split.argtypes = [_vp, _i32]
+    lib.tgb_add_contact_cables.argtypes = [_vp, C.POINTER(ContactCableDesc), _i32]
+    lib.tgb_num_contact_cables.argtypes = [_vp, C.POINTER(_i32)]
+    lib.tgb_get_contact_cable_obs.argtypes = [_vp, _i32, _i32, _vp]
+    lib.tgb_get_contact_cable_anchors.argtypes = [_vp, _i32, _i32, _i32, _vp]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tgb_abi_version", "tgb_last_error", "tgb_device_count"):
@@ -165,6 +181,8 @@ def load_host():
     h.tgh_free.argtypes = [_vp]
     h.tgh_counts.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     h.tgh_copy.argtypes = [_vp, C.POINTER(BodyDesc), C.POINTER(ShapeDesc), C.POINTER(CableDesc), C.POINTER(GroundDesc), _dp, _dp]
+    h.tgh_contact_cables.argtypes = [_vp, C.POINTER(ContactCableDesc), C.c_int]
+    h.tgh_contact_cables.restype = C.c_int
     h.tgh_tree_counts.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     h.tgh_escape_transform_actions.argtypes = [_vp, C.c_double, _vp]
     h.tgh_escape_transform_actions.restype = None

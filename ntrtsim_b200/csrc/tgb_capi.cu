@@ -46,6 +46,10 @@ struct tgb_world {
     std::vector<tgb_body_desc> bodies;
     std::vector<tgb_shape_desc> shapes;
     std::vector<tgb_cable_desc> cables;
+    std::vector<tgb_contact_cable_desc> contactCables; /* tgb_add_contact_cables; body indices already absolute */
+    int lastModelBody0 = 0;
+    double* d_cc_state = nullptr;  /* [n_env][nCC][TGB_CC_STATE] (tgb_ccable.cuh) */
+    double* d_cc_model = nullptr;  /* [nCC][TGB_CC_MODEL] */
     bool finalized = false;
     const tgb_ops* ops = nullptr;
     size_t scalarBytes = 4;
@@ -112,6 +116,14 @@ struct tgb_world {
         a.env_begin = envBegin; a.env_count = envCount;
         return a;
     }
+    tgb::tgb_ccable_args ccArgs(int envBegin, int envCount, double dt) const {
+        tgb::tgb_ccable_args a;
+        a.state = d_state; a.frame = d_frame; a.model_t = d_model_t; a.model_i = d_model_i;
+        a.cc_state = d_cc_state; a.cc_model = d_cc_model;
+        a.n_env = cfg.n_env; a.env_begin = envBegin; a.env_count = envCount; a.R = R; a.S = S; a.stride = stride;
+        a.n_cc = (int)contactCables.size(); a.dt = dt;
+        return a;
+    }
     tgb_status ensureStage(size_t doubles) {
         if (doubles > stageDoubles) {
             if (d_stage) cudaFree(d_stage);
@@ -157,6 +169,8 @@ struct tgb_world {
         if (d_cpg_topo) cudaFree(d_cpg_topo);
         if (d_cpg_imp) cudaFree(d_cpg_imp);
         if (d_cpg_state) cudaFree(d_cpg_state);
+        if (d_cc_state) cudaFree(d_cc_state);
+        if (d_cc_model) cudaFree(d_cc_model);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (int i = 0; i < kPipe; ++i) {
@@ -513,7 +527,34 @@ int splitChunk(const tgb_world* w) {
     return w->splitMode == 1 ? 100 : (1 << 30); /* measured on B200 (bench workload, 1000 steps): launches of 125 / 250 / 500 / 1000 steps 8.0 / 6.9 / 6.4 / 6.4 ms */
 }
 
+/* Worlds with contact cables: the cable's step (tgBulletContactSpringCable::step) follows the models half of every single step, so a
+   call of n steps is n launches of the step kernel, each followed by one of the contact-cable kernel (tgb_ccable.cuh). */
+tgb_status launchWithContactCables(tgb_world* w, double dt, int nSteps, int phases, int envBegin, int envCount, cudaStream_t s) {
+    tgb_step_args a = stepArgs(w, dt, 1);
+    a.phases = phases;
+    a.env_begin = envBegin;
+    a.n_env = envBegin + envCount;
+    a.coupled_steps = nullptr; /* no tail split here: launches of one step */
+    const tgb::tgb_ccable_args ca = w->ccArgs(envBegin, envCount, dt);
+    for (int i = 0; i < nSteps; ++i) {
+        cudaError_t e = w->ops->step(a, w->lanes, w->threads, s);
+        if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
+        w->launches += 1;
+        if (phases & 2) {
+            e = w->ops->ccable_step(ca, s);
+            if (e != cudaSuccess) return cudaFail(e, "contact cable kernel launch");
+            w->launches += 1;
+        }
+    }
+    return TGB_OK;
+}
+
 tgb_status launchStep(tgb_world* w, double dt, int nSteps, int phases = 3) {
+    if (!w->contactCables.empty()) {
+        tgb_status st = launchWithContactCables(w, dt, nSteps, phases, 0, w->cfg.n_env, w->stream);
+        if (st == TGB_OK && (phases & 1)) w->time += dt * nSteps;
+        return st;
+    }
     if (w->d_stats && std::getenv("TGB_STATS_RESET")) { /* instrumentation: the counters of the last launch only */
         cudaMemsetAsync(w->d_stats, 0, (128 + 8 * 4096) * sizeof(unsigned long long), w->stream);
         cudaMemsetAsync(w->d_stats + 53, 0xff, sizeof(unsigned long long), w->stream);
@@ -541,6 +582,7 @@ tgb_status launchStep(tgb_world* w, double dt, int nSteps, int phases = 3) {
 /* the same for the environments [envBegin, envBegin + envCount) only, on stream s; does not advance the world's clock.  slot: which
    of the world's list buffers the range may use (1 + chunk of tgb_rollout_host) */
 tgb_status launchStepRange(tgb_world* w, double dt, int nSteps, int envBegin, int envCount, cudaStream_t s, int slot) {
+    if (!w->contactCables.empty()) return launchWithContactCables(w, dt, nSteps, 3, envBegin, envCount, s);
     tgb_step_args a = stepArgs(w, dt, nSteps);
     if (splitWanted(w, a, envCount)) {
         const int chunk = splitChunk(w);
@@ -642,6 +684,7 @@ tgb_status tgb_add_model_flat(tgb_world* w, const tgb_body_desc* bodies, int32_t
     if (n_bodies < 0 || n_shapes < 0 || n_cables < 0 || (n_bodies && !bodies) || (n_shapes && !shapes) || (n_cables && !cables))
         return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_model_flat: bad array arguments");
     const int body0 = (int)w->bodies.size(), shape0 = (int)w->shapes.size();
+    w->lastModelBody0 = body0;
     for (int i = 0; i < n_bodies; ++i) {
         const tgb_body_desc& b = bodies[i];
         if (b.mass < 0.0 || b.shape_begin < 0 || b.shape_count < 0 || b.shape_begin + b.shape_count > n_shapes)
@@ -675,6 +718,35 @@ tgb_status tgb_add_model_flat(tgb_world* w, const tgb_body_desc* bodies, int32_t
         c.body_a += body0; c.body_b += body0;
         w->cables.push_back(c);
     }
+    return TGB_OK;
+}
+
+tgb_status tgb_add_contact_cables(tgb_world* w, const tgb_contact_cable_desc* cables, int32_t n_cables) {
+    if (!w) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_contact_cables: NULL world");
+    if (w->finalized) return fail(TGB_ERR_STATE, "tgb_add_contact_cables: world already finalized");
+    if (n_cables < 0 || (n_cables && !cables)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_contact_cables: bad array arguments");
+    const int nb = (int)w->bodies.size() - w->lastModelBody0;
+    for (int i = 0; i < n_cables; ++i) {
+        const tgb_contact_cable_desc& c = cables[i];
+        if (c.body_a < 0 || c.body_a >= nb || c.body_b < 0 || c.body_b >= nb)
+            return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_add_contact_cables: cable body index out of range");
+        /* tgBulletContactSpringCable::invariant (tgBulletContactSpringCable.cpp:939-952) */
+        if (!(c.stiffness > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "stiffness is not positive.");
+        if (c.damping < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "damping is negative.");
+        if (c.rest_length < 0.0 || c.prev_length < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "Pretension causes string to shorten past rest length!");
+        if (c.thickness < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "thickness is negative.");
+        if (!(c.resolution > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "resolution is not positive.");
+    }
+    for (int i = 0; i < n_cables; ++i) {
+        tgb_contact_cable_desc c = cables[i];
+        c.body_a += w->lastModelBody0; c.body_b += w->lastModelBody0;
+        w->contactCables.push_back(c);
+    }
+    return TGB_OK;
+}
+tgb_status tgb_num_contact_cables(const tgb_world* w, int32_t* out) {
+    if (!w || !out) return fail(TGB_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = (int32_t)w->contactCables.size();
     return TGB_OK;
 }
 
@@ -877,6 +949,25 @@ tgb_status tgb_finalize(tgb_world* w) {
         if (smem > 227 * 1024) return fail(TGB_ERR_UNSUPPORTED, "tgb_finalize: model too large for one CTA's shared memory");
     }
 
+    if (!w->contactCables.empty()) {
+        const int ncc = (int)w->contactCables.size();
+        std::vector<double> cm((size_t)ncc * tgb::TGB_CC_MODEL, 0.0), cs((size_t)ncc * tgb::TGB_CC_STATE, 0.0);
+        for (int i = 0; i < ncc; ++i) {
+            const tgb_contact_cable_desc& c = w->contactCables[i];
+            double* m = &cm[(size_t)i * tgb::TGB_CC_MODEL];
+            m[tgb::CCM_A] = c.body_a; m[tgb::CCM_B] = c.body_b;
+            for (int k = 0; k < 3; ++k) { m[tgb::CCM_LA + k] = c.local_a[k]; m[tgb::CCM_LB + k] = c.local_b[k]; }
+            m[tgb::CCM_K] = c.stiffness; m[tgb::CCM_C] = c.damping; m[tgb::CCM_THICK] = c.thickness; m[tgb::CCM_RES] = c.resolution;
+            cs[(size_t)i * tgb::TGB_CC_STATE + tgb::CCS_REST] = c.rest_length;
+            cs[(size_t)i * tgb::TGB_CC_STATE + tgb::CCS_PREV] = c.prev_length;
+        }
+        TGB_CUDA(cudaMalloc(&w->d_cc_model, cm.size() * sizeof(double)));
+        TGB_CUDA(cudaMemcpy(w->d_cc_model, cm.data(), cm.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<double> all((size_t)n * cs.size());
+        for (int e = 0; e < n; ++e) std::copy(cs.begin(), cs.end(), all.begin() + (size_t)e * cs.size());
+        TGB_CUDA(cudaMalloc(&w->d_cc_state, all.size() * sizeof(double)));
+        TGB_CUDA(cudaMemcpy(w->d_cc_state, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     /* replicate the model's initial state into every environment */
     std::vector<double> rods((size_t)w->R * TGB_NBS, 0.0), cab((size_t)std::max(1, w->C) * 2, 0.0);
     for (int b = 0; b < w->R; ++b) {
@@ -945,6 +1036,33 @@ tgb_status tgb_get_rod_state(tgb_world* w, int32_t env_begin, int32_t env_count,
     if (st != TGB_OK) return st;
     TGB_CUDA(w->ops->unpack_rods(w->ioArgs(env_begin, env_count), w->d_stage, w->stream));
     TGB_CUDA(cudaMemcpyAsync(state, w->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_get_contact_cable_obs(tgb_world* w, int32_t env_begin, int32_t env_count, double* obs) {
+    TGB_NEED_FINAL(w);
+    if (!obs || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_contact_cable_obs: bad range or NULL buffer");
+    const size_t n = (size_t)env_count * w->contactCables.size() * TGB_CCABLE_OBS_DOUBLES;
+    if (n == 0) return TGB_OK;
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(w->ops->ccable_obs(w->ccArgs(env_begin, env_count, 0.0), w->d_stage, -1, nullptr, w->stream));
+    TGB_CUDA(cudaMemcpyAsync(obs, w->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_get_contact_cable_anchors(tgb_world* w, int32_t cable, int32_t env_begin, int32_t env_count, double* out) {
+    TGB_NEED_FINAL(w);
+    if (!out || !rangeOk(w, env_begin, env_count) || cable < 0 || cable >= (int)w->contactCables.size())
+        return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_get_contact_cable_anchors: bad cable, range or NULL buffer");
+    const size_t n = (size_t)env_count * TGB_CCABLE_MAX_SLIDING * TGB_CCABLE_ANCHOR_DOUBLES;
+    if (n == 0) return TGB_OK;
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(w->ops->ccable_obs(w->ccArgs(env_begin, env_count, 0.0), nullptr, cable, w->d_stage, w->stream));
+    TGB_CUDA(cudaMemcpyAsync(out, w->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
     TGB_CUDA(cudaStreamSynchronize(w->stream));
     return TGB_OK;
 }

@@ -65,7 +65,20 @@ cudaError_t com(const tgb::tgb_io_args& a, int mode, double* scores, float* scor
     return cudaGetLastError();
 }
 
-const tgb_ops kOps = {sizeof(scalar_t), step, wide_ctas_per_sm, step_smem, pack_rods, unpack_rods, pack_cables, cable_obs, control_input, com};
+cudaError_t ccable_step(const tgb::tgb_ccable_args& a, cudaStream_t s) {
+    if (a.env_count <= 0 || a.n_cc <= 0) return cudaSuccess;
+    tgb::ccable_step_kernel<scalar_t><<<blocksFor(a.env_count, 64), 64, 0, s>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t ccable_obs(const tgb::tgb_ccable_args& a, double* obs, int cable, double* anchors, cudaStream_t s) {
+    const int n = a.env_count * a.n_cc;
+    if (n <= 0) return cudaSuccess;
+    tgb::ccable_obs_kernel<scalar_t><<<blocksFor(n, 128), 128, 0, s>>>(a, obs, cable, anchors);
+    return cudaGetLastError();
+}
+
+const tgb_ops kOps = {sizeof(scalar_t), step, wide_ctas_per_sm, step_smem, pack_rods, unpack_rods, pack_cables, cable_obs, control_input, com,
+                      ccable_step, ccable_obs};
 
 } // namespace
 

@@ -11,6 +11,7 @@
 #include <stddef.h>
 #include "tgb_dev.h"
 #include "tgb_io.cuh"
+#include "tgb_ccable.cuh"
 
 struct tgb_ops {
     size_t scalar_bytes;
@@ -24,6 +25,9 @@ struct tgb_ops {
     cudaError_t (*cable_obs)(const tgb::tgb_io_args& a, double* dst, cudaStream_t s);
     cudaError_t (*control_input)(const tgb::tgb_io_args& a, const double* input, int broadcast, double dt, cudaStream_t s);
     cudaError_t (*com)(const tgb::tgb_io_args& a, int mode, double* scores, float* scores_f, cudaStream_t s);
+    /* contact cables (tgb_ccable.cuh): one step of every contact cable of the environments in the range; observations / anchors */
+    cudaError_t (*ccable_step)(const tgb::tgb_ccable_args& a, cudaStream_t s);
+    cudaError_t (*ccable_obs)(const tgb::tgb_ccable_args& a, double* obs, int cable, double* anchors, cudaStream_t s);
 };
 
 const tgb_ops* tgb_ops_f32();

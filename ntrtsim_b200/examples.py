@@ -9,7 +9,7 @@ from . import _capi as capi
 from .world import FlatModel
 
 EXAMPLES = ("3_prism", "3_prism_noground", "SUPERball", "SUPERball_flat", "Escape", "Escape_c3", "tsTestRig_basic",
-            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3", "TetraSpineStatic_hf", "Escape_crater", "Escape_crater_shallow", "SUPERball_stairs", "SUPERball_blocks", "SUPERball_wall")
+            "tsTestRig_kinematic", "TetraSpine", "FlemonsSpine", "FlemonsSpine3", "TetraSpineStatic_hf", "Escape_crater", "Escape_crater_shallow", "SUPERball_stairs", "SUPERball_blocks", "SUPERball_wall", "ContactCableDemo")
 
 
 def build_example(name):
@@ -28,7 +28,12 @@ def build_example(name):
         h.tgh_copy(m, bodies, shapes, cables, C.byref(ground), C.byref(g), C.byref(dt))
         shapes = (capi.ShapeDesc * ns.value).from_buffer_copy(bytes(shapes)[: C.sizeof(capi.ShapeDesc) * ns.value])
         cables = (capi.CableDesc * nc.value).from_buffer_copy(bytes(cables)[: C.sizeof(capi.CableDesc) * nc.value])
-        return FlatModel(bodies, shapes, cables, ground, g.value, dt.value, name)
+        ncc = h.tgh_contact_cables(m, None, 0)
+        cc = None
+        if ncc > 0:
+            cc = (capi.ContactCableDesc * ncc)()
+            h.tgh_contact_cables(m, cc, ncc)
+        return FlatModel(bodies, shapes, cables, ground, g.value, dt.value, name, contact_cables=cc)
     finally:
         h.tgh_free(m)
 

@@ -618,6 +618,30 @@ tgModel* tgBasicActuatorInfo::createModel(tgWorldB200Impl& world) {
     return new tgBasicActuator(&world, m_cable, getTags(), m_config, m_startLength);
 }
 
+tgBasicContactCableInfo::tgBasicContactCableInfo(const tgBasicActuator::Config& config) : m_config(config), m_cable(-1), m_startLength(0) {}
+tgBasicContactCableInfo::tgBasicContactCableInfo(const tgBasicActuator::Config& config, const tgTags& tags, const tgPair& pair)
+    : tgConnectorInfo(tags + pair.getTags(), pair), m_config(config), m_cable(-1), m_startLength(0) {}
+tgConnectorInfo* tgBasicContactCableInfo::createConnectorInfo(const tgPair& pair, const tgTagSearch& search) const {
+    if (!search.matches(pair.getTags())) return 0;
+    return new tgBasicContactCableInfo(m_config, getTags(), pair);
+}
+void tgBasicContactCableInfo::initConnector(tgWorldB200Impl& world) {
+    tgSpringCableActuator::Config cfg = m_config;
+    cfg.moveCablePointAToEdge = cfg.moveCablePointBToEdge = true; /* tgBasicContactCableInfo.cpp:90-91 */
+    const tgb_cable_desc plain = describeCable(cfg, world, m_startLength);
+    tgb_contact_cable_desc c = tgb_contact_cable_desc();
+    c.body_a = plain.body_a; c.body_b = plain.body_b;
+    for (int k = 0; k < 3; ++k) { c.local_a[k] = plain.local_a[k]; c.local_b[k] = plain.local_b[k]; }
+    c.stiffness = plain.stiffness; c.damping = plain.damping;
+    c.rest_length = plain.rest_length; c.prev_length = plain.prev_length;
+    c.thickness = 0.001; c.resolution = 0.1;
+    m_cable = world.addContactCable(c);
+}
+tgModel* tgBasicContactCableInfo::createModel(tgWorldB200Impl& world) {
+    if (m_cable < 0) initConnector(world);
+    return new tgBasicActuator(&world, m_cable, getTags(), m_config, m_startLength);
+}
+
 tgKinematicActuatorInfo::tgKinematicActuatorInfo(const tgKinematicActuator::Config& config) : m_config(config), m_cable(-1), m_startLength(0) {}
 tgKinematicActuatorInfo::tgKinematicActuatorInfo(const tgKinematicActuator::Config& config, const tgTags& tags, const tgPair& pair)
     : tgConnectorInfo(tags + pair.getTags(), pair), m_config(config), m_cable(-1), m_startLength(0) {}

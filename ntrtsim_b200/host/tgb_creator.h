@@ -307,6 +307,23 @@ private:
     double m_startLength;
 };
 
+/* tgBasicContactCableInfo (src/tgcreator/tgBasicContactCableInfo.cpp:62-131): a tgBasicActuator on a tgBulletContactSpringCable -- a
+   cable that collides with the rigid bodies and bends around them over sliding anchors (include/ntrtsim_b200.h "Contact cables").
+   Both ends always move to the rigids' connection points (:90-91), thickness 0.001 and resolution 0.1 are the cable's defaults
+   (src/core/tgBulletContactSpringCable.h:89-90). */
+class tgBasicContactCableInfo : public tgConnectorInfo {
+public:
+    explicit tgBasicContactCableInfo(const tgBasicActuator::Config& config);
+    tgBasicContactCableInfo(const tgBasicActuator::Config& config, const tgTags& tags, const tgPair& pair);
+    tgConnectorInfo* createConnectorInfo(const tgPair& pair, const tgTagSearch& search) const;
+    void initConnector(tgWorldB200Impl& world);
+    tgModel* createModel(tgWorldB200Impl& world);
+private:
+    tgBasicActuator::Config m_config;
+    int m_cable;
+    double m_startLength;
+};
+
 class tgKinematicActuatorInfo : public tgConnectorInfo {
 public:
     explicit tgKinematicActuatorInfo(const tgKinematicActuator::Config& config);

@@ -69,6 +69,50 @@ void PrismModel::teardown() {
     tgModel::teardown();
 }
 
+/* ---- contact cable demo ------------------------------------------------------------------------------ */
+ContactCableDemo::ContactCableDemo() : tgModel() {}
+void ContactCableDemo::setup(tgWorld& world) {
+    const double rodDensity = 1, rodRadius = 0.25;
+    const tgRod::Config rodConfig(rodRadius, rodDensity);
+    const tgBox::Config boxConfig(rodRadius, rodRadius, rodDensity);
+
+    tgStructure s;
+    s.addNode(0, 2, 0);
+    s.addNode(0, 4, 0);
+    s.addNode(0, 12, 0);
+    s.addNode(0, 14, 0);
+    /* the rod the cable runs into */
+    s.addNode(-1, 8, 5);
+    s.addNode(1, 8, 5);
+    s.addPair(0, 1, "rod");
+    s.addPair(2, 3, "box");
+    s.addPair(4, 5, "rod");
+    s.addPair(1, 2, "muscle");
+    s.addRotation(btVector3(0.0, 0.0, 0.0), btVector3(0.0, 1.0, 0.0), M_PI / 4);
+    tgSpringCableActuator::Config muscleConfig(1000, 0, 0.0, false, 600000000);
+
+    tgBuildSpec spec;
+    spec.addBuilder("box", new tgBoxInfo(boxConfig));
+    spec.addBuilder("rod", new tgRodInfo(rodConfig));
+    spec.addBuilder("muscle", new tgBasicContactCableInfo(muscleConfig));
+    tgStructureInfo structureInfo(s, spec);
+    structureInfo.buildInto(*this, world);
+
+    m_muscles = tgCast::filter<tgModel, tgSpringCableActuator>(getDescendants());
+    notifySetup();
+    tgModel::setup(world);
+}
+void ContactCableDemo::step(double dt) {
+    if (dt <= 0.0) throw std::invalid_argument("dt is not positive");
+    notifyStep(dt);
+    tgModel::step(dt);
+}
+void ContactCableDemo::teardown() {
+    notifyTeardown();
+    m_muscles.clear();
+    tgModel::teardown();
+}
+
 /* ---- crater obstacles -------------------------------------------------------------------------------- */
 tgCraterDeep::tgCraterDeep() : m_origin(0, 0, 0), m_halfSize(15.0) {}
 tgCraterDeep::tgCraterDeep(btVector3 center) : m_origin(center), m_halfSize(15.0) {}

@@ -21,6 +21,20 @@ private:
     std::vector<tgSpringCableActuator*> m_actuators;
 };
 
+/* A rod and a box joined by one contact cable that runs into a third rod (src/examples/contactCables/ContactCableDemo.cpp:49-128; the
+   model of test_integration/MuscleNP/MuscleNP_test.cpp).  The reference's setup also gives the first two bodies a central impulse of
+   (0.4, 0, 0.4) through their btRigidBody; here the caller sets the corresponding velocities in the rod state. */
+class ContactCableDemo : public tgSubject<ContactCableDemo>, public tgModel {
+public:
+    ContactCableDemo();
+    virtual void setup(tgWorld& world);
+    virtual void step(double dt);
+    virtual void teardown();
+    const std::vector<tgSpringCableActuator*>& getAllMuscles() const { return m_muscles; }
+private:
+    std::vector<tgSpringCableActuator*> m_muscles;
+};
+
 /* SUPERball as shipped: 6 rods, 25 cables incl. the duplicated (2,4)/(4,2) (src/examples/SUPERball/T6Model.cpp:54-212) */
 class T6Model : public tgSubject<T6Model>, public tgModel {
 public:

@@ -154,6 +154,11 @@ int tgWorldB200Impl::addCable(const tgb_cable_desc& cable) {
     m_cables.push_back(cable);
     return (int)m_cables.size() - 1;
 }
+int tgWorldB200Impl::addContactCable(const tgb_contact_cable_desc& cable) {
+    if (m_handle) throw std::runtime_error("tgWorldB200Impl: cannot add cables after the world was finalized");
+    m_contactCables.push_back(cable);
+    return kContactCableBase + (int)m_contactCables.size() - 1;
+}
 void tgWorldB200Impl::setBatch(int n_env, tgb_precision precision, int device) {
     if (n_env < 1) throw std::invalid_argument("n_env must be positive");
     if (m_handle) throw std::runtime_error("tgWorldB200Impl: batch size is fixed once the world was finalized");
@@ -173,6 +178,7 @@ void tgWorldB200Impl::finalize() {
     check(tgb_create(&cfg, &m_ground, &h));
     int st = tgb_add_model_flat(h, m_bodies.data(), (int32_t)m_bodies.size(), m_shapes.data(), (int32_t)m_shapes.size(), m_cables.data(),
                                 (int32_t)m_cables.size());
+    if (st == TGB_OK && !m_contactCables.empty()) st = tgb_add_contact_cables(h, m_contactCables.data(), (int32_t)m_contactCables.size());
     if (st == TGB_OK) st = tgb_finalize(h);
     if (st != TGB_OK) { tgb_destroy(h); check(st); }
     m_handle = h;
@@ -207,6 +213,8 @@ void tgWorldB200Impl::refreshCache() {
     m_cableCache.resize((std::size_t)m_nEnv * m_cables.size() * TGB_CABLE_OBS_DOUBLES);
     check(tgb_get_rod_state(handle(), 0, m_nEnv, m_rodCache.data()));
     if (!m_cables.empty()) check(tgb_get_cable_obs(handle(), 0, m_nEnv, m_cableCache.data()));
+    m_ccCache.resize((std::size_t)m_nEnv * m_contactCables.size() * TGB_CCABLE_OBS_DOUBLES);
+    if (!m_contactCables.empty()) check(tgb_get_contact_cable_obs(handle(), 0, m_nEnv, m_ccCache.data()));
     m_cacheValid = true;
 }
 static void anchorsOf(const std::vector<tgb_body_desc>& bodies, const tgb_cable_desc& c, btVector3& p1, btVector3& p2) {
@@ -217,12 +225,37 @@ static void anchorsOf(const std::vector<tgb_body_desc>& bodies, const tgb_cable_
     p1 = ta * btVector3(c.local_a[0], c.local_a[1], c.local_a[2]);
     p2 = tb * btVector3(c.local_b[0], c.local_b[1], c.local_b[2]);
 }
+static void contactAnchorsOf(const std::vector<tgb_body_desc>& bodies, const tgb_contact_cable_desc& c, btVector3& p1, btVector3& p2) {
+    tgb_cable_desc plain = tgb_cable_desc();
+    plain.body_a = c.body_a; plain.body_b = c.body_b;
+    for (int k = 0; k < 3; ++k) { plain.local_a[k] = c.local_a[k]; plain.local_b[k] = c.local_b[k]; }
+    anchorsOf(bodies, plain, p1, p2);
+}
+int tgWorldB200Impl::contactCableAnchors(int cable, int env) {
+    if (!m_handle) return 0;
+    refreshCache();
+    return (int)m_ccCache[((std::size_t)env * m_contactCables.size() + (cable - kContactCableBase)) * TGB_CCABLE_OBS_DOUBLES + 4];
+}
 double tgWorldB200Impl::cableRestLength(int cable, int env) {
+    if (cable >= kContactCableBase) {
+        if (!m_handle) return m_contactCables.at(cable - kContactCableBase).rest_length;
+        refreshCache();
+        return m_ccCache[((std::size_t)env * m_contactCables.size() + (cable - kContactCableBase)) * TGB_CCABLE_OBS_DOUBLES + 0];
+    }
     if (!m_handle) return m_cables.at(cable).rest_length;
     refreshCache();
     return m_cableCache[((std::size_t)env * m_cables.size() + cable) * TGB_CABLE_OBS_DOUBLES + 0];
 }
 double tgWorldB200Impl::cableLength(int cable, int env) {
+    if (cable >= kContactCableBase) {
+        if (!m_handle) { /* no sliding anchor yet: the straight line between the two ends */
+            btVector3 p1, p2;
+            contactAnchorsOf(m_bodies, m_contactCables.at(cable - kContactCableBase), p1, p2);
+            return (p2 - p1).length();
+        }
+        refreshCache();
+        return m_ccCache[((std::size_t)env * m_contactCables.size() + (cable - kContactCableBase)) * TGB_CCABLE_OBS_DOUBLES + 1];
+    }
     if (!m_handle) {
         btVector3 p1, p2;
         anchorsOf(m_bodies, m_cables.at(cable), p1, p2);
@@ -232,6 +265,15 @@ double tgWorldB200Impl::cableLength(int cable, int env) {
     return m_cableCache[((std::size_t)env * m_cables.size() + cable) * TGB_CABLE_OBS_DOUBLES + 1];
 }
 double tgWorldB200Impl::cableTension(int cable, int env) {
+    if (cable >= kContactCableBase) {
+        if (!m_handle) {
+            const tgb_contact_cable_desc& c = m_contactCables.at(cable - kContactCableBase);
+            double t = (cableLength(cable, env) - c.rest_length) * c.stiffness;
+            return t < 0.0 ? 0.0 : t;
+        }
+        refreshCache();
+        return m_ccCache[((std::size_t)env * m_contactCables.size() + (cable - kContactCableBase)) * TGB_CCABLE_OBS_DOUBLES + 2];
+    }
     if (!m_handle) {
         const tgb_cable_desc& c = m_cables.at(cable);
         double t = (cableLength(cable, env) - c.rest_length) * c.stiffness;
@@ -241,6 +283,7 @@ double tgWorldB200Impl::cableTension(int cable, int env) {
     return m_cableCache[((std::size_t)env * m_cables.size() + cable) * TGB_CABLE_OBS_DOUBLES + 2];
 }
 double tgWorldB200Impl::cableMotorVelocity(int cable, int env) {
+    if (cable >= kContactCableBase) return 0.0;
     if (!m_handle) return 0.0;
     refreshCache();
     return m_cableCache[((std::size_t)env * m_cables.size() + cable) * TGB_CABLE_OBS_DOUBLES + 3];
@@ -259,6 +302,8 @@ btQuaternion tgWorldB200Impl::bodyOrientation(int body, int env) {
 }
 void tgWorldB200Impl::setControlInput(int cable, double input, double dt) {
     if (input < 0.0) throw std::invalid_argument("Rest length is negative.");
+    if (cable >= kContactCableBase)
+        throw std::runtime_error("tgWorldB200Impl: control input on a contact cable is not supported (its actuator runs without control input)");
     if (!m_handle) {
         /* before the device exists: tgBasicActuator::moveMotors on the flat descriptor (tgBasicActuator.cpp:170-225) */
         tgb_cable_desc& c = m_cables.at(cable);

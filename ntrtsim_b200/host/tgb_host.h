@@ -205,6 +205,12 @@ public:
     /* builder side */
     int addBody(const tgb_body_desc& body, const std::vector<tgb_shape_desc>& shapes);
     int addCable(const tgb_cable_desc& cable);
+    /* contact cables (tgBulletContactSpringCable) live in their own list; the returned index is kContactCableBase + position and is
+       understood by the cable observation calls below */
+    enum { kContactCableBase = 1 << 20 };
+    int addContactCable(const tgb_contact_cable_desc& cable);
+    const std::vector<tgb_contact_cable_desc>& contactCables() const { return m_contactCables; }
+    int contactCableAnchors(int cable, int env); /* number of sliding anchors (tgSpringCable::getAnchors().size() - 2) */
     const std::vector<tgb_body_desc>& bodies() const { return m_bodies; }
     const std::vector<tgb_shape_desc>& shapes() const { return m_shapes; }
     const std::vector<tgb_cable_desc>& cables() const { return m_cables; }
@@ -243,6 +249,8 @@ private:
     std::vector<tgb_body_desc> m_bodies;
     std::vector<tgb_shape_desc> m_shapes;
     std::vector<tgb_cable_desc> m_cables;
+    std::vector<tgb_contact_cable_desc> m_contactCables;
+    std::vector<double> m_ccCache;
     int m_nEnv;
     tgb_precision m_precision;
     int m_device;

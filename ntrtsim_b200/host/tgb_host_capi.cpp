@@ -65,6 +65,11 @@ Example* build(const std::string& name, int n_env = 1, int precision = TGB_F32) 
             e->world = new tgWorld(tgWorld::Config(981), ground);
             e->dt = 0.001;
             e->model = TGB_MODEL(name, new PrismModel());
+        } else if (name == "ContactCableDemo") {
+            /* MuscleNP_test.cpp:80-96: no gravity, tgEmptyGround, dt = 1e-3 */
+            e->world = new tgWorld(tgWorld::Config(0.0), new tgEmptyGround());
+            e->dt = 0.001;
+            e->model = TGB_MODEL(name, new ContactCableDemo());
         } else if (name == "SUPERball" || name == "SUPERball_flat") {
             const double pitch = name == "SUPERball" ? M_PI / 15.0 : 0.0;
             e->world = new tgWorld(tgWorld::Config(98.1), new tgBoxGround(tgBoxGround::Config(btVector3(0.0, pitch, 0.0))));
@@ -188,6 +193,15 @@ int tgh_copy(const tgh_model* m, tgb_body_desc* bodies, tgb_shape_desc* shapes, 
     if (gravity) *gravity = w.gravity();
     if (dt) *dt = e->dt;
     return 0;
+}
+
+/* the contact cables of the built world: returns their number, copies at most `cap` */
+int tgh_contact_cables(const tgh_model* m, tgb_contact_cable_desc* out, int cap) {
+    const Example* e = reinterpret_cast<const Example*>(m);
+    if (!e) return -1;
+    const std::vector<tgb_contact_cable_desc>& cc = e->world->b200().contactCables();
+    for (int i = 0; i < (int)cc.size() && i < cap && out; ++i) out[i] = cc[i];
+    return (int)cc.size();
 }
 
 /* The model tree as the reference would print it: number of tgRod and tgSpringCableActuator descendants. */

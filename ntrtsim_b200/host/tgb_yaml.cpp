@@ -526,11 +526,12 @@ void TensegrityModel::addBuilders(tgBuildSpec& spec, const Yam& builders) {
         const std::string builderClass = items[i].second["class"].str();
         const Yam& parameters = items[i].second["parameters"];
         if (builderClass == "tgRodInfo") addRodBuilder(builderClass, tagMatch, parameters, spec);
-        else if (builderClass == "tgBasicActuatorInfo") addBasicActuatorBuilder(builderClass, tagMatch, parameters, spec);
+        else if (builderClass == "tgBasicActuatorInfo" || builderClass == "tgBasicContactCableInfo")
+            addBasicActuatorBuilder(builderClass, tagMatch, parameters, spec);
         else if (builderClass == "tgKinematicActuatorInfo") addKinematicActuatorBuilder(builderClass, tagMatch, parameters, spec);
         else if (builderClass == "tgSphereInfo") addSphereBuilder(builderClass, tagMatch, parameters, spec);
         else if (builderClass == "tgBoxInfo") addBoxBuilder(builderClass, tagMatch, parameters, spec);
-        else if (builderClass == "tgBasicContactCableInfo" || builderClass == "tgKinematicContactCableInfo")
+        else if (builderClass == "tgKinematicContactCableInfo")
             throw std::invalid_argument("Unsupported builder class in this build: " + builderClass);
         else throw std::invalid_argument("Unsupported builder class: " + builderClass);
     }
@@ -563,10 +564,12 @@ void TensegrityModel::addBasicActuatorBuilder(const std::string& builderClass, c
     d["min_rest_length"] = stringMinRestLength; d["rotation"] = stringRotation;
     b["moveCablePointAToEdge"] = true; b["moveCablePointBToEdge"] = true;
     overwrite(d, parameters, builderClass, &b);
-    spec.addBuilder(tagMatch, new tgBasicActuatorInfo(tgBasicActuator::Config(d["stiffness"], d["damping"], d["pretension"], d["history"] != 0.0,
-                                                                               d["max_tension"], d["target_velocity"], d["min_actual_length"],
-                                                                               d["min_rest_length"], d["rotation"], b["moveCablePointAToEdge"],
-                                                                               b["moveCablePointBToEdge"])));
+    const tgBasicActuator::Config config(d["stiffness"], d["damping"], d["pretension"], d["history"] != 0.0, d["max_tension"], d["target_velocity"],
+                                         d["min_actual_length"], d["min_rest_length"], d["rotation"], b["moveCablePointAToEdge"],
+                                         b["moveCablePointBToEdge"]);
+    /* both builders share tgBasicActuator::Config (TensegrityModel.cpp:726-734) */
+    if (builderClass == "tgBasicContactCableInfo") spec.addBuilder(tagMatch, new tgBasicContactCableInfo(config));
+    else spec.addBuilder(tagMatch, new tgBasicActuatorInfo(config));
 }
 void TensegrityModel::addKinematicActuatorBuilder(const std::string& builderClass, const std::string& tagMatch, const Yam& parameters, tgBuildSpec& spec) {
     std::map<std::string, double> k;

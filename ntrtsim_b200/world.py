@@ -40,9 +40,15 @@ class FlatModel(object):
     """The flattened descriptors of one model: what tgStructureInfo::buildInto hands to the world
     (reference: src/tgcreator/tgStructureInfo.cpp:277-289) plus the world settings of its app."""
 
-    def __init__(self, bodies, shapes, cables, ground, gravity, dt, name=""):
+    def __init__(self, bodies, shapes, cables, ground, gravity, dt, name="", contact_cables=None):
         self.bodies, self.shapes, self.cables = bodies, shapes, cables
         self.ground, self.gravity, self.dt, self.name = ground, gravity, dt, name
+        # tgBulletContactSpringCable cables (tgBasicContactCableInfo): a ctypes array of tgb_contact_cable_desc, or None
+        self.contact_cables = contact_cables if contact_cables is not None and len(contact_cables) else None
+
+    @property
+    def n_contact_cables(self):
+        return 0 if self.contact_cables is None else len(self.contact_cables)
 
     @property
     def n_bodies(self):
@@ -77,6 +83,8 @@ class BatchedWorld(object):
         try:
             capi.check(self._lib.tgb_add_model_flat(h, model.bodies, len(model.bodies), model.shapes, len(model.shapes),
                                                     model.cables, len(model.cables)))
+            if getattr(model, "contact_cables", None) is not None:
+                capi.check(self._lib.tgb_add_contact_cables(h, model.contact_cables, len(model.contact_cables)))
             if lanes_per_env:
                 capi.check(self._lib.tgb_set_lanes_per_env(h, lanes_per_env))
             if block_threads:
@@ -115,6 +123,20 @@ class BatchedWorld(object):
         n = self.n_env - env_begin if env_count is None else env_count
         out = np.empty((n, self.R, capi.ROD_STATE_DOUBLES))
         capi.check(self._lib.tgb_get_rod_state(self._h, env_begin, n, _ptr(out)))
+        return out
+
+    def get_contact_cable_obs(self, env_begin=0, env_count=None):
+        """[n, n_contact_cables, 5]: rest length, actual length over all anchors, tension, velocity, number of sliding anchors"""
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.zeros((n, self.model.n_contact_cables, capi.CCABLE_OBS_DOUBLES))
+        capi.check(self._lib.tgb_get_contact_cable_obs(self._h, env_begin, n, _ptr(out)))
+        return out
+
+    def get_contact_cable_anchors(self, cable, env_begin=0, env_count=None):
+        """[n, 6, 7]: body (-1 = unused slot), world position, contact normal of the cable's sliding anchors in order"""
+        n = self.n_env - env_begin if env_count is None else env_count
+        out = np.zeros((n, capi.CCABLE_MAX_SLIDING, capi.CCABLE_ANCHOR_DOUBLES))
+        capi.check(self._lib.tgb_get_contact_cable_anchors(self._h, int(cable), env_begin, n, _ptr(out)))
         return out
 
     def set_cable_state(self, rest_prev, env_begin=0):

@@ -49,6 +49,10 @@ def load():
     lib.tgo_set_cpg_controller.argtypes = [vp, vp, vp, i]
     lib.tgo_get_status.argtypes = [vp]
     lib.tgo_get_cpg_state.argtypes = [vp, vp]
+    lib.tgo_add_contact_cables.argtypes = [vp, vp, i]
+    lib.tgo_num_contact_cables.argtypes = [vp]
+    lib.tgo_get_contact_cable_obs.argtypes = [vp, vp]
+    lib.tgo_get_contact_cable_anchors.argtypes = [vp, i, vp]
     lib.tgo_track_max_tension.argtypes = [vp, i]
     lib.tgo_get_max_tension.argtypes = [vp, vp]
     _lib = lib
@@ -70,6 +74,22 @@ class OracleWorld(object):
         self._lib.tgo_add_model_flat(self._h, model.bodies, len(model.bodies), model.shapes, len(model.shapes), model.cables,
                                      len(model.cables))
         self.R, self.C = len(model.bodies), len(model.cables)
+        self.n_cc = 0
+        if getattr(model, "contact_cables", None) is not None:
+            rc = self._lib.tgo_add_contact_cables(self._h, model.contact_cables, len(model.contact_cables))
+            if rc != 0:
+                raise ValueError("oracle: bad contact cable descriptor (%d)" % rc)
+            self.n_cc = len(model.contact_cables)
+
+    def get_contact_cable_obs(self):
+        out = np.zeros((self.n_cc, 5))
+        self._lib.tgo_get_contact_cable_obs(self._h, _p(out))
+        return out
+
+    def get_contact_cable_anchors(self, cable):
+        out = np.zeros((6, 7))
+        self._lib.tgo_get_contact_cable_anchors(self._h, int(cable), _p(out))
+        return out
 
     def close(self):
         if self._h:

@@ -153,6 +153,22 @@ struct Cable {
     double motorVel, desiredTorque;
 };
 
+/* tgBulletContactSpringCable (src/core/tgBulletContactSpringCable.cpp) with its sliding anchors
+   (src/core/tgBulletSpringCableAnchor.cpp); see include/ntrtsim_b200.h "Contact cables" for the restatement's terms. */
+struct SlideAnchor {
+    int body;
+    V3 local;  /* attachedRelativeOriginalPosition */
+    V3 normal; /* contactNormal: world vector fixed at creation (USE_BASIS off, SKIP_CONTACT_UPDATE on), from the cable into the body */
+};
+struct ContactCable {
+    int a, b;
+    V3 la, lb;
+    double k, c, rest, prev, velocity, damping, thickness, resolution;
+    std::vector<SlideAnchor> slides; /* between the two permanent anchors, in order */
+};
+/* one point of the "manifold" of (cable, body) */
+struct CablePoint { int body; V3 pos; V3 normal; double dist; };
+
 struct Contact {
     int body;
     long long key = -1; /* identity of the manifold point across steps (persistent manifold): see warmStartKey */
@@ -216,6 +232,8 @@ struct tgo_world {
     std::vector<Body> bodies;
     std::vector<Shape> shapes;
     std::vector<Cable> cables;
+    std::vector<ContactCable> contactCables;
+    int modelBody0 = 0; /* first body of the model added last (tgo_add_contact_cables indexes relative to it) */
     std::vector<Contact> contacts;
     int ctrlKind = TGB_CTRL_NONE;
     std::vector<double> ctrlParams;
@@ -393,6 +411,229 @@ struct tgo_world {
         applyImpulse(B, -force * dt, p2 - B.pos);
     }
 
+
+    /* ---- contact cables ---------------------------------------------------------------------- */
+    enum { kMaxSliding = TGB_CCABLE_MAX_SLIDING, kMaxCablePoints = 64 };
+    V3 toLocal(const Body& b, const V3& world) const { return vecMat(world - b.pos, b.basis); } /* basis^T (world - pos) */
+    /* world positions of the anchor chain, tgBulletContactSpringCable::m_anchors */
+    void ccChain(const ContactCable& cc, std::vector<V3>& P) const {
+        P.clear();
+        P.push_back(anchorWorld(bodies[cc.a], cc.la));
+        for (const SlideAnchor& q : cc.slides) P.push_back(anchorWorld(bodies[q.body], q.local));
+        P.push_back(anchorWorld(bodies[cc.b], cc.lb));
+    }
+    /* getActualLength, tgBulletContactSpringCable.cpp:84-95 */
+    static double ccLength(const std::vector<V3>& P) {
+        double L = 0.0;
+        for (size_t i = 0; i + 1 < P.size(); ++i) L += (P[i] - P[i + 1]).length();
+        return L;
+    }
+    double contactCableLength(const ContactCable& cc) const { std::vector<V3> P; ccChain(cc, P); return ccLength(P); }
+    double contactCableTension(const ContactCable& cc) const {
+        const double t = (contactCableLength(cc) - cc.rest) * cc.k;
+        return t < 0.0 ? 0.0 : t;
+    }
+    /* the manifold point of `body` nearest to p: its distance to p (INFINITY when the body has none) and its normal */
+    static double ccNearest(const std::vector<CablePoint>& pts, int body, const V3& p, V3& normal, V3& pos) {
+        double best = INFINITY;
+        for (const CablePoint& m : pts) {
+            if (m.body != body) continue;
+            const double d = (m.pos - p).length();
+            if (d < best) { best = d; normal = m.normal; pos = m.pos; }
+        }
+        return best;
+    }
+    /* tgBulletSpringCableAnchor::getManifoldDistance (:279-334) of a sliding anchor: distance to the nearest point of its body's
+       manifold, and that point's normal when it lies within 0.1 (else the anchor's own) */
+    double ccManifoldDistance(const std::vector<CablePoint>& pts, const SlideAnchor& q, int body, V3& normalOut) const {
+        normalOut = q.normal;
+        if (q.body != body) return INFINITY;
+        V3 n, pos;
+        const double len = ccNearest(pts, body, anchorWorld(bodies[q.body], q.local), n, pos);
+        if (len < 0.1) normalOut = n;
+        return len;
+    }
+    /* tgBulletSpringCableAnchor::updateManifold (:232-277) when the manifold of (cable, body) is the one the anchor already holds:
+       accepted unless the nearest point's normal opposes the anchor's */
+    bool ccUpdateManifold(const std::vector<CablePoint>& pts, const SlideAnchor& q, int body) const {
+        if (q.body != body) return false;
+        V3 newNormal;
+        ccManifoldDistance(pts, q, body, newNormal);
+        return !((newNormal + q.normal).length() < 0.5);
+    }
+    /* the segment of the chain nearest to pos: the restatement's findNearestPastAnchor (:799-937) */
+    static int ccNearestSegment(const std::vector<V3>& P, const V3& pos) {
+        int best = 0;
+        double bestD = INFINITY;
+        for (size_t j = 0; j + 1 < P.size(); ++j) {
+            const V3 e = P[j + 1] - P[j];
+            const double e2 = e.length2();
+            double t = e2 > 0.0 ? (pos - P[j]).dot(e) / e2 : 0.0;
+            t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+            const double d = (P[j] + e * t - pos).length();
+            if (d < bestD) { bestD = d; best = (int)j; }
+        }
+        return best;
+    }
+    /* tgBulletSpringCableAnchor::setWorldPosition (:89-184) */
+    bool ccSetWorldPosition(const std::vector<CablePoint>& pts, SlideAnchor& q, const V3& newPos) {
+        const Body& b = bodies[q.body];
+        const V3 current = anchorWorld(b, q.local);
+        V3 newNormal = q.normal, contactPos = current;
+        const double length = ccNearest(pts, q.body, newPos, newNormal, contactPos);
+        if (length < 0.1) {
+            q.local = toLocal(b, newPos);
+            return !((newNormal + q.normal).length() < 0.5);
+        }
+        return (current - contactPos).length() <= 0.1;
+    }
+    /* updateAnchorPositions (:484-561); returns the number of anchors removed */
+    int ccUpdateAnchorPositions(ContactCable& cc, const std::vector<CablePoint>& pts) {
+        int numPruned = 0;
+        size_t i = 0;
+        std::vector<V3> P;
+        while (i < cc.slides.size()) {
+            ccChain(cc, P);
+            const V3 back = P[i], current = P[i + 1], forward = P[i + 2];
+            const V3 lineA = forward - current, lineB = back - current;
+            const V3 n = cc.slides[i].normal;
+            V3 tangentMove(0, 0, 0);
+            const V3 along = lineB - lineA;
+            const double al = along.length();
+            if (al > 0.0) {
+                const V3 td = (along / al).cross(n);
+                const double tl = td.length();
+                if (tl > 0.0) {
+                    const V3 tangentDir = td / tl;
+                    tangentMove = tangentDir * (lineB + lineA).dot(tangentDir);
+                }
+            }
+            const V3 newPos = current + tangentMove;
+            if (!ccSetWorldPosition(pts, cc.slides[i], newPos)) {
+                cc.slides.erase(cc.slides.begin() + i);
+                ++numPruned;
+            } else ++i;
+        }
+        return numPruned;
+    }
+    /* tgBulletContactSpringCable::step (:97-125) */
+    void contactCableStep(ContactCable& cc, double dt) {
+        std::vector<V3> P;
+        ccChain(cc, P);
+        /* updateManifolds: this step's contact points of the segments with every body */
+        std::vector<CablePoint> pts;
+        for (size_t i = 0; i + 1 < P.size(); ++i) {
+            const V3 e = P[i + 1] - P[i];
+            const double len = e.length();
+            Segment gs;
+            gs.p = (P[i] + P[i + 1]) * 0.5;
+            gs.d = len > 1e-12 ? e / len : V3(0, 1, 0);
+            gs.h = len > 1e-12 ? 0.5 * len : 0.0;
+            gs.r = cc.thickness;
+            for (size_t bi = 0; bi < bodies.size(); ++bi) {
+                const Body& b = bodies[bi];
+                for (int si = b.shapeBegin; si < b.shapeBegin + b.shapeCount; ++si) {
+                    Segment gb;
+                    if (!shapeSegment(b, shapes[si], gb)) continue;
+                    double s0, t0, bb, c0, f0;
+                    closestSegmentParams(gs, gb, s0, t0, bb, c0, f0);
+                    const V3 ca = gs.p + gs.d * s0, cb = gb.p + gb.d * t0;
+                    const V3 dv = ca - cb;
+                    const double d = dv.length();
+                    if (!(d > 1e-9)) continue; /* the axes meet: no direction */
+                    const double dist = d - gb.r - gs.r;
+                    if (dist > kBreakingThreshold) continue;
+                    if ((int)pts.size() >= kMaxCablePoints) continue;
+                    const V3 u = dv / d;
+                    CablePoint m;
+                    m.body = (int)bi; m.pos = cb + u * gb.r; m.normal = -u; m.dist = dist;
+                    pts.push_back(m);
+                }
+            }
+        }
+        /* updateManifolds + updateAnchorList: proposals of the penetrating points, one after the other */
+        for (size_t pi = 0; pi < pts.size(); ++pi) {
+            const CablePoint m = pts[pi];
+            if (!(m.dist < 0.0)) continue;
+            ccChain(cc, P);
+            const int j = ccNearestSegment(P, m.pos); /* back anchor = chain index j, forward = j + 1 */
+            const V3 lineA = P[j + 1] - m.pos, lineB = P[j] - m.pos;
+            const double lengthA = lineA.length(), lengthB = lineB.length();
+            SlideAnchor* backS = j >= 1 ? &cc.slides[j - 1] : nullptr;                          /* NULL: permanent */
+            SlideAnchor* fwdS = j + 1 <= (int)cc.slides.size() ? &cc.slides[j] : nullptr;
+            V3 tmp;
+            const double mDistB = backS ? ccManifoldDistance(pts, *backS, m.body, tmp) : INFINITY;
+            const double mDistA = fwdS ? ccManifoldDistance(pts, *fwdS, m.body, tmp) : INFINITY;
+            const int backBody = backS ? backS->body : cc.a, fwdBody = fwdS ? fwdS->body : cc.b;
+            bool del = false;
+            if (lengthB <= cc.resolution && m.body == backBody && mDistB < mDistA)
+                if (backS && ccUpdateManifold(pts, *backS, m.body)) del = true;
+            if (lengthA <= cc.resolution && m.body == fwdBody && (!del || mDistA < mDistB))
+                if (fwdS && ccUpdateManifold(pts, *fwdS, m.body)) del = true;
+            if (del) continue;
+            if (lineA.dot(m.normal) < 0.0 || lineB.dot(m.normal) < 0.0) continue;
+            const V3 backNormal = backS ? backS->normal : V3(0, 0, 0), fwdNormal = fwdS ? fwdS->normal : V3(0, 0, 0);
+            if ((backNormal.dot(m.normal) < 0.0 && m.body == backBody) || (fwdNormal.dot(m.normal) < 0.0 && m.body == fwdBody)) continue;
+            if ((int)cc.slides.size() >= kMaxSliding) continue;
+            SlideAnchor q;
+            q.body = m.body; q.local = toLocal(bodies[m.body], m.pos); q.normal = m.normal;
+            cc.slides.insert(cc.slides.begin() + j, q);
+            if (contactCableLength(cc) > cc.prev + 2.0 * cc.resolution) cc.slides.erase(cc.slides.begin() + j);
+        }
+        /* pruneAnchors */
+        int numPruned = 0, passes = 0;
+        for (size_t i = 0; i < cc.slides.size();) {
+            V3 n, pos;
+            if (ccNearest(pts, cc.slides[i].body, anchorWorld(bodies[cc.slides[i].body], cc.slides[i].local), n, pos) == INFINITY) {
+                cc.slides.erase(cc.slides.begin() + i);
+                ++numPruned;
+            } else ++i;
+        }
+        while (numPruned > 0 || passes <= 3) {
+            numPruned = ccUpdateAnchorPositions(cc, pts);
+            if (numPruned == 0) {
+                size_t i = 0;
+                while (i < cc.slides.size()) {
+                    ccChain(cc, P);
+                    const V3 lineA = P[i + 2] - P[i + 1], lineB = P[i] - P[i + 1];
+                    const V3 n = cc.slides[i].normal;
+                    double nv1, nv2;
+                    if (lineA.length() < cc.resolution / 2.0 || lineB.length() < cc.resolution / 2.0) nv1 = nv2 = -1.0;
+                    else { nv1 = lineA.dot(n); nv2 = lineB.dot(n); }
+                    if (nv1 < 0.0 || nv2 < 0.0) { cc.slides.erase(cc.slides.begin() + i); ++numPruned; }
+                    else ++i;
+                }
+            }
+            if (numPruned == 0) ++passes; else passes = 0;
+        }
+        /* calculateAndApplyForce (:127-194) */
+        ccChain(cc, P);
+        const double currLength = ccLength(P);
+        double tension = (currLength - cc.rest) * cc.k;
+        if (tension < 0.0) tension = 0.0;
+        cc.velocity = (currLength - cc.prev) / dt;
+        cc.damping = cc.c * cc.velocity;
+        if (std::fabs(tension) * 1.0 < std::fabs(cc.damping)) cc.damping = (cc.damping > 0.0 ? tension * 1.0 : -tension * 1.0);
+        const double magnitude = tension + cc.damping;
+        const size_t n = P.size();
+        for (size_t i = 0; i < n; ++i) {
+            V3 force(0, 0, 0);
+            if (i == 0) { const V3 d = P[1] - P[0]; const double l = d.length(); if (l > 0.0) force = (d / l) * magnitude; }
+            else if (i == n - 1) { const V3 d = P[i] - P[i - 1]; const double l = d.length(); if (l > 0.0) force = -(d / l) * magnitude; }
+            else {
+                const V3 first = P[i + 1] - P[i], second = P[i - 1] - P[i];
+                const double l1 = first.length(), l2 = second.length();
+                V3 dir(0, 0, 0);
+                if (l1 > 0.0) dir += first / l1;
+                if (l2 > 0.0) dir += second / l2;
+                force = dir * magnitude;
+            }
+            Body& body = bodies[i == 0 ? cc.a : (i == n - 1 ? cc.b : cc.slides[i - 1].body)];
+            applyImpulse(body, force * dt, P[i] - body.pos);
+        }
+        cc.prev = currLength;
+    }
+
     /* tgBasicActuator::moveMotors */
     void moveMotors(Cable& c, double dt) {
         double stepSize = c.tVel * dt;
@@ -553,6 +794,8 @@ struct tgo_world {
             /* logHistory (hist = true): the tension after the cable's step joins the history; only its maximum is kept */
             if (trackMaxTension) maxTension[i] = std::max(maxTension[i], cableTension(c));
         }
+        /* tgBasicActuator::step of a contact cable = tgBulletContactSpringCable::step (no control input) */
+        for (ContactCable& cc : contactCables) contactCableStep(cc, dt);
     }
 
     /* ---- world step (Bullet restatement) ----------------------------------------------------- */
@@ -1093,6 +1336,7 @@ int tgo_add_model_flat(tgo_world* w, const tgb_body_desc* bodies, int n_bodies, 
                        int n_shapes, const tgb_cable_desc* cables, int n_cables) {
     const int body0 = (int)w->bodies.size();
     const int shape0 = (int)w->shapes.size();
+    w->modelBody0 = body0;
     for (int i = 0; i < n_shapes; ++i) {
         Shape s;
         s.kind = shapes[i].kind;
@@ -1138,6 +1382,46 @@ int tgo_add_model_flat(tgo_world* w, const tgb_body_desc* bodies, int n_bodies, 
     }
     w->episodeStartCom = w->centerOfMass();
     return 0;
+}
+
+int tgo_add_contact_cables(tgo_world* w, const tgb_contact_cable_desc* cables, int n) {
+    for (int i = 0; i < n; ++i) {
+        const tgb_contact_cable_desc& d = cables[i];
+        if (d.body_a < 0 || d.body_b < 0 || w->modelBody0 + d.body_a >= (int)w->bodies.size() || w->modelBody0 + d.body_b >= (int)w->bodies.size() ||
+            !(d.stiffness > 0.0) || d.damping < 0.0 || d.rest_length < 0.0 || d.thickness < 0.0 || !(d.resolution > 0.0))
+            return TGB_ERR_INVALID_ARGUMENT; /* tgBulletContactSpringCable::invariant, :939-952 */
+        ContactCable cc;
+        cc.a = w->modelBody0 + d.body_a; cc.b = w->modelBody0 + d.body_b;
+        cc.la = V3(d.local_a[0], d.local_a[1], d.local_a[2]);
+        cc.lb = V3(d.local_b[0], d.local_b[1], d.local_b[2]);
+        cc.k = d.stiffness; cc.c = d.damping; cc.rest = d.rest_length; cc.prev = d.prev_length;
+        cc.velocity = 0; cc.damping = 0; cc.thickness = d.thickness; cc.resolution = d.resolution;
+        w->contactCables.push_back(cc);
+    }
+    return 0;
+}
+int tgo_num_contact_cables(const tgo_world* w) { return (int)w->contactCables.size(); }
+void tgo_get_contact_cable_obs(const tgo_world* w, double* o) {
+    for (size_t i = 0; i < w->contactCables.size(); ++i) {
+        const ContactCable& cc = w->contactCables[i];
+        o[5 * i + 0] = cc.rest;
+        o[5 * i + 1] = w->contactCableLength(cc);
+        o[5 * i + 2] = w->contactCableTension(cc);
+        o[5 * i + 3] = cc.velocity;
+        o[5 * i + 4] = (double)cc.slides.size();
+    }
+}
+void tgo_get_contact_cable_anchors(const tgo_world* w, int cable, double* out) {
+    const ContactCable& cc = w->contactCables[cable];
+    for (int k = 0; k < TGB_CCABLE_MAX_SLIDING; ++k) {
+        double* o = out + 7 * k;
+        for (int j = 0; j < 7; ++j) o[j] = 0.0;
+        o[0] = -1.0;
+        if (k >= (int)cc.slides.size()) continue;
+        const SlideAnchor& q = cc.slides[k];
+        const V3 p = w->anchorWorld(w->bodies[q.body], q.local);
+        o[0] = q.body; o[1] = p.x; o[2] = p.y; o[3] = p.z; o[4] = q.normal.x; o[5] = q.normal.y; o[6] = q.normal.z;
+    }
 }
 
 int tgo_num_bodies(const tgo_world* w) { return (int)w->bodies.size(); }

@@ -53,6 +53,12 @@ void       tgo_destroy(tgo_world* w);
 int        tgo_add_model_flat(tgo_world* w, const tgb_body_desc* bodies, int n_bodies,
                               const tgb_shape_desc* shapes, int n_shapes,
                               const tgb_cable_desc* cables, int n_cables);
+/* contact cables (tgBulletContactSpringCable, src/core/tgBulletContactSpringCable.cpp:97-190; see include/ntrtsim_b200.h): body
+   indices relative to the model added last.  obs [n][5]; anchors [TGB_CCABLE_MAX_SLIDING][7] */
+int  tgo_add_contact_cables(tgo_world* w, const tgb_contact_cable_desc* cables, int n);
+int  tgo_num_contact_cables(const tgo_world* w);
+void tgo_get_contact_cable_obs(const tgo_world* w, double* obs5);
+void tgo_get_contact_cable_anchors(const tgo_world* w, int cable, double* out);
 int  tgo_num_bodies(const tgo_world* w);
 int  tgo_num_cables(const tgo_world* w);
 

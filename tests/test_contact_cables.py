@@ -1,0 +1,295 @@
+"""Contact cables: tgBulletContactSpringCable / tgBasicContactCableInfo.
+
+CPU part: the oracle's restatement against what the reference suite pins for this path --
+test_integration/MuscleNP/MuscleNP_test.cpp:77-114 (ContactCableDemo, no gravity, no ground, 10 000 steps: linear momentum conserved,
+energy not increased) -- and against the plain cable it must equal while it touches nothing.
+GPU part: the CUDA path (step kernel + contact-cable kernel through the C ABI) against the oracle on the same seeded inputs.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import ntrtsim_b200 as nt  # noqa: E402
+from ntrtsim_b200 import _capi as capi  # noqa: E402
+from ntrtsim_b200.world import FlatModel  # noqa: E402
+import oracle_py  # noqa: E402
+from helpers import rod_errors  # noqa: E402
+
+DT = 0.001
+
+
+def demo_model():
+    return nt.build_example("ContactCableDemo")
+
+
+def demo_states(model, n_env, seed=77, spread=0.15):
+    """ContactCableDemo.cpp:104-110: the central impulse (0.4, 0, 0.4) on the first two bodies, per environment scaled and turned a
+    little so that the cable meets the third rod at different times and angles."""
+    rng = np.random.default_rng(seed)
+    s = np.tile(model.initial_rod_state()[None], (n_env, 1, 1))
+    for e in range(n_env):
+        imp = np.array([0.4, 0.0, 0.4]) * (1.0 if e == 0 else 1.0 + spread * rng.uniform(-1, 1))
+        if e > 0:
+            imp = imp + spread * 0.4 * rng.uniform(-1, 1, size=3)
+        for b in (0, 1):
+            s[e, b, 7:10] = imp / model.bodies[b].mass
+    return s
+
+
+def masses(model):
+    return np.array([b.mass for b in model.bodies])
+
+
+def momentum(model, st):
+    return (st[..., 7:10] * masses(model)[:, None]).sum(axis=-2)
+
+
+def demo_energy(model, st):
+    """ContactCableDemo::getEnergy (ContactCableDemo.cpp:184-198): sum of |v|^2 m over the rigids"""
+    return ((st[..., 7:10] ** 2).sum(axis=-1) * masses(model)).sum(axis=-1)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: builder and oracle
+def test_contact_cable_builder_matches_the_reference_construction():
+    m = demo_model()
+    assert (m.n_bodies, m.n_cables, m.n_contact_cables) == (3, 0, 1)
+    c = m.contact_cables[0]
+    assert (c.body_a, c.body_b) == (0, 1)
+    # tgBulletContactSpringCable.h:89-90 defaults; rest = |p2 - p1| - pretension / k with pretension 0; prev = rest
+    assert (c.thickness, c.resolution) == (0.001, 0.1)
+    assert (c.stiffness, c.damping) == (1000.0, 0.0)
+    # both ends on the surface of their rigid (tgBasicContactCableInfo.cpp:90-91 getConnectionPoint): radius 0.25 off the axis
+    assert abs(np.hypot(c.local_a[0], c.local_a[2]) - 0.25) < 1e-12 and abs(np.hypot(c.local_b[0], c.local_b[2]) - 0.25) < 1e-12
+    assert abs(c.rest_length - 8.0) < 1e-9 and c.prev_length == c.rest_length
+    # the model tree holds one tgBasicActuator (tgBasicContactCableInfo::createModel) beside the three rigids
+    assert nt.examples.tree_counts("ContactCableDemo")[1] == 1
+
+
+def test_muscle_np_momentum_and_energy_like_the_reference_suite():
+    """MuscleNP_test.cpp:77-114"""
+    m = demo_model()
+    w = oracle_py.OracleWorld(m, capi.WorldCfg)
+    w.set_rod_state(demo_states(m, 1)[0])
+    st0 = w.get_rod_state()
+    p0, e0 = momentum(m, st0), demo_energy(m, st0)
+    max_anchors, energies = 0, [e0]
+    for _ in range(100):
+        assert w.step(DT, 100) == 0
+        max_anchors = max(max_anchors, int(w.get_contact_cable_obs()[0, 4]))
+        energies.append(demo_energy(m, w.get_rod_state()))
+    st = w.get_rod_state()
+    p1 = momentum(m, st)
+    # EXPECT_FLOAT_EQ on x and z (4 float ulps), EXPECT_NEAR 1e-10 on y
+    assert abs(p1[0] - p0[0]) <= 4 * np.spacing(np.float32(p0[0])) and abs(p1[2] - p0[2]) <= 4 * np.spacing(np.float32(p0[2]))
+    assert abs(p1[1] - p0[1]) < 1e-10
+    # far tighter in fact: the anchor forces of a step sum to zero (tgBulletContactSpringCable.cpp:183-187)
+    assert np.abs(p1 - p0).max() < 1e-12
+    assert energies[-1] <= e0                                    # EXPECT_LE(energyEnd, energyStart)
+    assert np.all(np.diff(energies) <= 1e-9)                     # and never rises on the way (no damping in the cable: contact only removes energy)
+    assert max_anchors >= 2                                      # the cable did meet the third rod and bent around it
+    assert st[2, 7:10].dot(st[2, 7:10]) > 1e-4                   # and set it moving
+
+
+def test_sliding_anchors_sit_on_the_body_and_the_cable_pulls_not_pushes():
+    m = demo_model()
+    w = oracle_py.OracleWorld(m, capi.WorldCfg)
+    w.set_rod_state(demo_states(m, 1)[0])
+    seen = 0
+    for _ in range(800):
+        w.step(DT, 10)
+        a = w.get_contact_cable_anchors(0)
+        st = w.get_rod_state()
+        n = int(w.get_contact_cable_obs()[0, 4])
+        assert np.all(a[:n, 0] == 2) and np.all(a[n:, 0] == -1)   # only the free rod is ever touched; unused slots are marked
+        if n == 0:
+            continue
+        seen += 1
+        # distance of every anchor from the rod's axis segment = its radius (the capsule the restatement collides with), within the
+        # sideways slides of a step
+        from helpers import quat_rotate
+        axis = quat_rotate(st[2, 3:7][None], np.array([[0.0, 1.0, 0.0]]))[0]
+        for k in range(n):
+            rel = a[k, 1:4] - st[2, 0:3]
+            t = np.clip(rel.dot(axis), -0.75, 0.75)
+            assert abs(np.linalg.norm(rel - t * axis) - 0.25) < 0.02
+            assert abs(np.linalg.norm(a[k, 4:7]) - 1.0) < 1e-9
+    assert seen > 50
+
+
+def test_a_contact_cable_that_touches_nothing_is_a_plain_cable():
+    """While no body is near, tgBulletContactSpringCable::calculateAndApplyForce (two anchors) is tgBulletSpringCable's:
+    same tension, same clamped damping, same impulses.  (The slack branch differs in form only: force 0 either way.)"""
+    m = demo_model()
+    cc = m.contact_cables[0]
+    cc.damping = 5.0
+    cc.rest_length = cc.prev_length = 7.5   # pretension so that the cable works from the first step
+    plain = (capi.CableDesc * 1)()
+    p = plain[0]
+    p.body_a, p.body_b = cc.body_a, cc.body_b
+    for k in range(3):
+        p.local_a[k], p.local_b[k] = cc.local_a[k], cc.local_b[k]
+    p.stiffness, p.damping, p.rest_length, p.prev_length = cc.stiffness, cc.damping, cc.rest_length, cc.prev_length
+    p.actuator = capi.TGB_ACT_PASSIVE
+    p.max_tension, p.target_velocity, p.min_actual_length, p.min_rest_length = 1e9, 100.0, 0.1, 0.1
+    p.motor_radius, p.motor_inertia = 1.0, 1.0
+    m_plain = FlatModel(m.bodies, m.shapes, plain, m.ground, m.gravity, m.dt, "plain")
+    wa, wb = oracle_py.OracleWorld(m, capi.WorldCfg), oracle_py.OracleWorld(m_plain, capi.WorldCfg)
+    s = demo_states(m, 1)[0]
+    s[:, 7:10] *= 0.1     # slowly: the cable stays clear of the third rod for the whole run
+    wa.set_rod_state(s)
+    wb.set_rod_state(s)
+    for _ in range(30):   # 300 steps: the pretension pulls the two ends together; they are still 3 units apart then
+        wa.step(DT, 10)
+        wb.step(DT, 10)
+        assert int(wa.get_contact_cable_obs()[0, 4]) == 0
+        assert np.array_equal(wa.get_rod_state(), wb.get_rod_state())
+        assert np.allclose(wa.get_contact_cable_obs()[0, :3], wb.get_cable_obs()[0, :3], rtol=0, atol=1e-12)
+
+
+def test_contact_cable_descriptor_checks():
+    m = demo_model()
+    lib = oracle_py.load()
+    for field, bad in (("stiffness", 0.0), ("damping", -1.0), ("resolution", 0.0), ("thickness", -1.0), ("body_b", 7)):
+        mm = demo_model()
+        setattr(mm.contact_cables[0], field, bad)
+        with pytest.raises(ValueError):
+            oracle_py.OracleWorld(mm, capi.WorldCfg)
+    assert lib.tgo_num_contact_cables is not None and m.n_contact_cables == 1
+
+
+def test_yaml_front_end_builds_contact_cables(tmp_path):
+    """TensegrityModel.cpp:609-611,731-734: tgBasicContactCableInfo shares tgBasicActuatorInfo's parameters"""
+    text = """
+nodes:
+  a: [0, 2, 0]
+  b: [0, 4, 0]
+  c: [0, 12, 0]
+  d: [0, 14, 0]
+pair_groups:
+  rod:
+    - [a, b]
+    - [c, d]
+  wire:
+    - [b, c]
+builders:
+  rod:
+    class: tgRodInfo
+    parameters:
+      density: 1
+      radius: 0.25
+  wire:
+    class: tgBasicContactCableInfo
+    parameters:
+      stiffness: 500
+      damping: 2
+      pretension: 100
+"""
+    path = os.path.join(str(tmp_path), "cc.yaml")
+    open(path, "w").write(text)
+    m = nt.examples.build_yaml(path)
+    assert (m.n_bodies, m.n_cables, m.n_contact_cables) == (2, 0, 1)
+    c = m.contact_cables[0]
+    assert (c.stiffness, c.damping) == (500.0, 2.0)
+    assert abs(c.rest_length - (8.0 - 100.0 / 500.0)) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _device_run(model, states, precision, steps, chunk):
+    w = nt.BatchedWorld(model, states.shape[0], precision=precision)
+    try:
+        w.set_rod_state(states)
+        out = []
+        for _ in range(steps // chunk):
+            w.step(DT, chunk)
+            w.sync()
+            out.append((w.get_rod_state(), w.get_contact_cable_obs(), w.get_contact_cable_anchors(0)))
+        return out
+    finally:
+        w.close()
+
+
+def _oracle_run(model, states, steps, chunk):
+    worlds = [oracle_py.OracleWorld(model, capi.WorldCfg) for _ in range(states.shape[0])]
+    for w, s in zip(worlds, states):
+        w.set_rod_state(s)
+    out = []
+    for _ in range(steps // chunk):
+        for w in worlds:
+            w.step(DT, chunk)
+        out.append((np.stack([w.get_rod_state() for w in worlds]), np.stack([w.get_contact_cable_obs() for w in worlds]),
+                    np.stack([w.get_contact_cable_anchors(0) for w in worlds])))
+    return out
+
+
+@pytest.mark.gpu
+def test_contact_cable_demo_f64_matches_the_oracle():
+    """Double precision, 32 environments, 7000 steps (the cable meets the rod around step 4000 and bends around it): rod states, cable
+    length / tension and the anchor lists themselves, checkpoint by checkpoint."""
+    m = demo_model()
+    states = demo_states(m, 32)
+    dev = _device_run(m, states, "f64", 7000, 500)
+    ora = _oracle_run(m, states, 7000, 500)
+    touched = 0
+    for (rd, od, ad), (ro, oo, ao) in zip(dev, ora):
+        assert max(rod_errors(rd, ro, 10.0)) < 1e-7
+        assert np.array_equal(od[..., 4], oo[..., 4])                   # the same number of sliding anchors everywhere
+        assert np.abs(od[..., :2] - oo[..., :2]).max() < 1e-7           # rest, length
+        assert np.abs(od[..., 2] - oo[..., 2]).max() < 1e-4             # tension = 1000 x stretch
+        assert np.array_equal(ad[..., 0], ao[..., 0])                   # on the same bodies
+        assert np.abs(ad[..., 1:] - ao[..., 1:]).max() < 1e-6           # at the same places with the same normals
+        touched = max(touched, int((oo[..., 4] > 0).sum()))
+    assert touched >= 16
+
+
+@pytest.mark.gpu
+def test_contact_cable_demo_f32_conserves_momentum_and_follows_the_oracle():
+    m = demo_model()
+    states = demo_states(m, 256, seed=5)
+    dev = _device_run(m, states, "f32", 6000, 1000)
+    p0 = momentum(m, states)
+    e0 = demo_energy(m, states)
+    rd, od, ad = dev[-1]
+    # MuscleNP_test.cpp:108-112 on the device: single precision keeps the momentum to float round-off over 6000 steps
+    assert np.abs(momentum(m, rd) - p0).max() < 2e-4
+    assert np.all(demo_energy(m, rd) <= e0 * (1 + 1e-4))
+    assert (od[..., 4] > 0).sum() >= 64 or any((o[1][..., 4] > 0).sum() >= 64 for o in dev)
+    # up to first contact (checkpoint 3000) the single-precision trajectories are the oracle's within the stated tolerance
+    ora = _oracle_run(m, states[:32], 3000, 1000)
+    r3 = dev[2][0][:32]
+    assert max(rod_errors(r3, ora[2][0], 10.0)) < 1e-4
+
+
+@pytest.mark.gpu
+def test_contact_cable_world_steps_through_the_halves_and_rollout_host():
+    """tgb_step(w, dt, n) == n x (tgb_step_world, tgb_step_models) == tgb_rollout_host for a world with a contact cable"""
+    m = demo_model()
+    states = demo_states(m, 8, seed=9)
+    states[:, :2, 7:10] *= 4.0   # reach the rod within 1200 steps
+    a = nt.BatchedWorld(m, 8, precision="f64")
+    b = nt.BatchedWorld(m, 8, precision="f64")
+    c = nt.BatchedWorld(m, 8, precision="f64")
+    try:
+        a.set_rod_state(states)
+        b.set_rod_state(states)
+        a.step(DT, 1200)
+        for _ in range(1200):
+            b.step_world(DT)
+            b.step_models(DT)
+        a.sync()
+        b.sync()
+        assert np.array_equal(a.get_rod_state(), b.get_rod_state())
+        assert np.array_equal(a.get_contact_cable_obs(), b.get_contact_cable_obs())
+        assert (a.get_contact_cable_obs()[..., 4] > 0).any()
+        rods_out, _ = c.rollout_host(states, np.zeros((8, 0, 2)), DT, 1200)
+        assert np.array_equal(rods_out, a.get_rod_state())
+    finally:
+        a.close()
+        b.close()
+        c.close()

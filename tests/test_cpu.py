@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     # 2: tgb_cpg_desc gained cable_control and the PID gains; 3: box shapes (tgb_shape_desc.half_extent_z); 4: contact between bodies
-    assert lib.tgb_abi_version() == 5
+    assert lib.tgb_abi_version() == 6
 
 
 def test_create_fails_loudly_without_a_gpu():

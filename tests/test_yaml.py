@@ -361,7 +361,7 @@ def test_box_builder(tmp_path):
 @pytest.mark.parametrize("text,msg", [
     ("nodez:\n  a: [0, 0, 0]\n", "contains invalid key: nodez"),
     ("nodes:\n  a: [0, 0, 0]\n  a: [1, 0, 0]\n", "contains duplicate key: a"),
-    ("builders:\n  rod:\n    class: tgBasicContactCableInfo\n", "Unsupported builder class in this build"),
+    ("builders:\n  rod:\n    class: tgKinematicContactCableInfo\n", "Unsupported builder class in this build"),
     ("builders:\n  rod:\n    class: tgFooInfo\n", "Unsupported builder class: tgFooInfo"),
     ("builders:\n  rod:\n    parameters:\n      radius: 1\n", "Builder class not supplied for tag: rod"),
     ("builders:\n  rod:\n    class: tgRodInfo\n    parameters:\n      radios: 1\n", "Unsupported tgRodInfo parameter: radios"),
