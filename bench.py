@@ -71,6 +71,16 @@ def build_workload(name, n_env, seed):
         params = nt.escape_transform_actions(rng.uniform(size=(n_env, 32)), 9.0)
         ctrl = capi.TGB_CTRL_ESCAPE_SINE
         p_ctrl = 32
+    elif name == "contact_cable":
+        # ContactCableDemo (test_integration/MuscleNP), an ensemble of launch impulses; the cable meets the free rod
+        # within the first thousand steps and bends around it over sliding anchors
+        model = nt.build_example("ContactCableDemo")
+        rng = np.random.default_rng(seed)
+        rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
+        imp = 4.0 * (np.array([0.4, 0.0, 0.4]) * (1.0 + 0.15 * rng.uniform(-1, 1, size=(n_env, 1))) + 0.06 * rng.uniform(-1, 1, size=(n_env, 3)))
+        for b in (0, 1):
+            rods[:, b, 7:10] = imp / model.bodies[b].mass
+        params, ctrl, p_ctrl = None, capi.TGB_CTRL_NONE, 2 * (4 + 7 * 6)   # the cable's state incl. its sliding anchors, read and written
     elif name == "prism":
         model = nt.build_example("3_prism_noground")
         rods = random_poses(model, n_env, seed=seed)
@@ -111,6 +121,8 @@ def workload_desc(name, n_env, H, n_gpus):
     what = {"superball_noground": "SUPERball + sine controller, NO ground, zero gravity (tuning aid)",
             "superball": "SUPERball (EscapeModel: 6 rods, 24 basic-actuator cables) + EscapeController sine, flat box ground, g=98.1",
             "prism": "3-prism (3 rods, 9 cables), no ground, g=981 (contact-free drop)",
+            "contact_cable": "ContactCableDemo (rod + box joined by one tgBulletContactSpringCable that runs into a free rod), no ground, g=0 "
+                             "(MuscleNP_test); one step-kernel launch + one contact-cable launch per sim step",
             "crater": "SUPERball (EscapeModel) + EscapeController sine on tgCraterDeep (4 static box walls), box ground, g=98.1 (AppEscape)",
             "tetraspine": "TetraSpine (3 compound bodies, 12 basic-actuator cables) + CPG/impedance control, population evaluation, box ground, g=981",
             "flemons": "kinematic tetrahedral-complex spine (12 compound bodies, 88 kinematic-actuator cables) + CPG/impedance/PID control, "
@@ -266,7 +278,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--sim-steps", type=int, default=1000, help="simulation steps per launch (H)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--workload", default="superball", choices=["superball", "prism", "superball_noground", "tetraspine", "flemons", "crater"])
+    ap.add_argument("--workload", default="superball", choices=["superball", "prism", "superball_noground", "tetraspine", "flemons", "crater", "contact_cable"])
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -453,7 +465,7 @@ def main():
         hand_over()
     barrier()
     e2e_total = sum(e2e_s)
-    e2e_checksum = float(np.abs(cab_out[..., 2]).mean())
+    e2e_checksum = float(np.abs(cab_out[..., 2]).mean()) if w.C else float(np.abs(rod_out[..., 7:10]).mean())
 
     # max over ranks; the per-rank kernel durations travel too, so that the line names what limits the scaling
     per_rank_kernel = [ms_kernel]

@@ -50,6 +50,11 @@ struct tgb_world {
     int lastModelBody0 = 0;
     double* d_cc_state = nullptr;  /* [n_env][nCC][TGB_CC_STATE] (tgb_ccable.cuh) */
     double* d_cc_model = nullptr;  /* [nCC][TGB_CC_MODEL] */
+    /* CUDA graphs of `steps` x (step kernel, contact-cable kernel) for one range of environments, replayed by tgb_step: a world with
+       contact cables is launch bound (two small launches per simulation step) */
+    struct CcGraph { tgb_step_args args; int steps, envBegin, envCount; cudaGraphExec_t exec; };
+    std::vector<CcGraph> ccGraphs;
+    bool ccLaunchedDirectly = false; /* the kernels have been launched once outside a capture (function attributes set) */
     bool finalized = false;
     const tgb_ops* ops = nullptr;
     size_t scalarBytes = 4;
@@ -169,6 +174,7 @@ struct tgb_world {
         if (d_cpg_topo) cudaFree(d_cpg_topo);
         if (d_cpg_imp) cudaFree(d_cpg_imp);
         if (d_cpg_state) cudaFree(d_cpg_state);
+        for (CcGraph& g : ccGraphs) cudaGraphExecDestroy(g.exec);
         if (d_cc_state) cudaFree(d_cc_state);
         if (d_cc_model) cudaFree(d_cc_model);
         if (ev0) cudaEventDestroy(ev0);
@@ -529,6 +535,18 @@ int splitChunk(const tgb_world* w) {
 
 /* Worlds with contact cables: the cable's step (tgBulletContactSpringCable::step) follows the models half of every single step, so a
    call of n steps is n launches of the step kernel, each followed by one of the contact-cable kernel (tgb_ccable.cuh). */
+tgb_status launchContactCableSteps(tgb_world* w, const tgb_step_args& a, const tgb::tgb_ccable_args& ca, int nSteps, cudaStream_t s) {
+    for (int i = 0; i < nSteps; ++i) {
+        cudaError_t e = w->ops->step(a, w->lanes, w->threads, s);
+        if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
+        if (a.phases & 2) {
+            e = w->ops->ccable_step(ca, s);
+            if (e != cudaSuccess) return cudaFail(e, "contact cable kernel launch");
+        }
+    }
+    return TGB_OK;
+}
+
 tgb_status launchWithContactCables(tgb_world* w, double dt, int nSteps, int phases, int envBegin, int envCount, cudaStream_t s) {
     tgb_step_args a = stepArgs(w, dt, 1);
     a.phases = phases;
@@ -536,15 +554,47 @@ tgb_status launchWithContactCables(tgb_world* w, double dt, int nSteps, int phas
     a.n_env = envBegin + envCount;
     a.coupled_steps = nullptr; /* no tail split here: launches of one step */
     const tgb::tgb_ccable_args ca = w->ccArgs(envBegin, envCount, dt);
-    for (int i = 0; i < nSteps; ++i) {
-        cudaError_t e = w->ops->step(a, w->lanes, w->threads, s);
-        if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
-        w->launches += 1;
-        if (phases & 2) {
-            e = w->ops->ccable_step(ca, s);
-            if (e != cudaSuccess) return cudaFail(e, "contact cable kernel launch");
-            w->launches += 1;
+    const int perStep = (phases & 2) ? 2 : 1;
+    static const bool useGraphs = !(std::getenv("TGB_CC_GRAPHS") && std::atoi(std::getenv("TGB_CC_GRAPHS")) == 0);
+    const int kChunk = 250; /* steps per graph: 500 kernel nodes; longer calls replay it */
+    int done = 0;
+    while (useGraphs && nSteps - done >= 8) {
+        const int steps = std::min(kChunk, nSteps - done);
+        cudaGraphExec_t exec = nullptr;
+        for (const tgb_world::CcGraph& g : w->ccGraphs)
+            if (g.steps == steps && g.envBegin == envBegin && g.envCount == envCount && std::memcmp(&g.args, &a, sizeof(a)) == 0) { exec = g.exec; break; }
+        if (!exec) {
+            /* one untimed direct step first: the kernels' function attributes are set outside the capture */
+            if (!w->ccLaunchedDirectly) {
+                tgb_status st = launchContactCableSteps(w, a, ca, 1, s);
+                if (st != TGB_OK) return st;
+                w->ccLaunchedDirectly = true;
+                w->launches += perStep;
+                ++done;
+                continue;
+            }
+            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); break; }
+            const tgb_status st = launchContactCableSteps(w, a, ca, steps, s);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+            if (st != TGB_OK || ee != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); break; }
+            const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) { cudaGetLastError(); break; }
+            if (w->ccGraphs.size() >= 16) { cudaGraphExecDestroy(w->ccGraphs.front().exec); w->ccGraphs.erase(w->ccGraphs.begin()); }
+            tgb_world::CcGraph g;
+            g.args = a; g.steps = steps; g.envBegin = envBegin; g.envCount = envCount; g.exec = exec;
+            w->ccGraphs.push_back(g);
         }
+        const cudaError_t e = cudaGraphLaunch(exec, s);
+        if (e != cudaSuccess) return cudaFail(e, "contact cable graph launch");
+        w->launches += (int64_t)perStep * steps;
+        done += steps;
+    }
+    if (done < nSteps) {
+        tgb_status st = launchContactCableSteps(w, a, ca, nSteps - done, s);
+        if (st != TGB_OK) return st;
+        w->launches += (int64_t)perStep * (nSteps - done);
     }
     return TGB_OK;
 }

@@ -43,20 +43,29 @@ typedef V3<double> D3;
 struct CcAnchor { int body; D3 local, normal; };
 struct CcPoint { int body; D3 pos, normal; double dist; };
 
-/* the environment's record seen in double */
+/* the environment's record seen in double.  Bodies do not move during a cable's step (only velocities change), so their poses are
+   converted once per launch into a per-thread cache (local memory, L1-resident: 96 bytes per body) instead of once per use -- the
+   anchor passes ask for world positions some hundred times per step. */
+enum { TGB_CC_MAX_BODIES = 32 }; /* tgb_finalize refuses more than 32 bodies per environment */
 template <typename T>
 struct CcEnv {
     T* rec;
     const T* mt;
     const int* mi;
     int R, S;
-    __device__ D3 pos(int b) const { const T* s = rec + b * TGB_NBS; return D3((double)s[0], (double)s[1], (double)s[2]); }
-    __device__ M3<double> basis(int b) const {
-        const T* s = rec + b * TGB_NBS;
-        return M3<double>::fromQuat(Q4<double>((double)s[3], (double)s[4], (double)s[5], (double)s[6]));
+    D3 cpos[TGB_CC_MAX_BODIES];
+    M3<double> cbasis[TGB_CC_MAX_BODIES];
+    __device__ void cachePoses() {
+        for (int b = 0; b < R; ++b) {
+            const T* s = rec + b * TGB_NBS;
+            cpos[b] = D3((double)s[0], (double)s[1], (double)s[2]);
+            cbasis[b] = M3<double>::fromQuat(Q4<double>((double)s[3], (double)s[4], (double)s[5], (double)s[6]));
+        }
     }
-    __device__ D3 world(int b, const D3& local) const { return basis(b) * local + pos(b); }
-    __device__ D3 local(int b, const D3& w) const { return basis(b).tmul(w - pos(b)); }
+    __device__ const D3& pos(int b) const { return cpos[b]; }
+    __device__ const M3<double>& basis(int b) const { return cbasis[b]; }
+    __device__ D3 world(int b, const D3& local) const { return cbasis[b] * local + cpos[b]; }
+    __device__ D3 local(int b, const D3& w) const { return cbasis[b].tmul(w - cpos[b]); }
     __device__ double bodyField(int f, int b) const { return (double)mt[f * R + b]; }
     __device__ double shapeField(int f, int s) const { return (double)mt[TGB_NBF * R + f * S + s]; }
     __device__ int bodyInt(int f, int b) const { return mi[f * R + b]; }
@@ -65,8 +74,7 @@ struct CcEnv {
         const double im = bodyField(BF_INVMASS, b);
         if (im == 0.0) return;
         T* s = rec + b * TGB_NBS;
-        const M3<double> B = basis(b);
-        const M3<double> Iinv = B.conjugateDiag(D3(bodyField(BF_INVIX, b), bodyField(BF_INVIY, b), bodyField(BF_INVIZ, b)));
+        const M3<double> Iinv = cbasis[b].conjugateDiag(D3(bodyField(BF_INVIX, b), bodyField(BF_INVIY, b), bodyField(BF_INVIZ, b)));
         const D3 dw = Iinv * rel.cross(J);
         s[7] = (T)((double)s[7] + J.x * im); s[8] = (T)((double)s[8] + J.y * im); s[9] = (T)((double)s[9] + J.z * im);
         s[10] = (T)((double)s[10] + dw.x); s[11] = (T)((double)s[11] + dw.y); s[12] = (T)((double)s[12] + dw.z);
@@ -95,15 +103,18 @@ __device__ inline void ccErase(CcCable& c, int i) {
     for (int k = i; k + 1 < c.n; ++k) c.s[k] = c.s[k + 1];
     --c.n;
 }
-/* the manifold point of `body` nearest to p */
+/* the manifold point of `body` nearest to p (compared by squared distance; one square root at the end) */
 __device__ inline double ccNearest(const CcPoint* pts, int np, int body, const D3& p, D3& normal, D3& pos) {
-    double best = INFINITY;
+    double best2 = INFINITY;
+    int bi = -1;
     for (int i = 0; i < np; ++i) {
         if (pts[i].body != body) continue;
-        const double d = (pts[i].pos - p).length();
-        if (d < best) { best = d; normal = pts[i].normal; pos = pts[i].pos; }
+        const double d2 = (pts[i].pos - p).length2();
+        if (d2 < best2) { best2 = d2; bi = i; }
     }
-    return best;
+    if (bi < 0) return INFINITY;
+    normal = pts[bi].normal; pos = pts[bi].pos;
+    return sqrt(best2);
 }
 /* tgBulletSpringCableAnchor::getManifoldDistance, :279-334 */
 template <typename T>
@@ -126,14 +137,14 @@ __device__ bool ccUpdateManifold(const CcEnv<T>& E, const CcPoint* pts, int np, 
 /* findNearestPastAnchor, :799-937, restated: the segment of the chain nearest to pos */
 __device__ inline int ccNearestSegment(const D3* P, int n, const D3& pos) {
     int best = 0;
-    double bestD = INFINITY;
+    double bestD2 = INFINITY;
     for (int j = 0; j + 1 < n; ++j) {
         const D3 e = P[j + 1] - P[j];
         const double e2 = e.length2();
         double t = e2 > 0.0 ? (pos - P[j]).dot(e) / e2 : 0.0;
         t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
-        const double d = (P[j] + e * t - pos).length();
-        if (d < bestD) { bestD = d; best = j; }
+        const double d2 = (P[j] + e * t - pos).length2();
+        if (d2 < bestD2) { bestD2 = d2; best = j; }
     }
     return best;
 }
@@ -149,13 +160,12 @@ __device__ bool ccSetWorldPosition(const CcEnv<T>& E, const CcPoint* pts, int np
     }
     return (current - contactPos).length() <= 0.1;
 }
-/* updateAnchorPositions, :484-561 */
+/* updateAnchorPositions, :484-561.  P = the chain, kept current: only the moved anchor's entry changes (recomputed from its new local
+   position exactly as ccChain would), a removed anchor's entry is closed up. */
 template <typename T>
-__device__ int ccUpdateAnchorPositions(const CcEnv<T>& E, const CcPoint* pts, int np, CcCable& c) {
+__device__ int ccUpdateAnchorPositions(const CcEnv<T>& E, const CcPoint* pts, int np, CcCable& c, D3* P) {
     int numPruned = 0, i = 0;
-    D3 P[TGB_CC_CHAIN];
     while (i < c.n) {
-        ccChain(E, c, P);
         const D3 back = P[i], current = P[i + 1], forward = P[i + 2];
         const D3 lineA = forward - current, lineB = back - current;
         const D3 n = c.s[i].normal;
@@ -171,8 +181,14 @@ __device__ int ccUpdateAnchorPositions(const CcEnv<T>& E, const CcPoint* pts, in
             }
         }
         const D3 newPos = current + tangentMove;
-        if (!ccSetWorldPosition(E, pts, np, c.s[i], newPos)) { ccErase(c, i); ++numPruned; }
-        else ++i;
+        if (!ccSetWorldPosition(E, pts, np, c.s[i], newPos)) {
+            ccErase(c, i);
+            for (int k = i + 1; k < c.n + 2; ++k) P[k] = P[k + 1];
+            ++numPruned;
+        } else {
+            P[i + 1] = E.world(c.s[i].body, c.s[i].local);
+            ++i;
+        }
     }
     return numPruned;
 }
@@ -191,7 +207,7 @@ __device__ inline void ccClosest(const D3& pa, const D3& da, double ha, const D3
 }
 
 template <typename T>
-__global__ void __launch_bounds__(64) ccable_step_kernel(tgb_ccable_args a) {
+__global__ void __launch_bounds__(32) ccable_step_kernel(tgb_ccable_args a) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= a.env_count) return;
     const int env = a.env_begin + e;
@@ -200,6 +216,7 @@ __global__ void __launch_bounds__(64) ccable_step_kernel(tgb_ccable_args a) {
     E.mt = reinterpret_cast<const T*>(a.model_t);
     E.mi = a.model_i;
     E.R = a.R; E.S = a.S;
+    E.cachePoses();
     const double dt = a.dt;
     const double kBreaking = 0.02; /* gContactBreakingThreshold */
     CcPoint pts[TGB_CC_MAX_POINTS];
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__(64) ccable_step_kernel(tgb_ccable_args a) {
             for (int bi = 0; bi < a.R; ++bi) {
                 const int s0 = E.bodyInt(BI_SHAPE_BEGIN, bi), sn = E.bodyInt(BI_SHAPE_COUNT, bi);
                 if (sn <= 0) continue;
-                const M3<double> B = E.basis(bi);
+                const M3<double>& B = E.basis(bi);
                 const D3 x = E.pos(bi);
                 for (int si = s0; si < s0 + sn; ++si) {
                     if (E.shapeField(SF_KIND, si) == (double)TGB_SHAPE_BOX) continue;
@@ -291,22 +308,27 @@ __global__ void __launch_bounds__(64) ccable_step_kernel(tgb_ccable_args a) {
             if (ccNearest(pts, np, c.s[i].body, E.world(c.s[i].body, c.s[i].local), n, pos) == INFINITY) { ccErase(c, i); ++numPruned; }
             else ++i;
         }
+        nP = ccChain(E, c, P);
         while (numPruned > 0 || passes <= 3) {
-            numPruned = ccUpdateAnchorPositions(E, pts, np, c);
+            numPruned = ccUpdateAnchorPositions(E, pts, np, c, P);
             if (numPruned == 0) {
                 int i = 0;
                 while (i < c.n) {
-                    ccChain(E, c, P);
                     const D3 lineA = P[i + 2] - P[i + 1], lineB = P[i] - P[i + 1];
                     const D3 n = c.s[i].normal;
                     double nv1, nv2;
-                    if (lineA.length() < resolution / 2.0 || lineB.length() < resolution / 2.0) nv1 = nv2 = -1.0;
+                    const double half = resolution / 2.0;
+                    if (lineA.length2() < half * half || lineB.length2() < half * half) nv1 = nv2 = -1.0;
                     else { nv1 = lineA.dot(n); nv2 = lineB.dot(n); }
-                    if (nv1 < 0.0 || nv2 < 0.0) { ccErase(c, i); ++numPruned; }
-                    else ++i;
+                    if (nv1 < 0.0 || nv2 < 0.0) {
+                        ccErase(c, i);
+                        for (int k = i + 1; k < c.n + 2; ++k) P[k] = P[k + 1];
+                        ++numPruned;
+                    } else ++i;
                 }
             }
             if (numPruned == 0) ++passes; else passes = 0;
+            if (c.n == 0) break; /* nothing left to slide or remove: the remaining passes are empty */
         }
         /* calculateAndApplyForce, :127-194 */
         nP = ccChain(E, c, P);
@@ -356,6 +378,7 @@ __global__ void ccable_obs_kernel(tgb_ccable_args a, double* __restrict__ obs, i
     E.mt = reinterpret_cast<const T*>(a.model_t);
     E.mi = a.model_i;
     E.R = a.R; E.S = a.S;
+    E.cachePoses();
     const double* cm = a.cc_model + (size_t)ci * TGB_CC_MODEL;
     const double* cs = a.cc_state + ((size_t)env * a.n_cc + ci) * TGB_CC_STATE;
     CcCable c;

@@ -67,7 +67,7 @@ cudaError_t com(const tgb::tgb_io_args& a, int mode, double* scores, float* scor
 
 cudaError_t ccable_step(const tgb::tgb_ccable_args& a, cudaStream_t s) {
     if (a.env_count <= 0 || a.n_cc <= 0) return cudaSuccess;
-    tgb::ccable_step_kernel<scalar_t><<<blocksFor(a.env_count, 64), 64, 0, s>>>(a);
+    tgb::ccable_step_kernel<scalar_t><<<blocksFor(a.env_count, 32), 32, 0, s>>>(a);
     return cudaGetLastError();
 }
 cudaError_t ccable_obs(const tgb::tgb_ccable_args& a, double* obs, int cable, double* anchors, cudaStream_t s) {

@@ -50,6 +50,7 @@ def load():
     lib.tgo_get_status.argtypes = [vp]
     lib.tgo_get_cpg_state.argtypes = [vp, vp]
     lib.tgo_add_contact_cables.argtypes = [vp, vp, i]
+    lib.tgo_set_batch_contact_cables.argtypes = [vp, i]
     lib.tgo_num_contact_cables.argtypes = [vp]
     lib.tgo_get_contact_cable_obs.argtypes = [vp, vp]
     lib.tgo_get_contact_cable_anchors.argtypes = [vp, i, vp]
@@ -206,6 +207,8 @@ def rollout_batch(model, cfg_cls, rod_in, cable_in, dt, n_steps, ctrl_kind=0, ct
     cab_out = np.empty((n_env, Cn, 4))
     scores = np.empty((n_env, 2))
     status = np.zeros(n_env, dtype=np.int32)
+    cc = getattr(model, "contact_cables", None)
+    lib.tgo_set_batch_contact_cables(cc, 0 if cc is None else len(cc))
     rc = lib.tgo_rollout_batch(C.byref(cfg), C.byref(model.ground), model.bodies, R, model.shapes, len(model.shapes), model.cables, Cn,
                                ctrl_kind, _p(ctrl_params), per_env, _p(setup_input), setup_dt, n_env, _p(rod_in), _p(cable_in), dt,
                                n_steps, n_threads, _p(rod_out), _p(cab_out), None if cpg_desc is None else C.byref(cpg_desc),

@@ -435,13 +435,16 @@ struct tgo_world {
     }
     /* the manifold point of `body` nearest to p: its distance to p (INFINITY when the body has none) and its normal */
     static double ccNearest(const std::vector<CablePoint>& pts, int body, const V3& p, V3& normal, V3& pos) {
-        double best = INFINITY;
+        double best2 = INFINITY;
+        const CablePoint* bm = nullptr;
         for (const CablePoint& m : pts) {
             if (m.body != body) continue;
-            const double d = (m.pos - p).length();
-            if (d < best) { best = d; normal = m.normal; pos = m.pos; }
+            const double d2 = (m.pos - p).length2();
+            if (d2 < best2) { best2 = d2; bm = &m; }
         }
-        return best;
+        if (!bm) return INFINITY;
+        normal = bm->normal; pos = bm->pos;
+        return std::sqrt(best2);
     }
     /* tgBulletSpringCableAnchor::getManifoldDistance (:279-334) of a sliding anchor: distance to the nearest point of its body's
        manifold, and that point's normal when it lies within 0.1 (else the anchor's own) */
@@ -470,7 +473,7 @@ struct tgo_world {
             const double e2 = e.length2();
             double t = e2 > 0.0 ? (pos - P[j]).dot(e) / e2 : 0.0;
             t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
-            const double d = (P[j] + e * t - pos).length();
+            const double d = (P[j] + e * t - pos).length2();
             if (d < bestD) { bestD = d; best = (int)j; }
         }
         return best;
@@ -598,7 +601,8 @@ struct tgo_world {
                     const V3 lineA = P[i + 2] - P[i + 1], lineB = P[i] - P[i + 1];
                     const V3 n = cc.slides[i].normal;
                     double nv1, nv2;
-                    if (lineA.length() < cc.resolution / 2.0 || lineB.length() < cc.resolution / 2.0) nv1 = nv2 = -1.0;
+                    const double half = cc.resolution / 2.0;
+                    if (lineA.length2() < half * half || lineB.length2() < half * half) nv1 = nv2 = -1.0;
                     else { nv1 = lineA.dot(n); nv2 = lineB.dot(n); }
                     if (nv1 < 0.0 || nv2 < 0.0) { cc.slides.erase(cc.slides.begin() + i); ++numPruned; }
                     else ++i;
@@ -1553,6 +1557,12 @@ void tgo_set_warm_start(tgo_world* w, double factor) { w->warmStart = factor; w-
 double tgo_get_min_clearance(const tgo_world* w) { return w->minClearance; }
 void tgo_reset_min_clearance(tgo_world* w) { w->minClearance = 1e30; }
 
+/* contact cables added to every world tgo_rollout_batch creates (body indices relative to its model); n = 0 clears */
+static std::vector<tgb_contact_cable_desc> g_batchContactCables;
+void tgo_set_batch_contact_cables(const tgb_contact_cable_desc* cables, int n) {
+    g_batchContactCables.assign(cables, cables + (n > 0 ? n : 0));
+}
+
 int tgo_rollout_batch(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, const tgb_body_desc* bodies, int n_bodies,
                       const tgb_shape_desc* shapes, int n_shapes, const tgb_cable_desc* cables, int n_cables, int ctrl_kind,
                       const double* ctrl_params, int params_per_env, const double* setup_input, double setup_dt, int n_env,
@@ -1564,6 +1574,7 @@ int tgo_rollout_batch(const tgb_world_cfg* cfg, const tgb_ground_desc* ground, c
         for (int e = t; e < n_env; e += n_threads) {
             tgo_world* w = tgo_create(cfg, ground);
             tgo_add_model_flat(w, bodies, n_bodies, shapes, n_shapes, cables, n_cables);
+            if (!g_batchContactCables.empty()) tgo_add_contact_cables(w, g_batchContactCables.data(), (int)g_batchContactCables.size());
             if (rod_state_in) tgo_set_rod_state(w, rod_state_in + (size_t)e * n_bodies * 13);
             if (cable_state_in) tgo_set_cable_state(w, cable_state_in + (size_t)e * n_cables * 2);
             if (setup_input) tgo_set_control_input(w, setup_input, setup_dt);
