@@ -271,35 +271,39 @@ __global__ void __launch_bounds__(32) ccable_step_kernel(tgb_ccable_args a) {
                 }
             }
         }
-        /* updateManifolds + updateAnchorList (:196-482): proposals of the penetrating points, one after the other */
+        /* updateManifolds + updateAnchorList (:196-482): proposals of the penetrating points, one after the other.  A proposal changes
+           the cable only if it passes every test (the tests themselves change nothing here: an anchor's manifold is its body's point
+           set), so they run cheapest first -- the cap, the two sides of the contact plane, the neighbours' normals -- and the merge
+           test with its manifold distances last; the chain is recomputed only after an insertion. */
+        nP = ccChain(E, c, P);
         for (int pi = 0; pi < np; ++pi) {
-            const CcPoint m = pts[pi];
+            if (c.n >= TGB_CCABLE_MAX_SLIDING) break;
+            const CcPoint& m = pts[pi];
             if (!(m.dist < 0.0)) continue;
-            nP = ccChain(E, c, P);
             const int j = ccNearestSegment(P, nP, m.pos);
             const D3 lineA = P[j + 1] - m.pos, lineB = P[j] - m.pos;
-            const double lengthA = lineA.length(), lengthB = lineB.length();
-            const bool backSliding = j >= 1, fwdSliding = j + 1 <= c.n;
-            D3 tmp;
-            const double mDistB = backSliding ? ccManifoldDistance(E, pts, np, c.s[j - 1], m.body, tmp) : INFINITY;
-            const double mDistA = fwdSliding ? ccManifoldDistance(E, pts, np, c.s[j], m.body, tmp) : INFINITY;
-            const int backBody = backSliding ? c.s[j - 1].body : c.a, fwdBody = fwdSliding ? c.s[j].body : c.b;
-            bool del = false;
-            if (lengthB <= resolution && m.body == backBody && mDistB < mDistA)
-                if (backSliding && ccUpdateManifold(E, pts, np, c.s[j - 1], m.body)) del = true;
-            if (lengthA <= resolution && m.body == fwdBody && (!del || mDistA < mDistB))
-                if (fwdSliding && ccUpdateManifold(E, pts, np, c.s[j], m.body)) del = true;
-            if (del) continue;
             if (lineA.dot(m.normal) < 0.0 || lineB.dot(m.normal) < 0.0) continue;
-            const D3 zero(0.0, 0.0, 0.0);
-            const D3 backNormal = backSliding ? c.s[j - 1].normal : zero, fwdNormal = fwdSliding ? c.s[j].normal : zero;
-            if ((backNormal.dot(m.normal) < 0.0 && m.body == backBody) || (fwdNormal.dot(m.normal) < 0.0 && m.body == fwdBody)) continue;
-            if (c.n >= TGB_CCABLE_MAX_SLIDING) continue;
+            const bool backSliding = j >= 1, fwdSliding = j + 1 <= c.n;
+            const int backBody = backSliding ? c.s[j - 1].body : c.a, fwdBody = fwdSliding ? c.s[j].body : c.b;
+            if ((backSliding && m.body == backBody && c.s[j - 1].normal.dot(m.normal) < 0.0) ||
+                (fwdSliding && m.body == fwdBody && c.s[j].normal.dot(m.normal) < 0.0)) continue;
+            const double lengthA = lineA.length(), lengthB = lineB.length();
+            const bool nearBack = lengthB <= resolution && m.body == backBody && backSliding;
+            const bool nearFwd = lengthA <= resolution && m.body == fwdBody && fwdSliding;
+            if (nearBack || nearFwd) {
+                D3 tmp;
+                const double mDistB = backSliding ? ccManifoldDistance(E, pts, np, c.s[j - 1], m.body, tmp) : INFINITY;
+                const double mDistA = fwdSliding ? ccManifoldDistance(E, pts, np, c.s[j], m.body, tmp) : INFINITY;
+                bool del = false;
+                if (nearBack && mDistB < mDistA && ccUpdateManifold(E, pts, np, c.s[j - 1], m.body)) del = true;
+                if (nearFwd && (!del || mDistA < mDistB) && ccUpdateManifold(E, pts, np, c.s[j], m.body)) del = true;
+                if (del) continue;
+            }
             for (int q = c.n; q > j; --q) c.s[q] = c.s[q - 1];
             c.s[j].body = m.body; c.s[j].local = E.local(m.body, m.pos); c.s[j].normal = m.normal;
             ++c.n;
             nP = ccChain(E, c, P);
-            if (ccLength(P, nP) > prev + 2.0 * resolution) ccErase(c, j);
+            if (ccLength(P, nP) > prev + 2.0 * resolution) { ccErase(c, j); nP = ccChain(E, c, P); }
         }
         /* pruneAnchors, :563-673 */
         int numPruned = 0, passes = 0;
