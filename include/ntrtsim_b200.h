@@ -369,9 +369,10 @@ tgb_status tgb_get_min_clearance(tgb_world* w, int32_t env_begin, int32_t env_co
    tgb_set_pair_contact_cap): a cylinder counts as the capsule inscribed in it, a sphere as itself, boxes take no part; the "manifold" of
    (cable, body) is the set of closest-point pairs of this step's segments with the body's shapes that are nearer than Bullet's contact
    breaking threshold (0.02), evaluated at the poses of the cable's step (Bullet's are one world step old).  At most
-   TGB_CCABLE_MAX_SLIDING sliding anchors per cable: further proposals are dropped.  The actuator is tgBasicActuator with no control
-   input (its step is the cable's step, src/core/tgBasicActuator.cpp:227-241).  Worlds with contact cables run one launch of the step
-   kernel plus one of the contact-cable kernel per step. */
+   TGB_CCABLE_MAX_SLIDING sliding anchors per cable: further proposals are dropped.  The actuator is tgBasicActuator: its step is the
+   cable's step (src/core/tgBasicActuator.cpp:227-241); control input arrives through tgb_set_contact_cable_control_input (the
+   device-side controllers of tgb_set_controller drive the two-anchor cables only).  Worlds with contact cables run one launch of
+   the step kernel plus one of the contact-cable kernel per step. */
 #define TGB_CCABLE_MAX_SLIDING 6
 /* per-cable observation: rest length, actual length (over all anchors), tension, velocity, number of sliding anchors */
 #define TGB_CCABLE_OBS_DOUBLES 5
@@ -385,6 +386,8 @@ typedef struct {
     double prev_length;    /* == rest_length (tgBulletSpringCable.cpp:47, the first-step damping artefact) */
     double thickness;      /* tgBulletContactSpringCable.h:89: 0.001 */
     double resolution;     /* tgBulletContactSpringCable.h:90: 0.1 */
+    /* the tgBasicActuator around it (tgSpringCableActuator::Config): used by tgb_set_contact_cable_control_input */
+    double max_tension, target_velocity, min_actual_length, min_rest_length;
 } tgb_contact_cable_desc;
 
 /* Append contact cables (body indices relative to the model added LAST with tgb_add_model_flat).  Before tgb_finalize. */
@@ -395,6 +398,11 @@ tgb_status tgb_get_contact_cable_obs(tgb_world* w, int32_t env_begin, int32_t en
 /* the sliding anchors of one contact cable, in order from anchor 1 to anchor 2: out[env_count][TGB_CCABLE_MAX_SLIDING][7], unused
    slots zero with body index -1 (tgSpringCable::getAnchors without the two permanent ends) */
 tgb_status tgb_get_contact_cable_anchors(tgb_world* w, int32_t cable, int32_t env_begin, int32_t env_count, double* out);
+/* tgBasicActuator::setControlInput(input, dt) (src/core/tgBasicActuator.cpp:149-168) on the contact cables of every environment in the
+   range, once, now: preferred length = input, then moveMotors(dt) (:170-225) with the cable's actual length over all its anchors.
+   input: [n_contact_cables] (broadcast != 0) or [env_count][n_contact_cables]; negative -> TGB_ERR_INVALID_ARGUMENT, NaN = leave alone. */
+tgb_status tgb_set_contact_cable_control_input(tgb_world* w, int32_t env_begin, int32_t env_count, const double* input, int32_t broadcast,
+                                               double dt);
 
 /* Threads per CTA of the step kernel (32, 64, 96, 128; a multiple of lanes per env); 0 = automatic
    (also settable through the environment variable TGB_BLOCK_THREADS). */

@@ -50,7 +50,8 @@ class CableDesc(C.Structure):
 class ContactCableDesc(C.Structure):
     _fields_ = [("body_a", C.c_int32), ("body_b", C.c_int32), ("local_a", C.c_double * 3), ("local_b", C.c_double * 3),
                 ("stiffness", C.c_double), ("damping", C.c_double), ("rest_length", C.c_double), ("prev_length", C.c_double),
-                ("thickness", C.c_double), ("resolution", C.c_double)]
+                ("thickness", C.c_double), ("resolution", C.c_double), ("max_tension", C.c_double), ("target_velocity", C.c_double),
+                ("min_actual_length", C.c_double), ("min_rest_length", C.c_double)]
 
 
 CCABLE_MAX_SLIDING = 6
@@ -83,6 +84,7 @@ ABI_SYMBOLS = [
     "tgb_set_block_threads", "tgb_set_wide_layout", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
     "tgb_set_pair_contact_cap", "tgb_get_min_clearance", "tgb_set_warm_starting", "tgb_set_tail_split",
     "tgb_add_contact_cables", "tgb_num_contact_cables", "tgb_get_contact_cable_obs", "tgb_get_contact_cable_anchors",
+    "tgb_set_contact_cable_control_input",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -157,6 +159,7 @@ def load():
     lib.tgb_num_contact_cables.argtypes = [_vp, C.POINTER(_i32)]
     lib.tgb_get_contact_cable_obs.argtypes = [_vp, _i32, _i32, _vp]
     lib.tgb_get_contact_cable_anchors.argtypes = [_vp, _i32, _i32, _i32, _vp]
+    lib.tgb_set_contact_cable_control_input.argtypes = [_vp, _i32, _i32, _vp, _i32, C.c_double]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tgb_abi_version", "tgb_last_error", "tgb_device_count"):

@@ -786,6 +786,10 @@ tgb_status tgb_add_contact_cables(tgb_world* w, const tgb_contact_cable_desc* ca
         if (c.rest_length < 0.0 || c.prev_length < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "Pretension causes string to shorten past rest length!");
         if (c.thickness < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "thickness is negative.");
         if (!(c.resolution > 0.0)) return fail(TGB_ERR_INVALID_ARGUMENT, "resolution is not positive.");
+        /* tgSpringCableActuator::Config (tgSpringCableActuator.cpp:61-87) */
+        if (c.max_tension < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "max tension is negative.");
+        if (c.min_actual_length < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "min Actual Length is negative.");
+        if (c.min_rest_length < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "min Rest Length is negative.");
     }
     for (int i = 0; i < n_cables; ++i) {
         tgb_contact_cable_desc c = cables[i];
@@ -1008,6 +1012,9 @@ tgb_status tgb_finalize(tgb_world* w) {
             m[tgb::CCM_A] = c.body_a; m[tgb::CCM_B] = c.body_b;
             for (int k = 0; k < 3; ++k) { m[tgb::CCM_LA + k] = c.local_a[k]; m[tgb::CCM_LB + k] = c.local_b[k]; }
             m[tgb::CCM_K] = c.stiffness; m[tgb::CCM_C] = c.damping; m[tgb::CCM_THICK] = c.thickness; m[tgb::CCM_RES] = c.resolution;
+            m[tgb::CCM_MAXTENS] = c.max_tension; m[tgb::CCM_TVEL] = c.target_velocity; m[tgb::CCM_MINAL] = c.min_actual_length;
+            m[tgb::CCM_MINRL] = c.min_rest_length;
+            cs[(size_t)i * tgb::TGB_CC_STATE + tgb::CCS_PREF] = c.rest_length; /* tgBasicActuator ctor: preferred = rest */
             cs[(size_t)i * tgb::TGB_CC_STATE + tgb::CCS_REST] = c.rest_length;
             cs[(size_t)i * tgb::TGB_CC_STATE + tgb::CCS_PREV] = c.prev_length;
         }
@@ -1099,6 +1106,23 @@ tgb_status tgb_get_contact_cable_obs(tgb_world* w, int32_t env_begin, int32_t en
     if (st != TGB_OK) return st;
     TGB_CUDA(w->ops->ccable_obs(w->ccArgs(env_begin, env_count, 0.0), w->d_stage, -1, nullptr, w->stream));
     TGB_CUDA(cudaMemcpyAsync(obs, w->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    return TGB_OK;
+}
+
+tgb_status tgb_set_contact_cable_control_input(tgb_world* w, int32_t env_begin, int32_t env_count, const double* input, int32_t broadcast,
+                                               double dt) {
+    TGB_NEED_FINAL(w);
+    if (!input || !rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_set_contact_cable_control_input: bad range or NULL buffer");
+    const size_t ncc = w->contactCables.size();
+    const size_t n = (broadcast ? 1 : (size_t)env_count) * ncc;
+    if (n == 0 || env_count == 0) return TGB_OK;
+    for (size_t i = 0; i < n; ++i)
+        if (input[i] < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "Rest length is negative."); /* tgBasicActuator.cpp:139-142 */
+    tgb_status st = w->ensureStage(n);
+    if (st != TGB_OK) return st;
+    TGB_CUDA(cudaMemcpyAsync(w->d_stage, input, n * sizeof(double), cudaMemcpyHostToDevice, w->stream));
+    TGB_CUDA(w->ops->ccable_control(w->ccArgs(env_begin, env_count, dt), w->d_stage, broadcast ? 1 : 0, w->stream));
     TGB_CUDA(cudaStreamSynchronize(w->stream));
     return TGB_OK;
 }

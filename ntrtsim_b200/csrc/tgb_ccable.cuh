@@ -13,7 +13,7 @@
  * All arithmetic is double (the cable is thin -- 1e-3 against rods of 0.25 -- and the anchor tests compare lengths with sums of
  * lengths); the record is read and written in the world's scalar type.
  *
- * HBM: cc_state double[n_env][n_cc][TGB_CC_STATE] = rest length, previous length, velocity, number of sliding anchors, then
+ * HBM: cc_state double[n_env][n_cc][TGB_CC_STATE] = rest length, previous length, velocity, number of sliding anchors, preferred length, then
  * TGB_CCABLE_MAX_SLIDING x (body, local position 3, contact normal 3); cc_model double[n_cc][TGB_CC_MODEL].
  */
 #pragma once
@@ -23,8 +23,8 @@
 
 namespace tgb {
 
-enum { CCM_A = 0, CCM_B, CCM_LA = 2, CCM_LB = 5, CCM_K = 8, CCM_C, CCM_THICK, CCM_RES, TGB_CC_MODEL = 12 };
-enum { CCS_REST = 0, CCS_PREV, CCS_VEL, CCS_N, CCS_ANCHOR = 4, TGB_CC_ANCHOR = 7, TGB_CC_STATE = CCS_ANCHOR + TGB_CCABLE_MAX_SLIDING * TGB_CC_ANCHOR };
+enum { CCM_A = 0, CCM_B, CCM_LA = 2, CCM_LB = 5, CCM_K = 8, CCM_C, CCM_THICK, CCM_RES, CCM_MAXTENS, CCM_TVEL, CCM_MINAL, CCM_MINRL, TGB_CC_MODEL = 16 };
+enum { CCS_REST = 0, CCS_PREV, CCS_VEL, CCS_N, CCS_PREF, CCS_ANCHOR = 5, TGB_CC_ANCHOR = 7, TGB_CC_STATE = CCS_ANCHOR + TGB_CCABLE_MAX_SLIDING * TGB_CC_ANCHOR };
 enum { TGB_CC_MAX_POINTS = 64, TGB_CC_CHAIN = TGB_CCABLE_MAX_SLIDING + 2 };
 
 struct tgb_ccable_args {
@@ -368,6 +368,52 @@ __global__ void __launch_bounds__(32) ccable_step_kernel(tgb_ccable_args a) {
             q[4] = c.s[i].normal.x; q[5] = c.s[i].normal.y; q[6] = c.s[i].normal.z;
         }
     }
+}
+
+/* tgBasicActuator::setControlInput(input, dt) -> moveMotors (src/core/tgBasicActuator.cpp:149-225) for every contact cable; NaN input =
+   leave the cable alone.  One thread per (environment, cable). */
+template <typename T>
+__global__ void ccable_control_kernel(tgb_ccable_args a, const double* __restrict__ input, int broadcast) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.env_count * a.n_cc) return;
+    const int e = i / a.n_cc, ci = i - e * a.n_cc;
+    const int env = a.env_begin + e;
+    const double in = input[(size_t)(broadcast ? 0 : e) * a.n_cc + ci];
+    if (!(in >= 0.0)) return;
+    CcEnv<T> E;
+    E.rec = reinterpret_cast<T*>(a.state) + (size_t)env * a.stride;
+    E.mt = reinterpret_cast<const T*>(a.model_t);
+    E.mi = a.model_i;
+    E.R = a.R; E.S = a.S;
+    E.cachePoses();
+    const double* cm = a.cc_model + (size_t)ci * TGB_CC_MODEL;
+    double* cs = a.cc_state + ((size_t)env * a.n_cc + ci) * TGB_CC_STATE;
+    CcCable c;
+    c.a = (int)cm[CCM_A]; c.b = (int)cm[CCM_B];
+    c.la = D3(cm[CCM_LA], cm[CCM_LA + 1], cm[CCM_LA + 2]);
+    c.lb = D3(cm[CCM_LB], cm[CCM_LB + 1], cm[CCM_LB + 2]);
+    c.n = (int)cs[CCS_N];
+    for (int q = 0; q < c.n; ++q) {
+        const double* s = cs + CCS_ANCHOR + q * TGB_CC_ANCHOR;
+        c.s[q].body = (int)s[0];
+        c.s[q].local = D3(s[1], s[2], s[3]);
+    }
+    D3 P[TGB_CC_CHAIN];
+    const int nP = ccChain(E, c, P);
+    const double actual = ccLength(P, nP);
+    const double k = cm[CCM_K], maxTens = cm[CCM_MAXTENS];
+    double pref = in, rest = cs[CCS_REST];
+    const double stepSize = cm[CCM_TVEL] * a.dt;
+    if ((actual - pref) * k > maxTens) pref = actual - maxTens / k;
+    const double diff = pref - rest;
+    const double fabsDiff = fabs(diff);
+    if ((actual > cm[CCM_MINAL]) || (diff > 0.0)) {
+        if (fabsDiff > stepSize) rest += (diff / fabsDiff) * stepSize;
+        else rest += diff;
+    }
+    rest = (rest > cm[CCM_MINRL]) ? rest : cm[CCM_MINRL];
+    cs[CCS_REST] = rest;
+    cs[CCS_PREF] = pref;
 }
 
 /* observations [env_count][n_cc][5] and, with cable >= 0, that cable's sliding anchors [env_count][MAX][7] */

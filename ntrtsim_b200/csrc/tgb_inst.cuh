@@ -80,9 +80,15 @@ cudaError_t ccable_obs(const tgb::tgb_ccable_args& a, double* obs, int cable, do
     tgb::ccable_obs_kernel<scalar_t><<<blocksFor(n, 128), 128, 0, s>>>(a, obs, cable, anchors);
     return cudaGetLastError();
 }
+cudaError_t ccable_control(const tgb::tgb_ccable_args& a, const double* input, int broadcast, cudaStream_t s) {
+    const int n = a.env_count * a.n_cc;
+    if (n <= 0) return cudaSuccess;
+    tgb::ccable_control_kernel<scalar_t><<<blocksFor(n, 64), 64, 0, s>>>(a, input, broadcast);
+    return cudaGetLastError();
+}
 
 const tgb_ops kOps = {sizeof(scalar_t), step, wide_ctas_per_sm, step_smem, pack_rods, unpack_rods, pack_cables, cable_obs, control_input, com,
-                      ccable_step, ccable_obs};
+                      ccable_step, ccable_obs, ccable_control};
 
 } // namespace
 

@@ -28,6 +28,7 @@ struct tgb_ops {
     /* contact cables (tgb_ccable.cuh): one step of every contact cable of the environments in the range; observations / anchors */
     cudaError_t (*ccable_step)(const tgb::tgb_ccable_args& a, cudaStream_t s);
     cudaError_t (*ccable_obs)(const tgb::tgb_ccable_args& a, double* obs, int cable, double* anchors, cudaStream_t s);
+    cudaError_t (*ccable_control)(const tgb::tgb_ccable_args& a, const double* input, int broadcast, cudaStream_t s);
 };
 
 const tgb_ops* tgb_ops_f32();

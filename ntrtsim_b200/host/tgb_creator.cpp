@@ -635,6 +635,8 @@ void tgBasicContactCableInfo::initConnector(tgWorldB200Impl& world) {
     c.stiffness = plain.stiffness; c.damping = plain.damping;
     c.rest_length = plain.rest_length; c.prev_length = plain.prev_length;
     c.thickness = 0.001; c.resolution = 0.1;
+    c.max_tension = plain.max_tension; c.target_velocity = plain.target_velocity;
+    c.min_actual_length = plain.min_actual_length; c.min_rest_length = plain.min_rest_length;
     m_cable = world.addContactCable(c);
 }
 tgModel* tgBasicContactCableInfo::createModel(tgWorldB200Impl& world) {

@@ -302,8 +302,28 @@ btQuaternion tgWorldB200Impl::bodyOrientation(int body, int env) {
 }
 void tgWorldB200Impl::setControlInput(int cable, double input, double dt) {
     if (input < 0.0) throw std::invalid_argument("Rest length is negative.");
-    if (cable >= kContactCableBase)
-        throw std::runtime_error("tgWorldB200Impl: control input on a contact cable is not supported (its actuator runs without control input)");
+    if (cable >= kContactCableBase) {
+        const int i = cable - kContactCableBase;
+        if (!m_handle) {
+            /* before the device exists: moveMotors on the flat descriptor; no sliding anchor yet */
+            tgb_contact_cable_desc& c = m_contactCables.at(i);
+            double preferred = input;
+            const double stepSize = c.target_velocity * dt, actual = cableLength(cable, 0);
+            if ((actual - preferred) * c.stiffness > c.max_tension) preferred = actual - c.max_tension / c.stiffness;
+            const double diff = preferred - c.rest_length;
+            if (actual > c.min_actual_length || diff > 0) {
+                if (std::fabs(diff) > stepSize) c.rest_length += (diff / std::fabs(diff)) * stepSize;
+                else c.rest_length += diff;
+            }
+            c.rest_length = c.rest_length > c.min_rest_length ? c.rest_length : c.min_rest_length;
+            return;
+        }
+        std::vector<double> in(m_contactCables.size(), std::nan(""));
+        in.at(i) = input;
+        check(tgb_set_contact_cable_control_input(m_handle, 0, m_nEnv, in.data(), 1, dt));
+        m_cacheValid = false;
+        return;
+    }
     if (!m_handle) {
         /* before the device exists: tgBasicActuator::moveMotors on the flat descriptor (tgBasicActuator.cpp:170-225) */
         tgb_cable_desc& c = m_cables.at(cable);

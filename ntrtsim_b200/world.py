@@ -132,6 +132,17 @@ class BatchedWorld(object):
         capi.check(self._lib.tgb_get_contact_cable_obs(self._h, env_begin, n, _ptr(out)))
         return out
 
+    def set_contact_cable_control_input(self, inputs, dt, env_begin=0, env_count=None):
+        """tgBasicActuator::setControlInput(input, dt) on the contact cables: [n_contact_cables] for every environment of the range, or
+        one row per environment"""
+        n = self.n_env - env_begin if env_count is None else env_count
+        inputs = np.ascontiguousarray(inputs, dtype=np.float64)
+        broadcast = inputs.ndim == 1
+        want = self.model.n_contact_cables * (1 if broadcast else n)
+        if inputs.size != want:
+            raise ValueError("contact cable control input has %d elements, expected %d" % (inputs.size, want))
+        capi.check(self._lib.tgb_set_contact_cable_control_input(self._h, env_begin, n, _ptr(inputs), 1 if broadcast else 0, float(dt)))
+
     def get_contact_cable_anchors(self, cable, env_begin=0, env_count=None):
         """[n, 6, 7]: body (-1 = unused slot), world position, contact normal of the cable's sliding anchors in order"""
         n = self.n_env - env_begin if env_count is None else env_count

@@ -51,6 +51,7 @@ def load():
     lib.tgo_get_cpg_state.argtypes = [vp, vp]
     lib.tgo_add_contact_cables.argtypes = [vp, vp, i]
     lib.tgo_set_batch_contact_cables.argtypes = [vp, i]
+    lib.tgo_set_contact_cable_control_input.argtypes = [vp, vp, dbl]
     lib.tgo_num_contact_cables.argtypes = [vp]
     lib.tgo_get_contact_cable_obs.argtypes = [vp, vp]
     lib.tgo_get_contact_cable_anchors.argtypes = [vp, i, vp]
@@ -86,6 +87,10 @@ class OracleWorld(object):
         out = np.zeros((self.n_cc, 5))
         self._lib.tgo_get_contact_cable_obs(self._h, _p(out))
         return out
+
+    def set_contact_cable_control_input(self, inputs, dt):
+        inputs = np.ascontiguousarray(inputs, dtype=np.float64)
+        return self._lib.tgo_set_contact_cable_control_input(self._h, _p(inputs), dt)
 
     def get_contact_cable_anchors(self, cable):
         out = np.zeros((6, 7))

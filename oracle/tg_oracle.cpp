@@ -164,6 +164,7 @@ struct ContactCable {
     int a, b;
     V3 la, lb;
     double k, c, rest, prev, velocity, damping, thickness, resolution;
+    double maxTens, tVel, minAL, minRL, preferred; /* the tgBasicActuator around it */
     std::vector<SlideAnchor> slides; /* between the two permanent anchors, in order */
 };
 /* one point of the "manifold" of (cable, body) */
@@ -432,6 +433,22 @@ struct tgo_world {
     double contactCableTension(const ContactCable& cc) const {
         const double t = (contactCableLength(cc) - cc.rest) * cc.k;
         return t < 0.0 ? 0.0 : t;
+    }
+    /* tgBasicActuator::setControlInput(input, dt) -> moveMotors (tgBasicActuator.cpp:149-225) on a contact cable */
+    int contactCableControlInput(ContactCable& c, double input, double dt) {
+        if (input < 0.0) return TGB_ERR_INVALID_ARGUMENT;
+        c.preferred = input;
+        const double stepSize = c.tVel * dt;
+        const double actual = contactCableLength(c);
+        if ((actual - c.preferred) * c.k > c.maxTens) c.preferred = actual - c.maxTens / c.k;
+        const double diff = c.preferred - c.rest;
+        const double fabsDiff = std::fabs(diff);
+        if ((actual > c.minAL) || (diff > 0)) {
+            if (std::fabs(diff) > stepSize) c.rest += (diff / fabsDiff) * stepSize;
+            else c.rest += diff;
+        }
+        c.rest = (c.rest > c.minRL) ? c.rest : c.minRL;
+        return 0;
     }
     /* the manifold point of `body` nearest to p: its distance to p (INFINITY when the body has none) and its normal */
     static double ccNearest(const std::vector<CablePoint>& pts, int body, const V3& p, V3& normal, V3& pos) {
@@ -1400,7 +1417,17 @@ int tgo_add_contact_cables(tgo_world* w, const tgb_contact_cable_desc* cables, i
         cc.lb = V3(d.local_b[0], d.local_b[1], d.local_b[2]);
         cc.k = d.stiffness; cc.c = d.damping; cc.rest = d.rest_length; cc.prev = d.prev_length;
         cc.velocity = 0; cc.damping = 0; cc.thickness = d.thickness; cc.resolution = d.resolution;
+        cc.maxTens = d.max_tension; cc.tVel = d.target_velocity; cc.minAL = d.min_actual_length; cc.minRL = d.min_rest_length;
+        cc.preferred = cc.rest; /* tgBasicActuator ctor */
         w->contactCables.push_back(cc);
+    }
+    return 0;
+}
+int tgo_set_contact_cable_control_input(tgo_world* w, const double* input, double dt) {
+    for (size_t i = 0; i < w->contactCables.size(); ++i) {
+        if (input[i] != input[i]) continue; /* NaN: leave alone */
+        const int rc = w->contactCableControlInput(w->contactCables[i], input[i], dt);
+        if (rc != 0) return rc;
     }
     return 0;
 }

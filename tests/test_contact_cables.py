@@ -153,10 +153,79 @@ def test_a_contact_cable_that_touches_nothing_is_a_plain_cable():
         assert np.allclose(wa.get_contact_cable_obs()[0, :3], wb.get_cable_obs()[0, :3], rtol=0, atol=1e-12)
 
 
+def total_mechanical_energy(model, st, obs, k):
+    """translation + rotation of the rigids + the cable's spring energy 1/2 k stretch^2 over its whole path"""
+    from helpers import quat_rotate
+    inertia = np.array([list(b.inertia) for b in model.bodies])
+    ke = 0.5 * (masses(model) * (st[:, 7:10] ** 2).sum(axis=1)).sum()
+    w_body = quat_rotate(st[:, 3:7] * np.array([-1.0, -1.0, -1.0, 1.0]), st[:, 10:13])
+    kr = 0.5 * (inertia * w_body ** 2).sum()
+    stretch = max(0.0, obs[0, 1] - obs[0, 0])
+    return ke + kr + 0.5 * k * stretch * stretch
+
+
+def test_a_cable_sliding_around_a_body_does_no_work():
+    """Sliding anchors are frictionless and the cable has no damping here: the anchor forces T (unit(forward) + unit(back)) push
+    along the bisector of the bend, and what the cable takes from the bodies' motion it holds as stretch.  Through the whole
+    encounter -- anchors created, slid, removed -- the mechanical energy of bodies + cable stays within a few percent (the residue
+    is the path-length jump of an insertion, capped at 2 x resolution), for every member of an ensemble of launches."""
+    m = demo_model()
+    states = demo_states(m, 16, seed=5)
+    ratios = []
+    for e in range(16):
+        w = oracle_py.OracleWorld(m, capi.WorldCfg)
+        w.set_rod_state(states[e])
+        e0 = total_mechanical_energy(m, w.get_rod_state(), w.get_contact_cable_obs(), 1000.0)
+        n_max = 0
+        for _ in range(100):
+            w.step(DT, 100)
+            n_max = max(n_max, int(w.get_contact_cable_obs()[0, 4]))
+        assert n_max >= 2
+        ratios.append(total_mechanical_energy(m, w.get_rod_state(), w.get_contact_cable_obs(), 1000.0) / e0)
+    ratios = np.array(ratios)
+    assert np.abs(ratios - 1.0).max() < 0.05, ratios      # measured: worst +3.3 %
+    assert abs(np.median(ratios) - 1.0) < 0.005           # measured: median +0.15 %
+
+
+def test_control_input_on_a_contact_cable_is_the_basic_actuators():
+    """tgBasicContactCableInfo::createModel wraps the contact cable in a tgBasicActuator: setControlInput(input, dt) -> moveMotors uses the
+    cable's actual length (tgBasicActuator.cpp:149-225).  While the cable touches nothing that is a plain tgBasicActuator cable."""
+    m = demo_model()
+    cc = m.contact_cables[0]
+    assert (cc.max_tension, cc.target_velocity, cc.min_actual_length, cc.min_rest_length) == (600000000.0, 100.0, 0.1, 0.1)
+    cc.target_velocity = 2.0
+    plain = (capi.CableDesc * 1)()
+    p = plain[0]
+    p.body_a, p.body_b = cc.body_a, cc.body_b
+    for k in range(3):
+        p.local_a[k], p.local_b[k] = cc.local_a[k], cc.local_b[k]
+    p.stiffness, p.damping, p.rest_length, p.prev_length = cc.stiffness, cc.damping, cc.rest_length, cc.prev_length
+    p.actuator = capi.TGB_ACT_BASIC
+    p.max_tension, p.target_velocity, p.min_actual_length, p.min_rest_length = cc.max_tension, cc.target_velocity, 0.1, 0.1
+    p.motor_radius, p.motor_inertia = 1.0, 1.0
+    m_plain = FlatModel(m.bodies, m.shapes, plain, m.ground, m.gravity, m.dt, "plain")
+    wa, wb = oracle_py.OracleWorld(m, capi.WorldCfg), oracle_py.OracleWorld(m_plain, capi.WorldCfg)
+    s = demo_states(m, 1)[0]
+    s[:, 7:10] *= 0.1
+    wa.set_rod_state(s)
+    wb.set_rod_state(s)
+    for i in range(200):
+        target = 7.8 if i < 150 else 8.1      # reel in at 2 units / s (reached after 100 steps), then pay out for 50
+        assert wa.set_contact_cable_control_input(np.array([target]), DT) == 0
+        assert wb.set_control_input(np.array([target]), DT) == 0
+        wa.step(DT, 1)
+        wb.step(DT, 1)
+    assert int(wa.get_contact_cable_obs()[0, 4]) == 0
+    assert np.array_equal(wa.get_rod_state(), wb.get_rod_state())
+    assert np.allclose(wa.get_contact_cable_obs()[0, :3], wb.get_cable_obs()[0, :3], rtol=0, atol=1e-12)
+    assert abs(wa.get_contact_cable_obs()[0, 0] - 8.0) > 0.05   # the rest length did move
+    assert wa.set_contact_cable_control_input(np.array([-1.0]), DT) != 0   # "Rest length is negative."
+
+
 def test_contact_cable_descriptor_checks():
     m = demo_model()
     lib = oracle_py.load()
-    for field, bad in (("stiffness", 0.0), ("damping", -1.0), ("resolution", 0.0), ("thickness", -1.0), ("body_b", 7)):
+    for field, bad in (("stiffness", 0.0), ("damping", -1.0), ("resolution", 0.0), ("thickness", -1.0), ("body_b", 7)):  # the oracle's checks
         mm = demo_model()
         setattr(mm.contact_cables[0], field, bad)
         with pytest.raises(ValueError):
@@ -284,6 +353,40 @@ def test_contact_cable_demo_f32_conserves_momentum_and_follows_the_oracle():
         assert e[0] < 1e-4 and e[1] < 1e-4 and e[2] < 1e-3 and e[3] < 1e-3   # velocities reach ~10 and ~1 here
         assert (np.abs(od[..., 2] - oo[..., 2]) / np.maximum(oo[..., 2], 100.0)).max() < 1e-3
         assert np.array_equal(od[..., 4], oo[..., 4])
+
+
+@pytest.mark.gpu
+def test_contact_cable_control_input_on_the_device_matches_the_oracle():
+    """A host-side controller reeling the contact cable in while it bends around the rod: tgb_set_contact_cable_control_input every
+    step for 1500 steps (f64), against the oracle."""
+    m = demo_model()
+    states = demo_states(m, 8, seed=11)
+    states[:, :2, 7:10] *= 4.0
+    w = nt.BatchedWorld(m, 8, precision="f64")
+    worlds = [oracle_py.OracleWorld(m, capi.WorldCfg) for _ in range(8)]
+    try:
+        w.set_rod_state(states)
+        for o, s in zip(worlds, states):
+            o.set_rod_state(s)
+        for i in range(1500):
+            target = np.array([8.0 - 0.0005 * i])
+            w.set_contact_cable_control_input(target, DT)
+            w.step(DT, 1)
+            for o in worlds:
+                assert o.set_contact_cable_control_input(target, DT) == 0
+                o.step(DT, 1)
+        w.sync()
+        rd, od = w.get_rod_state(), w.get_contact_cable_obs()
+        ro = np.stack([o.get_rod_state() for o in worlds])
+        oo = np.stack([o.get_contact_cable_obs() for o in worlds])
+        assert (oo[..., 4] > 0).any()
+        assert np.array_equal(od[..., 4], oo[..., 4])
+        assert np.abs(od[..., 0] - oo[..., 0]).max() < 1e-9 and abs(oo[0, 0, 0] - 8.0) > 0.5
+        assert max(rod_errors(rd, ro, 10.0)) < 1e-6
+        with pytest.raises(capi.TgbError):
+            w.set_contact_cable_control_input(np.array([-1.0]), DT)
+    finally:
+        w.close()
 
 
 @pytest.mark.gpu
