@@ -269,6 +269,78 @@ builders:
     assert abs(c.rest_length - (8.0 - 100.0 / 500.0)) < 1e-9
 
 
+PRISM_WITH_CONTACT_CABLES = """
+nodes:
+  bottom1: [-5, 0, 0]
+  bottom2: [5, 0, 0]
+  bottom3: [0, 0, 8.66]
+  top1: [-5, 5, 0]
+  top2: [5, 5, 0]
+  top3: [0, 5, 8.66]
+pair_groups:
+  prism_rod:
+    - [bottom1, top2]
+    - [bottom2, top3]
+    - [bottom3, top1]
+  horizontal_string:
+    - [bottom1, bottom2]
+    - [bottom2, bottom3]
+    - [bottom1, bottom3]
+    - [top1, top2]
+    - [top2, top3]
+    - [top1, top3]
+  vertical_string:
+    - [bottom1, top1]
+    - [bottom2, top2]
+    - [bottom3, top3]
+builders:
+  prism_rod:
+    class: tgRodInfo
+    parameters:
+      density: 0.688
+      radius: 0.31
+  horizontal_string:
+    class: tgBasicActuatorInfo
+    parameters:
+      stiffness: 1000
+      damping: 10
+      pretension: 3000
+  vertical_string:
+    class: tgBasicContactCableInfo
+    parameters:
+      stiffness: 1000
+      damping: 10
+      pretension: 1000
+"""
+
+
+def prism_with_contact_cables(tmp_path):
+    """resources/YamlStructures/BaseStructures/3Prism.yaml with its three vertical strings built as contact cables: two-anchor cables,
+    contact cables, gravity, the ground and contact between the rods in one world."""
+    path = os.path.join(str(tmp_path), "3PrismContact.yaml")
+    open(path, "w").write(PRISM_WITH_CONTACT_CABLES)
+    return nt.examples.build_yaml(path)
+
+
+def test_contact_cables_beside_plain_cables_in_one_model(tmp_path):
+    m = prism_with_contact_cables(tmp_path)
+    assert (m.n_bodies, m.n_cables, m.n_contact_cables) == (3, 6, 3)
+    w = oracle_py.OracleWorld(m, capi.WorldCfg)
+    s = m.initial_rod_state()
+    s[:, 1] += 3.0
+    w.set_rod_state(s)
+    seen = 0
+    for _ in range(60):
+        assert w.step(DT, 10) == 0
+        o = w.get_contact_cable_obs()
+        assert np.all(np.isfinite(w.get_rod_state())) and np.all(o[:, 2] >= 0.0)
+        seen = max(seen, int(o[:, 4].max()))
+    # it fell onto the ground and stays above it, in one piece
+    y = w.get_rod_state()[:, 1]
+    assert y.max() < 5.4 and y.min() > 0.3 and np.abs(w.get_rod_state()[:, 7:13]).max() < 50.0
+    print("most sliding anchors on a cable:", seen)
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _device_run(model, states, precision, steps, chunk):
     w = nt.BatchedWorld(model, states.shape[0], precision=precision)
@@ -385,6 +457,49 @@ def test_contact_cable_control_input_on_the_device_matches_the_oracle():
         assert max(rod_errors(rd, ro, 10.0)) < 1e-6
         with pytest.raises(capi.TgbError):
             w.set_contact_cable_control_input(np.array([-1.0]), DT)
+    finally:
+        w.close()
+
+
+@pytest.mark.gpu
+def test_prism_with_contact_cables_f64_matches_the_oracle(tmp_path):
+    """plain cables + contact cables + gravity + ground + rod-rod contact in one world, 16 random poses, 400 steps"""
+    from helpers import random_poses
+    m = prism_with_contact_cables(tmp_path)
+    states = random_poses(m, 16, seed=21, translate=1.0, lift=(3.0, 6.0))
+    w = nt.BatchedWorld(m, 16, precision="f64")
+    worlds = [oracle_py.OracleWorld(m, capi.WorldCfg) for _ in range(16)]
+    pert = [oracle_py.OracleWorld(m, capi.WorldCfg) for _ in range(16)]
+    try:
+        w.set_rod_state(states)
+        noise = 1e-13 * np.random.default_rng(1).normal(size=states[:, :, 0:3].shape)
+        for o, p, s, dn in zip(worlds, pert, states, noise):
+            o.set_rod_state(s)
+            s2 = s.copy()
+            s2[:, 0:3] += dn
+            p.set_rod_state(s2)
+        anchors, compared = 0, 0
+        for _ in range(16):
+            w.step(DT, 25)
+            w.sync()
+            for o, p in zip(worlds, pert):
+                o.step(DT, 25)
+                p.step(DT, 25)
+            rd, cd, od = w.get_rod_state(), w.get_cable_obs(), w.get_contact_cable_obs()
+            ro = np.stack([o.get_rod_state() for o in worlds])
+            rp = np.stack([o.get_rod_state() for o in pert])
+            co = np.stack([o.get_cable_obs() for o in worlds])
+            oo = np.stack([o.get_contact_cable_obs() for o in worlds])
+            tol = max(1e-9, 20.0 * max(rod_errors(rp, ro, 10.0)))
+            if tol > 1e-5:
+                break   # landing on the ground with rods and cables touching amplifies a 1e-13 perturbation beyond use from here on
+            compared += 1
+            assert max(rod_errors(rd, ro, 10.0)) < tol
+            assert np.abs(cd[..., :2] - co[..., :2]).max() < tol and np.abs(od[..., :2] - oo[..., :2]).max() < tol
+            assert (od[..., 4] != oo[..., 4]).sum() <= (1 if tol > 1e-7 else 0)
+            anchors = max(anchors, int(oo[..., 4].max()))
+        print("checkpoints compared:", compared, "most sliding anchors on a cable:", anchors)
+        assert compared >= 4
     finally:
         w.close()
 
