@@ -98,8 +98,12 @@ struct tgb_world {
        environments in flight (slot 0: the whole world on `stream`; slot 1 + k: chunk k of tgb_rollout_host) the two lists of a launch */
     enum { kSplitSlots = 5 };
     int* d_coupled = nullptr;       /* [n_env] */
-    int* d_split_count = nullptr;   /* [kSplitSlots][2]: slow candidates, fast environments */
+    int* d_split_count = nullptr;   /* [kSplitSlots][4]: slow candidates, fast environments, medium candidates, spare */
     int* d_split_slow = nullptr;    /* [kSplitSlots][splitSlowCap] */
+    int* d_split_medium = nullptr;  /* [kSplitSlots][splitMediumCap]: environments run two to a warp (16 lanes each) */
+    int splitMediumCap = 0;
+    cudaStream_t splitStream2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t splitJoin2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int* d_split_fast = nullptr;    /* [n_env]: a range's fast list sits at its env_begin */
     int splitSlowCap = 0, splitMode = -1 /* -1 automatic, 0 off, 1 forced (tests) */, coupledLaunchSteps = 0;
     cudaStream_t splitStream[kSplitSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -164,6 +168,11 @@ struct tgb_world {
         if (d_coupled) cudaFree(d_coupled);
         if (d_split_count) cudaFree(d_split_count);
         if (d_split_slow) cudaFree(d_split_slow);
+        if (d_split_medium) cudaFree(d_split_medium);
+        for (int i = 0; i < 5; ++i) {
+            if (splitJoin2[i]) cudaEventDestroy(splitJoin2[i]);
+            if (splitStream2[i]) cudaStreamDestroy(splitStream2[i]);
+        }
         if (d_split_fast) cudaFree(d_split_fast);
         for (int i = 0; i < kSplitSlots; ++i) {
             if (splitStream[i]) cudaStreamDestroy(splitStream[i]);
@@ -379,10 +388,12 @@ bool wideLayout(const tgb_world* w) {
 }
 
 /* thresholds of the tail split's classification (environment variables: tuning aids) */
-struct SplitTuning { int totalDiv, recentThreshold; };
+struct SplitTuning { int totalDiv, recentThreshold, mediumDiv, mediumCap; };
 const SplitTuning& splitTuning() {
     static const SplitTuning t = [] {
-        SplitTuning v = {8, 8};
+        SplitTuning v = {8, 8, 64, 0}; /* the middle class is off: measured below */
+        if (const char* e = std::getenv("TGB_SPLIT_MEDIUM_DIV")) v.mediumDiv = std::max(1, std::atoi(e));
+        if (const char* e = std::getenv("TGB_SPLIT_MEDIUM_CAP")) v.mediumCap = std::max(0, std::atoi(e));
         if (const char* e = std::getenv("TGB_SPLIT_TOTAL_DIV")) v.totalDiv = std::max(1, std::atoi(e));
         if (const char* e = std::getenv("TGB_SPLIT_RECENT_THR")) v.recentThreshold = std::max(1, std::atoi(e));
         return v;
@@ -442,14 +453,21 @@ tgb_step_args stepArgs(const tgb_world* w, double dt, int nSteps) {
    else runs in the usual layout.  Both kernels take their environments from lists a small kernel writes (tgb_step_args.env_list).
    Results do not depend on which lanes simulate an environment (tested bit for bit), so the split changes durations only. */
 __global__ void tgb_classify_envs_kernel(const int* coupled, int envBegin, int envCount, int threshold, int recentThreshold, int slowCap, int* count,
-                                         int* slow, int* fast) {
+                                         int* slow, int* fast, int mediumThreshold, int mediumCap, int* medium) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= envCount) return;
     const int env = envBegin + i;
     const int total = coupled[env] & 0xfffff, recent = coupled[env] >> 20;
+    bool heavy = false;
     if (total >= threshold || recent >= recentThreshold) {
         const int k = atomicAdd(count, 1);
         if (k < slowCap) { slow[k] = env; return; }
+        heavy = true;
+    }
+    /* the middle class: heavy for a smaller part of the last launch (or one too many for the first list): two to a warp */
+    if (mediumCap > 0 && (heavy || total >= mediumThreshold)) {
+        const int k = atomicAdd(count + 2, 1);
+        if (k < mediumCap) { medium[k] = env; return; }
     }
     fast[atomicAdd(count + 1, 1)] = env;
 }
@@ -473,8 +491,22 @@ tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount
         TGB_CUDA(cudaEventCreateWithFlags(&w->splitFork[slot], cudaEventDisableTiming));
         TGB_CUDA(cudaEventCreateWithFlags(&w->splitJoin[slot], cudaEventDisableTiming));
     }
-    int* count = w->d_split_count + 2 * slot;
+    int* count = w->d_split_count + 4 * slot;
     int* slow = w->d_split_slow + (size_t)slot * w->splitSlowCap;
+    int* medium = w->d_split_medium + (size_t)slot * w->splitMediumCap;
+    /* the middle class needs 16-lane groups to be narrower than a warp's worth of the usual layout and room for its extra warps */
+    /* Measured on B200 (bench workload, same box, TGB_SPLIT_MEDIUM_CAP / _DIV): off 6.57 ms per 1000 steps; cap 32 / 64 / 128 / 192 / 296
+       give 7.27 / 6.99 / 7.75 / 8.48 / 8.98 -- a warp of two 16-lane environments takes longer than the usual layout's slowest warp (the
+       usual-layout kernel beside it 7.8 - 8.7 ms instead of 6.5), so the class stays off; the forced mode of the tests keeps it alive. */
+    const int mediumCap = w->splitMode == 1 ? std::min(w->splitMediumCap, std::max(16, splitTuning().mediumCap))
+                                            : ((w->lanes <= 8 && envCount >= 1024) ? std::min(w->splitMediumCap, splitTuning().mediumCap) : 0);
+    const int mediumThreshold = w->splitMode == 1 ? 1 : std::max(1, lastSteps / splitTuning().mediumDiv);
+    if (mediumCap > 0 && !w->splitStream2[slot]) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        TGB_CUDA(cudaStreamCreateWithPriority(&w->splitStream2[slot], cudaStreamNonBlocking, hi));
+        TGB_CUDA(cudaEventCreateWithFlags(&w->splitJoin2[slot], cudaEventDisableTiming));
+    }
     int* fast = w->d_split_fast + envBegin;
     const int slowCap = w->splitMode == 1 ? std::min(w->splitSlowCap, envCount) : std::min(w->splitSlowCap, std::max(1, envCount / 20));
     const int threshold = w->splitMode == 1 ? 1 : std::max(1, lastSteps / splitTuning().totalDiv);
@@ -482,17 +514,18 @@ tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount
        launch after launch one warp of the usual layout held an environment that was coupled for 840 - 1000 of the 1000 steps and had
        been for fewer than 125 of the launch before) */
     const int recentThreshold = w->splitMode == 1 ? 1 : std::max(1, std::min(lastSteps, splitTuning().recentThreshold));
-    TGB_CUDA(cudaMemsetAsync(count, 0, 2 * sizeof(int), s));
-    tgb_classify_envs_kernel<<<(envCount + 255) / 256, 256, 0, s>>>(w->d_coupled, envBegin, envCount, threshold, recentThreshold, slowCap, count, slow, fast);
+    TGB_CUDA(cudaMemsetAsync(count, 0, 4 * sizeof(int), s));
+    tgb_classify_envs_kernel<<<(envCount + 255) / 256, 256, 0, s>>>(w->d_coupled, envBegin, envCount, threshold, recentThreshold, slowCap, count, slow, fast,
+                                                                    mediumThreshold, mediumCap, medium);
     TGB_CUDA(cudaGetLastError());
     {
         static const char* dbg = std::getenv("TGB_SPLIT_DEBUG"); /* tuning aid: synchronises */
         if (dbg) {
-            int h[2] = {0, 0};
+            int h[4] = {0, 0, 0, 0};
             cudaMemcpyAsync(h, count, sizeof(h), cudaMemcpyDeviceToHost, s);
             cudaStreamSynchronize(s);
-            std::fprintf(stderr, "tgb tail split: %d environments coupled for >= %d of the last %d steps (cap %d), %d in the usual layout\n", h[0],
-                         threshold, lastSteps, slowCap, h[1]);
+            std::fprintf(stderr, "tgb tail split: %d environments coupled for >= %d of the last %d steps (cap %d), %d two to a warp (>= %d, cap %d), %d in the usual layout\n", h[0],
+                         threshold, lastSteps, slowCap, h[2], mediumThreshold, mediumCap, h[1]);
         }
     }
     TGB_CUDA(cudaEventRecord(w->splitFork[slot], s));
@@ -506,6 +539,15 @@ tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount
     if (e != cudaSuccess) return cudaFail(e, "step kernel launch (coupled environments)");
     if (dbgT) cudaEventRecord(dbgEv[1], w->splitStream[slot]);
     TGB_CUDA(cudaEventRecord(w->splitJoin[slot], w->splitStream[slot]));
+    if (mediumCap > 0) {
+        TGB_CUDA(cudaStreamWaitEvent(w->splitStream2[slot], w->splitFork[slot], 0));
+        tgb_step_args am = a;
+        am.env_list = medium; am.env_list_count = count + 2; am.env_list_slots = mediumCap;
+        e = w->ops->step(am, 16, 32, w->splitStream2[slot]);
+        if (e != cudaSuccess) return cudaFail(e, "step kernel launch (two environments to a warp)");
+        TGB_CUDA(cudaEventRecord(w->splitJoin2[slot], w->splitStream2[slot]));
+        w->launches += 1;
+    }
     tgb_step_args af = a;
     af.env_list = fast; af.env_list_count = count + 1; af.env_list_slots = envCount;
     if (dbgT) cudaEventRecord(dbgEv[2], s);
@@ -513,6 +555,7 @@ tgb_status launchSplit(tgb_world* w, tgb_step_args a, int envBegin, int envCount
     if (e != cudaSuccess) return cudaFail(e, "step kernel launch");
     if (dbgT) cudaEventRecord(dbgEv[3], s);
     TGB_CUDA(cudaStreamWaitEvent(s, w->splitJoin[slot], 0));
+    if (mediumCap > 0) TGB_CUDA(cudaStreamWaitEvent(s, w->splitJoin2[slot], 0));
     if (dbgT) {
         cudaStreamSynchronize(s);
         float ts = 0, tf = 0;
@@ -969,7 +1012,9 @@ tgb_status tgb_finalize(tgb_world* w) {
         w->splitSlowCap = std::max(16, std::min(n, w->smCount / 2));
         TGB_CUDA(cudaMalloc(&w->d_coupled, (size_t)n * sizeof(int)));
         TGB_CUDA(cudaMemset(w->d_coupled, 0, (size_t)n * sizeof(int)));
-        TGB_CUDA(cudaMalloc(&w->d_split_count, 2 * tgb_world::kSplitSlots * sizeof(int)));
+        w->splitMediumCap = std::max(16, std::min(n, 2 * w->smCount));
+        TGB_CUDA(cudaMalloc(&w->d_split_medium, (size_t)tgb_world::kSplitSlots * w->splitMediumCap * sizeof(int)));
+        TGB_CUDA(cudaMalloc(&w->d_split_count, 4 * tgb_world::kSplitSlots * sizeof(int)));
         TGB_CUDA(cudaMalloc(&w->d_split_slow, (size_t)tgb_world::kSplitSlots * w->splitSlowCap * sizeof(int)));
         TGB_CUDA(cudaMalloc(&w->d_split_fast, (size_t)n * sizeof(int)));
     }
