@@ -398,6 +398,10 @@ tgb_status tgb_get_contact_cable_obs(tgb_world* w, int32_t env_begin, int32_t en
 /* the sliding anchors of one contact cable, in order from anchor 1 to anchor 2: out[env_count][TGB_CCABLE_MAX_SLIDING][7], unused
    slots zero with body index -1 (tgSpringCable::getAnchors without the two permanent ends) */
 tgb_status tgb_get_contact_cable_anchors(tgb_world* w, int32_t cable, int32_t env_begin, int32_t env_count, double* out);
+/* Start the contact cables of the environments in the range afresh, as tgBasicContactCableInfo builds them: rest length and previous
+   length from rest_prev [env_count][n_contact_cables][2] (NULL: the descriptors' own), preferred length = rest length, velocity 0, no
+   sliding anchors -- the counterpart of tgb_set_cable_state for a new episode from tgb_set_rod_state. */
+tgb_status tgb_reset_contact_cables(tgb_world* w, int32_t env_begin, int32_t env_count, const double* rest_prev);
 /* tgBasicActuator::setControlInput(input, dt) (src/core/tgBasicActuator.cpp:149-168) on the contact cables of every environment in the
    range, once, now: preferred length = input, then moveMotors(dt) (:170-225) with the cable's actual length over all its anchors.
    input: [n_contact_cables] (broadcast != 0) or [env_count][n_contact_cables]; negative -> TGB_ERR_INVALID_ARGUMENT, NaN = leave alone. */

@@ -84,7 +84,7 @@ ABI_SYMBOLS = [
     "tgb_set_block_threads", "tgb_set_wide_layout", "tgb_state_bytes_per_env", "tgb_set_height_window", "tgb_stream_handle",
     "tgb_set_pair_contact_cap", "tgb_get_min_clearance", "tgb_set_warm_starting", "tgb_set_tail_split",
     "tgb_add_contact_cables", "tgb_num_contact_cables", "tgb_get_contact_cable_obs", "tgb_get_contact_cable_anchors",
-    "tgb_set_contact_cable_control_input",
+    "tgb_set_contact_cable_control_input", "tgb_reset_contact_cables",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -160,6 +160,7 @@ def load():
     lib.tgb_get_contact_cable_obs.argtypes = [_vp, _i32, _i32, _vp]
     lib.tgb_get_contact_cable_anchors.argtypes = [_vp, _i32, _i32, _i32, _vp]
     lib.tgb_set_contact_cable_control_input.argtypes = [_vp, _i32, _i32, _vp, _i32, C.c_double]
+    lib.tgb_reset_contact_cables.argtypes = [_vp, _i32, _i32, _vp]
     for name in ABI_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("tgb_abi_version", "tgb_last_error", "tgb_device_count"):

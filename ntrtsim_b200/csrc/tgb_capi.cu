@@ -1155,6 +1155,25 @@ tgb_status tgb_get_contact_cable_obs(tgb_world* w, int32_t env_begin, int32_t en
     return TGB_OK;
 }
 
+tgb_status tgb_reset_contact_cables(tgb_world* w, int32_t env_begin, int32_t env_count, const double* rest_prev) {
+    TGB_NEED_FINAL(w);
+    if (!rangeOk(w, env_begin, env_count)) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_reset_contact_cables: bad range");
+    const size_t ncc = w->contactCables.size();
+    if (ncc == 0 || env_count == 0) return TGB_OK;
+    std::vector<double> all((size_t)env_count * ncc * tgb::TGB_CC_STATE, 0.0);
+    for (int e = 0; e < env_count; ++e)
+        for (size_t i = 0; i < ncc; ++i) {
+            double* cs = &all[((size_t)e * ncc + i) * tgb::TGB_CC_STATE];
+            const double rest = rest_prev ? rest_prev[((size_t)e * ncc + i) * 2] : w->contactCables[i].rest_length;
+            const double prev = rest_prev ? rest_prev[((size_t)e * ncc + i) * 2 + 1] : w->contactCables[i].prev_length;
+            if (rest < 0.0 || prev < 0.0) return fail(TGB_ERR_INVALID_ARGUMENT, "tgb_reset_contact_cables: lengths must not be negative");
+            cs[tgb::CCS_REST] = rest; cs[tgb::CCS_PREV] = prev; cs[tgb::CCS_PREF] = rest;
+        }
+    TGB_CUDA(cudaStreamSynchronize(w->stream));
+    TGB_CUDA(cudaMemcpy(w->d_cc_state + (size_t)env_begin * ncc * tgb::TGB_CC_STATE, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return TGB_OK;
+}
+
 tgb_status tgb_set_contact_cable_control_input(tgb_world* w, int32_t env_begin, int32_t env_count, const double* input, int32_t broadcast,
                                                double dt) {
     TGB_NEED_FINAL(w);

@@ -143,6 +143,13 @@ class BatchedWorld(object):
             raise ValueError("contact cable control input has %d elements, expected %d" % (inputs.size, want))
         capi.check(self._lib.tgb_set_contact_cable_control_input(self._h, env_begin, n, _ptr(inputs), 1 if broadcast else 0, float(dt)))
 
+    def reset_contact_cables(self, rest_prev=None, env_begin=0, env_count=None):
+        """a new episode for the contact cables: rest / previous lengths ([n, n_contact_cables, 2], default the model's), no anchors"""
+        n = self.n_env - env_begin if env_count is None else env_count
+        if rest_prev is not None:
+            rest_prev = _host_buffer(rest_prev, (n, self.model.n_contact_cables, 2), "rest_prev")
+        capi.check(self._lib.tgb_reset_contact_cables(self._h, env_begin, n, _ptr(rest_prev) if rest_prev is not None else None))
+
     def get_contact_cable_anchors(self, cable, env_begin=0, env_count=None):
         """[n, 6, 7]: body (-1 = unused slot), world position, contact normal of the cable's sliding anchors in order"""
         n = self.n_env - env_begin if env_count is None else env_count

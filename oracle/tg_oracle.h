@@ -19,6 +19,11 @@
  *                         src/examples/learningSpines/{BaseSpineCPGControl,tgCPGActuatorControl,tgCPGCableControl}.cpp,
  *                         src/util/{CPGEquations,CPGNode}.cpp (Boost.Odeint integrate() restated in tg_odeint.h),
  *                         src/examples/IROS_2015/TetraSpineStatic/SerializedSpineControl.cpp:174-205,262-371
+ *   contact cables        src/core/tgBulletContactSpringCable.cpp:97-190 (step, calculateAndApplyForce, updateManifolds, updateAnchorList,
+ *                         pruneAnchors, updateAnchorPositions), src/core/tgBulletSpringCableAnchor.cpp:89-334 (sliding anchors) -- the cable
+ *                         logic restated as written; Bullet's ghost object and persistent manifolds behind it restated geometrically
+ *                         (include/ntrtsim_b200.h "Contact cables"): parity unpinned against Bullet, pinned by the reference suite's
+ *                         MuscleNP_test (momentum, energy) and by mechanics (the mechanical energy of bodies + cable through an encounter)
  *   world step            Bullet 2.82 btDiscreteDynamicsWorld::stepSimulation(dt,1,dt) as reached from
  *                         src/core/tgWorldBulletPhysicsImpl.cpp:209-221 -- Bullet itself is NOT in the
  *                         reference tree (conf/default/bullet.conf.default:34,44); its semantics are

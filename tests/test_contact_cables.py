@@ -527,6 +527,13 @@ def test_contact_cable_world_steps_through_the_halves_and_rollout_host():
         assert (a.get_contact_cable_obs()[..., 4] > 0).any()
         rods_out, _ = c.rollout_host(states, np.zeros((8, 0, 2)), DT, 1200)
         assert np.array_equal(rods_out, a.get_rod_state())
+        # a new episode on the same world: bodies back, cables afresh (no anchors, previous length = rest) -> the same trajectory
+        a.set_rod_state(states)
+        a.reset_contact_cables()
+        assert (a.get_contact_cable_obs()[..., 4] == 0).all()
+        a.step(DT, 1200)
+        a.sync()
+        assert np.array_equal(a.get_rod_state(), rods_out)
     finally:
         a.close()
         b.close()
