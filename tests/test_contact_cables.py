@@ -538,3 +538,38 @@ def test_contact_cable_world_steps_through_the_halves_and_rollout_host():
         a.close()
         b.close()
         c.close()
+
+
+@pytest.mark.gpu
+def test_host_api_drop_in_runs_a_contact_cable_model_on_the_device(tmp_path):
+    """tgSimulation::run of ContactCableDemo through the host mirror (tgWorldB200Impl finalises with the contact cables; the
+    tgBasicActuator of the cable reads its length and tension through the contact-cable observations), and the tgDataLogger2 line of
+    the same run."""
+    h = capi.load_host()
+    m = demo_model()
+    n_env, steps = 3, 60
+    rod = np.empty((n_env, m.n_bodies, 13))
+    cab = np.empty((n_env, max(1, m.n_cables), 4))
+    for fn in (h.tgh_run_example, h.tgh_run_example_stepwise):
+        rc = fn(b"ContactCableDemo", n_env, capi.TGB_F64, steps, rod.ctypes.data_as(C.c_void_p), cab.ctypes.data_as(C.c_void_p))
+        assert rc == 0, h.tgh_last_error()
+        w = nt.BatchedWorld(m, n_env, precision="f64")
+        try:
+            w.step(DT, steps)
+            w.sync()
+            assert np.array_equal(w.get_rod_state(), rod)
+        finally:
+            w.close()
+    buf = C.create_string_buffer(512)
+    rc = h.tgh_run_example_logged(b"ContactCableDemo", n_env, capi.TGB_F64, 20, str(tmp_path / "cc").encode(), 0.0, 1, buf, 512)
+    assert rc == 0, h.tgh_last_error()
+    lines = [ln for ln in open(buf.value.decode()).read().split("\n") if ln]
+    assert len(lines) == 2 + 20
+    header = lines[1].split(",")
+    cols = [i for i, c in enumerate(header) if "RestLen" in c or "CurrLen" in c or "Tension" in c]
+    assert len(cols) >= 3, header
+    last = lines[-1].split(",")
+    vals = {header[i]: float(last[i]) for i in cols}
+    rest = [v for k, v in vals.items() if "RestLen" in k][0]
+    curr = [v for k, v in vals.items() if "CurrLen" in k][0]
+    assert abs(rest - 8.0) < 1e-9 and abs(curr - 8.0) < 1e-6
