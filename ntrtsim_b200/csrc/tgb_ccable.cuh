@@ -40,7 +40,7 @@ struct tgb_ccable_args {
 
 typedef V3<double> D3;
 
-struct CcAnchor { int body; D3 local, normal; };
+struct CcAnchor { int body; D3 local, normal; }; /* normal: in the body frame (USE_BASIS), turned into the world frame on use */
 struct CcPoint { int body; D3 pos, normal; double dist; };
 
 /* the environment's record seen in double.  Bodies do not move during a cable's step (only velocities change), so their poses are
@@ -66,6 +66,12 @@ struct CcEnv {
     __device__ const M3<double>& basis(int b) const { return cbasis[b]; }
     __device__ D3 world(int b, const D3& local) const { return cbasis[b] * local + cpos[b]; }
     __device__ D3 local(int b, const D3& w) const { return cbasis[b].tmul(w - cpos[b]); }
+    /* tgBulletSpringCableAnchor::getContactNormal (:202-214, USE_BASIS): the anchor's body-frame normal in the world frame, normalised */
+    __device__ D3 worldNormal(int b, const D3& nl) const {
+        const D3 n = cbasis[b] * nl;
+        const double l = n.length();
+        return l > 0.0 ? n / l : D3(0.0, 0.0, 0.0);
+    }
     __device__ double bodyField(int f, int b) const { return (double)mt[f * R + b]; }
     __device__ double shapeField(int f, int s) const { return (double)mt[TGB_NBF * R + f * S + s]; }
     __device__ int bodyInt(int f, int b) const { return mi[f * R + b]; }
@@ -119,7 +125,7 @@ __device__ inline double ccNearest(const CcPoint* pts, int np, int body, const D
 /* tgBulletSpringCableAnchor::getManifoldDistance, :279-334 */
 template <typename T>
 __device__ double ccManifoldDistance(const CcEnv<T>& E, const CcPoint* pts, int np, const CcAnchor& q, int body, D3& normalOut) {
-    normalOut = q.normal;
+    normalOut = E.worldNormal(q.body, q.normal);
     if (q.body != body) return INFINITY;
     D3 n, pos;
     const double len = ccNearest(pts, np, body, E.world(q.body, q.local), n, pos);
@@ -132,7 +138,7 @@ __device__ bool ccUpdateManifold(const CcEnv<T>& E, const CcPoint* pts, int np, 
     if (q.body != body) return false;
     D3 nn;
     ccManifoldDistance(E, pts, np, q, body, nn);
-    return !((nn + q.normal).length() < 0.5);
+    return !((nn + E.worldNormal(q.body, q.normal)).length() < 0.5);
 }
 /* findNearestPastAnchor, :799-937, restated: the segment of the chain nearest to pos */
 __device__ inline int ccNearestSegment(const D3* P, int n, const D3& pos) {
@@ -152,11 +158,12 @@ __device__ inline int ccNearestSegment(const D3* P, int n, const D3& pos) {
 template <typename T>
 __device__ bool ccSetWorldPosition(const CcEnv<T>& E, const CcPoint* pts, int np, CcAnchor& q, const D3& newPos) {
     const D3 current = E.world(q.body, q.local);
-    D3 newNormal = q.normal, contactPos = current;
+    const D3 own = E.worldNormal(q.body, q.normal);
+    D3 newNormal = own, contactPos = current;
     const double length = ccNearest(pts, np, q.body, newPos, newNormal, contactPos);
     if (length < 0.1) {
         q.local = E.local(q.body, newPos);
-        return !((newNormal + q.normal).length() < 0.5);
+        return !((newNormal + own).length() < 0.5);
     }
     return (current - contactPos).length() <= 0.1;
 }
@@ -168,7 +175,7 @@ __device__ int ccUpdateAnchorPositions(const CcEnv<T>& E, const CcPoint* pts, in
     while (i < c.n) {
         const D3 back = P[i], current = P[i + 1], forward = P[i + 2];
         const D3 lineA = forward - current, lineB = back - current;
-        const D3 n = c.s[i].normal;
+        const D3 n = E.worldNormal(c.s[i].body, c.s[i].normal);
         D3 tangentMove(0.0, 0.0, 0.0);
         const D3 along = lineB - lineA;
         const double al = along.length();
@@ -285,8 +292,8 @@ __global__ void __launch_bounds__(32) ccable_step_kernel(tgb_ccable_args a) {
             if (lineA.dot(m.normal) < 0.0 || lineB.dot(m.normal) < 0.0) continue;
             const bool backSliding = j >= 1, fwdSliding = j + 1 <= c.n;
             const int backBody = backSliding ? c.s[j - 1].body : c.a, fwdBody = fwdSliding ? c.s[j].body : c.b;
-            if ((backSliding && m.body == backBody && c.s[j - 1].normal.dot(m.normal) < 0.0) ||
-                (fwdSliding && m.body == fwdBody && c.s[j].normal.dot(m.normal) < 0.0)) continue;
+            if ((backSliding && m.body == backBody && E.worldNormal(c.s[j - 1].body, c.s[j - 1].normal).dot(m.normal) < 0.0) ||
+                (fwdSliding && m.body == fwdBody && E.worldNormal(c.s[j].body, c.s[j].normal).dot(m.normal) < 0.0)) continue;
             const double lengthA = lineA.length(), lengthB = lineB.length();
             const bool nearBack = lengthB <= resolution && m.body == backBody && backSliding;
             const bool nearFwd = lengthA <= resolution && m.body == fwdBody && fwdSliding;
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(32) ccable_step_kernel(tgb_ccable_args a) {
                 if (del) continue;
             }
             for (int q = c.n; q > j; --q) c.s[q] = c.s[q - 1];
-            c.s[j].body = m.body; c.s[j].local = E.local(m.body, m.pos); c.s[j].normal = m.normal;
+            c.s[j].body = m.body; c.s[j].local = E.local(m.body, m.pos); c.s[j].normal = E.basis(m.body).tmul(m.normal); /* basis^-1 * cn */
             ++c.n;
             nP = ccChain(E, c, P);
             if (ccLength(P, nP) > prev + 2.0 * resolution) { ccErase(c, j); nP = ccChain(E, c, P); }
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(32) ccable_step_kernel(tgb_ccable_args a) {
                 int i = 0;
                 while (i < c.n) {
                     const D3 lineA = P[i + 2] - P[i + 1], lineB = P[i] - P[i + 1];
-                    const D3 n = c.s[i].normal;
+                    const D3 n = E.worldNormal(c.s[i].body, c.s[i].normal);
                     double nv1, nv2;
                     const double half = resolution / 2.0;
                     if (lineA.length2() < half * half || lineB.length2() < half * half) nv1 = nv2 = -1.0;
@@ -460,7 +467,8 @@ __global__ void ccable_obs_kernel(tgb_ccable_args a, double* __restrict__ obs, i
             if (q >= c.n) continue;
             r[0] = (double)c.s[q].body;
             r[1] = fr[FR_O] + P[q + 1].x; r[2] = fr[FR_O + 1] + P[q + 1].y; r[3] = fr[FR_O + 2] + P[q + 1].z;
-            r[4] = c.s[q].normal.x; r[5] = c.s[q].normal.y; r[6] = c.s[q].normal.z;
+            const D3 wn = E.worldNormal(c.s[q].body, c.s[q].normal);
+            r[4] = wn.x; r[5] = wn.y; r[6] = wn.z;
         }
     }
 }

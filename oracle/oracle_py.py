@@ -51,6 +51,7 @@ def load():
     lib.tgo_get_cpg_state.argtypes = [vp, vp]
     lib.tgo_add_contact_cables.argtypes = [vp, vp, i]
     lib.tgo_set_batch_contact_cables.argtypes = [vp, i]
+    lib.tgo_contact_cable_points.argtypes = [vp, i, vp, i, vp]
     lib.tgo_set_contact_cable_control_input.argtypes = [vp, vp, dbl]
     lib.tgo_num_contact_cables.argtypes = [vp]
     lib.tgo_get_contact_cable_obs.argtypes = [vp, vp]
@@ -87,6 +88,19 @@ class OracleWorld(object):
         out = np.zeros((self.n_cc, 5))
         self._lib.tgo_get_contact_cable_obs(self._h, _p(out))
         return out
+
+    def contact_cable_points(self, cable, chain):
+        """the geometric manifold of a cable whose anchors stand at chain [n, 3]: [k, 8] = body, position, normal into the body, distance"""
+        chain = np.ascontiguousarray(chain, dtype=np.float64)
+        out = np.zeros((64, 8))
+        k = self._lib.tgo_contact_cable_points(self._h, int(cable), _p(chain), chain.shape[0], _p(out))
+        return out[:k]
+
+    def world_step(self, dt):
+        self._lib.tgo_world_step(self._h, dt)
+
+    def models_step(self, dt):
+        self._lib.tgo_models_step(self._h, dt)
 
     def set_contact_cable_control_input(self, inputs, dt):
         inputs = np.ascontiguousarray(inputs, dtype=np.float64)

@@ -16,6 +16,7 @@ REFERENCE_SOURCES = [
     "src/core/tgSpringCable.cpp",
     "src/core/tgBulletSpringCable.cpp",
     "src/core/tgBulletSpringCableAnchor.cpp",
+    "src/core/tgBulletContactSpringCable.cpp",
     "src/core/tgSpringCableActuator.cpp",
     "src/core/tgBasicActuator.cpp",
     "src/core/tgKinematicActuator.cpp",

@@ -14,11 +14,31 @@
 #include "controllers/tgPIDController.h"
 #include "util/CPGEquations.h"
 #include "BulletDynamics/Dynamics/btRigidBody.h"
+#include "core/tgBulletContactSpringCable.h"
+#include "core/tgBulletUtil.h"
+#include "core/tgWorld.h"
+#include "ref_collision_shim.h"
 
 #include <stdexcept>
 #include <vector>
 
+/* the one Bullet world of the harness: tgBulletContactSpringCable asks tgBulletUtil for it (tgBulletContactSpringCable.cpp:76,206,682) */
+static btDynamicsWorld g_dynamicsWorld;
+btDynamicsWorld& tgBulletUtil::worldToDynamicsWorld(const tgWorld&) { return g_dynamicsWorld; }
+
+/* a contact cable of the reference with the collision-world objects its step reads: the ghost, one broadphase pair per rigid body,
+   each with an algorithm that holds one manifold (body0 = the ghost, body1 = the rigid body) */
+struct ref_contact_cable {
+    tgBulletContactSpringCable* cable;
+    tgBasicActuator* actuator;
+    btPairCachingGhostObject* ghost;
+    std::vector<btBroadphaseProxy*> proxies;
+    std::vector<btCollisionAlgorithm*> algorithms;
+    std::vector<btPersistentManifold*> manifolds;
+};
+
 struct ref_world {
+    std::vector<ref_contact_cable> contactCables;
     std::vector<btRigidBody*> bodies;
     std::vector<btVector3> invInertiaLocal;
     std::vector<tgSpringCableActuator*> actuators;
@@ -30,6 +50,12 @@ struct ref_world {
         for (size_t i = 0; i < tensionControllers.size(); ++i) delete tensionControllers[i];
         for (size_t i = 0; i < pids.size(); ++i) delete pids[i];
         for (size_t i = 0; i < actuators.size(); ++i) delete actuators[i]; /* deletes its cable and the anchors */
+        for (size_t i = 0; i < contactCables.size(); ++i) {
+            delete contactCables[i].actuator; /* deletes the cable, which deletes its ghost object and shapes */
+            for (size_t k = 0; k < contactCables[i].proxies.size(); ++k) {
+                delete contactCables[i].proxies[k]; delete contactCables[i].algorithms[k]; delete contactCables[i].manifolds[k];
+            }
+        }
         for (size_t i = 0; i < bodies.size(); ++i) delete bodies[i];
     }
 };
@@ -169,6 +195,95 @@ int ref_step_actuators(ref_world* w, double dt) {
         for (size_t i = 0; i < w->actuators.size(); ++i) w->actuators[i]->step(dt);
         return 0;
     } catch (const std::invalid_argument& e) { g_err = e.what(); return 1; }
+}
+
+/* ---- contact cables: src/core/tgBulletContactSpringCable.cpp compiled in place ------------------------------ */
+/* cfg = {k, c, pretension, thickness, resolution}; the ends as world points on bodies a and b */
+int ref_add_contact_cable(ref_world* w, int a, int b, const double* worldA, const double* worldB, const double* cfg) {
+    try {
+        static char worldStorage[4096]; /* a tgWorld is only ever handed to tgBulletUtil::worldToDynamicsWorld above */
+        tgWorld& world = *reinterpret_cast<tgWorld*>(worldStorage);
+        ref_contact_cable cc;
+        cc.ghost = new btPairCachingGhostObject();
+        cc.ghost->setCollisionShape(new btCompoundShape());
+        for (size_t i = 0; i < w->bodies.size(); ++i) {
+            btBroadphaseProxy* proxy = new btBroadphaseProxy();
+            proxy->m_clientObject = static_cast<btCollisionObject*>(w->bodies[i]);
+            btPersistentManifold* m = new btPersistentManifold();
+            m->m_body0 = cc.ghost; m->m_body1 = w->bodies[i];
+            btCollisionAlgorithm* alg = new btCollisionAlgorithm();
+            alg->m_manifolds.push_back(m);
+            btBroadphasePair pair;
+            pair.m_pProxy0 = cc.ghost->getBroadphaseHandle(); pair.m_pProxy1 = proxy; pair.m_algorithm = alg;
+            cc.ghost->getOverlappingPairCache()->getOverlappingPairArray().push_back(pair);
+            g_dynamicsWorld.getBroadphase()->getOverlappingPairCache()->getOverlappingPairArray().push_back(pair);
+            cc.proxies.push_back(proxy); cc.algorithms.push_back(alg); cc.manifolds.push_back(m);
+        }
+        std::vector<tgBulletSpringCableAnchor*> anchors;
+        anchors.push_back(new tgBulletSpringCableAnchor(w->bodies[a], btVector3(worldA[0], worldA[1], worldA[2])));
+        anchors.push_back(new tgBulletSpringCableAnchor(w->bodies[b], btVector3(worldB[0], worldB[1], worldB[2])));
+        cc.cable = new tgBulletContactSpringCable(cc.ghost, world, anchors, cfg[0], cfg[1], cfg[2], cfg[3], cfg[4]);
+        tgSpringCableActuator::Config bc(cfg[0], cfg[1], cfg[2], false, 600000000);
+        cc.actuator = new tgBasicActuator(cc.cable, tgTags("muscle"), bc); /* tgBasicContactCableInfo::createModel */
+        w->contactCables.push_back(cc);
+        return (int)w->contactCables.size() - 1;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+/* the cable's anchors in order: world positions [n][3]; returns n */
+int ref_cc_chain(ref_world* w, int c, double* out, int cap) {
+    const std::vector<const tgSpringCableAnchor*> anchors = w->contactCables[c].cable->getAnchors();
+    for (int i = 0; i < (int)anchors.size() && i < cap; ++i) {
+        const btVector3 p = anchors[i]->getWorldPosition();
+        out[3 * i] = p.x(); out[3 * i + 1] = p.y(); out[3 * i + 2] = p.z();
+    }
+    return (int)anchors.size();
+}
+/* this step's contact points of the cable, as the oracle's geometric manifold finds them: pts [n][8] = body, position on the body
+   (3), normal from the cable into the body (3), distance.  Bullet's convention for a manifold with the ghost as body 0:
+   m_positionWorldOnB on the rigid body, m_normalWorldOnB from the rigid body towards the ghost. */
+void ref_cc_set_points(ref_world* w, int c, int n, const double* pts) {
+    ref_contact_cable& cc = w->contactCables[c];
+    for (size_t i = 0; i < cc.manifolds.size(); ++i) cc.manifolds[i]->m_points.clear();
+    for (int i = 0; i < n; ++i) {
+        const double* p = pts + 8 * i;
+        btManifoldPoint pt;
+        pt.m_positionWorldOnB = btVector3(p[1], p[2], p[3]);
+        pt.m_normalWorldOnB = btVector3(-p[4], -p[5], -p[6]);
+        pt.m_positionWorldOnA = pt.m_positionWorldOnB + pt.m_normalWorldOnB * p[7];
+        pt.m_distance1 = p[7];
+        cc.manifolds[(int)p[0]]->m_points.push_back(pt);
+    }
+}
+/* tgBasicActuator::step(dt) of the contact cable's actuator = tgBulletContactSpringCable::step; 5 = std::runtime_error */
+int ref_cc_step(ref_world* w, int c, double dt) {
+    try {
+        w->contactCables[c].actuator->step(dt);
+        return 0;
+    } catch (const std::invalid_argument& e) { g_err = e.what(); return 1;
+    } catch (const std::exception& e) { g_err = e.what(); return 5; }
+}
+/* out = {rest length, actual length, tension, number of anchors} */
+void ref_cc_get(ref_world* w, int c, double* out) {
+    tgBulletContactSpringCable* cable = w->contactCables[c].cable;
+    out[0] = cable->getRestLength(); out[1] = cable->getActualLength(); out[2] = cable->getTension();
+    out[3] = (double)cable->getAnchors().size();
+}
+/* the sliding anchors: [k][7] = index of the attached body, world position, contact normal; returns their number */
+int ref_cc_anchors(ref_world* w, int c, double* out, int cap) {
+    const std::vector<const tgSpringCableAnchor*> anchors = w->contactCables[c].cable->getAnchors();
+    int k = 0;
+    for (size_t i = 1; i + 1 < anchors.size() && k < cap; ++i, ++k) {
+        const tgBulletSpringCableAnchor* a = static_cast<const tgBulletSpringCableAnchor*>(anchors[i]);
+        int body = -1;
+        for (size_t b = 0; b < w->bodies.size(); ++b) if (w->bodies[b] == a->attachedBody) body = (int)b;
+        const btVector3 p = a->getWorldPosition(), n = a->getContactNormal();
+        double* o = out + 7 * k;
+        o[0] = body; o[1] = p.x(); o[2] = p.y(); o[3] = p.z(); o[4] = n.x(); o[5] = n.y(); o[6] = n.z();
+    }
+    return k;
 }
 
 /* ---- CPG ------------------------------------------------------------------------------------------------- */

@@ -1,4 +1,4 @@
-/* Inert stub (oracle/ref shim). */
+/* Shim (oracle/ref). */
 #ifndef REF_SHIM_BT_COLLISION_WORLD_H
 #define REF_SHIM_BT_COLLISION_WORLD_H
 #include "BulletCollision/NarrowPhaseCollision/btPersistentManifold.h"

@@ -1,8 +1,10 @@
-/* Inert stubs (oracle/ref shim) for the sliding-anchor methods that share a translation unit with the pin-anchor code
-   (tgBulletSpringCableAnchor.cpp:89-334). Pin anchors pass manifold = NULL, so none of this is ever executed. */
+/* Shim (oracle/ref) of the part of btPersistentManifold the sliding-anchor / contact-cable sources read
+   (tgBulletSpringCableAnchor.cpp:89-334, tgBulletContactSpringCable.cpp:196-365): the two bodies and a list of contact points.  The
+   harness fills the points (ref_harness.cpp ref_cc_set_points); pin anchors pass manifold = NULL and never get here. */
 #ifndef REF_SHIM_BT_PERSISTENT_MANIFOLD_H
 #define REF_SHIM_BT_PERSISTENT_MANIFOLD_H
 #include "LinearMath/btVector3.h"
+#include <vector>
 class btCollisionObject;
 class btManifoldPoint {
 public:
@@ -18,11 +20,11 @@ public:
     btPersistentManifold() : m_body0(0), m_body1(0) {}
     const btCollisionObject* getBody0() const { return m_body0; }
     const btCollisionObject* getBody1() const { return m_body1; }
-    int getNumContacts() const { return 0; }
-    const btManifoldPoint& getContactPoint(int) const { return m_point; }
-    btManifoldPoint& getContactPoint(int) { return m_point; }
+    int getNumContacts() const { return (int)m_points.size(); }
+    const btManifoldPoint& getContactPoint(int i) const { return m_points[i]; }
+    btManifoldPoint& getContactPoint(int i) { return m_points[i]; }
     const btCollisionObject* m_body0;
     const btCollisionObject* m_body1;
-    btManifoldPoint m_point;
+    std::vector<btManifoldPoint> m_points;
 };
 #endif

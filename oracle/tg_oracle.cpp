@@ -158,7 +158,8 @@ struct Cable {
 struct SlideAnchor {
     int body;
     V3 local;  /* attachedRelativeOriginalPosition */
-    V3 normal; /* contactNormal: world vector fixed at creation (USE_BASIS off, SKIP_CONTACT_UPDATE on), from the cable into the body */
+    V3 normal; /* contactNormal in the BODY frame (tgBulletSpringCableAnchor.cpp:38 USE_BASIS: basis^-1 * cn at creation, :56-57), never
+                  updated afterwards (:40 SKIP_CONTACT_UPDATE); the world normal, from the cable into the body, turns with the body */
 };
 struct ContactCable {
     int a, b;
@@ -416,6 +417,12 @@ struct tgo_world {
     /* ---- contact cables ---------------------------------------------------------------------- */
     enum { kMaxSliding = TGB_CCABLE_MAX_SLIDING, kMaxCablePoints = 64 };
     V3 toLocal(const Body& b, const V3& world) const { return vecMat(world - b.pos, b.basis); } /* basis^T (world - pos) */
+    /* tgBulletSpringCableAnchor::getContactNormal (:202-214): the stored normal turned into the world frame and normalised */
+    V3 ccWorldNormal(const SlideAnchor& q) const {
+        const V3 n = bodies[q.body].basis * q.normal;
+        const double l = n.length();
+        return l > 0.0 ? n / l : V3(0, 0, 0);
+    }
     /* world positions of the anchor chain, tgBulletContactSpringCable::m_anchors */
     void ccChain(const ContactCable& cc, std::vector<V3>& P) const {
         P.clear();
@@ -466,7 +473,7 @@ struct tgo_world {
     /* tgBulletSpringCableAnchor::getManifoldDistance (:279-334) of a sliding anchor: distance to the nearest point of its body's
        manifold, and that point's normal when it lies within 0.1 (else the anchor's own) */
     double ccManifoldDistance(const std::vector<CablePoint>& pts, const SlideAnchor& q, int body, V3& normalOut) const {
-        normalOut = q.normal;
+        normalOut = ccWorldNormal(q);
         if (q.body != body) return INFINITY;
         V3 n, pos;
         const double len = ccNearest(pts, body, anchorWorld(bodies[q.body], q.local), n, pos);
@@ -479,7 +486,7 @@ struct tgo_world {
         if (q.body != body) return false;
         V3 newNormal;
         ccManifoldDistance(pts, q, body, newNormal);
-        return !((newNormal + q.normal).length() < 0.5);
+        return !((newNormal + ccWorldNormal(q)).length() < 0.5); /* the reference compares in the body frame: the same length */
     }
     /* the segment of the chain nearest to pos: the restatement's findNearestPastAnchor (:799-937) */
     static int ccNearestSegment(const std::vector<V3>& P, const V3& pos) {
@@ -499,11 +506,12 @@ struct tgo_world {
     bool ccSetWorldPosition(const std::vector<CablePoint>& pts, SlideAnchor& q, const V3& newPos) {
         const Body& b = bodies[q.body];
         const V3 current = anchorWorld(b, q.local);
-        V3 newNormal = q.normal, contactPos = current;
+        const V3 own = ccWorldNormal(q);
+        V3 newNormal = own, contactPos = current;
         const double length = ccNearest(pts, q.body, newPos, newNormal, contactPos);
         if (length < 0.1) {
             q.local = toLocal(b, newPos);
-            return !((newNormal + q.normal).length() < 0.5);
+            return !((newNormal + own).length() < 0.5);
         }
         return (current - contactPos).length() <= 0.1;
     }
@@ -516,7 +524,7 @@ struct tgo_world {
             ccChain(cc, P);
             const V3 back = P[i], current = P[i + 1], forward = P[i + 2];
             const V3 lineA = forward - current, lineB = back - current;
-            const V3 n = cc.slides[i].normal;
+            const V3 n = ccWorldNormal(cc.slides[i]);
             V3 tangentMove(0, 0, 0);
             const V3 along = lineB - lineA;
             const double al = along.length();
@@ -536,12 +544,10 @@ struct tgo_world {
         }
         return numPruned;
     }
-    /* tgBulletContactSpringCable::step (:97-125) */
-    void contactCableStep(ContactCable& cc, double dt) {
-        std::vector<V3> P;
-        ccChain(cc, P);
-        /* updateManifolds: this step's contact points of the segments with every body */
-        std::vector<CablePoint> pts;
+    /* the "manifolds" of a cable whose anchors stand at P: closest-point pairs of its segments with every shape of every body nearer
+       than the contact breaking threshold (see include/ntrtsim_b200.h "Contact cables") */
+    void ccDetect(const std::vector<V3>& P, double thickness, std::vector<CablePoint>& pts) const {
+        pts.clear();
         for (size_t i = 0; i + 1 < P.size(); ++i) {
             const V3 e = P[i + 1] - P[i];
             const double len = e.length();
@@ -549,7 +555,7 @@ struct tgo_world {
             gs.p = (P[i] + P[i + 1]) * 0.5;
             gs.d = len > 1e-12 ? e / len : V3(0, 1, 0);
             gs.h = len > 1e-12 ? 0.5 * len : 0.0;
-            gs.r = cc.thickness;
+            gs.r = thickness;
             for (size_t bi = 0; bi < bodies.size(); ++bi) {
                 const Body& b = bodies[bi];
                 for (int si = b.shapeBegin; si < b.shapeBegin + b.shapeCount; ++si) {
@@ -571,6 +577,14 @@ struct tgo_world {
                 }
             }
         }
+    }
+    /* tgBulletContactSpringCable::step (:97-125) */
+    void contactCableStep(ContactCable& cc, double dt) {
+        std::vector<V3> P;
+        ccChain(cc, P);
+        /* updateManifolds: this step's contact points of the segments with every body */
+        std::vector<CablePoint> pts;
+        ccDetect(P, cc.thickness, pts);
         /* updateManifolds + updateAnchorList: proposals of the penetrating points, one after the other */
         for (size_t pi = 0; pi < pts.size(); ++pi) {
             const CablePoint m = pts[pi];
@@ -592,11 +606,11 @@ struct tgo_world {
                 if (fwdS && ccUpdateManifold(pts, *fwdS, m.body)) del = true;
             if (del) continue;
             if (lineA.dot(m.normal) < 0.0 || lineB.dot(m.normal) < 0.0) continue;
-            const V3 backNormal = backS ? backS->normal : V3(0, 0, 0), fwdNormal = fwdS ? fwdS->normal : V3(0, 0, 0);
+            const V3 backNormal = backS ? ccWorldNormal(*backS) : V3(0, 0, 0), fwdNormal = fwdS ? ccWorldNormal(*fwdS) : V3(0, 0, 0);
             if ((backNormal.dot(m.normal) < 0.0 && m.body == backBody) || (fwdNormal.dot(m.normal) < 0.0 && m.body == fwdBody)) continue;
             if ((int)cc.slides.size() >= kMaxSliding) continue;
             SlideAnchor q;
-            q.body = m.body; q.local = toLocal(bodies[m.body], m.pos); q.normal = m.normal;
+            q.body = m.body; q.local = toLocal(bodies[m.body], m.pos); q.normal = vecMat(m.normal, bodies[m.body].basis); /* basis^-1 * cn */
             cc.slides.insert(cc.slides.begin() + j, q);
             if (contactCableLength(cc) > cc.prev + 2.0 * cc.resolution) cc.slides.erase(cc.slides.begin() + j);
         }
@@ -616,7 +630,7 @@ struct tgo_world {
                 while (i < cc.slides.size()) {
                     ccChain(cc, P);
                     const V3 lineA = P[i + 2] - P[i + 1], lineB = P[i] - P[i + 1];
-                    const V3 n = cc.slides[i].normal;
+                    const V3 n = ccWorldNormal(cc.slides[i]);
                     double nv1, nv2;
                     const double half = cc.resolution / 2.0;
                     if (lineA.length2() < half * half || lineB.length2() < half * half) nv1 = nv2 = -1.0;
@@ -1431,6 +1445,21 @@ int tgo_set_contact_cable_control_input(tgo_world* w, const double* input, doubl
     }
     return 0;
 }
+/* the contact points the oracle's geometric manifold gives cable `cable` if its anchors stood at chain[n][3] (the reference-source
+   harness feeds them to the reference's own anchor logic, oracle/ref): out [<= 64][8] = body, position on the body, normal from the
+   cable into the body, distance; returns their number */
+int tgo_contact_cable_points(const tgo_world* w, int cable, const double* chain, int n, double* out) {
+    std::vector<V3> P;
+    for (int i = 0; i < n; ++i) P.push_back(V3(chain[3 * i], chain[3 * i + 1], chain[3 * i + 2]));
+    std::vector<CablePoint> pts;
+    w->ccDetect(P, w->contactCables[cable].thickness, pts);
+    for (size_t i = 0; i < pts.size(); ++i) {
+        double* o = out + 8 * i;
+        o[0] = pts[i].body; o[1] = pts[i].pos.x; o[2] = pts[i].pos.y; o[3] = pts[i].pos.z;
+        o[4] = pts[i].normal.x; o[5] = pts[i].normal.y; o[6] = pts[i].normal.z; o[7] = pts[i].dist;
+    }
+    return (int)pts.size();
+}
 int tgo_num_contact_cables(const tgo_world* w) { return (int)w->contactCables.size(); }
 void tgo_get_contact_cable_obs(const tgo_world* w, double* o) {
     for (size_t i = 0; i < w->contactCables.size(); ++i) {
@@ -1451,7 +1480,8 @@ void tgo_get_contact_cable_anchors(const tgo_world* w, int cable, double* out) {
         if (k >= (int)cc.slides.size()) continue;
         const SlideAnchor& q = cc.slides[k];
         const V3 p = w->anchorWorld(w->bodies[q.body], q.local);
-        o[0] = q.body; o[1] = p.x; o[2] = p.y; o[3] = p.z; o[4] = q.normal.x; o[5] = q.normal.y; o[6] = q.normal.z;
+        const V3 wn = w->ccWorldNormal(q);
+        o[0] = q.body; o[1] = p.x; o[2] = p.y; o[3] = p.z; o[4] = wn.x; o[5] = wn.y; o[6] = wn.z;
     }
 }
 

@@ -62,6 +62,7 @@ int        tgo_add_model_flat(tgo_world* w, const tgb_body_desc* bodies, int n_b
    indices relative to the model added last.  obs [n][5]; anchors [TGB_CCABLE_MAX_SLIDING][7] */
 int  tgo_add_contact_cables(tgo_world* w, const tgb_contact_cable_desc* cables, int n);
 int  tgo_num_contact_cables(const tgo_world* w);
+int  tgo_contact_cable_points(const tgo_world* w, int cable, const double* chain, int n, double* out); /* out [<= 64][8] */
 int  tgo_set_contact_cable_control_input(tgo_world* w, const double* input, double dt); /* [n_contact_cables] */
 void tgo_set_batch_contact_cables(const tgb_contact_cable_desc* cables, int n); /* for the worlds of tgo_rollout_batch; 0 clears */
 void tgo_get_contact_cable_obs(const tgo_world* w, double* obs5);
