@@ -376,7 +376,8 @@ tgb_status tgb_get_min_clearance(tgb_world* w, int32_t env_begin, int32_t env_co
 #define TGB_CCABLE_MAX_SLIDING 6
 /* per-cable observation: rest length, actual length (over all anchors), tension, velocity, number of sliding anchors */
 #define TGB_CCABLE_OBS_DOUBLES 5
-/* per-anchor record of tgb_get_contact_cable_anchors: body index, world position (3), contact normal (3) */
+/* per-anchor record of tgb_get_contact_cable_anchors: body index, world position (3), contact normal in the world frame (3; the
+   anchor keeps it in its body's frame, tgBulletSpringCableAnchor.cpp:38,56-57,202-214) */
 #define TGB_CCABLE_ANCHOR_DOUBLES 7
 typedef struct {
     int32_t body_a, body_b;
