@@ -51,6 +51,12 @@ struct ref_world {
         for (size_t i = 0; i < pids.size(); ++i) delete pids[i];
         for (size_t i = 0; i < actuators.size(); ++i) delete actuators[i]; /* deletes its cable and the anchors */
         for (size_t i = 0; i < contactCables.size(); ++i) {
+            /* the world's pair cache outlives this harness world: take this cable's pairs out before its objects go */
+            btBroadphasePairArray& all = g_dynamicsWorld.getBroadphase()->getOverlappingPairCache()->getOverlappingPairArray();
+            btBroadphasePairArray kept;
+            for (int k = 0; k < all.size(); ++k)
+                if (all[k].m_pProxy0 != contactCables[i].ghost->getBroadphaseHandle()) kept.push_back(all[k]);
+            all = kept;
             delete contactCables[i].actuator; /* deletes the cable, which deletes its ghost object and shapes */
             for (size_t k = 0; k < contactCables[i].proxies.size(); ++k) {
                 delete contactCables[i].proxies[k]; delete contactCables[i].algorithms[k]; delete contactCables[i].manifolds[k];
