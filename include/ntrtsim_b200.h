@@ -369,7 +369,7 @@ tgb_status tgb_get_min_clearance(tgb_world* w, int32_t env_begin, int32_t env_co
    tgb_set_pair_contact_cap): a cylinder counts as the capsule inscribed in it, a sphere as itself, boxes take no part; the "manifold" of
    (cable, body) is the set of closest-point pairs of this step's segments with the body's shapes that are nearer than Bullet's contact
    breaking threshold (0.02), evaluated at the poses of the cable's step (Bullet's are one world step old).  At most
-   TGB_CCABLE_MAX_SLIDING sliding anchors per cable: further proposals are dropped.  The actuator is tgBasicActuator: its step is the
+   TGB_CCABLE_MAX_SLIDING sliding anchors per cable (further proposals are dropped) and 64 manifold points per cable and step.  The actuator is tgBasicActuator: its step is the
    cable's step (src/core/tgBasicActuator.cpp:227-241); control input arrives through tgb_set_contact_cable_control_input (the
    device-side controllers of tgb_set_controller drive the two-anchor cables only).  Worlds with contact cables run one launch of
    the step kernel plus one of the contact-cable kernel per step. */

@@ -624,7 +624,11 @@ tgb_status launchWithContactCables(tgb_world* w, double dt, int nSteps, int phas
             const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ei != cudaSuccess) { cudaGetLastError(); break; }
-            if (w->ccGraphs.size() >= 16) { cudaGraphExecDestroy(w->ccGraphs.front().exec); w->ccGraphs.erase(w->ccGraphs.begin()); }
+            if (w->ccGraphs.size() >= 16) { /* the oldest graph may still be replaying on another stream of this world */
+                cudaDeviceSynchronize();
+                cudaGraphExecDestroy(w->ccGraphs.front().exec);
+                w->ccGraphs.erase(w->ccGraphs.begin());
+            }
             tgb_world::CcGraph g;
             g.args = a; g.steps = steps; g.envBegin = envBegin; g.envCount = envCount; g.exec = exec;
             w->ccGraphs.push_back(g);
