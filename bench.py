@@ -72,15 +72,18 @@ def build_workload(name, n_env, seed):
         ctrl = capi.TGB_CTRL_ESCAPE_SINE
         p_ctrl = 32
     elif name == "contact_cable":
-        # ContactCableDemo (test_integration/MuscleNP), an ensemble of launch impulses; the cable meets the free rod
-        # within the first thousand steps and bends around it over sliding anchors
+        # ContactCableDemo as test_integration/MuscleNP runs it (launch impulse (0.4, 0, 0.4) on the two end bodies),
+        # an ensemble of launches (+- 15 % and a small turn); the cable meets the free rod between steps 3000 and 5000 and bends around it
+        # over sliding anchors.  TGB_CC_BENCH_SPEED=4 launches four times as fast: the cable then goes slack and winds itself around its
+        # own end rod with up to 12 anchors (a harder case for the one-thread-per-environment kernel: DESIGN.md section 3.7)
         model = nt.build_example("ContactCableDemo")
         rng = np.random.default_rng(seed)
         rods = np.tile(model.initial_rod_state(), (n_env, 1, 1))
-        imp = 4.0 * (np.array([0.4, 0.0, 0.4]) * (1.0 + 0.15 * rng.uniform(-1, 1, size=(n_env, 1))) + 0.06 * rng.uniform(-1, 1, size=(n_env, 3)))
+        speed = float(os.environ.get("TGB_CC_BENCH_SPEED", "1"))
+        imp = speed * (np.array([0.4, 0.0, 0.4]) * (1.0 + 0.15 * rng.uniform(-1, 1, size=(n_env, 1))) + 0.06 * rng.uniform(-1, 1, size=(n_env, 3)))
         for b in (0, 1):
             rods[:, b, 7:10] = imp / model.bodies[b].mass
-        params, ctrl, p_ctrl = None, capi.TGB_CTRL_NONE, 2 * (4 + 7 * 6)   # the cable's state incl. its sliding anchors, read and written
+        params, ctrl, p_ctrl = None, capi.TGB_CTRL_NONE, 2 * (5 + 7 * 12)   # the cable's state incl. its sliding anchors, read and written
     elif name == "prism":
         model = nt.build_example("3_prism_noground")
         rods = random_poses(model, n_env, seed=seed)

@@ -373,7 +373,7 @@ tgb_status tgb_get_min_clearance(tgb_world* w, int32_t env_begin, int32_t env_co
    cable's step (src/core/tgBasicActuator.cpp:227-241); control input arrives through tgb_set_contact_cable_control_input (the
    device-side controllers of tgb_set_controller drive the two-anchor cables only).  Worlds with contact cables run one launch of
    the step kernel plus one of the contact-cable kernel per step. */
-#define TGB_CCABLE_MAX_SLIDING 6
+#define TGB_CCABLE_MAX_SLIDING 12
 /* per-cable observation: rest length, actual length (over all anchors), tension, velocity, number of sliding anchors */
 #define TGB_CCABLE_OBS_DOUBLES 5
 /* per-anchor record of tgb_get_contact_cable_anchors: body index, world position (3), contact normal in the world frame (3; the

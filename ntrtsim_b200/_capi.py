@@ -54,7 +54,7 @@ class ContactCableDesc(C.Structure):
                 ("min_actual_length", C.c_double), ("min_rest_length", C.c_double)]
 
 
-CCABLE_MAX_SLIDING = 6
+CCABLE_MAX_SLIDING = 12
 CCABLE_OBS_DOUBLES = 5
 CCABLE_ANCHOR_DOUBLES = 7
 

@@ -151,7 +151,7 @@ class BatchedWorld(object):
         capi.check(self._lib.tgb_reset_contact_cables(self._h, env_begin, n, _ptr(rest_prev) if rest_prev is not None else None))
 
     def get_contact_cable_anchors(self, cable, env_begin=0, env_count=None):
-        """[n, 6, 7]: body (-1 = unused slot), world position, contact normal of the cable's sliding anchors in order"""
+        """[n, 12, 7]: body (-1 = unused slot), world position, contact normal of the cable's sliding anchors in order"""
         n = self.n_env - env_begin if env_count is None else env_count
         out = np.zeros((n, capi.CCABLE_MAX_SLIDING, capi.CCABLE_ANCHOR_DOUBLES))
         capi.check(self._lib.tgb_get_contact_cable_anchors(self._h, int(cable), env_begin, n, _ptr(out)))

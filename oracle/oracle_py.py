@@ -107,7 +107,7 @@ class OracleWorld(object):
         return self._lib.tgo_set_contact_cable_control_input(self._h, _p(inputs), dt)
 
     def get_contact_cable_anchors(self, cable):
-        out = np.zeros((6, 7))
+        out = np.zeros((12, 7))
         self._lib.tgo_get_contact_cable_anchors(self._h, int(cable), _p(out))
         return out
 

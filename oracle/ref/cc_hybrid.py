@@ -53,6 +53,7 @@ class HybridWorld(object):
         lib.ref_cc_step.argtypes = [vp, i, d]
         lib.ref_cc_get.argtypes = [vp, i, vp]
         lib.ref_cc_anchors.argtypes = [vp, i, vp, i]
+        lib.ref_cc_set_control_input_dt.argtypes = [vp, i, d, d]
         self.model = model
         self.ora = oracle_py.OracleWorld(model, capi.WorldCfg)
         self.ora.set_rod_state(state)
@@ -64,7 +65,7 @@ class HybridWorld(object):
             pa = state[c.body_a, 0:3] + _quat_rotate(state[c.body_a, 3:7], np.array(list(c.local_a)))
             pb = state[c.body_b, 0:3] + _quat_rotate(state[c.body_b, 3:7], np.array(list(c.local_b)))
             pretension = (np.linalg.norm(pb - pa) - c.rest_length) * c.stiffness
-            cfg = np.array([c.stiffness, c.damping, pretension, c.thickness, c.resolution])
+            cfg = np.array([c.stiffness, c.damping, pretension, c.thickness, c.resolution, c.target_velocity])
             idx = lib.ref_add_contact_cable(self.w, c.body_a, c.body_b, _p(np.ascontiguousarray(pa)), _p(np.ascontiguousarray(pb)), _p(cfg))
             if idx < 0:
                 raise RuntimeError(lib.ref_last_error().decode())
@@ -75,10 +76,19 @@ class HybridWorld(object):
             self.lib.ref_destroy(self.w)
             self.w = None
 
-    def step(self, n=1):
+    def step(self, n=1, control=None):
+        """control: preferred length per contact cable, handed to the reference's tgBasicActuator::setControlInput(input, dt) before
+        every step (a model-level controller's onStep runs before the children step, tgModel.cpp / tgSubject)"""
         lib, R = self.lib, len(self.model.bodies)
         for _ in range(n):
             self.ora.world_step(DT)
+            if control is not None:
+                st = self.ora.get_rod_state()
+                for b in range(R):
+                    lib.ref_set_body(self.w, b, _p(np.ascontiguousarray(st[b])))
+                for k, idx in enumerate(self.cc):
+                    if lib.ref_cc_set_control_input_dt(self.w, idx, float(control[k]), DT) != 0:
+                        raise RuntimeError(lib.ref_last_error().decode())
             st = self.ora.get_rod_state()
             for b in range(R):
                 lib.ref_set_body(self.w, b, _p(np.ascontiguousarray(st[b])))
@@ -145,7 +155,7 @@ def make_cc_golden(path=None, n_env=4, steps=7000, chunk=500, seed=77):
     states = t.demo_states(m, n_env, seed=seed)
     rods = np.zeros((n_env, steps // chunk, len(m.bodies), 13))
     cab = np.zeros((n_env, steps // chunk, 4))
-    anch = np.full((n_env, steps // chunk, 6, 7), 0.0)
+    anch = np.full((n_env, steps // chunk, 12, 7), 0.0)
     anch[..., 0] = -1.0
     for e in range(n_env):
         hyb = HybridWorld(m, states[e])
@@ -153,7 +163,7 @@ def make_cc_golden(path=None, n_env=4, steps=7000, chunk=500, seed=77):
             hyb.step(chunk)
             rods[e, k] = hyb.rod_state()
             cab[e, k] = hyb.cable()
-            a = hyb.anchors()[:6]
+            a = hyb.anchors()[:12]
             anch[e, k, :a.shape[0]] = a
         hyb.close()
     path = path or os.path.join(ROOT, "tests", "golden", "contact_cable_demo.npz")

@@ -229,7 +229,7 @@ int ref_add_contact_cable(ref_world* w, int a, int b, const double* worldA, cons
         anchors.push_back(new tgBulletSpringCableAnchor(w->bodies[a], btVector3(worldA[0], worldA[1], worldA[2])));
         anchors.push_back(new tgBulletSpringCableAnchor(w->bodies[b], btVector3(worldB[0], worldB[1], worldB[2])));
         cc.cable = new tgBulletContactSpringCable(cc.ghost, world, anchors, cfg[0], cfg[1], cfg[2], cfg[3], cfg[4]);
-        tgSpringCableActuator::Config bc(cfg[0], cfg[1], cfg[2], false, 600000000);
+        tgSpringCableActuator::Config bc(cfg[0], cfg[1], cfg[2], false, 600000000, cfg[5] > 0.0 ? cfg[5] : 100.0);
         cc.actuator = new tgBasicActuator(cc.cable, tgTags("muscle"), bc); /* tgBasicContactCableInfo::createModel */
         w->contactCables.push_back(cc);
         return (int)w->contactCables.size() - 1;
@@ -271,10 +271,18 @@ int ref_cc_step(ref_world* w, int c, double dt) {
     } catch (const std::invalid_argument& e) { g_err = e.what(); return 1;
     } catch (const std::exception& e) { g_err = e.what(); return 5; }
 }
+/* tgBasicActuator::setControlInput(input, dt) on the contact cable's actuator (moveMotors on the length over all anchors);
+   1 = std::invalid_argument */
+int ref_cc_set_control_input_dt(ref_world* w, int c, double input, double dt) {
+    try {
+        w->contactCables[c].actuator->setControlInput(input, dt);
+        return 0;
+    } catch (const std::invalid_argument& e) { g_err = e.what(); return 1; }
+}
 /* out = {rest length, actual length, tension, number of anchors} */
 void ref_cc_get(ref_world* w, int c, double* out) {
     tgBulletContactSpringCable* cable = w->contactCables[c].cable;
-    out[0] = cable->getRestLength(); out[1] = cable->getActualLength(); out[2] = cable->getTension();
+    out[0] = w->contactCables[c].actuator->getRestLength(); out[1] = cable->getActualLength(); out[2] = w->contactCables[c].actuator->getTension();
     out[3] = (double)cable->getAnchors().size();
 }
 /* the sliding anchors: [k][7] = index of the attached body, world position, contact normal; returns their number */

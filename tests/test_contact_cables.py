@@ -392,6 +392,28 @@ def test_reference_cable_code_live_against_the_oracle():
         pytest.skip("oracle/_ref/libntrt_ref.so predates the contact-cable harness")
     for e, worst, same, checks, nmax in cc_hybrid.compare(n_env=3, steps=6000, chunk=500, seed=123, verbose=False):
         assert worst < 1e-6 and same == checks, (e, worst, same, checks)
+    # with a controller: tgBasicActuator::setControlInput(input, dt) before every step reels the cable in while it bends around the rod
+    import bench
+    model, rods, _, _, _, _ = bench.build_workload("contact_cable", 2, bench.SEED)
+    model.contact_cables[0].target_velocity = 2.0
+    for e in range(2):
+        hyb = cc_hybrid.HybridWorld(model, rods[e])
+        ora = oracle_py.OracleWorld(model, capi.WorldCfg)
+        ora.set_rod_state(rods[e])
+        most = 0
+        for k in range(1800):
+            target = np.array([8.0 - 0.0008 * k])
+            hyb.step(1, control=target)
+            ora.world_step(DT)
+            assert ora.set_contact_cable_control_input(target, DT) == 0
+            ora.models_step(DT)
+            if k % 100 == 99:
+                assert np.abs(hyb.rod_state() - ora.get_rod_state()).max() < 1e-7
+                o = ora.get_contact_cable_obs()[0]
+                assert abs(hyb.cable()[0] - o[0]) < 1e-12 and hyb.anchors().shape[0] == int(o[4])
+                most = max(most, int(o[4]))
+        assert most >= 2
+        hyb.close()
 
 
 # ------------------------------------------------------------------------------------------------ GPU

@@ -3,6 +3,7 @@ sys.path.insert(0,'/root/repo/oracle/ref'); sys.path.insert(0,'/root/repo')
 import cc_hybrid as H
 import numpy as np, bench, oracle_py
 from ntrtsim_b200 import _capi as capi
+import os; os.environ["TGB_CC_BENCH_SPEED"] = "4"
 model, rods, cab, ctrl, params, _ = bench.build_workload("contact_cable", 12, bench.SEED)
 for e in range(12):
     hyb=H.HybridWorld(model, rods[e]); ora=oracle_py.OracleWorld(model,capi.WorldCfg); ora.set_rod_state(rods[e])
